@@ -1,0 +1,208 @@
+/*
+ * ufemism_b200.h -- C ABI of libufemism_b200.so: the B200-native ice-dynamics hot path of UFEMISM.
+ *
+ * The reference (IMAU-paleo/UFEMISM v1.1.1, Fortran 90 + MPI shared memory) has no plugin or FFI
+ * interface for this path; it sits behind four module procedures called from run_model
+ * (src/UFEMISM_main_model.f90:90,115,124,132).  This header IS the drop-in boundary: every entry
+ * point names the reference routine whose body it replaces.  The ISO_C_BINDING interfaces that bind
+ * it are in ufemism_b200/fortran/ufemism_b200_shim.f90; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; all reals are IEEE fp64 (dp = KIND(1.0D0), src/configuration_module.f90:24),
+ *    all integers 32-bit, LOGICAL passed as int.
+ *  - host arrays are in the reference's own layout: column-major, 1-based indices stored in the
+ *    arrays, leading dimension = number of rows given in the descriptor.  The library copies; the
+ *    host keeps ownership of every pointer it passes.
+ *  - return code 0 = ok; > 0 = warning the reference only prints (WRITE(0,*)) and carries on;
+ *    < 0 = fatal (the reference calls MPI_ABORT); <= -100 = CUDA error (-100 - cudaError_t).
+ *    ufm_last_error() returns the message.  No exceptions cross the boundary.
+ *  - one handle = one model region on one GPU, one CUDA stream, single host thread, non-reentrant.
+ *    In the SPMD host only par%master (or one rank per GPU) enters the library, followed by CALL sync.
+ *  - there is no CPU fallback: without a usable CUDA device ufm_create fails.
+ */
+#ifndef UFEMISM_B200_H
+#define UFEMISM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UFM_ABI_VERSION 1
+#define UFM_MAX_NZ 32
+
+typedef struct ufm_handle ufm_handle;
+
+/* choice_benchmark_experiment (src/configuration_module.f90:69-70); 0 = do_benchmark_experiment .FALSE. */
+enum ufm_benchmark {
+  UFM_BM_NONE = 0, UFM_BM_EISMINT_1 = 1, UFM_BM_EISMINT_2, UFM_BM_EISMINT_3, UFM_BM_EISMINT_4, UFM_BM_EISMINT_5,
+  UFM_BM_EISMINT_6, UFM_BM_HALFAR = 7, UFM_BM_BUELER = 8, UFM_BM_MISMIP_MOD = 9, UFM_BM_MESH_GENERATION_TEST = 10,
+  UFM_BM_SSA_ICESTREAM = 11
+};
+
+/* The C%... scalars this path reads (src/configuration_module.f90:37,124-126,169-184).  Physical
+ * constants of src/parameters_module.f90:9-21 are compile-time constants in the kernels, as they
+ * are PARAMETERs in the reference. */
+typedef struct ufm_params {
+  int    nZ;                      /* C%nZ, <= UFM_MAX_NZ */
+  double zeta[UFM_MAX_NZ];        /* C%zeta(1:nZ) */
+  double m_enh_sia, m_enh_ssa;    /* C%m_enh_sia, C%m_enh_ssa */
+  int    use_analytical_GL_flux;  /* C%use_analytical_GL_flux */
+  double SSA_RN_tol;              /* 1e-5 */
+  int    SSA_max_outer_loops;     /* 50 */
+  double SSA_max_residual_UV;     /* 2.5 */
+  double SSA_SOR_omega;           /* 1.2 */
+  int    SSA_max_inner_loops;     /* 10000 */
+  double dt_max;                  /* 10 */
+  int    benchmark;               /* enum ufm_benchmark */
+  int    exact_xy;                /* 1 (default): evaluate the 3*V_xy / 3*U_xy cross terms of the SOR
+                                     sweep coefficient by coefficient exactly as
+                                     get_mesh_curvatures_vertex_AaAc does (bit-identical results);
+                                     0: use the pre-summed row sum (saves 8(n+1) B per vertex and sweep,
+                                     differs from the reference by O(1 ulp) per update). */
+} ufm_params;
+
+/* type_mesh fields used by the path (src/data_types_module.f90:216-345).  ld* = allocated rows. */
+typedef struct ufm_mesh_desc {
+  int nV, nAc, nC_mem;            /* mesh%nV, mesh%nAc, mesh%nC_mem (= C%nconmax, 16) */
+  int ldV, ldAc, ldAaAc;          /* leading dimensions of the (nV,..), (nAc,..), (nV+nAc,..) arrays */
+  const double *V;                /* (ldV,2) */
+  const double *A;                /* (nV) Voronoi cell areas */
+  const int    *nC, *C;           /* (nV), (ldV,nC_mem) */
+  const double *Cw;               /* (ldV,nC_mem) */
+  const int    *edge_index;       /* (nV) 0..8 */
+  const double *Nx, *Ny;          /* (ldV,nC_mem+1) */
+  const int    *Aci;              /* (ldAc,4) [vi,vj,vl,vr] */
+  const int    *iAci;             /* (ldV,nC_mem) */
+  const int    *edge_index_Ac;    /* (nAc) */
+  const double *Nx_Ac, *Ny_Ac, *No_Ac; /* (ldAc,4) */
+  const double *Np_Ac;            /* (nAc) */
+  const int    *nCAaAc, *CAaAc;   /* (nV+nAc), (ldAaAc,nC_mem) */
+  const double *Nx_AaAc, *Ny_AaAc, *Nxx_AaAc, *Nxy_AaAc, *Nyy_AaAc; /* (ldAaAc,nC_mem+1) */
+  const int    *colour_vi;        /* (ldAaAc,5) */
+  const int    *colour_nV;        /* (5) */
+} ufm_mesh_desc;
+
+/* Fields of type_ice_model (src/data_types_module.f90:15-214) that can cross the boundary.
+ * AA = on vertices (nV), AC = staggered (nAc), AAAC = combined (nV+nAc); I = INTEGER array. */
+enum ufm_field {
+  /* inputs written by CPU components (ELRA, SMB, BMB, remapping) */
+  UFM_F_HI = 0, UFM_F_HB, UFM_F_SL, UFM_F_DHB_DT, UFM_F_SMB_YEAR, UFM_F_BMB, UFM_F_MASK_NOICE /*I*/,
+  /* Aa outputs */
+  UFM_F_HS, UFM_F_DHI_DT, UFM_F_DHS_DT, UFM_F_HI_PREV, UFM_F_DHI_DX, UFM_F_DHI_DY, UFM_F_DHS_DX, UFM_F_DHS_DY,
+  UFM_F_DHS_DX_SHELF, UFM_F_DHS_DY_SHELF, UFM_F_A_FLOW_MEAN, UFM_F_U_SIA, UFM_F_V_SIA, UFM_F_D_SIA, UFM_F_U_SSA, UFM_F_V_SSA,
+  UFM_F_MASK_LAND /*I*/, UFM_F_MASK_OCEAN, UFM_F_MASK_LAKE, UFM_F_MASK_ICE, UFM_F_MASK_SHEET, UFM_F_MASK_SHELF,
+  UFM_F_MASK_COAST, UFM_F_MASK_MARGIN, UFM_F_MASK_GL, UFM_F_MASK_CF, UFM_F_MASK,
+  /* Ac outputs */
+  UFM_F_HI_AC, UFM_F_HB_AC, UFM_F_HS_AC, UFM_F_SL_AC,
+  UFM_F_DHI_DX_AC, UFM_F_DHI_DY_AC, UFM_F_DHI_DP_AC, UFM_F_DHI_DO_AC,
+  UFM_F_DHB_DX_AC, UFM_F_DHB_DY_AC, UFM_F_DHB_DP_AC, UFM_F_DHB_DO_AC,
+  UFM_F_DHS_DX_AC, UFM_F_DHS_DY_AC, UFM_F_DHS_DP_AC, UFM_F_DHS_DO_AC,
+  UFM_F_DSL_DX_AC, UFM_F_DSL_DY_AC, UFM_F_DSL_DP_AC, UFM_F_DSL_DO_AC,
+  UFM_F_DHS_DX_SHELF_AC, UFM_F_DHS_DY_SHELF_AC, UFM_F_A_FLOW_MEAN_AC,
+  UFM_F_UX_SIA_AC, UFM_F_UY_SIA_AC, UFM_F_UP_SIA_AC, UFM_F_UO_SIA_AC, UFM_F_D_SIA_AC,
+  UFM_F_UX_SSA_AC, UFM_F_UY_SSA_AC, UFM_F_UP_SSA_AC, UFM_F_UO_SSA_AC, UFM_F_QABS_GL_AC, UFM_F_QP_GL_AC,
+  UFM_F_MASK_LAND_AC /*I*/, UFM_F_MASK_OCEAN_AC, UFM_F_MASK_LAKE_AC, UFM_F_MASK_ICE_AC, UFM_F_MASK_SHEET_AC, UFM_F_MASK_SHELF_AC,
+  UFM_F_MASK_COAST_AC, UFM_F_MASK_MARGIN_AC, UFM_F_MASK_GL_AC, UFM_F_MASK_CF_AC, UFM_F_MASK_AC,
+  /* AaAc (SSA work arrays, src/ice_dynamics_module.f90:1151-1176) */
+  UFM_F_U_SSA_AAAC, UFM_F_V_SSA_AAAC, UFM_F_ETA_AAAC, UFM_F_N_AAAC, UFM_F_S_AAAC, UFM_F_TAU_C_AAAC, UFM_F_PHI_FRIC_AAAC,
+  UFM_F_RHSX_AAAC, UFM_F_RHSY_AAAC, UFM_F_EU_I_AAAC, UFM_F_EV_I_AAAC,
+  UFM_F_DU_DX_AAAC, UFM_F_DU_DY_AAAC, UFM_F_DV_DX_AAAC, UFM_F_DV_DY_AAAC,
+  /* (nV,nZ) */
+  UFM_F_U_3D, UFM_F_V_3D,
+  UFM_F_COUNT
+};
+
+/* what solve_SSA would have printed had its WRITE statements not been commented out
+ * (src/ice_dynamics_module.f90:519,666,675); parity is defined "after the same SOR iteration count". */
+typedef struct ufm_ssa_stats {
+  int    n_outer;            /* viscosity iterations started */
+  int    n_inner_total;      /* SOR iterations summed over all linear solves */
+  int    n_inner_last;       /* SOR iterations of the last linear solve */
+  int    did_reset;          /* velocities were reset to zero once (:679-684) */
+  int    rc;                 /* 0 ok, 1 = "WARNING - SSA SOR solver doesnt converge!" (:686), -1 = unstable twice (:537) */
+  double last_max_residual;  /* max(|resU|,|resV|) of the last SOR iteration */
+  double last_RN;            /* sqrt(sum (N-Nprev)^2 / sum N^2) of the last viscosity iteration */
+} ufm_ssa_stats;
+
+/* work counters / timers since ufm_create or the last ufm_counters_reset */
+typedef struct ufm_counters {
+  long long kernel_launches;       /* kernels launched by this library */
+  long long sor_iterations;        /* SOR iterations executed */
+  double    sor_ms;                /* device time inside the SOR kernel (CUDA events on the handle's stream) */
+  long long sor_launches;
+  double    sor_bytes_per_iteration; /* algorithmic bytes of one full 5-colour iteration: sum_i (80 + 20 n_i) */
+  double    h2d_bytes, d2h_bytes;  /* bytes moved by ufm_state_upload / ufm_state_download */
+} ufm_counters;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* after initialize_main_constants (src/UFEMISM_program.f90:103): copies the scalars, selects the device */
+int ufm_create(int device, const ufm_params *params, ufm_handle **out);
+int ufm_destroy(ufm_handle *h);
+int ufm_set_params(ufm_handle *h, const ufm_params *params);
+/* use an existing CUDA stream (cudaStream_t / CUstream) instead of the handle's own; NULL restores it */
+int ufm_set_stream(ufm_handle *h, void *cuda_stream);
+int ufm_synchronize(ufm_handle *h);
+const char *ufm_last_error(void);
+int ufm_abi_version(void);
+
+/* ---- mesh: end of create_final_mesh_from_merged_submesh (src/mesh_creation_module.f90:1737),
+ *      read_mesh_from_restart_file (src/restart_module.f90:102), mesh swap (src/UFEMISM_main_model.f90:294).
+ *      Copies, renumbers (colour-major, degree-sliced, space-filling order) and compacts the mesh;
+ *      allocates and zero-fills all state (U_SSA is not remapped by the reference: :1212-1213).
+ *      A second call replaces the mesh (device re-upload after a CPU mesh update). ---- */
+int ufm_mesh_upload(ufm_handle *h, const ufm_mesh_desc *mesh);
+int ufm_mesh_free(ufm_handle *h);
+
+/* ---- state: explicit, field-granular, reference vertex order ---- */
+int ufm_state_upload(ufm_handle *h, int field, const void *host);
+int ufm_state_download(ufm_handle *h, int field, void *host);
+
+/* ---- the four drop-in entry points ---- */
+/* body of calculate_ice_thickness_change (src/ice_dynamics_module.f90:31-237) */
+int ufm_thickness_update(ufm_handle *h, double dt);
+/* body of update_general_ice_model_data (src/general_ice_model_data_module.f90:23-96) */
+int ufm_update_general(ufm_handle *h, double time);
+/* body of solve_SIA (src/ice_dynamics_module.f90:240-314) */
+int ufm_solve_SIA(ufm_handle *h);
+/* body of solve_SSA (src/ice_dynamics_module.f90:408-557) */
+int ufm_solve_SSA(ufm_handle *h, ufm_ssa_stats *stats);
+/* critical time steps of determine_timesteps_and_actions (src/UFEMISM_main_model.f90:738-778):
+ * out = {dt_D_2D_min, dt_V_2D_SSA_min, dt_V_3D_SIA_min}, each already multiplied by 0.9 */
+int ufm_cfl(ufm_handle *h, double out3[3]);
+
+/* ---- pieces of solve_SSA, for kernel-level parity tests and profiling ---- */
+/* basal_yield_stress [+ calculate_GL_flux] + gather into the AaAc arrays (:468-496) */
+int ufm_ssa_prepare(ufm_handle *h);
+/* SSA_effective_viscosity (:695-726) + the two sums of :512-513; sums2 = {sum_DN_sq, sum_N_sq} */
+int ufm_ssa_viscosity(ufm_handle *h, double sums2[2]);
+/* SSA_sliding_term (:727-779) + RHS and centre coefficients of solve_SSA_linearised (:581-596) */
+int ufm_ssa_sliding_and_setup(ufm_handle *h);
+/* SOR loop of solve_SSA_linearised (:598-692).  max_inner_override > 0 replaces C%SSA_max_inner_loops;
+ * force_iters != 0 disables the stop tests so exactly that many iterations run. */
+int ufm_ssa_sor(ufm_handle *h, int max_inner_override, int force_iters, ufm_ssa_stats *stats);
+/* scatter AaAc -> U_SSA, V_SSA, Ux/Uy_SSA_Ac and rotate_xy_to_po (:548-555) */
+int ufm_ssa_finish(ufm_handle *h);
+
+/* ---- region time loop for benchmark physics (row N1: run_model, src/UFEMISM_main_model.f90:78-214,
+ *      with determine_timesteps_and_actions :708-843 and the closed-form benchmark SMB,
+ *      src/SMB_module.f90:55-97,172-238): no host round trip of fields per step ---- */
+enum { UFM_T_SIA = 0, UFM_T_SSA, UFM_T_THERMO, UFM_T_CLIMATE, UFM_T_SMB, UFM_T_BMB, UFM_T_ELRA, UFM_T_OUTPUT, UFM_NT };
+typedef struct ufm_region {
+  double time, dt, dt_prev;
+  double t0[UFM_NT], t1[UFM_NT], dtc[UFM_NT];
+  int    do_[UFM_NT];
+  double H0, R0, lambda;
+  long   n_steps, n_sia, n_ssa, n_sor_total, n_outer_total;
+  double dt_crit_last[3];
+} ufm_region;
+int ufm_region_init(ufm_region *r, double start_time);
+int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps);
+
+/* ---- instrumentation ---- */
+int ufm_counters_get(ufm_handle *h, ufm_counters *out);
+int ufm_counters_reset(ufm_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

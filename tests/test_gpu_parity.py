@@ -1,0 +1,265 @@
+"""GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same inputs.
+
+Bar: BIT-EXACT wherever the arithmetic is add/mul/div/sqrt/compare (stencils, masks, thickness update,
+SOR sweep, Neumann pass, CFL); |rel| <= 1e-13 where one CUDA libm pow()/tan() sits on the path (<= 2 ulp vs
+glibc); north_star tolerances for composed results: velocities <= 1e-10 rel-L2 after the same SOR iteration
+count, ice thickness <= 1e-8 rel after N model years.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import get_mesh
+from tests.util import assert_bits_equal, make_gpu, make_oracle, rel_l2
+from ufemism_b200 import scenarios as S
+
+pytestmark = pytest.mark.gpu
+
+AA_EXACT = ["Hs", "dHs_dt", "dHi_dx", "dHi_dy", "dHs_dx", "dHs_dy", "dHs_dx_shelf", "dHs_dy_shelf"]
+AC_EXACT = ["Hi_Ac", "Hb_Ac", "Hs_Ac", "SL_Ac"] + [f"d{f}_d{c}_Ac" for f in ("Hi", "Hb", "Hs", "SL") for c in "xypo"] + ["dHs_dx_shelf_Ac", "dHs_dy_shelf_Ac"]
+MASKS = ["mask_land", "mask_ocean", "mask_lake", "mask_ice", "mask_sheet", "mask_shelf", "mask_coast", "mask_margin", "mask_gl", "mask_cf", "mask"]
+
+
+def scenario(mesh, name):
+    if name == "halfar":
+        return S.state_halfar(mesh)
+    if name == "icestream":
+        return S.state_ssa_icestream(mesh, scale=750e3 / 1800e3)
+    if name == "mismip":
+        st = S.state_mismip(mesh)
+        r = np.hypot(mesh.V[:, 0], mesh.V[:, 1])
+        st["Hi"] = np.where(r < 600e3, 800.0 - 600.0 * r / 600e3, 0.0) + np.where((r >= 600e3) & (r < 680e3), 150.0, 0.0)
+        st["Hi"][mesh.edge_index > 0] = 0.0
+        return st
+    raise ValueError(name)
+
+
+@pytest.mark.parametrize("name", ["halfar", "icestream", "mismip"])
+def test_update_general_bit_exact(mesh_10k, name):
+    st = scenario(mesh_10k, name)
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    o.update_general_ice_model_data(0.0)
+    g.update_general_ice_model_data(0.0)
+    for f in AA_EXACT + AC_EXACT:
+        assert_bits_equal(g.download(f), o[f], f)
+    for mname in MASKS:
+        assert_bits_equal(g.download(mname), o[mname], mname)
+        assert_bits_equal(g.download(mname + "_Ac"), o[mname + "_Ac"], mname + "_Ac")
+    assert_bits_equal(g.download("A_flow_mean"), o["A_flow_mean"], "A_flow_mean")
+
+
+@pytest.mark.parametrize("name", ["halfar", "mismip"])
+def test_solve_SIA(mesh_10k, name):
+    st = scenario(mesh_10k, name)
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    g.update_general_ice_model_data(0.0); g.solve_SIA()
+    for f in ["D_SIA_Ac", "Ux_SIA_Ac", "Uy_SIA_Ac", "Up_SIA_Ac", "Uo_SIA_Ac", "U_SIA", "V_SIA", "D_SIA"]:
+        a, b = g.download(f), o[f]
+        assert np.abs(b).max() > 0, f
+        # one CUDA pow(x, 3.0) per column: <= 2 ulp
+        np.testing.assert_allclose(a, b, rtol=1e-14, atol=1e-14 * np.abs(b).max(), err_msg=f)
+    assert (o["D_SIA_Ac"] <= 0).all()  # negative by construction
+
+
+@pytest.mark.parametrize("name,dt", [("halfar", 0.05), ("halfar", 0.0), ("mismip", 0.5), ("mismip", 40.0)])
+def test_thickness_update_bit_exact(mesh_10k, name, dt):
+    st = scenario(mesh_10k, name)
+    if name == "mismip":
+        st["SMB_year"] = np.where(np.hypot(mesh_10k.V[:, 0], mesh_10k.V[:, 1]) > 400e3, -3.0, 0.3)  # melt-all + limiter branches
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    g.update_general_ice_model_data(0.0)
+    # identical velocities on both sides so the flux arithmetic itself is compared bit for bit
+    g.upload("Up_SIA_Ac", o["Up_SIA_Ac"])
+    rng = np.random.default_rng(1)
+    up_ssa = rng.normal(0, 50.0, mesh_10k.nAc) * (o["mask_ice_Ac"] > 0)
+    o["Up_SSA_Ac"][:] = up_ssa
+    g.upload("Up_SSA_Ac", up_ssa)
+    noice = (rng.random(mesh_10k.nV) < 0.01).astype(np.int32)
+    o["mask_noice"][:] = noice
+    g.upload("mask_noice", noice)
+    o.calculate_ice_thickness_change(dt)
+    g.calculate_ice_thickness_change(dt)
+    for f in ["Hi", "dHi_dt", "Hi_prev"]:
+        assert_bits_equal(g.download(f), o[f], f)
+    if dt > 0 and name == "mismip":
+        assert (o["Hi"] >= 0).all() and (o["Hi"] == 0).any()
+
+
+def _ssa_setup_pair(mesh, nthreads=1, **params):
+    st = scenario(mesh, "icestream")
+    o, g = make_oracle(mesh, st, nthreads=nthreads, **{k: v for k, v in params.items() if k != "exact_xy"}), make_gpu(mesh, st, **params)
+    o.update_general_ice_model_data(0.0)
+    g.update_general_ice_model_data(0.0)
+    return o, g
+
+
+def test_ssa_prepare_viscosity_setup(mesh_10k):
+    o, g = _ssa_setup_pair(mesh_10k)
+    o.basal_yield_stress(); o.SSA_gather_AaAc()
+    g.ssa_prepare()
+    assert_bits_equal(g.download("phi_fric_AaAc"), o["phi_fric_AaAc"], "phi_fric")
+    np.testing.assert_allclose(g.download("tau_c_AaAc"), o["tau_c_AaAc"], rtol=1e-14)  # tan()
+    # a smooth non-trivial velocity field, identical on both sides
+    x, y = mesh_10k.VAaAc[:, 0], mesh_10k.VAaAc[:, 1]
+    U = 100.0 * np.sin(x / 2e5) * np.cos(y / 3e5); V = -80.0 * np.cos(x / 2.5e5) * np.sin(y / 2e5)
+    o["U_SSA_AaAc"][:] = U; o["V_SSA_AaAc"][:] = V
+    g.upload("U_SSA_AaAc", U); g.upload("V_SSA_AaAc", V)
+    g.upload("tau_c_AaAc", o["tau_c_AaAc"])
+    o.SSA_effective_viscosity()
+    sums = g.ssa_viscosity()
+    for f, of in [("dU_dx_AaAc", "dU_SSA_dx_AaAc"), ("dU_dy_AaAc", "dU_SSA_dy_AaAc"), ("dV_dx_AaAc", "dV_SSA_dx_AaAc"), ("dV_dy_AaAc", "dV_SSA_dy_AaAc")]:
+        assert_bits_equal(g.download(f), o[of], f)
+    np.testing.assert_allclose(g.download("eta_AaAc"), o["eta_AaAc"], rtol=1e-14)  # pow()
+    n = o["N_AaAc"]
+    np.testing.assert_allclose(sums[1], float((n * n).sum()), rtol=1e-12)
+    # identical eta on both sides -> sliding term within pow() accuracy, RHS / centre coefficients bit-exact given S
+    g.upload("eta_AaAc", o["eta_AaAc"])
+    o.SSA_sliding_term()
+    o.solve_SSA_linearised(max_inner=1, force_iters=True)  # fills RHS, eu, ev (and does one sweep we do not look at)
+    g.ssa_sliding_and_setup()
+    np.testing.assert_allclose(g.download("S_AaAc"), o["S_AaAc"], rtol=1e-14)
+    assert_bits_equal(g.download("RHSx_AaAc"), o["RHSx_AaAc"], "RHSx")
+    assert_bits_equal(g.download("RHSy_AaAc"), o["RHSy_AaAc"], "RHSy")
+    fin = np.isfinite(o["eu_i_AaAc"])
+    np.testing.assert_allclose(g.download("eu_i_AaAc")[fin], o["eu_i_AaAc"][fin], rtol=1e-13)
+    np.testing.assert_allclose(g.download("ev_i_AaAc")[fin], o["ev_i_AaAc"][fin], rtol=1e-13)
+
+
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("nthreads", [1, 8])
+def test_sor_bit_exact_at_prescribed_iterations(mesh_10k, k, nthreads):
+    """SURVEY section 7 acceptance: identical linear system on both sides, k forced SOR iterations."""
+    o, g = _ssa_setup_pair(mesh_10k, nthreads=nthreads)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare()
+    # the oracle's eta / tau_c define the system on both sides
+    g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"])
+    g.ssa_sliding_and_setup()
+    g.upload("S_AaAc", o["S_AaAc"])
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=k, force_iters=True)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    st = g.ssa_sor(max_inner=k, force_iters=True)
+    assert st.n_inner_last == k == n
+    assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
+    assert_bits_equal(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
+    assert st.last_max_residual == res
+
+
+def test_sor_presummed_xy_within_tolerance(mesh_10k):
+    o, g = _ssa_setup_pair(mesh_10k, exact_xy=0)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    o.solve_SSA_linearised(max_inner=100, force_iters=True)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    g.ssa_sor(max_inner=100, force_iters=True)
+    assert rel_l2(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"]) <= 1e-10
+    assert rel_l2(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"]) <= 1e-10
+
+
+def test_sor_natural_stop_and_quirk(mesh_10k):
+    """Stop test on the un-relaxed residual (ice_dynamics_module.f90:651-659,676)."""
+    o, g = _ssa_setup_pair(mesh_10k)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    n, res, did_reset, warn = o.solve_SSA_linearised()
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    st = g.ssa_sor()
+    assert (st.n_inner_last, st.did_reset) == (n, did_reset)
+    assert st.last_max_residual == res and res < 2.5
+    assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U")
+
+
+@pytest.mark.parametrize("gl_flux", [0, 1])
+def test_solve_SSA_full(mesh_10k, gl_flux):
+    """north_star gate: velocities within 1e-10 relative L2 after the same SOR iteration count."""
+    st = scenario(mesh_10k, "icestream")
+    o = make_oracle(mesh_10k, st, nthreads=8, use_analytical_GL_flux=gl_flux)
+    g = make_gpu(mesh_10k, st, use_analytical_GL_flux=gl_flux)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert (sg.n_outer, sg.n_inner_total, sg.did_reset) == (so.n_outer, so.n_inner_total, so.did_reset)
+    assert so.n_inner_total > 10
+    for f in ("U_SSA", "V_SSA", "Ux_SSA_Ac", "Uy_SSA_Ac", "Up_SSA_Ac", "Uo_SSA_Ac"):
+        assert rel_l2(g.download(f), o[f]) <= 1e-10, f
+    np.testing.assert_allclose(sg.last_RN, so.last_RN, rtol=1e-9)
+    # second call starts from the previous solution and the left-over N (ice_dynamics_module.f90:505)
+    so2, sg2 = o.solve_SSA(), g.solve_SSA()
+    assert (sg2.n_outer, sg2.n_inner_total) == (so2.n_outer, so2.n_inner_total)
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10
+
+
+def test_solve_SSA_zero_branches(mesh_2k):
+    st = S.state_halfar(mesh_2k)
+    g = make_gpu(mesh_2k, st)
+    g.update_general_ice_model_data(0.0)
+    g.upload("U_SSA", np.ones(mesh_2k.nV))
+    s = g.solve_SSA()  # Halfar: SSA not solved, velocities set to zero (ice_dynamics_module.f90:431-465)
+    assert s.n_outer == 0 and not g.download("U_SSA").any()
+    st2 = S.state_mismip(mesh_2k); st2["Hi"][:] = 0.0
+    g2 = make_gpu(mesh_2k, st2)
+    g2.update_general_ice_model_data(0.0)
+    assert g2.solve_SSA().n_outer == 0  # no grounded ice anywhere
+
+
+def test_cfl_bit_exact(mesh_10k):
+    st = scenario(mesh_10k, "halfar")
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    g.update_general_ice_model_data(0.0)
+    rng = np.random.default_rng(3)
+    for f, n in (("D_SIA_Ac", mesh_10k.nAc), ("U_SSA", mesh_10k.nV), ("V_SSA", mesh_10k.nV)):
+        a = o[f] if f == "D_SIA_Ac" else rng.normal(0, 300.0, n)
+        o[f][:] = a; g.upload(f, a)
+    u3 = rng.normal(0, 100.0, (mesh_10k.nV, 15))
+    o["U_3D"][:] = u3; g.upload("U_3D", u3)
+    assert g.determine_timesteps() == o.determine_timesteps()
+
+
+def test_run_model_halfar(mesh_2k):
+    """north_star gate: ice thickness after N model years within 1e-8 relative (same dt sequence)."""
+    from oracle.oracle import T_THERMO
+    st = S.state_halfar(mesh_2k)
+    o, g = make_oracle(mesh_2k, st, nthreads=4), make_gpu(mesh_2k, st)
+    ro, rg = o.region(0.0), g.region(0.0)
+    ro.dtc[T_THERMO] = 5.0; rg.dtc[T_THERMO] = 5.0
+    assert o.run_model(ro, 20.0) == 0
+    g.run_model(rg, 20.0)
+    assert rg.n_steps == ro.n_steps and rg.time == ro.time == 20.0
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+    assert np.abs(g.download("Hi") - o["Hi"]).max() <= 1e-8 * o["Hi"].max()
+
+
+def test_run_model_mismip_hybrid(mesh_2k):
+    """Hybrid SIA/SSA (config 4 physics) for a few model years: thickness and velocities track the oracle."""
+    st = scenario(mesh_2k, "mismip")
+    o, g = make_oracle(mesh_2k, st, nthreads=4), make_gpu(mesh_2k, st)
+    ro, rg = o.region(0.0), g.region(0.0)
+    assert o.run_model(ro, 3.0) == 0
+    g.run_model(rg, 3.0)
+    assert rg.n_steps == ro.n_steps and rg.n_sor_total == ro.n_sor_total
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-8
+
+
+def test_mesh_reupload_and_errors(mesh_2k):
+    from ufemism_b200.capi import UfmError
+    st = S.state_halfar(mesh_2k)
+    g = make_gpu(mesh_2k, st)
+    m2 = get_mesh(3000, seed=7)
+    g.upload_mesh(m2)  # device re-upload after a CPU mesh update: state is reallocated and zero
+    assert not g.download("Hi").any() and g.download("Hi").shape == (m2.nV,)
+    with pytest.raises(UfmError):
+        g.upload("mask_ice", np.zeros(m2.nV, np.int32))  # masks are outputs
+    bad = get_mesh(2000)
+    col = bad.colour_vi.copy()
+    import copy
+    b2 = copy.copy(bad); b2.colour_vi = col.copy()
+    # break the colouring: move one vertex into a neighbour's colour
+    a = int(col[0, 0]); nb = int(bad.CAaAc[a - 1, 0]); cn = int(bad.colour[nb - 1])
+    b2.colour_vi[0, 0] = col[bad.colour_nV[cn - 1] - 1, cn - 1]; b2.colour_vi[bad.colour_nV[cn - 1] - 1, cn - 1] = a
+    with pytest.raises(UfmError):
+        g.upload_mesh(b2)

@@ -1,0 +1,286 @@
+"""ctypes binding of the C ABI (``include/ufemism_b200.h``) -- the same calls the Fortran shim
+(``fortran/ufemism_b200_shim.f90``) makes through ISO_C_BINDING, with Fortran-ordered numpy arrays
+standing in for the reference's shared-memory windows.
+
+``IceModelGPU`` mirrors the reference's call surface for this path
+(``calculate_ice_thickness_change``, ``update_general_ice_model_data``, ``solve_SIA``, ``solve_SSA``:
+src/UFEMISM_main_model.f90:90,115,124,132).  There is no CPU fallback: if the CUDA library is
+missing or no B200 is visible the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libufemism_b200.so")
+HEADER = os.path.join(_HERE, "..", "include", "ufemism_b200.h")
+UFM_MAX_NZ = 32
+UFM_NT = 8
+T_SIA, T_SSA, T_THERMO, T_CLIMATE, T_SMB, T_BMB, T_ELRA, T_OUTPUT = range(8)
+
+BENCHMARKS = {"none": 0, "EISMINT_1": 1, "EISMINT_2": 2, "EISMINT_3": 3, "EISMINT_4": 4, "EISMINT_5": 5, "EISMINT_6": 6,
+              "Halfar": 7, "Bueler": 8, "MISMIP_mod": 9, "mesh_generation_test": 10, "SSA_icestream": 11}
+
+
+class UfmError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"ufemism_b200 rc={rc}: {msg}")
+        self.rc = rc
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("nZ", ctypes.c_int), ("zeta", ctypes.c_double * UFM_MAX_NZ), ("m_enh_sia", ctypes.c_double), ("m_enh_ssa", ctypes.c_double),
+                ("use_analytical_GL_flux", ctypes.c_int), ("SSA_RN_tol", ctypes.c_double), ("SSA_max_outer_loops", ctypes.c_int),
+                ("SSA_max_residual_UV", ctypes.c_double), ("SSA_SOR_omega", ctypes.c_double), ("SSA_max_inner_loops", ctypes.c_int),
+                ("dt_max", ctypes.c_double), ("benchmark", ctypes.c_int), ("exact_xy", ctypes.c_int)]
+
+
+_MESH_PTRS = ["V", "A", "nC", "C", "Cw", "edge_index", "Nx", "Ny", "Aci", "iAci", "edge_index_Ac", "Nx_Ac", "Ny_Ac", "No_Ac", "Np_Ac",
+              "nCAaAc", "CAaAc", "Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "colour_vi", "colour_nV"]
+_INT_FIELDS = {"nC", "C", "edge_index", "Aci", "iAci", "edge_index_Ac", "nCAaAc", "CAaAc", "colour_vi", "colour_nV"}
+
+
+class MeshDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("nV", "nAc", "nC_mem", "ldV", "ldAc", "ldAaAc")] + [(n, ctypes.c_void_p) for n in _MESH_PTRS]
+
+
+class SsaStats(ctypes.Structure):
+    _fields_ = [("n_outer", ctypes.c_int), ("n_inner_total", ctypes.c_int), ("n_inner_last", ctypes.c_int), ("did_reset", ctypes.c_int),
+                ("rc", ctypes.c_int), ("last_max_residual", ctypes.c_double), ("last_RN", ctypes.c_double)]
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_longlong), ("sor_iterations", ctypes.c_longlong), ("sor_ms", ctypes.c_double),
+                ("sor_launches", ctypes.c_longlong), ("sor_bytes_per_iteration", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
+                ("d2h_bytes", ctypes.c_double)]
+
+
+class Region(ctypes.Structure):
+    _fields_ = [("time", ctypes.c_double), ("dt", ctypes.c_double), ("dt_prev", ctypes.c_double),
+                ("t0", ctypes.c_double * UFM_NT), ("t1", ctypes.c_double * UFM_NT), ("dtc", ctypes.c_double * UFM_NT), ("do_", ctypes.c_int * UFM_NT),
+                ("H0", ctypes.c_double), ("R0", ctypes.c_double), ("lam", ctypes.c_double),
+                ("n_steps", ctypes.c_long), ("n_sia", ctypes.c_long), ("n_ssa", ctypes.c_long), ("n_sor_total", ctypes.c_long),
+                ("n_outer_total", ctypes.c_long), ("dt_crit_last", ctypes.c_double * 3)]
+
+
+def _parse_fields():
+    txt = open(HEADER).read()
+    body = txt[txt.index("enum ufm_field {"):]
+    body = body[: body.index("};")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"UFM_F_(\w+)", body)
+    out, i = {}, 0
+    for n in names:
+        if n == "COUNT":
+            break
+        out[n] = i
+        i += 1
+    return out
+
+
+FIELD_IDS = _parse_fields()
+# reference field name -> (id, kind, dtype); kind in {"Aa","Ac","AaAc","3D"}
+_REF_NAMES = {}
+for _n, _i in FIELD_IDS.items():
+    if _n.endswith("_AAAC"):
+        kind = "AaAc"
+    elif _n.endswith("_AC"):
+        kind = "Ac"
+    elif _n in ("U_3D", "V_3D"):
+        kind = "3D"
+    else:
+        kind = "Aa"
+    _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
+
+EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
+            "ufm_mesh_upload", "ufm_mesh_free", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
+            "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
+            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_counters_get", "ufm_counters_reset"]
+
+_lib = None
+
+
+def load_library():
+    """Load libufemism_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UfmError(-5, f"{LIB_PATH} not built; run `python -m ufemism_b200.build` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        p, i, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.ufm_create.argtypes = [i, p, p]
+        L.ufm_destroy.argtypes = [p]
+        L.ufm_set_params.argtypes = [p, p]
+        L.ufm_set_stream.argtypes = [p, p]
+        L.ufm_synchronize.argtypes = [p]
+        L.ufm_last_error.restype = ctypes.c_char_p
+        L.ufm_mesh_upload.argtypes = [p, p]
+        L.ufm_mesh_free.argtypes = [p]
+        L.ufm_state_upload.argtypes = [p, i, p]
+        L.ufm_state_download.argtypes = [p, i, p]
+        L.ufm_thickness_update.argtypes = [p, d]
+        L.ufm_update_general.argtypes = [p, d]
+        L.ufm_solve_SIA.argtypes = [p]
+        L.ufm_solve_SSA.argtypes = [p, p]
+        L.ufm_cfl.argtypes = [p, p]
+        L.ufm_ssa_prepare.argtypes = [p]
+        L.ufm_ssa_viscosity.argtypes = [p, p]
+        L.ufm_ssa_sliding_and_setup.argtypes = [p]
+        L.ufm_ssa_sor.argtypes = [p, i, i, p]
+        L.ufm_ssa_finish.argtypes = [p]
+        L.ufm_region_init.argtypes = [p, d]
+        L.ufm_run_model.argtypes = [p, p, d, ctypes.c_long]
+        L.ufm_counters_get.argtypes = [p, p]
+        L.ufm_counters_reset.argtypes = [p]
+        _lib = L
+    return _lib
+
+
+def default_params(benchmark="Halfar", **kw) -> Params:
+    """Defaults of src/configuration_module.f90:37,124-126,169-184 with the benchmark configs' m_enh = 1."""
+    P = Params()
+    P.nZ = 15
+    for k, z in enumerate([0.00, 0.10, 0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.90, 0.925, 0.95, 0.975, 0.99, 1.00]):
+        P.zeta[k] = z
+    P.m_enh_sia = 1.0
+    P.m_enh_ssa = 1.0
+    P.use_analytical_GL_flux = 0
+    P.SSA_RN_tol = 1e-5
+    P.SSA_max_outer_loops = 50
+    P.SSA_max_residual_UV = 2.5
+    P.SSA_SOR_omega = 1.2
+    P.SSA_max_inner_loops = 10000
+    P.dt_max = 10.0
+    P.benchmark = BENCHMARKS[benchmark]
+    P.exact_xy = 1
+    for k, v in kw.items():
+        setattr(P, k, v)
+    return P
+
+
+class IceModelGPU:
+    """One model region resident on one B200."""
+
+    def __init__(self, mesh, benchmark="Halfar", device=0, **params):
+        self.L = load_library()
+        self.mesh = mesh
+        self.P = default_params(benchmark, **params)
+        self.h = ctypes.c_void_p()
+        self._ck(self.L.ufm_create(int(device), ctypes.byref(self.P), ctypes.byref(self.h)))
+        self.upload_mesh(mesh)
+
+    def _ck(self, rc, allow_warning=False):
+        if rc < 0 or (rc > 0 and not allow_warning):
+            raise UfmError(rc, self.L.ufm_last_error().decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.L.ufm_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self.P, k, BENCHMARKS[v] if k == "benchmark" and isinstance(v, str) else v)
+        self._ck(self.L.ufm_set_params(self.h, ctypes.byref(self.P)))
+
+    def upload_mesh(self, mesh):
+        d = MeshDesc(nV=mesh.nV, nAc=mesh.nAc, nC_mem=mesh.nC_mem, ldV=mesh.nV, ldAc=mesh.nAc, ldAaAc=mesh.nVAaAc)
+        keep = []
+        for n in _MESH_PTRS:
+            a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
+            keep.append(a)
+            setattr(d, n, a.ctypes.data)
+        self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
+        self.mesh = mesh
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.ufm_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.L.ufm_synchronize(self.h))
+
+    # ---- state ----
+    def _shape(self, kind):
+        m = self.mesh
+        return {"Aa": (m.nV,), "Ac": (m.nAc,), "AaAc": (m.nVAaAc,), "3D": (m.nV, self.P.nZ)}[kind]
+
+    def upload(self, name, arr):
+        fid, kind, dt = _REF_NAMES[name.upper()]
+        a = np.asfortranarray(arr, dtype=dt)
+        assert a.shape == self._shape(kind), (name, a.shape, self._shape(kind))
+        self._ck(self.L.ufm_state_upload(self.h, fid, a.ctypes.data))
+
+    def download(self, name, out=None):
+        fid, kind, dt = _REF_NAMES[name.upper()]
+        if out is None:
+            out = np.zeros(self._shape(kind), dtype=dt, order="F")
+        self._ck(self.L.ufm_state_download(self.h, fid, out.ctypes.data))
+        return out
+
+    # ---- the reference's call surface ----
+    def calculate_ice_thickness_change(self, dt):
+        self._ck(self.L.ufm_thickness_update(self.h, float(dt)))
+
+    def update_general_ice_model_data(self, time=0.0):
+        self._ck(self.L.ufm_update_general(self.h, float(time)))
+
+    def solve_SIA(self):
+        self._ck(self.L.ufm_solve_SIA(self.h))
+
+    def solve_SSA(self):
+        st = SsaStats()
+        self._ck(self.L.ufm_solve_SSA(self.h, ctypes.byref(st)), allow_warning=True)
+        return st
+
+    def determine_timesteps(self):
+        out = (ctypes.c_double * 3)()
+        self._ck(self.L.ufm_cfl(self.h, out))
+        return list(out)
+
+    # ---- pieces of solve_SSA ----
+    def ssa_prepare(self):
+        self._ck(self.L.ufm_ssa_prepare(self.h))
+
+    def ssa_viscosity(self):
+        out = (ctypes.c_double * 2)()
+        self._ck(self.L.ufm_ssa_viscosity(self.h, out))
+        return list(out)
+
+    def ssa_sliding_and_setup(self):
+        self._ck(self.L.ufm_ssa_sliding_and_setup(self.h))
+
+    def ssa_sor(self, max_inner=0, force_iters=False):
+        st = SsaStats()
+        self._ck(self.L.ufm_ssa_sor(self.h, int(max_inner), int(force_iters), ctypes.byref(st)))
+        return st
+
+    def ssa_finish(self):
+        self._ck(self.L.ufm_ssa_finish(self.h))
+
+    # ---- region loop ----
+    def region(self, start_time=0.0):
+        r = Region()
+        self._ck(self.L.ufm_region_init(ctypes.byref(r), float(start_time)))
+        return r
+
+    def run_model(self, region, t_end, max_steps=0):
+        return self._ck(self.L.ufm_run_model(self.h, ctypes.byref(region), float(t_end), int(max_steps)))
+
+    def counters(self):
+        c = Counters()
+        self._ck(self.L.ufm_counters_get(self.h, ctypes.byref(c)))
+        return c
+
+    def reset_counters(self):
+        self._ck(self.L.ufm_counters_reset(self.h))

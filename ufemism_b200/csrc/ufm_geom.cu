@@ -1,0 +1,486 @@
+// ufm_geom.cu -- per-model-step kernels: update_general_ice_model_data, solve_SIA,
+// calculate_ice_thickness_change, the CFL minima, and the permuted field copies.
+//
+// Same arithmetic contract as ufm_ssa.cu (-fmad=false, reference evaluation order): everything
+// here is add/mul/div/sqrt/compare and reproduces the CPU restatement bit for bit, except the one
+// pow(x, 3.0) in the SIA diffusivity (CUDA libm <= 2 ulp).
+//
+// All kernels are streaming / gather kernels bounded by HBM bandwidth; rows are Morton-ordered so the
+// gathers of a warp fall into a few neighbouring 128 B lines.
+#include <math.h>
+
+#include <climits>
+#include <cstring>
+
+#include "ufm_internal.cuh"
+
+static inline int grid_for(long long n, int b) { return (int)((n + b - 1) / b); }
+
+__device__ __forceinline__ bool g_is_floating(double Hi, double Hb, double SL)
+{
+  return Hi < (SL - Hb) * UFM_SEAWATER_DENSITY / UFM_ICE_DENSITY;
+}
+__device__ __forceinline__ double g_Hs(double Hi, double Hb, double SL)
+{
+  // general_ice_model_data_module.f90:46-52
+  return Hi + fmax(SL - UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY * Hi, Hb);
+}
+__device__ __forceinline__ unsigned g_bits1(double Hi, double Hb, double SL)
+{
+  // determine_masks stage 1, :129-160 ; mask codes :108-116
+  unsigned b, code = 0;
+  const bool ocean = g_is_floating(Hi, Hb, SL), ice = Hi > 0.0;
+  b = ocean ? MB_OCEAN : MB_LAND;
+  if (ocean) code = 1;
+  if (ice) b |= MB_ICE;
+  if (ice && !ocean) { b |= MB_SHEET; code = 3; }
+  if (ice && ocean) { b |= MB_SHELF; code = 4; }
+  return b | (code << MB_CODE_SHIFT);
+}
+
+// ---- Aa stage 1: Hs, dHs_dt, primary mask bits ----
+__global__ void k_geom_aa1(int nV, const double *__restrict__ Hi, const double *__restrict__ Hb, const double *__restrict__ SL,
+                           const double *__restrict__ dHb_dt, const double *__restrict__ dHi_dt, double *__restrict__ Hs,
+                           double *__restrict__ dHs_dt, unsigned *__restrict__ mbits)
+{
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const double hi = Hi[v], hb = Hb[v], sl = SL[v];
+  Hs[v] = g_Hs(hi, hb, sl);
+  dHs_dt[v] = dHb_dt[v] + dHi_dt[v];
+  mbits[v] = g_bits1(hi, hb, sl);
+}
+
+// ---- Aa stage 2: gradients of Hi and Hs (get_mesh_derivatives, mesh_derivatives_module.f90:315-371),
+//      neighbour-dependent masks (:163-226), shelf slopes (:70-79).  One warp per slice. ----
+struct GeomAa2Args {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg;
+  const int *C;
+  const double *Nx, *Ny, *Nx0, *Ny0;
+  const double *Hi, *Hs;
+  unsigned *mbits;
+  double *dHi_dx, *dHi_dy, *dHs_dx, *dHs_dy, *sx, *sy;
+};
+__global__ void __launch_bounds__(256) k_geom_aa2(GeomAa2Args a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int w = (int)((a.off[s + 1] - o) >> 5);
+    const int v = s * 32 + lane;
+    const int n = a.deg[v];
+    if (n == UFM_DEG_PAD) continue;
+    const double hi = a.Hi[v], hs = a.Hs[v];
+    const unsigned own = a.mbits[v];
+    double ix = a.Nx0[v] * hi, iy = a.Ny0[v] * hi, sx = a.Nx0[v] * hs, sy = a.Ny0[v] * hs;
+    unsigned any_ocean = 0, any_noice = 0, any_shelf = 0;
+    for (int c = 0; c < w; c++) {
+      if (c < n) {
+        const long long e = o + (long long)c * 32 + lane;
+        const int j = __ldcs(a.C + e);
+        const double cx = __ldcs(a.Nx + e), cy = __ldcs(a.Ny + e);
+        const double hj = a.Hi[j], sj = a.Hs[j];
+        const unsigned bj = a.mbits[j];
+        ix = ix + cx * hj; iy = iy + cy * hj;
+        sx = sx + cx * sj; sy = sy + cy * sj;
+        any_ocean |= bj & MB_OCEAN; any_noice |= (~bj) & MB_ICE; any_shelf |= bj & MB_SHELF;
+      }
+    }
+    unsigned b = own & 0x3F, code = (own >> MB_CODE_SHIFT) & 0xF;
+    if ((own & MB_LAND) && any_ocean) { b |= MB_COAST; code = 5; }
+    if ((own & MB_ICE) && any_noice) { b |= MB_MARGIN; code = 6; }
+    if ((own & MB_SHEET) && any_shelf) { b |= MB_GL; code = 7; }
+    if ((own & MB_ICE) && any_ocean) { b |= MB_CF; code = 8; }
+    a.mbits[v] = b | (code << MB_CODE_SHIFT);
+    a.dHi_dx[v] = ix; a.dHi_dy[v] = iy; a.dHs_dx[v] = sx; a.dHs_dy[v] = sy;
+    if (!(own & MB_OCEAN)) { a.sx[v] = sx; a.sy[v] = sy; }
+    else {
+      a.sx[v] = (1.0 - UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY) * ix;
+      a.sy[v] = (1.0 - UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY) * iy;
+    }
+  }
+}
+
+// ---- Ac: map_Aa_to_Ac x3, Hs_Ac, masks on Ac (:232-294), get_mesh_derivatives_Ac x4
+//      (mesh_ArakawaC_module.f90:542-581) fused: coefficients and indices are read once for 16 outputs ----
+struct GeomAcArgs {
+  int nAc;
+  const int4 *Aci;
+  const double *Nx[4], *Ny[4], *No[4], *Np;
+  const double *Hi, *Hb, *SL, *Hs;
+  const unsigned *mbits;
+  double *Hi_Ac, *Hb_Ac, *SL_Ac, *Hs_Ac;
+  double *dHi[4], *dHb[4], *dHs[4], *dSL[4];
+  double *sx, *sy;
+  unsigned *mbits_Ac;
+};
+__global__ void __launch_bounds__(256) k_geom_ac(GeomAcArgs a)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nAc) return;
+  const int4 v = a.Aci[i];
+  const int vv[4] = {v.x, v.y, v.z, v.w};
+  double hi[4], hb[4], sl[4], hs[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { hi[k] = a.Hi[vv[k]]; hb[k] = a.Hb[vv[k]]; sl[k] = a.SL[vv[k]]; hs[k] = a.Hs[vv[k]]; }
+  const double hi_ac = (hi[0] + hi[1]) / 2.0, hb_ac = (hb[0] + hb[1]) / 2.0, sl_ac = (sl[0] + sl[1]) / 2.0;
+  a.Hi_Ac[i] = hi_ac; a.Hb_Ac[i] = hb_ac; a.SL_Ac[i] = sl_ac;
+  a.Hs_Ac[i] = g_Hs(hi_ac, hb_ac, sl_ac);
+  double d[4][3];  // [field][x,y,o]
+#pragma unroll
+  for (int f = 0; f < 4; f++) { d[f][0] = 0.0; d[f][1] = 0.0; d[f][2] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double nx = __ldcs(a.Nx[k] + i), ny = __ldcs(a.Ny[k] + i), no = __ldcs(a.No[k] + i);
+    d[0][0] = d[0][0] + nx * hi[k]; d[0][1] = d[0][1] + ny * hi[k]; d[0][2] = d[0][2] + no * hi[k];
+    d[1][0] = d[1][0] + nx * hb[k]; d[1][1] = d[1][1] + ny * hb[k]; d[1][2] = d[1][2] + no * hb[k];
+    d[2][0] = d[2][0] + nx * hs[k]; d[2][1] = d[2][1] + ny * hs[k]; d[2][2] = d[2][2] + no * hs[k];
+    d[3][0] = d[3][0] + nx * sl[k]; d[3][1] = d[3][1] + ny * sl[k]; d[3][2] = d[3][2] + no * sl[k];
+  }
+  const double np = __ldcs(a.Np + i);
+  a.dHi[0][i] = d[0][0]; a.dHi[1][i] = d[0][1]; a.dHi[2][i] = np * (hi[1] - hi[0]); a.dHi[3][i] = d[0][2];
+  a.dHb[0][i] = d[1][0]; a.dHb[1][i] = d[1][1]; a.dHb[2][i] = np * (hb[1] - hb[0]); a.dHb[3][i] = d[1][2];
+  a.dHs[0][i] = d[2][0]; a.dHs[1][i] = d[2][1]; a.dHs[2][i] = np * (hs[1] - hs[0]); a.dHs[3][i] = d[2][2];
+  a.dSL[0][i] = d[3][0]; a.dSL[1][i] = d[3][1]; a.dSL[2][i] = np * (sl[1] - sl[0]); a.dSL[3][i] = d[3][2];
+  unsigned b = g_bits1(hi_ac, hb_ac, sl_ac), code = (b >> MB_CODE_SHIFT) & 0xF;
+  b &= 0x3F;
+  const unsigned bi = a.mbits[v.x], bj = a.mbits[v.y];
+  if (((bi & MB_LAND) && (bj & MB_OCEAN)) || ((bj & MB_LAND) && (bi & MB_OCEAN))) { b |= MB_COAST; code = 5; }
+  if (((bi & MB_ICE) && !(bj & MB_ICE)) || ((bj & MB_ICE) && !(bi & MB_ICE))) { b |= MB_MARGIN; code = 6; }
+  if (((bi & MB_SHEET) && (bj & MB_SHELF)) || ((bj & MB_SHEET) && (bi & MB_SHELF))) { b |= MB_GL; code = 7; }
+  if (((bi & MB_ICE) && !(bj & MB_SHELF) && (bj & MB_OCEAN)) || ((bj & MB_ICE) && !(bi & MB_SHELF) && (bi & MB_OCEAN))) { b |= MB_CF; code = 8; }
+  a.mbits_Ac[i] = b | (code << MB_CODE_SHIFT);
+  if (!(b & MB_OCEAN)) { a.sx[i] = d[2][0]; a.sy[i] = d[2][1]; }
+  else {
+    a.sx[i] = (1.0 - UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY) * d[0][0];
+    a.sy[i] = (1.0 - UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY) * d[0][1];
+  }
+}
+
+// ---- solve_SIA on Ac (ice_dynamics_module.f90:240-306); the 3-D diffusivity profile stays in registers.
+//      With the benchmark (vertically constant) flow factor the integral of m_enh*A*zeta^n is the same for
+//      every column and is evaluated once on the host exactly as vertical_integrate does (zeta_module.f90:58-85). ----
+struct SiaConst { int nZ; double I[UFM_MAX_NZ]; double dz[UFM_MAX_NZ]; };
+__global__ void __launch_bounds__(256) k_sia_ac(int nAc, SiaConst K, const unsigned *__restrict__ mbits_Ac, const double *__restrict__ Hi_Ac,
+                                                const double *__restrict__ hx, const double *__restrict__ hy, const double *__restrict__ hp,
+                                                const double *__restrict__ ho, double *__restrict__ D_SIA_Ac, double *__restrict__ Ux,
+                                                double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nAc) return;
+  double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
+  if (mbits_Ac[i] & MB_SHEET) {
+    const double D_uv_3D_cutoff = -1E5;
+    const double H = Hi_Ac[i], sp = hp[i], so = ho[i];
+    // (rho g H)**n_flow * (hp**2 + ho**2)**((n_flow-1)/2)   [x**1.0 == x]
+    const double D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
+    const double twoH = 2.0 * H;
+    double prev = D_0 * (twoH * K.I[0]);
+    if (prev < D_uv_3D_cutoff) prev = D_uv_3D_cutoff;
+    double avg = 0.0;
+    for (int k = 1; k < K.nZ; k++) {
+      double cur = D_0 * (twoH * K.I[k]);
+      if (cur < D_uv_3D_cutoff) cur = D_uv_3D_cutoff;
+      avg = avg + 0.5 * (cur + prev) * K.dz[k];  // vertical_average, zeta_module.f90:53-56
+      prev = cur;
+    }
+    D = H * avg; ux = avg * hx[i]; uy = avg * hy[i]; up = avg * sp; uo = avg * so;
+  }
+  D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo;
+}
+
+// ---- map_Ac_to_Aa x3 (mesh_ArakawaC_module.f90:770-791), diagnostic U_SIA, V_SIA, D_SIA ----
+struct SiaAaArgs {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg;
+  const int *iAci;
+  const double *Ux, *Uy, *D;
+  double *U_SIA, *V_SIA, *D_SIA;
+};
+__global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int w = (int)((a.off[s + 1] - o) >> 5);
+    const int v = s * 32 + lane;
+    const int n = a.deg[v];
+    if (n == UFM_DEG_PAD) continue;
+    const double dn = (double)n;
+    double u = 0.0, vv = 0.0, dd = 0.0;
+    for (int c = 0; c < w; c++) {
+      if (c < n) {
+        const int ac = a.iAci[o + (long long)c * 32 + lane] & 0x7fffffff;
+        u = u + a.Ux[ac] / dn; vv = vv + a.Uy[ac] / dn; dd = dd + a.D[ac] / dn;
+      }
+    }
+    a.U_SIA[v] = u; a.V_SIA[v] = vv; a.D_SIA[v] = dd;
+  }
+}
+
+// ---- calculate_ice_thickness_change (ice_dynamics_module.f90:31-237) as two gather passes.
+//      The limiter only rescales OUT-fluxes by a factor of the source vertex (:115-166), so the result is
+//      order independent: pass 1 = factor per vertex, pass 2 = flux sum with the neighbours' factors. ----
+struct ThkArgs {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg, *edge;
+  const int *C, *iAci;
+  const double *A, *Cw, *UpSIA, *UpSSA, *Hi, *SMB, *BMB;
+  const int *noice;
+  double dt;
+  double *factor, *smb;              // pass 1 out / pass 2 in
+  double *Hi_new, *dHi_dt;           // pass 2 out
+};
+__device__ __forceinline__ double thk_entry(const ThkArgs &a, long long e, int v, double hv, int *other)
+{
+  const int ia = a.iAci[e], j = a.C[e];
+  const bool first = ia < 0;
+  const int ac = ia & 0x7fffffff;
+  const double Upar = a.UpSIA[ac] + a.UpSSA[ac];
+  const double hj = a.Hi[j];
+  const double h_up = (Upar > 0.0) ? (first ? hv : hj) : (first ? hj : hv);
+  const double dVi = h_up * Upar * a.Cw[ac] * a.dt;
+  *other = j;
+  return first ? -dVi : dVi;
+}
+template <int PASS>
+__global__ void __launch_bounds__(256) k_thk(ThkArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int w = (int)((a.off[s + 1] - o) >> 5);
+    const int v = s * 32 + lane;
+    const int n = a.deg[v];
+    if (n == UFM_DEG_PAD) continue;
+    const double hv = a.Hi[v], Av = a.A[v];
+    if (PASS == 1) {
+      double Vi_out = 0.0;
+      for (int c = 0; c < w; c++) {
+        if (c < n) {
+          int j;
+          const double en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
+          if (!(en > 0.0)) Vi_out = Vi_out - en;
+        }
+      }
+      double Vi_SMB = (a.SMB[v] + a.BMB[v]) * Av * a.dt;
+      const double Vi_available = Av * hv;
+      double rescale_factor = 1.0;
+      if (-Vi_SMB >= Vi_available) { Vi_SMB = -Vi_available; rescale_factor = 0.0; }
+      if (Vi_out > Vi_available + Vi_SMB) rescale_factor = (Vi_available + Vi_SMB) / Vi_out;
+      a.factor[v] = rescale_factor; a.smb[v] = Vi_SMB;
+    } else {
+      const double fv = a.factor[v];
+      double dVi = 0.0;
+      for (int c = 0; c < w; c++) {
+        if (c < n) {
+          int j;
+          double en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
+          if (en < 0.0) { if (fv < 1.0) en = en * fv; }
+          else if (en > 0.0) { const double fj = a.factor[j]; if (fj < 1.0) en = -((-en) * fj); }
+          dVi = dVi + en;
+        }
+      }
+      double dh = (dVi + a.smb[v]) / (Av * a.dt);
+      if (a.dt == 0.0) dh = 0.0;
+      double hn = hv + (dh * a.dt);
+      if (a.edge[v] > 0) hn = 0.0;
+      if (a.noice[v] == 1) hn = 0.0;
+      a.dHi_dt[v] = dh; a.Hi_new[v] = hn;
+    }
+  }
+}
+
+// ---- critical time steps (UFEMISM_main_model.f90:747-768) ----
+__device__ __forceinline__ unsigned long long ord_key(double x)
+{
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double ord_unkey(unsigned long long k)
+{
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double x;
+#ifdef __CUDA_ARCH__
+  x = __longlong_as_double((long long)b);
+#else
+  memcpy(&x, &b, sizeof(x));
+#endif
+  return x;
+}
+__global__ void __launch_bounds__(256) k_cfl(int nV, int nVp, int nAc, int nZ, const int4 *__restrict__ Aci, const double *__restrict__ Dx_,
+                                             const double *__restrict__ Dy_, const double *__restrict__ D_SIA_Ac, const double *__restrict__ U,
+                                             const double *__restrict__ V, const double *__restrict__ sqrtApi, const double *__restrict__ U3,
+                                             const double *__restrict__ V3, unsigned long long *keys)
+{
+  double mD = 1000.0, mS = 1000.0, m3 = 1000.0;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int i = t0; i < nAc; i += nt) {
+    const int4 v = Aci[i];
+    const double dx = Dx_[i], dy = Dy_[i];
+    const double dist = sqrt(dx * dx + dy * dy);
+    const double dtD = (dist * dist) / (-6.0 * UFM_PI * (D_SIA_Ac[i] - (double)1E-09f));  // single-precision literal at :752
+    mD = fmin(dtD, mD);
+    mS = fmin(dist / (fabs(U[v.x]) + fabs(V[v.x])), mS);
+    mS = fmin(dist / (fabs(U[v.y]) + fabs(V[v.y])), mS);
+  }
+  for (int i = t0; i < nV; i += nt) {
+    const double r = sqrtApi[i];
+    mS = fmin(r / (fabs(U[i]) + fabs(V[i])), mS);
+    for (int k = 0; k < nZ; k++) m3 = fmin(r / (fabs(U3[(size_t)k * nVp + i]) + fabs(V3[(size_t)k * nVp + i])), m3);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mD = fmin(mD, __shfl_xor_sync(0xffffffffu, mD, o)); mS = fmin(mS, __shfl_xor_sync(0xffffffffu, mS, o)); m3 = fmin(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(keys + 0, ord_key(mD)); atomicMin(keys + 1, ord_key(mS)); atomicMin(keys + 2, ord_key(m3)); }
+}
+
+// ---- permuted copies between reference order (device staging) and device order ----
+// dev element (row r) lives at dev[r*stride + comp]; ref element i at ref[i]
+__global__ void k_perm_d(int n, const int *__restrict__ r2d, double *dev, int stride, int comp, double *ref, int to_device)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t p = (size_t)r2d[i] * stride + comp;
+  if (to_device) dev[p] = ref[i]; else ref[i] = dev[p];
+}
+__global__ void k_perm_i(int n, const int *__restrict__ r2d, int *dev, int *ref, int to_device)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_device) dev[r2d[i]] = ref[i]; else ref[i] = dev[r2d[i]];
+}
+// mode 0: (bits & arg) != 0 ; mode 1: the ice%mask code
+__global__ void k_perm_mask(int n, const int *__restrict__ r2d, const unsigned *__restrict__ bits, unsigned arg, int mode, int *ref)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned b = bits[r2d[i]];
+  ref[i] = mode ? (int)((b >> MB_CODE_SHIFT) & 0xF) : ((b & arg) ? 1 : 0);
+}
+__global__ void k_perm_3d(int n, int nZ, int nVp, const int *__restrict__ r2d, double *dev, double *ref, int to_device)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < nZ; k++) {
+    size_t p = (size_t)k * nVp + r2d[i], q = (size_t)k * n + i;
+    if (to_device) dev[p] = ref[q]; else ref[q] = dev[p];
+  }
+}
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+int ufm_perm_double(ufm_handle *h, int n, const int *r2d, double *dev, int stride, int comp, double *ref_dev, int to_device)
+{
+  k_perm_d<<<grid_for(n, 256), 256, 0, h->stream>>>(n, r2d, dev, stride, comp, ref_dev, to_device);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_perm_d");
+}
+int ufm_perm_int(ufm_handle *h, int n, const int *r2d, int *dev, int *ref_dev, int to_device)
+{
+  k_perm_i<<<grid_for(n, 256), 256, 0, h->stream>>>(n, r2d, dev, ref_dev, to_device);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_perm_i");
+}
+int ufm_perm_mask(ufm_handle *h, int n, const int *r2d, const unsigned *bits, unsigned arg, int mode, int *ref_dev)
+{
+  k_perm_mask<<<grid_for(n, 256), 256, 0, h->stream>>>(n, r2d, bits, arg, mode, ref_dev);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_perm_mask");
+}
+int ufm_perm_3d(ufm_handle *h, int n, int nZ, int nVp, const int *r2d, double *dev, double *ref_dev, int to_device)
+{
+  k_perm_3d<<<grid_for(n, 256), 256, 0, h->stream>>>(n, nZ, nVp, r2d, dev, ref_dev, to_device);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_perm_3d");
+}
+
+int ufm_k_geom(ufm_handle *h, double time)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  // ice_physical_properties, benchmark branches (general_ice_model_data_module.f90:321-368)
+  const int b = h->P.benchmark;
+  if (b == UFM_BM_NONE) return ufm_set_error(-4, "update_general_ice_model_data: temperature-dependent flow factor (do_benchmark_experiment = .FALSE.) is not on the device path yet");
+  double A_flow = 1.0E-16;
+  if (b == UFM_BM_MISMIP_MOD || b == UFM_BM_SSA_ICESTREAM) {
+    if (time < 25000.0) A_flow = 1.0E-16; else if (time < 50000.0) A_flow = 1.0E-17; else if (time < 75000.0) A_flow = 1.0E-16;
+  }
+  s.A_flow_const = A_flow;
+  k_geom_aa1<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, s.Hi, s.Hb, s.SL, s.dHb_dt, s.dHi_dt, s.Hs, s.dHs_dt, s.mbits);
+  GeomAa2Args a2;
+  a2.n_slices = m.aa.n_slices; a2.off = m.aa.off; a2.deg = m.aa.deg; a2.C = m.aa_C; a2.Nx = m.aa_Nx; a2.Ny = m.aa_Ny; a2.Nx0 = m.aa_Nx0; a2.Ny0 = m.aa_Ny0;
+  a2.Hi = s.Hi; a2.Hs = s.Hs; a2.mbits = s.mbits; a2.dHi_dx = s.dHi_dx; a2.dHi_dy = s.dHi_dy; a2.dHs_dx = s.dHs_dx; a2.dHs_dy = s.dHs_dy;
+  a2.sx = s.dHs_dx_shelf; a2.sy = s.dHs_dy_shelf;
+  int g2 = grid_for((long long)m.aa.n_slices * 32, 256);
+  k_geom_aa2<<<g2, 256, 0, h->stream>>>(a2);
+  GeomAcArgs ac;
+  ac.nAc = m.nAc; ac.Aci = m.ac_Aci; ac.Np = m.ac_Np;
+  for (int k = 0; k < 4; k++) { ac.Nx[k] = m.ac_Nx[k]; ac.Ny[k] = m.ac_Ny[k]; ac.No[k] = m.ac_No[k]; ac.dHi[k] = s.dHi_Ac[k]; ac.dHb[k] = s.dHb_Ac[k]; ac.dHs[k] = s.dHs_Ac[k]; ac.dSL[k] = s.dSL_Ac[k]; }
+  ac.Hi = s.Hi; ac.Hb = s.Hb; ac.SL = s.SL; ac.Hs = s.Hs; ac.mbits = s.mbits;
+  ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac;
+  k_geom_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(ac);
+  h->cnt.kernel_launches += 3;
+  return ufm_cuda_check(cudaGetLastError(), "k_geom");
+}
+
+int ufm_k_sia(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  SiaConst K;
+  K.nZ = h->P.nZ;
+  // vertical_integrate( C%m_enh_sia * A_flow_Ac(aci,:) * C%zeta**n_flow ), zeta_module.f90:81-84
+  double f[UFM_MAX_NZ];
+  for (int k = 0; k < K.nZ; k++) f[k] = h->P.m_enh_sia * s.A_flow_const * h->zeta3[k];
+  K.I[K.nZ - 1] = 0.0;
+  for (int k = K.nZ - 1; k >= 1; k--) K.I[k - 1] = K.I[k] - 0.5 * (f[k] + f[k - 1]) * (h->P.zeta[k] - h->P.zeta[k - 1]);
+  K.dz[0] = 0.0;
+  for (int k = 1; k < K.nZ; k++) K.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+  k_sia_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, K, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1], s.dHs_Ac[2], s.dHs_Ac[3],
+                                                       s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3]);
+  SiaAaArgs a;
+  a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.iAci = m.aa_iAci; a.Ux = s.U_SIA_Ac[0]; a.Uy = s.U_SIA_Ac[1]; a.D = s.D_SIA_Ac;
+  a.U_SIA = s.U_SIA; a.V_SIA = s.V_SIA; a.D_SIA = s.D_SIA;
+  k_sia_aa<<<grid_for((long long)m.aa.n_slices * 32, 256), 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches += 2;
+  return ufm_cuda_check(cudaGetLastError(), "k_sia");
+}
+
+int ufm_k_thickness(ufm_handle *h, double dt)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  ThkArgs a;
+  a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.edge = m.aa_edge; a.C = m.aa_C; a.iAci = m.aa_iAci; a.A = m.aa_A; a.Cw = m.ac_Cw;
+  a.UpSIA = s.U_SIA_Ac[2]; a.UpSSA = s.U_SSA_Ac[2]; a.Hi = s.Hi; a.SMB = s.SMB_year; a.BMB = s.BMB; a.noice = s.mask_noice; a.dt = dt;
+  a.factor = s.thk_factor; a.smb = s.thk_smb; a.Hi_new = s.Hi_alt; a.dHi_dt = s.dHi_dt;
+  int g = grid_for((long long)m.aa.n_slices * 32, 256);
+  k_thk<1><<<g, 256, 0, h->stream>>>(a);
+  k_thk<2><<<g, 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches += 2;
+  // Hi_prev = Hi ; Hi = new  (pointer swap: the old buffer IS Hi_prev)
+  double *t = s.Hi; s.Hi = s.Hi_alt; s.Hi_alt = t;
+  return ufm_cuda_check(cudaGetLastError(), "k_thk");
+}
+
+int ufm_k_cfl(ufm_handle *h, double out3[3])
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  unsigned long long *keys = s.ctrl + 24;
+  UFM_CUDA(cudaMemsetAsync(keys, 0xFF, 3 * sizeof(unsigned long long), h->stream));
+  k_cfl<<<h->num_sms * 4, 256, 0, h->stream>>>(m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_Aci, m.ac_Dx, m.ac_Dy, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
+                                               m.aa_sqrtApi, s.U_3D, s.V_3D, keys);
+  h->cnt.kernel_launches++;
+  unsigned long long *res = (unsigned long long *)(s.scal_h + 16);
+  UFM_CUDA(cudaMemcpyAsync(res, keys, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  const double dt_correction_factor = 0.9;
+  for (int k = 0; k < 3; k++) out3[k] = ord_unkey(res[k]) * dt_correction_factor;
+  return 0;
+}

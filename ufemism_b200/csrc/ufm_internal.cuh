@@ -1,0 +1,154 @@
+// ufm_internal.cuh -- device-side data layout of libufemism_b200.so (not part of the ABI).
+//
+// HBM layout:
+//  * three index spaces, each renumbered at upload for locality:
+//      Aa   (nV vertices)      : Morton order of V
+//      Ac   (nAc staggered)    : Morton order of the edge midpoint
+//      AaAc (nV+nAc combined)  : colour-major; inside a colour by (degree, Morton); every colour
+//                                block starts on a multiple of 32; domain-edge vertices (never swept)
+//                                form a sixth block at the end.  Padding rows have deg = DEG_PAD.
+//  * neighbour data are "sliced ELL": rows in groups of 32 (one warp), slice s has width w_s =
+//    max degree in the slice and its entries live at off_s + c*32 + lane, so a warp reading column c
+//    of its slice touches one contiguous 128 B (int) / 256 B (double) segment.
+//  * everything is SoA except (U,V), (RHSx,RHSy), (e_u,e_v) which are double2 pairs because they
+//    are always consumed together (one 16 B gather per neighbour instead of two 8 B gathers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ufemism_b200.h"
+
+#define UFM_DEG_PAD 0xFF
+#define UFM_SLICE 32
+
+// src/parameters_module.f90:9-21
+#define UFM_PI 3.141592653589793
+#define UFM_SEC_PER_YEAR 31556943.36
+#define UFM_GRAV 9.81
+#define UFM_N_FLOW 3.0
+#define UFM_ICE_DENSITY 910.0
+#define UFM_SEAWATER_DENSITY 1028.0
+#define UFM_SMT 271.15
+
+// mask bits (determine_masks, src/general_ice_model_data_module.f90:97-297); bits 12..15 = ice%mask code
+enum { MB_LAND = 1, MB_OCEAN = 2, MB_LAKE = 4, MB_ICE = 8, MB_SHEET = 16, MB_SHELF = 32, MB_COAST = 64, MB_MARGIN = 128,
+       MB_GL = 256, MB_CF = 512, MB_CODE_SHIFT = 12 };
+
+struct SlicedEll {
+  int n_rows = 0;            // padded to a multiple of 32
+  int n_slices = 0;
+  long long n_entries = 0;
+  long long *off = nullptr;  // [n_slices+1] element offsets (device)
+  unsigned char *deg = nullptr;  // [n_rows] (device) row degree, UFM_DEG_PAD for padding rows
+};
+
+struct DevMesh {
+  int nV = 0, nAc = 0, M = 0;     // reference sizes
+  int nVp = 0, nAcp = 0, Mp = 0;  // padded device sizes
+  // permutations (device + host copies): ref (0-based) -> device position, and back (-1 = padding)
+  int *aa_ref2dev = nullptr, *aa_dev2ref = nullptr;
+  int *ac_ref2dev = nullptr, *ac_dev2ref = nullptr;
+  int *m_ref2dev = nullptr, *m_dev2ref = nullptr;
+  // ---- Aa ----
+  SlicedEll aa;               // rows = Aa vertices
+  int *aa_C = nullptr;        // neighbour Aa (device idx)
+  int *aa_iAci = nullptr;     // Ac of each connection (device idx); bit 31 set when this vertex is Aci(aci,1)
+  double *aa_Nx = nullptr, *aa_Ny = nullptr;  // neighbour functions per connection
+  double *aa_Nx0 = nullptr, *aa_Ny0 = nullptr;  // home coefficients Nx(vi,nC+1)
+  double *aa_A = nullptr;     // Voronoi area
+  double *aa_sqrtApi = nullptr;  // SQRT(A/pi) (CFL)
+  unsigned char *aa_edge = nullptr;  // edge_index
+  // ---- Ac ----
+  int4 *ac_Aci = nullptr;     // vi, vj, vl, vr (device Aa idx)
+  double *ac_Nx[4] = {}, *ac_Ny[4] = {}, *ac_No[4] = {};
+  double *ac_Np = nullptr;
+  double *ac_Cw = nullptr;    // Cw( Aci(aci,1), ci ) as used at ice_dynamics_module.f90:95
+  double *ac_Dx = nullptr, *ac_Dy = nullptr;  // V(vj)-V(vi)
+  // ---- AaAc ----
+  SlicedEll m;
+  int *m_idx = nullptr;                   // neighbour positions
+  double *m_cU = nullptr, *m_cV = nullptr;  // 4Nxx+Nyy, 4Nyy+Nxx per neighbour
+  double *m_nxy = nullptr;                // Nxy per neighbour
+  double *m_nx = nullptr, *m_ny = nullptr;
+  double *m_nxy0 = nullptr, *m_nxysum = nullptr;  // home Nxy; pre-summed row (exact_xy = 0)
+  double *m_nx0 = nullptr, *m_ny0 = nullptr;
+  double *m_cU0 = nullptr, *m_cV0 = nullptr;      // 4Nxx+Nyy, 4Nyy+Nxx home
+  int *m_src = nullptr;        // >= 0: Aa device idx; < 0: ~(Ac device idx); INT_MIN: padding
+  int *aa2m = nullptr, *ac2m = nullptr;  // Aa / Ac device idx -> AaAc position
+  int col_begin[6] = {}, col_end[6] = {};  // slice ranges [begin,end) of colours 1..5 (non-edge rows) ; [5] = edge block
+  // Neumann boundary lists
+  int n_bc = 0;                // edge vertices except corners 1..4
+  int *bc_pos = nullptr, *bc_ptr = nullptr, *bc_nbr = nullptr;
+  int corner_pos[4] = {}, corner_n[4] = {};
+  int *col_dev = nullptr;      // [10] col_begin[0..4], col_end[0..4] (device copy for the SOR kernel)
+  int *corner_dev = nullptr;   // [8] corner_pos, corner_n
+  int *corner_nbr = nullptr;   // [4*16] neighbour position
+  int *corner_row = nullptr;   // [4*16] bc row of that neighbour, or -1 when it is not an edge vertex
+  double sor_bytes = 0;        // sum_i (80 + 20 n_i) over swept vertices
+};
+
+struct DevState {
+  // Aa
+  double *Hi = nullptr, *Hi_alt = nullptr, *Hb = nullptr, *SL = nullptr, *Hs = nullptr, *dHb_dt = nullptr, *dHi_dt = nullptr, *dHs_dt = nullptr;
+  double *dHi_dx = nullptr, *dHi_dy = nullptr, *dHs_dx = nullptr, *dHs_dy = nullptr, *dHs_dx_shelf = nullptr, *dHs_dy_shelf = nullptr;
+  double *U_SIA = nullptr, *V_SIA = nullptr, *D_SIA = nullptr, *U_SSA = nullptr, *V_SSA = nullptr, *SMB_year = nullptr, *BMB = nullptr;
+  double *thk_factor = nullptr, *thk_smb = nullptr;
+  double *U_3D = nullptr, *V_3D = nullptr;  // (nV,nZ) device layout k-major: [k*nVp + v]
+  int *mask_noice = nullptr;
+  unsigned *mbits = nullptr;
+  // Ac
+  double *Hi_Ac = nullptr, *Hb_Ac = nullptr, *SL_Ac = nullptr, *Hs_Ac = nullptr;
+  double *dHi_Ac[4] = {}, *dHb_Ac[4] = {}, *dHs_Ac[4] = {}, *dSL_Ac[4] = {};  // x, y, p, o
+  double *dHs_dx_shelf_Ac = nullptr, *dHs_dy_shelf_Ac = nullptr;
+  double *U_SIA_Ac[4] = {}, *U_SSA_Ac[4] = {};  // x, y, p, o
+  double *D_SIA_Ac = nullptr, *Qabs_GL_Ac = nullptr, *Qp_GL_Ac = nullptr;
+  unsigned *mbits_Ac = nullptr;
+  // AaAc
+  double2 *UV = nullptr, *RHS = nullptr, *E = nullptr, *rhsnum = nullptr, *dU = nullptr, *dV = nullptr;
+  double *eta = nullptr, *N = nullptr, *S = nullptr, *tau_c = nullptr, *phi = nullptr, *Hm = nullptr;
+  unsigned char *mflag = nullptr;  // bit0 grounded (not floating), bit1 held fixed (GL flux)
+  double A_flow_const = 1.0e-16;   // benchmark flow factor (ice_physical_properties)
+  // reductions / control
+  double *partials = nullptr;      // [2*n_partial]
+  unsigned long long *ctrl = nullptr;  // SOR control block
+  double *scal = nullptr;          // small result scratch (device), mirrored in pinned host memory
+  double *scal_h = nullptr;
+};
+
+struct ufm_handle {
+  int device = 0;
+  ufm_params P;
+  double zeta3[UFM_MAX_NZ];      // C%zeta**n_flow, evaluated with the host libm like the reference
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  bool has_mesh = false;
+  DevMesh mesh;
+  DevState st;
+  ufm_counters cnt;
+  int sor_grid = 0, sor_block = 256;
+  void *staging = nullptr;       // pinned host staging for upload/download permutation
+  size_t staging_bytes = 0;
+  void *dev_staging = nullptr;
+  size_t dev_staging_bytes = 0;
+};
+
+int ufm_set_error(int rc, const char *fmt, ...);
+int ufm_cuda_check(cudaError_t e, const char *what);
+#define UFM_CUDA(x) do { int rc__ = ufm_cuda_check((x), #x); if (rc__) return rc__; } while (0)
+
+// launchers (each returns 0 or a negative rc)
+int ufm_k_geom(ufm_handle *h, double time);
+int ufm_k_sia(ufm_handle *h);
+int ufm_k_thickness(ufm_handle *h, double dt);
+int ufm_k_cfl(ufm_handle *h, double out3[3]);
+int ufm_k_ssa_prepare(ufm_handle *h);
+int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2]);
+int ufm_k_ssa_sliding_setup(ufm_handle *h);
+int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *stats);
+int ufm_k_ssa_finish(ufm_handle *h);
+int ufm_k_ssa_zero(ufm_handle *h);
+int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out);
+int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double lambda);
+int ufm_k_permute(ufm_handle *h, int kind, int is_int, int to_device, void *dev_field, void *dev_staging, int n_ref);
+int ufm_sor_configure(ufm_handle *h);

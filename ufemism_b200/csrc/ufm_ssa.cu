@@ -1,0 +1,503 @@
+// ufm_ssa.cu -- SSA stress balance on the combined AaAc mesh: hand-written sm_100a kernels.
+//
+// Replaces the bodies of solve_SSA / solve_SSA_linearised / SSA_effective_viscosity /
+// SSA_sliding_term / basal_yield_stress / calculate_GL_flux (src/ice_dynamics_module.f90:408-949)
+// and the AaAc operators they call (src/mesh_ArakawaC_module.f90:583-724,815-844).
+//
+// Arithmetic contract: this translation unit is compiled with -fmad=false, every expression is
+// written in the reference's evaluation order, fp64 add/mul/div/sqrt are IEEE-exact on the GPU, so
+// the SOR sweep, the Neumann pass and the linear-system setup reproduce the CPU restatement BIT FOR
+// BIT; only pow() and tan() (CUDA libm <= 2 ulp vs glibc <= 1 ulp) can differ, by O(1e-16) relative.
+//
+// The hot loop is ONE persistent cooperative kernel per linear solve: 5 colour phases + 1 boundary
+// phase per SOR iteration separated by grid-wide barriers, the max-residual reduced with warp
+// shuffles + one atomicMax per CTA, the stop tests evaluated on the device.  No tensor cores: nothing
+// here is a dense contraction (irregular 4..8-point stencils); the bound is HBM bandwidth.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <climits>
+#include <cstdio>
+
+#include "ufm_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+// streaming (read-once) loads: evict-first so that (U,V) stays L2-resident across colour phases
+template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
+
+__device__ __forceinline__ bool d_is_floating(double Hi, double Hb, double SL)
+{
+  return Hi < (SL - Hb) * UFM_SEAWATER_DENSITY / UFM_ICE_DENSITY;  // general_ice_model_data_module.f90:464-475
+}
+
+// ---------------------------------------------------------------------------------------------
+// calculate_GL_flux, ice_dynamics_module.f90:848-949 (Coulomb_regularised).  One thread per Ac.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned *__restrict__ mbits_Ac, const unsigned *__restrict__ mbits,
+                          const double *__restrict__ Hi, const double *__restrict__ Hb, const double *__restrict__ SL,
+                          const double *__restrict__ phi_m, const int *__restrict__ aa2m, double A_flow,
+                          const double *__restrict__ dHi_dx, const double *__restrict__ dHi_dy, const double *__restrict__ dSL_dx,
+                          const double *__restrict__ dSL_dy, const double *__restrict__ dHb_dx, const double *__restrict__ dHb_dy,
+                          const double *__restrict__ Dx_, const double *__restrict__ Dy_, double factor_Tsai_noA,
+                          double *Qabs, double *Qp, double *Ux, double *Uy, const int *__restrict__ ac2m, double2 *UV)
+{
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nAc) return;
+  Qabs[a] = 0.0; Qp[a] = 0.0;
+  if (!(mbits_Ac[a] & MB_GL)) return;
+  int4 v = Aci[a];
+  const double rr = UFM_SEAWATER_DENSITY / UFM_ICE_DENSITY;
+  double TAFi = Hi[v.x] - ((SL[v.x] - Hb[v.x]) * rr);
+  double TAFj = Hi[v.y] - ((SL[v.y] - Hb[v.y]) * rr);
+  double lambda_GL = TAFi / (TAFi - TAFj);
+  double Hi_GL = (Hi[v.x] * (1.0 - lambda_GL)) + (Hi[v.y] * lambda_GL);
+  double phi_fric_GL = (mbits[v.x] & MB_SHEET) ? phi_m[aa2m[v.x]] : phi_m[aa2m[v.y]];
+  // factor_Tsai = 8 Q0 A (rho g)^n (1-rho_i/rho_w)^(n-1) / 4^n ; the A-independent part is evaluated on the host
+  double factor_Tsai = A_flow * factor_Tsai_noA;
+  double q = factor_Tsai * pow(Hi_GL, UFM_N_FLOW + 2.0) / tan(phi_fric_GL * (UFM_PI / 180.0));
+  Qabs[a] = q;
+  double Fx = -(dHi_dx[a] - ((dSL_dx[a] - dHb_dx[a]) * rr));
+  double Fy = -(dHi_dy[a] - ((dSL_dy[a] - dHb_dy[a]) * rr));
+  double F = hypot(Fx, Fy);
+  Fx = Fx / F; Fy = Fy / F;
+  const double ux = q * Fx / Hi_GL, uy = q * Fy / Hi_GL;
+  Ux[a] = ux; Uy[a] = uy;
+  UV[ac2m[a]] = make_double2(ux, uy);  // the gather of :494-495 happens after calculate_GL_flux in the reference
+  double Dx = Dx_[a], Dy = Dy_[a], D = hypot(Dx, Dy);
+  Dx = Dx / D; Dy = Dy / D;
+  Qp[a] = q * (Dx * Fx + Dy * Fy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// basal_yield_stress (:780-844) + gather of the Aa and Ac fields into AaAc order (:478-496).
+// One thread per AaAc row.
+// ---------------------------------------------------------------------------------------------
+struct PrepArgs {
+  int Mp;
+  const int *src;
+  const double *Hi, *Hb, *SL, *sx, *sy, *U, *V;              // Aa
+  const double *Hi_Ac, *Hb_Ac, *SL_Ac, *sx_Ac, *sy_Ac, *Ux_Ac, *Uy_Ac;  // Ac
+  const unsigned *mbits_Ac;
+  int gl_fix;
+  double2 *UV, *rhsnum;
+  double *tau_c, *phi, *Hm;
+  unsigned char *mflag;
+};
+__global__ void k_ssa_prepare(PrepArgs a)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Mp) return;
+  int s = a.src[p];
+  if (s == INT_MIN) return;
+  double Hi, Hb, SL, sx, sy, U, V;
+  unsigned char fl = 0;
+  if (s >= 0) { Hi = a.Hi[s]; Hb = a.Hb[s]; SL = a.SL[s]; sx = a.sx[s]; sy = a.sy[s]; U = a.U[s]; V = a.V[s]; }
+  else {
+    s = ~s;
+    Hi = a.Hi_Ac[s]; Hb = a.Hb_Ac[s]; SL = a.SL_Ac[s]; sx = a.sx_Ac[s]; sy = a.sy_Ac[s]; U = a.Ux_Ac[s]; V = a.Uy_Ac[s];
+    if (a.gl_fix && (a.mbits_Ac[s] & MB_GL)) fl |= 2;
+  }
+  const double pf1 = -1000.0, pf2 = 0.0, p_min = 5.0, p_max = 20.0;
+  double lambda_p = fmax(0.0, fmin(1.0, (1.0 - (Hb - SL) / 1000.0)));
+  double Hm = fmax(0.1, Hi);
+  double pore_water_pressure = 0.96 * UFM_ICE_DENSITY * UFM_GRAV * Hm * lambda_p;
+  double phi = fmax(p_min, fmin(p_max, (p_min + (p_max - p_min) * (1.0 + (Hb - pf2) / (pf2 - pf1)))));
+  double tau_c = tan((UFM_PI / 180.0) * phi) * (UFM_ICE_DENSITY * UFM_GRAV * Hm - pore_water_pressure);
+  if (!d_is_floating(Hi, Hb, SL)) fl |= 1;
+  a.UV[p] = make_double2(U, V);
+  a.rhsnum[p] = make_double2(UFM_ICE_DENSITY * UFM_GRAV * sx, UFM_ICE_DENSITY * UFM_GRAV * sy);
+  a.tau_c[p] = tau_c; a.phi[p] = phi; a.Hm[p] = Hm; a.mflag[p] = fl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSA_effective_viscosity (:695-726) incl. get_mesh_derivatives_AaAc (mesh_ArakawaC_module.f90:583-618),
+// N = eta*max(0.1,H), and the per-block partial sums of (N-Nprev)^2 and N^2 (:512-513).
+// One warp per slice, one thread per row, grid-stride over slices.
+// ---------------------------------------------------------------------------------------------
+struct ViscArgs {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg;
+  const int *idx;
+  const double *nx, *ny, *nx0, *ny0, *Hm;
+  const double2 *UV;
+  double visc_A;  // (m_enh_ssa * 0.5 * A_flow)**(-1/n_flow), host libm
+  double *eta, *N;
+  double2 *dU, *dV;
+  double *partials;
+};
+__global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  double s_dn = 0.0, s_n = 0.0;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int w = (int)((a.off[s + 1] - o) >> 5);
+    const int p = s * 32 + lane;
+    const int n = a.deg[p];
+    if (n == UFM_DEG_PAD) continue;
+    const double2 u = a.UV[p];
+    double ux = a.nx0[p] * u.x, uy = a.ny0[p] * u.x, vx = a.nx0[p] * u.y, vy = a.ny0[p] * u.y;
+    for (int c = 0; c < w; c++) {
+      if (c < n) {
+        const long long e = o + (long long)c * 32 + lane;
+        const double2 nb = a.UV[ld_stream(a.idx + e)];
+        const double cx = ld_stream(a.nx + e), cy = ld_stream(a.ny + e);
+        ux = ux + cx * nb.x; uy = uy + cy * nb.x;
+        vx = vx + cx * nb.y; vy = vy + cy * nb.y;
+      }
+    }
+    const double epsilon_sq_0 = 1E-12;
+    double eta = a.visc_A * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
+    double Nn = eta * a.Hm[p];
+    double dn = Nn - a.N[p];
+    s_dn = s_dn + dn * dn;
+    s_n = s_n + Nn * Nn;
+    a.eta[p] = eta; a.N[p] = Nn;
+    a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy);
+  }
+  // deterministic block reduction (fixed tree), one partial pair per block
+  __shared__ double sh[2][8];
+  for (int o = 16; o > 0; o >>= 1) { s_dn += __shfl_xor_sync(0xffffffffu, s_dn, o); s_n += __shfl_xor_sync(0xffffffffu, s_n, o); }
+  if (lane == 0) { sh[0][threadIdx.x >> 5] = s_dn; sh[1][threadIdx.x >> 5] = s_n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { t0 += sh[0][k]; t1 += sh[1][k]; }
+    a.partials[2 * blockIdx.x] = t0; a.partials[2 * blockIdx.x + 1] = t1;
+  }
+}
+__global__ void k_sum_partials(int n, const double *partials, double *out2)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < n; k++) { t0 += partials[2 * k]; t1 += partials[2 * k + 1]; }
+    out2[0] = t0; out2[1] = t1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSA_sliding_term (:727-779) fused with the RHS / centre coefficients of solve_SSA_linearised (:581-596)
+// ---------------------------------------------------------------------------------------------
+struct SetupArgs {
+  int Mp;
+  const unsigned char *deg, *mflag;
+  const double2 *UV, *rhsnum;
+  const double *tau_c, *eta, *Hm, *cU0, *cV0;
+  double thr;  // u_threshold**q_plastic, host libm
+  double *S;
+  double2 *RHS, *E;
+};
+__global__ void k_ssa_setup(SetupArgs a)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Mp || a.deg[p] == UFM_DEG_PAD) return;
+  const double delta_v = 1E-3, q_plastic = 0.30;
+  const double2 u = a.UV[p];
+  const double eta = a.eta[p];
+  double S = a.tau_c[p] * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
+  const double2 r = a.rhsnum[p];
+  a.RHS[p] = make_double2(r.x / eta, r.y / eta);
+  double eu = a.cU0[p], ev = a.cV0[p];
+  if (a.mflag[p] & 1) {
+    double t = S / (a.Hm[p] * eta);
+    eu = eu - t; ev = ev - t;
+  }
+  a.S[p] = S;
+  a.E[p] = make_double2(eu, ev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The SOR loop of solve_SSA_linearised (:598-692): persistent cooperative kernel.
+// ctrl[0..2]  rotating max-residual slots (bit pattern of a non-negative double; integer order = fp order)
+// ctrl[8]     iterations executed     ctrl[9] bit0 did_reset, bit1 warning (hit max_inner)
+// ctrl[10]    last max residual (bits)
+// ---------------------------------------------------------------------------------------------
+struct SorArgs {
+  const long long *off;
+  const unsigned char *deg, *mflag;
+  const int *idx;
+  const double *cU, *cV, *nxy, *nxy0, *nxysum;
+  const double2 *E, *RHS;
+  double2 *UV;
+  const int *col;   // [10] slice ranges: begin of colour c at col[c], end at col[5+c]   (device memory: indexed dynamically)
+  int n_bc;
+  const int *bc_pos, *bc_ptr, *bc_nbr;
+  const int *corner;  // [8] corner_pos[4], corner_n[4]
+  const int *corner_nbr, *corner_row;
+  int Mp;
+  int max_inner, force_iters;
+  double omega, tol;
+  unsigned long long *ctrl;
+};
+
+__device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
+{
+  double su = 0.0, sv = 0.0;
+  const int b = a.bc_ptr[row], e = a.bc_ptr[row + 1];
+  for (int k = b; k < e; k++) { const double2 q = a.UV[a.bc_nbr[k]]; su = su + q.x; sv = sv + q.y; }
+  const double nv = (double)(e - b);
+  return make_double2(su / nv, sv / nv);
+}
+
+template <bool EXACT, bool GLFIX>
+__global__ void __launch_bounds__(256, 4) k_ssa_sor(SorArgs a)
+{
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  __shared__ double sh[8];
+  int it = 0;
+  bool done = false;
+  unsigned flags = 0;
+  double maxres = 0.0;
+  while (!done && it < a.max_inner) {
+    it++;
+    if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
+    double tmax = 0.0;
+    for (int c = 0; c < 5; c++) {
+      const int s_end = a.col[5 + c];
+      for (int s = a.col[c] + wg; s < s_end; s += nw) {
+        const long long o = a.off[s];
+        const int w = (int)((a.off[s + 1] - o) >> 5);
+        const int p = s * 32 + lane;
+        const int n = a.deg[p];
+        if (n == UFM_DEG_PAD) continue;
+        if (GLFIX) { if (a.mflag[p] & 2) continue; }
+        const double2 u = a.UV[p];
+        double sumU = 0.0, sumV = 0.0, Uxy, Vxy;
+        if (EXACT) { const double h = ld_stream(a.nxy0 + p); Uxy = u.x * h; Vxy = u.y * h; }
+        for (int cc = 0; cc < w; cc++) {
+          if (cc < n) {
+            const long long e = o + (long long)cc * 32 + lane;
+            const double2 nb = a.UV[ld_stream(a.idx + e)];
+            sumU = sumU + nb.x * ld_stream(a.cU + e);
+            sumV = sumV + nb.y * ld_stream(a.cV + e);
+            if (EXACT) { const double t = ld_stream(a.nxy + e); Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+          }
+        }
+        if (!EXACT) { const double t = ld_stream(a.nxysum + p); Uxy = u.x * t; Vxy = u.y * t; }
+        const double2 e2 = ld_stream(a.E + p), r2 = ld_stream(a.RHS + p);
+        const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
+        const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
+        const double resU = (LHSx - r2.x) / e2.x;
+        const double resV = (LHSy - r2.y) / e2.y;
+        tmax = fmax(tmax, fabs(resU));
+        tmax = fmax(tmax, fabs(resV));
+        a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
+      }
+      if (c == 4) {  // publish this CTA's max residual before the barrier that precedes the stop test
+        for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) sh[threadIdx.x >> 5] = tmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double m = 0.0;
+          for (int k = 0; k < (int)(blockDim.x >> 5); k++) m = fmax(m, sh[k]);
+          atomicMax(a.ctrl + (it % 3), (unsigned long long)__double_as_longlong(m));
+        }
+      }
+      grid.sync();
+    }
+    // apply_Neumann_boundary_AaAc on U and V (mesh_ArakawaC_module.f90:660-724): edge rows from their
+    // non-edge neighbours; the four corners from all neighbours, edge neighbours taken at their NEW value
+    // (recomputed here from non-edge rows only, so the whole pass is one hazard-free phase).
+    for (int r = tid; r < a.n_bc + 4; r += nt) {
+      if (r < a.n_bc) a.UV[a.bc_pos[r]] = bc_mean(a, r);
+      else {
+        const int k = r - a.n_bc, n = a.corner[4 + k];
+        double su = 0.0, sv = 0.0;
+        for (int q = 0; q < n; q++) {
+          const int row = a.corner_row[k * 16 + q];
+          const double2 v = row >= 0 ? bc_mean(a, row) : a.UV[a.corner_nbr[k * 16 + q]];
+          su = su + v.x; sv = sv + v.y;
+        }
+        a.UV[a.corner[k]] = make_double2(su / (double)n, sv / (double)n);
+      }
+    }
+    grid.sync();
+    maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (it % 3))));
+    if (!a.force_iters) {
+      if (maxres < a.tol) done = true;
+      else if (maxres > 1E6) {
+        for (int p = tid; p < a.Mp; p += nt) a.UV[p] = make_double2(0.0, 0.0);
+        flags |= 1; done = true;
+      } else if (it == a.max_inner) flags |= 2;
+    }
+  }
+  if (tid == 0) { a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter AaAc -> Aa / Ac and rotate_xy_to_po (mesh_ArakawaC_module.f90:815-844)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ssa_finish(int nV, int nAc, const int *aa2m, const int *ac2m, const double2 *UV, const double *Dx_, const double *Dy_,
+                             double *U, double *V, double *Ux, double *Uy, double *Up, double *Uo)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nV) { const double2 q = UV[aa2m[i]]; U[i] = q.x; V[i] = q.y; }
+  if (i < nAc) {
+    const double2 q = UV[ac2m[i]];
+    const double Dx = Dx_[i], Dy = Dy_[i], D = sqrt(Dx * Dx + Dy * Dy);
+    Ux[i] = q.x; Uy[i] = q.y;
+    Up[i] = q.x * Dx / D + q.y * Dy / D;
+    Uo[i] = q.y * Dx / D - q.x * Dy / D;
+  }
+}
+
+__global__ void k_zero_d(size_t n, double *p) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.0; }
+
+__global__ void k_sum_mask_sheet(int nV, const unsigned *mbits, unsigned long long *out)
+{
+  unsigned long long c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) c += (mbits[i] & MB_SHEET) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+static inline int grid_for(int n, int b) { return (n + b - 1) / b; }
+
+int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out)
+{
+  DevState &s = h->st;
+  UFM_CUDA(cudaMemsetAsync(s.ctrl + 16, 0, sizeof(unsigned long long), h->stream));
+  k_sum_mask_sheet<<<h->num_sms * 2, 256, 0, h->stream>>>(h->mesh.nV, s.mbits, s.ctrl + 16);
+  h->cnt.kernel_launches++;
+  unsigned long long v = 0;
+  UFM_CUDA(cudaMemcpyAsync(&v, s.ctrl + 16, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  *out = (long long)v;
+  return 0;
+}
+
+int ufm_k_ssa_zero(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  UFM_CUDA(cudaMemsetAsync(s.UV, 0, sizeof(double2) * (size_t)m.Mp, h->stream));
+  UFM_CUDA(cudaMemsetAsync(s.U_SSA, 0, sizeof(double) * (size_t)m.nVp, h->stream));
+  UFM_CUDA(cudaMemsetAsync(s.V_SSA, 0, sizeof(double) * (size_t)m.nVp, h->stream));
+  for (int k = 0; k < 4; k++) UFM_CUDA(cudaMemsetAsync(s.U_SSA_Ac[k], 0, sizeof(double) * (size_t)m.nAcp, h->stream));
+  return 0;
+}
+
+int ufm_k_ssa_prepare(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  PrepArgs a;
+  a.Mp = m.Mp; a.src = m.m_src;
+  a.Hi = s.Hi; a.Hb = s.Hb; a.SL = s.SL; a.sx = s.dHs_dx_shelf; a.sy = s.dHs_dy_shelf; a.U = s.U_SSA; a.V = s.V_SSA;
+  a.Hi_Ac = s.Hi_Ac; a.Hb_Ac = s.Hb_Ac; a.SL_Ac = s.SL_Ac; a.sx_Ac = s.dHs_dx_shelf_Ac; a.sy_Ac = s.dHs_dy_shelf_Ac;
+  a.Ux_Ac = s.U_SSA_Ac[0]; a.Uy_Ac = s.U_SSA_Ac[1]; a.mbits_Ac = s.mbits_Ac; a.gl_fix = h->P.use_analytical_GL_flux;
+  a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.phi = s.phi; a.Hm = s.Hm; a.mflag = s.mflag;
+  k_ssa_prepare<<<grid_for(m.Mp, 256), 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches++;
+  if (h->P.use_analytical_GL_flux) {
+    // factor_Tsai = 8 Q0 A (rho g)^n (1-rho_i/rho_w)^(n-1) / 4^n, evaluated left to right as at :906-909 (host libm)
+    const double Q0 = 0.61;
+    double f = 8.0 * Q0 * s.A_flow_const * pow(UFM_ICE_DENSITY * UFM_GRAV, UFM_N_FLOW) *
+               pow(1.0 - (UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY), UFM_N_FLOW - 1.0) / pow(4.0, UFM_N_FLOW);
+    k_gl_flux<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.ac_Aci, s.mbits_Ac, s.mbits, s.Hi, s.Hb, s.SL, s.phi, m.aa2m, 1.0,
+                                                           s.dHi_Ac[0], s.dHi_Ac[1], s.dSL_Ac[0], s.dSL_Ac[1], s.dHb_Ac[0], s.dHb_Ac[1],
+                                                           m.ac_Dx, m.ac_Dy, f, s.Qabs_GL_Ac, s.Qp_GL_Ac, s.U_SSA_Ac[0], s.U_SSA_Ac[1],
+                                                           m.ac2m, s.UV);
+    h->cnt.kernel_launches++;
+  }
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_prepare");
+}
+
+int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  ViscArgs a;
+  a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
+  a.Hm = s.Hm; a.UV = s.UV;
+  a.visc_A = pow(h->P.m_enh_ssa * 0.5 * s.A_flow_const, -1.0 / UFM_N_FLOW);
+  a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
+  int grid = h->num_sms * 8;
+  if (grid > 4096) grid = 4096;
+  k_ssa_viscosity<<<grid, 256, 0, h->stream>>>(a);
+  k_sum_partials<<<1, 32, 0, h->stream>>>(grid, s.partials, s.scal);
+  h->cnt.kernel_launches += 2;
+  UFM_CUDA(cudaMemcpyAsync(s.scal_h, s.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  sums2[0] = s.scal_h[0]; sums2[1] = s.scal_h[1];
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
+}
+
+int ufm_k_ssa_sliding_setup(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  SetupArgs a;
+  a.Mp = m.Mp; a.deg = m.m.deg; a.mflag = s.mflag; a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.eta = s.eta; a.Hm = s.Hm;
+  a.cU0 = m.m_cU0; a.cV0 = m.m_cV0; a.thr = pow(100.0, 0.30); a.S = s.S; a.RHS = s.RHS; a.E = s.E;
+  k_ssa_setup<<<grid_for(m.Mp, 256), 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_setup");
+}
+
+typedef void (*sor_kernel_t)(SorArgs);
+static sor_kernel_t pick_sor(const ufm_handle *h)
+{
+  const bool ex = h->P.exact_xy != 0, gl = h->P.use_analytical_GL_flux != 0;
+  if (ex) return gl ? k_ssa_sor<true, true> : k_ssa_sor<true, false>;
+  return gl ? k_ssa_sor<false, true> : k_ssa_sor<false, false>;
+}
+
+int ufm_sor_configure(ufm_handle *h)
+{
+  int per_sm = 0;
+  UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, 0));
+  if (per_sm < 1) return ufm_set_error(-3, "SOR kernel cannot be made resident");
+  h->sor_grid = per_sm * h->num_sms;
+  return 0;
+}
+
+int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *st)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  int rc = ufm_sor_configure(h);
+  if (rc) return rc;
+  SorArgs a;
+  a.off = m.m.off; a.deg = m.m.deg; a.mflag = s.mflag; a.idx = m.m_idx; a.cU = m.m_cU; a.cV = m.m_cV; a.nxy = m.m_nxy; a.nxy0 = m.m_nxy0;
+  a.nxysum = m.m_nxysum; a.E = s.E; a.RHS = s.RHS; a.UV = s.UV;
+  a.col = m.col_dev; a.corner = m.corner_dev;
+  a.n_bc = m.n_bc; a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
+  a.corner_nbr = m.corner_nbr; a.corner_row = m.corner_row;
+  a.Mp = m.Mp; a.max_inner = max_inner; a.force_iters = force_iters; a.omega = h->P.SSA_SOR_omega; a.tol = h->P.SSA_max_residual_UV;
+  a.ctrl = s.ctrl;
+  UFM_CUDA(cudaMemsetAsync(s.ctrl, 0, 16 * sizeof(unsigned long long), h->stream));
+  void *args[] = {&a};
+  UFM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  UFM_CUDA(cudaLaunchCooperativeKernel((void *)pick_sor(h), dim3(h->sor_grid), dim3(h->sor_block), args, 0, h->stream));
+  UFM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  unsigned long long *res = (unsigned long long *)(s.scal_h + 8);
+  UFM_CUDA(cudaMemcpyAsync(res, s.ctrl + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  UFM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->cnt.kernel_launches++; h->cnt.sor_launches++; h->cnt.sor_ms += ms; h->cnt.sor_iterations += (long long)res[0];
+  if (st) {
+    st->n_inner_last = (int)res[0];
+    st->did_reset = (int)(res[1] & 1);
+    st->rc = (res[1] & 2) ? 1 : 0;
+    double r;
+    memcpy(&r, &res[2], sizeof(r));
+    st->last_max_residual = r;
+  }
+  return 0;
+}
+
+int ufm_k_ssa_finish(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  int n = m.nV > m.nAc ? m.nV : m.nAc;
+  k_ssa_finish<<<grid_for(n, 256), 256, 0, h->stream>>>(m.nV, m.nAc, m.aa2m, m.ac2m, s.UV, m.ac_Dx, m.ac_Dy, s.U_SSA, s.V_SSA,
+                                                        s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3]);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_finish");
+}

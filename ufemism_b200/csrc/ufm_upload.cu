@@ -1,0 +1,379 @@
+// ufm_upload.cu -- ufm_mesh_upload: copy, renumber and compact a reference mesh into the device layout.
+//
+// Host-side work only (runs once per mesh; mesh generation stays on the CPU per north_star and
+// triggers this re-upload, src/UFEMISM_main_model.f90:294).  Coefficients that the reference
+// combines inside the SOR sweep with a fixed expression -- 4*Nxx+Nyy, 4*Nyy+Nxx
+// (src/ice_dynamics_module.f90:642-643) -- are combined here with the same two fp64 operations
+// (this file is compiled without FMA contraction), so the products the sweep forms are bit-identical.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "ufm_internal.cuh"
+
+namespace {
+
+template <class T>
+int dev_upload(const std::vector<T> &v, T **out)
+{
+  *out = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  UFM_CUDA(cudaMalloc((void **)out, bytes));
+  if (!v.empty()) UFM_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+template <class T>
+int dev_zeros(size_t n, T **out)
+{
+  *out = nullptr;
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  UFM_CUDA(cudaMalloc((void **)out, bytes));
+  UFM_CUDA(cudaMemset(*out, 0, bytes));
+  return 0;
+}
+#define UP(vec, ptr) do { int rc_ = dev_upload(vec, &(ptr)); if (rc_) return rc_; } while (0)
+#define ZE(n, ptr) do { int rc_ = dev_zeros((size_t)(n), &(ptr)); if (rc_) return rc_; } while (0)
+
+inline uint32_t part1by1(uint32_t x)
+{
+  x &= 0x0000ffff;
+  x = (x ^ (x << 8)) & 0x00ff00ff;
+  x = (x ^ (x << 4)) & 0x0f0f0f0f;
+  x = (x ^ (x << 2)) & 0x33333333;
+  x = (x ^ (x << 1)) & 0x55555555;
+  return x;
+}
+inline uint32_t morton2(double x, double y, double x0, double y0, double sx, double sy)
+{
+  double fx = (x - x0) * sx, fy = (y - y0) * sy;
+  uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, fx)), iy = (uint32_t)std::min(65535.0, std::max(0.0, fy));
+  return part1by1(ix) | (part1by1(iy) << 1);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// slice offsets for rows with the given degrees (UFM_DEG_PAD rows count as degree 0)
+void build_slices(const std::vector<unsigned char> &deg, std::vector<long long> &off)
+{
+  int n_slices = (int)deg.size() / UFM_SLICE;
+  off.assign(n_slices + 1, 0);
+  for (int s = 0; s < n_slices; s++) {
+    int w = 0;
+    for (int l = 0; l < UFM_SLICE; l++) {
+      unsigned char d = deg[(size_t)s * UFM_SLICE + l];
+      if (d != UFM_DEG_PAD) w = std::max(w, (int)d);
+    }
+    off[s + 1] = off[s] + (long long)w * UFM_SLICE;
+  }
+}
+
+void free_ptr(void *p) { if (p) cudaFree(p); }
+
+}  // namespace
+
+#define F2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
+
+int ufm_mesh_free_impl(ufm_handle *h)
+{
+  DevMesh &m = h->mesh;
+  DevState &s = h->st;
+  void *mp[] = {m.aa_ref2dev, m.aa_dev2ref, m.ac_ref2dev, m.ac_dev2ref, m.m_ref2dev, m.m_dev2ref, m.aa.off, m.aa.deg, m.aa_C, m.aa_iAci,
+                m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0, m.aa_A, m.aa_sqrtApi, m.aa_edge, m.ac_Aci, m.ac_Np, m.ac_Cw, m.ac_Dx, m.ac_Dy,
+                m.m.off, m.m.deg, m.m_idx, m.m_cU, m.m_cV, m.m_nxy, m.m_nx, m.m_ny, m.m_nxy0, m.m_nxysum, m.m_nx0, m.m_ny0, m.m_cU0,
+                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.col_dev, m.corner_dev, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row};
+  for (void *p : mp) free_ptr(p);
+  for (int k = 0; k < 4; k++) { free_ptr(m.ac_Nx[k]); free_ptr(m.ac_Ny[k]); free_ptr(m.ac_No[k]); }
+  void *sp[] = {s.Hi, s.Hi_alt, s.Hb, s.SL, s.Hs, s.dHb_dt, s.dHi_dt, s.dHs_dt, s.dHi_dx, s.dHi_dy, s.dHs_dx, s.dHs_dy, s.dHs_dx_shelf,
+                s.dHs_dy_shelf, s.U_SIA, s.V_SIA, s.D_SIA, s.U_SSA, s.V_SSA, s.SMB_year, s.BMB, s.thk_factor, s.thk_smb, s.U_3D, s.V_3D,
+                s.mask_noice, s.mbits, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
+                s.Qabs_GL_Ac, s.Qp_GL_Ac, s.mbits_Ac, s.UV, s.RHS, s.E, s.rhsnum, s.dU, s.dV, s.eta, s.N, s.S, s.tau_c, s.phi, s.Hm,
+                s.mflag, s.partials, s.ctrl, s.scal};
+  for (void *p : sp) free_ptr(p);
+  for (int k = 0; k < 4; k++) { free_ptr(s.dHi_Ac[k]); free_ptr(s.dHb_Ac[k]); free_ptr(s.dHs_Ac[k]); free_ptr(s.dSL_Ac[k]); free_ptr(s.U_SIA_Ac[k]); free_ptr(s.U_SSA_Ac[k]); }
+  if (s.scal_h) cudaFreeHost(s.scal_h);
+  h->mesh = DevMesh();
+  h->st = DevState();
+  h->has_mesh = false;
+  return 0;
+}
+
+int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
+{
+  if (!d || !d->V || !d->nC || !d->C || !d->Aci || !d->iAci || !d->nCAaAc || !d->CAaAc || !d->colour_vi || !d->colour_nV)
+    return ufm_set_error(-2, "ufm_mesh_upload: NULL pointer in mesh descriptor");
+  const int N = d->nV, E = d->nAc, M = N + E, W = d->nC_mem;
+  const int ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E, ldM = d->ldAaAc ? d->ldAaAc : M;
+  if (N < 5 || E < 4 || W < 3 || W > 64) return ufm_set_error(-2, "ufm_mesh_upload: implausible sizes nV=%d nAc=%d nC_mem=%d", N, E, W);
+  if (h->has_mesh) ufm_mesh_free_impl(h);
+  DevMesh &m = h->mesh;
+  m.nV = N; m.nAc = E; m.M = M;
+
+  // ---- coordinates of all AaAc vertices, bounding box ----
+  std::vector<double> X(M), Y(M);
+  double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+  for (int v = 1; v <= N; v++) {
+    X[v - 1] = F2(d->V, v, 1, ldV); Y[v - 1] = F2(d->V, v, 2, ldV);
+    x0 = std::min(x0, X[v - 1]); x1 = std::max(x1, X[v - 1]); y0 = std::min(y0, Y[v - 1]); y1 = std::max(y1, Y[v - 1]);
+  }
+  for (int a = 1; a <= E; a++) {
+    int vi = F2(d->Aci, a, 1, ldAc), vj = F2(d->Aci, a, 2, ldAc);
+    if (vi < 1 || vi > N || vj < 1 || vj > N) return ufm_set_error(-2, "ufm_mesh_upload: Aci out of range at aci=%d", a);
+    X[N + a - 1] = 0.5 * (X[vi - 1] + X[vj - 1]); Y[N + a - 1] = 0.5 * (Y[vi - 1] + Y[vj - 1]);
+  }
+  const double sx = 65535.0 / std::max(x1 - x0, 1e-300), sy = 65535.0 / std::max(y1 - y0, 1e-300);
+  std::vector<uint32_t> mort(M);
+  for (int i = 0; i < M; i++) mort[i] = morton2(X[i], Y[i], x0, y0, sx, sy);
+
+  // ---- Aa and Ac orders: Morton ----
+  std::vector<int> aa_order(N), ac_order(E);
+  std::iota(aa_order.begin(), aa_order.end(), 0);
+  std::iota(ac_order.begin(), ac_order.end(), 0);
+  std::stable_sort(aa_order.begin(), aa_order.end(), [&](int a, int b) { return mort[a] < mort[b]; });
+  std::stable_sort(ac_order.begin(), ac_order.end(), [&](int a, int b) { return mort[N + a] < mort[N + b]; });
+  m.nVp = round_up(N, UFM_SLICE); m.nAcp = round_up(E, UFM_SLICE);
+  std::vector<int> aa_r2d(N), aa_d2r(m.nVp, -1), ac_r2d(E), ac_d2r(m.nAcp, -1);
+  for (int p = 0; p < N; p++) { aa_r2d[aa_order[p]] = p; aa_d2r[p] = aa_order[p]; }
+  for (int p = 0; p < E; p++) { ac_r2d[ac_order[p]] = p; ac_d2r[p] = ac_order[p]; }
+
+  // ---- AaAc order: colour-major, (degree, Morton) inside a colour, edge block last ----
+  std::vector<int> colour(M, 0);
+  for (int c = 1; c <= 5; c++) {
+    int nc = d->colour_nV[c - 1];
+    for (int k = 1; k <= nc; k++) {
+      int ai = F2(d->colour_vi, k, c, ldM);
+      if (ai < 1 || ai > M) return ufm_set_error(-2, "ufm_mesh_upload: colour_vi out of range");
+      colour[ai - 1] = c;
+    }
+  }
+  std::vector<unsigned char> is_edge(M), degv(M);
+  for (int ai = 0; ai < M; ai++) {
+    if (colour[ai] == 0) return ufm_set_error(-2, "ufm_mesh_upload: AaAc vertex %d has no colour", ai + 1);
+    is_edge[ai] = ai < N ? (d->edge_index[ai] > 0) : (d->edge_index_Ac[ai - N] > 0);
+    int n = d->nCAaAc[ai];
+    if (n < 1 || n > W) return ufm_set_error(-2, "ufm_mesh_upload: nCAaAc(%d) = %d out of range", ai + 1, n);
+    degv[ai] = (unsigned char)n;
+  }
+  // the sweep relies on same-coloured vertices being non-adjacent (check_solution, mesh_five_colour_module.f90:318-343)
+  for (int ai = 0; ai < M; ai++)
+    for (int c = 1; c <= degv[ai]; c++) {
+      int ac = F2(d->CAaAc, ai + 1, c, ldM);
+      if (ac < 1 || ac > M) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
+      if (colour[ac - 1] == colour[ai]) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", ai + 1, ac);
+    }
+  std::vector<int> m_order(M);
+  std::iota(m_order.begin(), m_order.end(), 0);
+  auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
+  std::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
+    int ba = blk(a), bb = blk(b);
+    if (ba != bb) return ba < bb;
+    if (degv[a] != degv[b]) return degv[a] < degv[b];
+    return mort[a] < mort[b];
+  });
+  std::vector<int> m_r2d(M), m_d2r;
+  m_d2r.reserve((size_t)M + 6 * UFM_SLICE);
+  {
+    int k = 0;
+    for (int b = 1; b <= 6; b++) {  // blocks 1..5 = colours (swept rows), 6 = domain-edge rows
+      m.col_begin[b - 1] = (int)(m_d2r.size() / UFM_SLICE);
+      while (k < M && blk(m_order[k]) == b) {
+        m_r2d[m_order[k]] = (int)m_d2r.size();
+        m_d2r.push_back(m_order[k]);
+        k++;
+      }
+      while (m_d2r.size() % UFM_SLICE) m_d2r.push_back(-1);
+      m.col_end[b - 1] = (int)(m_d2r.size() / UFM_SLICE);
+    }
+  }
+  m.Mp = (int)m_d2r.size();
+
+  // ---- AaAc sliced ELL ----
+  {
+    std::vector<unsigned char> deg(m.Mp, UFM_DEG_PAD);
+    for (int p = 0; p < m.Mp; p++) if (m_d2r[p] >= 0) deg[p] = degv[m_d2r[p]];
+    std::vector<long long> off;
+    build_slices(deg, off);
+    m.m.n_rows = m.Mp; m.m.n_slices = m.Mp / UFM_SLICE; m.m.n_entries = off.back();
+    size_t ne = (size_t)off.back();
+    std::vector<int> idx(ne);
+    std::vector<double> cU(ne, 0.0), cV(ne, 0.0), nxy(ne, 0.0), nx(ne, 0.0), ny(ne, 0.0);
+    std::vector<double> nxy0(m.Mp, 0.0), nxysum(m.Mp, 0.0), nx0(m.Mp, 0.0), ny0(m.Mp, 0.0), cU0(m.Mp, 0.0), cV0(m.Mp, 0.0);
+    std::vector<int> src(m.Mp, INT_MIN);
+    double bytes = 0.0;
+    for (int s = 0; s < m.m.n_slices; s++) {
+      int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
+      for (int l = 0; l < UFM_SLICE; l++) {
+        int p = s * UFM_SLICE + l, ai = m_d2r[p];
+        for (int c = 0; c < w; c++) idx[(size_t)off[s] + (size_t)c * UFM_SLICE + l] = p;  // padding entries point home
+        if (ai < 0) continue;
+        int n = degv[ai];
+        src[p] = ai < N ? aa_r2d[ai] : ~ac_r2d[ai - N];
+        for (int c = 1; c <= n; c++) {
+          size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
+          idx[e] = m_r2d[F2(d->CAaAc, ai + 1, c, ldM) - 1];
+          double Nxx = F2(d->Nxx_AaAc, ai + 1, c, ldM), Nyy = F2(d->Nyy_AaAc, ai + 1, c, ldM);
+          cU[e] = 4.0 * Nxx + Nyy;
+          cV[e] = 4.0 * Nyy + Nxx;
+          nxy[e] = F2(d->Nxy_AaAc, ai + 1, c, ldM);
+          nx[e] = F2(d->Nx_AaAc, ai + 1, c, ldM);
+          ny[e] = F2(d->Ny_AaAc, ai + 1, c, ldM);
+        }
+        double Nxx0 = F2(d->Nxx_AaAc, ai + 1, n + 1, ldM), Nyy0 = F2(d->Nyy_AaAc, ai + 1, n + 1, ldM);
+        cU0[p] = 4.0 * Nxx0 + Nyy0;
+        cV0[p] = 4.0 * Nyy0 + Nxx0;
+        nxy0[p] = F2(d->Nxy_AaAc, ai + 1, n + 1, ldM);
+        nx0[p] = F2(d->Nx_AaAc, ai + 1, n + 1, ldM);
+        ny0[p] = F2(d->Ny_AaAc, ai + 1, n + 1, ldM);
+        double ssum = nxy0[p];
+        for (int c = 1; c <= n; c++) ssum = ssum + F2(d->Nxy_AaAc, ai + 1, c, ldM);
+        nxysum[p] = ssum;
+        if (!is_edge[ai]) bytes += 80.0 + 20.0 * n;
+      }
+    }
+    m.sor_bytes = bytes;
+    UP(off, m.m.off); UP(deg, m.m.deg); UP(idx, m.m_idx); UP(cU, m.m_cU); UP(cV, m.m_cV); UP(nxy, m.m_nxy); UP(nx, m.m_nx); UP(ny, m.m_ny);
+    UP(nxy0, m.m_nxy0); UP(nxysum, m.m_nxysum); UP(nx0, m.m_nx0); UP(ny0, m.m_ny0); UP(cU0, m.m_cU0); UP(cV0, m.m_cV0); UP(src, m.m_src);
+    std::vector<int> aa2m(m.nVp, 0), ac2m(m.nAcp, 0);
+    for (int v = 0; v < N; v++) aa2m[aa_r2d[v]] = m_r2d[v];
+    for (int a = 0; a < E; a++) ac2m[ac_r2d[a]] = m_r2d[N + a];
+    UP(aa2m, m.aa2m); UP(ac2m, m.ac2m);
+  }
+
+  // ---- Neumann boundary lists (apply_Neumann_boundary_AaAc, mesh_ArakawaC_module.f90:660-724) ----
+  {
+    std::vector<int> bc_pos, bc_ptr(1, 0), bc_nbr, row_of(M, -1);
+    for (int ai = 4; ai < M; ai++) {  // ai = MAX(5,..) .. in 1-based terms
+      if (!is_edge[ai]) continue;
+      row_of[ai] = (int)bc_pos.size();
+      bc_pos.push_back(m_r2d[ai]);
+      for (int c = 1; c <= degv[ai]; c++) {
+        int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
+        if (is_edge[ac]) continue;
+        bc_nbr.push_back(m_r2d[ac]);
+      }
+      bc_ptr.push_back((int)bc_nbr.size());
+    }
+    m.n_bc = (int)bc_pos.size();
+    std::vector<int> cn(4 * 16, 0), cr(4 * 16, -1);
+    for (int k = 0; k < 4; k++) {
+      int ai = k;
+      m.corner_pos[k] = m_r2d[ai];
+      m.corner_n[k] = degv[ai];
+      if (degv[ai] > 16) return ufm_set_error(-2, "ufm_mesh_upload: corner vertex with more than 16 connections");
+      for (int c = 1; c <= degv[ai]; c++) {
+        int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
+        cn[k * 16 + c - 1] = m_r2d[ac];
+        cr[k * 16 + c - 1] = (ac >= 4 && is_edge[ac]) ? row_of[ac] : -1;
+        if (ac < 4) return ufm_set_error(-2, "ufm_mesh_upload: corner vertices adjacent on the AaAc mesh");
+      }
+    }
+    std::vector<int> colv(10), cornv(8);
+    for (int c = 0; c < 5; c++) { colv[c] = m.col_begin[c]; colv[5 + c] = m.col_end[c]; }
+    for (int k = 0; k < 4; k++) { cornv[k] = m.corner_pos[k]; cornv[4 + k] = m.corner_n[k]; }
+    UP(colv, m.col_dev); UP(cornv, m.corner_dev);
+    UP(bc_pos, m.bc_pos); UP(bc_ptr, m.bc_ptr); UP(bc_nbr, m.bc_nbr); UP(cn, m.corner_nbr); UP(cr, m.corner_row);
+  }
+
+  // ---- Aa sliced ELL ----
+  {
+    std::vector<unsigned char> deg(m.nVp, UFM_DEG_PAD), edge(m.nVp, 0);
+    for (int p = 0; p < N; p++) {
+      int n = d->nC[aa_d2r[p]];
+      if (n < 2 || n > W) return ufm_set_error(-2, "ufm_mesh_upload: nC(%d) = %d out of range", aa_d2r[p] + 1, n);
+      deg[p] = (unsigned char)n;
+      edge[p] = (unsigned char)d->edge_index[aa_d2r[p]];
+    }
+    std::vector<long long> off;
+    build_slices(deg, off);
+    m.aa.n_rows = m.nVp; m.aa.n_slices = m.nVp / UFM_SLICE; m.aa.n_entries = off.back();
+    size_t ne = (size_t)off.back();
+    std::vector<int> Cn(ne), iA(ne, 0);
+    std::vector<double> nx(ne, 0.0), ny(ne, 0.0), nx0(m.nVp, 0.0), ny0(m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
+    for (int s = 0; s < m.aa.n_slices; s++) {
+      int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
+      for (int l = 0; l < UFM_SLICE; l++) {
+        int p = s * UFM_SLICE + l, vi = aa_d2r[p];
+        for (int c = 0; c < w; c++) Cn[(size_t)off[s] + (size_t)c * UFM_SLICE + l] = p < N ? p : 0;
+        if (vi < 0) continue;
+        int n = deg[p];
+        for (int c = 1; c <= n; c++) {
+          size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
+          int vc = F2(d->C, vi + 1, c, ldV), aci = F2(d->iAci, vi + 1, c, ldV);
+          if (vc < 1 || vc > N || aci < 1 || aci > E) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", vi + 1);
+          Cn[e] = aa_r2d[vc - 1];
+          int first = (F2(d->Aci, aci, 1, ldAc) == vi + 1);
+          iA[e] = ac_r2d[aci - 1] | (first ? (int)0x80000000u : 0);
+          nx[e] = F2(d->Nx, vi + 1, c, ldV);
+          ny[e] = F2(d->Ny, vi + 1, c, ldV);
+        }
+        nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV);
+        ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV);
+        A[p] = d->A[vi];
+        sA[p] = std::sqrt(d->A[vi] / UFM_PI);
+      }
+    }
+    UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
+    UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge);
+  }
+
+  // ---- Ac arrays ----
+  {
+    std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
+    std::vector<double> c4[3][4], np(m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0);
+    for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(m.nAcp, 0.0);
+    for (int p = 0; p < E; p++) {
+      int a = ac_d2r[p] + 1;
+      int v[4];
+      for (int k = 0; k < 4; k++) {
+        v[k] = F2(d->Aci, a, k + 1, ldAc);
+        if (v[k] < 1 || v[k] > N) return ufm_set_error(-2, "ufm_mesh_upload: Aci out of range");
+        c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc);
+      }
+      aci[p] = make_int4(aa_r2d[v[0] - 1], aa_r2d[v[1] - 1], aa_r2d[v[2] - 1], aa_r2d[v[3] - 1]);
+      np[p] = d->Np_Ac[a - 1];
+      int ci = 0;
+      for (int c = 1; c <= d->nC[v[0] - 1]; c++) if (F2(d->C, v[0], c, ldV) == v[1]) { ci = c; break; }
+      if (!ci) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,1:2) is not a connection in C", a);
+      cw[p] = F2(d->Cw, v[0], ci, ldV);
+      dx[p] = F2(d->V, v[1], 1, ldV) - F2(d->V, v[0], 1, ldV);
+      dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
+    }
+    UP(aci, m.ac_Aci); UP(np, m.ac_Np); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
+    for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
+  }
+  UP(aa_r2d, m.aa_ref2dev); UP(aa_d2r, m.aa_dev2ref); UP(ac_r2d, m.ac_ref2dev); UP(ac_d2r, m.ac_dev2ref);
+  UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
+
+  // ---- state, zero-filled ----
+  DevState &s = h->st;
+  const size_t nv = m.nVp, na = m.nAcp, nm = m.Mp, nz = (size_t)h->P.nZ;
+  double **aa_d[] = {&s.Hi, &s.Hi_alt, &s.Hb, &s.SL, &s.Hs, &s.dHb_dt, &s.dHi_dt, &s.dHs_dt, &s.dHi_dx, &s.dHi_dy, &s.dHs_dx, &s.dHs_dy,
+                     &s.dHs_dx_shelf, &s.dHs_dy_shelf, &s.U_SIA, &s.V_SIA, &s.D_SIA, &s.U_SSA, &s.V_SSA, &s.SMB_year, &s.BMB, &s.thk_factor, &s.thk_smb};
+  for (double **p : aa_d) ZE(nv, *p);
+  ZE(nv * nz, s.U_3D); ZE(nv * nz, s.V_3D);
+  ZE(nv, s.mask_noice); ZE(nv, s.mbits);
+  double **ac_d[] = {&s.Hi_Ac, &s.Hb_Ac, &s.SL_Ac, &s.Hs_Ac, &s.dHs_dx_shelf_Ac, &s.dHs_dy_shelf_Ac, &s.D_SIA_Ac, &s.Qabs_GL_Ac, &s.Qp_GL_Ac};
+  for (double **p : ac_d) ZE(na, *p);
+  for (int k = 0; k < 4; k++) { ZE(na, s.dHi_Ac[k]); ZE(na, s.dHb_Ac[k]); ZE(na, s.dHs_Ac[k]); ZE(na, s.dSL_Ac[k]); ZE(na, s.U_SIA_Ac[k]); ZE(na, s.U_SSA_Ac[k]); }
+  ZE(na, s.mbits_Ac);
+  ZE(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
+  ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
+  ZE(2 * 4096, s.partials); ZE(64, s.ctrl); ZE(64, s.scal);
+  UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
+
+  // staging for permuted upload/download of one field
+  size_t need = std::max<size_t>((size_t)M, nv * nz) * sizeof(double);
+  if (h->staging_bytes < need) {
+    if (h->staging) cudaFreeHost(h->staging);
+    if (h->dev_staging) cudaFree(h->dev_staging);
+    UFM_CUDA(cudaMallocHost(&h->staging, need));
+    UFM_CUDA(cudaMalloc(&h->dev_staging, need));
+    h->staging_bytes = h->dev_staging_bytes = need;
+  }
+  h->has_mesh = true;
+  h->cnt.sor_bytes_per_iteration = m.sor_bytes;
+  return ufm_sor_configure(h);
+}
