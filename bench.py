@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 ice-dynamics hot path (contract: see the task statement).
+
+Workload (BASELINE.json configs[2]): SSA ice stream/shelf on a flat synthetic bed, ~1M-vertex mesh (4M AaAc
+vertices), MISMIP_mod physics switches with the analytical grounding-line flux, through the region time loop
+(thickness update -> general data -> SIA -> SSA viscosity/SOR -> CFL).  A "step" is one pass of that loop.
+
+  value  model-years per wall-hour, state resident in HBM                      (ufm_run_model)
+  e2e    the same steps in drop-in mode: host buffers, H2D/D2H every step      (ufm_run_model_host)
+  roofline  the SOR sweep kernel: algorithmic bytes sum_i(80+20 n_i) per iteration / CUDA-event time
+  cpu_baseline  the CPU oracle (restatement of the Fortran, OpenMP threads as MPI ranks) on a bounded sample
+
+`--impl reference` times that CPU restatement alone (the Fortran reference cannot be built in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "model_yr_per_wall_hr"
+UNIT = "model-yr/wall-hr"
+COUNTS_FILE = os.path.join(ROOT, "profiles", "config3_step_counts.json")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_workload(nv, seed=20211103):
+    from ufemism_b200 import mesh as M
+    from ufemism_b200 import scenarios as S
+
+    c = S.CONFIG3
+    t = time.time()
+    m = M.square_mesh_with_nv(c["half_width"], nv, seed=seed, order="random")
+    st = S.state_ssa_icestream(m, scale=1.0, Hb=c["Hb"], H_shelf=c["H_shelf"])
+    log(f"[bench] mesh nV={m.nV} nAc={m.nAc} nVAaAc={m.nVAaAc} built in {time.time() - t:.1f}s")
+    return m, st
+
+
+def workload_name(m):
+    return f"config3_ssa_icestream_flatbed_nV{m.nV}_AaAc{m.nVAaAc}_MISMIP_mod_GLflux"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement: per-routine unit costs at full size (bounded sample), scaled by iteration counts
+# ------------------------------------------------------------------------------------------------
+def cpu_unit_costs(m, st, nthreads, sor_iters=8):
+    from oracle.oracle import Oracle
+
+    o = Oracle(m, benchmark=st["benchmark"], nthreads=nthreads, use_analytical_GL_flux=1)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        o[k][:] = st[k]
+    T = {}
+
+    def tm(name, fn, reps=1):
+        t = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        T[name] = (time.perf_counter() - t) / reps
+
+    o.update_general_ice_model_data(0.0)  # warm the page tables
+    tm("geom", lambda: o.update_general_ice_model_data(0.0))
+    tm("sia", o.solve_SIA)
+    tm("thk", lambda: o.calculate_ice_thickness_change(0.0))
+    o.update_general_ice_model_data(0.0)
+    tm("cfl", o.determine_timesteps)
+    tm("ssa_prepare", lambda: (o.basal_yield_stress(), o.calculate_GL_flux(), o.SSA_gather_AaAc()))
+    tm("visc", o.SSA_effective_viscosity)
+    tm("slid", o.SSA_sliding_term)
+    o.solve_SSA_linearised(max_inner=1, force_iters=True)
+    t = time.perf_counter()
+    o.solve_SSA_linearised(max_inner=sor_iters, force_iters=True)
+    T["sor_iter"] = (time.perf_counter() - t) / sor_iters  # includes the O(M) RHS/centre-coefficient setup once (small)
+    T["sample_seconds"] = sum(v for k, v in T.items() if k != "sor_iter") + T["sor_iter"] * (sor_iters + 1)
+    return T
+
+
+def cpu_step_seconds(T, did_sia, did_ssa, n_outer, n_sor):
+    t = T["thk"] + T["geom"] + T["cfl"]
+    if did_sia:
+        t += T["sia"]
+    if did_ssa:
+        t += T["ssa_prepare"] + n_outer * (T["visc"] + T["slid"]) + n_sor * T["sor_iter"]
+    return t
+
+
+def load_counts(nv, n):
+    """Per-step iteration counts of this workload (identical on CPU and GPU by the parity tests), recorded by the GPU arm."""
+    if os.path.exists(COUNTS_FILE):
+        c = json.load(open(COUNTS_FILE))
+        if abs(c.get("nV", 0) - nv) <= 0.02 * nv and len(c.get("steps", [])) >= n:
+            return c["steps"][:n], f"iteration counts from {os.path.relpath(COUNTS_FILE, ROOT)}"
+    return None, None
+
+
+def counts_from_small_oracle(n_steps, nthreads):
+    """Fallback: iteration counts from the oracle itself on a 1/16-size mesh of the same geometry."""
+    m, st = build_workload(62500)
+    from oracle.oracle import Oracle
+
+    o = Oracle(m, benchmark=st["benchmark"], nthreads=nthreads, use_analytical_GL_flux=1)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        o[k][:] = st[k]
+    r = o.region(0.0)
+    steps = []
+    for _ in range(n_steps):
+        a = (r.n_sia, r.n_ssa, r.n_outer_total, r.n_sor_total)
+        o.run_model(r, 1e12, max_steps=1)
+        steps.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
+    return steps, "iteration counts from the oracle on a 62.5k-vertex mesh of the same geometry (counts file absent)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    m, st = build_workload(args.nv)
+    T = cpu_unit_costs(m, st, nthreads)
+    total = args.warmup + args.steps
+    steps, how = load_counts(m.nV, total)
+    if steps is None:
+        steps, how = counts_from_small_oracle(total, nthreads)
+    timed = steps[args.warmup:]
+    yrs = sum(s["dt"] for s in timed)
+    secs = sum(cpu_step_seconds(T, s["sia"], s["ssa"], s["n_outer"], s["n_sor"]) for s in timed)
+    value = yrs / secs * 3600.0
+    sample = (f"one pass of every hot-path routine + 9 forced SOR iterations at full size ({m.nV} vertices, {T['sample_seconds']:.1f} s of CPU work), "
+              f"scaled per step by its iteration counts; {how}")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": secs / max(len(timed), 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": workload_name(m), "flush": "inputs larger than L2"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                            "unit_costs_s": {k: round(v, 6) for k, v in T.items()}},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "note": "CPU restatement of the Fortran hot path (oracle/); the Fortran reference itself cannot be built here (no gfortran/MPI/NetCDF)"}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ufemism_b200 import scenarios as S
+    from ufemism_b200.capi import Counters, IceModelGPU, Region
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one model region per GPU (the reference runs its regions NAM/EAS/GRL/ANT independently: src/UFEMISM_program.f90:194-229)
+    m, st = build_workload(args.nv)
+    t = time.time()
+    g = IceModelGPU(m, benchmark=st["benchmark"], device=local, use_analytical_GL_flux=S.CONFIG3["use_analytical_GL_flux"], exact_xy=args.exact_xy)
+    log(f"[bench] rank {rank}: mesh upload {time.time() - t:.1f}s")
+    stream = torch.cuda.Stream()  # a non-default stream: the library launches on it, torch events time it
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
+
+    def fresh_state():
+        g.upload_mesh(m)  # re-upload: all state zero
+        g.set_stream(stream.cuda_stream)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+            g.upload(k, st[k])
+        return g.region(0.0)
+
+    def one_by_one(r, n, host=None):
+        rows = []
+        for _ in range(n):
+            a = (r.n_sia, r.n_ssa, r.n_outer_total, r.n_sor_total)
+            if host is None:
+                g.run_model(r, 1e12, max_steps=1)
+            else:
+                g._ck(g.L.ufm_run_model_host(g.h, ctypes.byref(r), ctypes.c_double(1e12), ctypes.c_long(1), ctypes.byref(host)))
+            rows.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
+        return rows
+
+    # ---------------- device-resident run: `value` ----------------
+    r = fresh_state()
+    warm_rows = one_by_one(r, args.warmup)
+    g.reset_counters()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_model0 = r.time
+    e0.record(stream)
+    rows = one_by_one(r, args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    cnt = g.counters()
+    yrs = r.time - t_model0
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * yrs / (ms * 1e-3) * 3600.0
+
+    # ---------------- drop-in mode with host buffers: `e2e` ----------------
+    class HostIce(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_void_p) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "mask_noice", "Hi_out", "Hi_prev", "dHi_dt", "Hs",
+                                                   "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA", "mask")]
+    nV = m.nV
+    hb = {n: np.zeros(nV) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "Hi_prev", "dHi_dt", "Hs", "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA")}
+    hb["mask_noice"] = np.zeros(nV, np.int32); hb["mask"] = np.zeros(nV, np.int32)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        hb[k][:] = st[k]
+    host = HostIce(**{n: hb[n].ctypes.data for n in ("Hb", "SL", "dHb_dt", "SMB_year", "BMB", "mask_noice", "Hi_prev", "dHi_dt", "Hs", "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA", "mask")},
+                   Hi=hb["Hi"].ctypes.data, Hi_out=hb["Hi"].ctypes.data)  # the host's Hi window is read and written in place
+    r2 = fresh_state()
+    one_by_one(r2, args.warmup, host)
+    g.reset_counters()
+    barrier()
+    t2_0 = r2.time
+    e0.record(stream)
+    one_by_one(r2, args.steps, host)
+    e1.record(stream)
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    cnt2 = g.counters()
+    if world > 1:
+        tt = torch.tensor([ms2], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms2 = float(tt.item())
+    e2e_value = world * (r2.time - t2_0) / (ms2 * 1e-3) * 3600.0
+    same = abs(r2.time - r.time) <= 1e-9 * max(1.0, abs(r.time))
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        t_iter = cnt.sor_ms * 1e-3 / max(cnt.sor_iterations, 1)
+        achieved = cnt.sor_bytes_per_iteration / t_iter / 1e9 if cnt.sor_iterations else 0.0
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(m), "parallelism": f"{world} independent region(s), one per GPU (no data-path collective)",
+                          "flush": "inputs larger than L2 (SOR streams ~1 GB of coefficients per iteration)", "exact_xy": int(args.exact_xy)},
+               "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cnt2.h2d_bytes / args.steps, "d2h_bytes_per_step": cnt2.d2h_bytes / args.steps,
+                       "ms_per_step": ms2 / args.steps, "same_trajectory_as_value": bool(same)},
+               "gpu_launches": int(cnt.kernel_launches),
+               "roofline": {"bound": "hbm", "kernel": "k_ssa_sor (five-colour SOR sweep, persistent cooperative)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_iteration": cnt.sor_bytes_per_iteration,
+                            "us_per_iteration": t_iter * 1e6, "iterations": int(cnt.sor_iterations), "launches": int(cnt.sor_launches),
+                            "sor_share_of_step": cnt.sor_ms / ms},
+               "ssa": {"model_years": yrs, "n_ssa_solves": int(sum(x["ssa"] for x in rows)), "n_outer": int(sum(x["n_outer"] for x in rows)),
+                       "n_sor": int(sum(x["n_sor"] for x in rows))}}
+        # record the per-step counts for the CPU arms
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump({"nV": m.nV, "warmup": args.warmup, "steps": warm_rows + rows}, open(os.path.join(ROOT, "gpurun_out", "config3_step_counts.json"), "w"))
+        if world == 1 and not args.no_cpu:
+            nthreads = os.cpu_count() or 1
+            T = cpu_unit_costs(m, st, nthreads)
+            secs = sum(cpu_step_seconds(T, s["sia"], s["ssa"], s["n_outer"], s["n_sor"]) for s in rows)
+            out["cpu_baseline"] = {"value": yrs / secs * 3600.0, "unit": UNIT, "cores": nthreads, "kind": "port",
+                                   "sample": (f"one pass of every hot-path routine + 9 forced SOR iterations at full size ({m.nV} vertices, "
+                                              f"{T['sample_seconds']:.1f} s of CPU work), scaled by this run's own per-step iteration counts"),
+                                   "unit_costs_s": {k: round(v, 6) for k, v in T.items()}}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nv", type=int, default=1000000)
+    ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

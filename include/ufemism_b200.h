@@ -198,6 +198,16 @@ typedef struct ufm_region {
 int ufm_region_init(ufm_region *r, double start_time);
 int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps);
 
+/* The same loop in drop-in mode: the Fortran host owns the fields (its MPI shared-memory windows), so every
+ * step uploads what CPU components may have changed (ELRA: Hb, dHb_dt, SL; SMB/BMB; remapped Hi; mask_noice)
+ * and downloads what they read afterwards (Hi, Hi_prev, dHi_dt, Hs, U/V_SSA, U/V_SIA, D_SIA, mask).
+ * All pointers are host arrays of length nV in reference vertex order; NULL members are skipped. */
+typedef struct ufm_host_ice {
+  const double *Hi, *Hb, *SL, *dHb_dt, *SMB_year, *BMB; const int *mask_noice;                 /* in  */
+  double *Hi_out, *Hi_prev, *dHi_dt, *Hs, *U_SSA, *V_SSA, *U_SIA, *V_SIA, *D_SIA; int *mask;    /* out */
+} ufm_host_ice;
+int ufm_run_model_host(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host);
+
 /* ---- instrumentation ---- */
 int ufm_counters_get(ufm_handle *h, ufm_counters *out);
 int ufm_counters_reset(ufm_handle *h);

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Isolated SOR-kernel probe on the bench workload: forced iteration counts, CUDA-event timing from the
+library's own counters.  Used for kernel tuning and as the short command wrapped by ncu
+(B200_PROFILING.md): a number printed under ncu is never a bench value."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nv", type=int, default=1000000)
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
+    ap.add_argument("--order", default="random")
+    ap.add_argument("--others", action="store_true", help="also time the per-step kernels")
+    a = ap.parse_args()
+    from ufemism_b200 import mesh as M
+    from ufemism_b200 import scenarios as S
+    from ufemism_b200.capi import IceModelGPU
+
+    c = S.CONFIG3
+    m = M.square_mesh_with_nv(c["half_width"], a.nv, order=a.order)
+    st = S.state_ssa_icestream(m, Hb=c["Hb"], H_shelf=c["H_shelf"])
+    g = IceModelGPU(m, benchmark=st["benchmark"], use_analytical_GL_flux=1, exact_xy=a.exact_xy)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        g.upload(k, st[k])
+    g.update_general_ice_model_data(0.0)
+    g.ssa_prepare(); g.ssa_viscosity(); g.ssa_sliding_and_setup()
+    g.ssa_sor(max_inner=5, force_iters=True)  # warm-up
+    res = []
+    for _ in range(a.reps):
+        g.reset_counters()
+        g.ssa_sor(max_inner=a.iters, force_iters=True)
+        cn = g.counters()
+        res.append(cn.sor_ms * 1e3 / cn.sor_iterations)
+    cn = g.counters()
+    out = {"nV": m.nV, "M": m.nVAaAc, "exact_xy": a.exact_xy, "iters": a.iters, "us_per_iteration": res,
+           "algorithmic_GB": cn.sor_bytes_per_iteration / 1e9, "achieved_GBps_best": cn.sor_bytes_per_iteration / (min(res) * 1e-6) / 1e9}
+    if a.others:
+        import torch
+        def tm(fn, n=5):
+            fn(); g.synchronize()
+            t = time.perf_counter()
+            for _ in range(n):
+                fn()
+            g.synchronize()
+            return (time.perf_counter() - t) / n * 1e3
+        out["ms"] = {"geom": tm(lambda: g.update_general_ice_model_data(0.0)), "sia": tm(g.solve_SIA), "thk": tm(lambda: g.calculate_ice_thickness_change(0.0)),
+                     "cfl": tm(g.determine_timesteps), "prepare": tm(g.ssa_prepare), "visc": tm(g.ssa_viscosity), "setup": tm(g.ssa_sliding_and_setup),
+                     "sor_1iter_launch": tm(lambda: g.ssa_sor(max_inner=1, force_iters=True)), "finish": tm(g.ssa_finish)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

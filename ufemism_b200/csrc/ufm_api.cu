@@ -338,7 +338,16 @@ int ufm_region_init(ufm_region *r, double start_time)
   return 0;
 }
 
-int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps)
+static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host);
+int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps) { return run_model_impl(h, r, t_end, max_steps, nullptr); }
+int ufm_run_model_host(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host)
+{
+  if (!host) return ufm_set_error(-2, "NULL host state");
+  return run_model_impl(h, r, t_end, max_steps, host);
+}
+}  // extern "C"
+
+static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host)
 {
   NEED_MESH(h);
   if (!r) return ufm_set_error(-2, "NULL region");
@@ -349,6 +358,11 @@ int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps)
   int rc;
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
     r->t0[UFM_T_ELRA] = r->time;  // run_ELRA_model, benchmark branch (bedrock_ELRA_module.f90:35-47)
+    if (host) {
+      const struct { int f; const void *p; } in[] = {{UFM_F_HI, host->Hi}, {UFM_F_HB, host->Hb}, {UFM_F_SL, host->SL}, {UFM_F_DHB_DT, host->dHb_dt},
+                                                     {UFM_F_SMB_YEAR, host->SMB_year}, {UFM_F_BMB, host->BMB}, {UFM_F_MASK_NOICE, host->mask_noice}};
+      for (auto &q : in) if (q.p && (rc = ufm_state_upload(h, q.f, q.p))) return rc;
+    }
     if ((rc = ufm_thickness_update(h, r->dt))) return rc;
     if ((rc = ufm_update_general(h, r->time))) return rc;
     if (r->do_[UFM_T_SIA]) { if ((rc = ufm_solve_SIA(h))) return rc; r->t0[UFM_T_SIA] = r->time; r->n_sia++; }
@@ -382,10 +396,17 @@ int ufm_run_model(ufm_handle *h, ufm_region *r, double t_end, long max_steps)
     }
     r->time = r->time + r->dt;
     steps++; r->n_steps++;
+    if (host) {
+      const struct { int f; void *p; } out[] = {{UFM_F_HI, host->Hi_out}, {UFM_F_HI_PREV, host->Hi_prev}, {UFM_F_DHI_DT, host->dHi_dt}, {UFM_F_HS, host->Hs},
+                                                {UFM_F_U_SSA, host->U_SSA}, {UFM_F_V_SSA, host->V_SSA}, {UFM_F_U_SIA, host->U_SIA}, {UFM_F_V_SIA, host->V_SIA},
+                                                {UFM_F_D_SIA, host->D_SIA}, {UFM_F_MASK, host->mask}};
+      for (auto &q : out) if (q.p && (rc = ufm_state_download(h, q.f, q.p))) return rc;
+    }
   }
   return 0;
 }
 
+extern "C" {
 int ufm_counters_get(ufm_handle *h, ufm_counters *out)
 {
   if (!h || !out) return ufm_set_error(-2, "NULL argument");

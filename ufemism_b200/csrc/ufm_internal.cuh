@@ -126,7 +126,7 @@ struct ufm_handle {
   DevMesh mesh;
   DevState st;
   ufm_counters cnt;
-  int sor_grid = 0, sor_block = 256;
+  int sor_grid = 0, sor_block = 128;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;

@@ -215,6 +215,12 @@ __global__ void k_ssa_setup(SetupArgs a)
 // ctrl[8]     iterations executed     ctrl[9] bit0 did_reset, bit1 warning (hit max_inner)
 // ctrl[10]    last max residual (bits)
 // ---------------------------------------------------------------------------------------------
+#ifndef SOR_BLOCK
+#define SOR_BLOCK 128
+#endif
+#ifndef SOR_MIN_BLOCKS
+#define SOR_MIN_BLOCKS 4
+#endif
 struct SorArgs {
   const long long *off;
   const unsigned char *deg, *mflag;
@@ -242,14 +248,55 @@ __device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
   return make_double2(su / nv, sv / nv);
 }
 
+// One SOR update of row p (ice_dynamics_module.f90:633-659).  W = slice width (compile time, so every index,
+// coefficient and neighbour load of the row is issued before the first use: ~4W independent loads in flight per
+// thread, which is what makes the sweep bandwidth- rather than latency-bound); n = row degree (<= W; the
+// padding entries of a mixed-degree slice point at the home row with zero coefficients and are not accumulated).
+template <int W, bool EXACT>
+__device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, const int lane, const int p, const int n, double tmax)
+{
+  int j[W];
+  double cu[W], cv[W], nx[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) {
+    const long long e = o + (long long)c * 32 + lane;
+    j[c] = ld_stream(a.idx + e);
+    cu[c] = ld_stream(a.cU + e);
+    cv[c] = ld_stream(a.cV + e);
+    if (EXACT) nx[c] = ld_stream(a.nxy + e);
+  }
+  const double2 u = a.UV[p];
+  const double2 e2 = ld_stream(a.E + p), r2 = ld_stream(a.RHS + p);
+  const double h = EXACT ? ld_stream(a.nxy0 + p) : ld_stream(a.nxysum + p);
+  double2 nb[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) nb[c] = a.UV[j[c]];
+  double Uxy = u.x * h, Vxy = u.y * h;   // get_mesh_curvatures_vertex_AaAc as coded: home value times every coefficient
+  if (EXACT) {
+#pragma unroll
+    for (int c = 0; c < W; c++) if (c < n) { Uxy = Uxy + u.x * nx[c]; Vxy = Vxy + u.y * nx[c]; }
+  }
+  double sumU = 0.0, sumV = 0.0;
+#pragma unroll
+  for (int c = 0; c < W; c++) if (c < n) { sumU = sumU + nb[c].x * cu[c]; sumV = sumV + nb[c].y * cv[c]; }
+  const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
+  const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
+  const double resU = (LHSx - r2.x) / e2.x;
+  const double resV = (LHSy - r2.y) / e2.y;
+  tmax = fmax(tmax, fabs(resU));
+  tmax = fmax(tmax, fabs(resV));
+  a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
+  return tmax;
+}
+
 template <bool EXACT, bool GLFIX>
-__global__ void __launch_bounds__(256, 4) k_ssa_sor(SorArgs a)
+__global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a)
 {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  __shared__ double sh[8];
+  __shared__ double sh[SOR_BLOCK / 32];
   int it = 0;
   bool done = false;
   unsigned flags = 0;
@@ -267,27 +314,36 @@ __global__ void __launch_bounds__(256, 4) k_ssa_sor(SorArgs a)
         const int n = a.deg[p];
         if (n == UFM_DEG_PAD) continue;
         if (GLFIX) { if (a.mflag[p] & 2) continue; }
-        const double2 u = a.UV[p];
-        double sumU = 0.0, sumV = 0.0, Uxy, Vxy;
-        if (EXACT) { const double h = ld_stream(a.nxy0 + p); Uxy = u.x * h; Vxy = u.y * h; }
-        for (int cc = 0; cc < w; cc++) {
-          if (cc < n) {
-            const long long e = o + (long long)cc * 32 + lane;
-            const double2 nb = a.UV[ld_stream(a.idx + e)];
-            sumU = sumU + nb.x * ld_stream(a.cU + e);
-            sumV = sumV + nb.y * ld_stream(a.cV + e);
-            if (EXACT) { const double t = ld_stream(a.nxy + e); Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+        switch (w) {  // warp-uniform
+          case 3: tmax = sor_row<3, EXACT>(a, o, lane, p, n, tmax); break;
+          case 4: tmax = sor_row<4, EXACT>(a, o, lane, p, n, tmax); break;
+          case 5: tmax = sor_row<5, EXACT>(a, o, lane, p, n, tmax); break;
+          case 6: tmax = sor_row<6, EXACT>(a, o, lane, p, n, tmax); break;
+          case 7: tmax = sor_row<7, EXACT>(a, o, lane, p, n, tmax); break;
+          case 8: tmax = sor_row<8, EXACT>(a, o, lane, p, n, tmax); break;
+          default: {  // rare high-degree rows: generic path with the same accumulation order
+            const double2 u = a.UV[p];
+            const double h = EXACT ? a.nxy0[p] : a.nxysum[p];
+            double sumU = 0.0, sumV = 0.0, Uxy = u.x * h, Vxy = u.y * h;
+            for (int cc = 0; cc < w; cc++) {
+              if (cc < n) {
+                const long long e = o + (long long)cc * 32 + lane;
+                const double2 nbv = a.UV[a.idx[e]];
+                sumU = sumU + nbv.x * a.cU[e];
+                sumV = sumV + nbv.y * a.cV[e];
+                if (EXACT) { const double t = a.nxy[e]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+              }
+            }
+            const double2 e2 = a.E[p], r2 = a.RHS[p];
+            const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
+            const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
+            const double resU = (LHSx - r2.x) / e2.x;
+            const double resV = (LHSy - r2.y) / e2.y;
+            tmax = fmax(tmax, fabs(resU));
+            tmax = fmax(tmax, fabs(resV));
+            a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
           }
         }
-        if (!EXACT) { const double t = ld_stream(a.nxysum + p); Uxy = u.x * t; Vxy = u.y * t; }
-        const double2 e2 = ld_stream(a.E + p), r2 = ld_stream(a.RHS + p);
-        const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
-        const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
-        const double resU = (LHSx - r2.x) / e2.x;
-        const double resV = (LHSy - r2.y) / e2.y;
-        tmax = fmax(tmax, fabs(resU));
-        tmax = fmax(tmax, fabs(resV));
-        a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
       }
       if (c == 4) {  // publish this CTA's max residual before the barrier that precedes the stop test
         for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));

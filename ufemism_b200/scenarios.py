@@ -51,16 +51,22 @@ def state_eismint1(mesh):
                 SMB_year=np.minimum(0.5, 1e-5 * (450000.0 - r)), BMB=np.zeros(mesh.nV))
 
 
-def state_ssa_icestream(mesh, scale=1.0):
+def state_ssa_icestream(mesh, scale=1.0, Hb=-500.0, H_shelf=300.0):
     """BASELINE config 3 (synthetic; the reference has no runnable SSA-only benchmark):
-    flat bed at -500 m, SL = 0; 1000 m grounded ice for r < r1, linear taper to a 300 m shelf at r2,
-    0.1 m thin-shelf convention beyond.  ``scale`` shrinks the radii with the domain."""
+    flat bed at ``Hb``, SL = 0; 1000 m grounded ice for r < r1, linear taper to an ``H_shelf`` thick shelf at
+    r2, 0.1 m thin-shelf convention beyond.  ``scale`` shrinks the radii with the domain.  Physics switches
+    follow the reference's only SSA benchmark, MISMIP_mod (flow factor, SMB 0.3 m/yr)."""
     r = np.hypot(mesh.V[:, 0], mesh.V[:, 1])
     r1, r2 = 1000e3 * scale, 1400e3 * scale
-    Hi = np.where(r < r1, 1000.0, np.where(r < r2, 1000.0 - 700.0 * (r - r1) / (r2 - r1), 0.1))
+    Hi = np.where(r < r1, 1000.0, np.where(r < r2, 1000.0 - (1000.0 - H_shelf) * (r - r1) / (r2 - r1), 0.1))
     Hi[mesh.edge_index > 0] = 0.0
-    return dict(benchmark="MISMIP_mod", Hi=Hi, Hb=np.full(mesh.nV, -500.0), SL=np.zeros(mesh.nV),
+    return dict(benchmark="MISMIP_mod", Hi=Hi, Hb=np.full(mesh.nV, float(Hb)), SL=np.zeros(mesh.nV),
                 SMB_year=np.full(mesh.nV, 0.3), BMB=np.zeros(mesh.nV))
+
+
+# bench.py workload (BASELINE configs[2]): bed at -250 m so that the grounding line sits at ~280 m thick ice and the
+# Tsai et al. grounding-line flux (use_analytical_GL_flux, as in config_MISMIP_mod_*) gives O(1 km/yr) velocities
+CONFIG3 = dict(half_width=1800e3, Hb=-250.0, H_shelf=150.0, use_analytical_GL_flux=1)
 
 
 def state_mismip(mesh, Hi0=100.0, half_width=750e3):
