@@ -238,7 +238,7 @@ def run_ours(args):
             if host is None:
                 g.run_model(r, 1e12, max_steps=1)
             else:
-                g._ck(g.L.ufm_run_model_host(g.h, ctypes.byref(r), ctypes.c_double(1e12), ctypes.c_long(1), ctypes.byref(host)))
+                g.run_model_host(r, 1e12, 1, host)
             rows.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
         return rows
 
@@ -265,9 +265,8 @@ def run_ours(args):
     value = world * yrs / (ms * 1e-3) * 3600.0
 
     # ---------------- drop-in mode with host buffers: `e2e` ----------------
-    class HostIce(ctypes.Structure):
-        _fields_ = [(n, ctypes.c_void_p) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "mask_noice", "Hi_out", "Hi_prev", "dHi_dt", "Hs",
-                                                   "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA", "mask")]
+    from ufemism_b200.capi import HostIce
+
     nV = m.nV
     hb = {n: np.zeros(nV) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "Hi_prev", "dHi_dt", "Hs", "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA")}
     hb["mask_noice"] = np.zeros(nV, np.int32); hb["mask"] = np.zeros(nV, np.int32)

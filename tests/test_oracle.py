@@ -1,0 +1,260 @@
+"""The oracle against the only known answers the reference holds (Halfar / Bueler closed forms,
+src/reference_fields_module.f90:707-795), its own committed golden vectors, and the properties and quirks
+SURVEY.md sections 0 and 4 list.  PARITY UNPINNED: the Fortran reference cannot be run here (see oracle/ufm_oracle.h)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import get_mesh
+from tests.util import make_oracle, rel_l2
+from ufemism_b200 import mesh as M
+from ufemism_b200 import scenarios as S
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ---------------------------------------------------------------- analytic known answers
+def test_halfar_closed_form_matches_numpy_restatement():
+    from oracle.oracle import halfar_solution
+
+    x = np.linspace(-4e5, 4e5, 41); y = np.linspace(-3e5, 3e5, 41)
+    for t in (0.0, 100.0, 5000.0):
+        a = halfar_solution(5000.0, 300000.0, x, y, t)
+        b = S.halfar_H(5000.0, 300000.0, x, y, t)
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)
+    # dome height at t = 0 is H0, margin at R0
+    assert halfar_solution(5000.0, 300000.0, [0.0], [0.0], 0.0)[0] == pytest.approx(5000.0, rel=1e-14)
+    assert halfar_solution(5000.0, 300000.0, [300000.0], [0.0], 0.0)[0] == 0.0
+
+
+def test_bueler_solution_and_mass_balance_consistent():
+    from oracle.oracle import bueler_solution, lib
+
+    L = lib()
+    H0, R0, lam = 3000.0, 500000.0, 5.0
+    x = np.array([0.0, 1e5, 2e5, 3e5]); y = np.zeros(4)
+    np.testing.assert_allclose(bueler_solution(H0, R0, lam, x, y, 2000.0), S.bueler_H(H0, R0, lam, x, y, 2000.0), rtol=1e-12)
+    # M = lambda/t * H  (src/SMB_module.f90:281)
+    for xi in x:
+        H = L.ora_Bueler_solution(H0, R0, lam, float(xi), 0.0, 2000.0)
+        Mb = L.ora_Bueler_solution_MB(H0, R0, lam, float(xi), 0.0, 2000.0)
+        assert Mb == pytest.approx(lam / 2000.0 * H, rel=1e-13)
+
+
+@pytest.mark.parametrize("nv,tol", [(2500, 0.08), (10000, 0.05)])
+def test_halfar_run_tracks_analytic_solution(nv, tol):
+    """SIA + mass continuity through run_model for 50 yr vs Halfar_solution(t): discretisation-level agreement,
+    improving with resolution; volume conserved (zero SMB, no clipping at the dome)."""
+    from oracle.oracle import T_THERMO
+
+    m = get_mesh(nv)
+    st = S.state_halfar(m)
+    o = make_oracle(m, st, nthreads=4)
+    vol0 = float((o["Hi"] * m.A).sum())
+    r = o.region(0.0); r.dtc[T_THERMO] = 5.0
+    assert o.run_model(r, 50.0) == 0 and r.time == 50.0
+    Han = S.halfar_H(5000.0, 300000.0, m.V[:, 0], m.V[:, 1], 50.0)
+    err = rel_l2(o["Hi"], Han)
+    assert err < tol, err
+    assert abs(float((o["Hi"] * m.A).sum()) / vol0 - 1.0) < 1e-12
+    test_halfar_run_tracks_analytic_solution.err = getattr(test_halfar_run_tracks_analytic_solution, "err", {}); test_halfar_run_tracks_analytic_solution.err[nv] = err
+
+
+def test_halfar_error_decreases_with_resolution():
+    e = getattr(test_halfar_run_tracks_analytic_solution, "err", {})
+    if len(e) < 2:
+        pytest.skip("needs the two resolutions above")
+    assert e[10000] < e[2500]
+
+
+# ---------------------------------------------------------------- golden vectors (regression pins of the oracle itself)
+def _golden_case():
+    m = M.Mesh.load(os.path.join(GOLDEN, "mesh_600.npz"))
+    g = np.load(os.path.join(GOLDEN, "oracle_600.npz"))
+    return m, g
+
+
+def test_mesh_substrate_reproduces_golden_mesh():
+    m, _ = _golden_case()
+    m2 = M.square_mesh_with_nv(750e3, 600, seed=11)
+    for k in ("V", "C", "nC", "Aci", "iAci", "CAaAc", "nCAaAc", "colour", "colour_nV", "edge_index_Ac"):
+        assert np.array_equal(getattr(m, k), getattr(m2, k)), k
+    for k in ("A", "Cw", "Nx", "Ny", "Nx_Ac", "No_Ac", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc"):
+        a, b = getattr(m, k), getattr(m2, k)
+        assert np.array_equal(a, b, equal_nan=True), k
+
+
+def test_oracle_reproduces_golden_vectors():
+    from tests.golden.make_golden import run_case
+
+    m, g = _golden_case()
+    out = run_case(m)
+    for k in g.files:
+        assert np.array_equal(out[k], g[k], equal_nan=True), k
+
+
+# ---------------------------------------------------------------- properties / quirks
+def test_mesh_invariants(mesh_2k):
+    M.check_mesh(mesh_2k)
+    m = mesh_2k
+    # Ac degree: 6 interior, 4 on the boundary; Aa vertices only neighbour Ac vertices
+    deg_ac = m.nCAaAc[m.nV:]
+    assert set(np.unique(deg_ac[m.edge_index_Ac == 0])) == {6} and set(np.unique(deg_ac[m.edge_index_Ac > 0])) == {4}
+    assert (m.CAaAc[: m.nV][m.CAaAc[: m.nV] > 0] > m.nV).all()
+    # neighbour functions differentiate linear fields exactly
+    f = 2.0 * m.V[:, 0] - 3.0 * m.V[:, 1] + 7.0
+    from oracle.oracle import Oracle
+    o = Oracle(m)
+    fx, fy = np.zeros(m.nV), np.zeros(m.nV)
+    o.L.ora_get_mesh_derivatives(*[__import__("ctypes").byref(x) for x in (o.cm, o.cfg)], f.ctypes.data, fx.ctypes.data, fy.ctypes.data)
+    np.testing.assert_allclose(fx, 2.0, atol=1e-9); np.testing.assert_allclose(fy, -3.0, atol=1e-9)
+
+
+def test_partition_list_semantics():
+    import ctypes
+    from oracle.oracle import lib
+    L = lib()
+    for ntot, n in ((10, 4), (7, 8), (1000003, 16), (5, 2)):
+        seen = []
+        for i in range(n):
+            a, b = ctypes.c_int(), ctypes.c_int()
+            L.ora_partition_list(ntot, i, n, ctypes.byref(a), ctypes.byref(b))
+            seen += list(range(a.value, b.value + 1))
+        assert seen == list(range(1, ntot + 1))  # ranges tile 1..ntot; tiny lists all go to rank 0 (mesh_help_functions_module.f90:1482-1493)
+
+
+def test_thickness_update_conserves_mass_without_clipping(mesh_2k):
+    m = mesh_2k
+    st = S.state_halfar(m)
+    st["SMB_year"] = 0.2 * np.ones(m.nV)
+    o = make_oracle(m, st)
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    dt = 0.01
+    H0 = o["Hi"].copy()
+    o.calculate_ice_thickness_change(dt)
+    inner = m.edge_index == 0
+    # sum A dH = sum A M dt over the vertices that are not reset by the boundary condition
+    lhs = float((m.A[inner] * (o["Hi"][inner] - H0[inner])).sum())
+    rhs = float((m.A[inner] * 0.2 * dt).sum())
+    assert lhs == pytest.approx(rhs, rel=1e-9)
+    assert np.array_equal(o["Hi_prev"], H0)
+    # dt = 0 on the first step: dHi_dt forced to zero (ice_dynamics_module.f90:179-180)
+    o.calculate_ice_thickness_change(0.0)
+    assert not o["dHi_dt"].any()
+
+
+def test_masks_consistent(mesh_2k):
+    st = S.state_ssa_icestream(mesh_2k, scale=750e3 / 1800e3)
+    o = make_oracle(mesh_2k, st)
+    o.update_general_ice_model_data(0.0)
+    f = o.f
+    assert np.array_equal(f["mask_land"] + f["mask_ocean"], np.ones(mesh_2k.nV, np.int32))
+    assert np.array_equal(f["mask_sheet"], f["mask_ice"] * f["mask_land"])
+    assert np.array_equal(f["mask_shelf"], f["mask_ice"] * f["mask_ocean"])
+    assert f["mask_gl"].sum() > 0 and f["mask_gl_Ac"].sum() > 0
+    assert (f["mask_gl"] <= f["mask_sheet"]).all()
+    assert set(np.unique(f["mask"])) <= set(range(9))
+
+
+def test_sia_diffusivity_negative_and_clipped(mesh_2k):
+    st = S.state_halfar(mesh_2k)
+    o = make_oracle(mesh_2k, st)
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    assert (o["D_SIA_3D_Ac"] <= 0).all() and o["D_SIA_3D_Ac"].min() >= -1e5
+    assert (o["D_SIA_Ac"] <= 0).all() and o["D_SIA_Ac"].min() < 0
+
+
+def test_cfl_uses_single_precision_literal(mesh_2k):
+    """`- 1E-09` at src/UFEMISM_main_model.f90:752 is a default-REAL constant."""
+    m = mesh_2k
+    o = make_oracle(m, S.state_halfar(m))
+    d = o.determine_timesteps()  # all fields zero: dt_D = min dist^2 / (6 pi 1e-9f), others 1000
+    vi, vj = m.Aci[:, 0] - 1, m.Aci[:, 1] - 1
+    dist = np.sqrt((m.V[vj, 0] - m.V[vi, 0]) ** 2 + (m.V[vj, 1] - m.V[vi, 1]) ** 2)
+    want = min(1000.0, float(((dist * dist) / (-6.0 * 3.141592653589793 * (0.0 - float(np.float32(1e-9))))).min())) * 0.9
+    assert d[0] == want and d[1] == 900.0 and d[2] == 900.0
+
+
+def _sor_system(mesh, nthreads=1):
+    st = S.state_ssa_icestream(mesh, scale=750e3 / 1800e3)
+    o = make_oracle(mesh, st, nthreads=nthreads)
+    o.update_general_ice_model_data(0.0)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    return o
+
+
+def test_sor_independent_of_rank_count(mesh_2k):
+    """src/changelog.txt:45-48: results no longer depend on the number of processes."""
+    a, b = _sor_system(mesh_2k, 1), _sor_system(mesh_2k, 7)
+    ra, rb = a.solve_SSA_linearised(max_inner=25, force_iters=True), b.solve_SSA_linearised(max_inner=25, force_iters=True)
+    assert ra[:2] == rb[:2]
+    assert np.array_equal(a["U_SSA_AaAc"], b["U_SSA_AaAc"]) and np.array_equal(a["V_SSA_AaAc"], b["V_SSA_AaAc"])
+
+
+def test_sor_cross_term_uses_home_value_quirk(mesh_2k):
+    """get_mesh_curvatures_vertex_AaAc multiplies every Nxy coefficient by d(ai), not d(ac).
+    Re-derive the first-colour update of one sweep in numpy both ways; the oracle must match the as-coded form."""
+    m = mesh_2k
+    o = _sor_system(m)
+    M_ = m.nVAaAc
+    rng = np.random.default_rng(5)
+    U0 = rng.normal(0, 100.0, M_); V0 = rng.normal(0, 100.0, M_)
+    o["U_SSA_AaAc"][:] = U0; o["V_SSA_AaAc"][:] = V0
+    o.solve_SSA_linearised(max_inner=1, force_iters=True)
+    eu, rx = o["eu_i_AaAc"], o["RHSx_AaAc"]
+    first = m.colour_vi[: m.colour_nV[0], 0] - 1
+    is_edge = np.concatenate([m.edge_index, m.edge_index_Ac]) > 0
+    checked = 0
+    for ai in first[:200]:
+        if is_edge[ai]:
+            continue
+        n = m.nCAaAc[ai]
+        nb = m.CAaAc[ai, :n] - 1
+        sumU = 0.0
+        for c in range(n):
+            sumU = sumU + U0[nb[c]] * (4.0 * m.Nxx_AaAc[ai, c] + m.Nyy_AaAc[ai, c])
+        vxy_code = V0[ai] * m.Nxy_AaAc[ai, n]
+        vxy_doc = V0[ai] * m.Nxy_AaAc[ai, n]
+        for c in range(n):
+            vxy_code = vxy_code + V0[ai] * m.Nxy_AaAc[ai, c]
+            vxy_doc = vxy_doc + V0[nb[c]] * m.Nxy_AaAc[ai, c]
+        res_code = ((sumU + (3.0 * vxy_code) + (eu[ai] * U0[ai])) - rx[ai]) / eu[ai]
+        res_doc = ((sumU + (3.0 * vxy_doc) + (eu[ai] * U0[ai])) - rx[ai]) / eu[ai]
+        assert o["resU_AaAc"][ai] == res_code
+        assert o["resU_AaAc"][ai] != res_doc
+        assert o["U_SSA_AaAc"][ai] == U0[ai] - 1.2 * res_code
+        checked += 1
+    assert checked > 50
+
+
+def test_neumann_boundary(mesh_2k):
+    m = mesh_2k
+    o = make_oracle(m, S.state_halfar(m))
+    rng = np.random.default_rng(9)
+    d = rng.normal(size=m.nVAaAc)
+    d0 = d.copy()
+    o.apply_Neumann_boundary_AaAc(d)
+    is_edge = np.concatenate([m.edge_index, m.edge_index_Ac]) > 0
+    assert np.array_equal(d[~is_edge], d0[~is_edge])
+    for ai in np.flatnonzero(is_edge)[:300]:
+        n = m.nCAaAc[ai]; nb = m.CAaAc[ai, :n] - 1
+        if ai < 4:
+            s = 0.0
+            for j in nb:
+                s += d[j]          # corners: all neighbours, at their NEW values
+            assert d[ai] == s / n
+        else:
+            vals = [d0[j] for j in nb if not is_edge[j]]
+            s = 0.0
+            for v in vals:
+                s += v
+            assert d[ai] == s / len(vals)
+
+
+def test_solve_ssa_refuses_unknown_and_zeroes(mesh_2k):
+    o = make_oracle(mesh_2k, S.state_halfar(mesh_2k))
+    o.update_general_ice_model_data(0.0)
+    o["U_SSA"][:] = 1.0
+    st = o.solve_SSA()
+    assert st.n_outer == 0 and not o["U_SSA"].any()

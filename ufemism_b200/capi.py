@@ -67,6 +67,12 @@ class Region(ctypes.Structure):
                 ("n_outer_total", ctypes.c_long), ("dt_crit_last", ctypes.c_double * 3)]
 
 
+class HostIce(ctypes.Structure):
+    """ufm_host_ice: host arrays (reference vertex order) moved every step in drop-in mode."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "mask_noice", "Hi_out", "Hi_prev", "dHi_dt", "Hs",
+                                               "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA", "mask")]
+
+
 def _parse_fields():
     txt = open(HEADER).read()
     body = txt[txt.index("enum ufm_field {"):]
@@ -99,7 +105,7 @@ for _n, _i in FIELD_IDS.items():
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
-            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_counters_get", "ufm_counters_reset"]
+            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
 _lib = None
 
@@ -134,6 +140,7 @@ def load_library():
         L.ufm_ssa_finish.argtypes = [p]
         L.ufm_region_init.argtypes = [p, d]
         L.ufm_run_model.argtypes = [p, p, d, ctypes.c_long]
+        L.ufm_run_model_host.argtypes = [p, p, d, ctypes.c_long, p]
         L.ufm_counters_get.argtypes = [p, p]
         L.ufm_counters_reset.argtypes = [p]
         _lib = L
@@ -276,6 +283,9 @@ class IceModelGPU:
 
     def run_model(self, region, t_end, max_steps=0):
         return self._ck(self.L.ufm_run_model(self.h, ctypes.byref(region), float(t_end), int(max_steps)))
+
+    def run_model_host(self, region, t_end, max_steps, host):
+        return self._ck(self.L.ufm_run_model_host(self.h, ctypes.byref(region), float(t_end), int(max_steps), ctypes.byref(host)))
 
     def counters(self):
         c = Counters()

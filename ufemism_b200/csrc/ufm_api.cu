@@ -211,6 +211,7 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   const int n = r.kind == K_AA ? m.nV : (r.kind == K_AC ? m.nAc : m.M);
   const int *r2d = r.kind == K_AA ? m.aa_ref2dev : (r.kind == K_AC ? m.ac_ref2dev : m.m_ref2dev);
   const size_t bytes = r.is3d ? (size_t)n * h->P.nZ * sizeof(double) : (size_t)n * (r.is_int ? sizeof(int) : sizeof(double));
+  if (!to_device && field >= UFM_F_DU_DX_AAAC && field <= UFM_F_DV_DY_AAAC) { if ((rc = ufm_k_ssa_gradients(h))) return rc; }
   if (to_device) {
     if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
     memcpy(h->staging, host, bytes);

@@ -126,7 +126,7 @@ struct ufm_handle {
   DevMesh mesh;
   DevState st;
   ufm_counters cnt;
-  int sor_grid = 0, sor_block = 128;
+  int sor_grid = 0, sor_block = 512;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;
@@ -145,6 +145,7 @@ int ufm_k_cfl(ufm_handle *h, double out3[3]);
 int ufm_k_ssa_prepare(ufm_handle *h);
 int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2]);
 int ufm_k_ssa_sliding_setup(ufm_handle *h);
+int ufm_k_ssa_gradients(ufm_handle *h);
 int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *stats);
 int ufm_k_ssa_finish(ufm_handle *h);
 int ufm_k_ssa_zero(ufm_handle *h);

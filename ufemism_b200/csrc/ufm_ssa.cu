@@ -127,6 +127,29 @@ struct ViscArgs {
   double2 *dU, *dV;
   double *partials;
 };
+template <int W>
+__device__ __forceinline__ void visc_row(const ViscArgs &a, const long long o, const int lane, const int p, const int n,
+                                         double &ux, double &uy, double &vx, double &vy)
+{
+  int j[W];
+  double cx[W], cy[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) {
+    const long long e = o + (long long)c * 32 + lane;
+    j[c] = ld_stream(a.idx + e); cx[c] = ld_stream(a.nx + e); cy[c] = ld_stream(a.ny + e);
+  }
+  const double2 u = a.UV[p];
+  const double hx = ld_stream(a.nx0 + p), hy = ld_stream(a.ny0 + p);
+  double2 nb[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) nb[c] = a.UV[j[c]];
+  ux = hx * u.x; uy = hy * u.x; vx = hx * u.y; vy = hy * u.y;
+#pragma unroll
+  for (int c = 0; c < W; c++)
+    if (c < n) { ux = ux + cx[c] * nb[c].x; uy = uy + cy[c] * nb[c].x; vx = vx + cx[c] * nb[c].y; vy = vy + cy[c] * nb[c].y; }
+}
+
+template <bool STORE_GRAD>
 __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
 {
   const int lane = threadIdx.x & 31;
@@ -138,17 +161,30 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
     const int p = s * 32 + lane;
     const int n = a.deg[p];
     if (n == UFM_DEG_PAD) continue;
-    const double2 u = a.UV[p];
-    double ux = a.nx0[p] * u.x, uy = a.ny0[p] * u.x, vx = a.nx0[p] * u.y, vy = a.ny0[p] * u.y;
-    for (int c = 0; c < w; c++) {
-      if (c < n) {
-        const long long e = o + (long long)c * 32 + lane;
-        const double2 nb = a.UV[ld_stream(a.idx + e)];
-        const double cx = ld_stream(a.nx + e), cy = ld_stream(a.ny + e);
-        ux = ux + cx * nb.x; uy = uy + cy * nb.x;
-        vx = vx + cx * nb.y; vy = vy + cy * nb.y;
+    double ux, uy, vx, vy;
+    switch (w) {
+      case 2: visc_row<2>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 3: visc_row<3>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 4: visc_row<4>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 5: visc_row<5>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 6: visc_row<6>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 7: visc_row<7>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      case 8: visc_row<8>(a, o, lane, p, n, ux, uy, vx, vy); break;
+      default: {
+        const double2 u = a.UV[p];
+        ux = a.nx0[p] * u.x; uy = a.ny0[p] * u.x; vx = a.nx0[p] * u.y; vy = a.ny0[p] * u.y;
+        for (int c = 0; c < w; c++) {
+          if (c < n) {
+            const long long e = o + (long long)c * 32 + lane;
+            const double2 nb = a.UV[a.idx[e]];
+            const double cx = a.nx[e], cy = a.ny[e];
+            ux = ux + cx * nb.x; uy = uy + cy * nb.x;
+            vx = vx + cx * nb.y; vy = vy + cy * nb.y;
+          }
+        }
       }
     }
+    if (STORE_GRAD) { a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy); continue; }
     const double epsilon_sq_0 = 1E-12;
     double eta = a.visc_A * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
     double Nn = eta * a.Hm[p];
@@ -156,8 +192,8 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
     s_dn = s_dn + dn * dn;
     s_n = s_n + Nn * Nn;
     a.eta[p] = eta; a.N[p] = Nn;
-    a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy);
   }
+  if (STORE_GRAD) return;
   // deterministic block reduction (fixed tree), one partial pair per block
   __shared__ double sh[2][8];
   for (int o = 16; o > 0; o >>= 1) { s_dn += __shfl_xor_sync(0xffffffffu, s_dn, o); s_n += __shfl_xor_sync(0xffffffffu, s_n, o); }
@@ -169,13 +205,19 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
     a.partials[2 * blockIdx.x] = t0; a.partials[2 * blockIdx.x + 1] = t1;
   }
 }
+// fixed-shape tree over the per-block partials: deterministic for a given grid size
 __global__ void k_sum_partials(int n, const double *partials, double *out2)
 {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int k = 0; k < n; k++) { t0 += partials[2 * k]; t1 += partials[2 * k + 1]; }
-    out2[0] = t0; out2[1] = t1;
+  __shared__ double sh[2][256];
+  double t0 = 0.0, t1 = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) { t0 += partials[2 * k]; t1 += partials[2 * k + 1]; }
+  sh[0][threadIdx.x] = t0; sh[1][threadIdx.x] = t1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
   }
+  if (threadIdx.x == 0) { out2[0] = sh[0][0]; out2[1] = sh[1][0]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,10 +258,10 @@ __global__ void k_ssa_setup(SetupArgs a)
 // ctrl[10]    last max residual (bits)
 // ---------------------------------------------------------------------------------------------
 #ifndef SOR_BLOCK
-#define SOR_BLOCK 128
+#define SOR_BLOCK 512
 #endif
 #ifndef SOR_MIN_BLOCKS
-#define SOR_MIN_BLOCKS 4
+#define SOR_MIN_BLOCKS 1
 #endif
 struct SorArgs {
   const long long *off;
@@ -476,13 +518,28 @@ int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
   a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
   if (grid > 4096) grid = 4096;
-  k_ssa_viscosity<<<grid, 256, 0, h->stream>>>(a);
-  k_sum_partials<<<1, 32, 0, h->stream>>>(grid, s.partials, s.scal);
+  k_ssa_viscosity<false><<<grid, 256, 0, h->stream>>>(a);
+  k_sum_partials<<<1, 256, 0, h->stream>>>(grid, s.partials, s.scal);
   h->cnt.kernel_launches += 2;
   UFM_CUDA(cudaMemcpyAsync(s.scal_h, s.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
   sums2[0] = s.scal_h[0]; sums2[1] = s.scal_h[1];
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
+}
+
+// dU_SSA_dx_AaAc ... dV_SSA_dy_AaAc are pure diagnostics in the reference (written at ice_dynamics_module.f90:712-713, read
+// nowhere else); the device path does not store them per viscosity iteration but recomputes them from the current
+// U,V when the host asks for them.
+int ufm_k_ssa_gradients(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  ViscArgs a;
+  a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
+  a.Hm = s.Hm; a.UV = s.UV; a.visc_A = 0.0; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
+  int grid = h->num_sms * 8;
+  k_ssa_viscosity<true><<<grid, 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_gradients");
 }
 
 int ufm_k_ssa_sliding_setup(ufm_handle *h)
