@@ -153,6 +153,21 @@ int ufm_abi_version(void);
 int ufm_mesh_upload(ufm_handle *h, const ufm_mesh_desc *mesh);
 int ufm_mesh_free(ufm_handle *h);
 
+/* ---- vertex-partitioned runs over the GPUs of one NVSwitch domain (replaces the index-range split of
+ *      partition_list, src/mesh_help_functions_module.f90:1475-1496, and the MPI_BARRIER / MPI_ALLREDUCE of the SOR loop,
+ *      src/ice_dynamics_module.f90:662,673).  One process per GPU.  Every rank uploads the same mesh and holds the whole
+ *      state; the SSA solve (viscosity, linear-system setup, SOR sweeps) is partitioned into x-strips balanced by row
+ *      count.  After each colour sweep the rows a neighbour strip reads are pushed straight into that GPU's (U,V) array
+ *      by the sweep kernel itself (NVLink peer stores through CUDA-IPC mappings) and epochs are exchanged through
+ *      per-GPU mailboxes; results are bit-identical to the single-GPU run.
+ *      Protocol:  ufm_partition_set -> ufm_mesh_upload -> ufm_comm_export -> (all-gather the blobs, e.g. with
+ *      torch.distributed / MPI_ALLGATHER) -> ufm_comm_connect -> (host barrier) -> compute calls, collectively. ---- */
+#define UFM_MAX_RANKS 8
+#define UFM_COMM_BLOB_BYTES 256
+int ufm_partition_set(ufm_handle *h, int rank, int nranks);
+int ufm_comm_export(ufm_handle *h, void *blob /* UFM_COMM_BLOB_BYTES */);
+int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_BYTES, in rank order */);
+
 /* ---- state: explicit, field-granular, reference vertex order ---- */
 int ufm_state_upload(ufm_handle *h, int field, const void *host);
 int ufm_state_download(ufm_handle *h, int field, void *host);

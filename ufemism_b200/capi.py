@@ -103,7 +103,7 @@ for _n, _i in FIELD_IDS.items():
     _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
 
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
-            "ufm_mesh_upload", "ufm_mesh_free", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
+            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
@@ -126,6 +126,9 @@ def load_library():
         L.ufm_last_error.restype = ctypes.c_char_p
         L.ufm_mesh_upload.argtypes = [p, p]
         L.ufm_mesh_free.argtypes = [p]
+        L.ufm_partition_set.argtypes = [p, i, i]
+        L.ufm_comm_export.argtypes = [p, p]
+        L.ufm_comm_connect.argtypes = [p, p]
         L.ufm_state_upload.argtypes = [p, i, p]
         L.ufm_state_download.argtypes = [p, i, p]
         L.ufm_thickness_update.argtypes = [p, d]
@@ -172,12 +175,15 @@ def default_params(benchmark="Halfar", **kw) -> Params:
 class IceModelGPU:
     """One model region resident on one B200."""
 
-    def __init__(self, mesh, benchmark="Halfar", device=0, **params):
+    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, **params):
         self.L = load_library()
         self.mesh = mesh
         self.P = default_params(benchmark, **params)
         self.h = ctypes.c_void_p()
+        self.rank, self.nranks = int(rank), int(nranks)
         self._ck(self.L.ufm_create(int(device), ctypes.byref(self.P), ctypes.byref(self.h)))
+        if self.nranks > 1:
+            self._ck(self.L.ufm_partition_set(self.h, self.rank, self.nranks))
         self.upload_mesh(mesh)
 
     def _ck(self, rc, allow_warning=False):
@@ -210,6 +216,30 @@ class IceModelGPU:
             setattr(d, n, a.ctypes.data)
         self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
         self.mesh = mesh
+
+    COMM_BLOB_BYTES = 256
+
+    def comm_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.COMM_BLOB_BYTES)
+        self._ck(self.L.ufm_comm_export(self.h, buf))
+        return buf.raw
+
+    def comm_connect(self, blobs):
+        """``blobs``: the COMM_BLOB_BYTES export of every rank, in rank order."""
+        assert len(blobs) == self.nranks and all(len(b) == self.COMM_BLOB_BYTES for b in blobs)
+        self._ck(self.L.ufm_comm_connect(self.h, b"".join(blobs)))
+
+    def connect(self, dist, device=None):
+        """All-gather the IPC blobs with ``torch.distributed`` (any backend) and connect; collective."""
+        import torch
+
+        mine = torch.frombuffer(bytearray(self.comm_export()), dtype=torch.uint8)
+        if device is not None:
+            mine = mine.to(device)
+        out = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(out, mine)
+        self.comm_connect([bytes(t.cpu().numpy().tobytes()) for t in out])
+        dist.barrier()
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.ufm_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr)))

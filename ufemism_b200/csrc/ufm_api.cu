@@ -136,6 +136,57 @@ int ufm_mesh_free(ufm_handle *h)
   return ufm_mesh_free_impl(h);
 }
 
+/* ---- partitioned runs: CUDA-IPC plumbing ---- */
+int ufm_partition_set(ufm_handle *h, int rank, int nranks)
+{
+  if (!h) return ufm_set_error(-2, "NULL handle");
+  if (nranks < 1 || nranks > UFM_MAX_RANKS || rank < 0 || rank >= nranks) return ufm_set_error(-2, "ufm_partition_set: rank %d of %d out of range (max %d ranks)", rank, nranks, UFM_MAX_RANKS);
+  if (h->has_mesh) return ufm_set_error(-2, "ufm_partition_set must precede ufm_mesh_upload");
+  h->part_rank = rank; h->part_n = nranks;
+  return 0;
+}
+int ufm_comm_export(ufm_handle *h, void *blob)
+{
+  if (!h || !h->has_mesh || !blob) return ufm_set_error(-2, "ufm_comm_export: no mesh resident");
+  UFM_CUDA(cudaSetDevice(h->device));
+  static_assert(3 * sizeof(cudaIpcMemHandle_t) <= UFM_COMM_BLOB_BYTES, "blob too small");
+  memset(blob, 0, UFM_COMM_BLOB_BYTES);
+  cudaIpcMemHandle_t hd[3];
+  UFM_CUDA(cudaIpcGetMemHandle(&hd[0], h->st.UV));
+  UFM_CUDA(cudaIpcGetMemHandle(&hd[1], h->st.partials));
+  UFM_CUDA(cudaIpcGetMemHandle(&hd[2], h->st.mail));
+  memcpy(blob, hd, sizeof(hd));
+  return 0;
+}
+int ufm_comm_connect(ufm_handle *h, const void *blobs)
+{
+  if (!h || !h->has_mesh || !blobs) return ufm_set_error(-2, "ufm_comm_connect: no mesh resident");
+  UFM_CUDA(cudaSetDevice(h->device));
+  ufm_comm_reset(h);
+  const int P = h->mesh.P, me = h->mesh.rank;
+  for (int q = 0; q < P; q++) {
+    if (q == me) continue;
+    cudaIpcMemHandle_t hd[3];
+    memcpy(hd, (const char *)blobs + (size_t)q * UFM_COMM_BLOB_BYTES, sizeof(hd));
+    void *ptr[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < 3; k++) {
+      UFM_CUDA(cudaIpcOpenMemHandle(&ptr[k], hd[k], cudaIpcMemLazyEnablePeerAccess));
+      h->ipc_opened[3 * q + k] = ptr[k];
+    }
+    h->comm.uv[q] = (double2 *)ptr[0]; h->comm.partials[q] = (double *)ptr[1]; h->comm.mail[q] = (unsigned long long *)ptr[2];
+  }
+  h->comm_connected = true;
+  return 0;
+}
+}  // extern "C"
+int ufm_comm_reset(ufm_handle *h)
+{
+  for (int k = 0; k < 3 * UFM_MAX_RANKS; k++) if (h->ipc_opened[k]) { cudaIpcCloseMemHandle(h->ipc_opened[k]); h->ipc_opened[k] = nullptr; }
+  h->comm_connected = false;
+  return 0;
+}
+extern "C" {
+
 /* ---- field table ---- */
 enum { K_AA = 0, K_AC = 1, K_M = 2 };
 struct FieldRef { int kind; int is_int; double *d; int stride, comp; int *i; const unsigned *bits; unsigned barg; int bmode; int is3d; };

@@ -20,6 +20,13 @@
 
 #define UFM_DEG_PAD 0xFF
 #define UFM_SLICE 32
+#define UFM_CHUNK 256       // rows per reduction chunk; every (block, owner) range of the AaAc layout is aligned to it
+// mailbox words (one mailbox per GPU, written by its peers over NVLink)
+#define MAIL_FLAG 0         // [q] epoch counter signalled by rank q
+#define MAIL_RESID 8        // [3][8] max-residual bits of rank q for SOR iteration it%3
+#define MAIL_EPOCH 40       // own epoch counter
+#define MAIL_ABORT 41       // set when a peer wait timed out
+#define MAIL_WORDS 64
 
 // src/parameters_module.f90:9-21
 #define UFM_PI 3.141592653589793
@@ -75,12 +82,21 @@ struct DevMesh {
   double *m_cU0 = nullptr, *m_cV0 = nullptr;      // 4Nxx+Nyy, 4Nyy+Nxx home
   int *m_src = nullptr;        // >= 0: Aa device idx; < 0: ~(Ac device idx); INT_MIN: padding
   int *aa2m = nullptr, *ac2m = nullptr;  // Aa / Ac device idx -> AaAc position
-  int col_begin[6] = {}, col_end[6] = {};  // slice ranges [begin,end) of colours 1..5 (non-edge rows) ; [5] = edge block
+  // vertex partition: rows of every block (colours 1..5, edge block) are grouped by owner rank, so rank r's
+  // share of block b is the contiguous slice range rng[b][r] = [begin, end); x-strips balanced by row count
+  int P = 1, rank = 0;
+  int rng[6][UFM_MAX_RANKS][2] = {};
+  int *rng_dev = nullptr;            // [(b*P + r)*2 + {0,1}]
+  int *rng_all_dev = nullptr;        // [b*2 + {0,1}]: whole blocks (all owners)
+  unsigned char *m_xmask = nullptr;  // per row: bit q set -> rank q reads this row, push new (U,V) to it
+  unsigned char *m_sowner = nullptr; // per slice: owner rank
+  int bc_rng[UFM_MAX_RANKS + 1] = {};  // Neumann rows grouped by owner
+  int corner_owner[4] = {};
+  int n_chunks = 0;
   // Neumann boundary lists
   int n_bc = 0;                // edge vertices except corners 1..4
   int *bc_pos = nullptr, *bc_ptr = nullptr, *bc_nbr = nullptr;
   int corner_pos[4] = {}, corner_n[4] = {};
-  int *col_dev = nullptr;      // [10] col_begin[0..4], col_end[0..4] (device copy for the SOR kernel)
   int *corner_dev = nullptr;   // [8] corner_pos, corner_n
   int *corner_nbr = nullptr;   // [4*16] neighbour position
   int *corner_row = nullptr;   // [4*16] bc row of that neighbour, or -1 when it is not an edge vertex
@@ -111,8 +127,17 @@ struct DevState {
   // reductions / control
   double *partials = nullptr;      // [2*n_partial]
   unsigned long long *ctrl = nullptr;  // SOR control block
+  unsigned long long *mail = nullptr;  // mailbox for peer GPUs
   double *scal = nullptr;          // small result scratch (device), mirrored in pinned host memory
   double *scal_h = nullptr;
+};
+
+// peer-mapped buffers of the other ranks of a partitioned run (CUDA IPC), index = rank; [own rank] = own buffers
+struct CommDev {
+  int P, rank;
+  double2 *uv[UFM_MAX_RANKS];
+  double *partials[UFM_MAX_RANKS];
+  unsigned long long *mail[UFM_MAX_RANKS];
 };
 
 struct ufm_handle {
@@ -127,6 +152,10 @@ struct ufm_handle {
   DevState st;
   ufm_counters cnt;
   int sor_grid = 0, sor_block = 512;
+  int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload
+  bool comm_connected = false;
+  CommDev comm;
+  void *ipc_opened[3 * UFM_MAX_RANKS] = {};
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;
@@ -146,6 +175,7 @@ int ufm_k_ssa_prepare(ufm_handle *h);
 int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2]);
 int ufm_k_ssa_sliding_setup(ufm_handle *h);
 int ufm_k_ssa_gradients(ufm_handle *h);
+int ufm_comm_reset(ufm_handle *h);
 int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *stats);
 int ufm_k_ssa_finish(ufm_handle *h);
 int ufm_k_ssa_zero(ufm_handle *h);

@@ -26,6 +26,66 @@ namespace cg = cooperative_groups;
 // streaming (read-once) loads: evict-first so that (U,V) stays L2-resident across colour phases
 template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 
+// ---------------------------------------------------------------------------------------------
+// Inter-GPU signalling over NVLink (vertex-partitioned runs).  Every rank owns a mailbox in its own
+// HBM that its peers write with plain system-scope stores through CUDA-IPC mapped pointers; a rank only ever
+// spins on its OWN memory.  peer_sync is an all-to-all epoch barrier executed by exactly one thread per GPU.
+// A wait that exceeds SPIN_LIMIT polls (seconds) raises MAIL_ABORT instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+#define SPIN_LIMIT 40000000LL
+__device__ __forceinline__ void peer_sync(const CommDev &cm)
+{
+  __threadfence_system();
+  volatile unsigned long long *mine = cm.mail[cm.rank];
+  const unsigned long long e = mine[MAIL_EPOCH] + 1ull;
+  mine[MAIL_EPOCH] = e;
+  for (int q = 0; q < cm.P; q++)
+    if (q != cm.rank) *((volatile unsigned long long *)(cm.mail[q] + MAIL_FLAG + cm.rank)) = e;
+  for (int q = 0; q < cm.P; q++) {
+    if (q == cm.rank) continue;
+    long long spins = 0;
+    while (mine[MAIL_FLAG + q] < e) {
+      if (++spins > SPIN_LIMIT) { mine[MAIL_ABORT] = 1ull; break; }
+    }
+  }
+  __threadfence_system();
+}
+__global__ void k_peer_barrier(CommDev cm) { if (threadIdx.x == 0 && blockIdx.x == 0) peer_sync(cm); }
+
+// Grid-wide barrier for the persistent kernels (all CTAs co-resident: cooperative launch).  The last CTA to arrive
+// runs `last()` (the NVLink epoch exchange in partitioned runs) before it releases the others.
+// HOOK variant: bar[32] = arrival count, bar[64] = generation (separate 128 B lines).
+template <bool HOOK, class F>
+__device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, F &&last)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (!HOOK) {
+      // single word: every CTA adds 1, CTA 0 adds 2^31 - (n-1), so bit 31 flips exactly when the last CTA arrives
+      // and the pollers see the release as a side effect of that last atomic (one L2 round trip less)
+      const unsigned add = blockIdx.x == 0 ? 0x80000000u - (unsigned)(nblocks - 1) : 1u;
+      __threadfence();
+      const unsigned old = atomicAdd(bar, add);
+      while ((((old ^ *((volatile unsigned *)bar)) & 0x80000000u) == 0u)) { }
+      __threadfence();
+    } else {
+      volatile unsigned *gen = bar + 64;
+      const unsigned g = *gen;
+      __threadfence();
+      if (atomicAdd(bar + 32, 1u) == (unsigned)nblocks - 1u) {
+        *((volatile unsigned *)(bar + 32)) = 0u;
+        last();
+        __threadfence();
+        *gen = g + 1u;
+      } else {
+        while (*gen == g) { }
+      }
+      __threadfence();
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ bool d_is_floating(double Hi, double Hb, double SL)
 {
   return Hi < (SL - Hb) * UFM_SEAWATER_DENSITY / UFM_ICE_DENSITY;  // general_ice_model_data_module.f90:464-475
@@ -116,6 +176,8 @@ __global__ void k_ssa_prepare(PrepArgs a)
 // One warp per slice, one thread per row, grid-stride over slices.
 // ---------------------------------------------------------------------------------------------
 struct ViscArgs {
+  CommDev cm;
+  const int *rng;
   int n_slices;
   const long long *off;
   const unsigned char *deg;
@@ -149,60 +211,68 @@ __device__ __forceinline__ void visc_row(const ViscArgs &a, const long long o, c
     if (c < n) { ux = ux + cx[c] * nb[c].x; uy = uy + cy[c] * nb[c].x; vx = vx + cx[c] * nb[c].y; vy = vy + cy[c] * nb[c].y; }
 }
 
+// One CTA (8 warps) per 256-row chunk, chunks of this rank's six block ranges taken grid-stride.  The two sums are
+// reduced per chunk in a fixed order and stored at partials[chunk] (and pushed to the peers of a partitioned run), so
+// the final fixed-shape tree over ALL chunks gives the same bits for any number of GPUs.
 template <bool STORE_GRAD>
 __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
 {
-  const int lane = threadIdx.x & 31;
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  double s_dn = 0.0, s_n = 0.0;
-  for (int s = wg; s < a.n_slices; s += nw) {
-    const long long o = a.off[s];
-    const int w = (int)((a.off[s + 1] - o) >> 5);
-    const int p = s * 32 + lane;
-    const int n = a.deg[p];
-    if (n == UFM_DEG_PAD) continue;
-    double ux, uy, vx, vy;
-    switch (w) {
-      case 2: visc_row<2>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 3: visc_row<3>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 4: visc_row<4>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 5: visc_row<5>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 6: visc_row<6>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 7: visc_row<7>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      case 8: visc_row<8>(a, o, lane, p, n, ux, uy, vx, vy); break;
-      default: {
-        const double2 u = a.UV[p];
-        ux = a.nx0[p] * u.x; uy = a.ny0[p] * u.x; vx = a.nx0[p] * u.y; vy = a.ny0[p] * u.y;
-        for (int c = 0; c < w; c++) {
-          if (c < n) {
-            const long long e = o + (long long)c * 32 + lane;
-            const double2 nb = a.UV[a.idx[e]];
-            const double cx = a.nx[e], cy = a.ny[e];
-            ux = ux + cx * nb.x; uy = uy + cy * nb.x;
-            vx = vx + cx * nb.y; vy = vy + cy * nb.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double sh[2][8];
+  for (int b = 0; b < 6; b++) {
+    const int c0 = a.rng[(b * a.cm.P + a.cm.rank) * 2] >> 3, c1 = (a.rng[(b * a.cm.P + a.cm.rank) * 2 + 1] + 7) >> 3;
+    for (int ch = c0 + blockIdx.x; ch < c1; ch += gridDim.x) {
+      const int s = ch * 8 + warp;
+      const long long o = a.off[s];
+      const int w = (int)((a.off[s + 1] - o) >> 5);
+      const int p = s * 32 + lane;
+      const int n = a.deg[p];
+      double s_dn = 0.0, s_n = 0.0;
+      if (n != UFM_DEG_PAD) {
+        double ux, uy, vx, vy;
+        switch (w) {
+          case 2: visc_row<2>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 3: visc_row<3>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 4: visc_row<4>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 5: visc_row<5>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 6: visc_row<6>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 7: visc_row<7>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          case 8: visc_row<8>(a, o, lane, p, n, ux, uy, vx, vy); break;
+          default: {
+            const double2 u = a.UV[p];
+            ux = a.nx0[p] * u.x; uy = a.ny0[p] * u.x; vx = a.nx0[p] * u.y; vy = a.ny0[p] * u.y;
+            for (int c = 0; c < w; c++) {
+              if (c < n) {
+                const long long e = o + (long long)c * 32 + lane;
+                const double2 nb = a.UV[a.idx[e]];
+                const double cx = a.nx[e], cy = a.ny[e];
+                ux = ux + cx * nb.x; uy = uy + cy * nb.x;
+                vx = vx + cx * nb.y; vy = vy + cy * nb.y;
+              }
+            }
           }
         }
+        if (STORE_GRAD) { a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy); }
+        else {
+          const double epsilon_sq_0 = 1E-12;
+          const double eta = a.visc_A * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
+          const double Nn = eta * a.Hm[p];
+          const double dn = Nn - a.N[p];
+          s_dn = dn * dn; s_n = Nn * Nn;
+          a.eta[p] = eta; a.N[p] = Nn;
+        }
       }
+      if (STORE_GRAD) continue;
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { s_dn += __shfl_xor_sync(0xffffffffu, s_dn, o2); s_n += __shfl_xor_sync(0xffffffffu, s_n, o2); }
+      if (lane == 0) { sh[0][warp] = s_dn; sh[1][warp] = s_n; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = 0; k < 8; k++) { t0 += sh[0][k]; t1 += sh[1][k]; }
+        for (int q = 0; q < a.cm.P; q++) { a.cm.partials[q][2 * ch] = t0; a.cm.partials[q][2 * ch + 1] = t1; }
+      }
+      __syncthreads();
     }
-    if (STORE_GRAD) { a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy); continue; }
-    const double epsilon_sq_0 = 1E-12;
-    double eta = a.visc_A * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
-    double Nn = eta * a.Hm[p];
-    double dn = Nn - a.N[p];
-    s_dn = s_dn + dn * dn;
-    s_n = s_n + Nn * Nn;
-    a.eta[p] = eta; a.N[p] = Nn;
-  }
-  if (STORE_GRAD) return;
-  // deterministic block reduction (fixed tree), one partial pair per block
-  __shared__ double sh[2][8];
-  for (int o = 16; o > 0; o >>= 1) { s_dn += __shfl_xor_sync(0xffffffffu, s_dn, o); s_n += __shfl_xor_sync(0xffffffffu, s_n, o); }
-  if (lane == 0) { sh[0][threadIdx.x >> 5] = s_dn; sh[1][threadIdx.x >> 5] = s_n; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { t0 += sh[0][k]; t1 += sh[1][k]; }
-    a.partials[2 * blockIdx.x] = t0; a.partials[2 * blockIdx.x + 1] = t1;
   }
 }
 // fixed-shape tree over the per-block partials: deterministic for a given grid size
@@ -224,7 +294,8 @@ __global__ void k_sum_partials(int n, const double *partials, double *out2)
 // SSA_sliding_term (:727-779) fused with the RHS / centre coefficients of solve_SSA_linearised (:581-596)
 // ---------------------------------------------------------------------------------------------
 struct SetupArgs {
-  int Mp;
+  int Mp, P, rank;
+  const unsigned char *sowner;
   const unsigned char *deg, *mflag;
   const double2 *UV, *rhsnum;
   const double *tau_c, *eta, *Hm, *cU0, *cV0;
@@ -236,6 +307,7 @@ __global__ void k_ssa_setup(SetupArgs a)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Mp || a.deg[p] == UFM_DEG_PAD) return;
+  if (a.P > 1 && a.sowner[p >> 5] != a.rank) return;
   const double delta_v = 1E-3, q_plastic = 0.30;
   const double2 u = a.UV[p];
   const double eta = a.eta[p];
@@ -264,14 +336,16 @@ __global__ void k_ssa_setup(SetupArgs a)
 #define SOR_MIN_BLOCKS 1
 #endif
 struct SorArgs {
+  CommDev cm;
   const long long *off;
-  const unsigned char *deg, *mflag;
+  const unsigned char *deg, *mflag, *xmask;
   const int *idx;
   const double *cU, *cV, *nxy, *nxy0, *nxysum;
   const double2 *E, *RHS;
   double2 *UV;
-  const int *col;   // [10] slice ranges: begin of colour c at col[c], end at col[5+c]   (device memory: indexed dynamically)
-  int n_bc;
+  const int *rng;   // slice range of block b, rank r at rng[(b*P + r)*2 + {0,1}]   (device memory: indexed dynamically)
+  int bc_begin, bc_end;      // this rank's Neumann rows
+  int corner_mask;           // bit k: corner k is owned by this rank
   const int *bc_pos, *bc_ptr, *bc_nbr;
   const int *corner;  // [8] corner_pos[4], corner_n[4]
   const int *corner_nbr, *corner_row;
@@ -290,11 +364,26 @@ __device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
   return make_double2(su / nv, sv / nv);
 }
 
+// store a freshly updated row and, in a partitioned run, push it over NVLink into the (U,V) array of every rank
+// that reads it (same row index on every rank: the layout is replicated, only the work is partitioned)
+template <bool MULTI>
+__device__ __forceinline__ void store_row(const SorArgs &a, const int p, const double2 v)
+{
+  a.UV[p] = v;
+  if (MULTI) {
+    const unsigned xm = a.xmask[p];
+    if (xm) {
+      for (int q = 0; q < a.cm.P; q++) if ((xm >> q) & 1u) a.cm.uv[q][p] = v;
+      __threadfence_system();
+    }
+  }
+}
+
 // One SOR update of row p (ice_dynamics_module.f90:633-659).  W = slice width (compile time, so every index,
 // coefficient and neighbour load of the row is issued before the first use: ~4W independent loads in flight per
 // thread, which is what makes the sweep bandwidth- rather than latency-bound); n = row degree (<= W; the
 // padding entries of a mixed-degree slice point at the home row with zero coefficients and are not accumulated).
-template <int W, bool EXACT>
+template <int W, bool EXACT, bool MULTI>
 __device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, const int lane, const int p, const int n, double tmax)
 {
   int j[W];
@@ -327,18 +416,26 @@ __device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, c
   const double resV = (LHSy - r2.y) / e2.y;
   tmax = fmax(tmax, fabs(resU));
   tmax = fmax(tmax, fabs(resV));
-  a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
+  store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
   return tmax;
 }
 
-template <bool EXACT, bool GLFIX>
+// ctrl[0..2]  rotating max-residual slots (bit pattern of a non-negative double; integer order = fp order)
+// ctrl[8]     iterations executed     ctrl[9] bit0 did_reset, bit1 warning (hit max_inner), bit2 peer wait timed out
+// ctrl[10]    last max residual (bits)   ctrl[32] grid barrier {count, generation}
+template <bool EXACT, bool GLFIX, bool MULTI>
 __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a)
 {
-  cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int nblocks = gridDim.x, P = MULTI ? a.cm.P : 1, rank = MULTI ? a.cm.rank : 0;
+  unsigned *bar = (unsigned *)(a.ctrl + 32);
+  volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
   __shared__ double sh[SOR_BLOCK / 32];
+  __shared__ int s_rng[10];   // this rank's slice ranges of the five colours (read once)
+  if (threadIdx.x < 10) s_rng[threadIdx.x] = a.rng[((threadIdx.x >> 1) * P + rank) * 2 + (threadIdx.x & 1)];
+  __syncthreads();
   int it = 0;
   bool done = false;
   unsigned flags = 0;
@@ -348,8 +445,8 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
     if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
     double tmax = 0.0;
     for (int c = 0; c < 5; c++) {
-      const int s_end = a.col[5 + c];
-      for (int s = a.col[c] + wg; s < s_end; s += nw) {
+      const int s_end = s_rng[2 * c + 1];
+      for (int s = s_rng[2 * c] + wg; s < s_end; s += nw) {
         const long long o = a.off[s];
         const int w = (int)((a.off[s + 1] - o) >> 5);
         const int p = s * 32 + lane;
@@ -357,12 +454,12 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
         if (n == UFM_DEG_PAD) continue;
         if (GLFIX) { if (a.mflag[p] & 2) continue; }
         switch (w) {  // warp-uniform
-          case 3: tmax = sor_row<3, EXACT>(a, o, lane, p, n, tmax); break;
-          case 4: tmax = sor_row<4, EXACT>(a, o, lane, p, n, tmax); break;
-          case 5: tmax = sor_row<5, EXACT>(a, o, lane, p, n, tmax); break;
-          case 6: tmax = sor_row<6, EXACT>(a, o, lane, p, n, tmax); break;
-          case 7: tmax = sor_row<7, EXACT>(a, o, lane, p, n, tmax); break;
-          case 8: tmax = sor_row<8, EXACT>(a, o, lane, p, n, tmax); break;
+          case 3: tmax = sor_row<3, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
+          case 4: tmax = sor_row<4, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
+          case 5: tmax = sor_row<5, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
+          case 6: tmax = sor_row<6, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
+          case 7: tmax = sor_row<7, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
+          case 8: tmax = sor_row<8, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
           default: {  // rare high-degree rows: generic path with the same accumulation order
             const double2 u = a.UV[p];
             const double h = EXACT ? a.nxy0[p] : a.nxysum[p];
@@ -383,7 +480,7 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
             const double resV = (LHSy - r2.y) / e2.y;
             tmax = fmax(tmax, fabs(resU));
             tmax = fmax(tmax, fabs(resV));
-            a.UV[p] = make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
+            store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
           }
         }
       }
@@ -397,27 +494,46 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
           atomicMax(a.ctrl + (it % 3), (unsigned long long)__double_as_longlong(m));
         }
       }
-      grid.sync();
+      // end of colour phase: grid barrier; in a partitioned run the last CTA exchanges epochs with the peers
+      // (and, after the fifth colour, this rank's max residual: the MPI_ALLREDUCE MAX of :673)
+      grid_barrier<MULTI>(bar, nblocks, [&]() {
+        if (MULTI) {
+          if (c == 4) {
+            const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
+            for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
+          }
+          peer_sync(a.cm);
+        }
+      });
     }
     // apply_Neumann_boundary_AaAc on U and V (mesh_ArakawaC_module.f90:660-724): edge rows from their
     // non-edge neighbours; the four corners from all neighbours, edge neighbours taken at their NEW value
     // (recomputed here from non-edge rows only, so the whole pass is one hazard-free phase).
-    for (int r = tid; r < a.n_bc + 4; r += nt) {
-      if (r < a.n_bc) a.UV[a.bc_pos[r]] = bc_mean(a, r);
+    for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
+      if (r < a.bc_end) store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r));
       else {
-        const int k = r - a.n_bc, n = a.corner[4 + k];
+        const int k = r - a.bc_end;
+        if (!((a.corner_mask >> k) & 1)) continue;
+        const int n = a.corner[4 + k];
         double su = 0.0, sv = 0.0;
         for (int q = 0; q < n; q++) {
           const int row = a.corner_row[k * 16 + q];
           const double2 v = row >= 0 ? bc_mean(a, row) : a.UV[a.corner_nbr[k * 16 + q]];
           su = su + v.x; sv = sv + v.y;
         }
-        a.UV[a.corner[k]] = make_double2(su / (double)n, sv / (double)n);
+        store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
       }
     }
-    grid.sync();
-    maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (it % 3))));
-    if (!a.force_iters) {
+    grid_barrier<MULTI>(bar, nblocks, [&]() { if (MULTI) peer_sync(a.cm); });
+    if (MULTI) {
+      unsigned long long r = 0ull;
+      for (int q = 0; q < P; q++) { const unsigned long long v = mail[MAIL_RESID + (it % 3) * UFM_MAX_RANKS + q]; r = v > r ? v : r; }
+      maxres = __longlong_as_double((long long)r);
+      if (mail[MAIL_ABORT]) { flags |= 4; done = true; }
+    } else {
+      maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (it % 3))));
+    }
+    if (!a.force_iters && !done) {
       if (maxres < a.tol) done = true;
       else if (maxres > 1E6) {
         for (int p = tid; p < a.Mp; p += nt) a.UV[p] = make_double2(0.0, 0.0);
@@ -426,6 +542,21 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
     }
   }
   if (tid == 0) { a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres); }
+}
+
+// all-gather of the final (U,V): every rank pushes its own rows to all peers (partitioned runs only)
+__global__ void k_push_uv(CommDev cm, int n_slices, const unsigned char *sowner, const unsigned char *deg, const double2 *UV)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < n_slices; s += nw) {
+    if (sowner[s] != cm.rank) continue;
+    const int p = s * 32 + lane;
+    if (deg[p] == UFM_DEG_PAD) continue;
+    const double2 v = UV[p];
+    for (int q = 0; q < cm.P; q++) if (q != cm.rank) cm.uv[q][p] = v;
+  }
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -512,14 +643,15 @@ int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   ViscArgs a;
+  a.cm = h->comm; a.rng = m.rng_dev;
   a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
   a.Hm = s.Hm; a.UV = s.UV;
   a.visc_A = pow(h->P.m_enh_ssa * 0.5 * s.A_flow_const, -1.0 / UFM_N_FLOW);
   a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
-  if (grid > 4096) grid = 4096;
   k_ssa_viscosity<false><<<grid, 256, 0, h->stream>>>(a);
-  k_sum_partials<<<1, 256, 0, h->stream>>>(grid, s.partials, s.scal);
+  if (m.P > 1) { k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm); h->cnt.kernel_launches++; }
+  k_sum_partials<<<1, 256, 0, h->stream>>>(m.n_chunks, s.partials, s.scal);
   h->cnt.kernel_launches += 2;
   UFM_CUDA(cudaMemcpyAsync(s.scal_h, s.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
@@ -534,6 +666,8 @@ int ufm_k_ssa_gradients(ufm_handle *h)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   ViscArgs a;
+  // diagnostic gradients on ALL rows (each rank's (U,V) is complete after ufm_ssa_finish): single-rank view of the ranges
+  a.cm = h->comm; a.cm.P = 1; a.cm.rank = 0; a.rng = m.rng_all_dev;
   a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
   a.Hm = s.Hm; a.UV = s.UV; a.visc_A = 0.0; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
@@ -546,7 +680,7 @@ int ufm_k_ssa_sliding_setup(ufm_handle *h)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   SetupArgs a;
-  a.Mp = m.Mp; a.deg = m.m.deg; a.mflag = s.mflag; a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.eta = s.eta; a.Hm = s.Hm;
+  a.Mp = m.Mp; a.P = m.P; a.rank = m.rank; a.sowner = m.m_sowner; a.deg = m.m.deg; a.mflag = s.mflag; a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.eta = s.eta; a.Hm = s.Hm;
   a.cU0 = m.m_cU0; a.cV0 = m.m_cV0; a.thr = pow(100.0, 0.30); a.S = s.S; a.RHS = s.RHS; a.E = s.E;
   k_ssa_setup<<<grid_for(m.Mp, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;
@@ -556,9 +690,13 @@ int ufm_k_ssa_sliding_setup(ufm_handle *h)
 typedef void (*sor_kernel_t)(SorArgs);
 static sor_kernel_t pick_sor(const ufm_handle *h)
 {
-  const bool ex = h->P.exact_xy != 0, gl = h->P.use_analytical_GL_flux != 0;
-  if (ex) return gl ? k_ssa_sor<true, true> : k_ssa_sor<true, false>;
-  return gl ? k_ssa_sor<false, true> : k_ssa_sor<false, false>;
+  const bool ex = h->P.exact_xy != 0, gl = h->P.use_analytical_GL_flux != 0, mu = h->mesh.P > 1;
+  if (mu) {
+    if (ex) return gl ? k_ssa_sor<true, true, true> : k_ssa_sor<true, false, true>;
+    return gl ? k_ssa_sor<false, true, true> : k_ssa_sor<false, false, true>;
+  }
+  if (ex) return gl ? k_ssa_sor<true, true, false> : k_ssa_sor<true, false, false>;
+  return gl ? k_ssa_sor<false, true, false> : k_ssa_sor<false, false, false>;
 }
 
 int ufm_sor_configure(ufm_handle *h)
@@ -575,11 +713,16 @@ int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *
   DevMesh &m = h->mesh; DevState &s = h->st;
   int rc = ufm_sor_configure(h);
   if (rc) return rc;
+  if (m.P > 1 && !h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
   SorArgs a;
+  a.cm = h->comm; a.xmask = m.m_xmask; a.rng = m.rng_dev;
+  a.bc_begin = m.bc_rng[m.rank]; a.bc_end = m.bc_rng[m.rank + 1];
+  a.corner_mask = 0;
+  for (int k = 0; k < 4; k++) if (m.corner_owner[k] == m.rank) a.corner_mask |= 1 << k;
   a.off = m.m.off; a.deg = m.m.deg; a.mflag = s.mflag; a.idx = m.m_idx; a.cU = m.m_cU; a.cV = m.m_cV; a.nxy = m.m_nxy; a.nxy0 = m.m_nxy0;
   a.nxysum = m.m_nxysum; a.E = s.E; a.RHS = s.RHS; a.UV = s.UV;
-  a.col = m.col_dev; a.corner = m.corner_dev;
-  a.n_bc = m.n_bc; a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
+  a.corner = m.corner_dev;
+  a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
   a.corner_nbr = m.corner_nbr; a.corner_row = m.corner_row;
   a.Mp = m.Mp; a.max_inner = max_inner; a.force_iters = force_iters; a.omega = h->P.SSA_SOR_omega; a.tol = h->P.SSA_max_residual_UV;
   a.ctrl = s.ctrl;
@@ -598,6 +741,7 @@ int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *
     st->n_inner_last = (int)res[0];
     st->did_reset = (int)(res[1] & 1);
     st->rc = (res[1] & 2) ? 1 : 0;
+    if (res[1] & 4) return ufm_set_error(-7, "SOR: wait for a peer GPU timed out (partitioned run)");
     double r;
     memcpy(&r, &res[2], sizeof(r));
     st->last_max_residual = r;
@@ -609,6 +753,12 @@ int ufm_k_ssa_finish(ufm_handle *h)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   int n = m.nV > m.nAc ? m.nV : m.nAc;
+  if (m.P > 1) {
+    if (!h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
+    k_push_uv<<<h->num_sms * 4, 256, 0, h->stream>>>(h->comm, m.m.n_slices, m.m_sowner, m.m.deg, s.UV);
+    k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm);
+    h->cnt.kernel_launches += 2;
+  }
   k_ssa_finish<<<grid_for(n, 256), 256, 0, h->stream>>>(m.nV, m.nAc, m.aa2m, m.ac2m, s.UV, m.ac_Dx, m.ac_Dy, s.U_SSA, s.V_SSA,
                                                         s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3]);
   h->cnt.kernel_launches++;

@@ -79,19 +79,20 @@ void free_ptr(void *p) { if (p) cudaFree(p); }
 
 int ufm_mesh_free_impl(ufm_handle *h)
 {
+  ufm_comm_reset(h);
   DevMesh &m = h->mesh;
   DevState &s = h->st;
   void *mp[] = {m.aa_ref2dev, m.aa_dev2ref, m.ac_ref2dev, m.ac_dev2ref, m.m_ref2dev, m.m_dev2ref, m.aa.off, m.aa.deg, m.aa_C, m.aa_iAci,
                 m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0, m.aa_A, m.aa_sqrtApi, m.aa_edge, m.ac_Aci, m.ac_Np, m.ac_Cw, m.ac_Dx, m.ac_Dy,
                 m.m.off, m.m.deg, m.m_idx, m.m_cU, m.m_cV, m.m_nxy, m.m_nx, m.m_ny, m.m_nxy0, m.m_nxysum, m.m_nx0, m.m_ny0, m.m_cU0,
-                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.col_dev, m.corner_dev, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row};
+                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.rng_dev, m.rng_all_dev, m.corner_dev, m.m_xmask, m.m_sowner, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row};
   for (void *p : mp) free_ptr(p);
   for (int k = 0; k < 4; k++) { free_ptr(m.ac_Nx[k]); free_ptr(m.ac_Ny[k]); free_ptr(m.ac_No[k]); }
   void *sp[] = {s.Hi, s.Hi_alt, s.Hb, s.SL, s.Hs, s.dHb_dt, s.dHi_dt, s.dHs_dt, s.dHi_dx, s.dHi_dy, s.dHs_dx, s.dHs_dy, s.dHs_dx_shelf,
                 s.dHs_dy_shelf, s.U_SIA, s.V_SIA, s.D_SIA, s.U_SSA, s.V_SSA, s.SMB_year, s.BMB, s.thk_factor, s.thk_smb, s.U_3D, s.V_3D,
                 s.mask_noice, s.mbits, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
                 s.Qabs_GL_Ac, s.Qp_GL_Ac, s.mbits_Ac, s.UV, s.RHS, s.E, s.rhsnum, s.dU, s.dV, s.eta, s.N, s.S, s.tau_c, s.phi, s.Hm,
-                s.mflag, s.partials, s.ctrl, s.scal};
+                s.mflag, s.partials, s.ctrl, s.scal, s.mail};
   for (void *p : sp) free_ptr(p);
   for (int k = 0; k < 4; k++) { free_ptr(s.dHi_Ac[k]); free_ptr(s.dHb_Ac[k]); free_ptr(s.dHs_Ac[k]); free_ptr(s.dSL_Ac[k]); free_ptr(s.U_SIA_Ac[k]); free_ptr(s.U_SSA_Ac[k]); }
   if (s.scal_h) cudaFreeHost(s.scal_h);
@@ -164,31 +165,46 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       if (ac < 1 || ac > M) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
       if (colour[ac - 1] == colour[ai]) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", ai + 1, ac);
     }
+  // owner rank of every AaAc row: x-strips balanced by row count (cf. partition_domain_x_balanced,
+  // src/mesh_help_functions_module.f90:1337-1404, which the reference uses for mesh generation)
+  const int P = h->part_n;
+  m.P = P; m.rank = h->part_rank;
+  std::vector<unsigned char> owner(M, 0);
+  if (P > 1) {
+    std::vector<int> byx(M);
+    std::iota(byx.begin(), byx.end(), 0);
+    std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
+    for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
+  }
   std::vector<int> m_order(M);
   std::iota(m_order.begin(), m_order.end(), 0);
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
   std::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
     int ba = blk(a), bb = blk(b);
     if (ba != bb) return ba < bb;
+    if (owner[a] != owner[b]) return owner[a] < owner[b];
     if (degv[a] != degv[b]) return degv[a] < degv[b];
     return mort[a] < mort[b];
   });
   std::vector<int> m_r2d(M), m_d2r;
-  m_d2r.reserve((size_t)M + 6 * UFM_SLICE);
+  m_d2r.reserve((size_t)M + 6 * (size_t)P * UFM_CHUNK);
   {
     int k = 0;
     for (int b = 1; b <= 6; b++) {  // blocks 1..5 = colours (swept rows), 6 = domain-edge rows
-      m.col_begin[b - 1] = (int)(m_d2r.size() / UFM_SLICE);
-      while (k < M && blk(m_order[k]) == b) {
-        m_r2d[m_order[k]] = (int)m_d2r.size();
-        m_d2r.push_back(m_order[k]);
-        k++;
+      for (int r = 0; r < P; r++) {
+        m.rng[b - 1][r][0] = (int)(m_d2r.size() / UFM_SLICE);
+        while (k < M && blk(m_order[k]) == b && owner[m_order[k]] == r) {
+          m_r2d[m_order[k]] = (int)m_d2r.size();
+          m_d2r.push_back(m_order[k]);
+          k++;
+        }
+        m.rng[b - 1][r][1] = (int)((m_d2r.size() + UFM_SLICE - 1) / UFM_SLICE);
+        while (m_d2r.size() % UFM_CHUNK) m_d2r.push_back(-1);
       }
-      while (m_d2r.size() % UFM_SLICE) m_d2r.push_back(-1);
-      m.col_end[b - 1] = (int)(m_d2r.size() / UFM_SLICE);
     }
   }
   m.Mp = (int)m_d2r.size();
+  m.n_chunks = m.Mp / UFM_CHUNK;
 
   // ---- AaAc sliced ELL ----
   {
@@ -234,6 +250,24 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       }
     }
     m.sor_bytes = bytes;
+    // who reads whom across the partition: every row reads its neighbours (sweep, viscosity, Neumann pass); a corner row
+    // additionally reads the non-edge neighbours of its edge neighbours (it recomputes their boundary value)
+    std::vector<unsigned char> xmask(m.Mp, 0), sowner(m.m.n_slices, 0);
+    for (int ai = 0; ai < M; ai++) {
+      const int r = owner[ai];
+      for (int c = 1; c <= degv[ai]; c++) {
+        const int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
+        if (owner[ac] != r) xmask[m_r2d[ac]] |= (unsigned char)(1u << r);
+        if (ai < 4 && is_edge[ac])
+          for (int c2 = 1; c2 <= degv[ac]; c2++) {
+            const int q = F2(d->CAaAc, ac + 1, c2, ldM) - 1;
+            if (owner[q] != r) xmask[m_r2d[q]] |= (unsigned char)(1u << r);
+          }
+      }
+    }
+    for (int sl = 0; sl < m.m.n_slices; sl++)
+      for (int l = 0; l < UFM_SLICE; l++) { int ai = m_d2r[sl * UFM_SLICE + l]; if (ai >= 0) { sowner[sl] = owner[ai]; break; } }
+    UP(xmask, m.m_xmask); UP(sowner, m.m_sowner);
     UP(off, m.m.off); UP(deg, m.m.deg); UP(idx, m.m_idx); UP(cU, m.m_cU); UP(cV, m.m_cV); UP(nxy, m.m_nxy); UP(nx, m.m_nx); UP(ny, m.m_ny);
     UP(nxy0, m.m_nxy0); UP(nxysum, m.m_nxysum); UP(nx0, m.m_nx0); UP(ny0, m.m_ny0); UP(cU0, m.m_cU0); UP(cV0, m.m_cV0); UP(src, m.m_src);
     std::vector<int> aa2m(m.nVp, 0), ac2m(m.nAcp, 0);
@@ -245,17 +279,22 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // ---- Neumann boundary lists (apply_Neumann_boundary_AaAc, mesh_ArakawaC_module.f90:660-724) ----
   {
     std::vector<int> bc_pos, bc_ptr(1, 0), bc_nbr, row_of(M, -1);
-    for (int ai = 4; ai < M; ai++) {  // ai = MAX(5,..) .. in 1-based terms
-      if (!is_edge[ai]) continue;
-      row_of[ai] = (int)bc_pos.size();
-      bc_pos.push_back(m_r2d[ai]);
-      for (int c = 1; c <= degv[ai]; c++) {
-        int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
-        if (is_edge[ac]) continue;
-        bc_nbr.push_back(m_r2d[ac]);
+    for (int r = 0; r < P; r++) {
+      m.bc_rng[r] = (int)bc_pos.size();
+      for (int ai = 4; ai < M; ai++) {  // ai = MAX(5,..) .. in 1-based terms
+        if (!is_edge[ai] || owner[ai] != r) continue;
+        row_of[ai] = (int)bc_pos.size();
+        bc_pos.push_back(m_r2d[ai]);
+        for (int c = 1; c <= degv[ai]; c++) {
+          int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
+          if (is_edge[ac]) continue;
+          bc_nbr.push_back(m_r2d[ac]);
+        }
+        bc_ptr.push_back((int)bc_nbr.size());
       }
-      bc_ptr.push_back((int)bc_nbr.size());
     }
+    m.bc_rng[P] = (int)bc_pos.size();
+    for (int k = 0; k < 4; k++) m.corner_owner[k] = owner[k];
     m.n_bc = (int)bc_pos.size();
     std::vector<int> cn(4 * 16, 0), cr(4 * 16, -1);
     for (int k = 0; k < 4; k++) {
@@ -270,10 +309,12 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         if (ac < 4) return ufm_set_error(-2, "ufm_mesh_upload: corner vertices adjacent on the AaAc mesh");
       }
     }
-    std::vector<int> colv(10), cornv(8);
-    for (int c = 0; c < 5; c++) { colv[c] = m.col_begin[c]; colv[5 + c] = m.col_end[c]; }
+    std::vector<int> rngv((size_t)6 * P * 2), cornv(8);
+    for (int b = 0; b < 6; b++) for (int r = 0; r < P; r++) { rngv[((size_t)b * P + r) * 2] = m.rng[b][r][0]; rngv[((size_t)b * P + r) * 2 + 1] = m.rng[b][r][1]; }
     for (int k = 0; k < 4; k++) { cornv[k] = m.corner_pos[k]; cornv[4 + k] = m.corner_n[k]; }
-    UP(colv, m.col_dev); UP(cornv, m.corner_dev);
+    std::vector<int> rnga(12);
+    for (int b = 0; b < 6; b++) { rnga[2 * b] = m.rng[b][0][0]; rnga[2 * b + 1] = (b < 5 ? m.rng[b + 1][0][0] : m.Mp / UFM_SLICE); }
+    UP(rngv, m.rng_dev); UP(rnga, m.rng_all_dev); UP(cornv, m.corner_dev);
     UP(bc_pos, m.bc_pos); UP(bc_ptr, m.bc_ptr); UP(bc_nbr, m.bc_nbr); UP(cn, m.corner_nbr); UP(cr, m.corner_row);
   }
 
@@ -361,7 +402,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   ZE(na, s.mbits_Ac);
   ZE(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
-  ZE(2 * 4096, s.partials); ZE(64, s.ctrl); ZE(64, s.scal);
+  ZE(2 * (size_t)m.n_chunks + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(MAIL_WORDS, s.mail);
   UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
 
   // staging for permuted upload/download of one field
@@ -374,6 +415,11 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     h->staging_bytes = h->dev_staging_bytes = need;
   }
   h->has_mesh = true;
+  // single-GPU view of the peer tables: this rank only
+  memset(&h->comm, 0, sizeof(h->comm));
+  h->comm.P = m.P; h->comm.rank = m.rank;
+  h->comm.uv[m.rank] = s.UV; h->comm.partials[m.rank] = s.partials; h->comm.mail[m.rank] = s.mail;
+  h->comm_connected = false;
   h->cnt.sor_bytes_per_iteration = m.sor_bytes;
   return ufm_sor_configure(h);
 }
