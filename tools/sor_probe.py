@@ -25,9 +25,17 @@ def main():
     from ufemism_b200.capi import IceModelGPU
 
     c = S.CONFIG3
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = M.square_mesh_with_nv(c["half_width"], a.nv, order=a.order)
     st = S.state_ssa_icestream(m, Hb=c["Hb"], H_shelf=c["H_shelf"])
-    g = IceModelGPU(m, benchmark=st["benchmark"], use_analytical_GL_flux=1, exact_xy=a.exact_xy)
+    g = IceModelGPU(m, benchmark=st["benchmark"], device=local, rank=rank, nranks=world, use_analytical_GL_flux=1, exact_xy=a.exact_xy)
+    if world > 1:
+        g.connect(dist, device=torch.device("cuda", local))
     for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
         g.upload(k, st[k])
     g.update_general_ice_model_data(0.0)
@@ -40,7 +48,7 @@ def main():
         cn = g.counters()
         res.append(cn.sor_ms * 1e3 / cn.sor_iterations)
     cn = g.counters()
-    out = {"nV": m.nV, "M": m.nVAaAc, "exact_xy": a.exact_xy, "iters": a.iters, "us_per_iteration": res,
+    out = {"ranks": world, "nV": m.nV, "M": m.nVAaAc, "exact_xy": a.exact_xy, "iters": a.iters, "us_per_iteration": res,
            "algorithmic_GB": cn.sor_bytes_per_iteration / 1e9, "achieved_GBps_best": cn.sor_bytes_per_iteration / (min(res) * 1e-6) / 1e9}
     if a.others:
         import torch
@@ -54,7 +62,11 @@ def main():
         out["ms"] = {"geom": tm(lambda: g.update_general_ice_model_data(0.0)), "sia": tm(g.solve_SIA), "thk": tm(lambda: g.calculate_ice_thickness_change(0.0)),
                      "cfl": tm(g.determine_timesteps), "prepare": tm(g.ssa_prepare), "visc": tm(g.ssa_viscosity), "setup": tm(g.ssa_sliding_and_setup),
                      "sor_1iter_launch": tm(lambda: g.ssa_sor(max_inner=1, force_iters=True)), "finish": tm(g.ssa_finish)}
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

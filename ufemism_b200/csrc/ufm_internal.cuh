@@ -85,9 +85,9 @@ struct DevMesh {
   // vertex partition: rows of every block (colours 1..5, edge block) are grouped by owner rank, so rank r's
   // share of block b is the contiguous slice range rng[b][r] = [begin, end); x-strips balanced by row count
   int P = 1, rank = 0;
-  int rng[6][UFM_MAX_RANKS][2] = {};
-  int *rng_dev = nullptr;            // [(b*P + r)*2 + {0,1}]
-  int *rng_all_dev = nullptr;        // [b*2 + {0,1}]: whole blocks (all owners)
+  int rng[6][UFM_MAX_RANKS][3] = {};   // [begin, boundary_begin, end): interior rows first, rows that read a peer-owned row last
+  int *rng_dev = nullptr;            // [(b*P + r)*3 + {0,1,2}]
+  int *rng_all_dev = nullptr;        // [b*3 + {0,1,2}]: whole blocks (all owners)
   unsigned char *m_xmask = nullptr;  // per row: bit q set -> rank q reads this row, push new (U,V) to it
   unsigned char *m_sowner = nullptr; // per slice: owner rank
   int bc_rng[UFM_MAX_RANKS + 1] = {};  // Neumann rows grouped by owner

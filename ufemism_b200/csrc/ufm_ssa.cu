@@ -55,12 +55,17 @@ __global__ void k_peer_barrier(CommDev cm) { if (threadIdx.x == 0 && blockIdx.x 
 // Grid-wide barrier for the persistent kernels (all CTAs co-resident: cooperative launch).  The last CTA to arrive
 // runs `last()` (the NVLink epoch exchange in partitioned runs) before it releases the others.
 // HOOK variant: bar[32] = arrival count, bar[64] = generation (separate 128 B lines).
-template <bool HOOK, class F>
-__device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, F &&last)
+// MULTI variant (vertex-partitioned run): bar[32] = arrival count, bar[64] = generation (= low bits of the epoch).
+// The last CTA to arrive releases the local CTAs, then runs pre() (e.g. publishes this rank's residual), issues ONE
+// system-scope fence (cumulative over the peer pushes of all CTAs, which it has observed through the arrival atomics) and
+// signals `epoch` into the mailbox of every peer.  Nobody waits for the peers here: rows that read peer-owned rows are
+// swept last in a phase and wait_peers() is called just before them, so the NVLink latency hides behind interior work.
+template <bool MULTI, class F>
+__device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, const CommDev &cm, const unsigned long long epoch, F &&pre)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (!HOOK) {
+    if (!MULTI) {
       // single word: every CTA adds 1, CTA 0 adds 2^31 - (n-1), so bit 31 flips exactly when the last CTA arrives
       // and the pollers see the release as a side effect of that last atomic (one L2 round trip less)
       const unsigned add = blockIdx.x == 0 ? 0x80000000u - (unsigned)(nblocks - 1) : 1u;
@@ -70,20 +75,36 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, F
       __threadfence();
     } else {
       volatile unsigned *gen = bar + 64;
-      const unsigned g = *gen;
       __threadfence();
       if (atomicAdd(bar + 32, 1u) == (unsigned)nblocks - 1u) {
         *((volatile unsigned *)(bar + 32)) = 0u;
-        last();
         __threadfence();
-        *gen = g + 1u;
+        *gen = (unsigned)epoch;
+        pre();
+        __threadfence_system();
+        for (int q = 0; q < cm.P; q++)
+          if (q != cm.rank) *((volatile unsigned long long *)(cm.mail[q] + MAIL_FLAG + cm.rank)) = epoch;
       } else {
-        while (*gen == g) { }
+        while (*gen != (unsigned)epoch) { }
       }
       __threadfence();
     }
   }
   __syncthreads();
+}
+// wait (on local memory) until every peer has signalled `epoch`; called by one lane, followed by a fence that also drops
+// stale L1 lines of rows the peers have pushed
+__device__ __forceinline__ void wait_peers(const CommDev &cm, const unsigned long long epoch)
+{
+  volatile unsigned long long *mine = cm.mail[cm.rank];
+  for (int q = 0; q < cm.P; q++) {
+    if (q == cm.rank) continue;
+    long long spins = 0;
+    while (mine[MAIL_FLAG + q] < epoch) {
+      if (++spins > SPIN_LIMIT) { mine[MAIL_ABORT] = 1ull; break; }
+    }
+  }
+  __threadfence();
 }
 
 __device__ __forceinline__ bool d_is_floating(double Hi, double Hb, double SL)
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ double sh[2][8];
   for (int b = 0; b < 6; b++) {
-    const int c0 = a.rng[(b * a.cm.P + a.cm.rank) * 2] >> 3, c1 = (a.rng[(b * a.cm.P + a.cm.rank) * 2 + 1] + 7) >> 3;
+    const int c0 = a.rng[(b * a.cm.P + a.cm.rank) * 3] >> 3, c1 = (a.rng[(b * a.cm.P + a.cm.rank) * 3 + 2] + 7) >> 3;
     for (int ch = c0 + blockIdx.x; ch < c1; ch += gridDim.x) {
       const int s = ch * 8 + warp;
       const long long o = a.off[s];
@@ -373,8 +394,7 @@ __device__ __forceinline__ void store_row(const SorArgs &a, const int p, const d
   if (MULTI) {
     const unsigned xm = a.xmask[p];
     if (xm) {
-      for (int q = 0; q < a.cm.P; q++) if ((xm >> q) & 1u) a.cm.uv[q][p] = v;
-      __threadfence_system();
+      for (int q = 0; q < a.cm.P; q++) if ((xm >> q) & 1u) a.cm.uv[q][p] = v;   // made visible by the barrier's system fence
     }
   }
 }
@@ -433,20 +453,27 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
   unsigned *bar = (unsigned *)(a.ctrl + 32);
   volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
   __shared__ double sh[SOR_BLOCK / 32];
-  __shared__ int s_rng[10];   // this rank's slice ranges of the five colours (read once)
-  if (threadIdx.x < 10) s_rng[threadIdx.x] = a.rng[((threadIdx.x >> 1) * P + rank) * 2 + (threadIdx.x & 1)];
+  __shared__ int s_rng[15];   // this rank's slice ranges [begin, boundary_begin, end) of the five colours (read once)
+  if (threadIdx.x < 15) s_rng[threadIdx.x] = a.rng[((threadIdx.x / 3) * P + rank) * 3 + (threadIdx.x % 3)];
   __syncthreads();
   int it = 0;
   bool done = false;
   unsigned flags = 0;
   double maxres = 0.0;
+  unsigned long long epoch = MULTI ? mail[MAIL_EPOCH] : 0ull;   // same on every rank: all ranks run the same barriers
   while (!done && it < a.max_inner) {
     it++;
     if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
     double tmax = 0.0;
     for (int c = 0; c < 5; c++) {
-      const int s_end = s_rng[2 * c + 1];
-      for (int s = s_rng[2 * c] + wg; s < s_end; s += nw) {
+      const int s_bnd = s_rng[3 * c + 1], s_end = s_rng[3 * c + 2];
+      bool waited = !MULTI;
+      for (int s = s_rng[3 * c] + wg; s < s_end; s += nw) {
+        if (MULTI && !waited && s >= s_bnd) {  // first boundary slice of this warp: the peers' previous phase must have landed
+          if (lane == 0) wait_peers(a.cm, epoch);
+          __syncwarp();
+          waited = true;
+        }
         const long long o = a.off[s];
         const int w = (int)((a.off[s + 1] - o) >> 5);
         const int p = s * 32 + lane;
@@ -496,19 +523,21 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
       }
       // end of colour phase: grid barrier; in a partitioned run the last CTA exchanges epochs with the peers
       // (and, after the fifth colour, this rank's max residual: the MPI_ALLREDUCE MAX of :673)
-      grid_barrier<MULTI>(bar, nblocks, [&]() {
-        if (MULTI) {
-          if (c == 4) {
-            const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
-            for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
-          }
-          peer_sync(a.cm);
+      ++epoch;
+      grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
+        if (MULTI && c == 4) {
+          const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
+          for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
         }
       });
     }
     // apply_Neumann_boundary_AaAc on U and V (mesh_ArakawaC_module.f90:660-724): edge rows from their
     // non-edge neighbours; the four corners from all neighbours, edge neighbours taken at their NEW value
     // (recomputed here from non-edge rows only, so the whole pass is one hazard-free phase).
+    if (MULTI) {  // the Neumann rows may read peer-owned rows of the fifth colour
+      if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+      __syncthreads();
+    }
     for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
       if (r < a.bc_end) store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r));
       else {
@@ -524,8 +553,10 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
         store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
       }
     }
-    grid_barrier<MULTI>(bar, nblocks, [&]() { if (MULTI) peer_sync(a.cm); });
+    ++epoch;
+    grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
     if (MULTI) {
+      // every rank's residual was published before it signalled the fifth-colour epoch, which wait_peers() above has seen
       unsigned long long r = 0ull;
       for (int q = 0; q < P; q++) { const unsigned long long v = mail[MAIL_RESID + (it % 3) * UFM_MAX_RANKS + q]; r = v > r ? v : r; }
       maxres = __longlong_as_double((long long)r);
@@ -540,6 +571,11 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
         flags |= 1; done = true;
       } else if (it == a.max_inner) flags |= 2;
     }
+  }
+  if (MULTI) {  // leave only when every peer push of this solve has landed in our (U,V)
+    if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+    __syncthreads();
+    if (tid == 0) mail[MAIL_EPOCH] = epoch;
   }
   if (tid == 0) { a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres); }
 }

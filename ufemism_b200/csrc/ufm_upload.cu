@@ -176,6 +176,13 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
     for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
   }
+  // rows that read a row owned by another rank ("boundary" rows of the partition) are swept last in every phase, so
+  // that the wait for the peers' pushes of the previous phase hides behind the interior rows
+  std::vector<unsigned char> isb(M, 0);
+  if (P > 1)
+    for (int ai = 0; ai < M; ai++)
+      for (int c = 1; c <= degv[ai]; c++)
+        if (owner[F2(d->CAaAc, ai + 1, c, ldM) - 1] != owner[ai]) { isb[ai] = 1; break; }
   std::vector<int> m_order(M);
   std::iota(m_order.begin(), m_order.end(), 0);
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
@@ -183,23 +190,27 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     int ba = blk(a), bb = blk(b);
     if (ba != bb) return ba < bb;
     if (owner[a] != owner[b]) return owner[a] < owner[b];
+    if (isb[a] != isb[b]) return isb[a] < isb[b];
     if (degv[a] != degv[b]) return degv[a] < degv[b];
     return mort[a] < mort[b];
   });
   std::vector<int> m_r2d(M), m_d2r;
-  m_d2r.reserve((size_t)M + 6 * (size_t)P * UFM_CHUNK);
+  m_d2r.reserve((size_t)M + 12 * (size_t)P * UFM_CHUNK);
   {
     int k = 0;
     for (int b = 1; b <= 6; b++) {  // blocks 1..5 = colours (swept rows), 6 = domain-edge rows
       for (int r = 0; r < P; r++) {
         m.rng[b - 1][r][0] = (int)(m_d2r.size() / UFM_SLICE);
-        while (k < M && blk(m_order[k]) == b && owner[m_order[k]] == r) {
-          m_r2d[m_order[k]] = (int)m_d2r.size();
-          m_d2r.push_back(m_order[k]);
-          k++;
+        for (int bd = 0; bd < 2; bd++) {
+          if (bd == 1) m.rng[b - 1][r][1] = (int)(m_d2r.size() / UFM_SLICE);
+          while (k < M && blk(m_order[k]) == b && owner[m_order[k]] == r && isb[m_order[k]] == bd) {
+            m_r2d[m_order[k]] = (int)m_d2r.size();
+            m_d2r.push_back(m_order[k]);
+            k++;
+          }
+          if (bd == 1) m.rng[b - 1][r][2] = (int)((m_d2r.size() + UFM_SLICE - 1) / UFM_SLICE);
+          while (m_d2r.size() % UFM_CHUNK) m_d2r.push_back(-1);
         }
-        m.rng[b - 1][r][1] = (int)((m_d2r.size() + UFM_SLICE - 1) / UFM_SLICE);
-        while (m_d2r.size() % UFM_CHUNK) m_d2r.push_back(-1);
       }
     }
   }
@@ -309,11 +320,11 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         if (ac < 4) return ufm_set_error(-2, "ufm_mesh_upload: corner vertices adjacent on the AaAc mesh");
       }
     }
-    std::vector<int> rngv((size_t)6 * P * 2), cornv(8);
-    for (int b = 0; b < 6; b++) for (int r = 0; r < P; r++) { rngv[((size_t)b * P + r) * 2] = m.rng[b][r][0]; rngv[((size_t)b * P + r) * 2 + 1] = m.rng[b][r][1]; }
+    std::vector<int> rngv((size_t)6 * P * 3), cornv(8);
+    for (int b = 0; b < 6; b++) for (int r = 0; r < P; r++) for (int q = 0; q < 3; q++) rngv[((size_t)b * P + r) * 3 + q] = m.rng[b][r][q];
     for (int k = 0; k < 4; k++) { cornv[k] = m.corner_pos[k]; cornv[4 + k] = m.corner_n[k]; }
-    std::vector<int> rnga(12);
-    for (int b = 0; b < 6; b++) { rnga[2 * b] = m.rng[b][0][0]; rnga[2 * b + 1] = (b < 5 ? m.rng[b + 1][0][0] : m.Mp / UFM_SLICE); }
+    std::vector<int> rnga(18);
+    for (int b = 0; b < 6; b++) { rnga[3 * b] = m.rng[b][0][0]; rnga[3 * b + 1] = rnga[3 * b + 2] = (b < 5 ? m.rng[b + 1][0][0] : m.Mp / UFM_SLICE); }
     UP(rngv, m.rng_dev); UP(rnga, m.rng_all_dev); UP(cornv, m.corner_dev);
     UP(bc_pos, m.bc_pos); UP(bc_ptr, m.bc_ptr); UP(bc_nbr, m.bc_nbr); UP(cn, m.corner_nbr); UP(cr, m.corner_row);
   }
