@@ -165,6 +165,8 @@ int ufm_mesh_free(ufm_handle *h);
 #define UFM_MAX_RANKS 8
 #define UFM_COMM_BLOB_BYTES 256
 int ufm_partition_set(ufm_handle *h, int rank, int nranks);
+/* host-only: owner rank (0..nranks-1) of each of the nV+nAc combined-mesh vertices, as ufm_mesh_upload will assign them */
+int ufm_partition_owners(const ufm_mesh_desc *mesh, int nranks, unsigned char *owner_out);
 int ufm_comm_export(ufm_handle *h, void *blob /* UFM_COMM_BLOB_BYTES */);
 int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_BYTES, in rank order */);
 

@@ -263,3 +263,21 @@ def test_mesh_reupload_and_errors(mesh_2k):
     b2.colour_vi[0, 0] = col[bad.colour_nV[cn - 1] - 1, cn - 1]; b2.colour_vi[bad.colour_nV[cn - 1] - 1, cn - 1] = a
     with pytest.raises(UfmError):
         g.upload_mesh(b2)
+
+
+def test_partitioned_multi_gpu_matches_single_gpu():
+    """vertex-partitioned solve over NVLink == single-GPU solve, bit for bit (needs >= 2 GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

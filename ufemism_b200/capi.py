@@ -103,7 +103,7 @@ for _n, _i in FIELD_IDS.items():
     _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
 
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
-            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
+            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
@@ -127,6 +127,7 @@ def load_library():
         L.ufm_mesh_upload.argtypes = [p, p]
         L.ufm_mesh_free.argtypes = [p]
         L.ufm_partition_set.argtypes = [p, i, i]
+        L.ufm_partition_owners.argtypes = [p, i, p]
         L.ufm_comm_export.argtypes = [p, p]
         L.ufm_comm_connect.argtypes = [p, p]
         L.ufm_state_upload.argtypes = [p, i, p]
@@ -172,6 +173,49 @@ def default_params(benchmark="Halfar", **kw) -> Params:
     return P
 
 
+def mesh_desc(mesh):
+    """ufm_mesh_desc over the Fortran-ordered arrays of a Mesh; returns (desc, keepalive)."""
+    d = MeshDesc(nV=mesh.nV, nAc=mesh.nAc, nC_mem=mesh.nC_mem, ldV=mesh.nV, ldAc=mesh.nAc, ldAaAc=mesh.nVAaAc)
+    keep = []
+    for n in _MESH_PTRS:
+        a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
+        keep.append(a)
+        setattr(d, n, a.ctypes.data)
+    return d, keep
+
+
+def partition_owners(mesh, nranks):
+    """Owner rank of every AaAc vertex (reference order) in an nranks-way vertex partition (host-only call)."""
+    L = load_library()
+    d, keep = mesh_desc(mesh)
+    out = np.zeros(mesh.nVAaAc, np.uint8)
+    rc = L.ufm_partition_owners(ctypes.byref(d), int(nranks), out.ctypes.data)
+    if rc:
+        raise UfmError(rc, L.ufm_last_error().decode())
+    return out
+
+
+def exchange_blobs(dist, blob: bytes, nranks: int, device=None):
+    """All-gather one fixed-size byte blob per rank with torch.distributed (any backend); returns them in rank order."""
+    import torch
+
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    out = [torch.empty_like(mine) for _ in range(nranks)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+def max_over_ranks(dist, value: float, device=None) -> float:
+    """The time every multi-rank number is based on: the slowest rank's."""
+    import torch
+
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 class IceModelGPU:
     """One model region resident on one B200."""
 
@@ -208,12 +252,7 @@ class IceModelGPU:
         self._ck(self.L.ufm_set_params(self.h, ctypes.byref(self.P)))
 
     def upload_mesh(self, mesh):
-        d = MeshDesc(nV=mesh.nV, nAc=mesh.nAc, nC_mem=mesh.nC_mem, ldV=mesh.nV, ldAc=mesh.nAc, ldAaAc=mesh.nVAaAc)
-        keep = []
-        for n in _MESH_PTRS:
-            a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
-            keep.append(a)
-            setattr(d, n, a.ctypes.data)
+        d, keep = mesh_desc(mesh)
         self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
         self.mesh = mesh
 
@@ -231,14 +270,7 @@ class IceModelGPU:
 
     def connect(self, dist, device=None):
         """All-gather the IPC blobs with ``torch.distributed`` (any backend) and connect; collective."""
-        import torch
-
-        mine = torch.frombuffer(bytearray(self.comm_export()), dtype=torch.uint8)
-        if device is not None:
-            mine = mine.to(device)
-        out = [torch.empty_like(mine) for _ in range(self.nranks)]
-        dist.all_gather(out, mine)
-        self.comm_connect([bytes(t.cpu().numpy().tobytes()) for t in out])
+        self.comm_connect(exchange_blobs(dist, self.comm_export(), self.nranks, device))
         dist.barrier()
 
     def set_stream(self, cuda_stream_ptr):

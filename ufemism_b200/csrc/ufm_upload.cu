@@ -77,6 +77,33 @@ void free_ptr(void *p) { if (p) cudaFree(p); }
 
 #define F2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
 
+// owner rank of every AaAc row from its x coordinate: P strips holding equally many rows
+static void ufm_partition_owners_impl(const std::vector<double> &X, int P, std::vector<unsigned char> &owner)
+{
+  const int M = (int)X.size();
+  owner.assign(M, 0);
+  if (P <= 1) return;
+  std::vector<int> byx(M);
+  std::iota(byx.begin(), byx.end(), 0);
+  std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
+  for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
+}
+
+// host-only planning entry point (no device work): the partition ufm_mesh_upload will use
+extern "C" int ufm_partition_owners(const ufm_mesh_desc *d, int nranks, unsigned char *owner_out)
+{
+  if (!d || !d->V || !d->Aci || !owner_out) return ufm_set_error(-2, "ufm_partition_owners: NULL argument");
+  if (nranks < 1 || nranks > UFM_MAX_RANKS) return ufm_set_error(-2, "ufm_partition_owners: nranks out of range");
+  const int N = d->nV, E = d->nAc, ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E;
+  std::vector<double> X((size_t)N + E);
+  for (int v = 1; v <= N; v++) X[v - 1] = F2(d->V, v, 1, ldV);
+  for (int a = 1; a <= E; a++) X[N + a - 1] = 0.5 * (X[F2(d->Aci, a, 1, ldAc) - 1] + X[F2(d->Aci, a, 2, ldAc) - 1]);
+  std::vector<unsigned char> owner;
+  ufm_partition_owners_impl(X, nranks, owner);
+  memcpy(owner_out, owner.data(), owner.size());
+  return 0;
+}
+
 int ufm_mesh_free_impl(ufm_handle *h)
 {
   ufm_comm_reset(h);
@@ -170,12 +197,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   const int P = h->part_n;
   m.P = P; m.rank = h->part_rank;
   std::vector<unsigned char> owner(M, 0);
-  if (P > 1) {
-    std::vector<int> byx(M);
-    std::iota(byx.begin(), byx.end(), 0);
-    std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
-    for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
-  }
+  ufm_partition_owners_impl(X, P, owner);
   // rows that read a row owned by another rank ("boundary" rows of the partition) are swept last in every phase, so
   // that the wait for the peers' pushes of the previous phase hides behind the interior rows
   std::vector<unsigned char> isb(M, 0);
