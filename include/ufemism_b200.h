@@ -109,6 +109,7 @@ enum ufm_field {
   UFM_F_DU_DX_AAAC, UFM_F_DU_DY_AAAC, UFM_F_DV_DX_AAAC, UFM_F_DV_DY_AAAC,
   /* (nV,nZ) */
   UFM_F_U_3D, UFM_F_V_3D,
+  UFM_F_TI, /* englacial temperature, input of the Arrhenius flow factor when do_benchmark_experiment is .FALSE. */
   UFM_F_COUNT
 };
 
@@ -173,6 +174,11 @@ int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_
 /* ---- state: explicit, field-granular, reference vertex order ---- */
 int ufm_state_upload(ufm_handle *h, int field, const void *host);
 int ufm_state_download(ufm_handle *h, int field, void *host);
+
+/* Page-lock a host array (e.g. one of the Fortran host's MPI shared-memory windows, src/parallel_module.f90:144-160) so that
+ * ufm_state_upload / ufm_state_download DMA it directly instead of bouncing through a staging buffer.  Optional. */
+int ufm_host_register(ufm_handle *h, void *host, unsigned long long bytes);
+int ufm_host_unregister(ufm_handle *h, void *host);
 
 /* ---- the four drop-in entry points ---- */
 /* body of calculate_ice_thickness_change (src/ice_dynamics_module.f90:31-237) */

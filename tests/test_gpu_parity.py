@@ -281,3 +281,62 @@ def test_partitioned_multi_gpu_matches_single_gpu():
            "--master-port", "29531", os.path.join(root, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def _realistic_pair(mesh, nthreads=4):
+    """do_benchmark_experiment = .FALSE.: temperature-dependent (Arrhenius) flow factor, Ti uploaded by the host."""
+    st = scenario(mesh, "icestream")
+    st["benchmark"] = "none"
+    x, y = mesh.V[:, 0], mesh.V[:, 1]
+    zeta = np.array([0.00, 0.10, 0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.90, 0.925, 0.95, 0.975, 0.99, 1.00])
+    Ts = 240.0 + 15.0 * np.sin(x / 4e5) * np.cos(y / 3e5)            # surface temperature
+    Ti = Ts[:, None] + (272.0 - Ts[:, None]) * zeta[None, :] ** 2      # warming towards the bed, crosses 263.15 K
+    o, g = make_oracle(mesh, st, nthreads=nthreads), make_gpu(mesh, st)
+    o["Ti"][:] = Ti
+    g.upload("Ti", Ti)
+    return o, g
+
+
+def test_realistic_flow_factor_general_and_sia(mesh_10k):
+    o, g = _realistic_pair(mesh_10k)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    for f in AA_EXACT + AC_EXACT:
+        assert_bits_equal(g.download(f), o[f], f)
+    # exp() per layer: CUDA libm vs glibc
+    np.testing.assert_allclose(g.download("A_flow_mean"), o["A_flow_mean"], rtol=1e-13)
+    np.testing.assert_allclose(g.download("A_flow_mean_Ac"), o["A_flow_mean_Ac"], rtol=1e-13)
+    assert o["A_flow_mean"].max() / o["A_flow_mean"].min() > 3.0
+    o.solve_SIA(); g.solve_SIA()
+    for f in ["D_SIA_Ac", "Up_SIA_Ac", "Uo_SIA_Ac", "U_SIA", "D_SIA"]:
+        b = o[f]
+        np.testing.assert_allclose(g.download(f), b, rtol=1e-12, atol=1e-13 * np.abs(b).max(), err_msg=f)
+
+
+@pytest.mark.parametrize("gl_flux", [0, 1])
+def test_realistic_flow_factor_solve_SSA(mesh_10k, gl_flux):
+    o, g = _realistic_pair(mesh_10k, nthreads=8)
+    o.cfg.use_analytical_GL_flux = gl_flux
+    g.set_params(use_analytical_GL_flux=gl_flux)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert (sg.n_outer, sg.n_inner_total, sg.did_reset) == (so.n_outer, so.n_inner_total, so.did_reset)
+    for f in ("U_SSA", "V_SSA", "Up_SSA_Ac"):
+        assert rel_l2(g.download(f), o[f]) <= 1e-10, f
+    # and one thickness step on top (mass continuity with SIA + SSA velocities)
+    o.solve_SIA(); g.solve_SIA()
+    o.calculate_ice_thickness_change(0.5); g.calculate_ice_thickness_change(0.5)
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+
+
+def test_host_registered_buffers(mesh_2k):
+    st = S.state_halfar(mesh_2k)
+    g = make_gpu(mesh_2k, st)
+    a = st["Hi"].copy()
+    out = np.zeros_like(a)
+    g.host_register(a); g.host_register(out)
+    g.upload("Hi", a)           # DMA straight from the registered array
+    g.download("Hi", out)
+    assert np.array_equal(out, st["Hi"])
+    g.host_unregister(a); g.host_unregister(out)
+    g.upload("Hi", a)
+    assert np.array_equal(g.download("Hi"), st["Hi"])

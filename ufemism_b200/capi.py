@@ -96,14 +96,14 @@ for _n, _i in FIELD_IDS.items():
         kind = "AaAc"
     elif _n.endswith("_AC"):
         kind = "Ac"
-    elif _n in ("U_3D", "V_3D"):
+    elif _n in ("U_3D", "V_3D", "TI"):
         kind = "3D"
     else:
         kind = "Aa"
     _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
 
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
-            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_thickness_update", "ufm_update_general",
+            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
@@ -132,6 +132,8 @@ def load_library():
         L.ufm_comm_connect.argtypes = [p, p]
         L.ufm_state_upload.argtypes = [p, i, p]
         L.ufm_state_download.argtypes = [p, i, p]
+        L.ufm_host_register.argtypes = [p, p, ctypes.c_ulonglong]
+        L.ufm_host_unregister.argtypes = [p, p]
         L.ufm_thickness_update.argtypes = [p, d]
         L.ufm_update_general.argtypes = [p, d]
         L.ufm_solve_SIA.argtypes = [p]
@@ -289,6 +291,13 @@ class IceModelGPU:
         a = np.asfortranarray(arr, dtype=dt)
         assert a.shape == self._shape(kind), (name, a.shape, self._shape(kind))
         self._ck(self.L.ufm_state_upload(self.h, fid, a.ctypes.data))
+
+    def host_register(self, arr):
+        """Page-lock a numpy array so uploads/downloads of it are DMA'd directly."""
+        self._ck(self.L.ufm_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._ck(self.L.ufm_host_unregister(self.h, arr.ctypes.data))
 
     def download(self, name, out=None):
         fid, kind, dt = _REF_NAMES[name.upper()]

@@ -87,6 +87,7 @@ int ufm_destroy(ufm_handle *h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   ufm_mesh_free_impl(h);
+  for (int k = 0; k < h->n_pinned; k++) cudaHostUnregister(h->pinned_base[k]);
   if (h->staging) cudaFreeHost(h->staging);
   if (h->dev_staging) cudaFree(h->dev_staging);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -101,6 +102,8 @@ int ufm_set_params(ufm_handle *h, const ufm_params *params)
   int rc = check_params(params);
   if (rc) return rc;
   if (h->has_mesh && params->nZ != h->P.nZ) return ufm_set_error(-2, "ufm_set_params: nZ cannot change while a mesh is resident");
+  if (h->has_mesh && (params->benchmark == UFM_BM_NONE) != (h->P.benchmark == UFM_BM_NONE))
+    return ufm_set_error(-2, "ufm_set_params: do_benchmark_experiment cannot change while a mesh is resident");
   h->P = *params;
   derive_params(h);
   return h->has_mesh ? ufm_sor_configure(h) : 0;
@@ -235,6 +238,11 @@ static int field_ref(ufm_handle *h, int f, FieldRef *r)
     case UFM_F_DU_DX_AAAC: D2_(s.dU, 0) case UFM_F_DU_DY_AAAC: D2_(s.dU, 1) case UFM_F_DV_DX_AAAC: D2_(s.dV, 0) case UFM_F_DV_DY_AAAC: D2_(s.dV, 1)
     case UFM_F_U_3D: { r->kind = K_AA; r->d = s.U_3D; r->is3d = 1; return 0; }
     case UFM_F_V_3D: { r->kind = K_AA; r->d = s.V_3D; r->is3d = 1; return 0; }
+    case UFM_F_TI: {
+      if (!s.realistic_A) return ufm_set_error(-2, "Ti is only resident when do_benchmark_experiment is .FALSE. (benchmark flow factors do not read it)");
+      r->kind = K_AA; r->d = s.Ti; r->is3d = 1; return 0;
+    }
+    case UFM_F_A_FLOW_MEAN: D_(K_AA, s.A_mean) case UFM_F_A_FLOW_MEAN_AC: D_(K_AC, s.A_mean_Ac)
     default: break;
   }
 #undef D_
@@ -243,13 +251,20 @@ static int field_ref(ufm_handle *h, int f, FieldRef *r)
   return ufm_set_error(-2, "unknown field id %d", f);
 }
 
+static bool is_pinned(const ufm_handle *h, const void *p, size_t bytes)
+{
+  for (int k = 0; k < h->n_pinned; k++)
+    if ((const char *)p >= (const char *)h->pinned_base[k] && (const char *)p + bytes <= (const char *)h->pinned_base[k] + h->pinned_bytes[k]) return true;
+  return false;
+}
+
 static int field_copy(ufm_handle *h, int field, void *host, int to_device)
 {
   if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
   if (!host) return ufm_set_error(-2, "NULL host pointer");
   UFM_CUDA(cudaSetDevice(h->device));
   DevMesh &m = h->mesh;
-  if (field == UFM_F_A_FLOW_MEAN || field == UFM_F_A_FLOW_MEAN_AC) {
+  if ((field == UFM_F_A_FLOW_MEAN || field == UFM_F_A_FLOW_MEAN_AC) && !h->st.realistic_A) {
     // benchmark flow factor: a scalar on the device (ice_physical_properties, general_ice_model_data_module.f90:321-368)
     if (to_device) return ufm_set_error(-2, "A_flow_mean is an output");
     const int nn = field == UFM_F_A_FLOW_MEAN ? m.nV : m.nAc;
@@ -265,8 +280,9 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   if (!to_device && field >= UFM_F_DU_DX_AAAC && field <= UFM_F_DV_DY_AAAC) { if ((rc = ufm_k_ssa_gradients(h))) return rc; }
   if (to_device) {
     if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
-    memcpy(h->staging, host, bytes);
-    UFM_CUDA(cudaMemcpyAsync(h->dev_staging, h->staging, bytes, cudaMemcpyHostToDevice, h->stream));
+    const void *src = host;
+    if (!is_pinned(h, host, bytes)) { memcpy(h->staging, host, bytes); src = h->staging; }
+    UFM_CUDA(cudaMemcpyAsync(h->dev_staging, src, bytes, cudaMemcpyHostToDevice, h->stream));
     h->cnt.h2d_bytes += (double)bytes;
   }
   if (r.is3d) rc = ufm_perm_3d(h, n, h->P.nZ, m.nVp, r2d, r.d, (double *)h->dev_staging, to_device);
@@ -275,9 +291,10 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   else rc = ufm_perm_double(h, n, r2d, r.d, r.stride, r.comp, (double *)h->dev_staging, to_device);
   if (rc) return rc;
   if (!to_device) {
-    UFM_CUDA(cudaMemcpyAsync(h->staging, h->dev_staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+    const bool direct = is_pinned(h, host, bytes);
+    UFM_CUDA(cudaMemcpyAsync(direct ? host : h->staging, h->dev_staging, bytes, cudaMemcpyDeviceToHost, h->stream));
     UFM_CUDA(cudaStreamSynchronize(h->stream));
-    memcpy(host, h->staging, bytes);
+    if (!direct) memcpy(host, h->staging, bytes);
     h->cnt.d2h_bytes += (double)bytes;
   } else {
     UFM_CUDA(cudaStreamSynchronize(h->stream));  // staging buffer is reused by the next call
@@ -285,6 +302,27 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   return 0;
 }
 
+int ufm_host_register(ufm_handle *h, void *host, unsigned long long bytes)
+{
+  if (!h || !host || !bytes) return ufm_set_error(-2, "ufm_host_register: bad argument");
+  if (is_pinned(h, host, (size_t)bytes)) return 0;
+  if (h->n_pinned >= 64) return ufm_set_error(-2, "ufm_host_register: too many registered buffers");
+  UFM_CUDA(cudaSetDevice(h->device));
+  UFM_CUDA(cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable));
+  h->pinned_base[h->n_pinned] = host; h->pinned_bytes[h->n_pinned] = (size_t)bytes; h->n_pinned++;
+  return 0;
+}
+int ufm_host_unregister(ufm_handle *h, void *host)
+{
+  if (!h) return ufm_set_error(-2, "NULL handle");
+  for (int k = 0; k < h->n_pinned; k++)
+    if (h->pinned_base[k] == host) {
+      cudaHostUnregister(host);
+      h->pinned_base[k] = h->pinned_base[h->n_pinned - 1]; h->pinned_bytes[k] = h->pinned_bytes[h->n_pinned - 1]; h->n_pinned--;
+      return 0;
+    }
+  return ufm_set_error(-2, "ufm_host_unregister: pointer was not registered");
+}
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }
 

@@ -160,6 +160,72 @@ __global__ void __launch_bounds__(256) k_geom_ac(GeomAcArgs a)
   }
 }
 
+// ---- ice_physical_properties, temperature-dependent branch (general_ice_model_data_module.f90:372-462): Arrhenius flow
+//      factor per layer; the (.,nZ) arrays A_flow / A_flow_Ac / Ti_Ac are never materialised, only their vertical means ----
+struct ZetaConst { int nZ; double dz[UFM_MAX_NZ]; double z3[UFM_MAX_NZ]; };
+__device__ __forceinline__ double g_arrhenius(double Ti)
+{
+  const double A_low_temp = 1.14E-05, A_high_temp = 5.47E+10, Q_low_temp = 6.0E+04, Q_high_temp = 13.9E+04, R_gas = 8.314;
+  return (Ti < 263.15) ? A_low_temp * exp(-Q_low_temp / (R_gas * Ti)) : A_high_temp * exp(-Q_high_temp / (R_gas * Ti));
+}
+// mode 0: Aa vertices; mode 1: Ac vertices with Ti_Ac = (Ti(vi)+Ti(vj))/2 (map_Aa_to_Ac_3D, mesh_ArakawaC_module.f90:748-769)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_flow_mean(int n, int nVp, ZetaConst Z, const int4 *__restrict__ Aci, const double *__restrict__ Ti,
+                                                   const unsigned *__restrict__ mbits, double *__restrict__ A_mean)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int vi = i, vj = i;
+  if (MODE == 1) { const int4 v = Aci[i]; vi = v.x; vj = v.y; }
+  auto T = [&](int k) { return MODE == 0 ? Ti[(size_t)k * nVp + vi] : (Ti[(size_t)k * nVp + vi] + Ti[(size_t)k * nVp + vj]) / 2.0; };
+  double out;
+  if (mbits[i] & MB_SHEET) {
+    double prev = g_arrhenius(T(0)), avg = 0.0;
+    for (int k = 1; k < Z.nZ; k++) { const double cur = g_arrhenius(T(k)); avg = avg + 0.5 * (cur + prev) * Z.dz[k]; prev = cur; }
+    out = avg;
+  } else {
+    out = g_arrhenius((T(0) + UFM_SMT) / 2.0);
+  }
+  A_mean[i] = out;
+}
+
+// solve_SIA with a per-layer flow factor: f(k) = m_enh_sia * A_flow_Ac(aci,k) * zeta(k)**n, integrated in registers
+__global__ void __launch_bounds__(256) k_sia_ac_T(int nAc, int nVp, ZetaConst Z, double m_enh_sia, const int4 *__restrict__ Aci, const double *__restrict__ Ti,
+                                                  const unsigned *__restrict__ mbits_Ac, const double *__restrict__ Hi_Ac, const double *__restrict__ hx,
+                                                  const double *__restrict__ hy, const double *__restrict__ hp, const double *__restrict__ ho,
+                                                  double *__restrict__ D_SIA_Ac, double *__restrict__ Ux, double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nAc) return;
+  double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
+  if (mbits_Ac[i] & MB_SHEET) {
+    const double D_uv_3D_cutoff = -1E5;
+    const int4 v = Aci[i];
+    const double H = Hi_Ac[i], sp = hp[i], so = ho[i];
+    const double D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
+    const double twoH = 2.0 * H;
+    double I[UFM_MAX_NZ];
+    I[Z.nZ - 1] = 0.0;
+    double fk1 = m_enh_sia * g_arrhenius((Ti[(size_t)(Z.nZ - 1) * nVp + v.x] + Ti[(size_t)(Z.nZ - 1) * nVp + v.y]) / 2.0) * Z.z3[Z.nZ - 1];
+    for (int k = Z.nZ - 2; k >= 0; k--) {   // vertical_integrate, zeta_module.f90:81-84
+      const double fk = m_enh_sia * g_arrhenius((Ti[(size_t)k * nVp + v.x] + Ti[(size_t)k * nVp + v.y]) / 2.0) * Z.z3[k];
+      I[k] = I[k + 1] - 0.5 * (fk1 + fk) * Z.dz[k + 1];
+      fk1 = fk;
+    }
+    double prev = D_0 * (twoH * I[0]);
+    if (prev < D_uv_3D_cutoff) prev = D_uv_3D_cutoff;
+    double avg = 0.0;
+    for (int k = 1; k < Z.nZ; k++) {
+      double cur = D_0 * (twoH * I[k]);
+      if (cur < D_uv_3D_cutoff) cur = D_uv_3D_cutoff;
+      avg = avg + 0.5 * (cur + prev) * Z.dz[k];
+      prev = cur;
+    }
+    D = H * avg; ux = avg * hx[i]; uy = avg * hy[i]; up = avg * sp; uo = avg * so;
+  }
+  D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo;
+}
+
 // ---- solve_SIA on Ac (ice_dynamics_module.f90:240-306); the 3-D diffusivity profile stays in registers.
 //      With the benchmark (vertically constant) flow factor the integral of m_enh*A*zeta^n is the same for
 //      every column and is evaluated once on the host exactly as vertical_integrate does (zeta_module.f90:58-85). ----
@@ -408,7 +474,6 @@ int ufm_k_geom(ufm_handle *h, double time)
   DevMesh &m = h->mesh; DevState &s = h->st;
   // ice_physical_properties, benchmark branches (general_ice_model_data_module.f90:321-368)
   const int b = h->P.benchmark;
-  if (b == UFM_BM_NONE) return ufm_set_error(-4, "update_general_ice_model_data: temperature-dependent flow factor (do_benchmark_experiment = .FALSE.) is not on the device path yet");
   double A_flow = 1.0E-16;
   if (b == UFM_BM_MISMIP_MOD || b == UFM_BM_SSA_ICESTREAM) {
     if (time < 25000.0) A_flow = 1.0E-16; else if (time < 50000.0) A_flow = 1.0E-17; else if (time < 75000.0) A_flow = 1.0E-16;
@@ -428,6 +493,15 @@ int ufm_k_geom(ufm_handle *h, double time)
   ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac;
   k_geom_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(ac);
   h->cnt.kernel_launches += 3;
+  if (s.realistic_A) {
+    ZetaConst Z;
+    Z.nZ = h->P.nZ; Z.dz[0] = 0.0;
+    for (int k = 1; k < Z.nZ; k++) Z.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+    for (int k = 0; k < Z.nZ; k++) Z.z3[k] = h->zeta3[k];
+    k_flow_mean<0><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, Z, m.ac_Aci, s.Ti, s.mbits, s.A_mean);
+    k_flow_mean<1><<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.nVp, Z, m.ac_Aci, s.Ti, s.mbits_Ac, s.A_mean_Ac);
+    h->cnt.kernel_launches += 2;
+  }
   return ufm_cuda_check(cudaGetLastError(), "k_geom");
 }
 
@@ -443,6 +517,14 @@ int ufm_k_sia(ufm_handle *h)
   for (int k = K.nZ - 1; k >= 1; k--) K.I[k - 1] = K.I[k] - 0.5 * (f[k] + f[k - 1]) * (h->P.zeta[k] - h->P.zeta[k - 1]);
   K.dz[0] = 0.0;
   for (int k = 1; k < K.nZ; k++) K.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+  if (s.realistic_A) {
+    ZetaConst Z;
+    Z.nZ = h->P.nZ; Z.dz[0] = 0.0;
+    for (int k = 1; k < Z.nZ; k++) Z.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+    for (int k = 0; k < Z.nZ; k++) Z.z3[k] = h->zeta3[k];
+    k_sia_ac_T<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.nVp, Z, h->P.m_enh_sia, m.ac_Aci, s.Ti, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1],
+                                                            s.dHs_Ac[2], s.dHs_Ac[3], s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3]);
+  } else
   k_sia_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, K, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1], s.dHs_Ac[2], s.dHs_Ac[3],
                                                        s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3]);
   SiaAaArgs a;

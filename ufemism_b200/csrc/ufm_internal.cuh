@@ -110,6 +110,10 @@ struct DevState {
   double *U_SIA = nullptr, *V_SIA = nullptr, *D_SIA = nullptr, *U_SSA = nullptr, *V_SSA = nullptr, *SMB_year = nullptr, *BMB = nullptr;
   double *thk_factor = nullptr, *thk_smb = nullptr;
   double *U_3D = nullptr, *V_3D = nullptr;  // (nV,nZ) device layout k-major: [k*nVp + v]
+  double *Ti = nullptr;                     // (nV,nZ) englacial temperature, k-major (realistic flow factor only)
+  double *A_mean = nullptr, *A_mean_Ac = nullptr;  // A_flow_mean on Aa / Ac (realistic flow factor only)
+  double *Afac = nullptr;                   // (m_enh_ssa*0.5*A_flow_mean_AaAc)**(-1/n) per AaAc row (realistic only)
+  bool realistic_A = false;                 // C%do_benchmark_experiment == .FALSE.
   int *mask_noice = nullptr;
   unsigned *mbits = nullptr;
   // Ac
@@ -156,6 +160,10 @@ struct ufm_handle {
   bool comm_connected = false;
   CommDev comm;
   void *ipc_opened[3 * UFM_MAX_RANKS] = {};
+  // host buffers page-locked with ufm_host_register (base, bytes): field copies from/to them are DMA'd directly
+  void *pinned_base[64] = {};
+  size_t pinned_bytes[64] = {};
+  int n_pinned = 0;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;

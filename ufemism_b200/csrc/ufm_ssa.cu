@@ -121,7 +121,8 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
                           const double *__restrict__ dHi_dx, const double *__restrict__ dHi_dy, const double *__restrict__ dSL_dx,
                           const double *__restrict__ dSL_dy, const double *__restrict__ dHb_dx, const double *__restrict__ dHb_dy,
                           const double *__restrict__ Dx_, const double *__restrict__ Dy_, double factor_Tsai_noA,
-                          double *Qabs, double *Qp, double *Ux, double *Uy, const int *__restrict__ ac2m, double2 *UV)
+                          double *Qabs, double *Qp, double *Ux, double *Uy, const int *__restrict__ ac2m, double2 *UV,
+                          const double *__restrict__ A_mean, double tsai_c1, double tsai_c2, double tsai_c3)
 {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nAc) return;
@@ -136,6 +137,10 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
   double phi_fric_GL = (mbits[v.x] & MB_SHEET) ? phi_m[aa2m[v.x]] : phi_m[aa2m[v.y]];
   // factor_Tsai = 8 Q0 A (rho g)^n (1-rho_i/rho_w)^(n-1) / 4^n ; the A-independent part is evaluated on the host
   double factor_Tsai = A_flow * factor_Tsai_noA;
+  if (A_mean) {  // temperature-dependent flow factor of the grounded side (:894-900); factor evaluated left to right as at :906-909
+    const double A_GL = (mbits[v.x] & MB_SHEET) ? A_mean[v.x] : A_mean[v.y];
+    factor_Tsai = 8.0 * 0.61 * A_GL * tsai_c1 * tsai_c2 / tsai_c3;
+  }
   double q = factor_Tsai * pow(Hi_GL, UFM_N_FLOW + 2.0) / tan(phi_fric_GL * (UFM_PI / 180.0));
   Qabs[a] = q;
   double Fx = -(dHi_dx[a] - ((dSL_dx[a] - dHb_dx[a]) * rr));
@@ -161,6 +166,9 @@ struct PrepArgs {
   const double *Hi_Ac, *Hb_Ac, *SL_Ac, *sx_Ac, *sy_Ac, *Ux_Ac, *Uy_Ac;  // Ac
   const unsigned *mbits_Ac;
   int gl_fix;
+  const double *A_mean, *A_mean_Ac;  // realistic flow factor (else NULL)
+  double m_enh_ssa;
+  double *Afac;
   double2 *UV, *rhsnum;
   double *tau_c, *phi, *Hm;
   unsigned char *mflag;
@@ -173,6 +181,10 @@ __global__ void k_ssa_prepare(PrepArgs a)
   if (s == INT_MIN) return;
   double Hi, Hb, SL, sx, sy, U, V;
   unsigned char fl = 0;
+  if (a.A_mean) {
+    const double A = s >= 0 ? a.A_mean[s] : a.A_mean_Ac[~s];
+    a.Afac[p] = pow(a.m_enh_ssa * 0.5 * A, -1.0 / UFM_N_FLOW);   // first factor of eta (ice_dynamics_module.f90:718)
+  }
   if (s >= 0) { Hi = a.Hi[s]; Hb = a.Hb[s]; SL = a.SL[s]; sx = a.sx[s]; sy = a.sy[s]; U = a.U[s]; V = a.V[s]; }
   else {
     s = ~s;
@@ -205,7 +217,8 @@ struct ViscArgs {
   const int *idx;
   const double *nx, *ny, *nx0, *ny0, *Hm;
   const double2 *UV;
-  double visc_A;  // (m_enh_ssa * 0.5 * A_flow)**(-1/n_flow), host libm
+  double visc_A;  // (m_enh_ssa * 0.5 * A_flow)**(-1/n_flow), host libm (benchmark flow factor)
+  const double *Afac;  // per-row factor (temperature-dependent flow factor), or NULL
   double *eta, *N;
   double2 *dU, *dV;
   double *partials;
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
         if (STORE_GRAD) { a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy); }
         else {
           const double epsilon_sq_0 = 1E-12;
-          const double eta = a.visc_A * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
+          const double eta = (a.Afac ? a.Afac[p] : a.visc_A) * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
           const double Nn = eta * a.Hm[p];
           const double dn = Nn - a.N[p];
           s_dn = dn * dn; s_n = Nn * Nn;
@@ -658,6 +671,7 @@ int ufm_k_ssa_prepare(ufm_handle *h)
   a.Hi = s.Hi; a.Hb = s.Hb; a.SL = s.SL; a.sx = s.dHs_dx_shelf; a.sy = s.dHs_dy_shelf; a.U = s.U_SSA; a.V = s.V_SSA;
   a.Hi_Ac = s.Hi_Ac; a.Hb_Ac = s.Hb_Ac; a.SL_Ac = s.SL_Ac; a.sx_Ac = s.dHs_dx_shelf_Ac; a.sy_Ac = s.dHs_dy_shelf_Ac;
   a.Ux_Ac = s.U_SSA_Ac[0]; a.Uy_Ac = s.U_SSA_Ac[1]; a.mbits_Ac = s.mbits_Ac; a.gl_fix = h->P.use_analytical_GL_flux;
+  a.A_mean = s.realistic_A ? s.A_mean : nullptr; a.A_mean_Ac = s.A_mean_Ac; a.m_enh_ssa = h->P.m_enh_ssa; a.Afac = s.Afac;
   a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.phi = s.phi; a.Hm = s.Hm; a.mflag = s.mflag;
   k_ssa_prepare<<<grid_for(m.Mp, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;
@@ -669,7 +683,8 @@ int ufm_k_ssa_prepare(ufm_handle *h)
     k_gl_flux<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.ac_Aci, s.mbits_Ac, s.mbits, s.Hi, s.Hb, s.SL, s.phi, m.aa2m, 1.0,
                                                            s.dHi_Ac[0], s.dHi_Ac[1], s.dSL_Ac[0], s.dSL_Ac[1], s.dHb_Ac[0], s.dHb_Ac[1],
                                                            m.ac_Dx, m.ac_Dy, f, s.Qabs_GL_Ac, s.Qp_GL_Ac, s.U_SSA_Ac[0], s.U_SSA_Ac[1],
-                                                           m.ac2m, s.UV);
+                                                           m.ac2m, s.UV, s.realistic_A ? s.A_mean : nullptr, pow(UFM_ICE_DENSITY * UFM_GRAV, UFM_N_FLOW),
+                                                           pow(1.0 - (UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY), UFM_N_FLOW - 1.0), pow(4.0, UFM_N_FLOW));
     h->cnt.kernel_launches++;
   }
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_prepare");
@@ -683,6 +698,7 @@ int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
   a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
   a.Hm = s.Hm; a.UV = s.UV;
   a.visc_A = pow(h->P.m_enh_ssa * 0.5 * s.A_flow_const, -1.0 / UFM_N_FLOW);
+  a.Afac = s.realistic_A ? s.Afac : nullptr;
   a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
   k_ssa_viscosity<false><<<grid, 256, 0, h->stream>>>(a);
@@ -705,7 +721,7 @@ int ufm_k_ssa_gradients(ufm_handle *h)
   // diagnostic gradients on ALL rows (each rank's (U,V) is complete after ufm_ssa_finish): single-rank view of the ranges
   a.cm = h->comm; a.cm.P = 1; a.cm.rank = 0; a.rng = m.rng_all_dev;
   a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
-  a.Hm = s.Hm; a.UV = s.UV; a.visc_A = 0.0; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
+  a.Hm = s.Hm; a.UV = s.UV; a.visc_A = 0.0; a.Afac = nullptr; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
   k_ssa_viscosity<true><<<grid, 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;

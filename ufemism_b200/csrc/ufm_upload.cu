@@ -117,7 +117,7 @@ int ufm_mesh_free_impl(ufm_handle *h)
   for (int k = 0; k < 4; k++) { free_ptr(m.ac_Nx[k]); free_ptr(m.ac_Ny[k]); free_ptr(m.ac_No[k]); }
   void *sp[] = {s.Hi, s.Hi_alt, s.Hb, s.SL, s.Hs, s.dHb_dt, s.dHi_dt, s.dHs_dt, s.dHi_dx, s.dHi_dy, s.dHs_dx, s.dHs_dy, s.dHs_dx_shelf,
                 s.dHs_dy_shelf, s.U_SIA, s.V_SIA, s.D_SIA, s.U_SSA, s.V_SSA, s.SMB_year, s.BMB, s.thk_factor, s.thk_smb, s.U_3D, s.V_3D,
-                s.mask_noice, s.mbits, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
+                s.mask_noice, s.mbits, s.Ti, s.A_mean, s.A_mean_Ac, s.Afac, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
                 s.Qabs_GL_Ac, s.Qp_GL_Ac, s.mbits_Ac, s.UV, s.RHS, s.E, s.rhsnum, s.dU, s.dV, s.eta, s.N, s.S, s.tau_c, s.phi, s.Hm,
                 s.mflag, s.partials, s.ctrl, s.scal, s.mail};
   for (void *p : sp) free_ptr(p);
@@ -428,6 +428,8 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
                      &s.dHs_dx_shelf, &s.dHs_dy_shelf, &s.U_SIA, &s.V_SIA, &s.D_SIA, &s.U_SSA, &s.V_SSA, &s.SMB_year, &s.BMB, &s.thk_factor, &s.thk_smb};
   for (double **p : aa_d) ZE(nv, *p);
   ZE(nv * nz, s.U_3D); ZE(nv * nz, s.V_3D);
+  s.realistic_A = (h->P.benchmark == UFM_BM_NONE);
+  if (s.realistic_A) { ZE(nv * nz, s.Ti); ZE(nv, s.A_mean); ZE(na, s.A_mean_Ac); ZE(nm, s.Afac); }
   ZE(nv, s.mask_noice); ZE(nv, s.mbits);
   double **ac_d[] = {&s.Hi_Ac, &s.Hb_Ac, &s.SL_Ac, &s.Hs_Ac, &s.dHs_dx_shelf_Ac, &s.dHs_dy_shelf_Ac, &s.D_SIA_Ac, &s.Qabs_GL_Ac, &s.Qp_GL_Ac};
   for (double **p : ac_d) ZE(na, *p);
