@@ -187,6 +187,10 @@ int ufm_thickness_update(ufm_handle *h, double dt);
 int ufm_update_general(ufm_handle *h, double time);
 /* body of solve_SIA (src/ice_dynamics_module.f90:240-314) */
 int ufm_solve_SIA(ufm_handle *h);
+/* U_3D / V_3D half of solve_SIA_3D (src/ice_dynamics_module.f90:317-367, called from update_ice_temperature,
+ * src/thermodynamics_module.f90:71) incl. apply_Neumann_boundary_3D; the vertical velocity W_3D feeds thermodynamics only
+ * and stays on the host.  U_3D / V_3D set the third critical time step. */
+int ufm_solve_SIA_3D(ufm_handle *h);
 /* body of solve_SSA (src/ice_dynamics_module.f90:408-557) */
 int ufm_solve_SSA(ufm_handle *h, ufm_ssa_stats *stats);
 /* critical time steps of determine_timesteps_and_actions (src/UFEMISM_main_model.f90:738-778):

@@ -84,6 +84,7 @@ def lib():
         L.ora_calculate_ice_thickness_change.argtypes = [p, p, p, d]
         L.ora_update_general_ice_model_data.argtypes = [p, p, p, d]
         L.ora_solve_SIA.argtypes = [p, p, p]
+        L.ora_solve_SIA_3D_UV.argtypes = [p, p, p]
         L.ora_solve_SSA.argtypes = [p, p, p, p]
         L.ora_determine_timesteps.argtypes = [p, p, p, p]
         for f in ("ora_basal_yield_stress", "ora_calculate_GL_flux", "ora_SSA_gather_AaAc", "ora_SSA_effective_viscosity", "ora_SSA_sliding_term"):
@@ -156,6 +157,9 @@ class Oracle:
 
     def solve_SIA(self):
         self.L.ora_solve_SIA(*self._a())
+
+    def solve_SIA_3D(self):
+        self.L.ora_solve_SIA_3D_UV(*self._a())
 
     def solve_SSA(self):
         st = OraSsaStats()

@@ -513,6 +513,75 @@ void ora_solve_SIA(const ora_mesh *m, ora_ice *ice, const ora_config *c)
   }
 }
 
+/* apply_Neumann_boundary_3D, src/mesh_derivatives_module.f90:538-597 (rank body) */
+static void apply_Neumann_boundary_3D_r(const ora_mesh *m, const rank_t *r, double *d, int nz)
+{
+  int nV = m->nV, W = m->nC_mem;
+  double vals[64];
+  for (int vi = (r->v1 > 5 ? r->v1 : 5); vi <= r->v2; vi++) {
+    if (A1(m->edge_index, vi) == 0) continue;
+    for (int k = 1; k <= nz; k++) {
+      for (int q = 0; q < W; q++) vals[q] = 0.0;
+      int nvals = 0;
+      for (int ci = 1; ci <= A1(m->nC, vi); ci++) {
+        int vc = A2(m->C, vi, ci, nV);
+        if (A1(m->edge_index, vc) > 0) continue;
+        nvals = nvals + 1;
+        vals[nvals - 1] = A2(d, vc, k, nV);
+      }
+      double s = 0.0;
+      for (int q = 0; q < W; q++) s = s + vals[q];
+      A2(d, vi, k, nV) = s / nvals;
+    }
+  }
+  SYNC
+  if (r->i == 0) {
+    for (int vi = 1; vi <= 4; vi++)
+      for (int k = 1; k <= nz; k++) {
+        for (int q = 0; q < W; q++) vals[q] = 0.0;
+        int nvals = 0;
+        for (int ci = 1; ci <= A1(m->nC, vi); ci++) { nvals = nvals + 1; vals[nvals - 1] = A2(d, A2(m->C, vi, ci, nV), k, nV); }
+        double s = 0.0;
+        for (int q = 0; q < W; q++) s = s + vals[q];
+        A2(d, vi, k, nV) = s / nvals;
+      }
+  }
+  SYNC
+}
+
+/* solve_SIA_3D, src/ice_dynamics_module.f90:317-367: the U_3D / V_3D half (the vertical velocity W_3D, :369-403, only feeds
+ * thermodynamics, out of scope).  U_3D / V_3D set the third critical time step (src/UFEMISM_main_model.f90:764-767). */
+void ora_solve_SIA_3D_UV(const ora_mesh *m, ora_ice *ice, const ora_config *c)
+{
+  const double D_uv_3D_cutoff = -1E5;
+  int nV = m->nV, nZ = c->nZ;
+#pragma omp parallel num_threads(c->nthreads)
+  {
+    rank_t r = rank_of(m);
+    double f[32], D_deformation[32];
+    for (int k = 1; k <= nZ; k++) for (int vi = r.v1; vi <= r.v2; vi++) { A2(ice->U_3D, vi, k, nV) = 0.0; A2(ice->V_3D, vi, k, nV) = 0.0; }
+    SYNC
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      for (int k = 1; k <= nZ; k++) { A2(ice->U_3D, vi, k, nV) = A1(ice->U_SSA, vi); A2(ice->V_3D, vi, k, nV) = A1(ice->V_SSA, vi); }
+      if (A1(ice->mask_shelf, vi) == 1) continue;
+      if (A1(ice->Hi, vi) == 0.0) continue;
+      double dx = A1(ice->dHs_dx, vi), dy = A1(ice->dHs_dy, vi);
+      double D_0 = pow(ice_density * grav * A1(ice->Hi, vi), n_flow) * pow((dx * dx + dy * dy), (n_flow - 1.0) / 2.0);
+      for (int k = 1; k <= nZ; k++) f[k - 1] = c->m_enh_sia * A2(ice->A_flow, vi, k, nV) * pow(c->zeta[k - 1], n_flow);
+      vertical_integrate(c, f, D_deformation);
+      for (int k = 1; k <= nZ; k++) D_deformation[k - 1] = 2.0 * A1(ice->Hi, vi) * D_deformation[k - 1];
+      for (int k = 1; k <= nZ; k++) {
+        double D_SIA_3D = fmax(D_0 * D_deformation[k - 1], D_uv_3D_cutoff);
+        A2(ice->U_3D, vi, k, nV) = D_SIA_3D * dx + A1(ice->U_SSA, vi);
+        A2(ice->V_3D, vi, k, nV) = D_SIA_3D * dy + A1(ice->V_SSA, vi);
+      }
+    }
+    SYNC
+    apply_Neumann_boundary_3D_r(m, &r, ice->U_3D, nZ);
+    apply_Neumann_boundary_3D_r(m, &r, ice->V_3D, nZ);
+  }
+}
+
 /* ============================================================================================
  * SSA
  * ============================================================================================ */
@@ -966,7 +1035,12 @@ int ora_run_model(const ora_mesh *m, ora_ice *ice, const ora_config *c, ora_regi
     if (r->do_[ORA_T_CLIMATE]) r->t0[ORA_T_CLIMATE] = r->time;
     if (r->do_[ORA_T_SMB]) { ora_run_SMB_benchmark(m, ice, c, r->time, r->H0, r->R0, r->lambda); r->t0[ORA_T_SMB] = r->time; }
     if (r->do_[ORA_T_BMB]) r->t0[ORA_T_BMB] = r->time;
-    if (r->do_[ORA_T_THERMO]) r->t0[ORA_T_THERMO] = r->time;
+    if (r->do_[ORA_T_THERMO]) {
+      /* update_ice_temperature (src/thermodynamics_module.f90:44-71): the EISMINT experiments (and realistic runs) refresh
+       * U_3D / V_3D through solve_SIA_3D; the heat equation itself is out of scope */
+      if ((c->benchmark >= ORA_BM_EISMINT_1 && c->benchmark <= ORA_BM_EISMINT_6) || c->benchmark == ORA_BM_NONE) ora_solve_SIA_3D_UV(m, ice, c);
+      r->t0[ORA_T_THERMO] = r->time;
+    }
     if (r->do_[ORA_T_OUTPUT]) r->t0[ORA_T_OUTPUT] = r->time;
     /* determine_timesteps_and_actions */
     double d3[3];

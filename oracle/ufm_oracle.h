@@ -114,6 +114,7 @@ void ora_partition_list(int ntot, int i, int n, int *i1, int *i2);
 void ora_calculate_ice_thickness_change(const ora_mesh *m, ora_ice *ice, const ora_config *c, double dt);
 void ora_update_general_ice_model_data(const ora_mesh *m, ora_ice *ice, const ora_config *c, double time);
 void ora_solve_SIA(const ora_mesh *m, ora_ice *ice, const ora_config *c);
+void ora_solve_SIA_3D_UV(const ora_mesh *m, ora_ice *ice, const ora_config *c);
 int  ora_solve_SSA(const ora_mesh *m, ora_ice *ice, const ora_config *c, ora_ssa_stats *st);
 void ora_determine_timesteps(const ora_mesh *m, const ora_ice *ice, const ora_config *c, double out3[3]);
 

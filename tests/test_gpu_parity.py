@@ -340,3 +340,33 @@ def test_host_registered_buffers(mesh_2k):
     g.host_unregister(a); g.host_unregister(out)
     g.upload("Hi", a)
     assert np.array_equal(g.download("Hi"), st["Hi"])
+
+
+def test_solve_SIA_3D_uv(mesh_10k):
+    st = scenario(mesh_10k, "mismip")
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    rng = np.random.default_rng(2)
+    us, vs = rng.normal(0, 20.0, mesh_10k.nV), rng.normal(0, 20.0, mesh_10k.nV)
+    o["U_SSA"][:] = us; o["V_SSA"][:] = vs
+    g.upload("U_SSA", us); g.upload("V_SSA", vs)
+    o.solve_SIA_3D(); g.solve_SIA_3D()
+    for f in ("U_3D", "V_3D"):
+        b = o[f]
+        assert np.abs(b - us[:, None] if f == "U_3D" else b - vs[:, None]).max() > 1.0   # SIA part is there
+        np.testing.assert_allclose(g.download(f), b, rtol=1e-13, atol=1e-13 * np.abs(b).max(), err_msg=f)
+    assert g.determine_timesteps()[2] == pytest.approx(o.determine_timesteps()[2], rel=1e-12)
+
+
+def test_run_model_eismint1(mesh_2k):
+    """BASELINE config 1: EISMINT-1 moving margin from an ice-free start; thermodynamics timer refreshes U_3D, which
+    limits dt: same step sequence and thickness within 1e-8 after 400 model years."""
+    st = S.state_eismint1(mesh_2k)
+    o, g = make_oracle(mesh_2k, st, nthreads=4), make_gpu(mesh_2k, st)
+    ro, rg = o.region(0.0), g.region(0.0)
+    assert o.run_model(ro, 400.0) == 0
+    g.run_model(rg, 400.0)
+    assert rg.n_steps == ro.n_steps and rg.time == ro.time == 400.0
+    assert o["Hi"].max() > 100.0 and np.abs(o["U_3D"]).max() > 0.0
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+    assert rel_l2(g.download("U_3D"), o["U_3D"]) <= 1e-8

@@ -104,7 +104,7 @@ for _n, _i in FIELD_IDS.items():
 
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_thickness_update", "ufm_update_general",
-            "ufm_solve_SIA", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
+            "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
 _lib = None
@@ -137,6 +137,7 @@ def load_library():
         L.ufm_thickness_update.argtypes = [p, d]
         L.ufm_update_general.argtypes = [p, d]
         L.ufm_solve_SIA.argtypes = [p]
+        L.ufm_solve_SIA_3D.argtypes = [p]
         L.ufm_solve_SSA.argtypes = [p, p]
         L.ufm_cfl.argtypes = [p, p]
         L.ufm_ssa_prepare.argtypes = [p]
@@ -315,6 +316,9 @@ class IceModelGPU:
 
     def solve_SIA(self):
         self._ck(self.L.ufm_solve_SIA(self.h))
+
+    def solve_SIA_3D(self):
+        self._ck(self.L.ufm_solve_SIA_3D(self.h))
 
     def solve_SSA(self):
         st = SsaStats()

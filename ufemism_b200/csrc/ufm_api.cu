@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -71,6 +72,7 @@ int ufm_create(int device, const ufm_params *params, ufm_handle **out)
   h->device = device;
   h->P = *params;
   h->num_sms = prop.multiProcessorCount;
+  { const char *e = getenv("UFM_SOR_TMA"); h->sor_tma = e ? atoi(e) : 0; }
   memset(&h->cnt, 0, sizeof(h->cnt));
   derive_params(h);
   UFM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -91,6 +93,7 @@ int ufm_destroy(ufm_handle *h)
   if (h->staging) cudaFreeHost(h->staging);
   if (h->dev_staging) cudaFree(h->dev_staging);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  for (auto e : h->ev_pool) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -339,6 +342,7 @@ int ufm_thickness_update(ufm_handle *h, double dt)
 }
 int ufm_update_general(ufm_handle *h, double time) { NEED_MESH(h); return ufm_k_geom(h, time); }
 int ufm_solve_SIA(ufm_handle *h) { NEED_MESH(h); return ufm_k_sia(h); }
+int ufm_solve_SIA_3D(ufm_handle *h) { NEED_MESH(h); return ufm_k_sia3d(h); }
 int ufm_cfl(ufm_handle *h, double out3[3]) { NEED_MESH(h); return ufm_k_cfl(h, out3); }
 int ufm_ssa_prepare(ufm_handle *h) { NEED_MESH(h); return ufm_k_ssa_prepare(h); }
 int ufm_ssa_viscosity(ufm_handle *h, double sums2[2]) { NEED_MESH(h); return ufm_k_ssa_viscosity(h, sums2); }
@@ -379,34 +383,11 @@ int ufm_solve_SSA(ufm_handle *h, ufm_ssa_stats *stats)
   if (set_zero) return ufm_k_ssa_zero(h);
   int rc = ufm_k_ssa_prepare(h);
   if (rc) return rc;
-  bool has_converged = false, did_reset_before = false;
-  int it = 0;
-  while (!has_converged && it < h->P.SSA_max_outer_loops) {
-    it++;
-    double sums[2];
-    if ((rc = ufm_k_ssa_viscosity(h, sums))) return rc;
-    const double RN = sqrt(sums[0] / sums[1]);
-    stats->last_RN = RN;
-    if (RN < h->P.SSA_RN_tol) { has_converged = true; break; }
-    if ((rc = ufm_k_ssa_sliding_setup(h))) return rc;
-    ufm_ssa_stats lin;
-    memset(&lin, 0, sizeof(lin));
-    if ((rc = ufm_k_ssa_sor(h, h->P.SSA_max_inner_loops, 0, &lin))) return rc;
-    stats->n_inner_total += lin.n_inner_last;
-    stats->n_inner_last = lin.n_inner_last;
-    stats->last_max_residual = lin.last_max_residual;
-    if (lin.rc == 1) stats->rc = 1;
-    if (lin.did_reset) {
-      if (!did_reset_before) did_reset_before = true;
-      else {
-        stats->n_outer = it; stats->did_reset = 1; stats->rc = -1;
-        ufm_k_ssa_finish(h);
-        return ufm_set_error(-1, "solve_SSA - ERROR: SSA remains unstable after resetting velocities to zero!");
-      }
-    }
+  if ((rc = ufm_k_ssa_outer_loop(h, stats))) { ufm_k_ssa_finish(h); return rc; }
+  if (stats->rc == -1) {
+    ufm_k_ssa_finish(h);
+    return ufm_set_error(-1, "solve_SSA - ERROR: SSA remains unstable after resetting velocities to zero!");
   }
-  stats->n_outer = it;
-  stats->did_reset = did_reset_before ? 1 : 0;
   if ((rc = ufm_k_ssa_finish(h))) return rc;
   if (stats->rc == 1) { ufm_set_error(1, " WARNING - SSA SOR solver doesnt converge!"); return 1; }
   return 0;
@@ -442,8 +423,8 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
   NEED_MESH(h);
   if (!r) return ufm_set_error(-2, "NULL region");
   const int b = h->P.benchmark;
-  if (b == UFM_BM_NONE || b == UFM_BM_BUELER || (b >= UFM_BM_EISMINT_2 && b <= UFM_BM_EISMINT_6 && b != UFM_BM_EISMINT_4))
-    return ufm_set_error(-4, "ufm_run_model: time-dependent SMB of benchmark %d must be uploaded by the host each dt_SMB; use the step-wise entry points", b);
+  if (!host && (b == UFM_BM_NONE || b == UFM_BM_BUELER || (b >= UFM_BM_EISMINT_2 && b <= UFM_BM_EISMINT_6 && b != UFM_BM_EISMINT_4)))
+    return ufm_set_error(-4, "ufm_run_model: time-dependent SMB of benchmark %d must come from the host each dt_SMB; use ufm_run_model_host or the step-wise entry points", b);
   long steps = 0;
   int rc;
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
@@ -466,7 +447,11 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     if (r->do_[UFM_T_CLIMATE]) r->t0[UFM_T_CLIMATE] = r->time;
     if (r->do_[UFM_T_SMB]) r->t0[UFM_T_SMB] = r->time;
     if (r->do_[UFM_T_BMB]) r->t0[UFM_T_BMB] = r->time;
-    if (r->do_[UFM_T_THERMO]) r->t0[UFM_T_THERMO] = r->time;
+    if (r->do_[UFM_T_THERMO]) {
+      // update_ice_temperature (thermodynamics_module.f90:44-71): EISMINT and realistic runs refresh U_3D / V_3D
+      if ((b >= UFM_BM_EISMINT_1 && b <= UFM_BM_EISMINT_6) || b == UFM_BM_NONE) { if ((rc = ufm_solve_SIA_3D(h))) return rc; }
+      r->t0[UFM_T_THERMO] = r->time;
+    }
     if (r->do_[UFM_T_OUTPUT]) r->t0[UFM_T_OUTPUT] = r->time;
     double d3[3];
     if ((rc = ufm_cfl(h, d3))) return rc;

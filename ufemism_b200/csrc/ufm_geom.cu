@@ -258,6 +258,72 @@ __global__ void __launch_bounds__(256) k_sia_ac(int nAc, SiaConst K, const unsig
   D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo;
 }
 
+// ---- solve_SIA_3D, U_3D / V_3D half (ice_dynamics_module.f90:317-367) + apply_Neumann_boundary_3D
+//      (mesh_derivatives_module.f90:538-597).  Layout of the (nV,nZ) arrays: k-major, [k*nVp + v]. ----
+template <bool REALISTIC>
+__global__ void __launch_bounds__(256) k_sia3d_uv(int nV, int nVp, SiaConst K, ZetaConst Z, double m_enh_sia, const double *__restrict__ Ti,
+                                                  const unsigned *__restrict__ mbits, const double *__restrict__ Hi, const double *__restrict__ hx,
+                                                  const double *__restrict__ hy, const double *__restrict__ U_SSA, const double *__restrict__ V_SSA,
+                                                  double *__restrict__ U3, double *__restrict__ V3)
+{
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const double us = U_SSA[v], vs = V_SSA[v], H = Hi[v];
+  const bool plain = (mbits[v] & MB_SHELF) || (H == 0.0);
+  double I[UFM_MAX_NZ];
+  double D_0 = 0.0, dx = 0.0, dy = 0.0;
+  if (!plain) {
+    dx = hx[v]; dy = hy[v];
+    D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (dx * dx + dy * dy);
+    if (REALISTIC) {
+      I[Z.nZ - 1] = 0.0;
+      double fk1 = m_enh_sia * g_arrhenius(Ti[(size_t)(Z.nZ - 1) * nVp + v]) * Z.z3[Z.nZ - 1];
+      for (int k = Z.nZ - 2; k >= 0; k--) {
+        const double fk = m_enh_sia * g_arrhenius(Ti[(size_t)k * nVp + v]) * Z.z3[k];
+        I[k] = I[k + 1] - 0.5 * (fk1 + fk) * Z.dz[k + 1];
+        fk1 = fk;
+      }
+    }
+  }
+  const double twoH = 2.0 * H;
+  for (int k = 0; k < K.nZ; k++) {
+    double u = us, w = vs;
+    if (!plain) {
+      const double D = fmax(D_0 * (twoH * (REALISTIC ? I[k] : K.I[k])), -1E5);
+      u = D * dx + us; w = D * dy + vs;
+    }
+    U3[(size_t)k * nVp + v] = u; V3[(size_t)k * nVp + v] = w;
+  }
+}
+// stage 0: domain-edge vertices except the corners, from their non-edge neighbours; stage 1: the four corners (reference
+// vertices 1..4) from all neighbours at their new values
+__global__ void __launch_bounds__(256) k_neumann_3d(int stage, int n_slices, int nVp, int nZ, const long long *__restrict__ off,
+                                                    const unsigned char *__restrict__ deg, const unsigned char *__restrict__ edge,
+                                                    const int *__restrict__ dev2ref, const int *__restrict__ C, double *U3, double *V3)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < n_slices; s += nw) {
+    const int v = s * 32 + lane;
+    const int n = deg[v];
+    if (n == UFM_DEG_PAD || edge[v] == 0) continue;
+    const bool corner = dev2ref[v] < 4;
+    if (corner != (stage == 1)) continue;
+    const long long o = off[s];
+    for (int k = 0; k < nZ; k++) {
+      double su = 0.0, sv = 0.0;
+      int nvals = 0;
+      for (int c = 0; c < n; c++) {
+        const int j = C[o + (long long)c * 32 + lane];
+        if (stage == 0 && edge[j] > 0) continue;
+        nvals++;
+        su = su + U3[(size_t)k * nVp + j]; sv = sv + V3[(size_t)k * nVp + j];
+      }
+      U3[(size_t)k * nVp + v] = su / (double)nvals; V3[(size_t)k * nVp + v] = sv / (double)nvals;
+    }
+  }
+}
+
 // ---- map_Ac_to_Aa x3 (mesh_ArakawaC_module.f90:770-791), diagnostic U_SIA, V_SIA, D_SIA ----
 struct SiaAaArgs {
   int n_slices;
@@ -533,6 +599,30 @@ int ufm_k_sia(ufm_handle *h)
   k_sia_aa<<<grid_for((long long)m.aa.n_slices * 32, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches += 2;
   return ufm_cuda_check(cudaGetLastError(), "k_sia");
+}
+
+int ufm_k_sia3d(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  SiaConst K;
+  ZetaConst Z;
+  K.nZ = Z.nZ = h->P.nZ;
+  double f[UFM_MAX_NZ];
+  for (int k = 0; k < K.nZ; k++) f[k] = h->P.m_enh_sia * s.A_flow_const * h->zeta3[k];
+  K.I[K.nZ - 1] = 0.0;
+  for (int k = K.nZ - 1; k >= 1; k--) K.I[k - 1] = K.I[k] - 0.5 * (f[k] + f[k - 1]) * (h->P.zeta[k] - h->P.zeta[k - 1]);
+  K.dz[0] = Z.dz[0] = 0.0;
+  for (int k = 1; k < K.nZ; k++) K.dz[k] = Z.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+  for (int k = 0; k < K.nZ; k++) Z.z3[k] = h->zeta3[k];
+  if (s.realistic_A)
+    k_sia3d_uv<true><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D);
+  else
+    k_sia3d_uv<false><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D);
+  int g = grid_for((long long)m.aa.n_slices * 32, 256);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(0, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(1, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D);
+  h->cnt.kernel_launches += 3;
+  return ufm_cuda_check(cudaGetLastError(), "k_sia3d");
 }
 
 int ufm_k_thickness(ufm_handle *h, double dt)

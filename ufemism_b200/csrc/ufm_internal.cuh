@@ -150,12 +150,15 @@ struct ufm_handle {
   double zeta3[UFM_MAX_NZ];      // C%zeta**n_flow, evaluated with the host libm like the reference
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_pool[32] = {};
   int num_sms = 0;
   bool has_mesh = false;
   DevMesh mesh;
   DevState st;
   ufm_counters cnt;
   int sor_grid = 0, sor_block = 512;
+  size_t sor_smem = 0;
+  int sor_tma = 0;               // 1: TMA-staged SOR kernel (env UFM_SOR_TMA, default set in ufm_create)
   int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload
   bool comm_connected = false;
   CommDev comm;
@@ -177,6 +180,7 @@ int ufm_cuda_check(cudaError_t e, const char *what);
 // launchers (each returns 0 or a negative rc)
 int ufm_k_geom(ufm_handle *h, double time);
 int ufm_k_sia(ufm_handle *h);
+int ufm_k_sia3d(ufm_handle *h);
 int ufm_k_thickness(ufm_handle *h, double dt);
 int ufm_k_cfl(ufm_handle *h, double out3[3]);
 int ufm_k_ssa_prepare(ufm_handle *h);
@@ -186,6 +190,7 @@ int ufm_k_ssa_gradients(ufm_handle *h);
 int ufm_comm_reset(ufm_handle *h);
 int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *stats);
 int ufm_k_ssa_finish(ufm_handle *h);
+int ufm_k_ssa_outer_loop(ufm_handle *h, ufm_ssa_stats *stats);
 int ufm_k_ssa_zero(ufm_handle *h);
 int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out);
 int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double lambda);

@@ -33,6 +33,17 @@ template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return _
 // A wait that exceeds SPIN_LIMIT polls (seconds) raises MAIL_ABORT instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------
 #define SPIN_LIMIT 40000000LL
+// device-side control of one solve_SSA call (words of DevState::ctrl): lets a batch of outer iterations run back to back
+// without a host round trip; every kernel of the batch first looks at SCTL_STOP
+#define SCTL_BASE 96
+#define SCTL_STOP 0       // 1: converged (RN < tol), aborted, or failed -> remaining kernels of the batch return at once
+#define SCTL_NOUTER 1     // viscosity iterations started
+#define SCTL_NINNER 2     // SOR iterations, total
+#define SCTL_RESET 3      // velocities were reset once
+#define SCTL_RC 4         // bit0 SOR hit max_inner (warning), bit1 unstable twice (abort), bit2 peer wait timed out
+#define SCTL_RN 5         // last RN (double bits)
+#define SCTL_MAXRES 6     // last max residual (double bits)
+#define SCTL_NLAST 7      // SOR iterations of the last linear solve
 __device__ __forceinline__ void peer_sync(const CommDev &cm)
 {
   __threadfence_system();
@@ -219,6 +230,15 @@ struct ViscArgs {
   const double2 *UV;
   double visc_A;  // (m_enh_ssa * 0.5 * A_flow)**(-1/n_flow), host libm (benchmark flow factor)
   const double *Afac;  // per-row factor (temperature-dependent flow factor), or NULL
+  // fused SSA_sliding_term + RHS + centre coefficients (k_ssa_setup's work, done while eta is still in a register)
+  int fuse_setup;
+  const unsigned char *mflag;
+  const double2 *rhsnum;
+  const double *tau_c, *cU0, *cV0;
+  double thr;
+  double *S;
+  double2 *RHS, *E;
+  const unsigned long long *sctl;  // device-side solve control (SCTL_*), or NULL
   double *eta, *N;
   double2 *dU, *dV;
   double *partials;
@@ -245,18 +265,19 @@ __device__ __forceinline__ void visc_row(const ViscArgs &a, const long long o, c
     if (c < n) { ux = ux + cx[c] * nb[c].x; uy = uy + cy[c] * nb[c].x; vx = vx + cx[c] * nb[c].y; vy = vy + cy[c] * nb[c].y; }
 }
 
-// One CTA (8 warps) per 256-row chunk, chunks of this rank's six block ranges taken grid-stride.  The two sums are
-// reduced per chunk in a fixed order and stored at partials[chunk] (and pushed to the peers of a partitioned run), so
-// the final fixed-shape tree over ALL chunks gives the same bits for any number of GPUs.
+// One warp per slice, slices of this rank's six block ranges taken grid-stride (no block-level synchronisation in the
+// streaming loop).  The two sums are reduced per slice with a fixed xor-shuffle tree and stored at partials[slice] (and
+// pushed to the peers of a partitioned run), so the final fixed-shape reduction over ALL slices gives the same bits for
+// any number of GPUs and any grid size.
 template <bool STORE_GRAD>
 __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ double sh[2][8];
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  if (a.sctl && a.sctl[SCTL_STOP]) return;   // the solve has already converged / aborted (device-side control flow)
   for (int b = 0; b < 6; b++) {
-    const int c0 = a.rng[(b * a.cm.P + a.cm.rank) * 3] >> 3, c1 = (a.rng[(b * a.cm.P + a.cm.rank) * 3 + 2] + 7) >> 3;
-    for (int ch = c0 + blockIdx.x; ch < c1; ch += gridDim.x) {
-      const int s = ch * 8 + warp;
+    const int s0 = a.rng[(b * a.cm.P + a.cm.rank) * 3], s1 = a.rng[(b * a.cm.P + a.cm.rank) * 3 + 2];
+    for (int s = s0 + wg; s < s1; s += nw) {
       const long long o = a.off[s];
       const int w = (int)((a.off[s + 1] - o) >> 5);
       const int p = s * 32 + lane;
@@ -294,34 +315,48 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
           const double dn = Nn - a.N[p];
           s_dn = dn * dn; s_n = Nn * Nn;
           a.eta[p] = eta; a.N[p] = Nn;
+          if (a.fuse_setup) {   // identical expressions to k_ssa_setup
+            const double delta_v = 1E-3, q_plastic = 0.30;
+            const double2 u = a.UV[p];
+            const double S = a.tau_c[p] * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
+            const double2 r = a.rhsnum[p];
+            a.RHS[p] = make_double2(r.x / eta, r.y / eta);
+            double eu = a.cU0[p], ev = a.cV0[p];
+            if (a.mflag[p] & 1) { const double t = S / (a.Hm[p] * eta); eu = eu - t; ev = ev - t; }
+            a.S[p] = S;
+            a.E[p] = make_double2(eu, ev);
+          }
         }
       }
       if (STORE_GRAD) continue;
       for (int o2 = 16; o2 > 0; o2 >>= 1) { s_dn += __shfl_xor_sync(0xffffffffu, s_dn, o2); s_n += __shfl_xor_sync(0xffffffffu, s_n, o2); }
-      if (lane == 0) { sh[0][warp] = s_dn; sh[1][warp] = s_n; }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double t0 = 0.0, t1 = 0.0;
-        for (int k = 0; k < 8; k++) { t0 += sh[0][k]; t1 += sh[1][k]; }
-        for (int q = 0; q < a.cm.P; q++) { a.cm.partials[q][2 * ch] = t0; a.cm.partials[q][2 * ch + 1] = t1; }
-      }
-      __syncthreads();
+      if (lane == 0)
+        for (int q = 0; q < a.cm.P; q++) { a.cm.partials[q][2 * s] = s_dn; a.cm.partials[q][2 * s + 1] = s_n; }
     }
   }
 }
 // fixed-shape tree over the per-block partials: deterministic for a given grid size
-__global__ void k_sum_partials(int n, const double *partials, double *out2)
+__global__ void __launch_bounds__(1024) k_sum_partials(int n, const double *partials, double *out2, unsigned long long *sctl, double RN_tol)
 {
-  __shared__ double sh[2][256];
+  __shared__ double sh[2][1024];
+  if (sctl && sctl[SCTL_STOP]) return;
   double t0 = 0.0, t1 = 0.0;
-  for (int k = threadIdx.x; k < n; k += 256) { t0 += partials[2 * k]; t1 += partials[2 * k + 1]; }
+  for (int k = threadIdx.x; k < n; k += 1024) { const double2 v = ((const double2 *)partials)[k]; t0 += v.x; t1 += v.y; }
   sh[0][threadIdx.x] = t0; sh[1][threadIdx.x] = t1;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { out2[0] = sh[0][0]; out2[1] = sh[1][0]; }
+  if (threadIdx.x == 0) {
+    out2[0] = sh[0][0]; out2[1] = sh[1][0];
+    if (sctl) {   // viscosity_iteration_i += 1 ; RN = SQRT(sum_DN_sq / sum_N_sq) ; IF (RN < C%SSA_RN_tol) EXIT  (:503-524)
+      const double RN = sqrt(sh[0][0] / sh[1][0]);
+      sctl[SCTL_NOUTER] += 1ull;
+      sctl[SCTL_RN] = (unsigned long long)__double_as_longlong(RN);
+      if (RN < RN_tol) sctl[SCTL_STOP] = 1ull;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,6 +401,9 @@ __global__ void k_ssa_setup(SetupArgs a)
 #ifndef SOR_BLOCK
 #define SOR_BLOCK 512
 #endif
+#ifndef SOR_PREFETCH
+#define SOR_PREFETCH 0
+#endif
 #ifndef SOR_MIN_BLOCKS
 #define SOR_MIN_BLOCKS 1
 #endif
@@ -387,6 +425,7 @@ struct SorArgs {
   int max_inner, force_iters;
   double omega, tol;
   unsigned long long *ctrl;
+  unsigned long long *sctl;   // device-side solve control, or NULL when driven call by call
 };
 
 __device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
@@ -409,6 +448,33 @@ __device__ __forceinline__ void store_row(const SorArgs &a, const int p, const d
     if (xm) {
       for (int q = 0; q < a.cm.P; q++) if ((xm >> q) & 1u) a.cm.uv[q][p] = v;   // made visible by the barrier's system fence
     }
+  }
+}
+
+// Pull the read-only streams of slice s (the NEXT slice this warp will sweep) into L2 while the current slice is being
+// computed: one prefetch instruction per 128 B line, lines spread over the lanes.  Costs no registers and no DRAM traffic
+// (the lines are read exactly once either way); the demand loads of the next round then hit L2 (~300 ns) instead of HBM.
+template <bool EXACT>
+__device__ __forceinline__ void prefetch_slice(const SorArgs &a, const int s, const int lane)
+{
+  const long long o = a.off[s];
+  const int w = (int)((a.off[s + 1] - o) >> 5);
+  const int n_lines = (EXACT ? 7 : 5) * w + 10;
+  for (int t = lane; t < n_lines; t += 32) {
+    const char *ptr;
+    int u = t;
+    if (u < w) ptr = (const char *)(a.idx + o) + u * 128;
+    else if ((u -= w) < 2 * w) ptr = (const char *)(a.cU + o) + u * 128;
+    else if ((u -= 2 * w) < 2 * w) ptr = (const char *)(a.cV + o) + u * 128;
+    else if (EXACT && (u -= 2 * w) < 2 * w) ptr = (const char *)(a.nxy + o) + u * 128;
+    else {
+      if (!EXACT) u -= 2 * w; else u -= 2 * w;
+      const int p = s * 32;
+      if (u < 4) ptr = (const char *)(a.E + p) + u * 128;
+      else if (u < 8) ptr = (const char *)(a.RHS + p) + (u - 4) * 128;
+      else ptr = (const char *)((EXACT ? a.nxy0 : a.nxysum) + p) + (u - 8) * 128;
+    }
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
   }
 }
 
@@ -467,6 +533,7 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
   volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
   __shared__ double sh[SOR_BLOCK / 32];
   __shared__ int s_rng[15];   // this rank's slice ranges [begin, boundary_begin, end) of the five colours (read once)
+  if (a.sctl && a.sctl[SCTL_STOP]) return;   // uniform over the grid and over the ranks: nobody enters a barrier
   if (threadIdx.x < 15) s_rng[threadIdx.x] = a.rng[((threadIdx.x / 3) * P + rank) * 3 + (threadIdx.x % 3)];
   __syncthreads();
   int it = 0;
@@ -487,6 +554,7 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
           __syncwarp();
           waited = true;
         }
+        if (SOR_PREFETCH && s + nw < s_end) prefetch_slice<EXACT>(a, s + nw, lane);
         const long long o = a.off[s];
         const int w = (int)((a.off[s + 1] - o) >> 5);
         const int p = s * 32 + lane;
@@ -590,7 +658,287 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
     __syncthreads();
     if (tid == 0) mail[MAIL_EPOCH] = epoch;
   }
-  if (tid == 0) { a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres); }
+  if (tid == 0) {
+    a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres);
+    if (a.sctl) {   // bookkeeping of solve_SSA's outer loop (:530-540)
+      a.sctl[SCTL_NINNER] += (unsigned long long)it; a.sctl[SCTL_NLAST] = (unsigned long long)it;
+      a.sctl[SCTL_MAXRES] = (unsigned long long)__double_as_longlong(maxres);
+      if (flags & 2) a.sctl[SCTL_RC] |= 1ull;
+      if (flags & 4) { a.sctl[SCTL_RC] |= 4ull; a.sctl[SCTL_STOP] = 1ull; }
+      if (flags & 1) {
+        if (a.sctl[SCTL_RESET]) { a.sctl[SCTL_RC] |= 2ull; a.sctl[SCTL_STOP] = 1ull; }
+        else a.sctl[SCTL_RESET] = 1ull;
+      }
+    }
+  }
+}
+
+// =============================================================================================
+// TMA-staged variant of the SOR kernel.  Same arithmetic, same phases, same barriers; only the way the
+// read-only per-slice streams (neighbour indices, cU, cV, Nxy row, e, RHS, home Nxy, degrees) reach the SM differs:
+// lane 0 of every warp issues 1-D bulk async copies (cp.async.bulk, the TMA engine) of the NEXT slices of its warp into
+// a private ring of shared-memory stages and all lanes wait on the stage's mbarrier.  The copies are contiguous
+// because of the sliced-ELL layout (one slice = w*32 consecutive entries per array).  Bytes in flight no longer cost
+// registers, so the stream stays deep (TMA_STAGES x 8.4 KB per warp) while the SM computes the current slice.
+// (U,V) itself is NOT staged: it changes during the kernel and is gathered through the generic path as before.
+// =============================================================================================
+#define TMA_WARPS 12
+#define TMA_STAGES 2
+#define TMA_WMAX 8
+#define ST_IDX 0
+#define ST_CU 1024
+#define ST_CV 3072
+#define ST_NXY 5120
+#define ST_E 7168
+#define ST_RHS 7680
+#define ST_H0 8192
+#define ST_DEG 8448
+#define TMA_STAGE_BYTES 8576
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// issue the bulk copies of slice s into stage st (called by lane 0 only); slices wider than TMA_WMAX are not staged
+template <bool EXACT>
+__device__ __forceinline__ void tma_issue(const SorArgs &a, const int s, char *st, unsigned long long *bar)
+{
+  const long long o = a.off[s];
+  const int w = (int)((a.off[s + 1] - o) >> 5);
+  const int p = s * 32;
+  if (w > TMA_WMAX || w == 0) { mbar_expect_tx(bar, 32u); bulk_g2s(st + ST_DEG, a.deg + p, 32u, bar); return; }
+  const unsigned bi = (unsigned)w * 128u, bd = (unsigned)w * 256u;
+  mbar_expect_tx(bar, bi + 2u * bd + (EXACT ? bd : 0u) + 512u + 512u + 256u + 32u);
+  bulk_g2s(st + ST_IDX, a.idx + o, bi, bar);
+  bulk_g2s(st + ST_CU, a.cU + o, bd, bar);
+  bulk_g2s(st + ST_CV, a.cV + o, bd, bar);
+  if (EXACT) bulk_g2s(st + ST_NXY, a.nxy + o, bd, bar);
+  bulk_g2s(st + ST_E, a.E + p, 512u, bar);
+  bulk_g2s(st + ST_RHS, a.RHS + p, 512u, bar);
+  bulk_g2s(st + ST_H0, (EXACT ? a.nxy0 : a.nxysum) + p, 256u, bar);
+  bulk_g2s(st + ST_DEG, a.deg + p, 32u, bar);
+}
+
+template <int W, bool EXACT, bool MULTI>
+__device__ __forceinline__ double sor_row_st(const SorArgs &a, const char *st, const int lane, const int p, const int n, double tmax)
+{
+  const int *sidx = (const int *)(st + ST_IDX);
+  const double *scu = (const double *)(st + ST_CU), *scv = (const double *)(st + ST_CV), *snx = (const double *)(st + ST_NXY);
+  int j[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) j[c] = sidx[c * 32 + lane];
+  const double2 u = a.UV[p];
+  double2 nb[W];
+#pragma unroll
+  for (int c = 0; c < W; c++) nb[c] = a.UV[j[c]];
+  const double2 e2 = ((const double2 *)(st + ST_E))[lane], r2 = ((const double2 *)(st + ST_RHS))[lane];
+  const double h = ((const double *)(st + ST_H0))[lane];
+  double Uxy = u.x * h, Vxy = u.y * h;
+  if (EXACT) {
+#pragma unroll
+    for (int c = 0; c < W; c++) if (c < n) { const double t = snx[c * 32 + lane]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+  }
+  double sumU = 0.0, sumV = 0.0;
+#pragma unroll
+  for (int c = 0; c < W; c++) if (c < n) { sumU = sumU + nb[c].x * scu[c * 32 + lane]; sumV = sumV + nb[c].y * scv[c * 32 + lane]; }
+  const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
+  const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
+  const double resU = (LHSx - r2.x) / e2.x;
+  const double resV = (LHSy - r2.y) / e2.y;
+  tmax = fmax(tmax, fabs(resU));
+  tmax = fmax(tmax, fabs(resV));
+  store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
+  return tmax;
+}
+
+template <bool EXACT, bool GLFIX, bool MULTI>
+__global__ void __launch_bounds__(TMA_WARPS * 32, 1) k_ssa_sor_tma(SorArgs a)
+{
+  extern __shared__ __align__(128) char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  const int nblocks = gridDim.x, P = MULTI ? a.cm.P : 1, rank = MULTI ? a.cm.rank : 0;
+  unsigned *bar = (unsigned *)(a.ctrl + 32);
+  volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
+  __shared__ double sh[TMA_WARPS];
+  __shared__ int s_rng[15];
+  __shared__ __align__(8) unsigned long long s_full[TMA_WARPS][TMA_STAGES];
+  char *my = smem + (size_t)warp * TMA_STAGES * TMA_STAGE_BYTES;
+  if (a.sctl && a.sctl[SCTL_STOP]) return;
+  if (threadIdx.x < 15) s_rng[threadIdx.x] = a.rng[((threadIdx.x / 3) * P + rank) * 3 + (threadIdx.x % 3)];
+  if (lane == 0) for (int q = 0; q < TMA_STAGES; q++) mbar_init(&s_full[warp][q], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned phbits = 0u;   // bit q = parity the next wait on stage q expects
+  int it = 0;
+  bool done = false;
+  unsigned flags = 0;
+  double maxres = 0.0;
+  unsigned long long epoch = MULTI ? mail[MAIL_EPOCH] : 0ull;
+  while (!done && it < a.max_inner) {
+    it++;
+    if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
+    double tmax = 0.0;
+    for (int c = 0; c < 5; c++) {
+      const int s_beg = s_rng[3 * c] + wg, s_bnd = s_rng[3 * c + 1], s_end = s_rng[3 * c + 2];
+      bool waited = !MULTI;
+      // prologue: fill the ring
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < TMA_STAGES; q++) { const int sq = s_beg + q * nw; if (sq < s_end) tma_issue<EXACT>(a, sq, my + q * TMA_STAGE_BYTES, &s_full[warp][q]); }
+      }
+      int k = 0;
+      for (int s = s_beg; s < s_end; s += nw, k++) {
+        const int q = k % TMA_STAGES;
+        const char *st = my + q * TMA_STAGE_BYTES;
+        if (MULTI && !waited && s >= s_bnd) {
+          if (lane == 0) wait_peers(a.cm, epoch);
+          __syncwarp();
+          waited = true;
+        }
+        mbar_wait(&s_full[warp][q], (phbits >> q) & 1u);
+        phbits ^= 1u << q;
+        const int p = s * 32 + lane;
+        const int n = ((const unsigned char *)(st + ST_DEG))[lane];
+        bool skip = (n == UFM_DEG_PAD);
+        if (GLFIX) { if (!skip && (a.mflag[p] & 2)) skip = true; }
+        if (!skip) {
+          const long long o = a.off[s];
+          const int w = (int)((a.off[s + 1] - o) >> 5);
+          switch (w) {  // warp-uniform
+            case 3: tmax = sor_row_st<3, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            case 4: tmax = sor_row_st<4, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            case 5: tmax = sor_row_st<5, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            case 6: tmax = sor_row_st<6, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            case 7: tmax = sor_row_st<7, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            case 8: tmax = sor_row_st<8, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
+            default: {  // unstaged slice (w > TMA_WMAX or w < 3): generic path with the same accumulation order
+              const double2 u = a.UV[p];
+              const double h = EXACT ? a.nxy0[p] : a.nxysum[p];
+              double sumU = 0.0, sumV = 0.0, Uxy = u.x * h, Vxy = u.y * h;
+              for (int cc = 0; cc < w; cc++) {
+                if (cc < n) {
+                  const long long e = o + (long long)cc * 32 + lane;
+                  const double2 nbv = a.UV[a.idx[e]];
+                  sumU = sumU + nbv.x * a.cU[e];
+                  sumV = sumV + nbv.y * a.cV[e];
+                  if (EXACT) { const double t = a.nxy[e]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+                }
+              }
+              const double2 e2 = a.E[p], r2 = a.RHS[p];
+              const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
+              const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
+              const double resU = (LHSx - r2.x) / e2.x;
+              const double resV = (LHSy - r2.y) / e2.y;
+              tmax = fmax(tmax, fabs(resU));
+              tmax = fmax(tmax, fabs(resV));
+              store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
+            }
+          }
+        }
+        __syncwarp();   // every lane is done reading this stage: refill it with the slice TMA_STAGES ahead
+        if (lane == 0) { const int sn = s + TMA_STAGES * nw; if (sn < s_end) tma_issue<EXACT>(a, sn, my + q * TMA_STAGE_BYTES, &s_full[warp][q]); }
+      }
+      if (c == 4) {
+        for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) sh[warp] = tmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double m = 0.0;
+          for (int q = 0; q < TMA_WARPS; q++) m = fmax(m, sh[q]);
+          atomicMax(a.ctrl + (it % 3), (unsigned long long)__double_as_longlong(m));
+        }
+      }
+      ++epoch;
+      grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
+        if (MULTI && c == 4) {
+          const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
+          for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
+        }
+      });
+    }
+    if (MULTI) {
+      if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+      __syncthreads();
+    }
+    for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
+      if (r < a.bc_end) store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r));
+      else {
+        const int k = r - a.bc_end;
+        if (!((a.corner_mask >> k) & 1)) continue;
+        const int n = a.corner[4 + k];
+        double su = 0.0, sv = 0.0;
+        for (int q = 0; q < n; q++) {
+          const int row = a.corner_row[k * 16 + q];
+          const double2 v = row >= 0 ? bc_mean(a, row) : a.UV[a.corner_nbr[k * 16 + q]];
+          su = su + v.x; sv = sv + v.y;
+        }
+        store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
+      }
+    }
+    ++epoch;
+    grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
+    if (MULTI) {
+      unsigned long long r = 0ull;
+      for (int q = 0; q < P; q++) { const unsigned long long v = mail[MAIL_RESID + (it % 3) * UFM_MAX_RANKS + q]; r = v > r ? v : r; }
+      maxres = __longlong_as_double((long long)r);
+      if (mail[MAIL_ABORT]) { flags |= 4; done = true; }
+    } else {
+      maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (it % 3))));
+    }
+    if (!a.force_iters && !done) {
+      if (maxres < a.tol) done = true;
+      else if (maxres > 1E6) {
+        for (int p = tid; p < a.Mp; p += nt) a.UV[p] = make_double2(0.0, 0.0);
+        flags |= 1; done = true;
+      } else if (it == a.max_inner) flags |= 2;
+    }
+  }
+  if (MULTI) {
+    if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+    __syncthreads();
+    if (tid == 0) mail[MAIL_EPOCH] = epoch;
+  }
+  if (tid == 0) {
+    a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres);
+    if (a.sctl) {   // bookkeeping of solve_SSA's outer loop (:530-540)
+      a.sctl[SCTL_NINNER] += (unsigned long long)it; a.sctl[SCTL_NLAST] = (unsigned long long)it;
+      a.sctl[SCTL_MAXRES] = (unsigned long long)__double_as_longlong(maxres);
+      if (flags & 2) a.sctl[SCTL_RC] |= 1ull;
+      if (flags & 4) { a.sctl[SCTL_RC] |= 4ull; a.sctl[SCTL_STOP] = 1ull; }
+      if (flags & 1) {
+        if (a.sctl[SCTL_RESET]) { a.sctl[SCTL_RC] |= 2ull; a.sctl[SCTL_STOP] = 1ull; }
+        else a.sctl[SCTL_RESET] = 1ull;
+      }
+    }
+  }
 }
 
 // all-gather of the final (U,V): every rank pushes its own rows to all peers (partitioned runs only)
@@ -690,25 +1038,43 @@ int ufm_k_ssa_prepare(ufm_handle *h)
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_prepare");
 }
 
-int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
+static void fill_visc_args(ufm_handle *h, ViscArgs &a, bool fuse, bool device_ctl)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
-  ViscArgs a;
   a.cm = h->comm; a.rng = m.rng_dev;
   a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
   a.Hm = s.Hm; a.UV = s.UV;
   a.visc_A = pow(h->P.m_enh_ssa * 0.5 * s.A_flow_const, -1.0 / UFM_N_FLOW);
   a.Afac = s.realistic_A ? s.Afac : nullptr;
   a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
-  int grid = h->num_sms * 8;
-  k_ssa_viscosity<false><<<grid, 256, 0, h->stream>>>(a);
+  a.fuse_setup = fuse ? 1 : 0; a.mflag = s.mflag; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.cU0 = m.m_cU0; a.cV0 = m.m_cV0;
+  a.thr = pow(100.0, 0.30); a.S = s.S; a.RHS = s.RHS; a.E = s.E;
+  a.sctl = device_ctl ? s.ctrl + SCTL_BASE : nullptr;
+}
+
+// one viscosity evaluation (+ fused sliding term / linear-system setup) and the RN sums; no host synchronisation
+static int enqueue_viscosity(ufm_handle *h, bool fuse, bool device_ctl)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  if (m.P > 1 && !h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
+  ViscArgs a;
+  fill_visc_args(h, a, fuse, device_ctl);
+  k_ssa_viscosity<false><<<h->num_sms * 8, 256, 0, h->stream>>>(a);
   if (m.P > 1) { k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm); h->cnt.kernel_launches++; }
-  k_sum_partials<<<1, 256, 0, h->stream>>>(m.n_chunks, s.partials, s.scal);
+  k_sum_partials<<<1, 1024, 0, h->stream>>>(m.m.n_slices, s.partials, s.scal, device_ctl ? s.ctrl + SCTL_BASE : nullptr, h->P.SSA_RN_tol);
   h->cnt.kernel_launches += 2;
+  return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
+}
+
+int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2])
+{
+  DevState &s = h->st;
+  int rc = enqueue_viscosity(h, true, false);
+  if (rc) return rc;
   UFM_CUDA(cudaMemcpyAsync(s.scal_h, s.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
   sums2[0] = s.scal_h[0]; sums2[1] = s.scal_h[1];
-  return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
+  return 0;
 }
 
 // dU_SSA_dx_AaAc ... dV_SSA_dy_AaAc are pure diagnostics in the reference (written at ice_dynamics_module.f90:712-713, read
@@ -719,9 +1085,8 @@ int ufm_k_ssa_gradients(ufm_handle *h)
   DevMesh &m = h->mesh; DevState &s = h->st;
   ViscArgs a;
   // diagnostic gradients on ALL rows (each rank's (U,V) is complete after ufm_ssa_finish): single-rank view of the ranges
-  a.cm = h->comm; a.cm.P = 1; a.cm.rank = 0; a.rng = m.rng_all_dev;
-  a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.idx = m.m_idx; a.nx = m.m_nx; a.ny = m.m_ny; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0;
-  a.Hm = s.Hm; a.UV = s.UV; a.visc_A = 0.0; a.Afac = nullptr; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
+  fill_visc_args(h, a, false, false);
+  a.cm.P = 1; a.cm.rank = 0; a.rng = m.rng_all_dev; a.visc_A = 0.0; a.Afac = nullptr; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
   k_ssa_viscosity<true><<<grid, 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;
@@ -743,6 +1108,14 @@ typedef void (*sor_kernel_t)(SorArgs);
 static sor_kernel_t pick_sor(const ufm_handle *h)
 {
   const bool ex = h->P.exact_xy != 0, gl = h->P.use_analytical_GL_flux != 0, mu = h->mesh.P > 1;
+  if (h->sor_tma) {
+    if (mu) {
+      if (ex) return gl ? k_ssa_sor_tma<true, true, true> : k_ssa_sor_tma<true, false, true>;
+      return gl ? k_ssa_sor_tma<false, true, true> : k_ssa_sor_tma<false, false, true>;
+    }
+    if (ex) return gl ? k_ssa_sor_tma<true, true, false> : k_ssa_sor_tma<true, false, false>;
+    return gl ? k_ssa_sor_tma<false, true, false> : k_ssa_sor_tma<false, false, false>;
+  }
   if (mu) {
     if (ex) return gl ? k_ssa_sor<true, true, true> : k_ssa_sor<true, false, true>;
     return gl ? k_ssa_sor<false, true, true> : k_ssa_sor<false, false, true>;
@@ -754,17 +1127,18 @@ static sor_kernel_t pick_sor(const ufm_handle *h)
 int ufm_sor_configure(ufm_handle *h)
 {
   int per_sm = 0;
-  UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, 0));
+  h->sor_block = h->sor_tma ? TMA_WARPS * 32 : SOR_BLOCK;
+  h->sor_smem = h->sor_tma ? (size_t)TMA_WARPS * TMA_STAGES * TMA_STAGE_BYTES : 0;
+  if (h->sor_smem) UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sor_smem));
+  UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, h->sor_smem));
   if (per_sm < 1) return ufm_set_error(-3, "SOR kernel cannot be made resident");
   h->sor_grid = per_sm * h->num_sms;
   return 0;
 }
 
-int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *st)
+static int enqueue_sor(ufm_handle *h, int max_inner, int force_iters, bool device_ctl, cudaEvent_t e0, cudaEvent_t e1)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
-  int rc = ufm_sor_configure(h);
-  if (rc) return rc;
   if (m.P > 1 && !h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
   SorArgs a;
   a.cm = h->comm; a.xmask = m.m_xmask; a.rng = m.rng_dev;
@@ -777,18 +1151,28 @@ int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *
   a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
   a.corner_nbr = m.corner_nbr; a.corner_row = m.corner_row;
   a.Mp = m.Mp; a.max_inner = max_inner; a.force_iters = force_iters; a.omega = h->P.SSA_SOR_omega; a.tol = h->P.SSA_max_residual_UV;
-  a.ctrl = s.ctrl;
+  a.ctrl = s.ctrl; a.sctl = device_ctl ? s.ctrl + SCTL_BASE : nullptr;
   UFM_CUDA(cudaMemsetAsync(s.ctrl, 0, 16 * sizeof(unsigned long long), h->stream));
   void *args[] = {&a};
-  UFM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  UFM_CUDA(cudaLaunchCooperativeKernel((void *)pick_sor(h), dim3(h->sor_grid), dim3(h->sor_block), args, 0, h->stream));
-  UFM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  UFM_CUDA(cudaEventRecord(e0, h->stream));
+  UFM_CUDA(cudaLaunchCooperativeKernel((void *)pick_sor(h), dim3(h->sor_grid), dim3(h->sor_block), args, h->sor_smem, h->stream));
+  UFM_CUDA(cudaEventRecord(e1, h->stream));
+  h->cnt.kernel_launches++; h->cnt.sor_launches++;
+  return 0;
+}
+
+int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *st)
+{
+  DevState &s = h->st;
+  int rc = ufm_sor_configure(h);
+  if (rc) return rc;
+  if ((rc = enqueue_sor(h, max_inner, force_iters, false, h->ev0, h->ev1))) return rc;
   unsigned long long *res = (unsigned long long *)(s.scal_h + 8);
   UFM_CUDA(cudaMemcpyAsync(res, s.ctrl + 8, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   UFM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->cnt.kernel_launches++; h->cnt.sor_launches++; h->cnt.sor_ms += ms; h->cnt.sor_iterations += (long long)res[0];
+  h->cnt.sor_ms += ms; h->cnt.sor_iterations += (long long)res[0];
   if (st) {
     st->n_inner_last = (int)res[0];
     st->did_reset = (int)(res[1] & 1);
@@ -798,6 +1182,46 @@ int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *
     memcpy(&r, &res[2], sizeof(r));
     st->last_max_residual = r;
   }
+  return 0;
+}
+
+// The outer (viscosity) loop of solve_SSA (:501-543) with device-side control flow: UFM_OUTER_BATCH outer iterations are
+// enqueued back to back (viscosity+setup, RN reduction, SOR) and every kernel returns at once when SCTL_STOP is set, so
+// the host synchronises once per batch instead of twice per outer iteration.
+#define UFM_OUTER_BATCH 10
+int ufm_k_ssa_outer_loop(ufm_handle *h, ufm_ssa_stats *st)
+{
+  DevState &s = h->st;
+  int rc = ufm_sor_configure(h);
+  if (rc) return rc;
+  if (!h->ev_pool[0]) for (int k = 0; k < 2 * UFM_OUTER_BATCH; k++) UFM_CUDA(cudaEventCreate(&h->ev_pool[k]));
+  UFM_CUDA(cudaMemsetAsync(s.ctrl + SCTL_BASE, 0, 8 * sizeof(unsigned long long), h->stream));
+  unsigned long long *c = (unsigned long long *)(s.scal_h + 24);
+  const int max_outer = h->P.SSA_max_outer_loops;
+  int launched = 0;
+  long long inner_before = 0;
+  bool stop = false;
+  while (!stop && launched < max_outer) {
+    const int nb = (max_outer - launched) < UFM_OUTER_BATCH ? (max_outer - launched) : UFM_OUTER_BATCH;
+    for (int k = 0; k < nb; k++) {
+      if ((rc = enqueue_viscosity(h, true, true))) return rc;
+      if ((rc = enqueue_sor(h, h->P.SSA_max_inner_loops, 0, true, h->ev_pool[2 * k], h->ev_pool[2 * k + 1]))) return rc;
+    }
+    launched += nb;
+    UFM_CUDA(cudaMemcpyAsync(c, s.ctrl + SCTL_BASE, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    UFM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < nb; k++) { float ms = 0.f; UFM_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * k], h->ev_pool[2 * k + 1])); h->cnt.sor_ms += ms; }
+    h->cnt.sor_iterations += (long long)c[SCTL_NINNER] - inner_before;
+    inner_before = (long long)c[SCTL_NINNER];
+    stop = c[SCTL_STOP] != 0;
+  }
+  double d;
+  st->n_outer = (int)c[SCTL_NOUTER]; st->n_inner_total = (int)c[SCTL_NINNER]; st->n_inner_last = (int)c[SCTL_NLAST];
+  st->did_reset = (int)c[SCTL_RESET];
+  memcpy(&d, &c[SCTL_RN], sizeof(d)); st->last_RN = d;
+  memcpy(&d, &c[SCTL_MAXRES], sizeof(d)); st->last_max_residual = d;
+  st->rc = (c[SCTL_RC] & 2) ? -1 : ((c[SCTL_RC] & 1) ? 1 : 0);
+  if (c[SCTL_RC] & 4) return ufm_set_error(-7, "SOR: wait for a peer GPU timed out (partitioned run)");
   return 0;
 }
 

@@ -437,7 +437,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   ZE(na, s.mbits_Ac);
   ZE(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
-  ZE(2 * (size_t)m.n_chunks + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(MAIL_WORDS, s.mail);
+  ZE(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(MAIL_WORDS, s.mail);
   UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
 
   // staging for permuted upload/download of one field
