@@ -311,6 +311,14 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         if part:
             peak, peak_src = peak * world, peak_src + f" x {world} GPUs"
+        traffic, traffic_src = None, None
+        tf = os.path.join(ROOT, "profiles", "sor_traffic_r01.json")
+        if os.path.exists(tf):
+            tj = json.load(open(tf))
+            if abs(tj["nVAaAc"] - m.nVAaAc) <= 0.02 * m.nVAaAc and int(args.exact_xy) == 1:
+                # ncu dram__bytes_read+write per SOR iteration x mean iterations per launch of this run
+                traffic = tj["dram_bytes_per_iteration"] * cnt.sor_iterations / max(cnt.sor_launches, 1)
+                traffic_src = "ncu --set full capture of 10 forced iterations (profiles/sor_traffic_r01.json) scaled to this run's mean iterations per launch"
         t_iter = cnt.sor_ms * 1e-3 / max(cnt.sor_iterations, 1)
         achieved = cnt.sor_bytes_per_iteration / t_iter / 1e9 if cnt.sor_iterations else 0.0
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,7 +332,8 @@ def run_ours(args):
                        "ms_per_step": ms2 / args.steps, "same_trajectory_as_value": bool(same)},
                "gpu_launches": int(cnt.kernel_launches),
                "roofline": {"bound": "hbm", "kernel": "k_ssa_sor (five-colour SOR sweep, persistent cooperative)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_iteration": cnt.sor_bytes_per_iteration,
+                            "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": cnt.sor_bytes_per_iteration * cnt.sor_iterations / max(cnt.sor_launches, 1), "peak_source": peak_src, "algorithmic_bytes_per_iteration": cnt.sor_bytes_per_iteration,
                             "us_per_iteration": t_iter * 1e6, "iterations": int(cnt.sor_iterations), "launches": int(cnt.sor_launches),
                             "sor_share_of_step": cnt.sor_ms / ms},
                "ssa": {"model_years": yrs, "n_ssa_solves": int(sum(x["ssa"] for x in rows)), "n_outer": int(sum(x["n_outer"] for x in rows)),

@@ -137,6 +137,36 @@ MODULE ufemism_b200_shim
       REAL(C_DOUBLE), INTENT(OUT) :: out3( 3)
       INTEGER(C_INT)              :: rc
     END FUNCTION ufm_cfl
+    FUNCTION ufm_solve_SIA_3D( handle) BIND(C, NAME='ufm_solve_SIA_3D') RESULT( rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE          :: handle
+      INTEGER(C_INT)              :: rc
+    END FUNCTION ufm_solve_SIA_3D
+    FUNCTION ufm_host_register( handle, host, bytes) BIND(C, NAME='ufm_host_register') RESULT( rc)
+      IMPORT :: C_INT, C_PTR, C_LONG_LONG
+      TYPE(C_PTR), VALUE          :: handle
+      TYPE(C_PTR), VALUE          :: host
+      INTEGER(C_LONG_LONG), VALUE :: bytes
+      INTEGER(C_INT)              :: rc
+    END FUNCTION ufm_host_register
+    FUNCTION ufm_partition_set( handle, rank, nranks) BIND(C, NAME='ufm_partition_set') RESULT( rc)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE          :: handle
+      INTEGER(C_INT), VALUE       :: rank, nranks
+      INTEGER(C_INT)              :: rc
+    END FUNCTION ufm_partition_set
+    FUNCTION ufm_comm_export( handle, blob) BIND(C, NAME='ufm_comm_export') RESULT( rc)
+      IMPORT :: C_INT, C_PTR, C_CHAR
+      TYPE(C_PTR), VALUE          :: handle
+      CHARACTER(KIND=C_CHAR), INTENT(OUT) :: blob( 256)
+      INTEGER(C_INT)              :: rc
+    END FUNCTION ufm_comm_export
+    FUNCTION ufm_comm_connect( handle, blobs) BIND(C, NAME='ufm_comm_connect') RESULT( rc)
+      IMPORT :: C_INT, C_PTR, C_CHAR
+      TYPE(C_PTR), VALUE          :: handle
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: blobs( *)
+      INTEGER(C_INT)              :: rc
+    END FUNCTION ufm_comm_connect
     FUNCTION ufm_last_error() BIND(C, NAME='ufm_last_error') RESULT( msg)
       IMPORT :: C_PTR
       TYPE(C_PTR)                 :: msg
@@ -317,6 +347,27 @@ CONTAINS
     END IF
     CALL sync
   END SUBROUTINE solve_SSA_b200
+
+  SUBROUTINE b200_connect_gpus()
+    ! Vertex-partitioned run, one MPI rank per GPU (instead of "master only"): call after b200_upload_mesh on every rank.
+    ! MPI_ALLGATHER stands where the Python drivers use torch.distributed.
+    CHARACTER(KIND=C_CHAR) :: blob( 256)
+    CHARACTER(KIND=C_CHAR), ALLOCATABLE :: blobs(:)
+    ALLOCATE( blobs( 256 * par%n))
+    CALL b200_check( ufm_comm_export( b200_handle, blob), 'ufm_comm_export')
+    CALL MPI_ALLGATHER( blob, 256, MPI_CHARACTER, blobs, 256, MPI_CHARACTER, MPI_COMM_WORLD, ierr)
+    CALL b200_check( ufm_comm_connect( b200_handle, blobs), 'ufm_comm_connect')
+    CALL sync
+    DEALLOCATE( blobs)
+  END SUBROUTINE b200_connect_gpus
+
+  SUBROUTINE solve_SIA_3D_b200( mesh, ice)
+    ! U_3D / V_3D half of solve_SIA_3D (src/ice_dynamics_module.f90:317-367); W_3D stays with the thermodynamics on the host
+    TYPE(type_mesh),                     INTENT(IN)    :: mesh
+    TYPE(type_ice_model), TARGET,        INTENT(INOUT) :: ice
+    IF (par%master) CALL b200_check( ufm_solve_SIA_3D( b200_handle), 'solve_SIA_3D')
+    CALL sync
+  END SUBROUTINE solve_SIA_3D_b200
 
   SUBROUTINE critical_timesteps_b200( dt_D_2D_min, dt_V_2D_SSA_min, dt_V_3D_SIA_min)
     ! Replaces the three loops + MPI_ALLREDUCE MIN of determine_timesteps_and_actions
