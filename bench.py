@@ -307,6 +307,42 @@ def run_ours(args):
     e2e_value = nreg * (r2.time - t2_0) / (ms2 * 1e-3) * 3600.0
     same = abs(r2.time - r.time) <= 1e-9 * max(1.0, abs(r.time))
 
+    # steady-state SOR kernel alone (forced iteration count, no stop test), both cross-term modes, for the roofline discussion
+    sor_forced = {}
+    if not part:
+        for mode in (1, 0):
+            g.set_params(exact_xy=mode)
+            g.ssa_sor(max_inner=5, force_iters=True)
+            g.reset_counters()
+            g.ssa_sor(max_inner=100, force_iters=True)
+            c_ = g.counters()
+            us = c_.sor_ms * 1e3 / max(c_.sor_iterations, 1)
+            sor_forced[f"exact_xy={mode}"] = {"us_per_iteration": us, "achieved_GBps": c_.sor_bytes_per_iteration / (us * 1e-6) / 1e9}
+        g.set_params(exact_xy=int(args.exact_xy))
+
+    # N > 1: also time the communication-free alternative (one independent region per GPU) for the record
+    regions = None
+    if part and not args.no_regions:
+        g.close()
+        g = IceModelGPU(m, benchmark=st["benchmark"], device=local, use_analytical_GL_flux=S.CONFIG3["use_analytical_GL_flux"], exact_xy=args.exact_xy)
+        g.set_stream(stream.cuda_stream)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+            g.upload(k, st[k])
+        r3 = g.region(0.0)
+        one_by_one(r3, args.warmup)
+        barrier()
+        t3 = r3.time
+        e0.record(stream)
+        one_by_one(r3, args.steps)
+        e1.record(stream)
+        barrier()
+        ms3 = e0.elapsed_time(e1)
+        tt = torch.tensor([ms3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms3 = float(tt.item())
+        regions = {"value": world * (r3.time - t3) / (ms3 * 1e-3) * 3600.0, "unit": UNIT, "ms_per_step": ms3 / args.steps, "scaling": "weak",
+                   "what": f"{world} independent regions of the same workload, one per GPU, no communication (aggregate model-years)"}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         if part:
@@ -338,6 +374,13 @@ def run_ours(args):
                             "sor_share_of_step": cnt.sor_ms / ms},
                "ssa": {"model_years": yrs, "n_ssa_solves": int(sum(x["ssa"] for x in rows)), "n_outer": int(sum(x["n_outer"] for x in rows)),
                        "n_sor": int(sum(x["n_sor"] for x in rows))}}
+        if regions:
+            out["independent_regions_mode"] = regions
+        if sor_forced:
+            pk, _ = hbm_peak()
+            for v in sor_forced.values():
+                v["frac"] = v["achieved_GBps"] / pk
+            out["roofline"]["steady_state_100_forced_iterations"] = sor_forced
         # record the per-step counts for the CPU arms
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump({"nV": m.nV, "warmup": args.warmup, "steps": warm_rows + rows}, open(os.path.join(ROOT, "gpurun_out", "config3_step_counts.json"), "w"))
@@ -363,6 +406,7 @@ def main():
     ap.add_argument("--nv", type=int, default=1000000)
     ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-regions", action="store_true", help="N > 1: skip the extra independent-regions measurement")
     ap.add_argument("--multi", default="partition", choices=["partition", "regions"], help="what N > 1 GPUs do (see run_ours)")
     args = ap.parse_args()
     if args.warmup < 3:

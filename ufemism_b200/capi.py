@@ -16,7 +16,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libufemism_b200.so")
+LIB_PATH = os.environ.get("UFM_B200_LIB", os.path.join(_HERE, "libufemism_b200.so"))  # env override: kernel-tuning builds only
 HEADER = os.path.join(_HERE, "..", "include", "ufemism_b200.h")
 UFM_MAX_NZ = 32
 UFM_NT = 8

@@ -156,7 +156,7 @@ struct ufm_handle {
   DevMesh mesh;
   DevState st;
   ufm_counters cnt;
-  int sor_grid = 0, sor_block = 512;
+  int sor_grid = 0, sor_block = 1024;
   size_t sor_smem = 0;
   int sor_tma = 0;               // 1: TMA-staged SOR kernel (env UFM_SOR_TMA, default set in ufm_create)
   int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload

@@ -284,6 +284,15 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
       const int n = a.deg[p];
       double s_dn = 0.0, s_n = 0.0;
       if (n != UFM_DEG_PAD) {
+        // row-local operands of the fused epilogue are requested up front so that they are in flight together with the
+        // stencil streams (otherwise they would only be issued after the first pow())
+        double hm = 0.0, nold = 0.0, tauc = 0.0, cu0 = 0.0, cv0 = 0.0;
+        double2 rn = make_double2(0.0, 0.0);
+        unsigned char mf = 0;
+        if (!STORE_GRAD) {
+          hm = a.Hm[p]; nold = a.N[p];
+          if (a.fuse_setup) { tauc = ld_stream(a.tau_c + p); rn = ld_stream(a.rhsnum + p); cu0 = ld_stream(a.cU0 + p); cv0 = ld_stream(a.cV0 + p); mf = a.mflag[p]; }
+        }
         double ux, uy, vx, vy;
         switch (w) {
           case 2: visc_row<2>(a, o, lane, p, n, ux, uy, vx, vy); break;
@@ -311,18 +320,17 @@ __global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
         else {
           const double epsilon_sq_0 = 1E-12;
           const double eta = (a.Afac ? a.Afac[p] : a.visc_A) * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
-          const double Nn = eta * a.Hm[p];
-          const double dn = Nn - a.N[p];
+          const double Nn = eta * hm;
+          const double dn = Nn - nold;
           s_dn = dn * dn; s_n = Nn * Nn;
           a.eta[p] = eta; a.N[p] = Nn;
           if (a.fuse_setup) {   // identical expressions to k_ssa_setup
             const double delta_v = 1E-3, q_plastic = 0.30;
             const double2 u = a.UV[p];
-            const double S = a.tau_c[p] * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
-            const double2 r = a.rhsnum[p];
-            a.RHS[p] = make_double2(r.x / eta, r.y / eta);
-            double eu = a.cU0[p], ev = a.cV0[p];
-            if (a.mflag[p] & 1) { const double t = S / (a.Hm[p] * eta); eu = eu - t; ev = ev - t; }
+            const double S = tauc * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
+            a.RHS[p] = make_double2(rn.x / eta, rn.y / eta);
+            double eu = cu0, ev = cv0;
+            if (mf & 1) { const double t = S / (hm * eta); eu = eu - t; ev = ev - t; }
             a.S[p] = S;
             a.E[p] = make_double2(eu, ev);
           }
@@ -399,7 +407,7 @@ __global__ void k_ssa_setup(SetupArgs a)
 // ctrl[10]    last max residual (bits)
 // ---------------------------------------------------------------------------------------------
 #ifndef SOR_BLOCK
-#define SOR_BLOCK 512
+#define SOR_BLOCK 1024
 #endif
 #ifndef SOR_PREFETCH
 #define SOR_PREFETCH 0
