@@ -758,7 +758,8 @@ static void solve_SSA_linearised_r(const ora_mesh *m, const rank_t *r, ora_ice *
     } else if (inner_loop_i == max_inner) { warn = 1; }
   }
   SYNC
-  if (r->i == 0) { *n_inner_out = inner_loop_i; *max_res_out = max_residual_UV; *did_reset_out = did_reset; *warn_out = warn; }
+  /* every rank holds the same values (the reference's loop variables are rank-local copies too) */
+  *n_inner_out = inner_loop_i; *max_res_out = max_residual_UV; *did_reset_out = did_reset; *warn_out = warn;
 }
 
 /* solve_SSA, src/ice_dynamics_module.f90:408-557 */

@@ -430,3 +430,27 @@ def test_full_size_thickness_update_conserves_mass(big_case):
     lost_to_edge = float((m.A[~inner] * H0[~inner]).sum())
     assert abs(dV - smb) <= 1e-9 * abs(smb) + lost_to_edge + 1e-6 * float((m.A * H0).sum()) * dt
     assert (H1 >= -1e-9).all()
+
+
+def test_solve_SSA_warning_and_instability_paths(mesh_2k):
+    """Error behaviour of solve_SSA (src/ice_dynamics_module.f90:679-689, 533-540): hitting SSA_max_inner_loops only warns
+    (rc 1, run continues); max_res > 1e6 resets the velocities once; a second reset aborts (rc -1).  Same on both sides."""
+    from ufemism_b200.capi import UfmError
+    st = S.state_ssa_icestream(mesh_2k, scale=750e3 / 1800e3, Hb=-250.0, H_shelf=150.0)
+    # (1) too few inner loops -> warning, identical counts and velocities
+    o = make_oracle(mesh_2k, st, nthreads=2, use_analytical_GL_flux=1, SSA_max_inner_loops=3, SSA_max_outer_loops=6)
+    g = make_gpu(mesh_2k, st, use_analytical_GL_flux=1, SSA_max_inner_loops=3, SSA_max_outer_loops=6)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert so.rc == 1 and sg.rc == 1
+    assert (sg.n_outer, sg.n_inner_total) == (so.n_outer, so.n_inner_total) == (6, 18)
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10
+    # (2) over-relaxation far beyond 2 -> SOR diverges -> reset -> diverges again -> abort
+    o = make_oracle(mesh_2k, st, nthreads=2, use_analytical_GL_flux=1, SSA_SOR_omega=3.5)
+    g = make_gpu(mesh_2k, st, use_analytical_GL_flux=1, SSA_SOR_omega=3.5)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    so = o.solve_SSA()
+    assert so.rc == -1 and so.did_reset == 1
+    with pytest.raises(UfmError) as ei:
+        g.solve_SSA()
+    assert ei.value.rc == -1 and "unstable" in str(ei.value)
