@@ -454,3 +454,46 @@ def test_solve_SSA_warning_and_instability_paths(mesh_2k):
     with pytest.raises(UfmError) as ei:
         g.solve_SSA()
     assert ei.value.rc == -1 and "unstable" in str(ei.value)
+
+
+def test_cpp_host_mirror(mesh_2k, tmp_path):
+    """The reference's call sequence (src/UFEMISM_main_model.f90:90-135) issued from COMPILED host code through
+    host/ufemism_host.hpp (the C++ twin of the Fortran shim) reproduces the oracle running the same sequence."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "run_steps")
+    libdir = os.path.join(root, "ufemism_b200")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "host", "run_steps.cpp"), "-o", exe,
+                    "-L", libdir, "-lufemism_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    m = mesh_2k
+    st = S.state_ssa_icestream(m, scale=750e3 / 1800e3, Hb=-250.0, H_shelf=150.0)
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        np.array([m.nV, m.nAc, m.nC_mem], np.int32).tofile(f)
+        for name, dt in (("V", "f8"), ("A", "f8"), ("nC", "i4"), ("C", "i4"), ("Cw", "f8"), ("edge_index", "i4"), ("Nx", "f8"), ("Ny", "f8"), ("Aci", "i4"),
+                         ("iAci", "i4"), ("edge_index_Ac", "i4"), ("Nx_Ac", "f8"), ("Ny_Ac", "f8"), ("No_Ac", "f8"), ("Np_Ac", "f8"), ("nCAaAc", "i4"), ("CAaAc", "i4"),
+                         ("Nx_AaAc", "f8"), ("Ny_AaAc", "f8"), ("Nxx_AaAc", "f8"), ("Nxy_AaAc", "f8"), ("Nyy_AaAc", "f8"), ("colour_vi", "i4"), ("colour_nV", "i4")):
+            np.asfortranarray(getattr(m, name), dtype=dt).ravel(order="F").tofile(f)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+            np.asarray(st[k], "f8").tofile(f)
+    n_steps = 3
+    subprocess.run([exe, inp, outp, str(n_steps), "1"], check=True, timeout=300)
+    raw = open(outp, "rb").read()
+    N = m.nV
+    Hi, U, V, Usia = (np.frombuffer(raw, "f8", N, i * 8 * N) for i in range(4))
+    mask = np.frombuffer(raw, "i4", N, 32 * N)
+    n_outer, n_inner = np.frombuffer(raw, "i4", 2, 36 * N)
+    time = np.frombuffer(raw, "f8", 1, 36 * N + 8)[0]
+    # the oracle, same sequence
+    o = make_oracle(m, st, nthreads=2, use_analytical_GL_flux=1)
+    t, dt, no, ni = 0.0, 0.0, 0, 0
+    for _ in range(n_steps):
+        o.calculate_ice_thickness_change(dt); o.update_general_ice_model_data(t); o.solve_SIA()
+        s_ = o.solve_SSA(); no += s_.n_outer; ni += s_.n_inner_total
+        dt = min(min(o.determine_timesteps()), 10.0); t += dt
+    assert (n_outer, n_inner) == (no, ni) and abs(time - t) <= 1e-12 * t
+    assert rel_l2(Hi, o["Hi"]) <= 1e-8 and rel_l2(U, o["U_SSA"]) <= 1e-10 and rel_l2(V, o["V_SSA"]) <= 1e-10
+    np.testing.assert_allclose(Usia, o["U_SIA"], rtol=1e-12, atol=1e-12 * np.abs(o["U_SIA"]).max())
+    assert np.array_equal(mask, o["mask"])
