@@ -497,3 +497,34 @@ def test_cpp_host_mirror(mesh_2k, tmp_path):
     assert rel_l2(Hi, o["Hi"]) <= 1e-8 and rel_l2(U, o["U_SSA"]) <= 1e-10 and rel_l2(V, o["V_SSA"]) <= 1e-10
     np.testing.assert_allclose(Usia, o["U_SIA"], rtol=1e-12, atol=1e-12 * np.abs(o["U_SIA"]).max())
     assert np.array_equal(mask, o["mask"])
+
+
+def test_hybrid_run_with_mesh_update(mesh_2k):
+    """BASELINE config 4 in miniature: hybrid SIA/SSA steps, then a CPU mesh update (new mesh, Hi remapped on the host,
+    everything else reallocated: src/UFEMISM_main_model.f90:240-315, src/ice_dynamics_module.f90:1208-1218) -> device
+    re-upload -> more steps.  U_SSA restarts from zero after the update on both sides."""
+    from scipy.spatial import cKDTree
+    st = scenario(mesh_2k, "mismip")
+    o, g = make_oracle(mesh_2k, st, nthreads=2, use_analytical_GL_flux=1), make_gpu(mesh_2k, st, use_analytical_GL_flux=1)
+    ro, rg = o.region(0.0), g.region(0.0)
+    o.run_model(ro, 1e12, max_steps=2); g.run_model(rg, 1e12, max_steps=2)
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+    # "run_model_update_mesh": a finer mesh; the host remaps Hi (nearest vertex here), Hb/SL/SMB are re-evaluated
+    m2 = get_mesh(3500, seed=99)
+    idx = cKDTree(mesh_2k.V).query(m2.V)[1]
+    st2 = scenario(m2, "mismip")
+    Hi_o, Hi_g = o["Hi"][idx].copy(), g.download("Hi")[idx].copy()
+    Hi_o[m2.edge_index > 0] = 0.0; Hi_g[m2.edge_index > 0] = 0.0
+    o2 = make_oracle(m2, dict(st2, Hi=Hi_o), nthreads=2, use_analytical_GL_flux=1)
+    g.upload_mesh(m2)
+    for k in ("Hb", "SL", "SMB_year", "BMB"):
+        g.upload(k, st2[k])
+    g.upload("Hi", Hi_g)
+    assert not g.download("U_SSA").any()
+    # all "do" flags true after a mesh update (:307-313), dt carried over
+    ro2, rg2 = o2.region(ro.time), g.region(rg.time)
+    ro2.dt = ro.dt; rg2.dt = rg.dt
+    o2.run_model(ro2, 1e12, max_steps=3); g.run_model(rg2, 1e12, max_steps=3)
+    assert (rg2.n_steps, rg2.n_sor_total, rg2.n_outer_total) == (ro2.n_steps, ro2.n_sor_total, ro2.n_outer_total)
+    assert rel_l2(g.download("Hi"), o2["Hi"]) <= 1e-8
+    assert rel_l2(g.download("U_SSA"), o2["U_SSA"]) <= 1e-8
