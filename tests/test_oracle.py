@@ -42,23 +42,45 @@ def test_bueler_solution_and_mass_balance_consistent():
         assert Mb == pytest.approx(lam / 2000.0 * H, rel=1e-13)
 
 
-@pytest.mark.parametrize("nv,tol", [(2500, 0.08), (10000, 0.05)])
+@pytest.mark.parametrize("nv,tol", [(2500, 0.025), (10000, 0.015)])
 def test_halfar_run_tracks_analytic_solution(nv, tol):
-    """SIA + mass continuity through run_model for 50 yr vs Halfar_solution(t): discretisation-level agreement,
-    improving with resolution; volume conserved (zero SMB, no clipping at the dome)."""
+    """SIA + mass continuity through run_model from Halfar_solution(t = 1000 yr) for 3000 model years, against
+    Halfar_solution(t = 4000 yr): the solution changes by 21 % over the window, the run stays within 1-2 % of the closed form
+    (improving with resolution), the dome height within 0.1 %, volume is conserved (zero SMB).
+    (Started late on purpose: in the first centuries of the H0 = 5000 m dome the reference's diffusivity clip at -1e5 is active
+    and the as-coded model deliberately departs from Halfar; see test_halfar_early_phase_is_clipped.)"""
     from oracle.oracle import T_THERMO
 
     m = get_mesh(nv)
-    st = S.state_halfar(m)
+    st = S.state_halfar(m, t=1000.0)
     o = make_oracle(m, st, nthreads=4)
     vol0 = float((o["Hi"] * m.A).sum())
     r = o.region(0.0); r.dtc[T_THERMO] = 5.0
-    assert o.run_model(r, 50.0) == 0 and r.time == 50.0
-    Han = S.halfar_H(5000.0, 300000.0, m.V[:, 0], m.V[:, 1], 50.0)
+    assert o.run_model(r, 3000.0) == 0 and r.time == 3000.0
+    assert o["D_SIA_3D_Ac"].min() > -1e5
+    Han = S.halfar_H(5000.0, 300000.0, m.V[:, 0], m.V[:, 1], 4000.0)
+    assert rel_l2(st["Hi"], Han) > 0.15
     err = rel_l2(o["Hi"], Han)
     assert err < tol, err
+    assert abs(o["Hi"].max() / Han.max() - 1.0) < 2e-3
     assert abs(float((o["Hi"] * m.A).sum()) / vol0 - 1.0) < 1e-12
     test_halfar_run_tracks_analytic_solution.err = getattr(test_halfar_run_tracks_analytic_solution, "err", {}); test_halfar_run_tracks_analytic_solution.err[nv] = err
+
+
+def test_halfar_early_phase_is_clipped(mesh_2k):
+    """Reference quirk: D_SIA_3D is clipped from below at -1e5 (src/ice_dynamics_module.f90:257,285-289).  For the
+    benchmark's own initial state (H0 = 5000 m at t = 0) the clip is active over most of the dome, so the as-coded model thins
+    several times more slowly than Halfar's solution at first."""
+    m = mesh_2k
+    o = make_oracle(m, S.state_halfar(m))
+    r = o.region(0.0)
+    o.run_model(r, 1e12, max_steps=2)
+    assert o["D_SIA_3D_Ac"].min() == -1e5
+    rr = np.hypot(m.V[:, 0], m.V[:, 1])
+    sel = rr < 150e3
+    eps = 1e-4
+    an = (S.halfar_H(5000.0, 300000.0, m.V[:, 0], m.V[:, 1], eps) - S.halfar_H(5000.0, 300000.0, m.V[:, 0], m.V[:, 1], 0.0)) / eps
+    assert o["dHi_dt"][sel].mean() / an[sel].mean() < 0.3
 
 
 def test_halfar_error_decreases_with_resolution():
