@@ -180,6 +180,22 @@ int ufm_state_download(ufm_handle *h, int field, void *host);
 int ufm_host_register(ufm_handle *h, void *host, unsigned long long bytes);
 int ufm_host_unregister(ufm_handle *h, void *host);
 
+/* ---- mesh update data path (row N3): APPLICATION of the conservative remapping on the device, so that Hi (and the other
+ *      fields the reference remaps, src/ice_dynamics_module.f90:1208-1218) need not travel to the host when the CPU
+ *      replaces the mesh.  The remapping weights (type_remapping_conservative, src/data_types_module.f90:544-556) are still
+ *      BUILT on the CPU (src/mesh_mapping_module.f90:673-3843, out of scope) and handed over as they are.
+ *      Protocol: ufm_remap_stash(field) on the old mesh -> ufm_mesh_upload(new mesh) -> ufm_remap_apply(field, map, order).
+ *      Replaces remap_cons_1st_order_2D / remap_cons_2nd_order_2D (src/mesh_mapping_module.f90:3964-3983, 4010-4043). ---- */
+typedef struct ufm_remap_cons {
+  int nV_dst;               /* vertices of the new mesh */
+  int n_tot;                /* entries of vi / w0 / w1x / w1y */
+  const int *vli1, *vli2;   /* (nV_dst) 1-based inclusive entry range of each destination vertex */
+  const int *vi;            /* (n_tot) 1-based source vertex */
+  const double *w0, *w1x, *w1y; /* (n_tot); w1x, w1y may be NULL for order 1 */
+} ufm_remap_cons;
+int ufm_remap_stash(ufm_handle *h, int field);
+int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int order);
+
 /* ---- the four drop-in entry points ---- */
 /* body of calculate_ice_thickness_change (src/ice_dynamics_module.f90:31-237) */
 int ufm_thickness_update(ufm_handle *h, double dt);

@@ -93,6 +93,7 @@ def lib():
         L.ora_apply_Neumann_boundary_AaAc.argtypes = [p, p, p]
         L.ora_get_mesh_derivatives.argtypes = [p, p, p, p, p]
         L.ora_map_Ac_to_Aa.argtypes = [p, p, p, p]
+        L.ora_remap_cons_2D.argtypes = [i, i, p, p, p, p, p, p, p, p, p, p]
         L.ora_Halfar_solution.argtypes = [d] * 5
         L.ora_Halfar_solution.restype = d
         L.ora_Bueler_solution.argtypes = [d] * 6
@@ -190,6 +191,21 @@ class Oracle:
         n, r, rs = ctypes.c_int(0), ctypes.c_double(0), ctypes.c_int(0)
         warn = self.L.ora_solve_SSA_linearised(*self._a(), int(max_inner), int(force_iters), ctypes.byref(n), ctypes.byref(r), ctypes.byref(rs))
         return n.value, r.value, rs.value, warn
+
+    def get_mesh_derivatives(self, d):
+        ddx, ddy = np.zeros(self.mesh.nV), np.zeros(self.mesh.nV)
+        d = np.ascontiguousarray(d, np.float64)
+        self.L.ora_get_mesh_derivatives(ctypes.byref(self.cm), ctypes.byref(self.cfg), d.ctypes.data, ddx.ctypes.data, ddy.ctypes.data)
+        return ddx, ddy
+
+    def remap_cons_2D(self, order, vli1, vli2, vi, w0, w1x, w1y, d_src):
+        """Apply a conservative remapping from this oracle's mesh to a destination mesh with len(vli1) vertices."""
+        ddx, ddy = self.get_mesh_derivatives(d_src)
+        a = [np.ascontiguousarray(x, np.int32) for x in (vli1, vli2, vi)] + [np.ascontiguousarray(x, np.float64) for x in (w0, w1x if w1x is not None else w0, w1y if w1y is not None else w0)]
+        d_src = np.ascontiguousarray(d_src, np.float64)
+        out = np.zeros(len(a[0]))
+        self.L.ora_remap_cons_2D(int(order), len(a[0]), *[x.ctypes.data for x in a], d_src.ctypes.data, ddx.ctypes.data, ddy.ctypes.data, out.ctypes.data)
+        return out
 
     def apply_Neumann_boundary_AaAc(self, d):
         assert d.dtype == np.float64 and d.size == self.mesh.nVAaAc

@@ -889,6 +889,20 @@ void ora_map_Ac_to_Aa(const ora_mesh *m, const ora_config *c, const double *d_Ac
   { rank_t r = rank_of(m); map_Ac_to_Aa_r(m, &r, d_Ac, d_Aa); }
 }
 
+/* remap_cons_1st_order_2D / remap_cons_2nd_order_2D, src/mesh_mapping_module.f90:3964-3983, 4010-4043 (application only;
+ * ddx_src, ddy_src = get_mesh_derivatives of d_src on the source mesh, computed by the caller with ora_get_mesh_derivatives) */
+void ora_remap_cons_2D(int order, int nV_dst, const int *vli1, const int *vli2, const int *vi, const double *w0, const double *w1x, const double *w1y,
+                       const double *d_src, const double *ddx_src, const double *ddy_src, double *d_dst)
+{
+  for (int vi_dst = 1; vi_dst <= nV_dst; vi_dst++) {
+    A1(d_dst, vi_dst) = 0.0;
+    for (int vli = A1(vli1, vi_dst); vli <= A1(vli2, vi_dst); vli++) {
+      if (order == 1) A1(d_dst, vi_dst) = A1(d_dst, vi_dst) + (A1(d_src, A1(vi, vli)) * A1(w0, vli));
+      else A1(d_dst, vi_dst) = A1(d_dst, vi_dst) + (A1(d_src, A1(vi, vli)) * A1(w0, vli)) + (A1(ddx_src, A1(vi, vli)) * A1(w1x, vli)) + (A1(ddy_src, A1(vi, vli)) * A1(w1y, vli));
+    }
+  }
+}
+
 /* ============================================================================================
  * determine_timesteps_and_actions, critical time steps, src/UFEMISM_main_model.f90:738-778.
  * out3 = {dt_D_2D_min, dt_V_2D_SSA_min, dt_V_3D_SIA_min}, each already times 0.9.

@@ -129,6 +129,8 @@ int  ora_solve_SSA_linearised(const ora_mesh *m, ora_ice *ice, const ora_config 
                               int *n_inner, double *max_residual, int *did_reset);
 void ora_apply_Neumann_boundary_AaAc(const ora_mesh *m, const ora_config *c, double *d_AaAc);
 void ora_get_mesh_derivatives(const ora_mesh *m, const ora_config *c, const double *d, double *ddx, double *ddy);
+void ora_remap_cons_2D(int order, int nV_dst, const int *vli1, const int *vli2, const int *vi, const double *w0, const double *w1x, const double *w1y,
+                       const double *d_src, const double *ddx_src, const double *ddy_src, double *d_dst);
 void ora_map_Ac_to_Aa(const ora_mesh *m, const ora_config *c, const double *d_Ac, double *d_Aa);
 
 /* benchmark forcing + analytic solutions (host side in the reference too) */

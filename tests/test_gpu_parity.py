@@ -550,3 +550,32 @@ def test_halfar_250k_vs_analytic_and_oracle():
     assert rel_l2(H, Han) < 0.004                  # ... and the run followed it
     assert abs(H.max() / Han.max() - 1.0) < 1e-3
     assert abs(float((H * m.A).sum()) / vol0 - 1.0) < 1e-9
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_conservative_remap_application(mesh_2k, order):
+    """Row N3: remap_cons_{1st,2nd}_order_2D applied on the device across a mesh update, bit-exact against the oracle.  The
+    weights are synthetic (3 nearest source vertices, inverse-distance w0, w1 = w0 * offset); building real conservative
+    weights is CPU work outside the path."""
+    from scipy.spatial import cKDTree
+    st = scenario(mesh_2k, "mismip")
+    o, g = make_oracle(mesh_2k, st), make_gpu(mesh_2k, st)
+    m2 = get_mesh(3500, seed=99)
+    dist, idx = cKDTree(mesh_2k.V).query(m2.V, k=3)
+    w = 1.0 / (dist + 1.0); w /= w.sum(1, keepdims=True)
+    n = m2.nV
+    vli1 = 1 + 3 * np.arange(n); vli2 = vli1 + 2
+    vli2[::7] = vli1[::7] + 1                      # ragged: some destination vertices use only two entries
+    vli1[5::11] = 1; vli2[5::11] = 0               # ... and some none (empty range -> 0)
+    vi = (idx + 1).ravel(); w0 = w.ravel()
+    w1x = (w * (m2.V[:, None, 0] - mesh_2k.V[idx, 0])).ravel(); w1y = (w * (m2.V[:, None, 1] - mesh_2k.V[idx, 1])).ravel()
+    want = o.remap_cons_2D(order, vli1, vli2, vi, w0, w1x if order == 2 else None, w1y if order == 2 else None, st["Hi"])
+    g.remap_stash("Hi")
+    g.upload_mesh(m2)
+    g.remap_apply("Hi", vli1, vli2, vi, w0, *( (w1x, w1y) if order == 2 else ()))
+    got = g.download("Hi")
+    assert_bits_equal(got, want, "remapped Hi")
+    assert got[5] == 0.0 and np.abs(got).max() > 100.0
+    from ufemism_b200.capi import UfmError
+    with pytest.raises(UfmError):
+        g.remap_apply("Hi", vli1, vli2, vi, w0)    # nothing stashed any more

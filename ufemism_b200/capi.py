@@ -67,6 +67,10 @@ class Region(ctypes.Structure):
                 ("n_outer_total", ctypes.c_long), ("dt_crit_last", ctypes.c_double * 3)]
 
 
+class RemapCons(ctypes.Structure):
+    _fields_ = [("nV_dst", ctypes.c_int), ("n_tot", ctypes.c_int)] + [(n, ctypes.c_void_p) for n in ("vli1", "vli2", "vi", "w0", "w1x", "w1y")]
+
+
 class HostIce(ctypes.Structure):
     """ufm_host_ice: host arrays (reference vertex order) moved every step in drop-in mode."""
     _fields_ = [(n, ctypes.c_void_p) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "mask_noice", "Hi_out", "Hi_prev", "dHi_dt", "Hs",
@@ -103,7 +107,7 @@ for _n, _i in FIELD_IDS.items():
     _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
 
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
-            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_thickness_update", "ufm_update_general",
+            "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
 
@@ -134,6 +138,8 @@ def load_library():
         L.ufm_state_download.argtypes = [p, i, p]
         L.ufm_host_register.argtypes = [p, p, ctypes.c_ulonglong]
         L.ufm_host_unregister.argtypes = [p, p]
+        L.ufm_remap_stash.argtypes = [p, i]
+        L.ufm_remap_apply.argtypes = [p, i, p, i]
         L.ufm_thickness_update.argtypes = [p, d]
         L.ufm_update_general.argtypes = [p, d]
         L.ufm_solve_SIA.argtypes = [p]
@@ -299,6 +305,17 @@ class IceModelGPU:
 
     def host_unregister(self, arr):
         self._ck(self.L.ufm_host_unregister(self.h, arr.ctypes.data))
+
+    def remap_stash(self, name):
+        self._ck(self.L.ufm_remap_stash(self.h, _REF_NAMES[name.upper()][0]))
+
+    def remap_apply(self, name, vli1, vli2, vi, w0, w1x=None, w1y=None):
+        order = 1 if w1x is None else 2
+        arrs = [np.ascontiguousarray(vli1, np.int32), np.ascontiguousarray(vli2, np.int32), np.ascontiguousarray(vi, np.int32), np.ascontiguousarray(w0, np.float64)]
+        arrs += [np.ascontiguousarray(w1x, np.float64), np.ascontiguousarray(w1y, np.float64)] if order == 2 else []
+        mp = RemapCons(nV_dst=len(arrs[0]), n_tot=len(arrs[2]), vli1=arrs[0].ctypes.data, vli2=arrs[1].ctypes.data, vi=arrs[2].ctypes.data, w0=arrs[3].ctypes.data,
+                       w1x=arrs[4].ctypes.data if order == 2 else None, w1y=arrs[5].ctypes.data if order == 2 else None)
+        self._ck(self.L.ufm_remap_apply(self.h, _REF_NAMES[name.upper()][0], ctypes.byref(mp), order))
 
     def download(self, name, out=None):
         fid, kind, dt = _REF_NAMES[name.upper()]

@@ -90,6 +90,7 @@ int ufm_destroy(ufm_handle *h)
   cudaStreamSynchronize(h->stream);
   ufm_mesh_free_impl(h);
   for (int k = 0; k < h->n_pinned; k++) cudaHostUnregister(h->pinned_base[k]);
+  for (auto &q : h->stash) if (q.d) { cudaFree(q.d); cudaFree(q.ddx); cudaFree(q.ddy); }
   if (h->staging) cudaFreeHost(h->staging);
   if (h->dev_staging) cudaFree(h->dev_staging);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -325,6 +326,45 @@ int ufm_host_unregister(ufm_handle *h, void *host)
       return 0;
     }
   return ufm_set_error(-2, "ufm_host_unregister: pointer was not registered");
+}
+static int stash_slot(ufm_handle *h, int field, bool create)
+{
+  for (int k = 0; k < 4; k++) if (h->stash[k].field == field) return k;
+  if (!create) return -1;
+  for (int k = 0; k < 4; k++) if (h->stash[k].field < 0) { h->stash[k].field = field; return k; }
+  return -1;
+}
+int ufm_remap_stash(ufm_handle *h, int field)
+{
+  if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
+  UFM_CUDA(cudaSetDevice(h->device));
+  FieldRef r;
+  int rc = field_ref(h, field, &r);
+  if (rc) return rc;
+  if (r.kind != K_AA || r.is_int || r.is3d || r.stride != 1 || !r.d) return ufm_set_error(-2, "ufm_remap_stash: only fp64 fields on the Aa vertices can be remapped");
+  const int slot = stash_slot(h, field, true);
+  if (slot < 0) return ufm_set_error(-2, "ufm_remap_stash: at most 4 fields can be stashed");
+  return ufm_k_remap_stash(h, slot, r.d);
+}
+int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int order)
+{
+  if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
+  UFM_CUDA(cudaSetDevice(h->device));
+  if (!map || !map->vli1 || !map->vli2 || !map->vi || !map->w0) return ufm_set_error(-2, "ufm_remap_apply: NULL pointer in the remapping arrays");
+  if (order != 1 && order != 2) return ufm_set_error(-2, "ufm_remap_apply: order must be 1 or 2");
+  if (order == 2 && (!map->w1x || !map->w1y)) return ufm_set_error(-2, "ufm_remap_apply: 2nd order needs w1x and w1y");
+  if (map->nV_dst != h->mesh.nV) return ufm_set_error(-2, "ufm_remap_apply: map is for %d destination vertices, the resident mesh has %d", map->nV_dst, h->mesh.nV);
+  const int slot = stash_slot(h, field, false);
+  if (slot < 0 || !h->stash[slot].d) return ufm_set_error(-2, "ufm_remap_apply: field %d was not stashed on the old mesh", field);
+  for (int i = 0; i < map->n_tot; i++) if (map->vi[i] < 1 || map->vi[i] > h->stash[slot].n) return ufm_set_error(-2, "ufm_remap_apply: source vertex index out of range");
+  FieldRef r;
+  int rc = field_ref(h, field, &r);
+  if (rc) return rc;
+  rc = ufm_k_remap_apply(h, slot, map, order, r.d);
+  if (rc) return rc;
+  cudaFree(h->stash[slot].d); cudaFree(h->stash[slot].ddx); cudaFree(h->stash[slot].ddy);
+  h->stash[slot] = ufm_handle::Stash();
+  return 0;
 }
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }

@@ -430,6 +430,53 @@ __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
   }
 }
 
+// ---- conservative remapping, application only (mesh_mapping_module.f90:3964-3983, 4010-4043) ----
+// gradients of an Aa field on the old mesh (get_mesh_derivatives), written in REFERENCE order next to the field itself
+struct StashArgs {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg;
+  const int *C, *dev2ref;
+  const double *Nx, *Ny, *Nx0, *Ny0, *f;
+  double *d, *ddx, *ddy;
+};
+__global__ void __launch_bounds__(256) k_remap_stash(StashArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int v = s * 32 + lane;
+    const int n = a.deg[v];
+    if (n == UFM_DEG_PAD) continue;
+    const double fv = a.f[v];
+    double gx = a.Nx0[v] * fv, gy = a.Ny0[v] * fv;
+    for (int c = 0; c < n; c++) {
+      const long long e = o + (long long)c * 32 + lane;
+      const double fj = a.f[a.C[e]];
+      gx = gx + a.Nx[e] * fj; gy = gy + a.Ny[e] * fj;
+    }
+    const int r = a.dev2ref[v];
+    a.d[r] = fv; a.ddx[r] = gx; a.ddy[r] = gy;
+  }
+}
+// one thread per destination vertex, entries accumulated in list order exactly as the reference loop does
+__global__ void __launch_bounds__(256) k_remap_apply(int nV_dst, int order, const int *__restrict__ vli1, const int *__restrict__ vli2, const int *__restrict__ vi,
+                                                     const double *__restrict__ w0, const double *__restrict__ w1x, const double *__restrict__ w1y,
+                                                     const double *__restrict__ d, const double *__restrict__ ddx, const double *__restrict__ ddy,
+                                                     const int *__restrict__ ref2dev, double *out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nV_dst) return;
+  double acc = 0.0;
+  for (int l = vli1[i]; l <= vli2[i]; l++) {
+    const int sv = vi[l - 1] - 1;
+    if (order == 1) acc = acc + (d[sv] * w0[l - 1]);
+    else acc = acc + (d[sv] * w0[l - 1]) + (ddx[sv] * w1x[l - 1]) + (ddy[sv] * w1y[l - 1]);
+  }
+  out[ref2dev[i]] = acc;
+}
+
 // ---- critical time steps (UFEMISM_main_model.f90:747-768) ----
 __device__ __forceinline__ unsigned long long ord_key(double x)
 {
@@ -623,6 +670,49 @@ int ufm_k_sia3d(ufm_handle *h)
   k_neumann_3d<<<g, 256, 0, h->stream>>>(1, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D);
   h->cnt.kernel_launches += 3;
   return ufm_cuda_check(cudaGetLastError(), "k_sia3d");
+}
+
+int ufm_k_remap_stash(ufm_handle *h, int slot, double *field_dev)
+{
+  DevMesh &m = h->mesh;
+  ufm_handle::Stash &st = h->stash[slot];
+  if (st.d) { cudaFree(st.d); cudaFree(st.ddx); cudaFree(st.ddy); st.d = st.ddx = st.ddy = nullptr; }
+  st.n = m.nV;
+  UFM_CUDA(cudaMalloc((void **)&st.d, sizeof(double) * (size_t)m.nV));
+  UFM_CUDA(cudaMalloc((void **)&st.ddx, sizeof(double) * (size_t)m.nV));
+  UFM_CUDA(cudaMalloc((void **)&st.ddy, sizeof(double) * (size_t)m.nV));
+  StashArgs a;
+  a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.C = m.aa_C; a.dev2ref = m.aa_dev2ref; a.Nx = m.aa_Nx; a.Ny = m.aa_Ny;
+  a.Nx0 = m.aa_Nx0; a.Ny0 = m.aa_Ny0; a.f = field_dev; a.d = st.d; a.ddx = st.ddx; a.ddy = st.ddy;
+  k_remap_stash<<<grid_for((long long)m.aa.n_slices * 32, 256), 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches++;
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  return ufm_cuda_check(cudaGetLastError(), "k_remap_stash");
+}
+
+int ufm_k_remap_apply(ufm_handle *h, int slot, const ufm_remap_cons *map, int order, double *field_dev)
+{
+  DevMesh &m = h->mesh;
+  ufm_handle::Stash &st = h->stash[slot];
+  int *vli1 = nullptr, *vli2 = nullptr, *vi = nullptr;
+  double *w0 = nullptr, *w1x = nullptr, *w1y = nullptr;
+  const size_t nd = (size_t)map->nV_dst, nt = (size_t)(map->n_tot > 0 ? map->n_tot : 1);
+  UFM_CUDA(cudaMalloc((void **)&vli1, 4 * nd)); UFM_CUDA(cudaMalloc((void **)&vli2, 4 * nd)); UFM_CUDA(cudaMalloc((void **)&vi, 4 * nt));
+  UFM_CUDA(cudaMalloc((void **)&w0, 8 * nt)); UFM_CUDA(cudaMalloc((void **)&w1x, 8 * nt)); UFM_CUDA(cudaMalloc((void **)&w1y, 8 * nt));
+  UFM_CUDA(cudaMemcpyAsync(vli1, map->vli1, 4 * nd, cudaMemcpyHostToDevice, h->stream));
+  UFM_CUDA(cudaMemcpyAsync(vli2, map->vli2, 4 * nd, cudaMemcpyHostToDevice, h->stream));
+  UFM_CUDA(cudaMemcpyAsync(vi, map->vi, 4 * (size_t)map->n_tot, cudaMemcpyHostToDevice, h->stream));
+  UFM_CUDA(cudaMemcpyAsync(w0, map->w0, 8 * (size_t)map->n_tot, cudaMemcpyHostToDevice, h->stream));
+  if (order == 2) {
+    UFM_CUDA(cudaMemcpyAsync(w1x, map->w1x, 8 * (size_t)map->n_tot, cudaMemcpyHostToDevice, h->stream));
+    UFM_CUDA(cudaMemcpyAsync(w1y, map->w1y, 8 * (size_t)map->n_tot, cudaMemcpyHostToDevice, h->stream));
+  }
+  k_remap_apply<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, order, vli1, vli2, vi, w0, w1x, w1y, st.d, st.ddx, st.ddy, m.aa_ref2dev, field_dev);
+  h->cnt.kernel_launches++;
+  h->cnt.h2d_bytes += 8.0 * nd + (4.0 + 8.0 * (order == 2 ? 3 : 1)) * (double)map->n_tot;
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(vli1); cudaFree(vli2); cudaFree(vi); cudaFree(w0); cudaFree(w1x); cudaFree(w1y);
+  return ufm_cuda_check(cudaGetLastError(), "k_remap_apply");
 }
 
 int ufm_k_thickness(ufm_handle *h, double dt)

@@ -163,6 +163,8 @@ struct ufm_handle {
   bool comm_connected = false;
   CommDev comm;
   void *ipc_opened[3 * UFM_MAX_RANKS] = {};
+  // remap stash: a field of the OLD mesh and its Aa gradients, reference order, survives ufm_mesh_upload
+  struct Stash { int field = -1; int n = 0; double *d = nullptr, *ddx = nullptr, *ddy = nullptr; } stash[4];
   // host buffers page-locked with ufm_host_register (base, bytes): field copies from/to them are DMA'd directly
   void *pinned_base[64] = {};
   size_t pinned_bytes[64] = {};
@@ -181,6 +183,8 @@ int ufm_cuda_check(cudaError_t e, const char *what);
 int ufm_k_geom(ufm_handle *h, double time);
 int ufm_k_sia(ufm_handle *h);
 int ufm_k_sia3d(ufm_handle *h);
+int ufm_k_remap_stash(ufm_handle *h, int slot, double *field_dev);
+int ufm_k_remap_apply(ufm_handle *h, int slot, const ufm_remap_cons *map, int order, double *field_dev);
 int ufm_k_thickness(ufm_handle *h, double dt);
 int ufm_k_cfl(ufm_handle *h, double out3[3]);
 int ufm_k_ssa_prepare(ufm_handle *h);
