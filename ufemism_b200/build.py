@@ -15,7 +15,7 @@ CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-ccbin", "/usr/bin/g++",
+    "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fopenmp", "-ccbin", "/usr/bin/g++",
 ]
 
 
@@ -37,7 +37,7 @@ def build_cuda(force=False, verbose=False):
                 cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
                 subprocess.run(cmd, check=True)
             objs.append(o)
-        subprocess.run([NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs, check=True)
+        subprocess.run([NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp"] + objs, check=True)
     return LIB
 
 

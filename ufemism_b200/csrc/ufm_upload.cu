@@ -6,6 +6,9 @@
 // (src/ice_dynamics_module.f90:642-643) -- are combined here with the same two fp64 operations
 // (this file is compiled without FMA contraction), so the products the sweep forms are bit-identical.
 #include <algorithm>
+#include <chrono>
+#include <parallel/algorithm>
+#include <omp.h>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -85,7 +88,7 @@ static void ufm_partition_owners_impl(const std::vector<double> &X, int P, std::
   if (P <= 1) return;
   std::vector<int> byx(M);
   std::iota(byx.begin(), byx.end(), 0);
-  std::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
+  __gnu_parallel::stable_sort(byx.begin(), byx.end(), [&](int a, int b) { return X[a] < X[b]; });
   for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
 }
 
@@ -139,6 +142,14 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   if (h->has_mesh) ufm_mesh_free_impl(h);
   DevMesh &m = h->mesh;
   m.nV = N; m.nAc = E; m.M = M;
+  const bool timing = getenv("UFM_UPLOAD_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ufm_mesh_upload] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
 
   // ---- coordinates of all AaAc vertices, bounding box ----
   std::vector<double> X(M), Y(M);
@@ -156,17 +167,19 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   std::vector<uint32_t> mort(M);
   for (int i = 0; i < M; i++) mort[i] = morton2(X[i], Y[i], x0, y0, sx, sy);
 
+  lap("coordinates + morton");
   // ---- Aa and Ac orders: Morton ----
   std::vector<int> aa_order(N), ac_order(E);
   std::iota(aa_order.begin(), aa_order.end(), 0);
   std::iota(ac_order.begin(), ac_order.end(), 0);
-  std::stable_sort(aa_order.begin(), aa_order.end(), [&](int a, int b) { return mort[a] < mort[b]; });
-  std::stable_sort(ac_order.begin(), ac_order.end(), [&](int a, int b) { return mort[N + a] < mort[N + b]; });
+  __gnu_parallel::stable_sort(aa_order.begin(), aa_order.end(), [&](int a, int b) { return mort[a] < mort[b]; });
+  __gnu_parallel::stable_sort(ac_order.begin(), ac_order.end(), [&](int a, int b) { return mort[N + a] < mort[N + b]; });
   m.nVp = round_up(N, UFM_SLICE); m.nAcp = round_up(E, UFM_SLICE);
   std::vector<int> aa_r2d(N), aa_d2r(m.nVp, -1), ac_r2d(E), ac_d2r(m.nAcp, -1);
   for (int p = 0; p < N; p++) { aa_r2d[aa_order[p]] = p; aa_d2r[p] = aa_order[p]; }
   for (int p = 0; p < E; p++) { ac_r2d[ac_order[p]] = p; ac_d2r[p] = ac_order[p]; }
 
+  lap("Aa/Ac sort");
   // ---- AaAc order: colour-major, (degree, Morton) inside a colour, edge block last ----
   std::vector<int> colour(M, 0);
   for (int c = 1; c <= 5; c++) {
@@ -192,6 +205,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       if (ac < 1 || ac > M) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
       if (colour[ac - 1] == colour[ai]) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", ai + 1, ac);
     }
+  lap("colour + validity checks");
   // owner rank of every AaAc row: x-strips balanced by row count (cf. partition_domain_x_balanced,
   // src/mesh_help_functions_module.f90:1337-1404, which the reference uses for mesh generation)
   const int P = h->part_n;
@@ -208,7 +222,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   std::vector<int> m_order(M);
   std::iota(m_order.begin(), m_order.end(), 0);
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
-  std::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
+  __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
     int ba = blk(a), bb = blk(b);
     if (ba != bb) return ba < bb;
     if (owner[a] != owner[b]) return owner[a] < owner[b];
@@ -239,6 +253,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   m.Mp = (int)m_d2r.size();
   m.n_chunks = m.Mp / UFM_CHUNK;
 
+  lap("AaAc sort + layout");
   // ---- AaAc sliced ELL ----
   {
     std::vector<unsigned char> deg(m.Mp, UFM_DEG_PAD);
@@ -252,6 +267,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     std::vector<double> nxy0(m.Mp, 0.0), nxysum(m.Mp, 0.0), nx0(m.Mp, 0.0), ny0(m.Mp, 0.0), cU0(m.Mp, 0.0), cV0(m.Mp, 0.0);
     std::vector<int> src(m.Mp, INT_MIN);
     double bytes = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : bytes)
     for (int s = 0; s < m.m.n_slices; s++) {
       int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
       for (int l = 0; l < UFM_SLICE; l++) {
@@ -286,7 +302,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     // who reads whom across the partition: every row reads its neighbours (sweep, viscosity, Neumann pass); a corner row
     // additionally reads the non-edge neighbours of its edge neighbours (it recomputes their boundary value)
     std::vector<unsigned char> xmask(m.Mp, 0), sowner(m.m.n_slices, 0);
-    for (int ai = 0; ai < M; ai++) {
+    for (int ai = 0; ai < M && P > 1; ai++) {
       const int r = owner[ai];
       for (int c = 1; c <= degv[ai]; c++) {
         const int ac = F2(d->CAaAc, ai + 1, c, ldM) - 1;
@@ -309,6 +325,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     UP(aa2m, m.aa2m); UP(ac2m, m.ac2m);
   }
 
+  lap("AaAc ELL fill + upload");
   // ---- Neumann boundary lists (apply_Neumann_boundary_AaAc, mesh_ArakawaC_module.f90:660-724) ----
   {
     std::vector<int> bc_pos, bc_ptr(1, 0), bc_nbr, row_of(M, -1);
@@ -351,6 +368,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     UP(bc_pos, m.bc_pos); UP(bc_ptr, m.bc_ptr); UP(bc_nbr, m.bc_nbr); UP(cn, m.corner_nbr); UP(cr, m.corner_row);
   }
 
+  lap("boundary lists");
   // ---- Aa sliced ELL ----
   {
     std::vector<unsigned char> deg(m.nVp, UFM_DEG_PAD), edge(m.nVp, 0);
@@ -366,6 +384,8 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     size_t ne = (size_t)off.back();
     std::vector<int> Cn(ne), iA(ne, 0);
     std::vector<double> nx(ne, 0.0), ny(ne, 0.0), nx0(m.nVp, 0.0), ny0(m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
+    int bad_vertex = 0;
+#pragma omp parallel for schedule(static)
     for (int s = 0; s < m.aa.n_slices; s++) {
       int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
       for (int l = 0; l < UFM_SLICE; l++) {
@@ -376,7 +396,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         for (int c = 1; c <= n; c++) {
           size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
           int vc = F2(d->C, vi + 1, c, ldV), aci = F2(d->iAci, vi + 1, c, ldV);
-          if (vc < 1 || vc > N || aci < 1 || aci > E) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", vi + 1);
+          if (vc < 1 || vc > N || aci < 1 || aci > E) { bad_vertex = vi + 1; continue; }
           Cn[e] = aa_r2d[vc - 1];
           int first = (F2(d->Aci, aci, 1, ldAc) == vi + 1);
           iA[e] = ac_r2d[aci - 1] | (first ? (int)0x80000000u : 0);
@@ -389,38 +409,45 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         sA[p] = std::sqrt(d->A[vi] / UFM_PI);
       }
     }
+    if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
     UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
     UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge);
   }
 
+  lap("Aa ELL fill + upload");
   // ---- Ac arrays ----
   {
     std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
     std::vector<double> c4[3][4], np(m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0);
     for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(m.nAcp, 0.0);
+    int bad_ac = 0;
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < E; p++) {
       int a = ac_d2r[p] + 1;
       int v[4];
+      bool ok = true;
       for (int k = 0; k < 4; k++) {
         v[k] = F2(d->Aci, a, k + 1, ldAc);
-        if (v[k] < 1 || v[k] > N) return ufm_set_error(-2, "ufm_mesh_upload: Aci out of range");
+        if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
         c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc);
       }
       aci[p] = make_int4(aa_r2d[v[0] - 1], aa_r2d[v[1] - 1], aa_r2d[v[2] - 1], aa_r2d[v[3] - 1]);
       np[p] = d->Np_Ac[a - 1];
       int ci = 0;
       for (int c = 1; c <= d->nC[v[0] - 1]; c++) if (F2(d->C, v[0], c, ldV) == v[1]) { ci = c; break; }
-      if (!ci) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,1:2) is not a connection in C", a);
+      if (!ci || !ok) { bad_ac = a; continue; }
       cw[p] = F2(d->Cw, v[0], ci, ldV);
       dx[p] = F2(d->V, v[1], 1, ldV) - F2(d->V, v[0], 1, ldV);
       dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
     }
+    if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
     UP(aci, m.ac_Aci); UP(np, m.ac_Np); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
     for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
   }
   UP(aa_r2d, m.aa_ref2dev); UP(aa_d2r, m.aa_dev2ref); UP(ac_r2d, m.ac_ref2dev); UP(ac_d2r, m.ac_dev2ref);
   UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
 
+  lap("Ac arrays + upload");
   // ---- state, zero-filled ----
   DevState &s = h->st;
   const size_t nv = m.nVp, na = m.nAcp, nm = m.Mp, nz = (size_t)h->P.nZ;
@@ -449,6 +476,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     UFM_CUDA(cudaMalloc(&h->dev_staging, need));
     h->staging_bytes = h->dev_staging_bytes = need;
   }
+  lap("state allocation");
   h->has_mesh = true;
   // single-GPU view of the peer tables: this rank only
   memset(&h->comm, 0, sizeof(h->comm));
