@@ -254,6 +254,10 @@ int ufm_run_model_host(ufm_handle *h, ufm_region *r, double t_end, long max_step
 /* ---- instrumentation ---- */
 int ufm_counters_get(ufm_handle *h, ufm_counters *out);
 int ufm_counters_reset(ufm_handle *h);
+/* tuning aid: with UFM_SOR_TRACE set in the environment the SOR kernel records, for its fourth iteration, per CTA and
+ * phase (5 colours) the %globaltimer values {phase start, first warp done, last warp done, barrier left}; this copies up
+ * to n_words 64-bit words of that record (layout [cta][6][4]) to `out`.  Returns the number of CTAs, <0 on error. */
+int ufm_sor_trace_get(ufm_handle *h, unsigned long long *out, int n_words);
 
 #ifdef __cplusplus
 }

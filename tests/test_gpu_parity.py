@@ -147,6 +147,31 @@ def test_sor_bit_exact_at_prescribed_iterations(mesh_10k, k, nthreads):
     assert st.last_max_residual == res
 
 
+@pytest.mark.parametrize("variant", [
+    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "1"},
+    {"UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "1"},
+], ids=["plain", "equal_share", "fused_neumann", "release_barrier", "default"])
+def test_sor_schedule_variants_bit_exact(mesh_10k, monkeypatch, variant):
+    """The SOR kernel's scheduling switches (equal slice shares per warp, Neumann pass inside the fifth colour phase,
+    release/acquire grid barrier) only reorder work inside a colour phase: every variant must give the oracle's bits."""
+    for k_, v_ in variant.items():
+        monkeypatch.setenv(k_, v_)
+    o, g = _ssa_setup_pair(mesh_10k, nthreads=8)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=57, force_iters=True)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    st = g.ssa_sor(max_inner=57, force_iters=True)
+    assert st.n_inner_last == 57 == n
+    assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
+    assert_bits_equal(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
+    assert st.last_max_residual == res
+
+
 def test_sor_presummed_xy_within_tolerance(mesh_10k):
     o, g = _ssa_setup_pair(mesh_10k, exact_xy=0)
     o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()

@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
     ap.add_argument("--order", default="random")
     ap.add_argument("--others", action="store_true", help="also time the per-step kernels")
+    ap.add_argument("--variants", default="", help="semicolon-separated env settings to compare in one process, e.g. "
+                    "'UFM_SOR_CHUNK=1;UFM_SOR_CHUNK=1,UFM_SOR_BAR=1' (the library re-reads them on every SOR launch)")
     a = ap.parse_args()
     from ufemism_b200 import mesh as M
     from ufemism_b200 import scenarios as S
@@ -50,6 +52,44 @@ def main():
     cn = g.counters()
     out = {"ranks": world, "nV": m.nV, "M": m.nVAaAc, "exact_xy": a.exact_xy, "iters": a.iters, "us_per_iteration": res,
            "algorithmic_GB": cn.sor_bytes_per_iteration / 1e9, "achieved_GBps_best": cn.sor_bytes_per_iteration / (min(res) * 1e-6) / 1e9}
+    if a.variants:
+        import numpy as np
+        base = None
+        out["variants"] = {}
+        for spec in ["UFM_SOR_CHUNK=0,UFM_SOR_FUSE_BC=0,UFM_SOR_BAR=0"] + a.variants.split(";"):
+            for kv in ("UFM_SOR_CHUNK=0,UFM_SOR_FUSE_BC=0,UFM_SOR_BAR=0," + spec).split(","):
+                k_, v_ = kv.split("=")
+                os.environ[k_] = v_
+            g.upload("U_SSA_AaAc", np.zeros(m.nVAaAc)); g.upload("V_SSA_AaAc", np.zeros(m.nVAaAc))
+            g.ssa_sor(max_inner=20, force_iters=True)
+            uv = g.download("U_SSA_AaAc")
+            if base is None:
+                base = uv
+            ts = []
+            for _ in range(a.reps):
+                g.reset_counters()
+                g.ssa_sor(max_inner=a.iters, force_iters=True)
+                cn = g.counters()
+                ts.append(round(cn.sor_ms * 1e3 / cn.sor_iterations, 2))
+            out["variants"][spec] = {"us_per_iteration": ts, "same_bits_as_baseline_after_20": bool(np.array_equal(uv, base))}
+    if os.environ.get("UFM_SOR_TRACE"):
+        import numpy as np
+        for kv in os.environ.get("UFM_SOR_TRACE_VARIANT", "UFM_SOR_CHUNK=0,UFM_SOR_FUSE_BC=0,UFM_SOR_BAR=0").split(","):
+            k_, v_ = kv.split("=")
+            os.environ[k_] = v_
+        g.ssa_sor(max_inner=8, force_iters=True)
+        t = g.sor_trace().astype(np.int64)[:, :5, :]          # (cta, colour, {start, first done, last done, left})
+        t0 = t[:, :, 0].min(axis=0)                            # earliest phase start over the grid, per colour
+        rel = t - t0[None, :, None]
+        out["trace_us"] = {
+            "phase_len": ((t[:, :, 3].max(axis=0) - t0) / 1e3).round(2).tolist(),
+            "start_spread": ((t[:, :, 0].max(axis=0) - t0) / 1e3).round(2).tolist(),
+            "first_warp_done_min_med_max": [[round(float(x) / 1e3, 2) for x in (rel[:, c, 1].min(), np.median(rel[:, c, 1]), rel[:, c, 1].max())] for c in range(5)],
+            "last_warp_done_min_med_max": [[round(float(x) / 1e3, 2) for x in (rel[:, c, 2].min(), np.median(rel[:, c, 2]), rel[:, c, 2].max())] for c in range(5)],
+            "left_barrier_min_med_max": [[round(float(x) / 1e3, 2) for x in (rel[:, c, 3].min(), np.median(rel[:, c, 3]), rel[:, c, 3].max())] for c in range(5)],
+            "next_start_minus_last_done_max": [round(float(t[:, (c + 1) % 5, 0].min() - t[:, c, 2].max()) / 1e3, 2) for c in range(4)],
+        }
+        np.save("gpurun_out/sor_trace.npy", t)
     if a.others:
         import torch
         def tm(fn, n=5):

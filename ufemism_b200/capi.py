@@ -109,7 +109,7 @@ for _n, _i in FIELD_IDS.items():
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
-            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset"]
+            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get"]
 
 _lib = None
 
@@ -155,6 +155,7 @@ def load_library():
         L.ufm_run_model.argtypes = [p, p, d, ctypes.c_long]
         L.ufm_run_model_host.argtypes = [p, p, d, ctypes.c_long, p]
         L.ufm_counters_get.argtypes = [p, p]
+        L.ufm_sor_trace_get.argtypes = [p, p, ctypes.c_int]
         L.ufm_counters_reset.argtypes = [p]
         _lib = L
     return _lib
@@ -383,6 +384,14 @@ class IceModelGPU:
         c = Counters()
         self._ck(self.L.ufm_counters_get(self.h, ctypes.byref(c)))
         return c
+
+    def sor_trace(self):
+        """Phase timestamps of the SOR kernel's fourth iteration, shape (n_ctas, 6, 4) in ns (needs UFM_SOR_TRACE=1)."""
+        buf = np.zeros(4096 * 24, np.uint64)
+        n = self.L.ufm_sor_trace_get(self.h, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
+        if n < 0:
+            self._ck(n)
+        return buf[: n * 24].reshape(n, 6, 4)
 
     def reset_counters(self):
         self._ck(self.L.ufm_counters_reset(self.h))

@@ -528,6 +528,15 @@ int ufm_counters_get(ufm_handle *h, ufm_counters *out)
   *out = h->cnt;
   return 0;
 }
+int ufm_sor_trace_get(ufm_handle *h, unsigned long long *out, int n_words)
+{
+  if (!h || !out) return ufm_set_error(-2, "NULL argument");
+  if (!h->sor_trace) return ufm_set_error(-2, "ufm_sor_trace_get: UFM_SOR_TRACE was not set when the SOR kernel was configured");
+  if (n_words > 4096 * 24) n_words = 4096 * 24;
+  UFM_CUDA(cudaStreamSynchronize(h->stream));
+  UFM_CUDA(cudaMemcpy(out, h->sor_trace, (size_t)n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return h->sor_grid;
+}
 int ufm_counters_reset(ufm_handle *h)
 {
   if (!h) return ufm_set_error(-2, "NULL handle");

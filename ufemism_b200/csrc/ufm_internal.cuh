@@ -94,6 +94,7 @@ struct DevMesh {
   int corner_owner[4] = {};
   int n_chunks = 0;
   // Neumann boundary lists
+  int adj5_end = 0;            // single-GPU layout: slices [rng[4][0][0], adj5_end) hold the colour-5 rows adjacent to a domain-edge row
   int n_bc = 0;                // edge vertices except corners 1..4
   int *bc_pos = nullptr, *bc_ptr = nullptr, *bc_nbr = nullptr;
   int corner_pos[4] = {}, corner_n[4] = {};
@@ -144,6 +145,9 @@ struct CommDev {
   unsigned long long *mail[UFM_MAX_RANKS];
 };
 
+#define UFM_SOR_CHUNK_DEFAULT 1
+#define UFM_SOR_FUSE_BC_DEFAULT 1
+#define UFM_SOR_BAR_DEFAULT 1
 struct ufm_handle {
   int device = 0;
   ufm_params P;
@@ -158,6 +162,8 @@ struct ufm_handle {
   ufm_counters cnt;
   int sor_grid = 0, sor_block = 1024;
   size_t sor_smem = 0;
+  int sor_chunk = 0, sor_fuse_bc = 0, sor_bar = 0;  // SOR scheduling switches (env UFM_SOR_CHUNK / _FUSE_BC / _BAR)
+  unsigned long long *sor_trace = nullptr;   // tuning aid, see SorArgs::trace
   int sor_tma = 0;               // 1: TMA-staged SOR kernel (env UFM_SOR_TMA, default set in ufm_create)
   int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload
   bool comm_connected = false;

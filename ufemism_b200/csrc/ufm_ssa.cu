@@ -409,9 +409,6 @@ __global__ void k_ssa_setup(SetupArgs a)
 #ifndef SOR_BLOCK
 #define SOR_BLOCK 1024
 #endif
-#ifndef SOR_PREFETCH
-#define SOR_PREFETCH 0
-#endif
 #ifndef SOR_MIN_BLOCKS
 #define SOR_MIN_BLOCKS 1
 #endif
@@ -431,6 +428,11 @@ struct SorArgs {
   const int *corner_nbr, *corner_row;
   int Mp;
   int max_inner, force_iters;
+  int chunk;      // 1: equal shares of a colour's slices per active warp (see colour_share); 0: plain grid-wide round robin
+  int fuse_bc;    // 1 (single-GPU): the Neumann pass runs inside the fifth colour phase (see k_ssa_sor); 0: own phase
+  int adj_end;    // fused Neumann pass: slices [begin of colour 5, adj_end) hold the colour-5 rows that the Neumann rows read
+  unsigned long long *trace;   // tuning aid (env UFM_SOR_TRACE): per CTA and phase {start, first warp done, last warp done, barrier left} in ns
+  int bar_rel;    // 1 (single GPU): grid barrier = release reduction + acquire poll against a locally tracked phase bit
   double omega, tol;
   unsigned long long *ctrl;
   unsigned long long *sctl;   // device-side solve control, or NULL when driven call by call
@@ -440,7 +442,7 @@ __device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
 {
   double su = 0.0, sv = 0.0;
   const int b = a.bc_ptr[row], e = a.bc_ptr[row + 1];
-  for (int k = b; k < e; k++) { const double2 q = a.UV[a.bc_nbr[k]]; su = su + q.x; sv = sv + q.y; }
+  for (int k = b; k < e; k++) { const double2 q = __ldcg(a.UV + a.bc_nbr[k]); su = su + q.x; sv = sv + q.y; }
   const double nv = (double)(e - b);
   return make_double2(su / nv, sv / nv);
 }
@@ -459,31 +461,22 @@ __device__ __forceinline__ void store_row(const SorArgs &a, const int p, const d
   }
 }
 
-// Pull the read-only streams of slice s (the NEXT slice this warp will sweep) into L2 while the current slice is being
-// computed: one prefetch instruction per 128 B line, lines spread over the lanes.  Costs no registers and no DRAM traffic
-// (the lines are read exactly once either way); the demand loads of the next round then hit L2 (~300 ns) instead of HBM.
-template <bool EXACT>
-__device__ __forceinline__ void prefetch_slice(const SorArgs &a, const int s, const int lane)
+// Neumann row r of this rank: an edge row (mean of its non-edge neighbours) or, for r >= bc_end, one of the four corners
+// (mean of all neighbours; edge neighbours at their NEW value, recomputed here from non-edge rows only)
+template <bool MULTI>
+__device__ __forceinline__ void neumann_row(const SorArgs &a, const int r)
 {
-  const long long o = a.off[s];
-  const int w = (int)((a.off[s + 1] - o) >> 5);
-  const int n_lines = (EXACT ? 7 : 5) * w + 10;
-  for (int t = lane; t < n_lines; t += 32) {
-    const char *ptr;
-    int u = t;
-    if (u < w) ptr = (const char *)(a.idx + o) + u * 128;
-    else if ((u -= w) < 2 * w) ptr = (const char *)(a.cU + o) + u * 128;
-    else if ((u -= 2 * w) < 2 * w) ptr = (const char *)(a.cV + o) + u * 128;
-    else if (EXACT && (u -= 2 * w) < 2 * w) ptr = (const char *)(a.nxy + o) + u * 128;
-    else {
-      if (!EXACT) u -= 2 * w; else u -= 2 * w;
-      const int p = s * 32;
-      if (u < 4) ptr = (const char *)(a.E + p) + u * 128;
-      else if (u < 8) ptr = (const char *)(a.RHS + p) + (u - 4) * 128;
-      else ptr = (const char *)((EXACT ? a.nxy0 : a.nxysum) + p) + (u - 8) * 128;
-    }
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
+  if (r < a.bc_end) { store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r)); return; }
+  const int k = r - a.bc_end;
+  if (!((a.corner_mask >> k) & 1)) return;
+  const int n = a.corner[4 + k];
+  double su = 0.0, sv = 0.0;
+  for (int q = 0; q < n; q++) {
+    const int row = a.corner_row[k * 16 + q];
+    const double2 v = row >= 0 ? bc_mean(a, row) : __ldcg(a.UV + a.corner_nbr[k * 16 + q]);
+    su = su + v.x; sv = sv + v.y;
   }
+  store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
 }
 
 // One SOR update of row p (ice_dynamics_module.f90:633-659).  W = slice width (compile time, so every index,
@@ -527,6 +520,45 @@ __device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, c
   return tmax;
 }
 
+// The slices [first, end) step `step` of colour c that the calling warp sweeps.  Single-GPU runs give every CTA one
+// contiguous chunk of the colour block (equal to within one slice per SM, and spatially compact because rows are in
+// Morton order inside a degree class, so neighbour gathers of one SM share L1 lines); its warps take the chunk round
+// robin.  Partitioned runs keep the grid-wide round robin: their boundary slices sit at the end of the range and must be
+// reached last by every warp.
+// all CTAs co-resident (cooperative launch); `phase` is the caller's copy of bit 31 of the barrier word
+__device__ __forceinline__ void grid_barrier_rel(unsigned *bar, const int nblocks, unsigned &phase)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned add = blockIdx.x == 0 ? 0x80000000u - (unsigned)(nblocks - 1) : 1u;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(add) : "memory");
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (((v ^ phase) & 0x80000000u) == 0u);
+  }
+  phase ^= 0x80000000u;
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+template <bool MULTI>
+__device__ __forceinline__ void colour_share(const SorArgs &a, const int *s_rng, const int c, const int wg, const int nw, int &first, int &end, int &step)
+{
+  const int b = s_rng[3 * c], e = s_rng[3 * c + 2];
+  if (!MULTI && a.chunk) {
+    // equal shares: k = ceil(slices / warps) slices for each of ceil(slices / k) warps, the other warps sit the phase out.
+    // With the plain round robin most warps finish after floor(slices / warps) rounds and the last round runs with a
+    // fraction of the loads in flight (measured: 5 us of a 37 us phase); here every active warp streams until the end.
+    // The active warps are spread evenly over the CTAs and keep the CTA-contiguous numbering (L1 reuse of the gathers).
+    const int n = e - b, k = (n + nw - 1) / nw;
+    const int act = k > 0 ? (n + k - 1) / k : 0;
+    const int lo = (int)(((long long)act * blockIdx.x) / gridDim.x), hi = (int)(((long long)act * (blockIdx.x + 1)) / gridDim.x);
+    const int wib = (int)(threadIdx.x >> 5);
+    first = wib < hi - lo ? b + lo + wib : e; end = e; step = act;
+  } else {
+    first = b + wg; end = e; step = nw;
+  }
+}
+
 // ctrl[0..2]  rotating max-residual slots (bit pattern of a non-negative double; integer order = fp order)
 // ctrl[8]     iterations executed     ctrl[9] bit0 did_reset, bit1 warning (hit max_inner), bit2 peer wait timed out
 // ctrl[10]    last max residual (bits)   ctrl[32] grid barrier {count, generation}
@@ -541,35 +573,42 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
   volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
   __shared__ double sh[SOR_BLOCK / 32];
   __shared__ int s_rng[15];   // this rank's slice ranges [begin, boundary_begin, end) of the five colours (read once)
+  __shared__ unsigned long long s_tr[2];
   if (a.sctl && a.sctl[SCTL_STOP]) return;   // uniform over the grid and over the ranks: nobody enters a barrier
   if (threadIdx.x < 15) s_rng[threadIdx.x] = a.rng[((threadIdx.x / 3) * P + rank) * 3 + (threadIdx.x % 3)];
+  unsigned phase = *((volatile unsigned *)bar) & 0x80000000u;   // bit 31 cannot flip before this CTA's first arrival
   __syncthreads();
   int it = 0;
   bool done = false;
   unsigned flags = 0;
   double maxres = 0.0;
+  const bool fused = !MULTI && a.fuse_bc;
   unsigned long long epoch = MULTI ? mail[MAIL_EPOCH] : 0ull;   // same on every rank: all ranks run the same barriers
   while (!done && it < a.max_inner) {
     it++;
     if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
     double tmax = 0.0;
     for (int c = 0; c < 5; c++) {
-      const int s_bnd = s_rng[3 * c + 1], s_end = s_rng[3 * c + 2];
+      const int s_bnd = s_rng[3 * c + 1];
+      int s_first, s_end, s_step;
+      colour_share<MULTI>(a, s_rng, c, wg, nw, s_first, s_end, s_step);
       bool waited = !MULTI;
-      for (int s = s_rng[3 * c] + wg; s < s_end; s += nw) {
+      const bool tr = a.trace && it == 4;
+      if (tr && threadIdx.x == 0) { s_tr[0] = ~0ull; s_tr[1] = 0ull; a.trace[(blockIdx.x * 6 + c) * 4 + 0] = gtime(); }
+      if (tr) __syncthreads();
+      for (int s = s_first; s < s_end; s += s_step) {
         if (MULTI && !waited && s >= s_bnd) {  // first boundary slice of this warp: the peers' previous phase must have landed
           if (lane == 0) wait_peers(a.cm, epoch);
           __syncwarp();
           waited = true;
         }
-        if (SOR_PREFETCH && s + nw < s_end) prefetch_slice<EXACT>(a, s + nw, lane);
         const long long o = a.off[s];
         const int w = (int)((a.off[s + 1] - o) >> 5);
         const int p = s * 32 + lane;
         const int n = a.deg[p];
-        if (n == UFM_DEG_PAD) continue;
-        if (GLFIX) { if (a.mflag[p] & 2) continue; }
-        switch (w) {  // warp-uniform
+        bool act = n != UFM_DEG_PAD;
+        if (GLFIX) { if (a.mflag[p] & 2) act = false; }
+        if (act) switch (w) {  // warp-uniform
           case 3: tmax = sor_row<3, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
           case 4: tmax = sor_row<4, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
           case 5: tmax = sor_row<5, EXACT, MULTI>(a, o, lane, p, n, tmax); break;
@@ -599,6 +638,23 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
             store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
           }
         }
+        if (!MULTI && fused && c == 4 && s < a.adj_end) {  // a slice the Neumann rows read: count it once its rows are visible
+          __syncwarp();
+          __threadfence();
+          if (lane == 0) atomicAdd(a.ctrl + 12, 1ull);
+        }
+      }
+      if (tr && lane == 0) { const unsigned long long t = gtime(); atomicMin(&s_tr[0], t); atomicMax(&s_tr[1], t); }
+      if (!MULTI && fused && c == 4) {
+        // apply_Neumann_boundary_AaAc inside the fifth colour phase: the colour-5 rows next to the domain edge are the first
+        // slices of the colour block (upload order) and were counted above; every other row the pass reads belongs to
+        // colours 1-4 and is final.  The wait is on work that was started first in this phase and never waits itself.
+        const unsigned long long target = (unsigned long long)it * (unsigned long long)(a.adj_end - s_rng[12]);
+        bool ready = false;
+        for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
+          if (!ready) { while (*((volatile unsigned long long *)(a.ctrl + 12)) < target) { } __threadfence(); ready = true; }
+          neumann_row<MULTI>(a, r);
+        }
       }
       if (c == 4) {  // publish this CTA's max residual before the barrier that precedes the stop test
         for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
@@ -613,37 +669,28 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
       // end of colour phase: grid barrier; in a partitioned run the last CTA exchanges epochs with the peers
       // (and, after the fifth colour, this rank's max residual: the MPI_ALLREDUCE MAX of :673)
       ++epoch;
-      grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
+      if (!MULTI && a.bar_rel) grid_barrier_rel(bar, nblocks, phase);
+      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
         if (MULTI && c == 4) {
           const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
           for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
         }
       });
+      if (tr && threadIdx.x == 0) { unsigned long long *q = a.trace + (blockIdx.x * 6 + c) * 4; q[1] = s_tr[0]; q[2] = s_tr[1]; q[3] = gtime(); }
     }
     // apply_Neumann_boundary_AaAc on U and V (mesh_ArakawaC_module.f90:660-724): edge rows from their
     // non-edge neighbours; the four corners from all neighbours, edge neighbours taken at their NEW value
     // (recomputed here from non-edge rows only, so the whole pass is one hazard-free phase).
-    if (MULTI) {  // the Neumann rows may read peer-owned rows of the fifth colour
-      if (threadIdx.x == 0) wait_peers(a.cm, epoch);
-      __syncthreads();
-    }
-    for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
-      if (r < a.bc_end) store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r));
-      else {
-        const int k = r - a.bc_end;
-        if (!((a.corner_mask >> k) & 1)) continue;
-        const int n = a.corner[4 + k];
-        double su = 0.0, sv = 0.0;
-        for (int q = 0; q < n; q++) {
-          const int row = a.corner_row[k * 16 + q];
-          const double2 v = row >= 0 ? bc_mean(a, row) : a.UV[a.corner_nbr[k * 16 + q]];
-          su = su + v.x; sv = sv + v.y;
-        }
-        store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
+    if (MULTI || !fused) {
+      if (MULTI) {  // the Neumann rows may read peer-owned rows of the fifth colour
+        if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+        __syncthreads();
       }
+      for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) neumann_row<MULTI>(a, r);
+      ++epoch;
+      if (!MULTI && a.bar_rel) grid_barrier_rel(bar, nblocks, phase);
+      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
     }
-    ++epoch;
-    grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
     if (MULTI) {
       // every rank's residual was published before it signalled the fifth-colour epoch, which wait_peers() above has seen
       unsigned long long r = 0ull;
@@ -1135,6 +1182,11 @@ static sor_kernel_t pick_sor(const ufm_handle *h)
 int ufm_sor_configure(ufm_handle *h)
 {
   int per_sm = 0;
+  // tuning switches, re-read on every configure so that one process can compare variants (tools/sor_probe.py)
+  { const char *e = getenv("UFM_SOR_CHUNK"); h->sor_chunk = e ? atoi(e) : UFM_SOR_CHUNK_DEFAULT; }
+  if (getenv("UFM_SOR_TRACE") && !h->sor_trace) { UFM_CUDA(cudaMalloc((void **)&h->sor_trace, 4096 * 24 * sizeof(unsigned long long))); UFM_CUDA(cudaMemset(h->sor_trace, 0, 4096 * 24 * sizeof(unsigned long long))); }
+  { const char *e = getenv("UFM_SOR_BAR"); h->sor_bar = e ? atoi(e) : UFM_SOR_BAR_DEFAULT; }
+  { const char *e = getenv("UFM_SOR_FUSE_BC"); h->sor_fuse_bc = e ? atoi(e) : UFM_SOR_FUSE_BC_DEFAULT; }
   h->sor_block = h->sor_tma ? TMA_WARPS * 32 : SOR_BLOCK;
   h->sor_smem = h->sor_tma ? (size_t)TMA_WARPS * TMA_STAGES * TMA_STAGE_BYTES : 0;
   if (h->sor_smem) UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sor_smem));
@@ -1158,6 +1210,8 @@ static int enqueue_sor(ufm_handle *h, int max_inner, int force_iters, bool devic
   a.corner = m.corner_dev;
   a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
   a.corner_nbr = m.corner_nbr; a.corner_row = m.corner_row;
+  a.chunk = h->sor_chunk; a.trace = h->sor_trace; a.bar_rel = h->sor_bar;
+  a.fuse_bc = (h->sor_fuse_bc && m.P == 1 && !h->sor_tma) ? 1 : 0; a.adj_end = m.adj5_end;
   a.Mp = m.Mp; a.max_inner = max_inner; a.force_iters = force_iters; a.omega = h->P.SSA_SOR_omega; a.tol = h->P.SSA_max_residual_UV;
   a.ctrl = s.ctrl; a.sctl = device_ctl ? s.ctrl + SCTL_BASE : nullptr;
   UFM_CUDA(cudaMemsetAsync(s.ctrl, 0, 16 * sizeof(unsigned long long), h->stream));

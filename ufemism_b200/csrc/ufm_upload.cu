@@ -222,11 +222,22 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   std::vector<int> m_order(M);
   std::iota(m_order.begin(), m_order.end(), 0);
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
+  // single-GPU layout: the colour-5 rows that the Neumann pass reads (non-edge rows adjacent to a domain-edge row) lead
+  // their colour block, so that the pass can run inside the fifth colour phase as soon as those few slices are done
+  std::vector<unsigned char> late(M, 1);
+  int n_adj5 = 0;
+  if (P == 1)
+    for (int ai = 0; ai < M; ai++) {
+      if (colour[ai] != 5 || is_edge[ai]) continue;
+      for (int c = 1; c <= degv[ai]; c++)
+        if (is_edge[F2(d->CAaAc, ai + 1, c, ldM) - 1]) { late[ai] = 0; n_adj5++; break; }
+    }
   __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
     int ba = blk(a), bb = blk(b);
     if (ba != bb) return ba < bb;
     if (owner[a] != owner[b]) return owner[a] < owner[b];
     if (isb[a] != isb[b]) return isb[a] < isb[b];
+    if (late[a] != late[b]) return late[a] < late[b];
     if (degv[a] != degv[b]) return degv[a] < degv[b];
     return mort[a] < mort[b];
   });
@@ -252,6 +263,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   }
   m.Mp = (int)m_d2r.size();
   m.n_chunks = m.Mp / UFM_CHUNK;
+  m.adj5_end = m.rng[4][0][0] + (n_adj5 + UFM_SLICE - 1) / UFM_SLICE;
 
   lap("AaAc sort + layout");
   // ---- AaAc sliced ELL ----
