@@ -29,6 +29,10 @@ struct type_mesh {                 // src/data_types_module.f90:216-345 (members
   const int *nCAaAc = nullptr, *CAaAc = nullptr;
   const double *Nx_AaAc = nullptr, *Ny_AaAc = nullptr, *Nxx_AaAc = nullptr, *Nxy_AaAc = nullptr, *Nyy_AaAc = nullptr;
   const int *colour_vi = nullptr, *colour_nV = nullptr;
+  // read only by update_ice_temperature (upwind advection); leave Tri null to keep thermodynamics off the device
+  int nTri = 0;
+  const int *Tri = nullptr, *niTri = nullptr, *iTri = nullptr;
+  const double *R = nullptr, *NxTri = nullptr, *NyTri = nullptr;
 };
 
 struct type_ice_model {            // src/data_types_module.f90:15-214 (members the wrappers move)
@@ -38,7 +42,10 @@ struct type_ice_model {            // src/data_types_module.f90:15-214 (members 
   double *U_SIA = nullptr, *V_SIA = nullptr, *D_SIA = nullptr, *U_SSA = nullptr, *V_SSA = nullptr;
   int *mask = nullptr, *mask_land = nullptr, *mask_ocean = nullptr, *mask_ice = nullptr, *mask_sheet = nullptr, *mask_shelf = nullptr,
       *mask_coast = nullptr, *mask_margin = nullptr, *mask_gl = nullptr, *mask_cf = nullptr;
+  double *Ti = nullptr, *U_3D = nullptr, *V_3D = nullptr, *W_3D = nullptr;   // (nV,nZ) thermodynamics
+  const double *GHF = nullptr;
 };
+struct type_climate_model { const double *T2m = nullptr; };   // climate%applied%T2m (nV,12)
 struct type_SMB_model { const double *SMB_year = nullptr; };
 struct type_BMB_model { const double *BMB = nullptr; };
 
@@ -60,6 +67,7 @@ class B200IceDynamics {
     d.Aci = m.Aci; d.iAci = m.iAci; d.edge_index_Ac = m.edge_index_Ac; d.Nx_Ac = m.Nx_Ac; d.Ny_Ac = m.Ny_Ac; d.No_Ac = m.No_Ac; d.Np_Ac = m.Np_Ac;
     d.nCAaAc = m.nCAaAc; d.CAaAc = m.CAaAc; d.Nx_AaAc = m.Nx_AaAc; d.Ny_AaAc = m.Ny_AaAc; d.Nxx_AaAc = m.Nxx_AaAc; d.Nxy_AaAc = m.Nxy_AaAc;
     d.Nyy_AaAc = m.Nyy_AaAc; d.colour_vi = m.colour_vi; d.colour_nV = m.colour_nV;
+    d.nTri = m.nTri; d.ldTri = m.nTri; d.Tri = m.Tri; d.niTri = m.niTri; d.iTri = m.iTri; d.R = m.R; d.NxTri = m.NxTri; d.NyTri = m.NyTri;
     check(ufm_mesh_upload(h_, &d), "ufm_mesh_upload");
   }
 
@@ -92,6 +100,14 @@ class B200IceDynamics {
   {
     check(ufm_solve_SSA(h_, &last_ssa_stats), "solve_SSA");
     down(UFM_F_U_SSA, ice.U_SSA); down(UFM_F_V_SSA, ice.V_SSA);
+  }
+  // update_ice_temperature( mesh, ice, climate, SMB)   src/thermodynamics_module.f90:23
+  ufm_thermo_stats last_thermo_stats{};
+  void update_ice_temperature(const type_mesh &, type_ice_model &ice, const type_climate_model &climate, const type_SMB_model &SMB)
+  {
+    up(UFM_F_T2M, climate.T2m); up(UFM_F_SMB_YEAR, SMB.SMB_year); up(UFM_F_GHF, ice.GHF);
+    check(ufm_update_ice_temperature(h_, &last_thermo_stats), "update_ice_temperature");
+    down(UFM_F_TI, ice.Ti); down(UFM_F_U_3D, ice.U_3D); down(UFM_F_V_3D, ice.V_3D); down(UFM_F_W_3D, ice.W_3D);
   }
   // the three loops + MPI_ALLREDUCE MIN of determine_timesteps_and_actions (src/UFEMISM_main_model.f90:747-778)
   void critical_timesteps(double &dt_D_2D_min, double &dt_V_2D_SSA_min, double &dt_V_3D_SIA_min)

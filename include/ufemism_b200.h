@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UFM_ABI_VERSION 1
+#define UFM_ABI_VERSION 2
 #define UFM_MAX_NZ 32
 
 typedef struct ufm_handle ufm_handle;
@@ -59,6 +59,7 @@ typedef struct ufm_params {
                                      get_mesh_curvatures_vertex_AaAc does (bit-identical results);
                                      0: use the pre-summed row sum (saves 8(n+1) B per vertex and sweep,
                                      differs from the reference by O(1 ulp) per update). */
+  double dt_thermo;               /* C%dt_thermo (10 yr, src/configuration_module.f90:38): time step of the heat equation */
 } ufm_params;
 
 /* type_mesh fields used by the path (src/data_types_module.f90:216-345).  ld* = allocated rows. */
@@ -80,6 +81,13 @@ typedef struct ufm_mesh_desc {
   const double *Nx_AaAc, *Ny_AaAc, *Nxx_AaAc, *Nxy_AaAc, *Nyy_AaAc; /* (ldAaAc,nC_mem+1) */
   const int    *colour_vi;        /* (ldAaAc,5) */
   const int    *colour_nV;        /* (5) */
+  /* optional, read only by ufm_update_ice_temperature (upwind derivative of the temperature,
+   * src/mesh_derivatives_module.f90:435-483).  Tri == NULL: thermodynamics is not available on this mesh. */
+  int nTri, ldTri;                /* mesh%nTri and the leading dimension of the (nTri,3) arrays */
+  const int    *Tri;              /* (ldTri,3) */
+  const int    *niTri, *iTri;     /* (nV), (ldV,nC_mem) */
+  const double *R;                /* (nV) resolution */
+  const double *NxTri, *NyTri;    /* (ldTri,3) */
 } ufm_mesh_desc;
 
 /* Fields of type_ice_model (src/data_types_module.f90:15-214) that can cross the boundary.
@@ -110,6 +118,9 @@ enum ufm_field {
   /* (nV,nZ) */
   UFM_F_U_3D, UFM_F_V_3D,
   UFM_F_TI, /* englacial temperature, input of the Arrhenius flow factor when do_benchmark_experiment is .FALSE. */
+  /* thermodynamics (meshes uploaded with Tri): W_3D (nV,nZ) out; GHF (nV) in; T2m (nV,12) in = climate%applied%T2m;
+   * frictional_heating (nV) out */
+  UFM_F_W_3D, UFM_F_GHF, UFM_F_T2M, UFM_F_FRICTIONAL_HEATING,
   UFM_F_COUNT
 };
 
@@ -250,6 +261,19 @@ typedef struct ufm_host_ice {
   double *Hi_out, *Hi_prev, *dHi_dt, *Hs, *U_SSA, *V_SSA, *U_SIA, *V_SIA, *D_SIA; int *mask;    /* out */
 } ufm_host_ice;
 int ufm_run_model_host(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host);
+
+/* ---- thermodynamics ----
+ * ufm_update_ice_temperature replaces the body of update_ice_temperature (src/thermodynamics_module.f90:23-202): the
+ * whole solve_SIA_3D (U, V and W, src/ice_dynamics_module.f90:317-405), bottom_frictional_heating (:281-311), the zeta
+ * Jacobians (src/zeta_module.f90:86-112), one implicit step of the heat equation per column (DGTSV), the Neumann pass, and
+ * the Robin-solution safety net (:204-279).  Inputs on the device: GHF, T2m, Ti (+ what update_general / solve_SSA left).
+ * rc 0 ok (also for the benchmarks that skip thermodynamics, :44-64); -8: more than 1 % of the columns unstable (the
+ * reference STOPs, :195-199); -9: singular column system (DGTSV info /= 0, STOP at :353); -10: no upwind triangle. */
+typedef struct ufm_thermo_stats { int n_unstable; int rc; } ufm_thermo_stats;
+int ufm_update_ice_temperature(ufm_handle *h, ufm_thermo_stats *st);
+/* pieces, for kernel-level parity tests: W_3D from the resident U_3D / V_3D; the heat-equation step from the resident 3-D velocities */
+int ufm_thermo_w3d(ufm_handle *h);
+int ufm_thermo_heat(ufm_handle *h, ufm_thermo_stats *st);
 
 /* ---- instrumentation ---- */
 int ufm_counters_get(ufm_handle *h, ufm_counters *out);

@@ -40,7 +40,7 @@ ICE_FIELDS = _fields("ORA_ICE_FIELDS")
 
 
 class OraMesh(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int) for n in ("nV", "nAc", "nVAaAc", "nC_mem")] + [(n, ctypes.c_void_p) for _, n, _, _ in MESH_FIELDS]
+    _fields_ = [(n, ctypes.c_int) for n in ("nV", "nAc", "nVAaAc", "nC_mem", "nTri")] + [(n, ctypes.c_void_p) for _, n, _, _ in MESH_FIELDS]
 
 
 class OraIce(ctypes.Structure):
@@ -51,7 +51,8 @@ class OraConfig(ctypes.Structure):
     _fields_ = [("nZ", ctypes.c_int), ("zeta", ctypes.c_double * 32), ("m_enh_sia", ctypes.c_double), ("m_enh_ssa", ctypes.c_double),
                 ("use_analytical_GL_flux", ctypes.c_int), ("SSA_RN_tol", ctypes.c_double), ("SSA_max_outer_loops", ctypes.c_int),
                 ("SSA_max_residual_UV", ctypes.c_double), ("SSA_SOR_omega", ctypes.c_double), ("SSA_max_inner_loops", ctypes.c_int),
-                ("dt_max", ctypes.c_double), ("benchmark", ctypes.c_int), ("nthreads", ctypes.c_int)]
+                ("dt_max", ctypes.c_double), ("benchmark", ctypes.c_int), ("nthreads", ctypes.c_int), ("dt_thermo", ctypes.c_double),
+                ("thermo", ctypes.c_int)]
 
 
 class OraSsaStats(ctypes.Structure):
@@ -85,6 +86,10 @@ def lib():
         L.ora_update_general_ice_model_data.argtypes = [p, p, p, d]
         L.ora_solve_SIA.argtypes = [p, p, p]
         L.ora_solve_SIA_3D_UV.argtypes = [p, p, p]
+        L.ora_solve_SIA_3D.argtypes = [p, p, p]
+        L.ora_update_ice_temperature.argtypes = [p, p, p, p]
+        L.ora_replace_Ti_with_robin_solution.argtypes = [p, p, p, i]
+        L.ora_dgtsv.argtypes = [i, p, p, p, p, p]
         L.ora_solve_SSA.argtypes = [p, p, p, p]
         L.ora_determine_timesteps.argtypes = [p, p, p, p]
         for f in ("ora_basal_yield_stress", "ora_calculate_GL_flux", "ora_SSA_gather_AaAc", "ora_SSA_effective_viscosity", "ora_SSA_sliding_term"):
@@ -110,7 +115,7 @@ def lib():
 
 def _dim(tag, mesh, nZ):
     return {"NV": mesh.nV, "NAC": mesh.nAc, "NAA": mesh.nVAaAc, "NZ": nZ, "NCM": mesh.nC_mem, "NCM1": mesh.nC_mem + 1,
-            "N1": 1, "N2": 2, "N4": 4, "N5": 5}[tag]
+            "N1": 1, "N2": 2, "N3": 3, "N4": 4, "N5": 5, "N12": 12, "NTRI": mesh.nTri}[tag]
 
 
 class Oracle:
@@ -127,7 +132,7 @@ class Oracle:
             setattr(self.cfg, k, v)
         self.nZ = self.cfg.nZ
         self._keep = []
-        self.cm = OraMesh(nV=mesh.nV, nAc=mesh.nAc, nVAaAc=mesh.nVAaAc, nC_mem=mesh.nC_mem)
+        self.cm = OraMesh(nV=mesh.nV, nAc=mesh.nAc, nVAaAc=mesh.nVAaAc, nC_mem=mesh.nC_mem, nTri=mesh.nTri)
         for t, n, r, c in MESH_FIELDS:
             a = getattr(mesh, n)
             dt = np.float64 if t == "double" else np.int32
@@ -159,8 +164,17 @@ class Oracle:
     def solve_SIA(self):
         self.L.ora_solve_SIA(*self._a())
 
-    def solve_SIA_3D(self):
-        self.L.ora_solve_SIA_3D_UV(*self._a())
+    def solve_SIA_3D(self, with_W=False):
+        (self.L.ora_solve_SIA_3D if with_W else self.L.ora_solve_SIA_3D_UV)(*self._a())
+
+    def update_ice_temperature(self):
+        """Returns (rc, n_unstable); rc as documented at ora_update_ice_temperature."""
+        nu = ctypes.c_int(0)
+        rc = self.L.ora_update_ice_temperature(*self._a(), ctypes.byref(nu))
+        return rc, nu.value
+
+    def replace_Ti_with_robin_solution(self, vi):
+        self.L.ora_replace_Ti_with_robin_solution(*self._a(), int(vi))
 
     def solve_SSA(self):
         st = OraSsaStats()
@@ -221,6 +235,14 @@ class Oracle:
 
     def run_model(self, region, t_end, max_steps=0):
         return self.L.ora_run_model(*self._a(), ctypes.byref(region), float(t_end), int(max_steps))
+
+
+def dgtsv(dl, d, du, b):
+    """The oracle's restatement of LAPACK DGTSV (one right-hand side); returns (x, info)."""
+    dl, d, du, b = (np.array(v, np.float64) for v in (dl, d, du, b))
+    info = ctypes.c_int(0)
+    lib().ora_dgtsv(len(d), dl.ctypes.data, d.ctypes.data, du.ctypes.data, b.ctypes.data, ctypes.byref(info))
+    return b, info.value
 
 
 def halfar_solution(H0, R0, x, y, t):

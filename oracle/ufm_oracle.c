@@ -25,6 +25,8 @@ static const double n_flow = 3.0;
 static const double ice_density = 910.0;
 static const double seawater_density = 1028.0;
 static const double SMT = 271.15;
+static const double T0 = 273.16;
+static const double CC = 8.7E-04;
 
 #define A2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
 #define A1(a, i) (a)[(size_t)(i) - 1]
@@ -44,6 +46,7 @@ void ora_config_defaults(ora_config *c)
   c->dt_max = 10.0;
   c->benchmark = ORA_BM_HALFAR;
   c->nthreads = 1;
+  c->dt_thermo = 10.0;
 }
 
 /* partition_list, src/mesh_help_functions_module.f90:1475-1496 (i = 0-based rank) */
@@ -365,8 +368,7 @@ static void determine_masks_r(const ora_mesh *m, const rank_t *r, ora_ice *ice)
   SYNC
 }
 
-/* ice_physical_properties, src/general_ice_model_data_module.f90:298-462 (rank body; only the
- * flow-factor outputs the dynamics read -- Ki, Cpi, Ti_pmp feed thermodynamics, out of scope) */
+/* ice_physical_properties, src/general_ice_model_data_module.f90:298-462 (rank body) */
 static void ice_physical_properties_r(const ora_mesh *m, const rank_t *r, ora_ice *ice, const ora_config *c, double time)
 {
   const double A_low_temp = 1.14E-05, A_high_temp = 5.47E+10, Q_low_temp = 6.0E+04, Q_high_temp = 13.9E+04, R_gas = 8.314;
@@ -384,6 +386,14 @@ static void ice_physical_properties_r(const ora_mesh *m, const rank_t *r, ora_ic
     }
     for (int vi = r->v1; vi <= r->v2; vi++) A1(ice->A_flow_mean, vi) = A_flow;
     for (int aci = r->ac1; aci <= r->ac2; aci++) A1(ice->A_flow_mean_Ac, aci) = A_flow;
+    if (is_benchmark_simple(c->benchmark) || c->benchmark == ORA_BM_MESH_GENERATION_TEST) { /* :336-343 */
+      for (int k = 1; k <= nZ; k++)
+        for (int vi = r->v1; vi <= r->v2; vi++) {
+          A2(ice->Ki, vi, k, nV) = 2.1 * sec_per_year;
+          A2(ice->Cpi, vi, k, nV) = 2009.0;
+          A2(ice->Ti_pmp, vi, k, nV) = T0 - (c->zeta[k - 1] * A1(ice->Hi, vi) * 8.7E-04);
+        }
+    }
     SYNC
     return;
   }
@@ -391,8 +401,11 @@ static void ice_physical_properties_r(const ora_mesh *m, const rank_t *r, ora_ic
   for (int vi = r->v1; vi <= r->v2; vi++) {
     for (int k = 1; k <= nZ; k++) {
       double Ti = A2(ice->Ti, vi, k, nV);
+      A2(ice->Ti_pmp, vi, k, nV) = T0 - CC * A1(ice->Hi, vi) * c->zeta[k - 1];   /* :388 */
       if (Ti < 263.15) A2(ice->A_flow, vi, k, nV) = A_low_temp * exp(-Q_low_temp / (R_gas * Ti));
       else             A2(ice->A_flow, vi, k, nV) = A_high_temp * exp(-Q_high_temp / (R_gas * Ti));
+      A2(ice->Cpi, vi, k, nV) = 2115.3 + 7.79293 * (Ti - T0);                     /* :401 */
+      A2(ice->Ki, vi, k, nV) = 3.101E+08 * exp(-0.0057 * Ti);                     /* :404 */
     }
     if (A1(ice->mask_sheet, vi) == 1) {
       for (int k = 1; k <= nZ; k++) prof[k - 1] = A2(ice->A_flow, vi, k, nV);
@@ -580,6 +593,319 @@ void ora_solve_SIA_3D_UV(const ora_mesh *m, ora_ice *ice, const ora_config *c)
     apply_Neumann_boundary_3D_r(m, &r, ice->U_3D, nZ);
     apply_Neumann_boundary_3D_r(m, &r, ice->V_3D, nZ);
   }
+}
+
+/* ============================================================================================
+ * Thermodynamics: solve_SIA_3D W half, update_ice_temperature and what it calls
+ * ============================================================================================ */
+/* get_mesh_derivatives_vertex_3D, src/mesh_derivatives_module.f90:372-391 */
+static inline void get_mesh_derivatives_vertex_3D(const ora_mesh *m, const double *d, double *ddx, double *ddy, int vi, int k)
+{
+  int nV = m->nV, n = A1(m->nC, vi);
+  double x = A2(m->Nx, vi, n + 1, nV) * A2(d, vi, k, nV);
+  double y = A2(m->Ny, vi, n + 1, nV) * A2(d, vi, k, nV);
+  for (int ci = 1; ci <= n; ci++) {
+    int vc = A2(m->C, vi, ci, nV);
+    x = x + A2(m->Nx, vi, ci, nV) * A2(d, vc, k, nV);
+    y = y + A2(m->Ny, vi, ci, nV) * A2(d, vc, k, nV);
+  }
+  *ddx = x; *ddy = y;
+}
+
+/* is_in_triangle, src/mesh_help_functions_module.f90:648-672 */
+static inline int is_in_triangle(const double *pa, const double *pb, const double *pc, const double *p)
+{
+  const double tol = 1E-8;
+  double as_x = p[0] - pa[0], as_y = p[1] - pa[1];
+  double s1 = ((pb[0] - pa[0]) * as_y - (pb[1] - pa[1]) * as_x);
+  double s2 = ((pc[0] - pa[0]) * as_y - (pc[1] - pa[1]) * as_x);
+  double s3 = ((pc[0] - pb[0]) * (p[1] - pb[1]) - (pc[1] - pb[1]) * (p[0] - pb[0]));
+  return (s1 > -tol && s2 < tol && s3 > -tol);
+}
+
+/* get_upwind_derivative_vertex_3D, src/mesh_derivatives_module.f90:435-483; returns 0 when no upwind triangle is found */
+static int get_upwind_derivative_vertex_3D(const ora_mesh *m, const double *U, const double *V, const double *d, int vi, int k, double *ddx, double *ddy)
+{
+  int nV = m->nV, nTri = m->nTri;
+  double u = A2(U, vi, k, nV), v = A2(V, vi, k, nV);
+  *ddx = 0.0; *ddy = 0.0;
+  if (fabs(u) < 1E-10 && fabs(v) < 1E-10) { get_mesh_derivatives_vertex_3D(m, d, ddx, ddy, vi, k); return 1; }
+  double den = 4.0 * sqrt(u * u + v * v);
+  double W[2] = {u * A1(m->R, vi) / den, v * A1(m->R, vi) / den};
+  double p[2] = {A2(m->V, vi, 1, nV) - W[0], A2(m->V, vi, 2, nV) - W[1]};
+  int tup = 0;
+  for (int iti = 1; iti <= A1(m->niTri, vi); iti++) {
+    int ti = A2(m->iTri, vi, iti, nV);
+    double pa[2], pb[2], pc[2];
+    int a = A2(m->Tri, ti, 1, nTri), b = A2(m->Tri, ti, 2, nTri), cc = A2(m->Tri, ti, 3, nTri);
+    pa[0] = A2(m->V, a, 1, nV); pa[1] = A2(m->V, a, 2, nV);
+    pb[0] = A2(m->V, b, 1, nV); pb[1] = A2(m->V, b, 2, nV);
+    pc[0] = A2(m->V, cc, 1, nV); pc[1] = A2(m->V, cc, 2, nV);
+    if (is_in_triangle(pa, pb, pc, p)) { tup = ti; break; }
+  }
+  if (tup == 0) return 0;
+  int a = A2(m->Tri, tup, 1, nTri), b = A2(m->Tri, tup, 2, nTri), cc = A2(m->Tri, tup, 3, nTri);
+  *ddx = A2(m->NxTri, tup, 1, nTri) * A2(d, a, k, nV) + A2(m->NxTri, tup, 2, nTri) * A2(d, b, k, nV) + A2(m->NxTri, tup, 3, nTri) * A2(d, cc, k, nV);
+  *ddy = A2(m->NyTri, tup, 1, nTri) * A2(d, a, k, nV) + A2(m->NyTri, tup, 2, nTri) * A2(d, b, k, nV) + A2(m->NyTri, tup, 3, nTri) * A2(d, cc, k, nV);
+  return 1;
+}
+
+/* solve_SIA_3D, src/ice_dynamics_module.f90:317-405: U_3D / V_3D as ora_solve_SIA_3D_UV, then the vertical velocity (:369-403) */
+void ora_solve_SIA_3D(const ora_mesh *m, ora_ice *ice, const ora_config *c)
+{
+  int nV = m->nV, nZ = c->nZ;
+  ora_solve_SIA_3D_UV(m, ice, c);   /* :339-367 incl. W_3D = 0 (below) and the two Neumann passes */
+#pragma omp parallel num_threads(c->nthreads)
+  {
+    rank_t r = rank_of(m);
+    for (int k = 1; k <= nZ; k++) for (int vi = r.v1; vi <= r.v2; vi++) A2(ice->W_3D, vi, k, nV) = 0.0;
+    SYNC
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      if (A1(m->edge_index, vi) > 0) continue;
+      if (A1(ice->mask_sheet, vi) == 0) continue;
+      double dHb_dx = A1(ice->dHs_dx, vi) - A1(ice->dHi_dx, vi);
+      double dHb_dy = A1(ice->dHs_dy, vi) - A1(ice->dHi_dy, vi);
+      A2(ice->W_3D, vi, nZ, nV) = A1(ice->dHb_dt, vi) + A2(ice->U_3D, vi, nZ, nV) * dHb_dx + A2(ice->V_3D, vi, nZ, nV) * dHb_dy;
+      for (int k = nZ - 1; k >= 1; k--) {
+        double dUdx_k, dUdy_k, dUdx_kp1, dUdy_kp1, dVdx_k, dVdy_k, dVdx_kp1, dVdy_kp1;
+        get_mesh_derivatives_vertex_3D(m, ice->U_3D, &dUdx_k, &dUdy_k, vi, k);
+        get_mesh_derivatives_vertex_3D(m, ice->U_3D, &dUdx_kp1, &dUdy_kp1, vi, k + 1);
+        get_mesh_derivatives_vertex_3D(m, ice->V_3D, &dVdx_k, &dVdy_k, vi, k);
+        get_mesh_derivatives_vertex_3D(m, ice->V_3D, &dVdx_kp1, &dVdy_kp1, vi, k + 1);
+        double zk = c->zeta[k - 1], zk1 = c->zeta[k];
+        double w1 = (dUdx_k + dUdx_kp1) / 2.0;
+        double w2 = (dVdy_k + dVdy_kp1) / 2.0;
+        double w3 = ((A1(ice->dHs_dx, vi) - 0.5 * (zk1 + zk) * A1(ice->dHi_dx, vi)) / fmax(0.1, A1(ice->Hi, vi))) *
+                    ((A2(ice->U_3D, vi, k + 1, nV) - A2(ice->U_3D, vi, k, nV)) / (zk1 - zk));
+        double w4 = ((A1(ice->dHs_dy, vi) - 0.5 * (zk1 + zk) * A1(ice->dHi_dy, vi)) / fmax(0.1, A1(ice->Hi, vi))) *
+                    ((A2(ice->V_3D, vi, k + 1, nV) - A2(ice->V_3D, vi, k, nV)) / (zk1 - zk));
+        A2(ice->W_3D, vi, k, nV) = A2(ice->W_3D, vi, k + 1, nV) - A1(ice->Hi, vi) * (w1 + w2 + w3 + w4) * (zk1 - zk);
+      }
+    }
+    SYNC
+    apply_Neumann_boundary_3D_r(m, &r, ice->W_3D, nZ);
+  }
+}
+
+/* LAPACK DGTSV, NRHS = 1 (netlib reference implementation; the reference links the system LAPACK,
+ * src/thermodynamics_module.f90:339,348): Gaussian elimination with partial pivoting on a tridiagonal system. */
+void ora_dgtsv(int n, double *dl, double *d, double *du, double *b, int *info)
+{
+  *info = 0;
+  if (n == 0) return;
+#define DL(i) dl[(i) - 1]
+#define D(i) d[(i) - 1]
+#define DU(i) du[(i) - 1]
+#define B(i) b[(i) - 1]
+  for (int i = 1; i <= n - 2; i++) {
+    if (fabs(D(i)) >= fabs(DL(i))) {
+      if (D(i) != 0.0) {
+        double fact = DL(i) / D(i);
+        D(i + 1) = D(i + 1) - fact * DU(i);
+        B(i + 1) = B(i + 1) - fact * B(i);
+      } else { *info = i; return; }
+      DL(i) = 0.0;
+    } else {
+      double fact = D(i) / DL(i);
+      D(i) = DL(i);
+      double temp = D(i + 1);
+      D(i + 1) = DU(i) - fact * temp;
+      DL(i) = DU(i + 1);
+      DU(i + 1) = -fact * DL(i);
+      DU(i) = temp;
+      temp = B(i);
+      B(i) = B(i + 1);
+      B(i + 1) = temp - fact * B(i + 1);
+    }
+  }
+  if (n > 1) {
+    int i = n - 1;
+    if (fabs(D(i)) >= fabs(DL(i))) {
+      if (D(i) != 0.0) {
+        double fact = DL(i) / D(i);
+        D(i + 1) = D(i + 1) - fact * DU(i);
+        B(i + 1) = B(i + 1) - fact * B(i);
+      } else { *info = i; return; }
+    } else {
+      double fact = D(i) / DL(i);
+      D(i) = DL(i);
+      double temp = D(i + 1);
+      D(i + 1) = DU(i) - fact * temp;
+      DU(i) = temp;
+      temp = B(i);
+      B(i) = B(i + 1);
+      B(i + 1) = temp - fact * B(i + 1);
+    }
+  }
+  if (D(n) == 0.0) { *info = n; return; }
+  B(n) = B(n) / D(n);
+  if (n > 1) B(n - 1) = (B(n - 1) - DU(n - 1) * B(n)) / D(n - 1);
+  for (int i = n - 2; i >= 1; i--) B(i) = (B(i) - DU(i) * B(i + 1) - DL(i) * B(i + 2)) / D(i);
+#undef DL
+#undef D
+#undef DU
+#undef B
+}
+
+/* replace_Ti_with_robin_solution, src/thermodynamics_module.f90:204-279 */
+void ora_replace_Ti_with_robin_solution(const ora_mesh *m, ora_ice *ice, const ora_config *c, int vi)
+{
+  const double kappa_0_ice_conductivity = 9.828, kappa_e_ice_conductivity = 0.0057, c_0_specific_heat = 2127.5, Claus_Clap_gradient = 8.7E-04;
+  int nV = m->nV, nZ = c->nZ;
+  double thermal_conductivity_robin = kappa_0_ice_conductivity * sec_per_year * exp(-kappa_e_ice_conductivity * T0);
+  double thermal_diffusivity_robin = thermal_conductivity_robin / (ice_density * c_0_specific_heat);
+  double bottom_temperature_gradient_robin = -A1(ice->GHF, vi) / thermal_conductivity_robin;
+  double sT = 0.0;
+  for (int mo = 1; mo <= 12; mo++) sT = sT + A2(ice->T2m, vi, mo, nV);
+  double Ts = fmin(T0, sT / 12.0);
+  double Hi = A1(ice->Hi, vi);
+  if (A1(ice->mask_sheet, vi) == 1) {
+    if (A1(ice->SMB_year, vi) > 0.0) {
+      double thermal_length_scale = sqrt(2.0 * thermal_diffusivity_robin * Hi / A1(ice->SMB_year, vi));
+      for (int k = 1; k <= nZ; k++) {
+        double distance_above_bed = (1.0 - c->zeta[k - 1]) * Hi;
+        double erf1 = erf(distance_above_bed / thermal_length_scale);
+        double erf2 = erf(Hi / thermal_length_scale);
+        A2(ice->Ti, vi, k, nV) = Ts + sqrt(pi) / 2.0 * thermal_length_scale * bottom_temperature_gradient_robin * (erf1 - erf2);
+      }
+    } else {
+      for (int k = 1; k <= nZ; k++) A2(ice->Ti, vi, k, nV) = Ts + ((T0 - Claus_Clap_gradient * Hi) - Ts) * c->zeta[k - 1];
+    }
+  } else if (A1(ice->mask_shelf, vi) == 1) {
+    for (int k = 1; k <= nZ; k++) A2(ice->Ti, vi, k, nV) = Ts + c->zeta[k - 1] * (SMT - Ts);
+  } else {
+    for (int k = 1; k <= nZ; k++) A2(ice->Ti, vi, k, nV) = Ts;
+  }
+  for (int k = 1; k <= nZ; k++) A2(ice->Ti, vi, k, nV) = fmin(A2(ice->Ti, vi, k, nV), T0 - Claus_Clap_gradient * Hi * c->zeta[k - 1]);
+}
+
+/* update_ice_temperature, src/thermodynamics_module.f90:23-202, with bottom_frictional_heating (:281-311),
+ * calculate_zeta_derivatives (src/zeta_module.f90:86-112) and the coefficients of initialize_zeta_discretization (:113-173) */
+int ora_update_ice_temperature(const ora_mesh *m, ora_ice *ice, const ora_config *c, int *n_unstable_out)
+{
+  int nV = m->nV, nZ = c->nZ;
+  *n_unstable_out = 0;
+  if (c->benchmark == ORA_BM_MISMIP_MOD || c->benchmark == ORA_BM_MESH_GENERATION_TEST || c->benchmark == ORA_BM_HALFAR ||
+      c->benchmark == ORA_BM_BUELER || c->benchmark == ORA_BM_SSA_ICESTREAM) return 0;   /* :44-64 */
+  /* initialize_zeta_discretization */
+  double a_k[33], b_k[33], a_zeta[33], b_zeta[33], c_zeta[33], a_zetazeta[33], b_zetazeta[33], c_zetazeta[33];
+  for (int k = 2; k <= nZ; k++) a_k[k] = c->zeta[k - 1] - c->zeta[k - 2];
+  for (int k = 1; k <= nZ - 1; k++) b_k[k] = c->zeta[k] - c->zeta[k - 1];
+  for (int k = 2; k <= nZ - 1; k++) {
+    a_zeta[k] = -b_k[k] / (a_k[k] * (a_k[k] + b_k[k]));
+    b_zeta[k] = (b_k[k] - a_k[k]) / (a_k[k] * b_k[k]);
+    c_zeta[k] = a_k[k] / (b_k[k] * (a_k[k] + b_k[k]));
+    a_zetazeta[k] = 2.0 / (a_k[k] * (a_k[k] + b_k[k]));
+    b_zetazeta[k] = -2.0 / (a_k[k] * b_k[k]);
+    c_zetazeta[k] = 2.0 / (b_k[k] * (a_k[k] + b_k[k]));
+  }
+  ora_solve_SIA_3D(m, ice, c);
+  int rc = 0, n_unstable = 0;
+#pragma omp parallel num_threads(c->nthreads) reduction(+ : n_unstable)
+  {
+    rank_t r = rank_of(m);
+    for (int k = 1; k <= nZ; k++) for (int vi = r.v1; vi <= r.v2; vi++) A2(ice->Ti_new, vi, k, nV) = 0.0;
+    SYNC
+    /* bottom_frictional_heating */
+    {
+      const double delta_v = 1E-3, q_plastic = 0.30, u_threshold = 100.0;
+      for (int vi = r.v1; vi <= r.v2; vi++) A1(ice->frictional_heating, vi) = 0.0;
+      SYNC
+      for (int vi = r.v1; vi <= r.v2; vi++) {
+        if (A1(ice->mask_sheet, vi) == 1) {
+          double u = A1(ice->U_SSA, vi), v = A1(ice->V_SSA, vi);
+          double beta_base = A1(ice->tau_c_AaAc, vi) * (pow(delta_v * delta_v + u * u + v * v, 0.5 * (q_plastic - 1.0))) / pow(u_threshold, q_plastic);
+          A1(ice->frictional_heating, vi) = beta_base * (u * u + v * v);
+        }
+      }
+      SYNC
+    }
+    /* calculate_zeta_derivatives */
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      double inverse_Hi = 1.0 / fmax(0.1, A1(ice->Hi, vi));
+      A1(ice->dzeta_dz, vi) = -inverse_Hi;
+      for (int k = 1; k <= nZ; k++) {
+        A2(ice->dzeta_dt, vi, k, nV) = inverse_Hi * (A1(ice->dHs_dt, vi) - c->zeta[k - 1] * A1(ice->dHi_dt, vi));
+        A2(ice->dzeta_dx, vi, k, nV) = inverse_Hi * (A1(ice->dHs_dx, vi) - c->zeta[k - 1] * A1(ice->dHi_dx, vi));
+        A2(ice->dzeta_dy, vi, k, nV) = inverse_Hi * (A1(ice->dHs_dy, vi) - c->zeta[k - 1] * A1(ice->dHi_dy, vi));
+      }
+    }
+    SYNC
+    /* surface temperature = annual mean 2 m air temperature (:73-77) */
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      double sT = 0.0;
+      for (int mo = 1; mo <= 12; mo++) sT = sT + A2(ice->T2m, vi, mo, nV);
+      A2(ice->Ti, vi, 1, nV) = fmin(T0, sT / 12.0);
+    }
+    SYNC
+    /* heat equation, one column per vertex (:80-172) */
+    double alpha[33], beta[33], gamma[33], delta[33], dl[33], dd[33], du[33], x[33];
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      if (A1(m->edge_index, vi) > 0) continue;
+      if (A1(ice->mask_ice, vi) == 0) {
+        for (int k = 1; k <= nZ; k++) A2(ice->Ti_new, vi, k, nV) = A2(ice->Ti, vi, 1, nV);
+        continue;
+      }
+      beta[1] = 1.0; gamma[1] = 0.0; delta[1] = A2(ice->Ti, vi, 1, nV);
+      for (int k = 2; k <= nZ - 1; k++) {
+        double dTi_dx, dTi_dy, internal_heating;
+        if (!get_upwind_derivative_vertex_3D(m, ice->U_3D, ice->V_3D, ice->Ti, vi, k, &dTi_dx, &dTi_dy)) {
+#pragma omp atomic write
+          rc = -3;
+          dTi_dx = 0.0; dTi_dy = 0.0;
+        }
+        double Uk = A2(ice->U_3D, vi, k, nV), Vk = A2(ice->V_3D, vi, k, nV);
+        if (A1(ice->mask_sheet, vi) == 1) {
+          internal_heating = ((-grav * c->zeta[k - 1]) / A2(ice->Cpi, vi, k, nV)) * (
+              (a_zeta[k] * A2(ice->U_3D, vi, k - 1, nV) + b_zeta[k] * Uk + c_zeta[k] * A2(ice->U_3D, vi, k + 1, nV)) * A1(ice->dHs_dx, vi) +
+              (a_zeta[k] * A2(ice->V_3D, vi, k - 1, nV) + b_zeta[k] * Vk + c_zeta[k] * A2(ice->V_3D, vi, k + 1, nV)) * A1(ice->dHs_dy, vi));
+        } else internal_heating = 0.0;
+        double dz = A1(ice->dzeta_dz, vi);
+        double f1 = (A2(ice->Ki, vi, k, nV) * (dz * dz)) / (ice_density * A2(ice->Cpi, vi, k, nV));
+        double f2 = A2(ice->dzeta_dt, vi, k, nV) + A2(ice->dzeta_dx, vi, k, nV) * Uk + A2(ice->dzeta_dy, vi, k, nV) * Vk + dz * A2(ice->W_3D, vi, k, nV);
+        double f3 = internal_heating + (Uk * dTi_dx + Vk * dTi_dy) - A2(ice->Ti, vi, k, nV) / c->dt_thermo;
+        alpha[k] = f1 * a_zetazeta[k] - f2 * a_zeta[k];
+        beta[k] = f1 * b_zetazeta[k] - f2 * b_zeta[k] - 1.0 / c->dt_thermo;
+        gamma[k] = f1 * c_zetazeta[k] - f2 * c_zeta[k];
+        delta[k] = f3;
+      }
+      double bottom_flux = (c->zeta[nZ - 1] - c->zeta[nZ - 2]) * (A1(ice->GHF, vi) + A1(ice->frictional_heating, vi)) / (A1(ice->dzeta_dz, vi) * A2(ice->Ki, vi, nZ, nV));
+      if (A1(ice->mask_shelf, vi) == 1 || A1(ice->mask_gl, vi) == 1) {
+        alpha[nZ] = 0.0; beta[nZ] = 1.0; delta[nZ] = SMT;
+      } else {
+        alpha[nZ] = 1.0; beta[nZ] = -1.0; delta[nZ] = bottom_flux;
+        if (A2(ice->Ti, vi, nZ, nV) >= A2(ice->Ti_pmp, vi, nZ, nV)) { alpha[nZ] = 0.0; beta[nZ] = 1.0; delta[nZ] = A2(ice->Ti_pmp, vi, nZ, nV); }
+      }
+      /* tridiagonal_solve( alpha, beta, gamma, delta): ldiag = alpha(2:NZ), diag = beta, udiag = gamma(1:NZ-1) */
+      for (int k = 1; k <= nZ; k++) { dd[k - 1] = beta[k]; x[k - 1] = delta[k]; }
+      for (int k = 1; k <= nZ - 1; k++) { dl[k - 1] = alpha[k + 1]; du[k - 1] = gamma[k]; }
+      int info;
+      ora_dgtsv(nZ, dl, dd, du, x, &info);
+      if (info != 0) {
+#pragma omp atomic write
+        rc = -2;
+      }
+      for (int k = 1; k <= nZ; k++) A2(ice->Ti_new, vi, k, nV) = x[k - 1];
+      for (int k = 1; k <= nZ - 1; k++) A2(ice->Ti_new, vi, k, nV) = fmin(A2(ice->Ti_new, vi, k, nV), A2(ice->Ti_pmp, vi, k, nV));
+      if (A2(ice->Ti_new, vi, nZ, nV) >= A2(ice->Ti_pmp, vi, nZ, nV))
+        A2(ice->Ti_new, vi, nZ, nV) = fmin(A2(ice->Ti_pmp, vi, nZ, nV), A2(ice->Ti, vi, nZ - 1, nV) - bottom_flux);
+    }
+    SYNC
+    apply_Neumann_boundary_3D_r(m, &r, ice->Ti_new, nZ);
+    SYNC
+    for (int k = 1; k <= nZ; k++) for (int vi = r.v1; vi <= r.v2; vi++) A2(ice->Ti, vi, k, nV) = A2(ice->Ti_new, vi, k, nV);
+    SYNC
+    /* safety net (:181-200) */
+    for (int vi = r.v1; vi <= r.v2; vi++) {
+      double mn = A2(ice->Ti, vi, 1, nV);
+      for (int k = 2; k <= nZ; k++) mn = fmin(mn, A2(ice->Ti, vi, k, nV));
+      if (mn < 150.0) { ora_replace_Ti_with_robin_solution(m, ice, c, vi); n_unstable = n_unstable + 1; }
+    }
+  }
+  *n_unstable_out = n_unstable;
+  if (rc) return rc;
+  if (n_unstable > (int)ceil((double)(float)m->nV / 100.0)) return -1;
+  return 0;
 }
 
 /* ============================================================================================
@@ -1051,9 +1377,12 @@ int ora_run_model(const ora_mesh *m, ora_ice *ice, const ora_config *c, ora_regi
     if (r->do_[ORA_T_SMB]) { ora_run_SMB_benchmark(m, ice, c, r->time, r->H0, r->R0, r->lambda); r->t0[ORA_T_SMB] = r->time; }
     if (r->do_[ORA_T_BMB]) r->t0[ORA_T_BMB] = r->time;
     if (r->do_[ORA_T_THERMO]) {
-      /* update_ice_temperature (src/thermodynamics_module.f90:44-71): the EISMINT experiments (and realistic runs) refresh
-       * U_3D / V_3D through solve_SIA_3D; the heat equation itself is out of scope */
-      if ((c->benchmark >= ORA_BM_EISMINT_1 && c->benchmark <= ORA_BM_EISMINT_6) || c->benchmark == ORA_BM_NONE) ora_solve_SIA_3D_UV(m, ice, c);
+      /* update_ice_temperature (src/thermodynamics_module.f90:23-202): the EISMINT experiments and realistic runs; with
+       * c->thermo == 0 only its solve_SIA_3D U/V half runs (what the critical time step reads) */
+      if ((c->benchmark >= ORA_BM_EISMINT_1 && c->benchmark <= ORA_BM_EISMINT_6) || c->benchmark == ORA_BM_NONE) {
+        if (c->thermo) { int nu; int rc = ora_update_ice_temperature(m, ice, c, &nu); if (rc < 0) return rc - 10; }
+        else ora_solve_SIA_3D_UV(m, ice, c);
+      }
       r->t0[ORA_T_THERMO] = r->time;
     }
     if (r->do_[ORA_T_OUTPUT]) r->t0[ORA_T_OUTPUT] = r->time;

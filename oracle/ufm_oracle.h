@@ -31,7 +31,9 @@
   X(int, nCAaAc, NAA, N1) X(int, CAaAc, NAA, NCM) \
   X(double, Nx_AaAc, NAA, NCM1) X(double, Ny_AaAc, NAA, NCM1) X(double, Nxx_AaAc, NAA, NCM1) \
   X(double, Nxy_AaAc, NAA, NCM1) X(double, Nyy_AaAc, NAA, NCM1) \
-  X(int, colour_vi, NAA, N5) X(int, colour_nV, N5, N1)
+  X(int, colour_vi, NAA, N5) X(int, colour_nV, N5, N1) \
+  /* read only by thermodynamics (upwind derivative, src/mesh_derivatives_module.f90:435-483) */ \
+  X(double, R, NV, N1) X(int, Tri, NTRI, N3) X(int, niTri, NV, N1) X(int, iTri, NV, NCM) X(double, NxTri, NTRI, N3) X(double, NyTri, NTRI, N3)
 
 #define ORA_ICE_FIELDS(X) \
   /* Aa, src/data_types_module.f90:15-214 */ \
@@ -45,6 +47,10 @@
   X(int, mask_sheet, NV, N1) X(int, mask_shelf, NV, N1) X(int, mask_coast, NV, N1) X(int, mask_margin, NV, N1) \
   X(int, mask_gl, NV, N1) X(int, mask_cf, NV, N1) X(int, mask, NV, N1) \
   X(double, Ti, NV, NZ) X(double, A_flow, NV, NZ) X(double, U_3D, NV, NZ) X(double, V_3D, NV, NZ) X(double, dVi_in, NV, NCM) \
+  /* thermodynamics, src/data_types_module.f90:160-183 */ \
+  X(double, W_3D, NV, NZ) X(double, Ti_pmp, NV, NZ) X(double, Cpi, NV, NZ) X(double, Ki, NV, NZ) \
+  X(double, dzeta_dt, NV, NZ) X(double, dzeta_dx, NV, NZ) X(double, dzeta_dy, NV, NZ) X(double, dzeta_dz, NV, N1) \
+  X(double, frictional_heating, NV, N1) X(double, GHF, NV, N1) X(double, T2m, NV, N12) X(double, Ti_new, NV, NZ) \
   /* Ac */ \
   X(double, Hi_Ac, NAC, N1) X(double, Hb_Ac, NAC, N1) X(double, Hs_Ac, NAC, N1) X(double, SL_Ac, NAC, N1) \
   X(double, dHi_dx_Ac, NAC, N1) X(double, dHi_dy_Ac, NAC, N1) X(double, dHi_dp_Ac, NAC, N1) X(double, dHi_do_Ac, NAC, N1) \
@@ -71,7 +77,7 @@
   X(double, resU_AaAc, NAA, N1) X(double, resV_AaAc, NAA, N1)
 
 typedef struct {
-  int nV, nAc, nVAaAc, nC_mem;
+  int nV, nAc, nVAaAc, nC_mem, nTri;
 #define X(t, n, r, c) t *n;
   ORA_MESH_FIELDS(X)
 #undef X
@@ -101,6 +107,8 @@ typedef struct {
   double dt_max;
   int benchmark;
   int nthreads; /* how many MPI ranks the run is split into (OpenMP threads here) */
+  double dt_thermo; /* C%dt_thermo, src/configuration_module.f90:38 */
+  int thermo;       /* ora_run_model: 1 = the whole update_ice_temperature on the thermodynamics timer; 0 = its U_3D / V_3D half only */
 } ora_config;
 
 typedef struct {
@@ -115,6 +123,16 @@ void ora_calculate_ice_thickness_change(const ora_mesh *m, ora_ice *ice, const o
 void ora_update_general_ice_model_data(const ora_mesh *m, ora_ice *ice, const ora_config *c, double time);
 void ora_solve_SIA(const ora_mesh *m, ora_ice *ice, const ora_config *c);
 void ora_solve_SIA_3D_UV(const ora_mesh *m, ora_ice *ice, const ora_config *c);
+/* thermodynamics: the whole solve_SIA_3D (U, V and W), and update_ice_temperature.
+ * ora_update_ice_temperature returns 0, -1 (more than 1 % of the vertices unstable: the reference STOPs), -2 (DGTSV info /= 0:
+ * STOP) or -3 (no upwind triangle found: the reference prints an ERROR and then indexes NxTri(0,:)); *n_unstable = number of
+ * columns replaced by the Robin solution. */
+void ora_solve_SIA_3D(const ora_mesh *m, ora_ice *ice, const ora_config *c);
+int  ora_update_ice_temperature(const ora_mesh *m, ora_ice *ice, const ora_config *c, int *n_unstable);
+void ora_replace_Ti_with_robin_solution(const ora_mesh *m, ora_ice *ice, const ora_config *c, int vi);
+/* LAPACK DGTSV (netlib reference algorithm, NRHS = 1), called by tridiagonal_solve (src/thermodynamics_module.f90:313-358);
+ * dl, d, du, b are overwritten as LAPACK does.  Pinned against scipy's bundled LAPACK in tests/test_oracle.py. */
+void ora_dgtsv(int n, double *dl, double *d, double *du, double *b, int *info);
 int  ora_solve_SSA(const ora_mesh *m, ora_ice *ice, const ora_config *c, ora_ssa_stats *st);
 void ora_determine_timesteps(const ora_mesh *m, const ora_ice *ice, const ora_config *c, double out3[3]);
 

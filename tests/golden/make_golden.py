@@ -39,10 +39,34 @@ def run_case(m):
     return out
 
 
+def run_case_thermo(m):
+    """update_ice_temperature on the thermo dome: EISMINT ice properties (no libm call except pow in U_3D) and the
+    temperature-dependent properties with sliding (exp, pow); three steps each."""
+    from oracle.oracle import Oracle
+    from ufemism_b200 import scenarios as S
+
+    out = {}
+    for bm in ("EISMINT_1", "none"):
+        st = S.state_thermo_dome(m, benchmark=bm)
+        o = Oracle(m, benchmark=bm, nthreads=1)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            o[k][:] = st[k]
+        o.update_general_ice_model_data(0.0)
+        if bm == "none":
+            o.solve_SSA()
+        for _ in range(3):
+            rc, nu = o.update_ice_temperature()
+            assert rc == 0 and nu == 0
+        for k in ("Ti", "W_3D", "U_3D", "frictional_heating"):
+            out[f"{bm}_{k}"] = o[k].copy()
+    return out
+
+
 if __name__ == "__main__":
     from ufemism_b200 import mesh as M
 
     m = M.square_mesh_with_nv(750e3, 600, seed=11)
     m.save(os.path.join(HERE, "mesh_600.npz"))
     np.savez_compressed(os.path.join(HERE, "oracle_600.npz"), **run_case(m))
+    np.savez_compressed(os.path.join(HERE, "oracle_thermo_600.npz"), **run_case_thermo(m))
     print("written", os.listdir(HERE))

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ufemism_b200.h but not exported"
     assert set(capi.EXPORTED) <= set(names)
-    assert lib.ufm_abi_version() == 1
+    assert lib.ufm_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):

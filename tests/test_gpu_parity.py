@@ -604,3 +604,117 @@ def test_conservative_remap_application(mesh_2k, order):
     from ufemism_b200.capi import UfmError
     with pytest.raises(UfmError):
         g.remap_apply("Hi", vli1, vli2, vi, w0)    # nothing stashed any more
+
+
+# ---------------------------------------------------------------- thermodynamics
+THERMO_IN = ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti")
+
+
+def _thermo_pair(mesh, benchmark, nthreads=4, **params):
+    from oracle.oracle import Oracle
+    from ufemism_b200.capi import IceModelGPU
+
+    st = S.state_thermo_dome(mesh, benchmark=benchmark)
+    o = Oracle(mesh, benchmark=benchmark, nthreads=nthreads)
+    g = IceModelGPU(mesh, benchmark=benchmark, thermo=True, **params)
+    for k in THERMO_IN:
+        o[k][:] = st[k]
+        g.upload(k, st[k])
+    o.update_general_ice_model_data(0.0)
+    g.update_general_ice_model_data(0.0)
+    return st, o, g
+
+
+def test_thermo_w3d_and_heat_equation_bit_exact(mesh_10k):
+    """Vertical velocity, heat equation (upwind advection, DGTSV, pressure-melting clamps), 3-D Neumann pass: with the EISMINT
+    ice properties and no sliding every operation is +,-,*,/,sqrt, so from identical U_3D / V_3D the device must give the
+    oracle's bits, step after step."""
+    st, o, g = _thermo_pair(mesh_10k, "EISMINT_1")
+    o.solve_SIA_3D(with_W=True)
+    g.upload("U_3D", o["U_3D"]); g.upload("V_3D", o["V_3D"])
+    g.thermo_w3d()
+    assert np.abs(o["W_3D"]).max() > 0.1
+    assert_bits_equal(g.download("W_3D"), o["W_3D"], "W_3D")
+    for step in range(3):
+        rc, n_unstable = o.update_ice_temperature()
+        assert rc == 0 and n_unstable == 0
+        ts = g.thermo_heat()
+        assert ts.n_unstable == 0
+        assert_bits_equal(g.download("Ti"), o["Ti"], f"Ti after step {step + 1}")
+    assert_bits_equal(g.download("frictional_heating"), o["frictional_heating"], "frictional_heating")
+    assert np.abs(o["Ti"] - st["Ti"]).max() > 0.05          # the field did move
+
+
+@pytest.mark.parametrize("benchmark", ["EISMINT_1", "none"])
+def test_update_ice_temperature_whole_routine(mesh_10k, benchmark):
+    """ufm_update_ice_temperature end to end (solve_SIA_3D, frictional heating, heat equation, safety net) against the
+    oracle; the realistic branch adds sliding (pow), temperature-dependent conductivity (exp) and Arrhenius flow factors."""
+    st, o, g = _thermo_pair(mesh_10k, benchmark)
+    if benchmark == "none":
+        so, sg = o.solve_SSA(), g.solve_SSA()
+        assert (so.n_outer, so.n_inner_total) == (sg.n_outer, sg.n_inner_total)
+    for step in range(2):
+        rc, n_unstable = o.update_ice_temperature()
+        ts = g.update_ice_temperature()
+        assert rc == 0 and (ts.rc, ts.n_unstable) == (0, n_unstable)
+        o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    np.testing.assert_allclose(g.download("U_3D"), o["U_3D"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(g.download("W_3D"), o["W_3D"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(g.download("Ti"), o["Ti"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(g.download("frictional_heating"), o["frictional_heating"], rtol=1e-12, atol=1e-12)
+    if benchmark == "none":
+        assert o["frictional_heating"].max() > 1.0
+
+
+def test_thermo_safety_net_and_abort(mesh_2k):
+    """Columns colder than 150 K are replaced by the Robin solution (erf: <= 2 ulp vs glibc); more than 1 % of them is fatal
+    in the reference (STOP, src/thermodynamics_module.f90:195-199) -> rc -8."""
+    from ufemism_b200.capi import UfmError
+
+    st, o, g = _thermo_pair(mesh_2k, "EISMINT_1")
+    Ti = st["Ti"].copy()
+    cold = np.flatnonzero((mesh_2k.edge_index == 0) & (st["Hi"] > 1500.0))[:5]
+    Ti[cold, 7] = -4000.0        # a wildly wrong layer: the implicit step leaves the column below 150 K
+    o["Ti"][:] = Ti; g.upload("Ti", Ti)
+    rc, n_unstable = o.update_ice_temperature()
+    ts = g.update_ice_temperature()
+    assert rc == 0 and n_unstable >= 5 and ts.n_unstable == n_unstable
+    np.testing.assert_allclose(g.download("Ti"), o["Ti"], rtol=1e-12)
+    Ti[:] = 100.0
+    o["Ti"][:] = Ti; g.upload("Ti", Ti)
+    rc, _ = o.update_ice_temperature()
+    assert rc == -1
+    with pytest.raises(UfmError) as e:
+        g.update_ice_temperature()
+    assert e.value.rc == -8
+
+
+def test_thermo_needs_triangle_data(mesh_2k):
+    from ufemism_b200.capi import IceModelGPU, UfmError
+
+    g = IceModelGPU(mesh_2k, benchmark="EISMINT_1")
+    with pytest.raises(UfmError) as e:
+        g.update_ice_temperature()
+    assert e.value.rc == -2
+    g = IceModelGPU(mesh_2k, benchmark="Halfar", thermo=True)      # thermodynamics_module.f90:52-57: not included -> no-op
+    assert g.update_ice_temperature().rc == 0
+
+
+def test_run_model_eismint1_with_thermodynamics(mesh_2k):
+    """The region loop with the whole update_ice_temperature on the thermodynamics timer (dt_thermo = 10 yr)."""
+    from oracle.oracle import Oracle
+    from ufemism_b200.capi import IceModelGPU
+
+    st = S.state_thermo_dome(mesh_2k, benchmark="EISMINT_1")
+    o = Oracle(mesh_2k, benchmark="EISMINT_1", nthreads=4, thermo=1)
+    g = IceModelGPU(mesh_2k, benchmark="EISMINT_1", thermo=True)
+    for k in THERMO_IN:
+        o[k][:] = st[k]
+        g.upload(k, st[k])
+    ro, rg = o.region(0.0), g.region(0.0)
+    assert o.run_model(ro, 25.0) == 0
+    g.run_model(rg, 25.0)
+    assert (rg.n_steps, rg.n_sia) == (ro.n_steps, ro.n_sia) and rg.time == ro.time
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+    np.testing.assert_allclose(g.download("Ti"), o["Ti"], rtol=1e-11)
+    assert np.abs(o["Ti"] - st["Ti"]).max() > 0.05

@@ -280,3 +280,102 @@ def test_solve_ssa_refuses_unknown_and_zeroes(mesh_2k):
     o["U_SSA"][:] = 1.0
     st = o.solve_SSA()
     assert st.n_outer == 0 and not o["U_SSA"].any()
+
+
+# ---------------------------------------------------------------- thermodynamics
+def test_dgtsv_restatement_matches_lapack():
+    """tridiagonal_solve calls LAPACK DGTSV (src/thermodynamics_module.f90:339,348), a dependency that is not part of the
+    reference tree.  The oracle restates the netlib algorithm; scipy bundles a real LAPACK, so the restatement is pinned to
+    it bit for bit, pivoting and singular cases included."""
+    from scipy.linalg import lapack
+
+    from oracle.oracle import dgtsv
+
+    rng = np.random.default_rng(5)
+    for t in range(1500):
+        n = int(rng.integers(2, 20))
+        dl, d, du, b = rng.normal(size=n - 1), rng.normal(size=n) * (0.2 if t % 2 else 4.0), rng.normal(size=n - 1), rng.normal(size=n)
+        if t % 97 == 0:
+            d[0] = 0.0
+            dl[0] = 0.0          # singular leading block: info = 1
+        x, info = dgtsv(dl, d, du, b)
+        _, _, _, x_ref, info_ref = lapack.dgtsv(dl, d, du, b)
+        assert info == info_ref
+        if info == 0:
+            assert np.array_equal(x, x_ref), t
+
+
+def _slab(nv=400, H=1000.0, Ts=250.0, **cfg):
+    from oracle.oracle import Oracle
+
+    m = get_mesh(nv)
+    o = Oracle(m, benchmark="EISMINT_1", nthreads=1, **cfg)
+    o["Hi"][:] = H
+    o["SL"][:] = -10000.0
+    o["GHF"][:] = 0.042 * 31556943.36
+    o["T2m"][:] = Ts
+    o["Ti"][:] = Ts
+    return m, o
+
+
+def test_heat_equation_slab_reaches_the_conductive_profile():
+    """No flow, no thickness change: the implicit column solver must relax to T(zeta) = Ts + zeta * H * GHF / K, the steady
+    state of pure vertical conduction with the geothermal flux as the basal boundary condition (pins f1, the second-derivative
+    coefficients of initialize_zeta_discretization, the sign of dzeta_dz and the Neumann row of the tridiagonal system)."""
+    m, o = _slab(dt_thermo=200.0)
+    o.update_general_ice_model_data(0.0)
+    for _ in range(1500):
+        rc, n_unstable = o.update_ice_temperature()
+        assert rc == 0 and n_unstable == 0
+    zeta = np.array(o.cfg.zeta[:15])
+    expect = 250.0 + zeta * 1000.0 * 0.042 / 2.1
+    assert np.abs(o["Ti"] - expect).max() < 1e-6
+    assert np.abs(o["W_3D"]).max() < 1e-30      # the slab is flat up to rounding of the slope stencils
+
+
+def test_heat_equation_with_thickening_reaches_the_robin_profile():
+    """A uniformly thickening slab (dHi_dt = a, geometry held fixed) advects heat downwards like accumulation does:
+    kappa T'' + (a z / H) T' = 0, whose solution is the Robin profile the reference itself codes in
+    replace_Ti_with_robin_solution (src/thermodynamics_module.f90:204-279, Cuffey & Paterson eq. 9.13-9.22).  Pins the sign
+    and form of the advective term f2 of the heat equation (through dzeta_dt) against that closed form."""
+    from math import erf, pi, sqrt
+
+    a_acc, H, Ts = 0.3, 2000.0, 240.0
+    m, o = _slab(H=H, Ts=Ts, dt_thermo=500.0)
+    o["dHi_dt"][:] = a_acc
+    o.update_general_ice_model_data(0.0)
+    assert np.allclose(o["dHs_dt"], a_acc)
+    for _ in range(1500):
+        rc, n_unstable = o.update_ice_temperature()
+        assert rc == 0 and n_unstable == 0
+    K, rho, cp = 2.1 * 31556943.36, 910.0, 2009.0
+    kappa = K / (rho * cp)
+    L = sqrt(2.0 * kappa * H / a_acc)
+    G = -0.042 * 31556943.36 / K
+    zeta = np.array(o.cfg.zeta[:15])
+    robin = np.array([Ts + sqrt(pi) / 2.0 * L * G * (erf((1.0 - z) * H / L) - erf(H / L)) for z in zeta])
+    interior = m.edge_index == 0
+    err = np.abs(o["Ti"][interior] - robin).max()
+    assert err < 0.15, err          # 15 layers: discretisation error of the finite differences, basal warming is 13 K
+    assert robin[-1] - Ts > 10.0
+
+
+def test_robin_replacement_matches_closed_form_and_counts():
+    m, o = _slab(nv=400)
+    o["SMB_year"][:] = 0.25
+    o.update_general_ice_model_data(0.0)
+    o["Ti"][:] = 100.0                      # colder than 150 K everywhere: every column is replaced, more than 1 % -> the reference STOPs
+    rc, n_unstable = o.update_ice_temperature()
+    assert rc == -1 and n_unstable > m.nV // 2
+    ti = o["Ti"][np.flatnonzero(m.edge_index == 0)[3]]
+    assert 249.9 < ti[0] < 250.1 and ti[-1] > ti[0] and np.all(np.diff(ti) > 0)
+
+
+def test_thermodynamics_golden_vectors():
+    from tests.golden.make_golden import run_case_thermo
+
+    m = M.Mesh.load(os.path.join(GOLDEN, "mesh_600.npz"))
+    g = np.load(os.path.join(GOLDEN, "oracle_thermo_600.npz"))
+    out = run_case_thermo(m)
+    for k in g.files:
+        assert np.array_equal(out[k], g[k], equal_nan=True), k

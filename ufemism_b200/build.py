@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libufemism_b200.so")
-CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu"]
+CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu", "ufm_thermo.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

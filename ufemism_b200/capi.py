@@ -36,7 +36,7 @@ class Params(ctypes.Structure):
     _fields_ = [("nZ", ctypes.c_int), ("zeta", ctypes.c_double * UFM_MAX_NZ), ("m_enh_sia", ctypes.c_double), ("m_enh_ssa", ctypes.c_double),
                 ("use_analytical_GL_flux", ctypes.c_int), ("SSA_RN_tol", ctypes.c_double), ("SSA_max_outer_loops", ctypes.c_int),
                 ("SSA_max_residual_UV", ctypes.c_double), ("SSA_SOR_omega", ctypes.c_double), ("SSA_max_inner_loops", ctypes.c_int),
-                ("dt_max", ctypes.c_double), ("benchmark", ctypes.c_int), ("exact_xy", ctypes.c_int)]
+                ("dt_max", ctypes.c_double), ("benchmark", ctypes.c_int), ("exact_xy", ctypes.c_int), ("dt_thermo", ctypes.c_double)]
 
 
 _MESH_PTRS = ["V", "A", "nC", "C", "Cw", "edge_index", "Nx", "Ny", "Aci", "iAci", "edge_index_Ac", "Nx_Ac", "Ny_Ac", "No_Ac", "Np_Ac",
@@ -44,8 +44,17 @@ _MESH_PTRS = ["V", "A", "nC", "C", "Cw", "edge_index", "Nx", "Ny", "Aci", "iAci"
 _INT_FIELDS = {"nC", "C", "edge_index", "Aci", "iAci", "edge_index_Ac", "nCAaAc", "CAaAc", "colour_vi", "colour_nV"}
 
 
+_THERMO_PTRS = ["Tri", "niTri", "iTri", "R", "NxTri", "NyTri"]
+_INT_FIELDS |= {"Tri", "niTri", "iTri"}
+
+
 class MeshDesc(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int) for n in ("nV", "nAc", "nC_mem", "ldV", "ldAc", "ldAaAc")] + [(n, ctypes.c_void_p) for n in _MESH_PTRS]
+    _fields_ = ([(n, ctypes.c_int) for n in ("nV", "nAc", "nC_mem", "ldV", "ldAc", "ldAaAc")] + [(n, ctypes.c_void_p) for n in _MESH_PTRS] +
+                [("nTri", ctypes.c_int), ("ldTri", ctypes.c_int)] + [(n, ctypes.c_void_p) for n in _THERMO_PTRS])
+
+
+class ThermoStats(ctypes.Structure):
+    _fields_ = [("n_unstable", ctypes.c_int), ("rc", ctypes.c_int)]
 
 
 class SsaStats(ctypes.Structure):
@@ -100,8 +109,10 @@ for _n, _i in FIELD_IDS.items():
         kind = "AaAc"
     elif _n.endswith("_AC"):
         kind = "Ac"
-    elif _n in ("U_3D", "V_3D", "TI"):
+    elif _n in ("U_3D", "V_3D", "TI", "W_3D"):
         kind = "3D"
+    elif _n == "T2M":
+        kind = "12"
     else:
         kind = "Aa"
     _REF_NAMES[_n] = (_i, kind, np.int32 if _n.startswith("MASK") else np.float64)
@@ -109,7 +120,8 @@ for _n, _i in FIELD_IDS.items():
 EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "ufm_synchronize", "ufm_last_error", "ufm_abi_version",
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
-            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get"]
+            "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get",
+            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat"]
 
 _lib = None
 
@@ -157,6 +169,9 @@ def load_library():
         L.ufm_counters_get.argtypes = [p, p]
         L.ufm_sor_trace_get.argtypes = [p, p, ctypes.c_int]
         L.ufm_counters_reset.argtypes = [p]
+        L.ufm_update_ice_temperature.argtypes = [p, p]
+        L.ufm_thermo_w3d.argtypes = [p]
+        L.ufm_thermo_heat.argtypes = [p, p]
         _lib = L
     return _lib
 
@@ -178,16 +193,20 @@ def default_params(benchmark="Halfar", **kw) -> Params:
     P.dt_max = 10.0
     P.benchmark = BENCHMARKS[benchmark]
     P.exact_xy = 1
+    P.dt_thermo = 10.0
     for k, v in kw.items():
         setattr(P, k, v)
     return P
 
 
-def mesh_desc(mesh):
-    """ufm_mesh_desc over the Fortran-ordered arrays of a Mesh; returns (desc, keepalive)."""
+def mesh_desc(mesh, thermo=False):
+    """ufm_mesh_desc over the Fortran-ordered arrays of a Mesh; returns (desc, keepalive).  ``thermo`` adds the triangle
+    data that only update_ice_temperature reads."""
     d = MeshDesc(nV=mesh.nV, nAc=mesh.nAc, nC_mem=mesh.nC_mem, ldV=mesh.nV, ldAc=mesh.nAc, ldAaAc=mesh.nVAaAc)
     keep = []
-    for n in _MESH_PTRS:
+    if thermo:
+        d.nTri, d.ldTri = mesh.nTri, mesh.nTri
+    for n in _MESH_PTRS + (_THERMO_PTRS if thermo else []):
         a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
         keep.append(a)
         setattr(d, n, a.ctypes.data)
@@ -229,9 +248,10 @@ def max_over_ranks(dist, value: float, device=None) -> float:
 class IceModelGPU:
     """One model region resident on one B200."""
 
-    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, **params):
+    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, thermo=False, **params):
         self.L = load_library()
         self.mesh = mesh
+        self.thermo = bool(thermo)
         self.P = default_params(benchmark, **params)
         self.h = ctypes.c_void_p()
         self.rank, self.nranks = int(rank), int(nranks)
@@ -262,7 +282,7 @@ class IceModelGPU:
         self._ck(self.L.ufm_set_params(self.h, ctypes.byref(self.P)))
 
     def upload_mesh(self, mesh):
-        d, keep = mesh_desc(mesh)
+        d, keep = mesh_desc(mesh, thermo=self.thermo)
         self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
         self.mesh = mesh
 
@@ -292,7 +312,7 @@ class IceModelGPU:
     # ---- state ----
     def _shape(self, kind):
         m = self.mesh
-        return {"Aa": (m.nV,), "Ac": (m.nAc,), "AaAc": (m.nVAaAc,), "3D": (m.nV, self.P.nZ)}[kind]
+        return {"Aa": (m.nV,), "Ac": (m.nAc,), "AaAc": (m.nVAaAc,), "3D": (m.nV, self.P.nZ), "12": (m.nV, 12)}[kind]
 
     def upload(self, name, arr):
         fid, kind, dt = _REF_NAMES[name.upper()]
@@ -337,6 +357,20 @@ class IceModelGPU:
 
     def solve_SIA_3D(self):
         self._ck(self.L.ufm_solve_SIA_3D(self.h))
+
+    def update_ice_temperature(self):
+        """update_ice_temperature; returns ThermoStats (raises UfmError for rc -8 / -9 / -10)."""
+        st = ThermoStats()
+        self._ck(self.L.ufm_update_ice_temperature(self.h, ctypes.byref(st)))
+        return st
+
+    def thermo_w3d(self):
+        self._ck(self.L.ufm_thermo_w3d(self.h))
+
+    def thermo_heat(self):
+        st = ThermoStats()
+        self._ck(self.L.ufm_thermo_heat(self.h, ctypes.byref(st)))
+        return st
 
     def solve_SSA(self):
         st = SsaStats()

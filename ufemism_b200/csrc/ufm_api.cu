@@ -240,11 +240,19 @@ static int field_ref(ufm_handle *h, int f, FieldRef *r)
     case UFM_F_PHI_FRIC_AAAC: D_(K_M, s.phi)
     case UFM_F_RHSX_AAAC: D2_(s.RHS, 0) case UFM_F_RHSY_AAAC: D2_(s.RHS, 1) case UFM_F_EU_I_AAAC: D2_(s.E, 0) case UFM_F_EV_I_AAAC: D2_(s.E, 1)
     case UFM_F_DU_DX_AAAC: D2_(s.dU, 0) case UFM_F_DU_DY_AAAC: D2_(s.dU, 1) case UFM_F_DV_DX_AAAC: D2_(s.dV, 0) case UFM_F_DV_DY_AAAC: D2_(s.dV, 1)
-    case UFM_F_U_3D: { r->kind = K_AA; r->d = s.U_3D; r->is3d = 1; return 0; }
-    case UFM_F_V_3D: { r->kind = K_AA; r->d = s.V_3D; r->is3d = 1; return 0; }
+    case UFM_F_U_3D: { r->kind = K_AA; r->d = s.U_3D; r->is3d = h->P.nZ; return 0; }
+    case UFM_F_V_3D: { r->kind = K_AA; r->d = s.V_3D; r->is3d = h->P.nZ; return 0; }
     case UFM_F_TI: {
-      if (!s.realistic_A) return ufm_set_error(-2, "Ti is only resident when do_benchmark_experiment is .FALSE. (benchmark flow factors do not read it)");
-      r->kind = K_AA; r->d = s.Ti; r->is3d = 1; return 0;
+      if (!s.Ti) return ufm_set_error(-2, "Ti is only resident when do_benchmark_experiment is .FALSE. or the mesh carries Tri (thermodynamics)");
+      r->kind = K_AA; r->d = s.Ti; r->is3d = h->P.nZ; return 0;
+    }
+    case UFM_F_W_3D: case UFM_F_GHF: case UFM_F_T2M: case UFM_F_FRICTIONAL_HEATING: {
+      if (!h->mesh.has_tri) return ufm_set_error(-2, "thermodynamics fields need a mesh uploaded with Tri / iTri / R / NxTri / NyTri");
+      r->kind = K_AA;
+      if (f == UFM_F_W_3D) { r->d = s.W_3D; r->is3d = h->P.nZ; }
+      else if (f == UFM_F_T2M) { r->d = s.T2m; r->is3d = 12; }
+      else r->d = f == UFM_F_GHF ? s.GHF : s.fric_heat;
+      return 0;
     }
     case UFM_F_A_FLOW_MEAN: D_(K_AA, s.A_mean) case UFM_F_A_FLOW_MEAN_AC: D_(K_AC, s.A_mean_Ac)
     default: break;
@@ -280,7 +288,7 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   if (rc) return rc;
   const int n = r.kind == K_AA ? m.nV : (r.kind == K_AC ? m.nAc : m.M);
   const int *r2d = r.kind == K_AA ? m.aa_ref2dev : (r.kind == K_AC ? m.ac_ref2dev : m.m_ref2dev);
-  const size_t bytes = r.is3d ? (size_t)n * h->P.nZ * sizeof(double) : (size_t)n * (r.is_int ? sizeof(int) : sizeof(double));
+  const size_t bytes = r.is3d ? (size_t)n * r.is3d * sizeof(double) : (size_t)n * (r.is_int ? sizeof(int) : sizeof(double));
   if (!to_device && field >= UFM_F_DU_DX_AAAC && field <= UFM_F_DV_DY_AAAC) { if ((rc = ufm_k_ssa_gradients(h))) return rc; }
   if (to_device) {
     if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
@@ -289,7 +297,7 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
     UFM_CUDA(cudaMemcpyAsync(h->dev_staging, src, bytes, cudaMemcpyHostToDevice, h->stream));
     h->cnt.h2d_bytes += (double)bytes;
   }
-  if (r.is3d) rc = ufm_perm_3d(h, n, h->P.nZ, m.nVp, r2d, r.d, (double *)h->dev_staging, to_device);
+  if (r.is3d) rc = ufm_perm_3d(h, n, r.is3d, m.nVp, r2d, r.d, (double *)h->dev_staging, to_device);
   else if (r.bits) rc = ufm_perm_mask(h, n, r2d, r.bits, r.barg, r.bmode, (int *)h->dev_staging);
   else if (r.is_int) rc = ufm_perm_int(h, n, r2d, r.i, (int *)h->dev_staging, to_device);
   else rc = ufm_perm_double(h, n, r2d, r.d, r.stride, r.comp, (double *)h->dev_staging, to_device);
@@ -488,8 +496,12 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     if (r->do_[UFM_T_SMB]) r->t0[UFM_T_SMB] = r->time;
     if (r->do_[UFM_T_BMB]) r->t0[UFM_T_BMB] = r->time;
     if (r->do_[UFM_T_THERMO]) {
-      // update_ice_temperature (thermodynamics_module.f90:44-71): EISMINT and realistic runs refresh U_3D / V_3D
-      if ((b >= UFM_BM_EISMINT_1 && b <= UFM_BM_EISMINT_6) || b == UFM_BM_NONE) { if ((rc = ufm_solve_SIA_3D(h))) return rc; }
+      // update_ice_temperature (thermodynamics_module.f90:23-202), EISMINT and realistic runs: the whole routine when the
+      // mesh carries the triangle data its upwind advection reads, otherwise only the U_3D / V_3D refresh the time step needs
+      if ((b >= UFM_BM_EISMINT_1 && b <= UFM_BM_EISMINT_6) || b == UFM_BM_NONE) {
+        if (h->mesh.has_tri) { ufm_thermo_stats ts; if ((rc = ufm_update_ice_temperature(h, &ts))) return rc; }
+        else if ((rc = ufm_solve_SIA_3D(h))) return rc;
+      }
       r->t0[UFM_T_THERMO] = r->time;
     }
     if (r->do_[UFM_T_OUTPUT]) r->t0[UFM_T_OUTPUT] = r->time;

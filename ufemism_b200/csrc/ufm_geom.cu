@@ -672,6 +672,17 @@ int ufm_k_sia3d(ufm_handle *h)
   return ufm_cuda_check(cudaGetLastError(), "k_sia3d");
 }
 
+// apply_Neumann_boundary_3D on two (nV,nZ) fields at once (or one, passed twice)
+int ufm_k_neumann3d_pair(ufm_handle *h, double *A3, double *B3)
+{
+  DevMesh &m = h->mesh;
+  const int g = grid_for((long long)m.aa.n_slices * 32, 256);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(0, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, A3, B3);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(1, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, A3, B3);
+  h->cnt.kernel_launches += 2;
+  return ufm_cuda_check(cudaGetLastError(), "k_neumann_3d");
+}
+
 int ufm_k_remap_stash(ufm_handle *h, int slot, double *field_dev)
 {
   DevMesh &m = h->mesh;

@@ -49,6 +49,9 @@ struct SlicedEll {
   unsigned char *deg = nullptr;  // [n_rows] (device) row degree, UFM_DEG_PAD for padding rows
 };
 
+// one triangle as the upwind search reads it: corner coordinates (is_in_triangle), first-order neighbour functions, corners
+struct TriRec { double ax, ay, bx, by, cx, cy, nx[3], ny[3]; int v[3]; int pad; };
+
 struct DevMesh {
   int nV = 0, nAc = 0, M = 0;     // reference sizes
   int nVp = 0, nAcp = 0, Mp = 0;  // padded device sizes
@@ -102,7 +105,15 @@ struct DevMesh {
   int *corner_nbr = nullptr;   // [4*16] neighbour position
   int *corner_row = nullptr;   // [4*16] bc row of that neighbour, or -1 when it is not an edge vertex
   double sor_bytes = 0;        // sum_i (80 + 20 n_i) over swept vertices
+  // ---- thermodynamics only (present when the mesh was uploaded with Tri) ----
+  bool has_tri = false;
+  int nTri = 0;
+  int *aa_iTri = nullptr;      // triangles around each vertex in iTri order, same sliced-ELL shape as aa_C; -1 = none
+  double2 *aa_xy = nullptr;    // vertex coordinates
+  double *aa_R = nullptr;      // mesh%R
+  TriRec *tri = nullptr;  // [nTri] reference triangle order
 };
+
 
 struct DevState {
   // Aa
@@ -111,7 +122,9 @@ struct DevState {
   double *U_SIA = nullptr, *V_SIA = nullptr, *D_SIA = nullptr, *U_SSA = nullptr, *V_SSA = nullptr, *SMB_year = nullptr, *BMB = nullptr;
   double *thk_factor = nullptr, *thk_smb = nullptr;
   double *U_3D = nullptr, *V_3D = nullptr;  // (nV,nZ) device layout k-major: [k*nVp + v]
-  double *Ti = nullptr;                     // (nV,nZ) englacial temperature, k-major (realistic flow factor only)
+  double *Ti = nullptr;                     // (nV,nZ) englacial temperature, k-major (realistic flow factor or thermodynamics)
+  double *Ti_new = nullptr, *W_3D = nullptr;  // (nV,nZ) thermodynamics
+  double *GHF = nullptr, *T2m = nullptr, *fric_heat = nullptr;  // (nV), (nV,12) month-major, (nV)
   double *A_mean = nullptr, *A_mean_Ac = nullptr;  // A_flow_mean on Aa / Ac (realistic flow factor only)
   double *Afac = nullptr;                   // (m_enh_ssa*0.5*A_flow_mean_AaAc)**(-1/n) per AaAc row (realistic only)
   bool realistic_A = false;                 // C%do_benchmark_experiment == .FALSE.
@@ -189,6 +202,9 @@ int ufm_cuda_check(cudaError_t e, const char *what);
 int ufm_k_geom(ufm_handle *h, double time);
 int ufm_k_sia(ufm_handle *h);
 int ufm_k_sia3d(ufm_handle *h);
+int ufm_k_neumann3d_pair(ufm_handle *h, double *A3, double *B3);
+int ufm_k_thermo_w3d(ufm_handle *h);
+int ufm_k_thermo_heat(ufm_handle *h, ufm_thermo_stats *st);
 int ufm_k_remap_stash(ufm_handle *h, int slot, double *field_dev);
 int ufm_k_remap_apply(ufm_handle *h, int slot, const ufm_remap_cons *map, int order, double *field_dev);
 int ufm_k_thickness(ufm_handle *h, double dt);

@@ -115,14 +115,15 @@ int ufm_mesh_free_impl(ufm_handle *h)
   void *mp[] = {m.aa_ref2dev, m.aa_dev2ref, m.ac_ref2dev, m.ac_dev2ref, m.m_ref2dev, m.m_dev2ref, m.aa.off, m.aa.deg, m.aa_C, m.aa_iAci,
                 m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0, m.aa_A, m.aa_sqrtApi, m.aa_edge, m.ac_Aci, m.ac_Np, m.ac_Cw, m.ac_Dx, m.ac_Dy,
                 m.m.off, m.m.deg, m.m_idx, m.m_cU, m.m_cV, m.m_nxy, m.m_nx, m.m_ny, m.m_nxy0, m.m_nxysum, m.m_nx0, m.m_ny0, m.m_cU0,
-                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.rng_dev, m.rng_all_dev, m.corner_dev, m.m_xmask, m.m_sowner, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row};
+                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.rng_dev, m.rng_all_dev, m.corner_dev, m.m_xmask, m.m_sowner, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row,
+                m.aa_iTri, m.aa_xy, m.aa_R, m.tri};
   for (void *p : mp) free_ptr(p);
   for (int k = 0; k < 4; k++) { free_ptr(m.ac_Nx[k]); free_ptr(m.ac_Ny[k]); free_ptr(m.ac_No[k]); }
   void *sp[] = {s.Hi, s.Hi_alt, s.Hb, s.SL, s.Hs, s.dHb_dt, s.dHi_dt, s.dHs_dt, s.dHi_dx, s.dHi_dy, s.dHs_dx, s.dHs_dy, s.dHs_dx_shelf,
                 s.dHs_dy_shelf, s.U_SIA, s.V_SIA, s.D_SIA, s.U_SSA, s.V_SSA, s.SMB_year, s.BMB, s.thk_factor, s.thk_smb, s.U_3D, s.V_3D,
                 s.mask_noice, s.mbits, s.Ti, s.A_mean, s.A_mean_Ac, s.Afac, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
                 s.Qabs_GL_Ac, s.Qp_GL_Ac, s.mbits_Ac, s.UV, s.RHS, s.E, s.rhsnum, s.dU, s.dV, s.eta, s.N, s.S, s.tau_c, s.phi, s.Hm,
-                s.mflag, s.partials, s.ctrl, s.scal, s.mail};
+                s.mflag, s.partials, s.ctrl, s.scal, s.mail, s.Ti_new, s.W_3D, s.GHF, s.T2m, s.fric_heat};
   for (void *p : sp) free_ptr(p);
   for (int k = 0; k < 4; k++) { free_ptr(s.dHi_Ac[k]); free_ptr(s.dHb_Ac[k]); free_ptr(s.dHs_Ac[k]); free_ptr(s.dSL_Ac[k]); free_ptr(s.U_SIA_Ac[k]); free_ptr(s.U_SSA_Ac[k]); }
   if (s.scal_h) cudaFreeHost(s.scal_h);
@@ -397,6 +398,12 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     std::vector<int> Cn(ne), iA(ne, 0);
     std::vector<double> nx(ne, 0.0), ny(ne, 0.0), nx0(m.nVp, 0.0), ny0(m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
     int bad_vertex = 0;
+    // thermodynamics: triangles around every vertex (iTri order is the search order of get_upwind_derivative_vertex_3D)
+    const bool has_tri = d->Tri && d->niTri && d->iTri && d->R && d->NxTri && d->NyTri && d->nTri > 0;
+    m.has_tri = has_tri; m.nTri = has_tri ? d->nTri : 0;
+    std::vector<int> iT(has_tri ? ne : 0, -1);
+    std::vector<double2> xy(has_tri ? m.nVp : 0, make_double2(0.0, 0.0));
+    std::vector<double> Rr(has_tri ? m.nVp : 0, 1.0);
 #pragma omp parallel for schedule(static)
     for (int s = 0; s < m.aa.n_slices; s++) {
       int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
@@ -417,6 +424,17 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         }
         nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV);
         ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV);
+        if (has_tri) {
+          const int nt = d->niTri[vi];
+          if (nt < 0 || nt > n) { bad_vertex = vi + 1; continue; }
+          for (int c = 1; c <= nt; c++) {
+            const int ti = F2(d->iTri, vi + 1, c, ldV);
+            if (ti < 1 || ti > d->nTri) { bad_vertex = vi + 1; continue; }
+            iT[(size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l] = ti - 1;
+          }
+          xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
+          Rr[p] = d->R[vi];
+        }
         A[p] = d->A[vi];
         sA[p] = std::sqrt(d->A[vi] / UFM_PI);
       }
@@ -424,6 +442,32 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
     UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
     UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge);
+    if (has_tri) {
+      const int nT = d->nTri, ldT = d->ldTri ? d->ldTri : nT;
+      std::vector<TriRec> tr(nT);
+      int bad_tri = 0;
+#pragma omp parallel for schedule(static)
+      for (int t = 0; t < nT; t++) {
+        TriRec q;
+        int v[3];
+        bool ok = true;
+        for (int k = 0; k < 3; k++) {
+          v[k] = F2(d->Tri, t + 1, k + 1, ldT);
+          if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
+          q.v[k] = aa_r2d[v[k] - 1];
+          q.nx[k] = F2(d->NxTri, t + 1, k + 1, ldT);
+          q.ny[k] = F2(d->NyTri, t + 1, k + 1, ldT);
+        }
+        if (!ok) bad_tri = t + 1;
+        q.ax = F2(d->V, v[0], 1, ldV); q.ay = F2(d->V, v[0], 2, ldV);
+        q.bx = F2(d->V, v[1], 1, ldV); q.by = F2(d->V, v[1], 2, ldV);
+        q.cx = F2(d->V, v[2], 1, ldV); q.cy = F2(d->V, v[2], 2, ldV);
+        q.pad = 0;
+        tr[t] = q;
+      }
+      if (bad_tri) return ufm_set_error(-2, "ufm_mesh_upload: Tri(%d,:) out of range", bad_tri);
+      UP(iT, m.aa_iTri); UP(xy, m.aa_xy); UP(Rr, m.aa_R); UP(tr, m.tri);
+    }
   }
 
   lap("Aa ELL fill + upload");
@@ -469,6 +513,10 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   ZE(nv * nz, s.U_3D); ZE(nv * nz, s.V_3D);
   s.realistic_A = (h->P.benchmark == UFM_BM_NONE);
   if (s.realistic_A) { ZE(nv * nz, s.Ti); ZE(nv, s.A_mean); ZE(na, s.A_mean_Ac); ZE(nm, s.Afac); }
+  if (m.has_tri) {
+    if (!s.Ti) ZE(nv * nz, s.Ti);
+    ZE(nv * nz, s.Ti_new); ZE(nv * nz, s.W_3D); ZE(nv, s.GHF); ZE(nv * 12, s.T2m); ZE(nv, s.fric_heat);
+  }
   ZE(nv, s.mask_noice); ZE(nv, s.mbits);
   double **ac_d[] = {&s.Hi_Ac, &s.Hb_Ac, &s.SL_Ac, &s.Hs_Ac, &s.dHs_dx_shelf_Ac, &s.dHs_dy_shelf_Ac, &s.D_SIA_Ac, &s.Qabs_GL_Ac, &s.Qp_GL_Ac};
   for (double **p : ac_d) ZE(na, *p);
@@ -480,7 +528,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
 
   // staging for permuted upload/download of one field
-  size_t need = std::max<size_t>((size_t)M, nv * nz) * sizeof(double);
+  size_t need = std::max<size_t>((size_t)M, nv * std::max<size_t>(nz, 12)) * sizeof(double);
   if (h->staging_bytes < need) {
     if (h->staging) cudaFreeHost(h->staging);
     if (h->dev_staging) cudaFree(h->dev_staging);

@@ -23,7 +23,7 @@ MODULE ufemism_b200_shim
   USE mpi
   USE configuration_module,          ONLY: dp, C
   USE parallel_module,               ONLY: par, sync, ierr, cerr
-  USE data_types_module,             ONLY: type_mesh, type_ice_model, type_SMB_model, type_BMB_model
+  USE data_types_module,             ONLY: type_mesh, type_ice_model, type_SMB_model, type_BMB_model, type_climate_model
 
   IMPLICIT NONE
 
@@ -40,7 +40,9 @@ MODULE ufemism_b200_shim
                                UFM_F_U_SIA = 18, UFM_F_V_SIA = 19, UFM_F_D_SIA = 20, UFM_F_U_SSA = 21, UFM_F_V_SSA = 22, &
                                UFM_F_MASK_LAND = 23, UFM_F_MASK_OCEAN = 24, UFM_F_MASK_LAKE = 25, UFM_F_MASK_ICE = 26, &
                                UFM_F_MASK_SHEET = 27, UFM_F_MASK_SHELF = 28, UFM_F_MASK_COAST = 29, UFM_F_MASK_MARGIN = 30, &
-                               UFM_F_MASK_GL = 31, UFM_F_MASK_CF = 32, UFM_F_MASK = 33
+                               UFM_F_MASK_GL = 31, UFM_F_MASK_CF = 32, UFM_F_MASK = 33, &
+                               UFM_F_U_3D = 94, UFM_F_V_3D = 95, UFM_F_TI = 96, UFM_F_W_3D = 97, UFM_F_GHF = 98, &
+                               UFM_F_T2M = 99, UFM_F_FRICTIONAL_HEATING = 100
 
   TYPE, BIND(C) :: ufm_params
     INTEGER(C_INT)  :: nZ
@@ -54,6 +56,7 @@ MODULE ufemism_b200_shim
     REAL(C_DOUBLE)  :: dt_max
     INTEGER(C_INT)  :: benchmark
     INTEGER(C_INT)  :: exact_xy
+    REAL(C_DOUBLE)  :: dt_thermo
   END TYPE ufm_params
 
   TYPE, BIND(C) :: ufm_mesh_desc
@@ -63,7 +66,14 @@ MODULE ufemism_b200_shim
     TYPE(C_PTR)     :: Aci, iAci, edge_index_Ac, Nx_Ac, Ny_Ac, No_Ac, Np_Ac
     TYPE(C_PTR)     :: nCAaAc, CAaAc, Nx_AaAc, Ny_AaAc, Nxx_AaAc, Nxy_AaAc, Nyy_AaAc
     TYPE(C_PTR)     :: colour_vi, colour_nV
+    ! read only by update_ice_temperature_b200 (C_NULL_PTR: thermodynamics stays unavailable on the device)
+    INTEGER(C_INT)  :: nTri, ldTri
+    TYPE(C_PTR)     :: Tri, niTri, iTri, R, NxTri, NyTri
   END TYPE ufm_mesh_desc
+
+  TYPE, BIND(C) :: ufm_thermo_stats
+    INTEGER(C_INT)  :: n_unstable, rc
+  END TYPE ufm_thermo_stats
 
   TYPE, BIND(C) :: ufm_ssa_stats
     INTEGER(C_INT)  :: n_outer, n_inner_total, n_inner_last, did_reset, rc
@@ -142,6 +152,12 @@ MODULE ufemism_b200_shim
       TYPE(C_PTR), VALUE          :: handle
       INTEGER(C_INT)              :: rc
     END FUNCTION ufm_solve_SIA_3D
+    FUNCTION ufm_update_ice_temperature( handle, stats) BIND(C, NAME='ufm_update_ice_temperature') RESULT( rc)
+      IMPORT :: C_PTR, C_INT, ufm_thermo_stats
+      TYPE(C_PTR), VALUE        :: handle
+      TYPE(ufm_thermo_stats)    :: stats
+      INTEGER(C_INT)            :: rc
+    END FUNCTION ufm_update_ice_temperature
     FUNCTION ufm_host_register( handle, host, bytes) BIND(C, NAME='ufm_host_register') RESULT( rc)
       IMPORT :: C_INT, C_PTR, C_LONG_LONG
       TYPE(C_PTR), VALUE          :: handle
@@ -239,6 +255,7 @@ CONTAINS
       p%dt_max                  = C%dt_max
       p%benchmark               = b200_benchmark_id()
       p%exact_xy                = 1
+      p%dt_thermo               = C%dt_thermo
       CALL b200_check( ufm_create( INT( device, C_INT), p, b200_handle), 'ufm_create')
     END IF
     CALL sync
@@ -263,6 +280,10 @@ CONTAINS
       d%Nx_AaAc = C_LOC( mesh%Nx_AaAc);  d%Ny_AaAc = C_LOC( mesh%Ny_AaAc);  d%Nxx_AaAc = C_LOC( mesh%Nxx_AaAc)
       d%Nxy_AaAc = C_LOC( mesh%Nxy_AaAc);  d%Nyy_AaAc = C_LOC( mesh%Nyy_AaAc)
       d%colour_vi = C_LOC( mesh%colour_vi);  d%colour_nV = C_LOC( mesh%colour_nV)
+      ! triangle data of the upwind temperature advection (src/mesh_derivatives_module.f90:435-483)
+      d%nTri = mesh%nTri;  d%ldTri = SIZE( mesh%Tri, 1)
+      d%Tri = C_LOC( mesh%Tri);  d%niTri = C_LOC( mesh%niTri);  d%iTri = C_LOC( mesh%iTri);  d%R = C_LOC( mesh%R)
+      d%NxTri = C_LOC( mesh%NxTri);  d%NyTri = C_LOC( mesh%NyTri)
       CALL b200_check( ufm_mesh_upload( b200_handle, d), 'ufm_mesh_upload')
     END IF
     CALL sync
@@ -362,12 +383,35 @@ CONTAINS
   END SUBROUTINE b200_connect_gpus
 
   SUBROUTINE solve_SIA_3D_b200( mesh, ice)
-    ! U_3D / V_3D half of solve_SIA_3D (src/ice_dynamics_module.f90:317-367); W_3D stays with the thermodynamics on the host
+    ! U_3D / V_3D half of solve_SIA_3D (src/ice_dynamics_module.f90:317-367), what the critical time step reads; the
+    ! vertical velocity belongs to update_ice_temperature_b200
     TYPE(type_mesh),                     INTENT(IN)    :: mesh
     TYPE(type_ice_model), TARGET,        INTENT(INOUT) :: ice
     IF (par%master) CALL b200_check( ufm_solve_SIA_3D( b200_handle), 'solve_SIA_3D')
     CALL sync
   END SUBROUTINE solve_SIA_3D_b200
+
+  SUBROUTINE update_ice_temperature_b200( mesh, ice, climate, SMB)
+    ! Drop-in for update_ice_temperature (src/thermodynamics_module.f90:23-202): the CPU climate / SMB components own T2m and
+    ! SMB_year, the geothermal heat flux is static; Ti lives on the device between calls and is downloaded for output / restart.
+    TYPE(type_mesh),                     INTENT(IN)    :: mesh
+    TYPE(type_ice_model), TARGET,        INTENT(INOUT) :: ice
+    TYPE(type_climate_model), TARGET,    INTENT(IN)    :: climate
+    TYPE(type_SMB_model), TARGET,        INTENT(IN)    :: SMB
+    TYPE(ufm_thermo_stats) :: st
+    IF (par%master) THEN
+      CALL b200_check( ufm_state_upload( b200_handle, UFM_F_T2M,      C_LOC( climate%applied%T2m)), 'upload T2m')
+      CALL b200_check( ufm_state_upload( b200_handle, UFM_F_SMB_YEAR, C_LOC( SMB%SMB_year)),        'upload SMB_year')
+      CALL b200_check( ufm_state_upload( b200_handle, UFM_F_GHF,      C_LOC( ice%GHF)),             'upload GHF')
+      ! rc -8 = "heat equation solver unstable for more than 1% of vertices" (STOP at :195-199), -9 = DGTSV info /= 0 (STOP at :353)
+      CALL b200_check( ufm_update_ice_temperature( b200_handle, st), 'update_ice_temperature')
+      CALL b200_check( ufm_state_download( b200_handle, UFM_F_TI,   C_LOC( ice%Ti)),   'download Ti')
+      CALL b200_check( ufm_state_download( b200_handle, UFM_F_U_3D, C_LOC( ice%U_3D)), 'download U_3D')
+      CALL b200_check( ufm_state_download( b200_handle, UFM_F_V_3D, C_LOC( ice%V_3D)), 'download V_3D')
+      CALL b200_check( ufm_state_download( b200_handle, UFM_F_W_3D, C_LOC( ice%W_3D)), 'download W_3D')
+    END IF
+    CALL sync
+  END SUBROUTINE update_ice_temperature_b200
 
   SUBROUTINE critical_timesteps_b200( dt_D_2D_min, dt_V_2D_SSA_min, dt_V_3D_SIA_min)
     ! Replaces the three loops + MPI_ALLREDUCE MIN of determine_timesteps_and_actions

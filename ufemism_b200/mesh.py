@@ -98,6 +98,41 @@ class Mesh:
     colour_nV: np.ndarray
     extra: dict = field(default_factory=dict)
 
+    # ---- mesh data read only by thermodynamics (upwind temperature advection); derived on first use ----
+    @property
+    def R(self) -> np.ndarray:
+        """``determine_mesh_resolution`` (``src/mesh_help_functions_module.f90:189-216``): distance to the nearest neighbour."""
+        if "R" not in self.extra:
+            R = np.full(self.nV, self.xmax - self.xmin, np.float64)
+            for ci in range(self.nC_mem):
+                vj = self.C[:, ci]
+                has = vj > 0
+                dx = self.V[vj[has] - 1, 0] - self.V[has, 0]
+                dy = self.V[vj[has] - 1, 1] - self.V[has, 1]
+                R[has] = np.minimum(R[has], np.sqrt(dx * dx + dy * dy))
+            self.extra["R"] = R
+        return self.extra["R"]
+
+    def _tri_functions(self):
+        """First-order neighbour functions on the triangles (``src/mesh_derivatives_module.f90:30-47``)."""
+        if "NxTri" not in self.extra:
+            t = self.Tri.astype(np.int64) - 1
+            ax, ay = self.V[t[:, 0], 0], self.V[t[:, 0], 1]
+            bx, by = self.V[t[:, 1], 0], self.V[t[:, 1], 1]
+            cx, cy = self.V[t[:, 2], 0], self.V[t[:, 2], 1]
+            D = ax * (by - cy) + bx * (cy - ay) + cx * (ay - by)
+            self.extra["NxTri"] = np.asfortranarray(np.stack([(by - cy) / D, (cy - ay) / D, (ay - by) / D], 1))
+            self.extra["NyTri"] = np.asfortranarray(np.stack([(cx - bx) / D, (ax - cx) / D, (bx - ax) / D], 1))
+        return self.extra["NxTri"], self.extra["NyTri"]
+
+    @property
+    def NxTri(self) -> np.ndarray:
+        return self._tri_functions()[0]
+
+    @property
+    def NyTri(self) -> np.ndarray:
+        return self._tri_functions()[1]
+
     def save(self, path: str) -> None:
         d = {k: v for k, v in self.__dict__.items() if k != "extra"}
         np.savez_compressed(path, **d)

@@ -77,3 +77,24 @@ def state_mismip(mesh, Hi0=100.0, half_width=750e3):
     Hi[mesh.edge_index > 0] = 0.0
     return dict(benchmark="MISMIP_mod", Hi=Hi, Hb=720.0 - 778.5 * r / 750e3, SL=np.zeros(mesh.nV),
                 SMB_year=np.full(mesh.nV, 0.3), BMB=np.zeros(mesh.nV))
+
+
+def state_thermo_dome(mesh, benchmark="EISMINT_1", H0=3000.0, R0=500e3, nZ=15, zeta=None):
+    """Inputs for update_ice_temperature on a land-based dome: Halfar-shaped ice, SMB of the EISMINT-1
+    moving-margin experiment, a seasonal 2 m temperature around 270 K - 0.01 K/m * Hs (the EISMINT-1 surface temperature,
+    ``src/climate_module.f90``), a uniform geothermal heat flux of 0.0545 W m^-2 and a temperature field that rises linearly
+    from the surface value to 2 K below pressure melting at the bed.  The climate fields are host inputs in the reference."""
+    x, y = mesh.V[:, 0], mesh.V[:, 1]
+    r = np.hypot(x, y)
+    Hi = H0 * np.maximum(0.0, 1.0 - (r / R0) ** (4.0 / 3.0)) ** (3.0 / 7.0)
+    Hi[mesh.edge_index > 0] = 0.0
+    if zeta is None:
+        zeta = np.array([0.00, 0.10, 0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.90, 0.925, 0.95, 0.975, 0.99, 1.00])
+    Ts = 270.0 - 0.01 * Hi
+    month = np.arange(12)
+    T2m = np.asfortranarray(Ts[:, None] + 8.0 * np.cos(2.0 * np.pi * (month[None, :] + 0.5) / 12.0))
+    Tbed = 273.16 - 8.7e-4 * Hi - 2.0
+    Ti = np.asfortranarray(Ts[:, None] + zeta[None, :] * (Tbed - Ts)[:, None])
+    return dict(benchmark=benchmark, Hi=Hi, Hb=np.zeros(mesh.nV), SL=np.full(mesh.nV, -10000.0),
+                SMB_year=np.minimum(0.5, 1e-5 * (450000.0 - r)), BMB=np.zeros(mesh.nV),
+                T2m=T2m, GHF=np.full(mesh.nV, 0.0545 * SEC_PER_YEAR), Ti=Ti)
