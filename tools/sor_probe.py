@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
     ap.add_argument("--order", default="random")
     ap.add_argument("--others", action="store_true", help="also time the per-step kernels")
+    ap.add_argument("--thermo", action="store_true", help="time update_ice_temperature (row N2) on the same mesh, EISMINT ice properties")
     ap.add_argument("--variants", default="", help="semicolon-separated env settings to compare in one process, e.g. "
                     "'UFM_SOR_CHUNK=1;UFM_SOR_CHUNK=1,UFM_SOR_BAR=1' (the library re-reads them on every SOR launch)")
     a = ap.parse_args()
@@ -102,6 +103,31 @@ def main():
         out["ms"] = {"geom": tm(lambda: g.update_general_ice_model_data(0.0)), "sia": tm(g.solve_SIA), "thk": tm(lambda: g.calculate_ice_thickness_change(0.0)),
                      "cfl": tm(g.determine_timesteps), "prepare": tm(g.ssa_prepare), "visc": tm(g.ssa_viscosity), "setup": tm(g.ssa_sliding_and_setup),
                      "sor_1iter_launch": tm(lambda: g.ssa_sor(max_inner=1, force_iters=True)), "finish": tm(g.ssa_finish)}
+    if a.thermo and world == 1:
+        import numpy as np
+        from oracle.oracle import Oracle
+        st = S.state_thermo_dome(m, benchmark="EISMINT_1", H0=3000.0, R0=0.7 * c["half_width"])
+        gt = IceModelGPU(m, benchmark="EISMINT_1", device=local, thermo=True)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            gt.upload(k, st[k])
+        gt.update_general_ice_model_data(0.0)
+        def tmt(fn, n=5):
+            fn(); gt.synchronize()
+            t = time.perf_counter()
+            for _ in range(n):
+                fn()
+            gt.synchronize()
+            return (time.perf_counter() - t) / n * 1e3
+        out["thermo_ms"] = {"update_ice_temperature": tmt(gt.update_ice_temperature), "solve_SIA_3D_uv": tmt(gt.solve_SIA_3D),
+                            "w3d": tmt(gt.thermo_w3d), "heat": tmt(gt.thermo_heat)}
+        o = Oracle(m, benchmark="EISMINT_1", nthreads=os.cpu_count())
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            o[k][:] = st[k]
+        o.update_general_ice_model_data(0.0)
+        t = time.perf_counter(); o.update_ice_temperature(); out["thermo_ms"]["cpu_oracle_update_ice_temperature"] = (time.perf_counter() - t) * 1e3
+        out["thermo_ms"]["cpu_threads"] = os.cpu_count()
+        nz = 15
+        out["thermo_algorithmic_GB"] = {"w3d": m.nV * (3 * nz * 8 + 60) / 1e9, "heat": m.nV * ((2 + 3) * nz * 8 + 12 * 8 + 100 + 2 * nz * 8) / 1e9}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -188,12 +188,21 @@ struct ufm_handle {
   void *pinned_base[64] = {};
   size_t pinned_bytes[64] = {};
   int n_pinned = 0;
+  // device arena: every mesh / state array except the three CUDA-IPC-shared ones is carved out of a few large cudaMalloc
+  // chunks that SURVIVE ufm_mesh_free, so a re-upload after a mesh update (src/UFEMISM_main_model.f90:294) pays no
+  // allocation cost (cudaMalloc of ~100 arrays was 1-2 s of a 1 M-vertex upload)
+  struct Chunk { char *base; size_t cap; };
+  Chunk arena[64] = {};
+  int arena_n = 0, arena_cur = 0;
+  size_t arena_used = 0, arena_total = 0;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;
   size_t dev_staging_bytes = 0;
 };
 
+int ufm_arena_alloc(ufm_handle *h, size_t bytes, void **out);
+void ufm_arena_release(ufm_handle *h);
 int ufm_set_error(int rc, const char *fmt, ...);
 int ufm_cuda_check(cudaError_t e, const char *what);
 #define UFM_CUDA(x) do { int rc__ = ufm_cuda_check((x), #x); if (rc__) return rc__; } while (0)

@@ -269,8 +269,8 @@ __device__ __forceinline__ void visc_row(const ViscArgs &a, const long long o, c
 // streaming loop).  The two sums are reduced per slice with a fixed xor-shuffle tree and stored at partials[slice] (and
 // pushed to the peers of a partitioned run), so the final fixed-shape reduction over ALL slices gives the same bits for
 // any number of GPUs and any grid size.
-template <bool STORE_GRAD>
-__global__ void __launch_bounds__(256) k_ssa_viscosity(ViscArgs a)
+template <bool STORE_GRAD, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ssa_viscosity(ViscArgs a)
 {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -408,6 +408,9 @@ __global__ void k_ssa_setup(SetupArgs a)
 // ---------------------------------------------------------------------------------------------
 #ifndef SOR_BLOCK
 #define SOR_BLOCK 1024
+#endif
+#ifndef UFM_VISC_MINB_DEFAULT
+#define UFM_VISC_MINB_DEFAULT 4
 #endif
 #ifndef SOR_MIN_BLOCKS
 #define SOR_MIN_BLOCKS 1
@@ -1114,7 +1117,17 @@ static int enqueue_viscosity(ufm_handle *h, bool fuse, bool device_ctl)
   if (m.P > 1 && !h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
   ViscArgs a;
   fill_visc_args(h, a, fuse, device_ctl);
-  k_ssa_viscosity<false><<<h->num_sms * 8, 256, 0, h->stream>>>(a);
+  {
+    // resident CTAs per SM: 2 (about 120 registers, every load of a row in flight at once), 3 or 4 (64 registers, twice the warps)
+    static int minb = -1;
+    if (minb < 0) { const char *e = getenv("UFM_VISC_MINB"); minb = e ? atoi(e) : UFM_VISC_MINB_DEFAULT; }
+    if (minb == 6) k_ssa_viscosity<false, 6><<<h->num_sms * 6, 256, 0, h->stream>>>(a);
+    else if (minb == 5) k_ssa_viscosity<false, 5><<<h->num_sms * 5, 256, 0, h->stream>>>(a);
+    else if (minb == 4) k_ssa_viscosity<false, 4><<<h->num_sms * 4, 256, 0, h->stream>>>(a);
+    else if (minb == 3) k_ssa_viscosity<false, 3><<<h->num_sms * 3, 256, 0, h->stream>>>(a);
+    else if (minb == 2) k_ssa_viscosity<false, 2><<<h->num_sms * 2, 256, 0, h->stream>>>(a);
+    else k_ssa_viscosity<false, 1><<<h->num_sms * 8, 256, 0, h->stream>>>(a);
+  }
   if (m.P > 1) { k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm); h->cnt.kernel_launches++; }
   k_sum_partials<<<1, 1024, 0, h->stream>>>(m.m.n_slices, s.partials, s.scal, device_ctl ? s.ctrl + SCTL_BASE : nullptr, h->P.SSA_RN_tol);
   h->cnt.kernel_launches += 2;
@@ -1143,7 +1156,7 @@ int ufm_k_ssa_gradients(ufm_handle *h)
   fill_visc_args(h, a, false, false);
   a.cm.P = 1; a.cm.rank = 0; a.rng = m.rng_all_dev; a.visc_A = 0.0; a.Afac = nullptr; a.eta = s.eta; a.N = s.N; a.dU = s.dU; a.dV = s.dV; a.partials = s.partials;
   int grid = h->num_sms * 8;
-  k_ssa_viscosity<true><<<grid, 256, 0, h->stream>>>(a);
+  k_ssa_viscosity<true, 1><<<grid, 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_gradients");
 }

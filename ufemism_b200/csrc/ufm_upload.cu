@@ -21,25 +21,28 @@
 namespace {
 
 template <class T>
-int dev_upload(const std::vector<T> &v, T **out)
+int dev_upload(ufm_handle *h, const std::vector<T> &v, T **out)
 {
   *out = nullptr;
   size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-  UFM_CUDA(cudaMalloc((void **)out, bytes));
+  int rc = ufm_arena_alloc(h, bytes, (void **)out);
+  if (rc) return rc;
   if (!v.empty()) UFM_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   return 0;
 }
 template <class T>
-int dev_zeros(size_t n, T **out)
+int dev_zeros(ufm_handle *h, size_t n, T **out, bool own_allocation = false)
 {
   *out = nullptr;
   size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-  UFM_CUDA(cudaMalloc((void **)out, bytes));
+  if (own_allocation) UFM_CUDA(cudaMalloc((void **)out, bytes));   // buffers exported through CUDA IPC keep an allocation of their own
+  else { int rc = ufm_arena_alloc(h, bytes, (void **)out); if (rc) return rc; }
   UFM_CUDA(cudaMemset(*out, 0, bytes));
   return 0;
 }
-#define UP(vec, ptr) do { int rc_ = dev_upload(vec, &(ptr)); if (rc_) return rc_; } while (0)
-#define ZE(n, ptr) do { int rc_ = dev_zeros((size_t)(n), &(ptr)); if (rc_) return rc_; } while (0)
+#define UP(vec, ptr) do { int rc_ = dev_upload(h, vec, &(ptr)); if (rc_) return rc_; } while (0)
+#define ZE(n, ptr) do { int rc_ = dev_zeros(h, (size_t)(n), &(ptr)); if (rc_) return rc_; } while (0)
+#define ZE_OWN(n, ptr) do { int rc_ = dev_zeros(h, (size_t)(n), &(ptr), true); if (rc_) return rc_; } while (0)
 
 inline uint32_t part1by1(uint32_t x)
 {
@@ -78,6 +81,31 @@ void free_ptr(void *p) { if (p) cudaFree(p); }
 
 }  // namespace
 
+// bump allocator over a few large device chunks (see ufm_handle::arena); 256 B alignment keeps every array 128 B-line aligned
+int ufm_arena_alloc(ufm_handle *h, size_t bytes, void **out)
+{
+  bytes = (bytes + 255) & ~(size_t)255;
+  while (h->arena_cur < h->arena_n) {
+    ufm_handle::Chunk &c = h->arena[h->arena_cur];
+    if (h->arena_used + bytes <= c.cap) { *out = c.base + h->arena_used; h->arena_used += bytes; return 0; }
+    h->arena_cur++; h->arena_used = 0;
+  }
+  if (h->arena_n >= 64) return ufm_set_error(-3, "device arena: too many chunks");
+  size_t cap = std::max(bytes, std::min<size_t>(std::max<size_t>(h->arena_total, (size_t)32 << 20), (size_t)1 << 30));
+  char *p = nullptr;
+  UFM_CUDA(cudaMalloc((void **)&p, cap));
+  h->arena[h->arena_n] = {p, cap};
+  h->arena_cur = h->arena_n++;
+  h->arena_total += cap;
+  *out = p; h->arena_used = bytes;
+  return 0;
+}
+void ufm_arena_release(ufm_handle *h)
+{
+  for (int k = 0; k < h->arena_n; k++) cudaFree(h->arena[k].base);
+  h->arena_n = h->arena_cur = 0; h->arena_used = h->arena_total = 0;
+}
+
 #define F2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
 
 // owner rank of every AaAc row from its x coordinate: P strips holding equally many rows
@@ -109,24 +137,12 @@ extern "C" int ufm_partition_owners(const ufm_mesh_desc *d, int nranks, unsigned
 
 int ufm_mesh_free_impl(ufm_handle *h)
 {
+  cudaDeviceSynchronize();   // nothing may still be reading the arrays that are handed back to the arena
   ufm_comm_reset(h);
-  DevMesh &m = h->mesh;
   DevState &s = h->st;
-  void *mp[] = {m.aa_ref2dev, m.aa_dev2ref, m.ac_ref2dev, m.ac_dev2ref, m.m_ref2dev, m.m_dev2ref, m.aa.off, m.aa.deg, m.aa_C, m.aa_iAci,
-                m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0, m.aa_A, m.aa_sqrtApi, m.aa_edge, m.ac_Aci, m.ac_Np, m.ac_Cw, m.ac_Dx, m.ac_Dy,
-                m.m.off, m.m.deg, m.m_idx, m.m_cU, m.m_cV, m.m_nxy, m.m_nx, m.m_ny, m.m_nxy0, m.m_nxysum, m.m_nx0, m.m_ny0, m.m_cU0,
-                m.m_cV0, m.m_src, m.aa2m, m.ac2m, m.rng_dev, m.rng_all_dev, m.corner_dev, m.m_xmask, m.m_sowner, m.bc_pos, m.bc_ptr, m.bc_nbr, m.corner_nbr, m.corner_row,
-                m.aa_iTri, m.aa_xy, m.aa_R, m.tri};
-  for (void *p : mp) free_ptr(p);
-  for (int k = 0; k < 4; k++) { free_ptr(m.ac_Nx[k]); free_ptr(m.ac_Ny[k]); free_ptr(m.ac_No[k]); }
-  void *sp[] = {s.Hi, s.Hi_alt, s.Hb, s.SL, s.Hs, s.dHb_dt, s.dHi_dt, s.dHs_dt, s.dHi_dx, s.dHi_dy, s.dHs_dx, s.dHs_dy, s.dHs_dx_shelf,
-                s.dHs_dy_shelf, s.U_SIA, s.V_SIA, s.D_SIA, s.U_SSA, s.V_SSA, s.SMB_year, s.BMB, s.thk_factor, s.thk_smb, s.U_3D, s.V_3D,
-                s.mask_noice, s.mbits, s.Ti, s.A_mean, s.A_mean_Ac, s.Afac, s.Hi_Ac, s.Hb_Ac, s.SL_Ac, s.Hs_Ac, s.dHs_dx_shelf_Ac, s.dHs_dy_shelf_Ac, s.D_SIA_Ac,
-                s.Qabs_GL_Ac, s.Qp_GL_Ac, s.mbits_Ac, s.UV, s.RHS, s.E, s.rhsnum, s.dU, s.dV, s.eta, s.N, s.S, s.tau_c, s.phi, s.Hm,
-                s.mflag, s.partials, s.ctrl, s.scal, s.mail, s.Ti_new, s.W_3D, s.GHF, s.T2m, s.fric_heat};
-  for (void *p : sp) free_ptr(p);
-  for (int k = 0; k < 4; k++) { free_ptr(s.dHi_Ac[k]); free_ptr(s.dHb_Ac[k]); free_ptr(s.dHs_Ac[k]); free_ptr(s.dSL_Ac[k]); free_ptr(s.U_SIA_Ac[k]); free_ptr(s.U_SSA_Ac[k]); }
+  free_ptr(s.UV); free_ptr(s.partials); free_ptr(s.mail);   // own allocations (CUDA IPC)
   if (s.scal_h) cudaFreeHost(s.scal_h);
+  h->arena_cur = 0; h->arena_used = 0;   // every other array lives in the arena, which is kept for the next mesh
   h->mesh = DevMesh();
   h->st = DevState();
   h->has_mesh = false;
@@ -140,7 +156,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   const int N = d->nV, E = d->nAc, M = N + E, W = d->nC_mem;
   const int ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E, ldM = d->ldAaAc ? d->ldAaAc : M;
   if (N < 5 || E < 4 || W < 3 || W > 64) return ufm_set_error(-2, "ufm_mesh_upload: implausible sizes nV=%d nAc=%d nC_mem=%d", N, E, W);
-  if (h->has_mesh) ufm_mesh_free_impl(h);
+  ufm_mesh_free_impl(h);   // also after a failed upload: hands every array back to the arena
   DevMesh &m = h->mesh;
   m.nV = N; m.nAc = E; m.M = M;
   const bool timing = getenv("UFM_UPLOAD_TIMING") != nullptr;
@@ -312,6 +328,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       }
     }
     m.sor_bytes = bytes;
+    lap("AaAc ELL fill");
     // who reads whom across the partition: every row reads its neighbours (sweep, viscosity, Neumann pass); a corner row
     // additionally reads the non-edge neighbours of its edge neighbours (it recomputes their boundary value)
     std::vector<unsigned char> xmask(m.Mp, 0), sowner(m.m.n_slices, 0);
@@ -338,7 +355,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     UP(aa2m, m.aa2m); UP(ac2m, m.ac2m);
   }
 
-  lap("AaAc ELL fill + upload");
+  lap("AaAc upload");
   // ---- Neumann boundary lists (apply_Neumann_boundary_AaAc, mesh_ArakawaC_module.f90:660-724) ----
   {
     std::vector<int> bc_pos, bc_ptr(1, 0), bc_nbr, row_of(M, -1);
@@ -440,6 +457,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       }
     }
     if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
+    lap("Aa ELL fill");
     UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
     UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge);
     if (has_tri) {
@@ -470,7 +488,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     }
   }
 
-  lap("Aa ELL fill + upload");
+  lap("Aa (+ triangle) upload");
   // ---- Ac arrays ----
   {
     std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
@@ -497,13 +515,14 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
     }
     if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
+    lap("Ac fill");
     UP(aci, m.ac_Aci); UP(np, m.ac_Np); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
     for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
   }
   UP(aa_r2d, m.aa_ref2dev); UP(aa_d2r, m.aa_dev2ref); UP(ac_r2d, m.ac_ref2dev); UP(ac_d2r, m.ac_dev2ref);
   UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
 
-  lap("Ac arrays + upload");
+  lap("Ac + permutation upload");
   // ---- state, zero-filled ----
   DevState &s = h->st;
   const size_t nv = m.nVp, na = m.nAcp, nm = m.Mp, nz = (size_t)h->P.nZ;
@@ -522,9 +541,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   for (double **p : ac_d) ZE(na, *p);
   for (int k = 0; k < 4; k++) { ZE(na, s.dHi_Ac[k]); ZE(na, s.dHb_Ac[k]); ZE(na, s.dHs_Ac[k]); ZE(na, s.dSL_Ac[k]); ZE(na, s.U_SIA_Ac[k]); ZE(na, s.U_SSA_Ac[k]); }
   ZE(na, s.mbits_Ac);
-  ZE(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
+  ZE_OWN(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
-  ZE(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(MAIL_WORDS, s.mail);
+  ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE_OWN(MAIL_WORDS, s.mail);
   UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
 
   // staging for permuted upload/download of one field
