@@ -718,3 +718,21 @@ def test_run_model_eismint1_with_thermodynamics(mesh_2k):
     assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
     np.testing.assert_allclose(g.download("Ti"), o["Ti"], rtol=1e-11)
     assert np.abs(o["Ti"] - st["Ti"]).max() > 0.05
+
+
+# ---------------------------------------------------------------- mesh data derived on the device
+@pytest.mark.parametrize("exact_xy", [1, 0])
+def test_device_derived_neighbour_functions(mesh_10k, exact_xy):
+    """With no Nx_AaAc ... Nyy_AaAc in the mesh descriptor the library evaluates get_neighbour_functions_vertex_gr on the
+    device.  Everything downstream of those coefficients (viscosity gradients, centre coefficients, both cross-term modes of
+    the sweep, the whole solve) must have the bits of a run on host-built coefficients."""
+    st = scenario(mesh_10k, "icestream")
+    ga = make_gpu(mesh_10k, st, use_analytical_GL_flux=1, exact_xy=exact_xy)
+    gb = make_gpu(mesh_10k, st, use_analytical_GL_flux=1, exact_xy=exact_xy, derive_nf=True)
+    for g in (ga, gb):
+        g.update_general_ice_model_data(0.0)
+    sa, sb = ga.solve_SSA(), gb.solve_SSA()
+    assert (sa.n_outer, sa.n_inner_total, sa.last_max_residual, sa.last_RN) == (sb.n_outer, sb.n_inner_total, sb.last_max_residual, sb.last_RN)
+    assert sa.n_inner_total > 20
+    for f in ("U_SSA", "V_SSA", "U_SSA_AaAc", "V_SSA_AaAc", "eta_AaAc", "eu_i_AaAc", "ev_i_AaAc", "RHSx_AaAc", "dU_dx_AaAc", "dV_dy_AaAc", "dU_dy_AaAc"):
+        assert_bits_equal(gb.download(f), ga.download(f), f)

@@ -199,7 +199,10 @@ def default_params(benchmark="Halfar", **kw) -> Params:
     return P
 
 
-def mesh_desc(mesh, thermo=False):
+_NF_AAAC = ("Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc")
+
+
+def mesh_desc(mesh, thermo=False, derive_nf=False):
     """ufm_mesh_desc over the Fortran-ordered arrays of a Mesh; returns (desc, keepalive).  ``thermo`` adds the triangle
     data that only update_ice_temperature reads."""
     d = MeshDesc(nV=mesh.nV, nAc=mesh.nAc, nC_mem=mesh.nC_mem, ldV=mesh.nV, ldAc=mesh.nAc, ldAaAc=mesh.nVAaAc)
@@ -207,6 +210,8 @@ def mesh_desc(mesh, thermo=False):
     if thermo:
         d.nTri, d.ldTri = mesh.nTri, mesh.nTri
     for n in _MESH_PTRS + (_THERMO_PTRS if thermo else []):
+        if derive_nf and n in _NF_AAAC:
+            continue          # NULL: the library derives the AaAc neighbour functions on the device
         a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
         keep.append(a)
         setattr(d, n, a.ctypes.data)
@@ -248,10 +253,11 @@ def max_over_ranks(dist, value: float, device=None) -> float:
 class IceModelGPU:
     """One model region resident on one B200."""
 
-    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, thermo=False, **params):
+    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, thermo=False, derive_nf=False, **params):
         self.L = load_library()
         self.mesh = mesh
         self.thermo = bool(thermo)
+        self.derive_nf = bool(derive_nf)
         self.P = default_params(benchmark, **params)
         self.h = ctypes.c_void_p()
         self.rank, self.nranks = int(rank), int(nranks)
@@ -282,7 +288,7 @@ class IceModelGPU:
         self._ck(self.L.ufm_set_params(self.h, ctypes.byref(self.P)))
 
     def upload_mesh(self, mesh):
-        d, keep = mesh_desc(mesh, thermo=self.thermo)
+        d, keep = mesh_desc(mesh, thermo=self.thermo, derive_nf=self.derive_nf)
         self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
         self.mesh = mesh
 

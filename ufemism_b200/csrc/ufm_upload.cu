@@ -108,6 +108,161 @@ void ufm_arena_release(ufm_handle *h)
 
 #define F2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
 
+
+// ---------------------------------------------------------------------------------------------
+// Neighbour functions of the combined AaAc mesh derived ON THE DEVICE (second half): when the host
+// passes no Nx_AaAc ... Nyy_AaAc, the five (nV+nAc, nC_mem+1) arrays -- 2.7 GB at 1 M vertices, the bulk of the upload
+// and 1.6 s of host arithmetic -- are never built, renumbered or copied; one thread per AaAc row evaluates
+// get_neighbour_functions_vertex_gr (src/mesh_derivatives_module.f90:76-313, averaged-gradient approach; free and
+// boundary vertices) from the vertex coordinates and writes the pre-combined sweep coefficients straight into the sliced
+// ELL arrays.  Expression order follows the reference statement by statement (this file is compiled with -fmad=false),
+// so the coefficients are bit-identical to host-built ones (tests/test_gpu_parity.py::test_device_derived_neighbour_functions).
+// ---------------------------------------------------------------------------------------------
+#define NF_MAX 17
+struct NfArgs {
+  int n_slices;
+  const long long *off;
+  const unsigned char *deg, *is_edge;
+  const int *idx;
+  const double2 *xy;
+  double *cU, *cV, *nxy, *nx, *ny, *cU0, *cV0, *nxy0, *nx0, *ny0, *nxysum;
+};
+__device__ void d_neighbour_functions_vertex_gr(const double xi, const double yi, const int n, const double2 *V_vc, const bool is_edge,
+                                                double *Nx, double *Ny, double *Nxx, double *Nxy, double *Nyy)
+{
+  double NxTri[NF_MAX][3], NyTri[NF_MAX][3], NxSub[NF_MAX][3], NySub[NF_MAX][3];
+  for (int c = 0; c <= n; c++) { Nx[c] = 0; Ny[c] = 0; Nxx[c] = 0; Nxy[c] = 0; Nyy[c] = 0; }
+#define NX(c) Nx[(c) - 1]
+#define NY(c) Ny[(c) - 1]
+#define NXX(c) Nxx[(c) - 1]
+#define NXY(c) Nxy[(c) - 1]
+#define NYY(c) Nyy[(c) - 1]
+  const int nTri = is_edge ? n - 1 : n, nSub = is_edge ? n - 2 : n;
+  for (int ti = 1; ti <= nTri; ti++) {
+    int tip1s = ti + 1; if (tip1s > n) tip1s -= n;
+    const double xt = V_vc[ti - 1].x, yt = V_vc[ti - 1].y, xtp1s = V_vc[tip1s - 1].x, ytp1s = V_vc[tip1s - 1].y;
+    const double nzt = ((xt - xi) * (ytp1s - yi)) - ((yt - yi) * (xtp1s - xi));
+    NxTri[ti - 1][0] = (yt - ytp1s) / nzt; NxTri[ti - 1][1] = (ytp1s - yi) / nzt; NxTri[ti - 1][2] = (yi - yt) / nzt;
+    NyTri[ti - 1][0] = (xtp1s - xt) / nzt; NyTri[ti - 1][1] = (xi - xtp1s) / nzt; NyTri[ti - 1][2] = (xt - xi) / nzt;
+  }
+  for (int si = 1; si <= nSub; si++) {
+    int sip1s = si + 1; if (sip1s > n) sip1s -= n;
+    int sip2s = sip1s + 1; if (sip2s > n) sip2s -= n;
+    const double xs = V_vc[si - 1].x, ys = V_vc[si - 1].y;
+    const double xsp1s = V_vc[sip1s - 1].x, ysp1s = V_vc[sip1s - 1].y;
+    const double xsp2s = V_vc[sip2s - 1].x, ysp2s = V_vc[sip2s - 1].y;
+    const double third = 1.0 / 3.0;
+    const double nzs = (third * (xs + xsp1s - 2 * xi) * (ysp1s + ysp2s - 2 * yi)) -
+                       (third * (ys + ysp1s - 2 * yi) * (xsp1s + xsp2s - 2 * xi));
+    NxSub[si - 1][0] = (ys - ysp2s) / nzs; NxSub[si - 1][1] = (ysp1s + ysp2s - 2.0 * yi) / nzs; NxSub[si - 1][2] = (2.0 * yi - ys - ysp1s) / nzs;
+    NySub[si - 1][0] = (xsp2s - xs) / nzs; NySub[si - 1][1] = (2.0 * xi - xsp1s - xsp2s) / nzs; NySub[si - 1][2] = (xs + xsp1s - 2.0 * xi) / nzs;
+  }
+  if (!is_edge) {
+    const double rn = 1.0 / (double)n;
+    double sx = 0, sy = 0;
+    for (int t = 0; t < n; t++) { sx += NxTri[t][0]; sy += NyTri[t][0]; }
+    NX(n + 1) = rn * sx; NY(n + 1) = rn * sy;
+    for (int ci = 1; ci <= n; ci++) {
+      int cim1s = ci - 1; if (cim1s == 0) cim1s += n;
+      NX(ci) = rn * (NxTri[ci - 1][1] + NxTri[cim1s - 1][2]);
+      NY(ci) = rn * (NyTri[ci - 1][1] + NyTri[cim1s - 1][2]);
+    }
+    for (int si = 1; si <= n; si++) {
+      int sip1s = si + 1; if (sip1s > n) sip1s -= n;
+      NXX(n + 1) = NXX(n + 1) + (rn * ((NxSub[si - 1][0] * NX(n + 1)) + (NxSub[si - 1][1] * NxTri[si - 1][0]) + (NxSub[si - 1][2] * NxTri[sip1s - 1][0])));
+      NXY(n + 1) = NXY(n + 1) + (rn * ((NySub[si - 1][0] * NX(n + 1)) + (NySub[si - 1][1] * NxTri[si - 1][0]) + (NySub[si - 1][2] * NxTri[sip1s - 1][0])));
+      NYY(n + 1) = NYY(n + 1) + (rn * ((NySub[si - 1][0] * NY(n + 1)) + (NySub[si - 1][1] * NyTri[si - 1][0]) + (NySub[si - 1][2] * NyTri[sip1s - 1][0])));
+    }
+    double sNxSub1 = 0, sNySub1 = 0;
+    for (int q = 0; q < n; q++) { sNxSub1 += NxSub[q][0]; sNySub1 += NySub[q][0]; }
+    for (int si = 1; si <= n; si++) {
+      int sim1s = si - 1; if (sim1s < 1) sim1s += n;
+      int sim2s = sim1s - 1; if (sim2s < 1) sim2s += n;
+      NXX(si) = rn * ((NxTri[si - 1][1] * (NxSub[si - 1][1] + NxSub[sim1s - 1][2]) +
+                      (NxTri[sim1s - 1][2] * (NxSub[sim1s - 1][1] + NxSub[sim2s - 1][2]) + (NX(si) * sNxSub1))));
+      NXY(si) = rn * ((NxTri[si - 1][1] * (NySub[si - 1][1] + NySub[sim1s - 1][2]) +
+                      (NxTri[sim1s - 1][2] * (NySub[sim1s - 1][1] + NySub[sim2s - 1][2]) + (NX(si) * sNySub1))));
+      NYY(si) = rn * ((NyTri[si - 1][1] * (NySub[si - 1][1] + NySub[sim1s - 1][2]) +
+                      (NyTri[sim1s - 1][2] * (NySub[sim1s - 1][1] + NySub[sim2s - 1][2]) + (NY(si) * sNySub1))));
+    }
+  } else {
+    const double rn1 = 1.0 / (double)(n - 1), rn2 = 1.0 / (double)(n - 2);
+    double sx = 0, sy = 0;
+    for (int t = 0; t < n - 1; t++) { sx += NxTri[t][0]; sy += NyTri[t][0]; }
+    NX(n + 1) = rn1 * sx; NY(n + 1) = rn1 * sy;
+    for (int ci = 1; ci <= n; ci++) {
+      if (ci == 1) { NX(ci) = rn1 * NxTri[0][1]; NY(ci) = rn1 * NyTri[0][1]; }
+      else if (ci == n) { NX(ci) = rn1 * NxTri[n - 2][2]; NY(ci) = rn1 * NyTri[n - 2][2]; }
+      else { NX(ci) = rn1 * (NxTri[ci - 1][1] + NxTri[ci - 2][2]); NY(ci) = rn1 * (NyTri[ci - 1][1] + NyTri[ci - 2][2]); }
+    }
+    for (int si = 1; si <= n - 2; si++) {
+      NXX(n + 1) = NXX(n + 1) + (rn2 * ((NxSub[si - 1][0] * NX(n + 1)) + (NxSub[si - 1][1] * NxTri[si - 1][0]) + (NxSub[si - 1][2] * NxTri[si][0])));
+      NXY(n + 1) = NXY(n + 1) + (rn2 * ((NySub[si - 1][0] * NX(n + 1)) + (NySub[si - 1][1] * NxTri[si - 1][0]) + (NySub[si - 1][2] * NxTri[si][0])));
+      NYY(n + 1) = NYY(n + 1) + (rn2 * ((NySub[si - 1][0] * NY(n + 1)) + (NySub[si - 1][1] * NyTri[si - 1][0]) + (NySub[si - 1][2] * NyTri[si][0])));
+    }
+    double sNxSub1 = 0, sNySub1 = 0;
+    for (int q = 0; q < n - 2; q++) { sNxSub1 += NxSub[q][0]; sNySub1 += NySub[q][0]; }
+    for (int si = 1; si <= n; si++) {
+      double Axx = 0, Axy = 0, Ayy = 0, Bxx = 0, Bxy = 0, Byy = 0, Cxx = 0, Cxy = 0, Cyy = 0;
+      if (si < n - 1) {
+        Axx = NxSub[si - 1][1] * NxTri[si - 1][1]; Axy = NySub[si - 1][1] * NxTri[si - 1][1]; Ayy = NySub[si - 1][1] * NyTri[si - 1][1];
+      }
+      if (si > 1 && si < n) {
+        Bxx = (NxSub[si - 2][1] * NxTri[si - 2][2]) + (NxSub[si - 2][2] * NxTri[si - 1][1]);
+        Bxy = (NySub[si - 2][1] * NxTri[si - 2][2]) + (NySub[si - 2][2] * NxTri[si - 1][1]);
+        Byy = (NySub[si - 2][1] * NyTri[si - 2][2]) + (NySub[si - 2][2] * NyTri[si - 1][1]);
+      }
+      if (si > 2) {
+        Cxx = NxSub[si - 3][2] * NxTri[si - 2][2]; Cxy = NySub[si - 3][2] * NxTri[si - 2][2]; Cyy = NySub[si - 3][2] * NyTri[si - 2][2];
+      }
+      NXX(si) = rn2 * (Axx + Bxx + Cxx + (NX(si) * sNxSub1));
+      NXY(si) = rn2 * (Axy + Bxy + Cxy + (NX(si) * sNySub1));
+      NYY(si) = rn2 * (Ayy + Byy + Cyy + (NY(si) * sNySub1));
+    }
+  }
+#undef NX
+#undef NY
+#undef NXX
+#undef NXY
+#undef NYY
+}
+
+__global__ void __launch_bounds__(128) k_derive_nf_AaAc(NfArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    const long long o = a.off[s];
+    const int w = (int)((a.off[s + 1] - o) >> 5);
+    const int p = s * 32 + lane;
+    const int n = a.deg[p];
+    double Nx[NF_MAX], Ny[NF_MAX], Nxx[NF_MAX], Nxy[NF_MAX], Nyy[NF_MAX];
+    const bool live = n != UFM_DEG_PAD && n < NF_MAX;
+    if (live) {
+      double2 V_vc[NF_MAX];
+      for (int c = 0; c < n; c++) V_vc[c] = a.xy[a.idx[o + (long long)c * 32 + lane]];
+      const double2 vi = a.xy[p];
+      d_neighbour_functions_vertex_gr(vi.x, vi.y, n, V_vc, a.is_edge[p] != 0, Nx, Ny, Nxx, Nxy, Nyy);
+    }
+    for (int c = 0; c < w; c++) {
+      const long long e = o + (long long)c * 32 + lane;
+      const bool in = live && c < n;
+      a.cU[e] = in ? 4.0 * Nxx[c] + Nyy[c] : 0.0;
+      a.cV[e] = in ? 4.0 * Nyy[c] + Nxx[c] : 0.0;
+      a.nxy[e] = in ? Nxy[c] : 0.0;
+      a.nx[e] = in ? Nx[c] : 0.0;
+      a.ny[e] = in ? Ny[c] : 0.0;
+    }
+    double cu0 = 0.0, cv0 = 0.0, xy0 = 0.0, x0 = 0.0, y0 = 0.0, ssum = 0.0;
+    if (live) {
+      cu0 = 4.0 * Nxx[n] + Nyy[n]; cv0 = 4.0 * Nyy[n] + Nxx[n]; xy0 = Nxy[n]; x0 = Nx[n]; y0 = Ny[n];
+      ssum = xy0;
+      for (int c = 0; c < n; c++) ssum = ssum + Nxy[c];
+    }
+    a.cU0[p] = cu0; a.cV0[p] = cv0; a.nxy0[p] = xy0; a.nx0[p] = x0; a.ny0[p] = y0; a.nxysum[p] = ssum;
+  }
+}
+
 // owner rank of every AaAc row from its x coordinate: P strips holding equally many rows
 static void ufm_partition_owners_impl(const std::vector<double> &X, int P, std::vector<unsigned char> &owner)
 {
@@ -292,8 +447,11 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     m.m.n_rows = m.Mp; m.m.n_slices = m.Mp / UFM_SLICE; m.m.n_entries = off.back();
     size_t ne = (size_t)off.back();
     std::vector<int> idx(ne);
-    std::vector<double> cU(ne, 0.0), cV(ne, 0.0), nxy(ne, 0.0), nx(ne, 0.0), ny(ne, 0.0);
-    std::vector<double> nxy0(m.Mp, 0.0), nxysum(m.Mp, 0.0), nx0(m.Mp, 0.0), ny0(m.Mp, 0.0), cU0(m.Mp, 0.0), cV0(m.Mp, 0.0);
+    // no neighbour functions from the host: they are derived on the device below (k_derive_nf_AaAc)
+    const bool derive_nf = !d->Nx_AaAc || !d->Ny_AaAc || !d->Nxx_AaAc || !d->Nxy_AaAc || !d->Nyy_AaAc;
+    const size_t ne_h = derive_nf ? 0 : ne, np_h = derive_nf ? 0 : (size_t)m.Mp;
+    std::vector<double> cU(ne_h, 0.0), cV(ne_h, 0.0), nxy(ne_h, 0.0), nx(ne_h, 0.0), ny(ne_h, 0.0);
+    std::vector<double> nxy0(np_h, 0.0), nxysum(np_h, 0.0), nx0(np_h, 0.0), ny0(np_h, 0.0), cU0(np_h, 0.0), cV0(np_h, 0.0);
     std::vector<int> src(m.Mp, INT_MIN);
     double bytes = 0.0;
 #pragma omp parallel for schedule(static) reduction(+ : bytes)
@@ -305,6 +463,11 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         if (ai < 0) continue;
         int n = degv[ai];
         src[p] = ai < N ? aa_r2d[ai] : ~ac_r2d[ai - N];
+        if (!is_edge[ai]) bytes += 80.0 + 20.0 * n;
+        if (derive_nf) {
+          for (int c = 1; c <= n; c++) idx[(size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l] = m_r2d[F2(d->CAaAc, ai + 1, c, ldM) - 1];
+          continue;
+        }
         for (int c = 1; c <= n; c++) {
           size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
           idx[e] = m_r2d[F2(d->CAaAc, ai + 1, c, ldM) - 1];
@@ -324,7 +487,6 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         double ssum = nxy0[p];
         for (int c = 1; c <= n; c++) ssum = ssum + F2(d->Nxy_AaAc, ai + 1, c, ldM);
         nxysum[p] = ssum;
-        if (!is_edge[ai]) bytes += 80.0 + 20.0 * n;
       }
     }
     m.sor_bytes = bytes;
@@ -347,8 +509,34 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     for (int sl = 0; sl < m.m.n_slices; sl++)
       for (int l = 0; l < UFM_SLICE; l++) { int ai = m_d2r[sl * UFM_SLICE + l]; if (ai >= 0) { sowner[sl] = owner[ai]; break; } }
     UP(xmask, m.m_xmask); UP(sowner, m.m_sowner);
-    UP(off, m.m.off); UP(deg, m.m.deg); UP(idx, m.m_idx); UP(cU, m.m_cU); UP(cV, m.m_cV); UP(nxy, m.m_nxy); UP(nx, m.m_nx); UP(ny, m.m_ny);
-    UP(nxy0, m.m_nxy0); UP(nxysum, m.m_nxysum); UP(nx0, m.m_nx0); UP(ny0, m.m_ny0); UP(cU0, m.m_cU0); UP(cV0, m.m_cV0); UP(src, m.m_src);
+    UP(off, m.m.off); UP(deg, m.m.deg); UP(idx, m.m_idx); UP(src, m.m_src);
+    if (!derive_nf) {
+      UP(cU, m.m_cU); UP(cV, m.m_cV); UP(nxy, m.m_nxy); UP(nx, m.m_nx); UP(ny, m.m_ny);
+      UP(nxy0, m.m_nxy0); UP(nxysum, m.m_nxysum); UP(nx0, m.m_nx0); UP(ny0, m.m_ny0); UP(cU0, m.m_cU0); UP(cV0, m.m_cV0);
+    } else {
+      double **big[] = {&m.m_cU, &m.m_cV, &m.m_nxy, &m.m_nx, &m.m_ny};
+      double **row[] = {&m.m_nxy0, &m.m_nxysum, &m.m_nx0, &m.m_ny0, &m.m_cU0, &m.m_cV0};
+      for (double **q : big) { int rc_ = ufm_arena_alloc(h, std::max<size_t>(ne, 1) * sizeof(double), (void **)q); if (rc_) return rc_; }
+      for (double **q : row) { int rc_ = ufm_arena_alloc(h, (size_t)m.Mp * sizeof(double), (void **)q); if (rc_) return rc_; }
+      std::vector<double2> xy(m.Mp, make_double2(0.0, 0.0));
+      std::vector<unsigned char> edge_row(m.Mp, 0);
+#pragma omp parallel for schedule(static)
+      for (int p = 0; p < m.Mp; p++) {
+        const int ai = m_d2r[p];
+        if (ai >= 0) { xy[p] = make_double2(X[ai], Y[ai]); edge_row[p] = is_edge[ai]; }
+      }
+      double2 *xy_dev = nullptr;
+      unsigned char *edge_dev = nullptr;
+      UP(xy, xy_dev); UP(edge_row, edge_dev);
+      NfArgs a;
+      a.n_slices = m.m.n_slices; a.off = m.m.off; a.deg = m.m.deg; a.is_edge = edge_dev; a.idx = m.m_idx; a.xy = xy_dev;
+      a.cU = m.m_cU; a.cV = m.m_cV; a.nxy = m.m_nxy; a.nx = m.m_nx; a.ny = m.m_ny;
+      a.cU0 = m.m_cU0; a.cV0 = m.m_cV0; a.nxy0 = m.m_nxy0; a.nx0 = m.m_nx0; a.ny0 = m.m_ny0; a.nxysum = m.m_nxysum;
+      k_derive_nf_AaAc<<<(m.m.n_slices * 32 + 127) / 128, 128, 0, h->stream>>>(a);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      UFM_CUDA(cudaStreamSynchronize(h->stream));
+    }
     std::vector<int> aa2m(m.nVp, 0), ac2m(m.nAcp, 0);
     for (int v = 0; v < N; v++) aa2m[aa_r2d[v]] = m_r2d[v];
     for (int a = 0; a < E; a++) ac2m[ac_r2d[a]] = m_r2d[N + a];
