@@ -32,3 +32,30 @@ def mesh_2k():
 @pytest.fixture(scope="session")
 def mesh_10k():
     return get_mesh(10000)
+
+
+def fan_mesh(nv=2000, hw=750e3, fans=((-200e3, 100e3, 10), (250e3, -150e3, 14), (0.0, 300e3, 16))):
+    """A lattice mesh with three 'fans': vertices of degree 10, 14 and 16 (= nC_mem, the most the reference's arrays hold).
+    Rows wider than 8 take the generic (non-unrolled) paths of the kernels, which ordinary Delaunay meshes never reach."""
+    import numpy as np
+
+    from ufemism_b200 import mesh as M
+
+    area = (2 * hw) ** 2
+    h = np.sqrt(2 * area / (np.sqrt(3) * nv))
+    pts = M.make_points(-hw, hw, -hw, hw, h, seed=7)
+    corners, rest = pts[:4], pts[4:]
+    extra = []
+    for cx, cy, k in fans:
+        r0 = 1.6 * h
+        rest = rest[np.hypot(rest[:, 0] - cx, rest[:, 1] - cy) > r0]
+        ang = 2 * np.pi * np.arange(k) / k
+        extra.append(np.array([[cx, cy]]))
+        extra.append(np.stack([cx + 0.45 * r0 * np.cos(ang), cy + 0.45 * r0 * np.sin(ang)], 1))
+        extra.append(np.stack([cx + 0.8 * r0 * np.cos(ang + np.pi / k), cy + 0.8 * r0 * np.sin(ang + np.pi / k)], 1))
+    return M.build_mesh(np.concatenate([corners, rest] + extra), -hw, hw, -hw, hw)
+
+
+@pytest.fixture(scope="session")
+def mesh_fan():
+    return fan_mesh()

@@ -736,3 +736,54 @@ def test_device_derived_neighbour_functions(mesh_10k, exact_xy):
     assert sa.n_inner_total > 20
     for f in ("U_SSA", "V_SSA", "U_SSA_AaAc", "V_SSA_AaAc", "eta_AaAc", "eu_i_AaAc", "ev_i_AaAc", "RHSx_AaAc", "dU_dx_AaAc", "dV_dy_AaAc", "dU_dy_AaAc"):
         assert_bits_equal(gb.download(f), ga.download(f), f)
+
+
+# ---------------------------------------------------------------- rows wider than the unrolled kernels (degree 9..16)
+def test_high_degree_rows_take_the_generic_paths(mesh_fan):
+    """Degree-10, -14 and -16 vertices (16 = nC_mem): geometry, thickness update, SOR sweep (bit-exact at 40 iterations), the
+    whole SSA solve, device-derived neighbour functions and thermodynamics on a mesh whose widest slices use the generic
+    row loops instead of the width-templated ones."""
+    m = mesh_fan
+    st = scenario(m, "icestream")
+    o = make_oracle(m, st, nthreads=4)
+    g = make_gpu(m, st)
+    gd = make_gpu(m, st, derive_nf=True)
+    o.update_general_ice_model_data(0.0)
+    for q in (g, gd):
+        q.update_general_ice_model_data(0.0)
+    for f in AA_EXACT + AC_EXACT:
+        assert_bits_equal(g.download(f), o[f], f)
+    # SOR on the oracle's system
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    for q in (g, gd):
+        q.ssa_prepare(); q.upload("tau_c_AaAc", o["tau_c_AaAc"]); q.ssa_viscosity(); q.upload("eta_AaAc", o["eta_AaAc"]); q.ssa_sliding_and_setup()
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=40, force_iters=True)
+    for q in (g, gd):
+        for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+            q.upload(f, o[f])
+        stq = q.ssa_sor(max_inner=40, force_iters=True)
+        assert stq.n_inner_last == 40 == n and stq.last_max_residual == res
+        assert_bits_equal(q.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
+        assert_bits_equal(q.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
+    # whole solve + a thickness step
+    o2 = make_oracle(m, st, nthreads=4, use_analytical_GL_flux=1)
+    g2 = make_gpu(m, st, use_analytical_GL_flux=1)
+    o2.update_general_ice_model_data(0.0); g2.update_general_ice_model_data(0.0)
+    so, sg = o2.solve_SSA(), g2.solve_SSA()
+    assert (so.n_outer, so.n_inner_total) == (sg.n_outer, sg.n_inner_total)
+    assert rel_l2(g2.download("U_SSA"), o2["U_SSA"]) <= 1e-10 and rel_l2(g2.download("V_SSA"), o2["V_SSA"]) <= 1e-10
+    o2.solve_SIA(); g2.solve_SIA()
+    o2.calculate_ice_thickness_change(0.5); g2.calculate_ice_thickness_change(0.5)
+    assert rel_l2(g2.download("Hi"), o2["Hi"]) <= 1e-12
+
+
+def test_high_degree_thermodynamics_bit_exact(mesh_fan):
+    st, o, g = _thermo_pair(mesh_fan, "EISMINT_1")
+    o.solve_SIA_3D(with_W=True)
+    g.upload("U_3D", o["U_3D"]); g.upload("V_3D", o["V_3D"])
+    g.thermo_w3d()
+    assert_bits_equal(g.download("W_3D"), o["W_3D"], "W_3D")
+    rc, n_unstable = o.update_ice_temperature()
+    ts = g.thermo_heat()
+    assert rc == 0 and (ts.n_unstable, n_unstable) == (0, 0)
+    assert_bits_equal(g.download("Ti"), o["Ti"], "Ti")

@@ -379,3 +379,15 @@ def test_thermodynamics_golden_vectors():
     out = run_case_thermo(m)
     for k in g.files:
         assert np.array_equal(out[k], g[k], equal_nan=True), k
+
+
+def test_high_degree_mesh_is_valid_and_solvable(mesh_fan):
+    """Vertices with 10, 14 and 16 = nC_mem connections: the mesh substrate, the five-colouring and the oracle must cope."""
+    m = mesh_fan
+    M.check_mesh(m)
+    assert m.nC.max() == 16 and m.nCAaAc.max() == 16
+    st = S.state_ssa_icestream(m, scale=750e3 / 1800e3)
+    o = make_oracle(m, st, nthreads=2)
+    o.update_general_ice_model_data(0.0)
+    s = o.solve_SSA()
+    assert s.rc == 0 and s.n_inner_total > 10 and np.isfinite(o["U_SSA"]).all()
