@@ -787,3 +787,36 @@ def test_high_degree_thermodynamics_bit_exact(mesh_fan):
     ts = g.thermo_heat()
     assert rc == 0 and (ts.n_unstable, n_unstable) == (0, 0)
     assert_bits_equal(g.download("Ti"), o["Ti"], "Ti")
+
+
+# ---------------------------------------------------------------- closed-form benchmark SMB on the device (row N1)
+@pytest.mark.parametrize("benchmark", ["Bueler", "EISMINT_2", "EISMINT_5"])
+def test_run_model_time_dependent_benchmark_smb(mesh_2k, benchmark):
+    """run_SMB_model's benchmark branches are evaluated on the device on the SMB timer (src/SMB_module.f90:55-97, 172-283):
+    Bueler's mass balance (two pow per vertex) and the sinusoidal EISMINT forcings; same step sequence as the oracle."""
+    from oracle.oracle import Oracle, bueler_solution
+    from ufemism_b200.capi import IceModelGPU
+
+    m = mesh_2k
+    x, y = m.V[:, 0], m.V[:, 1]
+    if benchmark == "Bueler":
+        H0, R0, lam, t0 = 3000.0, 500e3, 5.0, 10764.260159329711
+        ts, te = 0.6 * t0, 0.6 * t0 + 120.0
+        Hi = bueler_solution(H0, R0, lam, x, y, ts)
+    else:
+        H0, R0, lam = 5000.0, 300e3, 5.0
+        ts, te = 4900.0, 5030.0          # a quarter period into the 20 kyr cycle: E resp. M_max well away from their means
+        Hi = S.state_thermo_dome(m)["Hi"]
+    o = Oracle(m, benchmark=benchmark, nthreads=4)
+    g = IceModelGPU(m, benchmark=benchmark)
+    o["Hi"][:] = Hi; o["SL"][:] = -10000.0
+    g.upload("Hi", Hi); g.upload("SL", np.full(m.nV, -10000.0))
+    ro, rg = o.region(ts), g.region(ts)
+    ro.H0, ro.R0, ro.lam = H0, R0, lam
+    rg.H0, rg.R0, rg.lam = H0, R0, lam
+    assert o.run_model(ro, te) == 0
+    g.run_model(rg, te)
+    assert (rg.n_steps, rg.n_sia) == (ro.n_steps, ro.n_sia) and abs(rg.time - ro.time) <= 1e-9 * te
+    np.testing.assert_allclose(g.download("SMB_year"), o["SMB_year"], rtol=1e-13, atol=1e-13)   # hypot: <= 1 ulp of ~1e5 m, times S_b = 1e-5
+    assert np.ptp(o["SMB_year"]) > 0.1
+    assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8

@@ -391,3 +391,28 @@ def test_high_degree_mesh_is_valid_and_solvable(mesh_fan):
     o.update_general_ice_model_data(0.0)
     s = o.solve_SSA()
     assert s.rc == 0 and s.n_inner_total > 10 and np.isfinite(o["U_SSA"]).all()
+
+
+def test_bueler_run_tracks_analytic_solution():
+    """The second closed form the reference holds (Bueler et al. 2005 with the reference's parameters, config_Bueler_*:
+    H0 = 3000 m, R0 = 500 km, lambda = 5): SIA + mass continuity + the time-dependent closed-form mass balance, refreshed every
+    dt_SMB = 10 yr as run_model does, from 0.6 t0 to 0.75 t0 (1600 model years, the exact solution changes by 68 %)."""
+    from oracle.oracle import Oracle, bueler_solution
+
+    H0, R0, lam, t0 = 3000.0, 500e3, 5.0, 10764.260159329711
+    errs = []
+    for nv in (2000, 8000):
+        m = get_mesh(nv)
+        x, y = m.V[:, 0], m.V[:, 1]
+        ts, te = 0.6 * t0, 0.75 * t0
+        o = Oracle(m, benchmark="Bueler", nthreads=4)
+        o["Hi"][:] = bueler_solution(H0, R0, lam, x, y, ts)
+        o["SL"][:] = -10000.0
+        r = o.region(ts)
+        r.H0, r.R0, r.lam = H0, R0, lam
+        assert o.run_model(r, te) == 0 and r.time == te
+        Ha, Hs = bueler_solution(H0, R0, lam, x, y, te), bueler_solution(H0, R0, lam, x, y, ts)
+        assert rel_l2(Hs, Ha) > 0.6
+        errs.append(rel_l2(o["Hi"], Ha))
+        assert abs(o["Hi"].max() / Ha.max() - 1.0) < 3e-3
+    assert errs[0] < 0.05 and errs[1] < 0.025 and errs[1] < 0.6 * errs[0], errs

@@ -472,8 +472,8 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
   NEED_MESH(h);
   if (!r) return ufm_set_error(-2, "NULL region");
   const int b = h->P.benchmark;
-  if (!host && (b == UFM_BM_NONE || b == UFM_BM_BUELER || (b >= UFM_BM_EISMINT_2 && b <= UFM_BM_EISMINT_6 && b != UFM_BM_EISMINT_4)))
-    return ufm_set_error(-4, "ufm_run_model: time-dependent SMB of benchmark %d must come from the host each dt_SMB; use ufm_run_model_host or the step-wise entry points", b);
+  if (!host && b == UFM_BM_NONE)
+    return ufm_set_error(-4, "ufm_run_model: without a benchmark experiment SMB and BMB come from the host's climate / SMB / BMB models each dt_SMB; use ufm_run_model_host or the step-wise entry points");
   long steps = 0;
   int rc;
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
@@ -492,9 +492,12 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
       if (rc < 0) return rc;
       r->t0[UFM_T_SSA] = r->time; r->n_ssa++; r->n_sor_total += st.n_inner_total; r->n_outer_total += st.n_outer;
     }
-    // climate / SMB / BMB: time-independent closed forms in these benchmarks (SMB_year, BMB stay as uploaded)
+    // climate / BMB: no-ops for the dynamics in the benchmark experiments (BMB = 0, src/BMB_module.f90:51-69)
     if (r->do_[UFM_T_CLIMATE]) r->t0[UFM_T_CLIMATE] = r->time;
-    if (r->do_[UFM_T_SMB]) r->t0[UFM_T_SMB] = r->time;
+    if (r->do_[UFM_T_SMB]) {   // run_SMB_model, benchmark branches: closed forms evaluated on the device (no host round trip)
+      if (!host && (rc = ufm_k_smb_benchmark(h, r->time, r->H0, r->R0, r->lambda))) return rc;
+      r->t0[UFM_T_SMB] = r->time;
+    }
     if (r->do_[UFM_T_BMB]) r->t0[UFM_T_BMB] = r->time;
     if (r->do_[UFM_T_THERMO]) {
       // update_ice_temperature (thermodynamics_module.f90:23-202), EISMINT and realistic runs: the whole routine when the

@@ -672,6 +672,63 @@ int ufm_k_sia3d(ufm_handle *h)
   return ufm_cuda_check(cudaGetLastError(), "k_sia3d");
 }
 
+// ---- run_SMB_model, benchmark branches (src/SMB_module.f90:55-97): EISMINT_SMB (:172-238), Bueler_solution_MB (:240-283),
+//      the constants of Halfar / MISMIP_mod, mesh_generation_test.  Everything that does not depend on the vertex is
+//      evaluated on the host with the host libm, as the reference does once per call. ----
+struct SmbArgs { int mode; double E, S_b, M_max, H0f1, f2, R0, lam_tp_spy, value; };
+__global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const double2 *__restrict__ xy, double *__restrict__ SMB_year)
+{
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nV) return;
+  const double2 p = xy[v];
+  double out;
+  if (a.mode == 0) out = a.value;
+  else if (a.mode == 1) out = fmin(a.M_max, a.S_b * (a.E - hypot(p.x, p.y)));   // dist = NORM2( mesh%V( vi,:))
+  else if (a.mode == 2) {
+    const double f3 = sqrt((p.x * p.x) + (p.y * p.y)) / a.R0;                     // x**2._dp: pow( x, 2) is exactly x*x
+    const double f4 = fmax(0.0, 1.0 - pow(a.f2 * f3, 4.0 / 3.0));
+    const double H = a.H0f1 * pow(f4, 3.0 / 7.0);
+    out = a.lam_tp_spy * H * UFM_SEC_PER_YEAR;
+  } else {
+    const double R = hypot(p.x, p.y);
+    out = R < 250000.0 ? 0.3 : fmax(-2.0, 0.3 - (R - 250000.0) / 200000.0);
+  }
+  SMB_year[v] = out;
+}
+int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double lambda)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  const int b = h->P.benchmark;
+  SmbArgs a;
+  memset(&a, 0, sizeof(a));
+  if (b >= UFM_BM_EISMINT_1 && b <= UFM_BM_EISMINT_6) {
+    a.mode = 1; a.E = 450000.0; a.S_b = 0.01 / 1000.0; a.M_max = 0.5;
+    if (b == UFM_BM_EISMINT_2) { if (!(time < 0.0)) a.E = 450000.0 + 100000.0 * sin(2.0 * UFM_PI * time / 20000.0); }
+    else if (b == UFM_BM_EISMINT_3) { if (!(time < 0.0)) a.E = 450000.0 + 100000.0 * sin(2.0 * UFM_PI * time / 40000.0); }
+    else if (b == UFM_BM_EISMINT_4) { a.M_max = 0.3; a.E = 999000.0; }
+    else if (b == UFM_BM_EISMINT_5) { a.E = 999000.0; a.M_max = time < 0.0 ? 0.3 : 0.3 + 0.2 * sin(2.0 * UFM_PI * time / 20000.0); }
+    else if (b == UFM_BM_EISMINT_6) { a.E = 999000.0; a.M_max = time < 0.0 ? 0.3 : 0.3 + 0.2 * sin(2.0 * UFM_PI * time / 40000.0); }
+  } else if (b == UFM_BM_HALFAR) { a.mode = 0; a.value = 0.0; }
+  else if (b == UFM_BM_MISMIP_MOD || b == UFM_BM_SSA_ICESTREAM) { a.mode = 0; a.value = 0.3; }
+  else if (b == UFM_BM_MESH_GENERATION_TEST) a.mode = 3;
+  else if (b == UFM_BM_BUELER) {
+    const double A_flow = 1E-16, rho = 910.0, g = 9.81, n = 3.0;
+    const double alpha = (2.0 - (n + 1.0) * lambda) / ((5.0 * n) + 3.0);
+    const double beta = (1.0 + ((2.0 * n) + 1.0) * lambda) / ((5.0 * n) + 3.0);
+    const double Gamma = 2.0 / 5.0 * (A_flow / UFM_SEC_PER_YEAR) * pow(rho * g, n);
+    double f1 = ((2.0 * n) + 1) / (n + 1.0);
+    double f2 = (pow(R0, n + 1.0)) / (pow(H0, (2.0 * n) + 1.0));
+    const double t0 = (beta / Gamma) * (pow(f1, n)) * f2;
+    const double tp = time * UFM_SEC_PER_YEAR;
+    f1 = pow(tp / t0, -alpha);
+    f2 = pow(tp / t0, -beta);
+    a.mode = 2; a.H0f1 = H0 * f1; a.f2 = f2; a.R0 = R0; a.lam_tp_spy = lambda / tp;
+  } else return ufm_set_error(-4, "no closed-form SMB for benchmark %d: SMB_year comes from the host", b);
+  k_smb_benchmark<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, a, m.aa_xy, s.SMB_year);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_smb_benchmark");
+}
+
 // apply_Neumann_boundary_3D on two (nV,nZ) fields at once (or one, passed twice)
 int ufm_k_neumann3d_pair(ufm_handle *h, double *A3, double *B3)
 {

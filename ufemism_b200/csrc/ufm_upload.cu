@@ -607,7 +607,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     const bool has_tri = d->Tri && d->niTri && d->iTri && d->R && d->NxTri && d->NyTri && d->nTri > 0;
     m.has_tri = has_tri; m.nTri = has_tri ? d->nTri : 0;
     std::vector<int> iT(has_tri ? ne : 0, -1);
-    std::vector<double2> xy(has_tri ? m.nVp : 0, make_double2(0.0, 0.0));
+    std::vector<double2> xy(m.nVp, make_double2(0.0, 0.0));   // vertex coordinates: benchmark SMB closed forms, upwind search
     std::vector<double> Rr(has_tri ? m.nVp : 0, 1.0);
 #pragma omp parallel for schedule(static)
     for (int s = 0; s < m.aa.n_slices; s++) {
@@ -637,9 +637,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
             if (ti < 1 || ti > d->nTri) { bad_vertex = vi + 1; continue; }
             iT[(size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l] = ti - 1;
           }
-          xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
           Rr[p] = d->R[vi];
         }
+        xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
         A[p] = d->A[vi];
         sA[p] = std::sqrt(d->A[vi] / UFM_PI);
       }
@@ -647,7 +647,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
     lap("Aa ELL fill");
     UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
-    UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge);
+    UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
     if (has_tri) {
       const int nT = d->nTri, ldT = d->ldTri ? d->ldTri : nT;
       std::vector<TriRec> tr(nT);
@@ -672,7 +672,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         tr[t] = q;
       }
       if (bad_tri) return ufm_set_error(-2, "ufm_mesh_upload: Tri(%d,:) out of range", bad_tri);
-      UP(iT, m.aa_iTri); UP(xy, m.aa_xy); UP(Rr, m.aa_R); UP(tr, m.tri);
+      UP(iT, m.aa_iTri); UP(Rr, m.aa_R); UP(tr, m.tri);
     }
   }
 
