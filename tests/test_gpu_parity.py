@@ -731,6 +731,8 @@ def test_device_derived_neighbour_functions(mesh_10k, exact_xy):
     gb = make_gpu(mesh_10k, st, use_analytical_GL_flux=1, exact_xy=exact_xy, derive_nf=True)
     for g in (ga, gb):
         g.update_general_ice_model_data(0.0)
+    for f in AA_EXACT + AC_EXACT:      # Aa (Nx, Ny) and Ac (Nx_Ac, Ny_Ac, No_Ac, Np_Ac) neighbour functions
+        assert_bits_equal(gb.download(f), ga.download(f), f)
     sa, sb = ga.solve_SSA(), gb.solve_SSA()
     assert (sa.n_outer, sa.n_inner_total, sa.last_max_residual, sa.last_RN) == (sb.n_outer, sb.n_inner_total, sb.last_max_residual, sb.last_RN)
     assert sa.n_inner_total > 20
@@ -753,6 +755,7 @@ def test_high_degree_rows_take_the_generic_paths(mesh_fan):
         q.update_general_ice_model_data(0.0)
     for f in AA_EXACT + AC_EXACT:
         assert_bits_equal(g.download(f), o[f], f)
+        assert_bits_equal(gd.download(f), o[f], f + " (device-derived neighbour functions)")
     # SOR on the oracle's system
     o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
     for q in (g, gd):

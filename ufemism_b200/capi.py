@@ -199,7 +199,7 @@ def default_params(benchmark="Halfar", **kw) -> Params:
     return P
 
 
-_NF_AAAC = ("Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc")
+_NF_AAAC = ("Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "Nx", "Ny", "Nx_Ac", "Ny_Ac", "No_Ac", "Np_Ac")
 
 
 def mesh_desc(mesh, thermo=False, derive_nf=False):
@@ -211,7 +211,7 @@ def mesh_desc(mesh, thermo=False, derive_nf=False):
         d.nTri, d.ldTri = mesh.nTri, mesh.nTri
     for n in _MESH_PTRS + (_THERMO_PTRS if thermo else []):
         if derive_nf and n in _NF_AAAC:
-            continue          # NULL: the library derives the AaAc neighbour functions on the device
+            continue          # NULL: the library derives the Aa, Ac and AaAc neighbour functions on the device
         a = np.asfortranarray(getattr(mesh, n), dtype=np.int32 if n in _INT_FIELDS else np.float64)
         keep.append(a)
         setattr(d, n, a.ctypes.data)

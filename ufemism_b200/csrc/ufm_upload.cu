@@ -263,6 +263,77 @@ __global__ void __launch_bounds__(128) k_derive_nf_AaAc(NfArgs a)
   }
 }
 
+// Aa neighbour functions Nx, Ny (the only two the path reads on the Aa mesh) from the vertex coordinates
+__global__ void __launch_bounds__(128) k_derive_nf_Aa(int n_slices, const long long *off, const unsigned char *deg, const unsigned char *edge,
+                                                      const int *C, const double2 *xy, double *Nx_o, double *Ny_o, double *Nx0, double *Ny0)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < n_slices; s += nw) {
+    const long long o = off[s];
+    const int w = (int)((off[s + 1] - o) >> 5);
+    const int p = s * 32 + lane;
+    const int n = deg[p];
+    double Nx[NF_MAX], Ny[NF_MAX], Nxx[NF_MAX], Nxy[NF_MAX], Nyy[NF_MAX];
+    const bool live = n != UFM_DEG_PAD && n < NF_MAX;
+    if (live) {
+      double2 V_vc[NF_MAX];
+      for (int c = 0; c < n; c++) V_vc[c] = xy[C[o + (long long)c * 32 + lane]];
+      const double2 vi = xy[p];
+      d_neighbour_functions_vertex_gr(vi.x, vi.y, n, V_vc, edge[p] != 0, Nx, Ny, Nxx, Nxy, Nyy);
+    }
+    for (int c = 0; c < w; c++) {
+      const long long e = o + (long long)c * 32 + lane;
+      Nx_o[e] = (live && c < n) ? Nx[c] : 0.0;
+      Ny_o[e] = (live && c < n) ? Ny[c] : 0.0;
+    }
+    Nx0[p] = live ? Nx[n] : 0.0; Ny0[p] = live ? Ny[n] : 0.0;
+  }
+}
+
+// Ac neighbour functions (make_Ac_mesh, src/mesh_ArakawaC_module.f90:24-234): gradients of the two triangles adjacent to the
+// edge, averaged; boundary segments have one triangle only.  One thread per staggered vertex.
+__device__ __forceinline__ bool d_is_boundary_segment(const int a, const int b)
+{
+  if (a == 0 || b == 0) return false;
+  if ((a == 1 || a == 2 || a == 8) && (b == 1 || b == 2 || b == 8)) return true;
+  if ((a == 2 || a == 3 || a == 4) && (b == 2 || b == 3 || b == 4)) return true;
+  if ((a == 4 || a == 5 || a == 6) && (b == 4 || b == 5 || b == 6)) return true;
+  if ((a == 6 || a == 7 || a == 8) && (b == 6 || b == 7 || b == 8)) return true;
+  return false;
+}
+struct NfAcArgs { int nAc; const int4 *Aci; const double2 *xy; const unsigned char *edge; double *Nx[4], *Ny[4], *No[4], *Np; };
+__global__ void __launch_bounds__(256) k_derive_nf_Ac(NfAcArgs a)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.nAc) return;
+  const int4 v = a.Aci[p];
+  const double2 Vi = a.xy[v.x], Vj = a.xy[v.y], Vl = a.xy[v.z];
+  double Nxl[4], Nyl[4], Nx[4], Ny[4];
+  Nxl[0] = Vl.y - Vj.y; Nxl[1] = Vi.y - Vl.y; Nxl[2] = Vj.y - Vi.y; Nxl[3] = 0.0;
+  Nyl[0] = Vj.x - Vl.x; Nyl[1] = Vl.x - Vi.x; Nyl[2] = Vi.x - Vj.x; Nyl[3] = 0.0;
+  const double Nzl = ((Vj.x - Vi.x) * (Vl.y - Vi.y)) - ((Vj.y - Vi.y) * (Vl.x - Vi.x));
+  if (!d_is_boundary_segment(a.edge[v.x], a.edge[v.y])) {
+    const double2 Vr = a.xy[v.w];
+    double Nxr[4], Nyr[4];
+    Nxr[0] = Vj.y - Vr.y; Nxr[1] = Vr.y - Vi.y; Nxr[2] = 0.0; Nxr[3] = Vi.y - Vj.y;
+    Nyr[0] = Vr.x - Vj.x; Nyr[1] = Vi.x - Vr.x; Nyr[2] = 0.0; Nyr[3] = Vj.x - Vi.x;
+    const double Nzr = ((Vr.x - Vi.x) * (Vj.y - Vi.y)) - ((Vr.y - Vi.y) * (Vj.x - Vi.x));
+    for (int k = 0; k < 4; k++) {
+      Nx[k] = -((Nxl[k] / Nzl) + (Nxr[k] / Nzr)) / 2.0;
+      Ny[k] = -((Nyl[k] / Nzl) + (Nyr[k] / Nzr)) / 2.0;
+    }
+  } else {
+    for (int k = 0; k < 4; k++) { Nx[k] = -Nxl[k] / Nzl; Ny[k] = -Nyl[k] / Nzl; }
+  }
+  const double Ux = Vj.x - Vi.x, Uy = Vj.y - Vi.y, U = sqrt(Ux * Ux + Uy * Uy);
+  a.Np[p] = 1.0 / U;
+  for (int k = 0; k < 4; k++) {
+    a.Nx[k][p] = Nx[k]; a.Ny[k][p] = Ny[k];
+    a.No[k][p] = (Ny[k] * Ux - Nx[k] * Uy) / U;
+  }
+}
+
 // owner rank of every AaAc row from its x coordinate: P strips holding equally many rows
 static void ufm_partition_owners_impl(const std::vector<double> &X, int P, std::vector<unsigned char> &owner)
 {
@@ -312,6 +383,17 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   const int ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E, ldM = d->ldAaAc ? d->ldAaAc : M;
   if (N < 5 || E < 4 || W < 3 || W > 64) return ufm_set_error(-2, "ufm_mesh_upload: implausible sizes nV=%d nAc=%d nC_mem=%d", N, E, W);
   ufm_mesh_free_impl(h);   // also after a failed upload: hands every array back to the arena
+  // The host-side renumbering below is OpenMP-parallel.  Launchers such as torchrun export OMP_NUM_THREADS=1 for every
+  // rank; one rank per GPU still has (cores / ranks) cores to itself, so use them for the duration of the upload.
+  struct OmpGuard {
+    int old;
+    explicit OmpGuard(int ranks) : old(omp_get_max_threads()) {
+      const char *e = getenv("UFM_UPLOAD_THREADS");
+      const int t = e ? atoi(e) : std::max(old, omp_get_num_procs() / std::max(1, ranks));
+      omp_set_num_threads(std::max(1, t));
+    }
+    ~OmpGuard() { omp_set_num_threads(old); }
+  } omp_guard(h->part_n);
   DevMesh &m = h->mesh;
   m.nV = N; m.nAc = E; m.M = M;
   const bool timing = getenv("UFM_UPLOAD_TIMING") != nullptr;
@@ -601,7 +683,8 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     m.aa.n_rows = m.nVp; m.aa.n_slices = m.nVp / UFM_SLICE; m.aa.n_entries = off.back();
     size_t ne = (size_t)off.back();
     std::vector<int> Cn(ne), iA(ne, 0);
-    std::vector<double> nx(ne, 0.0), ny(ne, 0.0), nx0(m.nVp, 0.0), ny0(m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
+    const bool derive_aa = !d->Nx || !d->Ny;   // no Aa neighbour functions from the host: derived on the device below
+    std::vector<double> nx(derive_aa ? 0 : ne, 0.0), ny(derive_aa ? 0 : ne, 0.0), nx0(derive_aa ? 0 : m.nVp, 0.0), ny0(derive_aa ? 0 : m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
     int bad_vertex = 0;
     // thermodynamics: triangles around every vertex (iTri order is the search order of get_upwind_derivative_vertex_3D)
     const bool has_tri = d->Tri && d->niTri && d->iTri && d->R && d->NxTri && d->NyTri && d->nTri > 0;
@@ -624,11 +707,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
           Cn[e] = aa_r2d[vc - 1];
           int first = (F2(d->Aci, aci, 1, ldAc) == vi + 1);
           iA[e] = ac_r2d[aci - 1] | (first ? (int)0x80000000u : 0);
-          nx[e] = F2(d->Nx, vi + 1, c, ldV);
-          ny[e] = F2(d->Ny, vi + 1, c, ldV);
+          if (!derive_aa) { nx[e] = F2(d->Nx, vi + 1, c, ldV); ny[e] = F2(d->Ny, vi + 1, c, ldV); }
         }
-        nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV);
-        ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV);
+        if (!derive_aa) { nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV); ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV); }
         if (has_tri) {
           const int nt = d->niTri[vi];
           if (nt < 0 || nt > n) { bad_vertex = vi + 1; continue; }
@@ -646,8 +727,20 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     }
     if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
     lap("Aa ELL fill");
-    UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci); UP(nx, m.aa_Nx); UP(ny, m.aa_Ny);
-    UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
+    UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci);
+    UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
+    if (!derive_aa) { UP(nx, m.aa_Nx); UP(ny, m.aa_Ny); UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); }
+    else {
+      double **q4[] = {&m.aa_Nx, &m.aa_Ny};
+      for (double **q : q4) { int rc_ = ufm_arena_alloc(h, std::max<size_t>(ne, 1) * sizeof(double), (void **)q); if (rc_) return rc_; }
+      double **q2[] = {&m.aa_Nx0, &m.aa_Ny0};
+      for (double **q : q2) { int rc_ = ufm_arena_alloc(h, (size_t)m.nVp * sizeof(double), (void **)q); if (rc_) return rc_; }
+      k_derive_nf_Aa<<<(m.aa.n_slices * 32 + 127) / 128, 128, 0, h->stream>>>(m.aa.n_slices, m.aa.off, m.aa.deg, m.aa_edge, m.aa_C, m.aa_xy,
+                                                                              m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      UFM_CUDA(cudaStreamSynchronize(h->stream));
+    }
     if (has_tri) {
       const int nT = d->nTri, ldT = d->ldTri ? d->ldTri : nT;
       std::vector<TriRec> tr(nT);
@@ -680,8 +773,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // ---- Ac arrays ----
   {
     std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
-    std::vector<double> c4[3][4], np(m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0);
-    for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(m.nAcp, 0.0);
+    const bool derive_ac = !d->Nx_Ac || !d->Ny_Ac || !d->No_Ac || !d->Np_Ac;   // derived on the device below
+    std::vector<double> c4[3][4], np(derive_ac ? 0 : m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0);
+    for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(derive_ac ? 0 : m.nAcp, 0.0);
     int bad_ac = 0;
 #pragma omp parallel for schedule(static)
     for (int p = 0; p < E; p++) {
@@ -691,10 +785,10 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       for (int k = 0; k < 4; k++) {
         v[k] = F2(d->Aci, a, k + 1, ldAc);
         if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
-        c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc);
+        if (!derive_ac) { c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc); }
       }
       aci[p] = make_int4(aa_r2d[v[0] - 1], aa_r2d[v[1] - 1], aa_r2d[v[2] - 1], aa_r2d[v[3] - 1]);
-      np[p] = d->Np_Ac[a - 1];
+      if (!derive_ac) np[p] = d->Np_Ac[a - 1];
       int ci = 0;
       for (int c = 1; c <= d->nC[v[0] - 1]; c++) if (F2(d->C, v[0], c, ldV) == v[1]) { ci = c; break; }
       if (!ci || !ok) { bad_ac = a; continue; }
@@ -704,8 +798,29 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     }
     if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
     lap("Ac fill");
-    UP(aci, m.ac_Aci); UP(np, m.ac_Np); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
-    for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
+    UP(aci, m.ac_Aci); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
+    if (!derive_ac) {
+      UP(np, m.ac_Np);
+      for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
+    } else {
+      NfAcArgs a;
+      a.nAc = E; a.Aci = m.ac_Aci; a.xy = m.aa_xy; a.edge = m.aa_edge;
+      const size_t bytes = (size_t)m.nAcp * sizeof(double);
+      int rc_ = ufm_arena_alloc(h, bytes, (void **)&m.ac_Np);
+      if (rc_) return rc_;
+      UFM_CUDA(cudaMemset(m.ac_Np, 0, bytes));
+      for (int k = 0; k < 4; k++) {
+        double **q3[] = {&m.ac_Nx[k], &m.ac_Ny[k], &m.ac_No[k]};
+        for (double **q : q3) { if ((rc_ = ufm_arena_alloc(h, bytes, (void **)q))) return rc_; UFM_CUDA(cudaMemset(*q, 0, bytes)); }
+        a.Nx[k] = m.ac_Nx[k]; a.Ny[k] = m.ac_Ny[k]; a.No[k] = m.ac_No[k];
+      }
+      a.Np = m.ac_Np;
+      UFM_CUDA(cudaDeviceSynchronize());
+      k_derive_nf_Ac<<<(E + 255) / 256, 256, 0, h->stream>>>(a);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      UFM_CUDA(cudaStreamSynchronize(h->stream));
+    }
   }
   UP(aa_r2d, m.aa_ref2dev); UP(aa_d2r, m.aa_dev2ref); UP(ac_r2d, m.ac_ref2dev); UP(ac_d2r, m.ac_dev2ref);
   UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
