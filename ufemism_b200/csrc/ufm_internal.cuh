@@ -144,6 +144,7 @@ struct DevState {
   double A_flow_const = 1.0e-16;   // benchmark flow factor (ice_physical_properties)
   // reductions / control
   double *partials = nullptr;      // [2*n_partial]
+  double *red_scratch = nullptr;   // [2*64] block sums of the RN reduction tree
   unsigned long long *ctrl = nullptr;  // SOR control block
   unsigned long long *mail = nullptr;  // mailbox for peer GPUs
   double *scal = nullptr;          // small result scratch (device), mirrored in pinned host memory

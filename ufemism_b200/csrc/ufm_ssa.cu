@@ -344,26 +344,41 @@ __global__ void __launch_bounds__(256, MINB) k_ssa_viscosity(ViscArgs a)
   }
 }
 // fixed-shape tree over the per-block partials: deterministic for a given grid size
-__global__ void __launch_bounds__(1024) k_sum_partials(int n, const double *partials, double *out2, unsigned long long *sctl, double RN_tol)
+#define SUM_BLOCKS 64
+__global__ void __launch_bounds__(256) k_sum_partials(int n, const double *partials, double *out2, unsigned long long *sctl, double RN_tol,
+                                                      double *scratch, unsigned *ticket)
 {
-  __shared__ double sh[2][1024];
+  // two-level tree of FIXED shape (depends on n only): SUM_BLOCKS CTAs reduce equal contiguous chunks, the last CTA to
+  // finish adds the SUM_BLOCKS block sums in index order -> same bits for any arrival order, any rank, any GPU count
+  __shared__ double sh[2][256];
+  __shared__ bool last;
   if (sctl && sctl[SCTL_STOP]) return;
+  const int len = (n + SUM_BLOCKS - 1) / SUM_BLOCKS, k0 = blockIdx.x * len, k1 = min(n, k0 + len);
   double t0 = 0.0, t1 = 0.0;
-  for (int k = threadIdx.x; k < n; k += 1024) { const double2 v = ((const double2 *)partials)[k]; t0 += v.x; t1 += v.y; }
+  for (int k = k0 + threadIdx.x; k < k1; k += 256) { const double2 v = ((const double2 *)partials)[k]; t0 += v.x; t1 += v.y; }
   sh[0][threadIdx.x] = t0; sh[1][threadIdx.x] = t1;
   __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
+  for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out2[0] = sh[0][0]; out2[1] = sh[1][0];
-    if (sctl) {   // viscosity_iteration_i += 1 ; RN = SQRT(sum_DN_sq / sum_N_sq) ; IF (RN < C%SSA_RN_tol) EXIT  (:503-524)
-      const double RN = sqrt(sh[0][0] / sh[1][0]);
-      sctl[SCTL_NOUTER] += 1ull;
-      sctl[SCTL_RN] = (unsigned long long)__double_as_longlong(RN);
-      if (RN < RN_tol) sctl[SCTL_STOP] = 1ull;
-    }
+    scratch[2 * blockIdx.x] = sh[0][0]; scratch[2 * blockIdx.x + 1] = sh[1][0];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == SUM_BLOCKS - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < SUM_BLOCKS; b++) { s0 += __ldcg(scratch + 2 * b); s1 += __ldcg(scratch + 2 * b + 1); }
+  *ticket = 0u;
+  out2[0] = s0; out2[1] = s1;
+  if (sctl) {   // viscosity_iteration_i += 1 ; RN = SQRT(sum_DN_sq / sum_N_sq) ; IF (RN < C%SSA_RN_tol) EXIT  (:503-524)
+    const double RN = sqrt(s0 / s1);
+    sctl[SCTL_NOUTER] += 1ull;
+    sctl[SCTL_RN] = (unsigned long long)__double_as_longlong(RN);
+    if (RN < RN_tol) sctl[SCTL_STOP] = 1ull;
   }
 }
 
@@ -1129,7 +1144,8 @@ static int enqueue_viscosity(ufm_handle *h, bool fuse, bool device_ctl)
     else k_ssa_viscosity<false, 1><<<h->num_sms * 8, 256, 0, h->stream>>>(a);
   }
   if (m.P > 1) { k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm); h->cnt.kernel_launches++; }
-  k_sum_partials<<<1, 1024, 0, h->stream>>>(m.m.n_slices, s.partials, s.scal, device_ctl ? s.ctrl + SCTL_BASE : nullptr, h->P.SSA_RN_tol);
+  k_sum_partials<<<SUM_BLOCKS, 256, 0, h->stream>>>(m.m.n_slices, s.partials, s.scal, device_ctl ? s.ctrl + SCTL_BASE : nullptr, h->P.SSA_RN_tol,
+                                                    s.red_scratch, (unsigned *)(s.ctrl + 26));
   h->cnt.kernel_launches += 2;
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
 }

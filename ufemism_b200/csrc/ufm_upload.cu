@@ -846,7 +846,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   ZE(na, s.mbits_Ac);
   ZE_OWN(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
-  ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE_OWN(MAIL_WORDS, s.mail);
+  ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(128, s.red_scratch); ZE_OWN(MAIL_WORDS, s.mail);
   UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
 
   // staging for permuted upload/download of one field
