@@ -12,10 +12,14 @@
 // evaluation order and the file is compiled with -fmad=false: with benchmark ice properties and no sliding the result is
 // bit-identical to the CPU restatement; pow (frictional heating), exp (Ki) and erf (Robin) differ from glibc by <= 2 ulp.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "ufm_internal.cuh"
 
+#ifndef UFM_HEAT_MINB_DEFAULT
+#define UFM_HEAT_MINB_DEFAULT 6
+#endif
 #define UFM_T0 273.16
 #define UFM_CC 8.7E-04
 
@@ -151,7 +155,8 @@ __device__ __forceinline__ double d_surface_temperature(const ThermoArgs &a, con
 }
 
 // ---- the heat equation, one implicit step per column (thermodynamics_module.f90:66-172) ----
-__global__ void __launch_bounds__(128) k_thermo_heat(ThermoArgs a, ThermoConst K)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_thermo_heat(ThermoArgs a, ThermoConst K)
 {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -361,7 +366,15 @@ int ufm_k_thermo_heat(ufm_handle *h, ufm_thermo_stats *st)
   int rc = thermo_setup(h, a, K);
   if (rc) return rc;
   UFM_CUDA(cudaMemsetAsync(a.status, 0, 2 * sizeof(unsigned long long), h->stream));
-  k_thermo_heat<<<grid_for((long long)a.n_slices * 32, 128), 128, 0, h->stream>>>(a, K);
+  {
+    static int minb = -1;   // resident CTAs per SM asked of ptxas (env UFM_HEAT_MINB): trades registers for warps
+    if (minb < 0) { const char *e = getenv("UFM_HEAT_MINB"); minb = e ? atoi(e) : UFM_HEAT_MINB_DEFAULT; }
+    const int g = grid_for((long long)a.n_slices * 32, 128);
+    if (minb >= 12) k_thermo_heat<12><<<g, 128, 0, h->stream>>>(a, K);
+    else if (minb >= 8) k_thermo_heat<8><<<g, 128, 0, h->stream>>>(a, K);
+    else if (minb >= 6) k_thermo_heat<6><<<g, 128, 0, h->stream>>>(a, K);
+    else k_thermo_heat<1><<<g, 128, 0, h->stream>>>(a, K);
+  }
   h->cnt.kernel_launches++;
   if ((rc = ufm_cuda_check(cudaGetLastError(), "k_thermo_heat"))) return rc;
   if ((rc = ufm_k_neumann3d_pair(h, s.Ti_new, s.Ti_new))) return rc;
