@@ -7,9 +7,12 @@
  * PARITY UNPINNED: the reference is Fortran 90 + MPI + NetCDF; this image has no Fortran
  * compiler, MPI or NetCDF, and the reference ships no tests, fixtures or golden vectors
  * (SURVEY.md section 0.2-0.3, 8c).  The oracle is therefore pinned only by (a) following the
- * Fortran statement by statement (file:line cited at every function) and (b) the two analytic
- * solutions hard-coded in the reference (Halfar, Bueler: src/reference_fields_module.f90:707-795),
- * checked in tests/test_oracle_analytic.py.
+ * Fortran statement by statement (file:line cited at every function), (b) model runs against the two
+ * analytic solutions hard-coded in the reference (Halfar, Bueler: src/reference_fields_module.f90:707-795,
+ * src/SMB_module.f90:240-283) and against two closed-form steady states of the heat equation (pure
+ * conduction; the Robin profile the reference codes in replace_Ti_with_robin_solution), and (c) for the one
+ * third-party routine on the path, LAPACK DGTSV, a bit-for-bit comparison with scipy's bundled LAPACK;
+ * all in tests/test_oracle.py.
  *
  * Layout = the reference's: column-major, 1-based indices stored in the integer arrays, padded
  * ELL rows (width nC_mem for connectivity, nC_mem+1 for neighbour functions).
