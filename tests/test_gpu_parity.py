@@ -823,3 +823,21 @@ def test_run_model_time_dependent_benchmark_smb(mesh_2k, benchmark):
     np.testing.assert_allclose(g.download("SMB_year"), o["SMB_year"], rtol=1e-13, atol=1e-13)   # hypot: <= 1 ulp of ~1e5 m, times S_b = 1e-5
     assert np.ptp(o["SMB_year"]) > 0.1
     assert rel_l2(g.download("Hi"), o["Hi"]) <= 1e-8
+
+
+def test_ssa_solve_after_cfl_with_3d_velocities(mesh_10k):
+    """Regression: the CFL minima, the RN reduction of the viscosity loop and the thermodynamics status share one control
+    block on the device.  With non-trivial U_3D / V_3D the third CFL key has arbitrary low bits; a solve_SSA issued after it
+    must still count its outer iterations exactly like the oracle."""
+    st, o, g = _thermo_pair(mesh_10k, "none")
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert (so.n_outer, so.n_inner_total) == (sg.n_outer, sg.n_inner_total)
+    o.update_ice_temperature(); g.update_ice_temperature()
+    do, dg = o.determine_timesteps(), g.determine_timesteps()
+    np.testing.assert_allclose(dg, do, rtol=1e-12)
+    assert do[2] < 900.0                      # the 3-D velocities do set a finite critical time step
+    o["Hi"][:] = o["Hi"] * 0.98; g.upload("Hi", o["Hi"])
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert so.n_outer >= 2 and (so.n_outer, so.n_inner_total) == (sg.n_outer, sg.n_inner_total)
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10

@@ -802,7 +802,7 @@ int ufm_k_thickness(ufm_handle *h, double dt)
 int ufm_k_cfl(ufm_handle *h, double out3[3])
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
-  unsigned long long *keys = s.ctrl + 24;
+  unsigned long long *keys = s.ctrl + CTRL_CFL_KEYS;
   UFM_CUDA(cudaMemsetAsync(keys, 0xFF, 3 * sizeof(unsigned long long), h->stream));
   k_cfl<<<h->num_sms * 4, 256, 0, h->stream>>>(m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_Aci, m.ac_Dx, m.ac_Dy, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
                                                m.aa_sqrtApi, s.U_3D, s.V_3D, keys);

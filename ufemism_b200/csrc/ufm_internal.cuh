@@ -159,6 +159,12 @@ struct CommDev {
   unsigned long long *mail[UFM_MAX_RANKS];
 };
 
+// words of DevState::ctrl (unsigned long long[128]) -- one table so that no two users overlap:
+//   [0..2] SOR max-residual slots   [8..10] SOR results   [12] SOR fused-Neumann counter   [16] mask_sheet sum
+//   [24..26] CFL minima keys   [28..29] thermodynamics status   [30] RN-reduction ticket   [32..95] SOR grid barrier   [96..103] SCTL_*
+#define CTRL_CFL_KEYS 24
+#define CTRL_THERMO_STATUS 28
+#define CTRL_RN_TICKET 30
 #define UFM_SOR_CHUNK_DEFAULT 1
 #define UFM_SOR_FUSE_BC_DEFAULT 1
 #define UFM_SOR_BAR_DEFAULT 1

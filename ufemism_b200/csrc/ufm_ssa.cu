@@ -1145,7 +1145,7 @@ static int enqueue_viscosity(ufm_handle *h, bool fuse, bool device_ctl)
   }
   if (m.P > 1) { k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm); h->cnt.kernel_launches++; }
   k_sum_partials<<<SUM_BLOCKS, 256, 0, h->stream>>>(m.m.n_slices, s.partials, s.scal, device_ctl ? s.ctrl + SCTL_BASE : nullptr, h->P.SSA_RN_tol,
-                                                    s.red_scratch, (unsigned *)(s.ctrl + 26));
+                                                    s.red_scratch, (unsigned *)(s.ctrl + CTRL_RN_TICKET));
   h->cnt.kernel_launches += 2;
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_viscosity");
 }

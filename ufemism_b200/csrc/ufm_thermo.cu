@@ -344,7 +344,7 @@ static int thermo_setup(ufm_handle *h, ThermoArgs &a, ThermoConst &K)
   a.Hi = s.Hi; a.dHs_dx = s.dHs_dx; a.dHs_dy = s.dHs_dy; a.dHi_dx = s.dHi_dx; a.dHi_dy = s.dHi_dy; a.dHb_dt = s.dHb_dt; a.dHs_dt = s.dHs_dt; a.dHi_dt = s.dHi_dt;
   a.U_SSA = s.U_SSA; a.V_SSA = s.V_SSA; a.tau_c = s.tau_c; a.GHF = s.GHF; a.T2m = s.T2m; a.SMB_year = s.SMB_year; a.aa2m = m.aa2m;
   a.U3 = s.U_3D; a.V3 = s.V_3D; a.W3 = s.W_3D; a.Ti = s.Ti; a.Ti_new = s.Ti_new; a.fric = s.fric_heat;
-  a.status = s.ctrl + 24;
+  a.status = s.ctrl + CTRL_THERMO_STATUS;
   return 0;
 }
 
