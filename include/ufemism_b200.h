@@ -185,6 +185,9 @@ int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_
 /* ---- state: explicit, field-granular, reference vertex order ---- */
 int ufm_state_upload(ufm_handle *h, int field, const void *host);
 int ufm_state_download(ufm_handle *h, int field, void *host);
+/* 1 when `field` can be copied with the resident mesh and parameters (Ti needs realistic flow factors or a thermodynamics mesh,
+ * W_3D / GHF / T2m a thermodynamics mesh), 0 when not, < 0 on a bad handle / field id */
+int ufm_field_resident(ufm_handle *h, int field);
 
 /* Page-lock a host array (e.g. one of the Fortran host's MPI shared-memory windows, src/parallel_module.f90:144-160) so that
  * ufm_state_upload / ufm_state_download DMA it directly instead of bouncing through a staging buffer.  Optional. */
@@ -274,6 +277,63 @@ int ufm_update_ice_temperature(ufm_handle *h, ufm_thermo_stats *st);
 /* pieces, for kernel-level parity tests: W_3D from the resident U_3D / V_3D; the heat-equation step from the resident 3-D velocities */
 int ufm_thermo_w3d(ufm_handle *h);
 int ufm_thermo_heat(ufm_handle *h, ufm_thermo_stats *st);
+
+/* ---- restart and help_fields files in the reference's own on-disk format.  NetCDF classic (CDF-1, or the
+ *      64-bit-offset variant when an offset exceeds 2 GiB), written and read without a NetCDF library; dimension / variable names,
+ *      order, types and attributes are those of create_restart_file_mesh / create_help_fields_file_mesh
+ *      (src/netcdf_module.f90:489-820), so the MATLAB tooling (MATLAB/ReadMeshFromFile.m) and a restart of the Fortran model
+ *      keep working.  All arrays are column-major with leading dimension = the mesh size given; NULL arrays are written as
+ *      the NetCDF fill value.  rc: -11 I/O error, -12 not a restart file / variable missing or mismatching (the reference STOPs
+ *      in inquire_*_var), -13 file exists (the reference aborts rather than overwrite, :508-512), -14 nZ mismatch (:3070),
+ *      -15 time_to_restart_from outside the file's range (:3154), -16 unknown help field (:1035). ---- */
+typedef struct ufm_nc_mesh {
+  int nV, nTri, nC_mem, nAc, nV_transect, nVAaAc, nTriAaAc;
+  const double *V;              /* (nV,2) */
+  const int    *Tri;            /* (nTri,3) */
+  const int    *nC, *C;         /* (nV), (nV,nC_mem) */
+  const int    *niTri, *iTri;   /* (nV), (nV,nC_mem) */
+  const int    *edge_index;     /* (nV) */
+  const double *Tricc;          /* (nTri,2) */
+  const int    *TriC;           /* (nTri,3) */
+  const int    *Tri_edge_index; /* (nTri) */
+  const double *VAc;            /* (nAc,2) */
+  const int    *Aci, *iAci;     /* (nAc,4), (nV,nC_mem) */
+  const double *VAaAc;          /* (nVAaAc,2) */
+  const int    *TriAaAc;        /* (nTriAaAc,3) */
+  const double *A, *R;          /* (nV) */
+  const int    *vi_transect;    /* (nV_transect,2) */
+  const double *w_transect;     /* (nV_transect,2) */
+} ufm_nc_mesh;
+typedef struct ufm_restart_frame {      /* what write_to_restart_file_mesh writes per time frame (src/netcdf_module.f90:195-205) */
+  const double *Hi, *Hb, *Hs, *U_SIA, *V_SIA, *U_SSA, *V_SSA;   /* (nV) */
+  const double *Ti;                      /* (nV,nZ) */
+  const double *FirnDepth;               /* (nV,12) */
+  const double *MeltPreviousYear;        /* (nV) */
+} ufm_restart_frame;
+typedef struct ufm_restart_frame_out {  /* what read_restart_file_init reads (src/netcdf_module.f90:3173-3180) */
+  double *Hi, *Hb, *Hs, *Ti, *U_SSA, *V_SSA, *MeltPreviousYear, *FirnDepth;
+} ufm_restart_frame_out;
+/* create_restart_file_mesh (src/netcdf_module.f90:489-633) */
+int ufm_restart_create(const char *filename, const ufm_nc_mesh *mesh, int nZ, const double *zeta);
+/* write_to_restart_file_mesh (:180-214): append one time frame from host arrays / from the device; returns the frame index (>= 1) */
+int ufm_restart_append(const char *filename, double time, const ufm_restart_frame *frame);
+int ufm_restart_write(ufm_handle *h, const char *filename, double time, const double *FirnDepth, const double *MeltPreviousYear);
+/* inquire_restart_file_mesh (:3012-3049), read_restart_file_mesh (:3104-3131): the primary mesh data */
+int ufm_restart_inquire_mesh(const char *filename, int *nV, int *nTri, int *nC_mem);
+int ufm_restart_read_mesh(const char *filename, double *V, int *nC, int *C, int *niTri, int *iTri, int *edge_index, int *Tri, double *Tricc,
+                          int *TriC, int *Tri_edge_index);
+/* inquire_restart_file_init (:3050-3103): rc 1 = zeta differs from the configuration (the reference only warns) */
+int ufm_restart_inquire_init(const char *filename, int nZ, const double *zeta, int *nt);
+/* read_restart_file_init (:3132-3185): the frame closest to time_to_restart_from, into host arrays / onto the device
+ * (ufm_restart_load uploads Hi, Hb, Ti, U_SSA, V_SSA and returns the frame index) */
+int ufm_restart_read_init(const char *filename, double time_to_restart_from, ufm_restart_frame_out *out, int *ti_out);
+int ufm_restart_load(ufm_handle *h, const char *filename, double time_to_restart_from, double *FirnDepth, double *MeltPreviousYear);
+/* create_help_fields_file_mesh (:634-820) with the fields of C%help_field_01..50; write_to_help_fields_file_mesh (:216-487):
+ * host_data[k] NULL = take the field from the device (h may be NULL when every field comes from the host) */
+int ufm_help_fields_create(const char *filename, const ufm_nc_mesh *mesh, int nZ, const double *zeta, int n_fields, const char *const *names);
+int ufm_help_fields_write(ufm_handle *h, const char *filename, double time, int n_fields, const char *const *names, const void *const *host_data);
+/* get_output_filenames (:66-174): first free <dir>restart_<NAM>_0000n.nc (kind 0) / <dir>help_fields_<NAM>_0000n.nc (kind 1); returns n */
+int ufm_output_filename(const char *output_dir, const char *region_name, int kind, char *out, int out_len);
 
 /* ---- instrumentation ---- */
 int ufm_counters_get(ufm_handle *h, ufm_counters *out);

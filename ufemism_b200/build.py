@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libufemism_b200.so")
 CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu", "ufm_thermo.cu"]
+# host-only sources of the same library (compiled by nvcc's host compiler): restart / help_fields files
+HOST_SOURCES = ["ufm_netcdf.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -27,12 +29,12 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES + HOST_SOURCES]
     deps = srcs + [os.path.join(CSRC, "ufm_internal.cuh"), os.path.join(HERE, "..", "include", "ufemism_b200.h")]
     if force or _stale(LIB, deps):
         objs = []
         for s in srcs:
-            o = s[:-3] + ".o"
+            o = os.path.splitext(s)[0] + ".o"
             if force or _stale(o, [s] + deps[len(srcs):]):
                 cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
                 subprocess.run(cmd, check=True)

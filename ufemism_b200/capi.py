@@ -121,7 +121,10 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get",
-            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat"]
+            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident",
+            "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
+            "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
+            "ufm_output_filename"]
 
 _lib = None
 
@@ -172,6 +175,19 @@ def load_library():
         L.ufm_update_ice_temperature.argtypes = [p, p]
         L.ufm_thermo_w3d.argtypes = [p]
         L.ufm_thermo_heat.argtypes = [p, p]
+        L.ufm_field_resident.argtypes = [p, i]
+        s = ctypes.c_char_p
+        L.ufm_restart_create.argtypes = [s, p, i, p]
+        L.ufm_restart_append.argtypes = [s, d, p]
+        L.ufm_restart_write.argtypes = [p, s, d, p, p]
+        L.ufm_restart_inquire_mesh.argtypes = [s, p, p, p]
+        L.ufm_restart_read_mesh.argtypes = [s] + [p] * 10
+        L.ufm_restart_inquire_init.argtypes = [s, i, p, p]
+        L.ufm_restart_read_init.argtypes = [s, d, p, p]
+        L.ufm_restart_load.argtypes = [p, s, d, p, p]
+        L.ufm_help_fields_create.argtypes = [s, p, i, p, i, p]
+        L.ufm_help_fields_write.argtypes = [p, s, d, i, p, p]
+        L.ufm_output_filename.argtypes = [s, s, i, p, i]
         _lib = L
     return _lib
 
@@ -435,3 +451,27 @@ class IceModelGPU:
 
     def reset_counters(self):
         self._ck(self.L.ufm_counters_reset(self.h))
+
+    # ---- restart / help_fields files (reference format; ufemism_b200/restart.py holds the host-only half) ----
+    def field_resident(self, name) -> bool:
+        return self._ck(self.L.ufm_field_resident(self.h, _REF_NAMES[name.upper()][0]), allow_warning=True) == 1
+
+    def write_restart(self, filename, time, FirnDepth=None, MeltPreviousYear=None) -> int:
+        """write_to_restart_file_mesh with the device's fields; returns the 1-based time-frame index."""
+        fd = None if FirnDepth is None else np.asfortranarray(FirnDepth, np.float64)
+        mp = None if MeltPreviousYear is None else np.ascontiguousarray(MeltPreviousYear, np.float64)
+        return self._ck(self.L.ufm_restart_write(self.h, os.fsencode(filename), float(time), None if fd is None else fd.ctypes.data,
+                                                 None if mp is None else mp.ctypes.data), allow_warning=True)
+
+    def load_restart(self, filename, time_to_restart_from) -> int:
+        """read_restart_file_init straight onto the device (Hi, Hb, U_SSA, V_SSA, Ti); returns the frame index read."""
+        return self._ck(self.L.ufm_restart_load(self.h, os.fsencode(filename), float(time_to_restart_from), None, None), allow_warning=True)
+
+    def write_help_fields(self, filename, time, names, host=None) -> int:
+        """write_to_help_fields_file_mesh: ``names`` as in C%help_field_01..50; ``host`` maps a name to a host array for the
+        fields the device does not hold."""
+        host = host or {}
+        keep = [np.asfortranarray(host[n]) if n in host else None for n in names]
+        arr = (ctypes.c_char_p * len(names))(*[n.encode() for n in names])
+        ptrs = (ctypes.c_void_p * len(names))(*[None if k is None else k.ctypes.data for k in keep])
+        return self._ck(self.L.ufm_help_fields_write(self.h, os.fsencode(filename), float(time), len(names), arr, ptrs), allow_warning=True)

@@ -377,6 +377,14 @@ int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int ord
 }
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }
+int ufm_field_resident(ufm_handle *h, int field)
+{
+  if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
+  if (field < 0 || field >= UFM_F_COUNT) return ufm_set_error(-2, "unknown field id %d", field);
+  if (field == UFM_F_A_FLOW_MEAN || field == UFM_F_A_FLOW_MEAN_AC) return 1;   // a scalar for the benchmarks, expanded on download
+  FieldRef r;
+  return field_ref(h, field, &r) == 0 ? 1 : 0;
+}
 
 #define NEED_MESH(h) do { if (!(h) || !(h)->has_mesh) return ufm_set_error(-2, "no mesh resident"); UFM_CUDA(cudaSetDevice((h)->device)); } while (0)
 

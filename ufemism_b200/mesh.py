@@ -133,6 +133,28 @@ class Mesh:
     def NyTri(self) -> np.ndarray:
         return self._tri_functions()[1]
 
+    @property
+    def TriC(self) -> np.ndarray:
+        """Triangle neighbours, ``TriC(ti,n)`` = the triangle across from the n-th vertex of ``ti`` (0 on the domain boundary),
+        ``src/data_types_module.f90:265``; written to the restart / help_fields files and read by ``MATLAB/ReadMeshFromFile.m``."""
+        if "TriC" not in self.extra:
+            t = self.Tri.astype(np.int64)
+            nT = len(t)
+            a = np.concatenate([t[:, 1], t[:, 2], t[:, 0]])          # edge opposite vertex n runs from vertex n+1 to vertex n+2
+            b = np.concatenate([t[:, 2], t[:, 0], t[:, 1]])
+            key = np.minimum(a, b) * (self.nV + 1) + np.maximum(a, b)
+            order = np.argsort(key, kind="stable")
+            ks = key[order]
+            same_next = np.zeros(len(ks), bool)
+            same_next[:-1] = ks[1:] == ks[:-1]
+            partner = np.full(len(ks), -1, np.int64)
+            i = np.nonzero(same_next)[0]
+            partner[order[i]] = order[i + 1]
+            partner[order[i + 1]] = order[i]
+            TriC = np.where(partner >= 0, partner % nT + 1, 0).astype(np.int32).reshape(3, nT).T
+            self.extra["TriC"] = np.asfortranarray(TriC)
+        return self.extra["TriC"]
+
     def save(self, path: str) -> None:
         d = {k: v for k, v in self.__dict__.items() if k != "extra"}
         np.savez_compressed(path, **d)
