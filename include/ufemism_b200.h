@@ -165,6 +165,33 @@ int ufm_abi_version(void);
 int ufm_mesh_upload(ufm_handle *h, const ufm_mesh_desc *mesh);
 int ufm_mesh_free(ufm_handle *h);
 
+/* ---- device re-upload from PRIMARY mesh data: what a mesh update (src/mesh_update_module.f90) or
+ *      read_mesh_from_restart_file (src/restart_module.f90:31-116) leaves before the reference rebuilds the secondary data on the CPU
+ *      (:88-103).  The library derives Voronoi areas, connection widths, the Ac and AaAc meshes and the five-colouring on the host
+ *      (same results as find_Voronoi_cell_areas / find_connection_widths / make_Ac_mesh / make_combined_AaAc_mesh /
+ *      calculate_five_colouring_AaAc) and all neighbour functions on the device, then proceeds as ufm_mesh_upload.
+ *      ufm_mesh_secondary_get lends the derived host arrays (valid until the next upload / ufm_mesh_free / ufm_destroy; the
+ *      neighbour-function members of *out are NULL, ldAc > nAc) so that the host need not recompute the ones it reads. ---- */
+typedef struct ufm_mesh_primary {
+  int nV, nTri, nC_mem;
+  int ldV, ldTri;                   /* leading dimensions of the (nV,..) / (nTri,..) arrays; 0 = nV / nTri */
+  double xmin, xmax, ymin, ymax;    /* mesh%xmin .. mesh%ymax: the model domain */
+  const double *V;                  /* (ldV,2) */
+  const int    *nC, *C;             /* (nV), (ldV,nC_mem) */
+  const int    *niTri, *iTri;       /* (nV), (ldV,nC_mem) */
+  const int    *edge_index;         /* (nV) */
+  const int    *Tri;                /* (ldTri,3), counter-clockwise */
+  int thermo;                       /* != 0: also derive R, NxTri, NyTri so that ufm_update_ice_temperature is available */
+} ufm_mesh_primary;
+int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *mesh);
+/* the host-only half on its own (no device needed): derive, look, free; *derived is an opaque object */
+int ufm_mesh_derive_secondary(const ufm_mesh_primary *mesh, void **derived);
+int ufm_mesh_derived_get(const void *derived, ufm_mesh_desc *out, const double **Tricc, const int **Tri_edge_index, const double **VAc,
+                         const double **VAaAc, const int **colour);
+void ufm_mesh_derived_free(void *derived);
+int ufm_mesh_secondary_get(ufm_handle *h, ufm_mesh_desc *out, const double **Tricc, const int **Tri_edge_index, const double **VAc,
+                           const double **VAaAc, const int **colour);
+
 /* ---- vertex-partitioned runs over the GPUs of one NVSwitch domain (replaces the index-range split of
  *      partition_list, src/mesh_help_functions_module.f90:1475-1496, and the MPI_BARRIER / MPI_ALLREDUCE of the SOR loop,
  *      src/ice_dynamics_module.f90:662,673).  One process per GPU.  Every rank uploads the same mesh and holds the whole

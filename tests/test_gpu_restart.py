@@ -1,0 +1,123 @@
+"""GPU half of rows N3 / N4: device upload from primary mesh data, restart and help_fields files written from and
+loaded onto the device.  Bit-exact throughout: files carry the fp64 fields unchanged, and a mesh whose secondary data were
+derived inside the library must behave exactly like one whose secondary data came from the host."""
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from tests.util import assert_bits_equal, make_gpu
+from ufemism_b200 import restart as R
+from ufemism_b200 import scenarios as S
+
+pytestmark = pytest.mark.gpu
+
+ZETA = [0.00, 0.10, 0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.90, 0.925, 0.95, 0.975, 0.99, 1.00]
+FIELDS = ("Hi", "Hs", "U_SIA", "V_SIA", "D_SIA", "U_SSA", "V_SSA", "dHs_dx", "dHs_dy", "mask", "Hi_Ac", "dHs_dp_Ac", "Up_SIA_Ac", "Up_SSA_Ac",
+          "U_SSA_AaAc", "tau_c_AaAc", "eta_AaAc")
+
+
+def test_upload_from_primary_mesh_data_is_bit_identical(mesh_2k):
+    """ufm_mesh_upload_primary (areas, Cw, Ac / AaAc meshes, colouring derived on the host inside the library, every neighbour
+    function on the device) vs ufm_mesh_upload with all arrays built by the host: the same hybrid SIA/SSA run, bit for bit."""
+    from tests.test_gpu_parity import scenario
+
+    st = scenario(mesh_2k, "mismip")
+    a, b = make_gpu(mesh_2k, st), make_gpu(mesh_2k, st, primary_only=True)
+    ra, rb = a.region(0.0), b.region(0.0)
+    a.run_model(ra, 2.0)
+    b.run_model(rb, 2.0)
+    assert (ra.n_steps, ra.n_sor_total, ra.n_outer_total) == (rb.n_steps, rb.n_sor_total, rb.n_outer_total) and ra.n_sor_total > 0
+    for f in FIELDS:
+        assert_bits_equal(b.download(f), a.download(f), f)
+    sec = b.secondary()
+    for n in ("A", "Cw", "Aci", "iAci", "nCAaAc", "CAaAc", "colour_vi", "colour_nV", "edge_index_Ac"):
+        assert np.array_equal(sec[n], np.asarray(getattr(mesh_2k, n))), n
+    # a plain upload afterwards drops the derived arrays (they described the replaced mesh)
+    from ufemism_b200.capi import UfmError
+    b.primary_only = False
+    b.upload_mesh(mesh_2k)
+    with pytest.raises(UfmError):
+        b.secondary()
+
+
+def test_primary_upload_with_thermodynamics(mesh_2k):
+    """thermo = 1: R, NxTri, NyTri derived inside the library; update_ice_temperature bit-identical to the host-built mesh."""
+    from tests.test_gpu_parity import THERMO_IN
+    from ufemism_b200.capi import IceModelGPU
+
+    st = S.state_thermo_dome(mesh_2k, benchmark="none")
+    g, g2 = IceModelGPU(mesh_2k, benchmark="none", thermo=True), IceModelGPU(mesh_2k, benchmark="none", thermo=True, primary_only=True)
+    for f in THERMO_IN:
+        g.upload(f, st[f]); g2.upload(f, st[f])
+    for m in (g, g2):
+        m.update_general_ice_model_data(0.0); m.solve_SIA(); m.solve_SSA()
+        m.update_ice_temperature()
+    assert np.abs(g.download("W_3D")).max() > 0.0 and np.ptp(g.download("Ti")) > 1.0
+    for f in ("Ti", "W_3D", "U_3D", "frictional_heating"):
+        assert_bits_equal(g2.download(f), g.download(f), f)
+
+
+def test_restart_and_help_fields_written_from_the_device(mesh_2k, tmp_path):
+    from tests.test_gpu_parity import scenario
+
+    st = scenario(mesh_2k, "mismip")
+    g = make_gpu(mesh_2k, st)
+    fn = R.output_filename(str(tmp_path) + "/", "ANT")
+    hf = R.output_filename(str(tmp_path) + "/", "ANT", kind="help_fields")
+    names = ["Hi", "Hb", "Hs", "SL", "dHs_dx", "dHs_dy", "U_SIA", "V_SIA", "U_SSA", "V_SSA", "D_SIA", "A_flow_mean", "SMB_year", "BMB", "mask",
+             "mask_land", "mask_ocean", "mask_ice", "mask_sheet", "mask_shelf", "mask_gl", "mask_cf", "mask_margin", "mask_coast", "mask_lake",
+             "phi_fric", "tau_yield", "U_3D", "V_3D", "resolution", "none", "lat"]
+    R.create_restart(fn, mesh_2k, ZETA, {"TriC": mesh_2k.TriC})
+    R.create_help_fields(hf, mesh_2k, ZETA, names, {"TriC": mesh_2k.TriC})
+    assert not g.field_resident("Ti") and g.field_resident("Hi") and g.field_resident("A_flow_mean")
+    r = g.region(0.0)
+    snaps = []
+    lat = np.linspace(-80.0, -60.0, mesh_2k.nV)
+    for k, t_end in enumerate([1.0, 2.0, 3.0]):
+        g.run_model(r, t_end)
+        melt = np.full(mesh_2k.nV, 0.25 * k)
+        assert g.write_restart(fn, r.time, MeltPreviousYear=melt) == k + 1
+        assert g.write_help_fields(hf, r.time, names, host={"lat": lat}) == k + 1
+        snaps.append({n: g.download(n) for n in ("Hi", "Hb", "Hs", "U_SIA", "V_SIA", "U_SSA", "V_SSA", "SL", "dHs_dx", "D_SIA", "SMB_year", "mask",
+                                                 "mask_gl", "mask_shelf", "U_3D", "tau_c_AaAc", "phi_fric_AaAc", "A_flow_mean")} | {"time": r.time, "melt": melt})
+    f = netcdf_file(fn, "r", mmap=False)
+    h = netcdf_file(hf, "r", mmap=False)
+    assert np.array_equal(f.variables["time"][:], [s["time"] for s in snaps]) and np.array_equal(h.variables["time"][:], f.variables["time"][:])
+    for k, s in enumerate(snaps):
+        for n in ("Hi", "Hb", "Hs", "U_SIA", "V_SIA", "U_SSA", "V_SSA"):
+            assert_bits_equal(f.variables[n][k], s[n], f"restart {n}[{k}]")
+        assert_bits_equal(f.variables["MeltPreviousYear"][k], s["melt"], "MeltPreviousYear")
+        assert (f.variables["Ti"][k] == np.float64(9.9692099683868690e+36)).all(), "Ti is not resident for this benchmark: fill value"
+        for n in ("Hi", "Hs", "SL", "dHs_dx", "D_SIA", "SMB_year", "mask", "mask_gl", "mask_shelf", "U_SSA", "A_flow_mean"):
+            assert_bits_equal(h.variables[n][k], s[n], f"help_fields {n}[{k}]")
+        assert_bits_equal(h.variables["U_3D"][k], s["U_3D"].T, "U_3D")
+        assert_bits_equal(h.variables["tau_yield"][k], s["tau_c_AaAc"][: mesh_2k.nV], "tau_yield")
+        assert_bits_equal(h.variables["phi_fric"][k], s["phi_fric_AaAc"][: mesh_2k.nV], "phi_fric")
+    assert_bits_equal(h.variables["lat"][:], lat, "lat")
+    assert snaps[2]["U_SSA"].any() and snaps[2]["mask_shelf"].any() and not np.array_equal(snaps[0]["Hi"], snaps[2]["Hi"])
+    f.close(); h.close()
+
+    # restart: mesh from the file's primary data, state from the frame nearest to the requested time
+    prim = R.read_restart_mesh(fn)
+    prim.update(xmin=mesh_2k.xmin, xmax=mesh_2k.xmax, ymin=mesh_2k.ymin, ymax=mesh_2k.ymax)
+
+    class PrimMesh:                                                   # what IceModelGPU needs of a mesh when it uploads primary data
+        nV, nTri, nC_mem, nAc, nVAaAc = mesh_2k.nV, mesh_2k.nTri, mesh_2k.nC_mem, mesh_2k.nAc, mesh_2k.nVAaAc
+        xmin, xmax, ymin, ymax = mesh_2k.xmin, mesh_2k.xmax, mesh_2k.ymin, mesh_2k.ymax
+    for n, a in prim.items():
+        setattr(PrimMesh, n, a)
+    from ufemism_b200.capi import IceModelGPU, UfmError
+    g2 = IceModelGPU(PrimMesh, benchmark=st["benchmark"], primary_only=True)
+    with pytest.raises(UfmError) as e:
+        g2.load_restart(fn, snaps[2]["time"] + 1.0)
+    assert e.value.rc == -15
+    assert g2.load_restart(fn, 0.5 * (snaps[1]["time"] + snaps[2]["time"]) + 1e-6) == 3
+    for n in ("Hi", "Hb", "U_SSA", "V_SSA"):
+        assert_bits_equal(g2.download(n), snaps[2][n], f"loaded {n}")
+    # what the reference recomputes after a restart is then identical to the original run's
+    for n in ("SL", "SMB_year", "BMB"):
+        g2.upload(n, st[n])
+    g2.update_general_ice_model_data(r.time); g.update_general_ice_model_data(r.time)
+    g2.solve_SIA(); g.solve_SIA()
+    for n in ("Hs", "dHs_dx", "mask", "mask_gl", "Hi_Ac", "U_SIA", "V_SIA", "D_SIA"):
+        assert_bits_equal(g2.download(n), g.download(n), f"after restart {n}")

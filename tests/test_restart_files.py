@@ -281,3 +281,70 @@ def test_every_help_field_name_of_the_reference_is_known(mesh, tmp_path):
     f.close()
     with pytest.raises(UfmError):                                     # the same name twice: NetCDF "name in use"
         R.create_help_fields(str(tmp_path / "dup.nc"), mesh, ZETA, ["Hi", "Hi"])
+
+
+# ---- row N3: secondary mesh data derived inside the library from the primary data a restart file (or a mesh update) holds ----
+def test_secondary_mesh_data_derived_from_a_restart_file(mesh, tmp_path):
+    """restart file -> ufm_restart_read_mesh -> ufm_mesh_derive_secondary reproduces every array of the mesh the file was written
+    from (the host-only half of ufm_mesh_upload_primary; the reference does the same with read_mesh_from_restart_file,
+    src/restart_module.f90:31-116)."""
+    from ufemism_b200 import capi
+
+    fn = str(tmp_path / "restart_ANT_00001.nc")
+    R.create_restart(fn, mesh, ZETA, {"TriC": mesh.TriC})
+    prim = R.read_restart_mesh(fn)
+    prim.update(xmin=mesh.xmin, xmax=mesh.xmax, ymin=mesh.ymin, ymax=mesh.ymax)
+    d = capi.derive_secondary(prim, thermo=True)
+    assert (d["nV"], d["nAc"], d["nVAaAc"]) == (mesh.nV, mesh.nAc, mesh.nVAaAc)
+    assert d["ldAc"] == mesh.nV + mesh.nTri and mesh.nAc == mesh.nV + mesh.nTri - 1, "Euler: a triangulated disc has nV + nTri - 1 edges"
+    for n in ("A", "Cw", "Aci", "iAci", "edge_index_Ac", "nCAaAc", "CAaAc", "colour", "colour_vi", "colour_nV", "Tricc", "Tri_edge_index", "VAc",
+              "VAaAc", "R", "NxTri", "NyTri"):
+        assert np.array_equal(d[n], np.asarray(getattr(mesh, n))), n
+    assert d["nf_pointers_null"], "neighbour functions are left to the device"
+    # leading dimensions larger than the mesh (the reference's nV_mem-sized arrays before crop_mesh_primary)
+    pad = 7
+    big = dict(prim)
+    for n in ("V", "C", "iTri"):
+        a = np.zeros((mesh.nV + pad, prim[n].shape[1]), prim[n].dtype, order="F")
+        a[: mesh.nV] = prim[n]
+        big[n] = a
+    p, keep = capi.mesh_primary(big)
+    p.nV = mesh.nV                                                   # mesh_primary took nV from the padded array
+    import ctypes
+    L = capi.load_library()
+    obj = ctypes.c_void_p()
+    assert L.ufm_mesh_derive_secondary(ctypes.byref(p), ctypes.byref(obj)) == 0, L.ufm_last_error()
+    d2 = capi._derived_to_dict(L, L.ufm_mesh_derived_get, obj, mesh.nV, mesh.nTri, mesh.nC_mem)
+    L.ufm_mesh_derived_free(obj)
+    for n in ("A", "Cw", "Aci", "CAaAc", "colour_vi"):
+        assert np.array_equal(d2[n], d[n]), n
+
+
+def test_derive_secondary_rejects_broken_primary_data(mesh):
+    from ufemism_b200 import capi
+
+    base = {n: np.array(getattr(mesh, n), order="F") for n in ("V", "nC", "C", "niTri", "iTri", "edge_index", "Tri")}
+    base.update(xmin=mesh.xmin, xmax=mesh.xmax, ymin=mesh.ymin, ymax=mesh.ymax)
+
+    def broken(**kw):
+        d = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in base.items()}
+        for k, f in kw.items():
+            d[k] = f(d[k])
+        return d
+
+    def poke(i, j, val):
+        def f(a):
+            if a.ndim == 1:
+                a[i] = val
+            else:
+                a[i, j] = val
+            return a
+        return f
+
+    cases = [broken(C=poke(10, 0, mesh.nV + 5)), broken(C=poke(10, 0, 0)), broken(nC=poke(3, None, mesh.nC_mem + 1)), broken(nC=poke(3, None, 1)),
+             broken(iTri=poke(7, 0, mesh.nTri + 1)), broken(Tri=poke(2, 1, 0)), broken(edge_index=poke(5, None, 9)), broken(xmax=lambda x: mesh.xmin),
+             broken(Tri=poke(2, 1, int(mesh.Tri[2, 0])))]           # the last one: a degenerate triangle -> an edge without its triangle
+    for k, d in enumerate(cases):
+        with pytest.raises(UfmError) as e:
+            capi.derive_secondary(d)
+        assert e.value.rc == -2, (k, str(e.value))

@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libufemism_b200.so")
 CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu", "ufm_thermo.cu"]
-# host-only sources of the same library (compiled by nvcc's host compiler): restart / help_fields files
-HOST_SOURCES = ["ufm_netcdf.cpp"]
+# host-only sources of the same library (compiled by nvcc's host compiler): restart / help_fields files, secondary mesh data
+HOST_SOURCES = ["ufm_netcdf.cpp", "ufm_mesh_primary.cpp", "mesh_host.c"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

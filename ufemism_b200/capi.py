@@ -53,6 +53,12 @@ class MeshDesc(ctypes.Structure):
                 [("nTri", ctypes.c_int), ("ldTri", ctypes.c_int)] + [(n, ctypes.c_void_p) for n in _THERMO_PTRS])
 
 
+class MeshPrimary(ctypes.Structure):
+    """ufm_mesh_primary"""
+    _fields_ = ([(n, ctypes.c_int) for n in ("nV", "nTri", "nC_mem", "ldV", "ldTri")] + [(n, ctypes.c_double) for n in ("xmin", "xmax", "ymin", "ymax")] +
+                [(n, ctypes.c_void_p) for n in ("V", "nC", "C", "niTri", "iTri", "edge_index", "Tri")] + [("thermo", ctypes.c_int)])
+
+
 class ThermoStats(ctypes.Structure):
     _fields_ = [("n_unstable", ctypes.c_int), ("rc", ctypes.c_int)]
 
@@ -124,7 +130,8 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident",
             "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
             "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
-            "ufm_output_filename"]
+            "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
+            "ufm_mesh_secondary_get"]
 
 _lib = None
 
@@ -188,6 +195,12 @@ def load_library():
         L.ufm_help_fields_create.argtypes = [s, p, i, p, i, p]
         L.ufm_help_fields_write.argtypes = [p, s, d, i, p, p]
         L.ufm_output_filename.argtypes = [s, s, i, p, i]
+        L.ufm_mesh_upload_primary.argtypes = [p, p]
+        L.ufm_mesh_derive_secondary.argtypes = [p, p]
+        L.ufm_mesh_derived_get.argtypes = [p] * 7
+        L.ufm_mesh_derived_free.argtypes = [p]
+        L.ufm_mesh_derived_free.restype = None
+        L.ufm_mesh_secondary_get.argtypes = [p] * 7
         _lib = L
     return _lib
 
@@ -234,6 +247,64 @@ def mesh_desc(mesh, thermo=False, derive_nf=False):
     return d, keep
 
 
+def mesh_primary(mesh, thermo=False):
+    """ufm_mesh_primary over the primary arrays of a Mesh (or of a dict as ``restart.read_restart_mesh`` returns, plus the domain
+    bounds); returns (struct, keepalive)."""
+    get = (lambda n: mesh[n]) if isinstance(mesh, dict) else (lambda n: getattr(mesh, n))
+    V = np.asfortranarray(get("V"), np.float64)
+    C = np.asfortranarray(get("C"), np.int32)
+    Tri = np.asfortranarray(get("Tri"), np.int32)
+    keep = [V, C, Tri, np.ascontiguousarray(get("nC"), np.int32), np.ascontiguousarray(get("niTri"), np.int32),
+            np.asfortranarray(get("iTri"), np.int32), np.ascontiguousarray(get("edge_index"), np.int32)]
+    p = MeshPrimary(nV=V.shape[0], nTri=Tri.shape[0], nC_mem=C.shape[1], ldV=V.shape[0], ldTri=Tri.shape[0],
+                    xmin=float(get("xmin")), xmax=float(get("xmax")), ymin=float(get("ymin")), ymax=float(get("ymax")),
+                    V=V.ctypes.data, C=C.ctypes.data, Tri=Tri.ctypes.data, nC=keep[3].ctypes.data, niTri=keep[4].ctypes.data,
+                    iTri=keep[5].ctypes.data, edge_index=keep[6].ctypes.data, thermo=int(bool(thermo)))
+    return p, keep
+
+
+def _derived_to_dict(L, getter, obj, nV, nTri, W):
+    """Copy the arrays behind ufm_mesh_derived_get / ufm_mesh_secondary_get into numpy (Fortran order, compacted)."""
+    d = MeshDesc()
+    ptrs = [ctypes.c_void_p() for _ in range(5)]
+    rc = getter(obj, ctypes.byref(d), *[ctypes.byref(q) for q in ptrs])
+    if rc:
+        raise UfmError(rc, L.ufm_last_error().decode())
+    nAc, ldAc, M = d.nAc, d.ldAc, d.nV + d.nAc
+
+    def arr(ptr, ct, rows, cols=None, ld=None):
+        ld = rows if ld is None else ld
+        n = ld * (cols or 1)
+        a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).copy()
+        return a if cols is None else np.asfortranarray(a.reshape(cols, ld).T[:rows])
+
+    I, D = ctypes.c_int, ctypes.c_double
+    out = {"nV": d.nV, "nAc": nAc, "nC_mem": d.nC_mem, "nVAaAc": M, "ldAc": ldAc,
+           "A": arr(d.A, D, nV), "Cw": arr(d.Cw, D, nV, W), "Aci": arr(d.Aci, I, nAc, 4, ldAc), "iAci": arr(d.iAci, I, nV, W),
+           "edge_index_Ac": arr(d.edge_index_Ac, I, ldAc)[:nAc], "nCAaAc": arr(d.nCAaAc, I, M), "CAaAc": arr(d.CAaAc, I, M, W),
+           "colour_vi": arr(d.colour_vi, I, M, 5), "colour_nV": arr(d.colour_nV, I, 5),
+           "Tricc": arr(ptrs[0], D, nTri, 2), "Tri_edge_index": arr(ptrs[1], I, nTri), "VAc": arr(ptrs[2], D, nAc, 2, ldAc),
+           "VAaAc": arr(ptrs[3], D, M, 2), "colour": arr(ptrs[4], I, M),
+           "nf_pointers_null": all(not getattr(d, n) for n in _NF_AAAC)}
+    if d.R:
+        out.update(R=arr(d.R, D, nV), NxTri=arr(d.NxTri, D, nTri, 3), NyTri=arr(d.NyTri, D, nTri, 3))
+    return out
+
+
+def derive_secondary(mesh, thermo=False):
+    """Host-only: what ufm_mesh_upload_primary derives from the primary mesh data, as a dict of numpy arrays."""
+    L = load_library()
+    p, keep = mesh_primary(mesh, thermo)
+    obj = ctypes.c_void_p()
+    rc = L.ufm_mesh_derive_secondary(ctypes.byref(p), ctypes.byref(obj))
+    if rc:
+        raise UfmError(rc, L.ufm_last_error().decode())
+    try:
+        return _derived_to_dict(L, L.ufm_mesh_derived_get, obj, p.nV, p.nTri, p.nC_mem)
+    finally:
+        L.ufm_mesh_derived_free(obj)
+
+
 def partition_owners(mesh, nranks):
     """Owner rank of every AaAc vertex (reference order) in an nranks-way vertex partition (host-only call)."""
     L = load_library()
@@ -269,11 +340,12 @@ def max_over_ranks(dist, value: float, device=None) -> float:
 class IceModelGPU:
     """One model region resident on one B200."""
 
-    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, thermo=False, derive_nf=False, **params):
+    def __init__(self, mesh, benchmark="Halfar", device=0, rank=0, nranks=1, thermo=False, derive_nf=False, primary_only=False, **params):
         self.L = load_library()
         self.mesh = mesh
         self.thermo = bool(thermo)
         self.derive_nf = bool(derive_nf)
+        self.primary_only = bool(primary_only)   # upload with ufm_mesh_upload_primary: the library derives all secondary mesh data
         self.P = default_params(benchmark, **params)
         self.h = ctypes.c_void_p()
         self.rank, self.nranks = int(rank), int(nranks)
@@ -304,9 +376,18 @@ class IceModelGPU:
         self._ck(self.L.ufm_set_params(self.h, ctypes.byref(self.P)))
 
     def upload_mesh(self, mesh):
-        d, keep = mesh_desc(mesh, thermo=self.thermo, derive_nf=self.derive_nf)
-        self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
+        if self.primary_only:
+            p, keep = mesh_primary(mesh, thermo=self.thermo)
+            self._ck(self.L.ufm_mesh_upload_primary(self.h, ctypes.byref(p)))
+        else:
+            d, keep = mesh_desc(mesh, thermo=self.thermo, derive_nf=self.derive_nf)
+            self._ck(self.L.ufm_mesh_upload(self.h, ctypes.byref(d)))
         self.mesh = mesh
+
+    def secondary(self):
+        """The host arrays ufm_mesh_upload_primary derived for the resident mesh (copies)."""
+        m = self.mesh
+        return _derived_to_dict(self.L, self.L.ufm_mesh_secondary_get, self.h, m.nV, m.nTri, m.nC_mem)
 
     COMM_BLOB_BYTES = 256
 

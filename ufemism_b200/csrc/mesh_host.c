@@ -156,6 +156,7 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
     int nt = niTri[vi - 1], ei = edge_index[vi - 1];
     double vor[40][2];
     int nv = 0;
+    if (nt + 3 > 40) return -3;
     for (int k = 1; k <= nt; k++) {
       int t = I2(iTri, vi, k, nV);
       double cx = clampd(I2(Tricc, t, 1, nTri), xmin, xmax), cy = clampd(I2(Tricc, t, 2, nTri), ymin, ymax);
@@ -417,8 +418,9 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
         for (int k = 0; k < 4; k++) { Nx[k] = -Nxl[k] / Nzl; Ny[k] = -Nyl[k] / Nzl; }
       }
       double Ux = VX(vj) - VX(vi), Uy = VY(vj) - VY(vi), U = sqrt(Ux * Ux + Uy * Uy);
-      Np_Ac[nAc - 1] = 1.0 / U;
-      for (int k = 0; k < 4; k++) {
+      /* the four operator arrays are optional: ufm_mesh_upload_primary lets the device derive them (k_derive_nf_Ac) */
+      if (Np_Ac) Np_Ac[nAc - 1] = 1.0 / U;
+      for (int k = 0; k < 4 && Nx_Ac && Ny_Ac && No_Ac; k++) {
         I2(Nx_Ac, nAc, k + 1, nAc_max) = Nx[k];
         I2(Ny_Ac, nAc, k + 1, nAc_max) = Ny[k];
         I2(No_Ac, nAc, k + 1, nAc_max) = (Ny[k] * Ux - Nx[k] * Uy) / U;

@@ -89,6 +89,7 @@ int ufm_destroy(ufm_handle *h)
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   ufm_mesh_free_impl(h);
+  ufm_secondary_free(h);
   ufm_arena_release(h);
   for (int k = 0; k < h->n_pinned; k++) cudaHostUnregister(h->pinned_base[k]);
   for (auto &q : h->stash) if (q.d) { cudaFree(q.d); cudaFree(q.ddx); cudaFree(q.ddy); }
@@ -135,12 +136,14 @@ int ufm_mesh_upload(ufm_handle *h, const ufm_mesh_desc *mesh)
   UFM_CUDA(cudaStreamSynchronize(h->stream));
   int rc = ufm_mesh_upload_impl(h, mesh);
   if (rc) ufm_mesh_free_impl(h);
+  ufm_secondary_free(h);   // host arrays derived by an earlier ufm_mesh_upload_primary describe the mesh that was just replaced
   return rc;
 }
 int ufm_mesh_free(ufm_handle *h)
 {
   if (!h) return ufm_set_error(-2, "NULL handle");
   UFM_CUDA(cudaStreamSynchronize(h->stream));
+  ufm_secondary_free(h);
   return ufm_mesh_free_impl(h);
 }
 

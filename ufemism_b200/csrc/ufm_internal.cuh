@@ -202,6 +202,7 @@ struct ufm_handle {
   Chunk arena[64] = {};
   int arena_n = 0, arena_cur = 0;
   size_t arena_used = 0, arena_total = 0;
+  void *secondary = nullptr;     // ufm_secondary: host arrays derived by ufm_mesh_upload_primary (ufm_mesh_primary.cpp)
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;
@@ -210,6 +211,7 @@ struct ufm_handle {
 
 int ufm_arena_alloc(ufm_handle *h, size_t bytes, void **out);
 void ufm_arena_release(ufm_handle *h);
+void ufm_secondary_free(ufm_handle *h);
 int ufm_set_error(int rc, const char *fmt, ...);
 int ufm_cuda_check(cudaError_t e, const char *what);
 #define UFM_CUDA(x) do { int rc__ = ufm_cuda_check((x), #x); if (rc__) return rc__; } while (0)

@@ -1,0 +1,198 @@
+// ufm_mesh_primary.cpp -- device re-upload from PRIMARY mesh data (second half).
+//
+// After a mesh update (src/mesh_update_module.f90) or a restart (read_mesh_from_restart_file, src/restart_module.f90:31-116) the
+// reference holds only the primary mesh data -- V, nC, C, niTri, iTri, edge_index, Tri -- and rebuilds everything else on the
+// CPU (src/restart_module.f90:88-103, src/mesh_creation_module.f90:1724-1737): find_Voronoi_cell_areas, find_connection_widths,
+// make_Ac_mesh, get_neighbour_functions, determine_mesh_resolution, make_combined_AaAc_mesh, calculate_five_colouring_AaAc.
+// ufm_mesh_upload_primary takes the primary data as they are and does that work inside the library:
+//   * Voronoi areas / connection widths, the staggered Ac mesh, the combined AaAc connectivity and the five-colouring on the
+//     host (csrc/mesh_host.c; the colouring is sequential by construction and its order is part of the parity contract:
+//     linked-list queues instead of the reference's array shifts, same result, linear time);
+//   * every neighbour function (Aa, Ac, AaAc: 5 x 17 doubles per AaAc vertex, the bulk of the data) on the device
+//     (k_derive_nf_Aa / _Ac / _AaAc in ufm_upload.cu), never materialised on the host;
+// and keeps the derived host arrays so that the Fortran host can copy the few it still reads itself (A for ice volumes, Aci /
+// iAci for output, the colour lists) with ufm_mesh_secondary_get instead of recomputing them.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ufm_internal.cuh"
+
+extern "C" {
+int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *Tri, const int *nC, const int *C, const int *niTri, const int *iTri,
+                      const int *edge_index, double xmin, double xmax, double ymin, double ymax, double *Tricc, int *Tri_edge_index, double *A, double *Cw);
+int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V, const int *Tri, const int *nC, const int *C, const int *niTri,
+                     const int *iTri, const int *edge_index, int *iAci, int *Aci, double *VAc, double *Nx_Ac, double *Ny_Ac, double *Np_Ac,
+                     double *No_Ac, int *edge_index_Ac);
+int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, const double *VAc, const int *nC, const int *C, const int *iAci,
+                       const int *Aci, const int *edge_index_Ac, double *VAaAc, int *nCAaAc, int *CAaAc);
+int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, int *colour, int *colour_vi, int *colour_nV);
+}
+
+struct ufm_secondary {
+  int nV = 0, nTri = 0, nAc = 0, ldAc = 0, W = 0;
+  std::vector<double> V, A, Cw, Tricc, VAc, VAaAc, R, NxTri, NyTri;
+  std::vector<int> nC, C, niTri, iTri, edge_index, Tri, Tri_edge_index, iAci, Aci, edge_index_Ac, nCAaAc, CAaAc, colour, colour_vi, colour_nV;
+  ufm_mesh_desc desc;
+};
+
+void ufm_secondary_free(ufm_handle *h)
+{
+  delete (ufm_secondary *)h->secondary;
+  h->secondary = nullptr;
+}
+
+namespace {
+// copy an (n, cols) column-major array with leading dimension ld into a dense one
+template <class T>
+void compact(std::vector<T> &dst, const T *src, int n, int cols, int ld)
+{
+  dst.resize((size_t)n * cols);
+  for (int c = 0; c < cols; c++) memcpy(dst.data() + (size_t)c * n, src + (size_t)c * ld, sizeof(T) * (size_t)n);
+}
+}  // namespace
+
+// host-only half: everything ufm_mesh_upload_primary derives before it touches the device
+extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **derived)
+{
+  if (!derived) return ufm_set_error(-2, "ufm_mesh_derive_secondary: NULL output");
+  *derived = nullptr;
+  if (!p || !p->V || !p->nC || !p->C || !p->niTri || !p->iTri || !p->edge_index || !p->Tri)
+    return ufm_set_error(-2, "ufm_mesh_upload_primary: NULL pointer in the primary mesh data");
+  const int N = p->nV, T = p->nTri, W = p->nC_mem;
+  if (N < 5 || T < 4 || W < 3 || W > 32) return ufm_set_error(-2, "ufm_mesh_upload_primary: implausible sizes nV=%d nTri=%d nC_mem=%d", N, T, W);
+  if (!(p->xmax > p->xmin) || !(p->ymax > p->ymin)) return ufm_set_error(-2, "ufm_mesh_upload_primary: empty domain [%g,%g] x [%g,%g]", p->xmin, p->xmax, p->ymin, p->ymax);
+  const int ldV = p->ldV ? p->ldV : N, ldT = p->ldTri ? p->ldTri : T;
+  if (ldV < N || ldT < T) return ufm_set_error(-2, "ufm_mesh_upload_primary: leading dimension smaller than the mesh");
+  const bool timing = getenv("UFM_UPLOAD_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+    t_last = t;
+  };
+  ufm_secondary *s = new ufm_secondary();
+  struct Guard { ufm_secondary *s; ~Guard() { delete s; } } guard{s};
+  s->nV = N; s->nTri = T; s->W = W;
+  compact(s->V, p->V, N, 2, ldV);
+  compact(s->C, p->C, N, W, ldV);
+  compact(s->iTri, p->iTri, N, W, ldV);
+  compact(s->Tri, p->Tri, T, 3, ldT);
+  s->nC.assign(p->nC, p->nC + N); s->niTri.assign(p->niTri, p->niTri + N); s->edge_index.assign(p->edge_index, p->edge_index + N);
+  // the host routines below index with what the arrays hold: validate first
+  for (int v = 0; v < N; v++) {
+    const int n = s->nC[v], nt = s->niTri[v], ei = s->edge_index[v];
+    if (n < 2 || n > W || nt < 1 || nt > W || ei < 0 || ei > 8) return ufm_set_error(-2, "ufm_mesh_upload_primary: vertex %d: nC=%d niTri=%d edge_index=%d out of range", v + 1, n, nt, ei);
+    for (int c = 0; c < n; c++) { const int q = s->C[(size_t)c * N + v]; if (q < 1 || q > N) return ufm_set_error(-2, "ufm_mesh_upload_primary: C(%d,%d)=%d out of range", v + 1, c + 1, q); }
+    for (int c = 0; c < nt; c++) { const int q = s->iTri[(size_t)c * N + v]; if (q < 1 || q > T) return ufm_set_error(-2, "ufm_mesh_upload_primary: iTri(%d,%d)=%d out of range", v + 1, c + 1, q); }
+  }
+  for (size_t k = 0; k < s->Tri.size(); k++) if (s->Tri[k] < 1 || s->Tri[k] > N) return ufm_set_error(-2, "ufm_mesh_upload_primary: Tri out of range");
+  lap("copy + validate");
+
+  s->A.resize(N); s->Cw.assign((size_t)N * W, 0.0); s->Tricc.resize((size_t)T * 2); s->Tri_edge_index.resize(T);
+  int rc = ufm_mesh_geometry(N, T, W, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(), s->edge_index.data(),
+                             p->xmin, p->xmax, p->ymin, p->ymax, s->Tricc.data(), s->Tri_edge_index.data(), s->A.data(), s->Cw.data());
+  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: Voronoi areas / connection widths failed (%d): C / iTri / Tri are inconsistent", rc);
+  lap("Voronoi areas, Cw");
+
+  // a planar triangulation of a simply connected domain has exactly nV + nTri - 1 edges (Euler)
+  const int nAc_max = N + T;
+  s->ldAc = nAc_max;
+  s->iAci.assign((size_t)N * W, 0); s->Aci.assign((size_t)nAc_max * 4, 0); s->VAc.assign((size_t)nAc_max * 2, 0.0); s->edge_index_Ac.assign(nAc_max, 0);
+  const int nAc = ufm_mesh_make_Ac(N, T, W, nAc_max, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(),
+                                   s->edge_index.data(), s->iAci.data(), s->Aci.data(), s->VAc.data(), nullptr, nullptr, nullptr, nullptr, s->edge_index_Ac.data());
+  if (nAc <= 0) return ufm_set_error(-2, "ufm_mesh_upload_primary: make_Ac_mesh failed (%d): %s", nAc, nAc == -1 ? "more edges than nV + nTri" : "an edge without its triangle(s)");
+  s->nAc = nAc;
+  lap("make_Ac_mesh");
+
+  const int M = N + nAc;
+  s->VAaAc.resize((size_t)M * 2); s->nCAaAc.resize(M); s->CAaAc.resize((size_t)M * W);
+  rc = ufm_mesh_make_AaAc(N, nAc, nAc_max, W, s->V.data(), s->VAc.data(), s->nC.data(), s->C.data(), s->iAci.data(), s->Aci.data(), s->edge_index_Ac.data(),
+                          s->VAaAc.data(), s->nCAaAc.data(), s->CAaAc.data());
+  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: make_combined_AaAc_mesh failed (%d)", rc);
+  lap("make_combined_AaAc_mesh");
+
+  s->colour.resize(M); s->colour_vi.assign((size_t)M * 5, 0); s->colour_nV.assign(5, 0);
+  rc = ufm_mesh_five_colouring(M, W, s->nCAaAc.data(), s->CAaAc.data(), s->colour.data(), s->colour_vi.data(), s->colour_nV.data());
+  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: five-colouring failed (%d)%s", rc, rc == -2 ? " (the reference aborts in IDENTIFY)" : "");
+  lap("five-colouring");
+
+  ufm_mesh_desc &d = s->desc;
+  memset(&d, 0, sizeof(d));
+  d.nV = N; d.nAc = nAc; d.nC_mem = W; d.ldV = N; d.ldAc = nAc_max; d.ldAaAc = M;
+  d.V = s->V.data(); d.A = s->A.data(); d.nC = s->nC.data(); d.C = s->C.data(); d.Cw = s->Cw.data(); d.edge_index = s->edge_index.data();
+  d.Aci = s->Aci.data(); d.iAci = s->iAci.data(); d.edge_index_Ac = s->edge_index_Ac.data();
+  d.nCAaAc = s->nCAaAc.data(); d.CAaAc = s->CAaAc.data(); d.colour_vi = s->colour_vi.data(); d.colour_nV = s->colour_nV.data();
+  // Nx .. Nyy_AaAc stay NULL: derived on the device
+  if (p->thermo) {
+    // determine_mesh_resolution (src/mesh_help_functions_module.f90:193-216), triangle neighbour functions (src/mesh_derivatives_module.f90:30-47)
+    s->R.assign(N, p->xmax - p->xmin);
+    const double *V = s->V.data();
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < N; v++)
+      for (int c = 0; c < s->nC[v]; c++) {
+        const int q = s->C[(size_t)c * N + v] - 1;
+        const double dx = V[q] - V[v], dy = V[N + q] - V[N + v];
+        s->R[v] = fmin(s->R[v], sqrt(dx * dx + dy * dy));
+      }
+    s->NxTri.resize((size_t)T * 3); s->NyTri.resize((size_t)T * 3);
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < T; t++) {
+      const int a = s->Tri[t] - 1, b = s->Tri[(size_t)T + t] - 1, c = s->Tri[(size_t)2 * T + t] - 1;
+      const double ax = V[a], ay = V[N + a], bx = V[b], by = V[N + b], cx = V[c], cy = V[N + c];
+      const double D = ax * (by - cy) + bx * (cy - ay) + cx * (ay - by);
+      s->NxTri[t] = (by - cy) / D; s->NxTri[(size_t)T + t] = (cy - ay) / D; s->NxTri[(size_t)2 * T + t] = (ay - by) / D;
+      s->NyTri[t] = (cx - bx) / D; s->NyTri[(size_t)T + t] = (ax - cx) / D; s->NyTri[(size_t)2 * T + t] = (bx - ax) / D;
+    }
+    d.nTri = T; d.ldTri = T; d.Tri = s->Tri.data(); d.niTri = s->niTri.data(); d.iTri = s->iTri.data(); d.R = s->R.data();
+    d.NxTri = s->NxTri.data(); d.NyTri = s->NyTri.data();
+    lap("resolution, NxTri/NyTri");
+  }
+  *derived = s;
+  guard.s = nullptr;
+  return 0;
+}
+extern "C" void ufm_mesh_derived_free(void *derived) { delete (ufm_secondary *)derived; }
+
+extern "C" int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *p)
+{
+  if (!h) return ufm_set_error(-2, "NULL handle");
+  void *derived = nullptr;
+  int rc = ufm_mesh_derive_secondary(p, &derived);
+  if (rc) return rc;
+  ufm_secondary *s = (ufm_secondary *)derived;
+  const auto t0 = std::chrono::steady_clock::now();
+  rc = ufm_mesh_upload(h, &s->desc);   // drops the arrays derived for the previous mesh
+  if (getenv("UFM_UPLOAD_TIMING"))
+    fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", "ufm_mesh_upload", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  if (rc) { delete s; return rc; }
+  h->secondary = s;
+  return 0;
+}
+
+// the derived arrays of the last ufm_mesh_upload_primary, valid until the next upload or ufm_destroy.  Neighbour-function members
+// are NULL (they exist only on the device); ldAc > nAc.
+extern "C" int ufm_mesh_derived_get(const void *derived, ufm_mesh_desc *out, const double **Tricc, const int **Tri_edge_index, const double **VAc,
+                                    const double **VAaAc, const int **colour)
+{
+  if (!derived || !out) return ufm_set_error(-2, "ufm_mesh_derived_get: NULL argument");
+  const ufm_secondary *s = (const ufm_secondary *)derived;
+  *out = s->desc;
+  if (Tricc) *Tricc = s->Tricc.data();
+  if (Tri_edge_index) *Tri_edge_index = s->Tri_edge_index.data();
+  if (VAc) *VAc = s->VAc.data();
+  if (VAaAc) *VAaAc = s->VAaAc.data();
+  if (colour) *colour = s->colour.data();
+  return 0;
+}
+extern "C" int ufm_mesh_secondary_get(ufm_handle *h, ufm_mesh_desc *out, const double **Tricc, const int **Tri_edge_index, const double **VAc,
+                                      const double **VAaAc, const int **colour)
+{
+  if (!h || !out) return ufm_set_error(-2, "ufm_mesh_secondary_get: NULL argument");
+  if (!h->secondary) return ufm_set_error(-2, "ufm_mesh_secondary_get: the resident mesh was not uploaded with ufm_mesh_upload_primary");
+  return ufm_mesh_derived_get(h->secondary, out, Tricc, Tri_edge_index, VAc, VAaAc, colour);
+}
