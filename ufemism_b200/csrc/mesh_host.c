@@ -127,6 +127,8 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
                       const int *edge_index, double xmin, double xmax, double ymin, double ymax,
                       double *Tricc, int *Tri_edge_index, double *A, double *Cw)
 {
+  int err = 0;
+#pragma omp parallel for schedule(static)
   for (int t = 1; t <= nTri; t++) {
     double p[3][2];
     int side[3];
@@ -151,12 +153,13 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
     Tri_edge_index[t - 1] = tei;
   }
   memset(Cw, 0, sizeof(double) * (size_t)nV * nC_mem);
+#pragma omp parallel for schedule(static)
   for (int vi = 1; vi <= nV; vi++) {
     double x0 = I2(V, vi, 1, nV), y0 = I2(V, vi, 2, nV);
     int nt = niTri[vi - 1], ei = edge_index[vi - 1];
     double vor[40][2];
     int nv = 0;
-    if (nt + 3 > 40) return -3;
+    if (nt + 3 > 40) { err = -3; continue; }
     for (int k = 1; k <= nt; k++) {
       int t = I2(iTri, vi, k, nV);
       double cx = clampd(I2(Tricc, t, 1, nTri), xmin, xmax), cy = clampd(I2(Tricc, t, 2, nTri), ymin, ymax);
@@ -191,7 +194,7 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
         for (int n = 1; n <= 3; n++) if (I2(Tri, t, n, nTri) == vj) has = 1;
         if (has) { if (!t1) t1 = t; else t2 = t; }
       }
-      if (!t1) return -1;
+      if (!t1) { err = -1; break; }
       double w;
       if (t2) {
         double dx = I2(Tricc, t1, 1, nTri) - I2(Tricc, t2, 1, nTri), dy = I2(Tricc, t1, 2, nTri) - I2(Tricc, t2, 2, nTri);
@@ -202,12 +205,12 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
         else if (tei == 3) w = fmax(0.0, xmax - I2(Tricc, t1, 1, nTri));
         else if (tei == 5) w = fmax(0.0, I2(Tricc, t1, 2, nTri) - ymin);
         else if (tei == 7) w = fmax(0.0, I2(Tricc, t1, 1, nTri) - xmin);
-        else return -2;
+        else { err = -2; break; }
       }
       I2(Cw, vi, ci, nV) = w;
     }
   }
-  return 0;
+  return err;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -361,16 +364,33 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
                      int *iAci, int *Aci, double *VAc, double *Nx_Ac, double *Ny_Ac, double *Np_Ac, double *No_Ac,
                      int *edge_index_Ac)
 {
-  int nAc = 0;
+  /* The reference numbers an edge the first time its walk (vi ascending, ci ascending) meets it and skips edges already
+   * numbered from the other end, i.e. every edge is numbered at its lower-index end.  The number of an edge is therefore
+   * (edges owned by lower vertices) + (its rank among vi's connections to higher vertices): a prefix sum, after which the
+   * vertices can be processed independently with the reference's numbering reproduced exactly. */
+  int err = 0;
   memset(iAci, 0, sizeof(int) * (size_t)nV * nC_mem);
+  int *first = (int *)malloc(sizeof(int) * ((size_t)nV + 2));
+  if (!first) return -3;
+#pragma omp parallel for schedule(static)
+  for (int vi = 1; vi <= nV; vi++) {
+    int k = 0;
+    for (int ci = 1; ci <= nC[vi - 1]; ci++) if (I2(C, vi, ci, nV) > vi) k++;
+    first[vi] = k;
+  }
+  long long tot = 0;
+  for (int vi = 1; vi <= nV; vi++) { int k = first[vi]; first[vi] = (int)tot; tot += k; }
+  if (tot > nAc_max) { free(first); return -1; }
+  const int nAc_total = (int)tot;
 #define VX(v) I2(V, v, 1, nV)
 #define VY(v) I2(V, v, 2, nV)
+#pragma omp parallel for schedule(dynamic, 1024)
   for (int vi = 1; vi <= nV; vi++) {
+    int nAc = first[vi];
     for (int ci = 1; ci <= nC[vi - 1]; ci++) {
       int vj = I2(C, vi, ci, nV);
-      if (I2(iAci, vi, ci, nV) > 0) continue;
+      if (vj <= vi) continue;
       nAc++;
-      if (nAc > nAc_max) return -1;
       I2(iAci, vi, ci, nV) = nAc;
       I2(VAc, nAc, 1, nAc_max) = (VX(vi) + VX(vj)) / 2.0;
       I2(VAc, nAc, 2, nAc_max) = (VY(vi) + VY(vj)) / 2.0;
@@ -388,7 +408,7 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
             else if (I2(Tri, ti, n1, nTri) == vj && I2(Tri, ti, n2, nTri) == vi) vr = I2(Tri, ti, n3, nTri);
           }
         }
-        if (!vl || !vr) return -2;
+        if (!vl || !vr) { err = -2; continue; }
         I2(Aci, nAc, 1, nAc_max) = vi; I2(Aci, nAc, 2, nAc_max) = vj; I2(Aci, nAc, 3, nAc_max) = vl; I2(Aci, nAc, 4, nAc_max) = vr;
         Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
         Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
@@ -410,7 +430,7 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
                 (I2(Tri, ti, n1, nTri) == vj && I2(Tri, ti, n2, nTri) == vi)) vl = I2(Tri, ti, n3, nTri);
           }
         }
-        if (!vl) return -2;
+        if (!vl) { err = -2; continue; }
         I2(Aci, nAc, 1, nAc_max) = vi; I2(Aci, nAc, 2, nAc_max) = vj; I2(Aci, nAc, 3, nAc_max) = vl; I2(Aci, nAc, 4, nAc_max) = 1;
         Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
         Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
@@ -427,7 +447,15 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
       }
     }
   }
+  free(first);
+  if (err) return err;
+  const int nAc = nAc_total;
+  /* a connection that its other end does not list (C not symmetric) was never numbered */
+  for (int vi = 1; vi <= nV && !err; vi++)
+    for (int ci = 1; ci <= nC[vi - 1]; ci++) if (I2(iAci, vi, ci, nV) < 1) { err = -2; break; }
+  if (err) return err;
   /* find_Ac_edge_indices, mesh_ArakawaC_module.f90:236-285 */
+#pragma omp parallel for schedule(static)
   for (int aci = 1; aci <= nAc; aci++) {
     int a = edge_index[I2(Aci, aci, 1, nAc_max) - 1], b = edge_index[I2(Aci, aci, 2, nAc_max) - 1], e = 0;
     if ((a == 8 || a == 1 || a == 2) && (b == 8 || b == 1 || b == 2)) e = 1;
@@ -449,13 +477,15 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
                        const int *nC, const int *C, const int *iAci, const int *Aci, const int *edge_index_Ac,
                        double *VAaAc, int *nCAaAc, int *CAaAc)
 {
-  int M = nV + nAc;
+  int M = nV + nAc, err = 0;
   memset(CAaAc, 0, sizeof(int) * (size_t)M * nC_mem);
+#pragma omp parallel for schedule(static)
   for (int vi = 1; vi <= nV; vi++) {
     I2(VAaAc, vi, 1, M) = I2(V, vi, 1, nV); I2(VAaAc, vi, 2, M) = I2(V, vi, 2, nV);
     nCAaAc[vi - 1] = nC[vi - 1];
     for (int ci = 1; ci <= nC[vi - 1]; ci++) I2(CAaAc, vi, ci, M) = I2(iAci, vi, ci, nV) + nV;
   }
+#pragma omp parallel for schedule(static)
   for (int aci = 1; aci <= nAc; aci++) {
     int ai = aci + nV;
     I2(VAaAc, ai, 1, M) = I2(VAc, aci, 1, ldAc); I2(VAaAc, ai, 2, M) = I2(VAc, aci, 2, ldAc);
@@ -472,7 +502,7 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
         if (I2(C, vk, ci, nV) == vi) aci1 = I2(iAci, vk, ci, nV);
         else if (I2(C, vk, ci, nV) == vj) aci2 = I2(iAci, vk, ci, nV);
       }
-      if (!aci1 || !aci2) return -1;
+      if (!aci1 || !aci2) { err = -1; continue; }
       nCAaAc[ai - 1] = 4;
       I2(CAaAc, ai, 1, M) = vi; I2(CAaAc, ai, 2, M) = aci1 + nV; I2(CAaAc, ai, 3, M) = aci2 + nV; I2(CAaAc, ai, 4, M) = vj;
     } else {
@@ -486,13 +516,13 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
         if (I2(C, vl, ci, nV) == vj) aci3 = I2(iAci, vl, ci, nV);
         else if (I2(C, vl, ci, nV) == vi) aci4 = I2(iAci, vl, ci, nV);
       }
-      if (!aci1 || !aci2 || !aci3 || !aci4) return -1;
+      if (!aci1 || !aci2 || !aci3 || !aci4) { err = -1; continue; }
       nCAaAc[ai - 1] = 6;
       I2(CAaAc, ai, 1, M) = vi; I2(CAaAc, ai, 2, M) = aci1 + nV; I2(CAaAc, ai, 3, M) = aci2 + nV;
       I2(CAaAc, ai, 4, M) = vj; I2(CAaAc, ai, 5, M) = aci3 + nV; I2(CAaAc, ai, 6, M) = aci4 + nV;
     }
   }
-  return 0;
+  return err;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -526,6 +556,7 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
   Q4.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q4.next = (int *)calloc((size_t)M + 1, sizeof(int));
   Q5.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q5.next = (int *)calloc((size_t)M + 1, sizeof(int));
   int rc = 0, Sn = 0, noofvert = M;
+#pragma omp parallel for schedule(static)
   for (int v = 1; v <= M; v++) {
     deg[v] = nCAaAc[v - 1];
     for (int c = 1; c <= nC_mem; c++) L[(size_t)(v - 1) * nC_mem + c - 1] = I2(CAaAc, v, c, M);
@@ -542,6 +573,12 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
     if (Q4.n == 0) { rc = -2; break; }                 /* reference: IDENTIFY -> 'beep' + MPI_ABORT */
     int vi = Q4.tail;
     int *Lv = L + (size_t)(vi - 1) * nC_mem;
+    for (int ci = 0; ci < deg[vi]; ci++) {   /* the neighbours' rows are scattered in memory: fetch them all before the first is used */
+      int wi = Lv[ci];
+      __builtin_prefetch(L + (size_t)(wi - 1) * nC_mem, 1);
+      __builtin_prefetch(deg + wi, 1); __builtin_prefetch(inq + wi, 1);
+      __builtin_prefetch(Q4.prev + wi, 1); __builtin_prefetch(Q4.next + wi, 1);
+    }
     for (int ci = 0; ci < deg[vi]; ci++) {
       int wi = Lv[ci];
       int *Lw = L + (size_t)(wi - 1) * nC_mem;
@@ -585,10 +622,13 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
   }
   if (rc == 0) {
     /* check_solution, :318-343 */
-    for (int v = 1; v <= M && rc == 0; v++) {
-      if (colour[v - 1] == 0) rc = -7;
-      for (int c = 1; c <= nCAaAc[v - 1]; c++) if (colour[I2(CAaAc, v, c, M) - 1] == colour[v - 1]) { rc = -7; break; }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int v = 1; v <= M; v++) {
+      if (colour[v - 1] == 0) bad |= 1;
+      for (int c = 1; c <= nCAaAc[v - 1]; c++) if (colour[I2(CAaAc, v, c, M) - 1] == colour[v - 1]) { bad |= 1; break; }
     }
+    if (bad) rc = -7;
   }
   if (rc == 0) {
     memset(colour_vi, 0, sizeof(int) * (size_t)M * 5);
