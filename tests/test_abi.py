@@ -55,11 +55,13 @@ def test_struct_layouts_match_header(tmp_path):
     from ufemism_b200 import restart as R
 
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ufemism_b200.h"\nint main(){'
-                   'printf("%zu %zu %zu %zu %zu\\n", sizeof(ufm_nc_mesh), sizeof(ufm_restart_frame), sizeof(ufm_restart_frame_out),'
-                   ' offsetof(ufm_nc_mesh, V), offsetof(ufm_nc_mesh, w_transect));return 0;}')
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ufm_nc_mesh), sizeof(ufm_restart_frame), sizeof(ufm_restart_frame_out),'
+                   ' offsetof(ufm_nc_mesh, V), offsetof(ufm_nc_mesh, w_transect), sizeof(ufm_mesh_primary), offsetof(ufm_mesh_primary, xmin),'
+                   ' offsetof(ufm_mesh_primary, thermo));return 0;}')
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert got == [ctypes.sizeof(R.NcMesh), ctypes.sizeof(R.RestartFrame), ctypes.sizeof(R.RestartFrameOut), R.NcMesh.V.offset, R.NcMesh.w_transect.offset]
+    assert got == [ctypes.sizeof(R.NcMesh), ctypes.sizeof(R.RestartFrame), ctypes.sizeof(R.RestartFrameOut), R.NcMesh.V.offset, R.NcMesh.w_transect.offset,
+                   ctypes.sizeof(capi.MeshPrimary), capi.MeshPrimary.xmin.offset, capi.MeshPrimary.thermo.offset]
 
 
 def test_fortran_shim_field_ids_match_header():

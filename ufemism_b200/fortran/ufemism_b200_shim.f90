@@ -23,7 +23,9 @@ MODULE ufemism_b200_shim
   USE mpi
   USE configuration_module,          ONLY: dp, C
   USE parallel_module,               ONLY: par, sync, ierr, cerr
-  USE data_types_module,             ONLY: type_mesh, type_ice_model, type_SMB_model, type_BMB_model, type_climate_model
+  USE data_types_module,             ONLY: type_mesh, type_ice_model, type_SMB_model, type_BMB_model, type_climate_model, type_model_region
+  USE data_types_netcdf_module,      ONLY: type_netcdf_restart
+  USE mesh_memory_module,            ONLY: allocate_mesh_primary
 
   IMPLICIT NONE
 
@@ -70,6 +72,22 @@ MODULE ufemism_b200_shim
     INTEGER(C_INT)  :: nTri, ldTri
     TYPE(C_PTR)     :: Tri, niTri, iTri, R, NxTri, NyTri
   END TYPE ufm_mesh_desc
+
+  ! primary mesh data only (row N3): the library derives A, Cw, the Ac / AaAc meshes, the colouring and all neighbour functions
+  TYPE, BIND(C) :: ufm_mesh_primary
+    INTEGER(C_INT)  :: nV, nTri, nC_mem
+    INTEGER(C_INT)  :: ldV, ldTri
+    REAL(C_DOUBLE)  :: xmin, xmax, ymin, ymax
+    TYPE(C_PTR)     :: V, nC, C, niTri, iTri, edge_index, Tri
+    INTEGER(C_INT)  :: thermo
+  END TYPE ufm_mesh_primary
+
+  ! restart / help_fields files (row N4)
+  TYPE, BIND(C) :: ufm_nc_mesh
+    INTEGER(C_INT)  :: nV, nTri, nC_mem, nAc, nV_transect, nVAaAc, nTriAaAc
+    TYPE(C_PTR)     :: V, Tri, nC, C, niTri, iTri, edge_index, Tricc, TriC, Tri_edge_index, VAc, Aci, iAci, VAaAc, TriAaAc, A, R
+    TYPE(C_PTR)     :: vi_transect, w_transect
+  END TYPE ufm_nc_mesh
 
   TYPE, BIND(C) :: ufm_thermo_stats
     INTEGER(C_INT)  :: n_unstable, rc
@@ -183,6 +201,82 @@ MODULE ufemism_b200_shim
       CHARACTER(KIND=C_CHAR), INTENT(IN) :: blobs( *)
       INTEGER(C_INT)              :: rc
     END FUNCTION ufm_comm_connect
+    FUNCTION ufm_mesh_upload_primary( handle, mesh) BIND(C, NAME='ufm_mesh_upload_primary') RESULT( rc)
+      IMPORT :: C_PTR, C_INT, ufm_mesh_primary
+      TYPE(C_PTR), VALUE         :: handle
+      TYPE(ufm_mesh_primary), INTENT(IN) :: mesh
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_mesh_secondary_get( handle, desc, Tricc, Tri_edge_index, VAc, VAaAc, colour) BIND(C, NAME='ufm_mesh_secondary_get') RESULT( rc)
+      IMPORT :: C_PTR, C_INT, ufm_mesh_desc
+      TYPE(C_PTR), VALUE         :: handle
+      TYPE(ufm_mesh_desc), INTENT(OUT) :: desc
+      TYPE(C_PTR), INTENT(OUT)   :: Tricc, Tri_edge_index, VAc, VAaAc, colour
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_create( filename, mesh, nZ, zeta) BIND(C, NAME='ufm_restart_create') RESULT( rc)
+      IMPORT :: C_CHAR, C_INT, C_DOUBLE, ufm_nc_mesh
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      TYPE(ufm_nc_mesh), INTENT(IN) :: mesh
+      INTEGER(C_INT), VALUE      :: nZ
+      REAL(C_DOUBLE), INTENT(IN) :: zeta( *)
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_write( handle, filename, time, FirnDepth, MeltPreviousYear) BIND(C, NAME='ufm_restart_write') RESULT( rc)
+      IMPORT :: C_PTR, C_CHAR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE         :: handle
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      REAL(C_DOUBLE), VALUE      :: time
+      TYPE(C_PTR), VALUE         :: FirnDepth, MeltPreviousYear
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_inquire_mesh( filename, nV, nTri, nC_mem) BIND(C, NAME='ufm_restart_inquire_mesh') RESULT( rc)
+      IMPORT :: C_CHAR, C_INT
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      INTEGER(C_INT), INTENT(OUT) :: nV, nTri, nC_mem
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_read_mesh( filename, V, nC, C, niTri, iTri, edge_index, Tri, Tricc, TriC, Tri_edge_index) &
+        BIND(C, NAME='ufm_restart_read_mesh') RESULT( rc)
+      IMPORT :: C_PTR, C_CHAR, C_INT
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      TYPE(C_PTR), VALUE         :: V, nC, C, niTri, iTri, edge_index, Tri, Tricc, TriC, Tri_edge_index
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_inquire_init( filename, nZ, zeta, nt) BIND(C, NAME='ufm_restart_inquire_init') RESULT( rc)
+      IMPORT :: C_CHAR, C_INT, C_DOUBLE
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      INTEGER(C_INT), VALUE      :: nZ
+      REAL(C_DOUBLE), INTENT(IN) :: zeta( *)
+      INTEGER(C_INT), INTENT(OUT) :: nt
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_restart_load( handle, filename, time_to_restart_from, FirnDepth, MeltPreviousYear) BIND(C, NAME='ufm_restart_load') RESULT( rc)
+      IMPORT :: C_PTR, C_CHAR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE         :: handle
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      REAL(C_DOUBLE), VALUE      :: time_to_restart_from
+      TYPE(C_PTR), VALUE         :: FirnDepth, MeltPreviousYear
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_help_fields_create( filename, mesh, nZ, zeta, n_fields, names) BIND(C, NAME='ufm_help_fields_create') RESULT( rc)
+      IMPORT :: C_PTR, C_CHAR, C_INT, C_DOUBLE, ufm_nc_mesh
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      TYPE(ufm_nc_mesh), INTENT(IN) :: mesh
+      INTEGER(C_INT), VALUE      :: nZ, n_fields
+      REAL(C_DOUBLE), INTENT(IN) :: zeta( *)
+      TYPE(C_PTR), INTENT(IN)    :: names( *)
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
+    FUNCTION ufm_help_fields_write( handle, filename, time, n_fields, names, host_data) BIND(C, NAME='ufm_help_fields_write') RESULT( rc)
+      IMPORT :: C_PTR, C_CHAR, C_INT, C_DOUBLE
+      TYPE(C_PTR), VALUE         :: handle
+      CHARACTER(KIND=C_CHAR), INTENT(IN) :: filename( *)
+      REAL(C_DOUBLE), VALUE      :: time
+      INTEGER(C_INT), VALUE      :: n_fields
+      TYPE(C_PTR), INTENT(IN)    :: names( *), host_data( *)
+      INTEGER(C_INT)             :: rc
+    END FUNCTION
     FUNCTION ufm_last_error() BIND(C, NAME='ufm_last_error') RESULT( msg)
       IMPORT :: C_PTR
       TYPE(C_PTR)                 :: msg
@@ -422,5 +516,110 @@ CONTAINS
     CALL MPI_BCAST( out3, 3, MPI_DOUBLE_PRECISION, 0, MPI_COMM_WORLD, ierr)
     dt_D_2D_min = out3( 1);  dt_V_2D_SSA_min = out3( 2);  dt_V_3D_SIA_min = out3( 3)
   END SUBROUTINE critical_timesteps_b200
+
+  ! ---- row N3: mesh update / restart without the CPU rebuild of the secondary mesh data --------------------------------
+
+  SUBROUTINE b200_upload_mesh_primary( mesh)
+    ! Call INSTEAD of the block find_Voronoi_cell_areas .. calculate_five_colouring_AaAc of read_mesh_from_restart_file
+    ! (src/restart_module.f90:88-103) / create_final_mesh_from_merged_submesh (src/mesh_creation_module.f90:1724-1737) when no
+    ! CPU component needs those arrays: only the primary mesh data must be valid.  The few derived arrays the host still reads
+    ! (A, Cw, Aci, iAci, VAc, colour lists) can be copied back with ufm_mesh_secondary_get.
+    TYPE(type_mesh), TARGET, INTENT(IN) :: mesh
+    TYPE(ufm_mesh_primary) :: p
+    IF (par%master) THEN
+      p%nV = mesh%nV;  p%nTri = mesh%nTri;  p%nC_mem = mesh%nC_mem
+      p%ldV = SIZE( mesh%V, 1);  p%ldTri = SIZE( mesh%Tri, 1)
+      p%xmin = mesh%xmin;  p%xmax = mesh%xmax;  p%ymin = mesh%ymin;  p%ymax = mesh%ymax
+      p%V = C_LOC( mesh%V);  p%nC = C_LOC( mesh%nC);  p%C = C_LOC( mesh%C);  p%niTri = C_LOC( mesh%niTri);  p%iTri = C_LOC( mesh%iTri)
+      p%edge_index = C_LOC( mesh%edge_index);  p%Tri = C_LOC( mesh%Tri)
+      p%thermo = 1
+      CALL b200_check( ufm_mesh_upload_primary( b200_handle, p), 'ufm_mesh_upload_primary')
+    END IF
+    CALL sync
+  END SUBROUTINE b200_upload_mesh_primary
+
+  ! ---- row N4: restart / help_fields files written from and read onto the device --------------------------------------
+
+  FUNCTION b200_cstring( f) RESULT( c)
+    CHARACTER(LEN=*), INTENT(IN) :: f
+    CHARACTER(KIND=C_CHAR)       :: c( LEN_TRIM( f) + 1)
+    INTEGER :: n
+    DO n = 1, LEN_TRIM( f)
+      c( n) = f( n:n)
+    END DO
+    c( LEN_TRIM( f) + 1) = C_NULL_CHAR
+  END FUNCTION b200_cstring
+
+  SUBROUTINE b200_nc_mesh( mesh, m)
+    TYPE(type_mesh), TARGET, INTENT(IN)  :: mesh
+    TYPE(ufm_nc_mesh),       INTENT(OUT) :: m
+    m%nV = mesh%nV;  m%nTri = mesh%nTri;  m%nC_mem = mesh%nC_mem;  m%nAc = mesh%nAc;  m%nV_transect = mesh%nV_transect
+    m%nVAaAc = mesh%nVAaAc;  m%nTriAaAc = mesh%nTriAaAc
+    m%V = C_LOC( mesh%V);  m%Tri = C_LOC( mesh%Tri);  m%nC = C_LOC( mesh%nC);  m%C = C_LOC( mesh%C);  m%niTri = C_LOC( mesh%niTri)
+    m%iTri = C_LOC( mesh%iTri);  m%edge_index = C_LOC( mesh%edge_index);  m%Tricc = C_LOC( mesh%Tricc);  m%TriC = C_LOC( mesh%TriC)
+    m%Tri_edge_index = C_LOC( mesh%Tri_edge_index);  m%VAc = C_LOC( mesh%VAc);  m%Aci = C_LOC( mesh%Aci);  m%iAci = C_LOC( mesh%iAci)
+    m%VAaAc = C_LOC( mesh%VAaAc);  m%TriAaAc = C_LOC( mesh%TriAaAc);  m%A = C_LOC( mesh%A);  m%R = C_LOC( mesh%R)
+    m%vi_transect = C_LOC( mesh%vi_transect);  m%w_transect = C_LOC( mesh%w_transect)
+  END SUBROUTINE b200_nc_mesh
+
+  SUBROUTINE create_restart_file_mesh_b200( region, netcdf)
+    ! Drop-in for create_restart_file_mesh (src/netcdf_module.f90:489-633): same file, no NetCDF library
+    TYPE(type_model_region),   INTENT(INOUT) :: region
+    TYPE(type_netcdf_restart), INTENT(INOUT) :: netcdf
+    TYPE(ufm_nc_mesh) :: m
+    IF (.NOT. par%master) RETURN
+    netcdf%ti = 1
+    CALL b200_nc_mesh( region%mesh, m)
+    CALL b200_check( ufm_restart_create( b200_cstring( netcdf%filename), m, INT( C%nZ, C_INT), C%zeta), 'create_restart_file_mesh')
+  END SUBROUTINE create_restart_file_mesh_b200
+
+  SUBROUTINE write_to_restart_file_mesh_b200( region, netcdf)
+    ! Drop-in for write_to_restart_file_mesh (src/netcdf_module.f90:180-214): Hi, Hb, Hs, U/V_SIA, U/V_SSA, Ti come straight
+    ! from the device; FirnDepth and MeltPreviousYear belong to the CPU SMB model
+    TYPE(type_model_region), TARGET, INTENT(INOUT) :: region
+    TYPE(type_netcdf_restart),       INTENT(INOUT) :: netcdf
+    INTEGER(C_INT) :: ti
+    IF (.NOT. par%master) RETURN
+    ti = ufm_restart_write( b200_handle, b200_cstring( netcdf%filename), region%time, C_LOC( region%SMB%FirnDepth), C_LOC( region%SMB%MeltPreviousYear))
+    IF (ti < 0) CALL b200_check( ti, 'write_to_restart_file_mesh')
+    netcdf%ti = ti + 1
+  END SUBROUTINE write_to_restart_file_mesh_b200
+
+  SUBROUTINE read_mesh_from_restart_file_b200( region)
+    ! Drop-in for read_mesh_from_restart_file (src/restart_module.f90:31-116): primary mesh data from the file, everything
+    ! else derived inside the library and resident on the device when this returns
+    TYPE(type_model_region), TARGET, INTENT(INOUT) :: region
+    INTEGER(C_INT) :: nV, nTri, nC_mem
+    IF (par%master) CALL b200_check( ufm_restart_inquire_mesh( b200_cstring( region%init%netcdf_restart%filename), nV, nTri, nC_mem), 'inquire_restart_file_mesh')
+    CALL MPI_BCAST( nV,     1, MPI_INTEGER, 0, MPI_COMM_WORLD, ierr)
+    CALL MPI_BCAST( nTri,   1, MPI_INTEGER, 0, MPI_COMM_WORLD, ierr)
+    CALL MPI_BCAST( nC_mem, 1, MPI_INTEGER, 0, MPI_COMM_WORLD, ierr)
+    CALL allocate_mesh_primary( region%mesh, region%name, nV, nTri, nC_mem)
+    IF (par%master) THEN
+      region%mesh%nV = nV;  region%mesh%nTri = nTri
+      CALL b200_check( ufm_restart_read_mesh( b200_cstring( region%init%netcdf_restart%filename), C_LOC( region%mesh%V), C_LOC( region%mesh%nC), &
+        C_LOC( region%mesh%C), C_LOC( region%mesh%niTri), C_LOC( region%mesh%iTri), C_LOC( region%mesh%edge_index), C_LOC( region%mesh%Tri), &
+        C_LOC( region%mesh%Tricc), C_LOC( region%mesh%TriC), C_LOC( region%mesh%Tri_edge_index)), 'read_restart_file_mesh')
+      region%mesh%xmin = MINVAL( region%mesh%V( 1:nV,1));  region%mesh%xmax = MAXVAL( region%mesh%V( 1:nV,1))
+      region%mesh%ymin = MINVAL( region%mesh%V( 1:nV,2));  region%mesh%ymax = MAXVAL( region%mesh%V( 1:nV,2))
+    END IF
+    CALL sync
+    CALL b200_upload_mesh_primary( region%mesh)
+  END SUBROUTINE read_mesh_from_restart_file_b200
+
+  SUBROUTINE read_init_data_from_restart_file_b200( region)
+    ! Drop-in for read_init_data_from_restart_file (src/restart_module.f90:118-142): the time frame closest to
+    ! C%time_to_restart_from goes straight to the device (Hi, Hb, Ti, U_SSA, V_SSA); the SMB model's fields to the host
+    TYPE(type_model_region), TARGET, INTENT(INOUT) :: region
+    INTEGER(C_INT) :: rc, nt
+    IF (par%master) THEN
+      rc = ufm_restart_inquire_init( b200_cstring( region%init%netcdf_restart%filename), INT( C%nZ, C_INT), C%zeta, nt)
+      CALL b200_check( rc, 'inquire_restart_file_init')        ! rc 1: zeta differs, the reference only warns
+      rc = ufm_restart_load( b200_handle, b200_cstring( region%init%netcdf_restart%filename), C%time_to_restart_from, &
+                             C_LOC( region%init%FirnDepth), C_LOC( region%init%MeltPreviousYear))
+      IF (rc < 0) CALL b200_check( rc, 'read_restart_file_init')
+    END IF
+    CALL sync
+  END SUBROUTINE read_init_data_from_restart_file_b200
 
 END MODULE ufemism_b200_shim
