@@ -348,3 +348,18 @@ def test_derive_secondary_rejects_broken_primary_data(mesh):
         with pytest.raises(UfmError) as e:
             capi.derive_secondary(d)
         assert e.value.rc == -2, (k, str(e.value))
+
+
+def test_relabelled_five_colouring_gives_the_same_colouring(mesh):
+    """ufm_mesh_upload_primary runs calculate_five_colouring_AaAc on a Morton relabelling of the graph (cache locality).  The
+    relabelled run must take the decisions of the plain run: same colour for every vertex, for any permutation."""
+    lib = M._load()
+    Mv, p = mesh.nVAaAc, M._p
+    rng = np.random.default_rng(11)
+    by_x = np.empty(Mv, np.int32)
+    by_x[np.argsort(mesh.VAaAc[:, 0], kind="stable")] = np.arange(1, Mv + 1, dtype=np.int32)
+    for label in (None, (rng.permutation(Mv) + 1).astype(np.int32), by_x, np.arange(Mv, 0, -1, dtype=np.int32)):
+        colour, cvi, cn = np.zeros(Mv, np.int32), np.zeros((Mv, 5), np.int32, order="F"), np.zeros(5, np.int32)
+        rc = lib.ufm_mesh_five_colouring_labelled(Mv, mesh.nC_mem, p(mesh.nCAaAc), p(mesh.CAaAc), None if label is None else p(label), p(colour), p(cvi), p(cn))
+        assert rc == 0
+        assert np.array_equal(colour, mesh.colour) and np.array_equal(cvi, mesh.colour_vi) and np.array_equal(cn, mesh.colour_nV)

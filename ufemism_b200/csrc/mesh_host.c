@@ -544,8 +544,14 @@ static void dl_remove(dlist *q, int v)
   q->prev[v] = q->next[v] = 0; q->n--;
 }
 
-int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAaAc,
-                            int *colour, int *colour_vi, int *colour_nV)
+/* `label` (optional): a permutation of 1..M.  The algorithm then runs on the relabelled graph -- vertex v is stored, queued and
+ * stacked as label[v-1] -- with the initial queues filled in ORIGINAL index order, so that every decision it takes is the one it
+ * would take without relabelling (adjacency rows keep their order; queue and stack discipline do not look at the labels).  The
+ * colouring is identical; what changes is where the rows live in memory: with a space-filling-curve labelling the delete loop,
+ * which walks from a deleted vertex to its neighbours, stays in cache (reference-ordered meshes are numbered in refinement
+ * order, i.e. randomly in space). */
+int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label,
+                                     int *colour, int *colour_vi, int *colour_nV)
 {
   int *deg = (int *)malloc(sizeof(int) * ((size_t)M + 1));
   int *L = (int *)malloc(sizeof(int) * (size_t)M * nC_mem);           /* row-major copy: L[(v-1)*nC_mem + c] */
@@ -556,16 +562,19 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
   Q4.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q4.next = (int *)calloc((size_t)M + 1, sizeof(int));
   Q5.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q5.next = (int *)calloc((size_t)M + 1, sizeof(int));
   int rc = 0, Sn = 0, noofvert = M;
+#define LAB(v) (label ? label[(v) - 1] : (v))
 #pragma omp parallel for schedule(static)
   for (int v = 1; v <= M; v++) {
-    deg[v] = nCAaAc[v - 1];
-    for (int c = 1; c <= nC_mem; c++) L[(size_t)(v - 1) * nC_mem + c - 1] = I2(CAaAc, v, c, M);
+    const int q = LAB(v);
+    deg[q] = nCAaAc[v - 1];
+    for (int c = 1; c <= nC_mem; c++) { const int w = I2(CAaAc, v, c, M); L[(size_t)(q - 1) * nC_mem + c - 1] = w > 0 ? LAB(w) : 0; }
   }
 #define CHECK(w) do { int d_ = deg[w]; \
     if (d_ <= 4) { if (inq[w] == 5) { dl_remove(&Q5, w); inq[w] = 0; } if (inq[w] != 4) { dl_push(&Q4, w); inq[w] = 4; } } \
     else if (d_ == 5) { if (inq[w] == 4) { dl_remove(&Q4, w); inq[w] = 0; } if (inq[w] != 5) { dl_push(&Q5, w); inq[w] = 5; } } \
     else { if (inq[w] == 4) { rc = -3; } if (inq[w] == 5) { dl_remove(&Q5, w); inq[w] = 0; } } } while (0)
-  for (int v = 1; v <= M; v++) {
+  for (int v0 = 1; v0 <= M; v0++) {   /* original index order */
+    const int v = LAB(v0);
     if (deg[v] <= 4) { dl_push(&Q4, v); inq[v] = 4; }
     else if (deg[v] == 5) { dl_push(&Q5, v); inq[v] = 5; }
   }
@@ -620,6 +629,13 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
       colour[vi - 1] = col;
     }
   }
+  if (rc == 0 && label) {   /* back to the caller's numbering; S_vi doubles as scratch */
+#pragma omp parallel for schedule(static)
+    for (int v = 1; v <= M; v++) S_vi[v] = colour[label[v - 1] - 1];
+#pragma omp parallel for schedule(static)
+    for (int v = 1; v <= M; v++) colour[v - 1] = S_vi[v];
+  }
+#undef LAB
   if (rc == 0) {
     /* check_solution, :318-343 */
     int bad = 0;
@@ -642,4 +658,9 @@ int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAa
   free(deg); free(L); free(inq); free(S_vi); free(S_L);
   free(Q4.prev); free(Q4.next); free(Q5.prev); free(Q5.next);
   return rc;
+}
+
+int ufm_mesh_five_colouring(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, int *colour, int *colour_vi, int *colour_nV)
+{
+  return ufm_mesh_five_colouring_labelled(M, nC_mem, nCAaAc, CAaAc, NULL, colour, colour_vi, colour_nV);
 }
