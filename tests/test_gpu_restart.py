@@ -121,3 +121,44 @@ def test_restart_and_help_fields_written_from_the_device(mesh_2k, tmp_path):
     g2.solve_SIA(); g.solve_SIA()
     for n in ("Hs", "dHs_dx", "mask", "mask_gl", "Hi_Ac", "U_SIA", "V_SIA", "D_SIA"):
         assert_bits_equal(g2.download(n), g.download(n), f"after restart {n}")
+
+
+# ---- drop-in loop: ufm_run_model_host moves the host's fields every step; copies overlap each other and the SSA solve ----
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_run_model_host_matches_device_resident_run(mesh_2k, monkeypatch, pinned, overlap):
+    """Same trajectory as ufm_run_model, every downloaded field bit-identical to a download after the step -- with page-locked
+    and with pageable host arrays, with the overlapped copies (default) and with one synchronous copy per field."""
+    from tests.test_gpu_parity import scenario
+    from ufemism_b200.capi import HostIce
+
+    monkeypatch.setenv("UFM_XFER_OVERLAP", overlap)
+    st = scenario(mesh_2k, "mismip")
+    a, b = make_gpu(mesh_2k, st), make_gpu(mesh_2k, st)
+    nV = mesh_2k.nV
+    hb = {n: np.zeros(nV) for n in ("Hi", "Hb", "SL", "dHb_dt", "SMB_year", "BMB", "Hi_prev", "dHi_dt", "Hs", "U_SSA", "V_SSA", "U_SIA", "V_SIA", "D_SIA")}
+    hb["mask_noice"] = np.zeros(nV, np.int32); hb["mask"] = np.zeros(nV, np.int32)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        hb[k][:] = st[k]
+    host = HostIce(**{n: hb[n].ctypes.data for n in hb if n != "Hi"}, Hi=hb["Hi"].ctypes.data, Hi_out=hb["Hi"].ctypes.data)
+    if pinned:
+        for v in hb.values():
+            b.host_register(v)
+    ra, rb = a.region(0.0), b.region(0.0)
+    for step in range(4):
+        a.run_model(ra, 1e12, max_steps=1)
+        b.run_model_host(rb, 1e12, 1, host)
+        assert (ra.time, ra.dt, ra.n_sor_total, ra.n_outer_total) == (rb.time, rb.dt, rb.n_sor_total, rb.n_outer_total)
+        for hname, fname in [("Hi", "Hi"), ("Hi_prev", "Hi_prev"), ("dHi_dt", "dHi_dt"), ("Hs", "Hs"), ("U_SSA", "U_SSA"), ("V_SSA", "V_SSA"),
+                             ("U_SIA", "U_SIA"), ("V_SIA", "V_SIA"), ("D_SIA", "D_SIA"), ("mask", "mask")]:
+            assert_bits_equal(hb[hname], a.download(fname), f"step {step} {hname}")
+    assert ra.n_sor_total > 0 and hb["U_SSA"].any() and np.ptp(hb["Hi"]) > 0
+    # the host edits a field between steps (what ELRA / SMB components do): the next step must see it
+    hb["Hb"][:] = hb["Hb"] + 5.0
+    a.upload("Hb", hb["Hb"])
+    a.run_model(ra, 1e12, max_steps=1); b.run_model_host(rb, 1e12, 1, host)
+    a.run_model(ra, 1e12, max_steps=1); b.run_model_host(rb, 1e12, 1, host)
+    assert_bits_equal(hb["Hi"], a.download("Hi"), "Hi after the host changed Hb")
+    assert_bits_equal(hb["Hs"], a.download("Hs"), "Hs after the host changed Hb")
+    cnt = b.counters()
+    assert cnt.h2d_bytes == 6 * (6 * 8 + 4) * nV and cnt.d2h_bytes == 6 * (9 * 8 + 4) * nV

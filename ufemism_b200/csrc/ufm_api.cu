@@ -95,6 +95,10 @@ int ufm_destroy(ufm_handle *h)
   for (auto &q : h->stash) if (q.d) { cudaFree(q.d); cudaFree(q.ddx); cudaFree(q.ddy); }
   if (h->staging) cudaFreeHost(h->staging);
   if (h->dev_staging) cudaFree(h->dev_staging);
+  if (h->xfer_dev) cudaFree(h->xfer_dev);
+  if (h->xfer_host) cudaFreeHost(h->xfer_host);
+  for (auto e : h->xfer_ev) if (e) cudaEventDestroy(e);
+  if (h->xfer_stream) cudaStreamDestroy(h->xfer_stream);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   for (auto e : h->ev_pool) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->own_stream);
@@ -478,6 +482,73 @@ int ufm_run_model_host(ufm_handle *h, ufm_region *r, double t_end, long max_step
 }
 }  // extern "C"
 
+// ---- overlapped field transfers of the drop-in loop ------------------------------------------------------------------
+// One slot per field and direction.  Upload: H2D on the copy stream -> event -> permutation kernel on the compute stream.
+// Download: permutation kernel on the compute stream (right after the field's producer) -> event -> D2H on the copy stream,
+// which therefore runs underneath whatever the compute stream does next (the SSA solve).  The host synchronises once per
+// step (xfer_finish).  Only Aa fields (nV doubles / ints) travel this way.
+static int xfer_prepare(ufm_handle *h, bool need_host_slots)
+{
+  const size_t slot = (((size_t)h->mesh.nV * sizeof(double)) + 255) & ~(size_t)255;
+  if (!h->xfer_stream) {
+    UFM_CUDA(cudaStreamCreateWithFlags(&h->xfer_stream, cudaStreamNonBlocking));
+    for (auto &e : h->xfer_ev) UFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (h->xfer_slot_bytes < slot) {
+    UFM_CUDA(cudaStreamSynchronize(h->xfer_stream));
+    if (h->xfer_dev) cudaFree(h->xfer_dev);
+    if (h->xfer_host) cudaFreeHost(h->xfer_host);
+    h->xfer_dev = h->xfer_host = nullptr; h->xfer_slot_bytes = 0;
+    UFM_CUDA(cudaMalloc((void **)&h->xfer_dev, slot * UFM_XFER_SLOTS));
+    h->xfer_slot_bytes = slot;
+  }
+  if (need_host_slots && !h->xfer_host) UFM_CUDA(cudaMallocHost((void **)&h->xfer_host, h->xfer_slot_bytes * UFM_XFER_SLOTS));
+  h->xfer_n_pending = 0;
+  return 0;
+}
+static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int slot)
+{
+  FieldRef r;
+  int rc = field_ref(h, field, &r);
+  if (rc) return rc;
+  DevMesh &m = h->mesh;
+  if (r.kind != K_AA || r.is3d || slot < 0 || slot >= UFM_XFER_SLOTS) return ufm_set_error(-2, "xfer_begin: field %d does not travel through the overlapped path", field);
+  const int n = m.nV;
+  const size_t bytes = (size_t)n * (r.is_int ? sizeof(int) : sizeof(double));
+  char *dslot = h->xfer_dev + (size_t)slot * h->xfer_slot_bytes;
+  const bool direct = is_pinned(h, host, bytes);
+  char *hslot = direct ? (char *)host : h->xfer_host + (size_t)slot * h->xfer_slot_bytes;
+  cudaEvent_t ev = h->xfer_ev[slot];
+  if (to_device) {
+    if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
+    if (!direct) memcpy(hslot, host, bytes);
+    UFM_CUDA(cudaMemcpyAsync(dslot, hslot, bytes, cudaMemcpyHostToDevice, h->xfer_stream));
+    UFM_CUDA(cudaEventRecord(ev, h->xfer_stream));
+    UFM_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
+    rc = r.is_int ? ufm_perm_int(h, n, m.aa_ref2dev, r.i, (int *)dslot, 1) : ufm_perm_double(h, n, m.aa_ref2dev, r.d, r.stride, r.comp, (double *)dslot, 1);
+    h->cnt.h2d_bytes += (double)bytes;
+    return rc;
+  }
+  if (r.bits) rc = ufm_perm_mask(h, n, m.aa_ref2dev, r.bits, r.barg, r.bmode, (int *)dslot);
+  else if (r.is_int) rc = ufm_perm_int(h, n, m.aa_ref2dev, r.i, (int *)dslot, 0);
+  else rc = ufm_perm_double(h, n, m.aa_ref2dev, r.d, r.stride, r.comp, (double *)dslot, 0);
+  if (rc) return rc;
+  UFM_CUDA(cudaEventRecord(ev, h->stream));
+  UFM_CUDA(cudaStreamWaitEvent(h->xfer_stream, ev, 0));
+  UFM_CUDA(cudaMemcpyAsync(hslot, dslot, bytes, cudaMemcpyDeviceToHost, h->xfer_stream));
+  if (!direct) h->xfer_pending[h->xfer_n_pending++] = {host, hslot, bytes};
+  h->cnt.d2h_bytes += (double)bytes;
+  return 0;
+}
+// end of a step: every copy has landed; results that went through a pinned slot are handed to the caller's pageable arrays
+static int xfer_finish(ufm_handle *h)
+{
+  UFM_CUDA(cudaStreamSynchronize(h->xfer_stream));
+  for (int k = 0; k < h->xfer_n_pending; k++) memcpy(h->xfer_pending[k].dst, h->xfer_pending[k].src, h->xfer_pending[k].bytes);
+  h->xfer_n_pending = 0;
+  return 0;
+}
+
 static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host)
 {
   NEED_MESH(h);
@@ -487,22 +558,60 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     return ufm_set_error(-4, "ufm_run_model: without a benchmark experiment SMB and BMB come from the host's climate / SMB / BMB models each dt_SMB; use ufm_run_model_host or the step-wise entry points");
   long steps = 0;
   int rc;
+  // drop-in mode: UFM_XFER_OVERLAP=0 falls back to one synchronous copy per field (A/B measurements)
+  bool overlap = false;
+  if (host) {
+    const char *e = getenv("UFM_XFER_OVERLAP");
+    overlap = !e || atoi(e) != 0;
+    if (overlap) {
+      const size_t nb = (size_t)h->mesh.nV * sizeof(double), ni = (size_t)h->mesh.nV * sizeof(int);
+      const struct { const void *p; size_t b; } all[] = {{host->Hi, nb}, {host->Hb, nb}, {host->SL, nb}, {host->dHb_dt, nb}, {host->SMB_year, nb}, {host->BMB, nb},
+          {host->mask_noice, ni}, {host->Hi_out, nb}, {host->Hi_prev, nb}, {host->dHi_dt, nb}, {host->Hs, nb}, {host->U_SSA, nb}, {host->V_SSA, nb},
+          {host->U_SIA, nb}, {host->V_SIA, nb}, {host->D_SIA, nb}, {host->mask, ni}};
+      bool need_host_slots = false;
+      for (auto &q : all) if (q.p && !is_pinned(h, q.p, q.b)) need_host_slots = true;
+      if ((rc = xfer_prepare(h, need_host_slots))) return rc;
+    }
+  }
+  // what leaves the device, and after which stage of the step it is final
+  enum { AFTER_THK = 0, AFTER_GENERAL, AFTER_SIA, AFTER_SSA };
+  struct Out { int f; void *p; int stage; };
+  const Out outs[] = {{UFM_F_HI, host ? host->Hi_out : nullptr, AFTER_THK}, {UFM_F_HI_PREV, host ? host->Hi_prev : nullptr, AFTER_THK},
+                      {UFM_F_DHI_DT, host ? host->dHi_dt : nullptr, AFTER_THK}, {UFM_F_HS, host ? host->Hs : nullptr, AFTER_GENERAL},
+                      {UFM_F_U_SSA, host ? host->U_SSA : nullptr, AFTER_SSA}, {UFM_F_V_SSA, host ? host->V_SSA : nullptr, AFTER_SSA},
+                      {UFM_F_U_SIA, host ? host->U_SIA : nullptr, AFTER_SIA}, {UFM_F_V_SIA, host ? host->V_SIA : nullptr, AFTER_SIA},
+                      {UFM_F_D_SIA, host ? host->D_SIA : nullptr, AFTER_SIA}, {UFM_F_MASK, host ? host->mask : nullptr, AFTER_GENERAL}};
+  const int n_outs = (int)(sizeof(outs) / sizeof(outs[0]));
+  auto start_downloads = [&](int stage) -> int {
+    if (!overlap) return 0;
+    for (int k = 0; k < n_outs; k++)
+      if (outs[k].p && outs[k].stage == stage) { int rc_ = xfer_begin(h, outs[k].f, outs[k].p, 0, 8 + k); if (rc_) return rc_; }
+    return 0;
+  };
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
     r->t0[UFM_T_ELRA] = r->time;  // run_ELRA_model, benchmark branch (bedrock_ELRA_module.f90:35-47)
     if (host) {
       const struct { int f; const void *p; } in[] = {{UFM_F_HI, host->Hi}, {UFM_F_HB, host->Hb}, {UFM_F_SL, host->SL}, {UFM_F_DHB_DT, host->dHb_dt},
                                                      {UFM_F_SMB_YEAR, host->SMB_year}, {UFM_F_BMB, host->BMB}, {UFM_F_MASK_NOICE, host->mask_noice}};
-      for (auto &q : in) if (q.p && (rc = ufm_state_upload(h, q.f, q.p))) return rc;
+      int slot = 0;
+      for (auto &q : in) {
+        if (!q.p) continue;
+        if ((rc = overlap ? xfer_begin(h, q.f, (void *)q.p, 1, slot++) : ufm_state_upload(h, q.f, q.p))) return rc;
+      }
     }
     if ((rc = ufm_thickness_update(h, r->dt))) return rc;
+    if ((rc = start_downloads(AFTER_THK))) return rc;
     if ((rc = ufm_update_general(h, r->time))) return rc;
+    if ((rc = start_downloads(AFTER_GENERAL))) return rc;
     if (r->do_[UFM_T_SIA]) { if ((rc = ufm_solve_SIA(h))) return rc; r->t0[UFM_T_SIA] = r->time; r->n_sia++; }
+    if ((rc = start_downloads(AFTER_SIA))) return rc;
     if (r->do_[UFM_T_SSA]) {
       ufm_ssa_stats st;
       rc = ufm_solve_SSA(h, &st);
       if (rc < 0) return rc;
       r->t0[UFM_T_SSA] = r->time; r->n_ssa++; r->n_sor_total += st.n_inner_total; r->n_outer_total += st.n_outer;
     }
+    if ((rc = start_downloads(AFTER_SSA))) return rc;
     // climate / BMB: no-ops for the dynamics in the benchmark experiments (BMB = 0, src/BMB_module.f90:51-69)
     if (r->do_[UFM_T_CLIMATE]) r->t0[UFM_T_CLIMATE] = r->time;
     if (r->do_[UFM_T_SMB]) {   // run_SMB_model, benchmark branches: closed forms evaluated on the device (no host round trip)
@@ -538,11 +647,10 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     }
     r->time = r->time + r->dt;
     steps++; r->n_steps++;
-    if (host) {
-      const struct { int f; void *p; } out[] = {{UFM_F_HI, host->Hi_out}, {UFM_F_HI_PREV, host->Hi_prev}, {UFM_F_DHI_DT, host->dHi_dt}, {UFM_F_HS, host->Hs},
-                                                {UFM_F_U_SSA, host->U_SSA}, {UFM_F_V_SSA, host->V_SSA}, {UFM_F_U_SIA, host->U_SIA}, {UFM_F_V_SIA, host->V_SIA},
-                                                {UFM_F_D_SIA, host->D_SIA}, {UFM_F_MASK, host->mask}};
-      for (auto &q : out) if (q.p && (rc = ufm_state_download(h, q.f, q.p))) return rc;
+    if (host && overlap) {
+      if ((rc = xfer_finish(h))) return rc;
+    } else if (host) {
+      for (int k = 0; k < n_outs; k++) if (outs[k].p && (rc = ufm_state_download(h, outs[k].f, outs[k].p))) return rc;
     }
   }
   return 0;

@@ -165,6 +165,7 @@ struct CommDev {
 #define CTRL_CFL_KEYS 24
 #define CTRL_THERMO_STATUS 28
 #define CTRL_RN_TICKET 30
+#define UFM_XFER_SLOTS 20
 #define UFM_SOR_CHUNK_DEFAULT 1
 #define UFM_SOR_FUSE_BC_DEFAULT 1
 #define UFM_SOR_BAR_DEFAULT 1
@@ -202,6 +203,14 @@ struct ufm_handle {
   Chunk arena[64] = {};
   int arena_n = 0, arena_cur = 0;
   size_t arena_used = 0, arena_total = 0;
+  // drop-in mode (ufm_run_model_host): per-field device / pinned-host slots and a copy stream, so that the H2D / D2H copies of a
+  // step overlap each other and the SSA solve instead of being serialised with a host synchronisation each
+  cudaStream_t xfer_stream = nullptr;
+  cudaEvent_t xfer_ev[2 * UFM_XFER_SLOTS] = {};
+  char *xfer_dev = nullptr, *xfer_host = nullptr;   // UFM_XFER_SLOTS slots of xfer_slot_bytes each (host slots only if a buffer is not page-locked)
+  size_t xfer_slot_bytes = 0;
+  struct Pending { void *dst; const void *src; size_t bytes; } xfer_pending[UFM_XFER_SLOTS] = {};
+  int xfer_n_pending = 0;
   void *secondary = nullptr;     // ufm_secondary: host arrays derived by ufm_mesh_upload_primary (ufm_mesh_primary.cpp)
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
