@@ -161,4 +161,49 @@ def test_run_model_host_matches_device_resident_run(mesh_2k, monkeypatch, pinned
     assert_bits_equal(hb["Hi"], a.download("Hi"), "Hi after the host changed Hb")
     assert_bits_equal(hb["Hs"], a.download("Hs"), "Hs after the host changed Hb")
     cnt = b.counters()
-    assert cnt.h2d_bytes == 6 * (6 * 8 + 4) * nV and cnt.d2h_bytes == 6 * (9 * 8 + 4) * nV
+    # 5 set-up uploads, then per step 6 double + 1 int fields in, 9 double + 1 int fields out
+    assert cnt.h2d_bytes == (5 * 8 + 6 * (6 * 8 + 4)) * nV and cnt.d2h_bytes == 6 * (9 * 8 + 4) * nV
+
+
+def test_thermodynamics_fields_in_restart_and_help_fields(mesh_2k, tmp_path):
+    """With a thermodynamics mesh Ti is resident: it goes into the restart frame and comes back with ufm_restart_load; the
+    help fields derived from device arrays (Ti_basal = Ti(:,nZ), T2m_year = SUM(T2m,2)/12, src/netcdf_module.f90:348,388)
+    equal the same expressions evaluated on downloads."""
+    from tests.test_gpu_parity import THERMO_IN
+    from ufemism_b200.capi import IceModelGPU
+
+    st = S.state_thermo_dome(mesh_2k, benchmark="none")
+    g = IceModelGPU(mesh_2k, benchmark="none", thermo=True)
+    for f in THERMO_IN:
+        g.upload(f, st[f])
+    g.update_general_ice_model_data(0.0); g.solve_SIA(); g.solve_SSA(); g.update_ice_temperature()
+    fn, hf = str(tmp_path / "restart_GRL_00001.nc"), str(tmp_path / "help_fields_GRL_00001.nc")
+    names = ["Ti", "Ti_basal", "T2m", "T2m_year", "GHF", "W_3D", "A_flow_mean", "U_3D"]
+    R.create_restart(fn, mesh_2k, ZETA, {"TriC": mesh_2k.TriC})
+    R.create_help_fields(hf, mesh_2k, ZETA, names, {"TriC": mesh_2k.TriC})
+    assert g.field_resident("Ti") and g.field_resident("W_3D")
+    firn = np.asfortranarray(np.random.default_rng(3).random((mesh_2k.nV, 12)))
+    assert g.write_restart(fn, 10.0, FirnDepth=firn) == 1
+    assert g.write_help_fields(hf, 10.0, names) == 1
+    Ti, T2m = g.download("Ti"), g.download("T2m")
+    f, h = netcdf_file(fn, "r", mmap=False), netcdf_file(hf, "r", mmap=False)
+    assert_bits_equal(f.variables["Ti"][0], Ti.T, "restart Ti")
+    assert_bits_equal(f.variables["FirnDepth"][0], firn.T, "restart FirnDepth")
+    assert_bits_equal(h.variables["Ti"][0], Ti.T, "Ti")
+    assert_bits_equal(h.variables["Ti_basal"][0], Ti[:, -1], "Ti_basal")
+    t2y = np.zeros(mesh_2k.nV)
+    for m in range(12):                                               # SUM over the month dimension in index order, then / 12
+        t2y = t2y + T2m[:, m]
+    assert_bits_equal(h.variables["T2m_year"][0], t2y / 12.0, "T2m_year")
+    assert_bits_equal(h.variables["T2m"][0], T2m.T, "T2m")
+    assert_bits_equal(h.variables["GHF"][:], g.download("GHF"), "GHF")
+    assert_bits_equal(h.variables["W_3D"][0], g.download("W_3D").T, "W_3D")
+    assert_bits_equal(h.variables["A_flow_mean"][0], g.download("A_flow_mean"), "A_flow_mean")
+    assert np.ptp(Ti) > 1.0 and np.abs(h.variables["W_3D"][0]).max() > 0.0
+    f.close(); h.close()
+    g2 = IceModelGPU(mesh_2k, benchmark="none", thermo=True, primary_only=True)
+    firn2, melt2 = np.zeros((mesh_2k.nV, 12), order="F"), np.zeros(mesh_2k.nV)
+    assert g2._ck(g2.L.ufm_restart_load(g2.h, fn.encode(), 10.0, firn2.ctypes.data, melt2.ctypes.data), allow_warning=True) == 1
+    assert_bits_equal(g2.download("Ti"), Ti, "Ti loaded from the restart file")
+    assert_bits_equal(firn2, firn, "FirnDepth handed to the host")
+    assert (melt2 == np.float64(9.9692099683868690e+36)).all()      # never written: the fill value comes back, as with netcdf-fortran
