@@ -23,8 +23,26 @@
 
 namespace cg = cooperative_groups;
 
-// streaming (read-once) loads: evict-first so that (U,V) stays L2-resident across colour phases
+// streaming (read-once) loads: evict-first so that (U,V) stays L2-resident across colour phases.
+// UFM_LD_STREAM selects the cache policy at build time (tuning builds, tools/build_variant.py): 0 = ld.global.cs (LDG.EF),
+// 1 = L1::no_allocate (LDG.NA), 2 = L1::no_allocate + L2 evict-first policy, 3 = ld.global.cg (L1 bypassed).
+#ifndef UFM_LD_STREAM
+#define UFM_LD_STREAM 0
+#endif
+#if UFM_LD_STREAM == 0
 template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
+#elif UFM_LD_STREAM == 3
+template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcg(p); }
+#elif UFM_LD_STREAM == 1
+__device__ __forceinline__ int ld_stream(const int *p) { int v; asm("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ double ld_stream(const double *p) { double v; asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { double2 v; asm("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; }
+#else
+__device__ __forceinline__ unsigned long long ld_policy() { unsigned long long q; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(q)); return q; }
+__device__ __forceinline__ int ld_stream(const int *p) { int v; asm("ld.global.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(ld_policy())); return v; }
+__device__ __forceinline__ double ld_stream(const double *p) { double v; asm("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(ld_policy())); return v; }
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { double2 v; asm("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(ld_policy())); return v; }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Inter-GPU signalling over NVLink (vertex-partitioned runs).  Every rank owns a mailbox in its own
@@ -1219,6 +1237,17 @@ int ufm_sor_configure(ufm_handle *h)
   h->sor_block = h->sor_tma ? TMA_WARPS * 32 : SOR_BLOCK;
   h->sor_smem = h->sor_tma ? (size_t)TMA_WARPS * TMA_STAGES * TMA_STAGE_BYTES : 0;
   if (h->sor_smem) UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sor_smem));
+  // The streaming kernels keep ~230 B of loads per thread in flight and reuse gathered (U,V) lines: they want the unified
+  // L1 / shared-memory array as L1 (a 120 KB shared-memory carve-out costs the sweep 30 %).  UFM_L1_CARVEOUT
+  // (percent of shared memory, -1 = leave the driver's default) exists for A/B measurements.
+  {
+    const char *e = getenv("UFM_L1_CARVEOUT");
+    const int pct = e ? atoi(e) : 0;
+    if (pct >= 0 && !h->sor_tma) {
+      UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      UFM_CUDA(cudaFuncSetAttribute((const void *)k_ssa_viscosity<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
+  }
   UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, h->sor_smem));
   if (per_sm < 1) return ufm_set_error(-3, "SOR kernel cannot be made resident");
   h->sor_grid = per_sm * h->num_sms;
