@@ -90,6 +90,7 @@ int ufm_destroy(ufm_handle *h)
   cudaStreamSynchronize(h->stream);
   ufm_mesh_free_impl(h);
   ufm_secondary_free(h);
+  ufm_own_release(h);
   ufm_arena_release(h);
   for (int k = 0; k < h->n_pinned; k++) cudaHostUnregister(h->pinned_base[k]);
   for (auto &q : h->stash) if (q.d) { cudaFree(q.d); cudaFree(q.ddx); cudaFree(q.ddy); }

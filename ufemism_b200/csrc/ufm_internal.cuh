@@ -212,6 +212,10 @@ struct ufm_handle {
   struct Pending { void *dst; const void *src; size_t bytes; } xfer_pending[UFM_XFER_SLOTS] = {};
   int xfer_n_pending = 0;
   void *secondary = nullptr;     // ufm_secondary: host arrays derived by ufm_mesh_upload_primary (ufm_mesh_primary.cpp)
+  // the three buffers peers map through CUDA IPC keep allocations of their own (outside the arena); like the arena they survive
+  // ufm_mesh_free and are reused by the next upload when large enough (cudaFree / cudaMalloc cost 0.2 s of a re-upload)
+  struct OwnBuf { void *p = nullptr; size_t bytes = 0; } own_buf[3];
+  double *scal_h_keep = nullptr;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
   void *dev_staging = nullptr;
@@ -221,6 +225,7 @@ struct ufm_handle {
 int ufm_arena_alloc(ufm_handle *h, size_t bytes, void **out);
 void ufm_arena_release(ufm_handle *h);
 void ufm_secondary_free(ufm_handle *h);
+void ufm_own_release(ufm_handle *h);
 int ufm_set_error(int rc, const char *fmt, ...);
 int ufm_cuda_check(cudaError_t e, const char *what);
 #define UFM_CUDA(x) do { int rc__ = ufm_cuda_check((x), #x); if (rc__) return rc__; } while (0)

@@ -203,6 +203,8 @@ extern "C" int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *p)
     fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", "ufm_mesh_upload", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   if (rc) { delete s; return rc; }
   h->secondary = s;
+  if (getenv("UFM_UPLOAD_TIMING"))
+    fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", "total since derive", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return 0;
 }
 

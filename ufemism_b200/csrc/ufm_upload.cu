@@ -31,18 +31,26 @@ int dev_upload(ufm_handle *h, const std::vector<T> &v, T **out)
   return 0;
 }
 template <class T>
-int dev_zeros(ufm_handle *h, size_t n, T **out, bool own_allocation = false)
+int dev_zeros(ufm_handle *h, size_t n, T **out, int own_slot = -1)
 {
   *out = nullptr;
   size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-  if (own_allocation) UFM_CUDA(cudaMalloc((void **)out, bytes));   // buffers exported through CUDA IPC keep an allocation of their own
-  else { int rc = ufm_arena_alloc(h, bytes, (void **)out); if (rc) return rc; }
+  if (own_slot >= 0) {   // buffers exported through CUDA IPC keep an allocation of their own, reused across mesh updates
+    ufm_handle::OwnBuf &b = h->own_buf[own_slot];
+    if (b.bytes < bytes) {
+      if (b.p) cudaFree(b.p);
+      b.p = nullptr; b.bytes = 0;
+      UFM_CUDA(cudaMalloc(&b.p, bytes));
+      b.bytes = bytes;
+    }
+    *out = (T *)b.p;
+  } else { int rc = ufm_arena_alloc(h, bytes, (void **)out); if (rc) return rc; }
   UFM_CUDA(cudaMemset(*out, 0, bytes));
   return 0;
 }
 #define UP(vec, ptr) do { int rc_ = dev_upload(h, vec, &(ptr)); if (rc_) return rc_; } while (0)
 #define ZE(n, ptr) do { int rc_ = dev_zeros(h, (size_t)(n), &(ptr)); if (rc_) return rc_; } while (0)
-#define ZE_OWN(n, ptr) do { int rc_ = dev_zeros(h, (size_t)(n), &(ptr), true); if (rc_) return rc_; } while (0)
+#define ZE_OWN(n, ptr, slot) do { int rc_ = dev_zeros(h, (size_t)(n), &(ptr), slot); if (rc_) return rc_; } while (0)
 
 inline uint32_t part1by1(uint32_t x)
 {
@@ -77,8 +85,6 @@ void build_slices(const std::vector<unsigned char> &deg, std::vector<long long> 
   }
 }
 
-void free_ptr(void *p) { if (p) cudaFree(p); }
-
 }  // namespace
 
 // bump allocator over a few large device chunks (see ufm_handle::arena); 256 B alignment keeps every array 128 B-line aligned
@@ -99,6 +105,12 @@ int ufm_arena_alloc(ufm_handle *h, size_t bytes, void **out)
   h->arena_total += cap;
   *out = p; h->arena_used = bytes;
   return 0;
+}
+void ufm_own_release(ufm_handle *h)
+{
+  for (auto &b : h->own_buf) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  if (h->scal_h_keep) cudaFreeHost(h->scal_h_keep);
+  h->scal_h_keep = nullptr;
 }
 void ufm_arena_release(ufm_handle *h)
 {
@@ -366,8 +378,7 @@ int ufm_mesh_free_impl(ufm_handle *h)
   cudaDeviceSynchronize();   // nothing may still be reading the arrays that are handed back to the arena
   ufm_comm_reset(h);
   DevState &s = h->st;
-  free_ptr(s.UV); free_ptr(s.partials); free_ptr(s.mail);   // own allocations (CUDA IPC)
-  if (s.scal_h) cudaFreeHost(s.scal_h);
+  // s.UV, s.partials, s.mail (CUDA IPC) and the pinned scalars stay allocated in h->own_buf / h->scal_h_keep for the next mesh
   h->arena_cur = 0; h->arena_used = 0;   // every other array lives in the arena, which is kept for the next mesh
   h->mesh = DevMesh();
   h->st = DevState();
@@ -382,7 +393,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   const int N = d->nV, E = d->nAc, M = N + E, W = d->nC_mem;
   const int ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E, ldM = d->ldAaAc ? d->ldAaAc : M;
   if (N < 5 || E < 4 || W < 3 || W > 64) return ufm_set_error(-2, "ufm_mesh_upload: implausible sizes nV=%d nAc=%d nC_mem=%d", N, E, W);
+  const auto t_free0 = std::chrono::steady_clock::now();
   ufm_mesh_free_impl(h);   // also after a failed upload: hands every array back to the arena
+  const double ms_free = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_free0).count();
   // The host-side renumbering below is OpenMP-parallel.  Launchers such as torchrun export OMP_NUM_THREADS=1 for every
   // rank; one rank per GPU still has (cores / ranks) cores to itself, so use them for the duration of the upload.
   struct OmpGuard {
@@ -397,6 +410,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   DevMesh &m = h->mesh;
   m.nV = N; m.nAc = E; m.M = M;
   const bool timing = getenv("UFM_UPLOAD_TIMING") != nullptr;
+  if (timing) fprintf(stderr, "[ufm_mesh_upload] %-28s %8.1f ms\n", "free previous mesh", ms_free);
   auto t_last = std::chrono::steady_clock::now();
   auto lap = [&](const char *what) {
     if (!timing) return;
@@ -844,10 +858,14 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   for (double **p : ac_d) ZE(na, *p);
   for (int k = 0; k < 4; k++) { ZE(na, s.dHi_Ac[k]); ZE(na, s.dHb_Ac[k]); ZE(na, s.dHs_Ac[k]); ZE(na, s.dSL_Ac[k]); ZE(na, s.U_SIA_Ac[k]); ZE(na, s.U_SSA_Ac[k]); }
   ZE(na, s.mbits_Ac);
-  ZE_OWN(nm, s.UV); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
+  lap("state: Aa/Ac arrays");
+  ZE_OWN(nm, s.UV, 0); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
-  ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials); ZE(128, s.ctrl); ZE(64, s.scal); ZE(128, s.red_scratch); ZE_OWN(MAIL_WORDS, s.mail);
-  UFM_CUDA(cudaMallocHost((void **)&s.scal_h, 64 * sizeof(double)));
+  ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials, 1); ZE(128, s.ctrl); ZE(64, s.scal); ZE(128, s.red_scratch); ZE_OWN(MAIL_WORDS, s.mail, 2);
+  lap("state: AaAc arrays, IPC bufs");
+  if (!h->scal_h_keep) UFM_CUDA(cudaMallocHost((void **)&h->scal_h_keep, 64 * sizeof(double)));
+  s.scal_h = h->scal_h_keep;
+  lap("state: pinned scalars");
 
   // staging for permuted upload/download of one field
   size_t need = std::max<size_t>((size_t)M, nv * std::max<size_t>(nz, 12)) * sizeof(double);
@@ -858,7 +876,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     UFM_CUDA(cudaMalloc(&h->dev_staging, need));
     h->staging_bytes = h->dev_staging_bytes = need;
   }
-  lap("state allocation");
+  lap("state: staging");
   h->has_mesh = true;
   // single-GPU view of the peer tables: this rank only
   memset(&h->comm, 0, sizeof(h->comm));
@@ -866,5 +884,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   h->comm.uv[m.rank] = s.UV; h->comm.partials[m.rank] = s.partials; h->comm.mail[m.rank] = s.mail;
   h->comm_connected = false;
   h->cnt.sor_bytes_per_iteration = m.sor_bytes;
-  return ufm_sor_configure(h);
+  const int rc_cfg = ufm_sor_configure(h);
+  lap("SOR configure");
+  return rc_cfg;
 }
