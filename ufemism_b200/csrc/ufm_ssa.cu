@@ -1241,11 +1241,16 @@ int ufm_sor_configure(ufm_handle *h)
   // L1 / shared-memory array as L1 (a 120 KB shared-memory carve-out costs the sweep 30 %).  UFM_L1_CARVEOUT
   // (percent of shared memory, -1 = leave the driver's default) exists for A/B measurements.
   {
-    const char *e = getenv("UFM_L1_CARVEOUT");
-    const int pct = e ? atoi(e) : 0;
-    if (pct >= 0 && !h->sor_tma) {
-      UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-      UFM_CUDA(cudaFuncSetAttribute((const void *)k_ssa_viscosity<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    static const void *done_for = nullptr;   // once per kernel variant: ufm_sor_configure runs before every piecewise SOR call
+    const void *fn = (const void *)pick_sor(h);
+    if (done_for != fn && !h->sor_tma) {
+      const char *e = getenv("UFM_L1_CARVEOUT");
+      const int pct = e ? atoi(e) : 0;
+      if (pct >= 0) {
+        UFM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        UFM_CUDA(cudaFuncSetAttribute((const void *)k_ssa_viscosity<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      }
+      done_for = fn;
     }
   }
   UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, h->sor_smem));
