@@ -18,6 +18,23 @@
 #include <string.h>
 
 /* src/parameters_module.f90:9-21 */
+/* NORM2([x, y]) as gfortran evaluates it: the intrinsic calls libgfortran's _gfortran_norm2_r8 (m4/norm2.m4), a scaled sum of
+ * squares -- not the C library's hypotenuse function, from which it differs in the last bit for about one argument pair in three.
+ * Found by running the reference's own source through oracle/f90py.py (tests/test_reference_source.py). */
+static double ora_norm2_2(double x, double y)
+{
+  double result = 0.0, scale = 1.0;
+  const double v[2] = {x, y};
+  for (int k = 0; k < 2; k++) {
+    if (v[k] != 0.0) {
+      const double absX = fabs(v[k]);
+      if (scale < absX) { const double val = scale / absX; result = 1.0 + result * val * val; scale = absX; }
+      else { const double val = absX / scale; result += val * val; }
+    }
+  }
+  return scale * sqrt(result);
+}
+
 static const double pi = 3.141592653589793;
 static const double sec_per_year = 31556943.36;
 static const double grav = 9.81;
@@ -957,12 +974,12 @@ static void calculate_GL_flux_r(const ora_mesh *m, const rank_t *r, ora_ice *ice
       A1(ice->Qabs_GL_Ac, aci) = factor_Tsai * pow(Hi_GL, n_flow + 2.0) / tan(phi_fric_GL * (pi / 180.0));
       double Fx = -(A1(ice->dHi_dx_Ac, aci) - ((A1(ice->dSL_dx_Ac, aci) - A1(ice->dHb_dx_Ac, aci)) * (seawater_density / ice_density)));
       double Fy = -(A1(ice->dHi_dy_Ac, aci) - ((A1(ice->dSL_dy_Ac, aci) - A1(ice->dHb_dy_Ac, aci)) * (seawater_density / ice_density)));
-      double F = hypot(Fx, Fy); /* NORM2 */
+      double F = ora_norm2_2(Fx, Fy); /* NORM2 */
       Fx = Fx / F; Fy = Fy / F;
       A1(ice->Ux_SSA_Ac, aci) = A1(ice->Qabs_GL_Ac, aci) * Fx / Hi_GL;
       A1(ice->Uy_SSA_Ac, aci) = A1(ice->Qabs_GL_Ac, aci) * Fy / Hi_GL;
       double Dx = A2(m->V, vj, 1, nV) - A2(m->V, vi, 1, nV), Dy = A2(m->V, vj, 2, nV) - A2(m->V, vi, 2, nV);
-      double D = hypot(Dx, Dy);
+      double D = ora_norm2_2(Dx, Dy);
       Dx = Dx / D; Dy = Dy / D;
       A1(ice->Qp_GL_Ac, aci) = A1(ice->Qabs_GL_Ac, aci) * (Dx * Fx + Dy * Fy);
     }
@@ -1321,7 +1338,7 @@ void ora_run_SMB_benchmark(const ora_mesh *m, ora_ice *ice, const ora_config *c,
     else if (b == ORA_BM_EISMINT_5) { if (time < 0.0) { M_max = 0.3; E = 999000.0; } else { M_max = 0.3 + 0.2 * sin(2.0 * pi * time / 20000.0); E = 999000.0; } }
     else if (b == ORA_BM_EISMINT_6) { if (time < 0.0) { M_max = 0.3; E = 999000.0; } else { M_max = 0.3 + 0.2 * sin(2.0 * pi * time / 40000.0); E = 999000.0; } }
     for (int vi = 1; vi <= nV; vi++) {
-      double dist = hypot(A2(m->V, vi, 1, nV), A2(m->V, vi, 2, nV));
+      double dist = ora_norm2_2(A2(m->V, vi, 1, nV), A2(m->V, vi, 2, nV));
       A1(ice->SMB_year, vi) = fmin(M_max, S_b * (E - dist));
     }
   } else if (b == ORA_BM_HALFAR) {
@@ -1332,7 +1349,7 @@ void ora_run_SMB_benchmark(const ora_mesh *m, ora_ice *ice, const ora_config *c,
     for (int vi = 1; vi <= nV; vi++) A1(ice->SMB_year, vi) = 0.3;
   } else if (b == ORA_BM_MESH_GENERATION_TEST) {
     for (int vi = 1; vi <= nV; vi++) {
-      double R = hypot(A2(m->V, vi, 1, nV), A2(m->V, vi, 2, nV));
+      double R = ora_norm2_2(A2(m->V, vi, 1, nV), A2(m->V, vi, 2, nV));
       if (R < 250000.0) A1(ice->SMB_year, vi) = 0.3; else A1(ice->SMB_year, vi) = fmax(-2.0, 0.3 - (R - 250000.0) / 200000.0);
     }
   }

@@ -1,0 +1,41 @@
+"""The cases run through BOTH the translated reference source (tests/ref_source.py, where /root/reference is mounted) and the
+oracle / mesh substrate / CUDA path.  One definition, so that the golden vectors (tests/golden/reference_source_600.npz), the
+live comparison (tests/test_reference_source.py) and the GPU comparison use identical inputs."""
+import numpy as np
+
+SOR_ITERS = 4          # C%SSA_max_inner_loops of the SOR case (the sweep starts far from convergence: all of them run)
+SSA_OUTER = 5          # C%SSA_max_outer_loops of the solve_SSA case
+
+GENERAL_FIELDS = (["mask_land", "mask_ocean", "mask_lake", "mask_ice", "mask_sheet", "mask_shelf", "mask_coast", "mask_margin", "mask_gl", "mask_cf", "mask"] +
+                  [f + "_Ac" for f in ("mask_land", "mask_ocean", "mask_lake", "mask_ice", "mask_sheet", "mask_shelf", "mask_coast", "mask_margin", "mask_gl", "mask_cf", "mask")] +
+                  ["Hs", "dHs_dt", "dHi_dx", "dHi_dy", "dHs_dx", "dHs_dy", "dHs_dx_shelf", "dHs_dy_shelf", "Hi_Ac", "Hb_Ac", "Hs_Ac", "SL_Ac"] +
+                  [f"d{f}_d{c}_Ac" for f in ("Hi", "Hb", "Hs", "SL") for c in "xypo"] +
+                  ["dHs_dx_shelf_Ac", "dHs_dy_shelf_Ac", "A_flow_mean", "A_flow_mean_Ac"])
+THK_FIELDS = ["Hi", "dHi_dt", "Hi_prev", "dVi_in"]
+SIA_FIELDS = ["D_SIA_Ac", "Ux_SIA_Ac", "Uy_SIA_Ac", "Up_SIA_Ac", "Uo_SIA_Ac", "U_SIA", "V_SIA", "D_SIA", "D_SIA_3D_Ac"]
+PIECES_FIELDS = ["tau_c_AaAc", "phi_fric_AaAc", "dU_SSA_dx_AaAc", "dU_SSA_dy_AaAc", "dV_SSA_dx_AaAc", "dV_SSA_dy_AaAc", "eta_AaAc", "N_AaAc", "S_AaAc"]
+SOR_FIELDS = ["RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc", "U_SSA_AaAc", "V_SSA_AaAc", "resU_AaAc", "resV_AaAc"]
+SSA_FIELDS = ["U_SSA", "V_SSA", "Ux_SSA_Ac", "Uy_SSA_Ac", "Up_SSA_Ac", "Uo_SSA_Ac", "eta_AaAc", "N_AaAc", "S_AaAc", "tau_c_AaAc", "Qabs_GL_Ac", "Qp_GL_Ac", "U_SSA_AaAc", "V_SSA_AaAc"]
+MESH_FIELDS = ["A", "Cw", "Nx", "Ny", "Nxx", "Nxy", "Nyy", "NxTri", "NyTri", "Aci", "iAci", "VAc", "Nx_Ac", "Ny_Ac", "Np_Ac", "No_Ac", "edge_index_Ac", "nCAaAc", "CAaAc", "VAaAc",
+               "Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "colour", "colour_vi", "colour_nV"]
+
+
+def golden_mesh():
+    import os
+
+    from ufemism_b200 import mesh as M
+    return M.Mesh.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_600.npz"))
+
+
+def start_state(mesh):
+    """The hybrid SIA/SSA state every case starts from: an ice stream / shelf geometry (grounded sheet, grounding line, floating shelf,
+    ice-free ocean), with the velocities of two model steps of the oracle -- only used as INPUT, identical for both sides."""
+    from ufemism_b200 import scenarios as S
+    st = dict(S.state_ssa_icestream(mesh, scale=750e3 / 1800e3, Hb=-250.0, H_shelf=150.0))
+    st["benchmark"] = "MISMIP_mod"   # a choice_benchmark_experiment the reference itself knows ('SSA_icestream' is accepted by some routines only)
+    return st
+
+
+def random_velocities(mesh):
+    rng = np.random.default_rng(20211103)
+    return rng.normal(0.0, 50.0, mesh.nVAaAc), rng.normal(0.0, 50.0, mesh.nVAaAc)

@@ -1,0 +1,246 @@
+"""The oracle, the mesh substrate and the CUDA path against the REFERENCE'S OWN SOURCE.
+
+The Fortran reference cannot be compiled here, but its source can be read: oracle/f90py.py translates the text of 64 hot-path
+routines (src/ice_dynamics_module.f90, general_ice_model_data_module.f90, mesh_ArakawaC_module.f90, mesh_derivatives_module.f90,
+mesh_five_colour_module.f90, mesh_help_functions_module.f90 (Voronoi cell areas, connection widths), zeta_module.f90, UFEMISM_main_model.f90) statement by statement into
+Python (single MPI rank, IEEE double arithmetic in source order, libm for the transcendental intrinsics) and this module runs them
+on the golden 600-vertex mesh:
+
+* `test_live_*` (only where /root/reference is mounted): translated reference == oracle / mesh substrate, **bit for bit**, for
+  update_general_ice_model_data (all 22 masks, every gradient), calculate_ice_thickness_change, solve_SIA, basal_yield_stress,
+  SSA_effective_viscosity, SSA_sliding_term, the five-colour SOR sweep with its Neumann pass, the whole solve_SSA with the
+  analytical grounding-line flux, the critical time steps, find_Voronoi_cell_areas, find_connection_widths, get_neighbour_functions, make_Ac_mesh (+ the combined AaAc mesh and
+  its neighbour functions) and calculate_five_colouring_AaAc (the SOR order).
+* `test_golden_*` (everywhere): the same comparison against the committed outputs of the translated reference
+  (tests/golden/reference_source_600.npz, written by tests/golden/make_reference_source_golden.py), so the pin travels to machines
+  without the reference -- including the B200 box, where `test_gpu_matches_reference_source` holds the CUDA path to them.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests import ref_cases as RC
+from tests import ref_source as RS
+from tests.util import assert_bits_equal, make_oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_source_600.npz")
+
+
+def _arr(x):
+    from oracle import f90py as F
+    return x.a if isinstance(x, F.FArray) else np.asarray(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the cases, once for the translated reference source ...
+# ---------------------------------------------------------------------------------------------------------------------------
+def run_reference_source(mesh):
+    """Every case through the translated reference; returns {case__field: array}."""
+    from oracle import f90py as F
+
+    np.seterr(all="ignore")
+    st = RC.start_state(mesh)
+    o = make_oracle(mesh, st, nthreads=1, use_analytical_GL_flux=1)   # only a container of correctly shaped, zeroed reference arrays
+    P = RS.program(o.cfg)
+    P.C.choice_benchmark_experiment = st["benchmark"]
+    out = {}
+
+    def grab(case, ns, fields):
+        for f in fields:
+            out[f"{case}__{f}"] = np.array(_arr(getattr(ns, f)))
+
+    # mesh operators from the primary mesh data
+    mm = RS.mesh_ns(mesh)
+    for f in ("nx", "ny", "nxx", "nxy", "nyy", "nxtri", "nytri"):
+        getattr(mm, f).a[...] = -7.0
+    mm.a.a[...] = -7.0; mm.cw.a[...] = 0.0
+    P.find_voronoi_cell_areas(mm)
+    P.find_connection_widths(mm)            # the reference leaves Cw beyond nC(vi) untouched: compared as zeros on both sides
+    P.get_neighbour_functions(mm)
+    P.make_ac_mesh(mm)                      # includes find_Ac_edge_indices and make_combined_AaAc_mesh with its neighbour functions
+    P.calculate_five_colouring_aaac(mm)
+    nAc = int(mm.nac)
+    assert nAc == mesh.nAc
+    for f in RC.MESH_FIELDS:
+        a = np.array(_arr(getattr(mm, f)))
+        want = np.asarray(getattr(mesh, f)).shape
+        out[f"mesh__{f}"] = a[: want[0]] if a.ndim >= 1 and a.shape[0] > want[0] else a
+    # geometry, masks, gradients
+    mref = RS.mesh_ns(mesh)
+    ice = RS.ice_ns(o)
+    P.update_general_ice_model_data(mref, ice, np.float64(0.0))
+    grab("general", ice, RC.GENERAL_FIELDS)
+    # SIA
+    P.solve_sia(mref, ice)
+    grab("sia", ice, RC.SIA_FIELDS)
+    # pieces of solve_SSA from prescribed velocities
+    U, V = RC.random_velocities(mesh)
+    P.basal_yield_stress(mref, ice)
+    _gather_aaac(mesh, ice)
+    ice.u_ssa_aaac.a[:] = U; ice.v_ssa_aaac.a[:] = V
+    P.ssa_effective_viscosity(mref, ice)
+    P.ssa_sliding_term(mref, ice)
+    grab("pieces", ice, RC.PIECES_FIELDS)
+    # SOR: SOR_ITERS sweeps incl. the Neumann pass
+    P.C.ssa_max_inner_loops = RC.SOR_ITERS
+    P.solve_ssa_linearised(mref, ice, False)
+    grab("sor", ice, RC.SOR_FIELDS)
+    P.C.ssa_max_inner_loops = 10000
+    # the whole solve_SSA (analytical GL flux on), a few viscosity iterations, from rest
+    ice2 = RS.ice_ns(o)
+    P.update_general_ice_model_data(mref, ice2, np.float64(0.0))
+    P.solve_sia(mref, ice2)
+    P.C.ssa_max_outer_loops = RC.SSA_OUTER
+    P.solve_ssa(mref, ice2)
+    P.C.ssa_max_outer_loops = 50
+    grab("ssa", ice2, RC.SSA_FIELDS)
+    # mass continuity with those velocities, then the critical time steps
+    smb, bmb = F.NS(smb_year=np.array(st["SMB_year"])), F.NS(bmb=np.array(st["BMB"]))
+    P.calculate_ice_thickness_change(mref, ice2, smb, bmb, np.float64(0.5), np.zeros(mesh.nV, np.int32))
+    grab("thk", ice2, RC.THK_FIELDS)
+    P.C.dt_max, P.C.dt_thermo, P.C.dt_climate, P.C.dt_smb, P.C.dt_bmb, P.C.dt_bedrock_elra, P.C.dt_output = (np.float64(1e9),) * 7
+    region = F.NS(mesh=mref, ice=ice2, time=np.float64(0.0), dt=np.float64(0.0), dt_prev=np.float64(1.0))
+    for t in ("sia", "ssa", "thermo", "climate", "smb", "bmb", "elra", "output"):
+        setattr(region, "t0_" + t, np.float64(0.0))
+    P.determine_timesteps_and_actions(region, np.float64(1e12))
+    out["cfl__dt_SIA_dt_SSA"] = np.array([region.dt_sia, region.dt_ssa])
+    return out
+
+
+def _gather_aaac(mesh, ice):
+    """The inline gather of solve_SSA (src/ice_dynamics_module.f90:468-496): Aa and Ac fields side by side on the combined mesh."""
+    nV = mesh.nV
+    for f in ("Hi", "Hb", "SL", "dHs_dx_shelf", "dHs_dy_shelf", "A_flow_mean"):
+        getattr(ice, f + "_AaAc").a[:nV] = getattr(ice, f).a
+        getattr(ice, f + "_AaAc").a[nV:] = getattr(ice, f + "_Ac").a
+
+
+# ... and once for the oracle + mesh substrate
+def run_oracle(mesh):
+    from ufemism_b200 import mesh as M
+
+    st = RC.start_state(mesh)
+    out = {}
+    fresh = M.build_mesh(np.array(mesh.V), mesh.xmin, mesh.xmax, mesh.ymin, mesh.ymax)   # the substrate, from the primary data again
+    assert np.array_equal(fresh.Tri, mesh.Tri)
+    for f in RC.MESH_FIELDS:
+        out[f"mesh__{f}"] = np.asarray(getattr(fresh, f))
+    out["mesh__Cw"] = np.where(np.arange(mesh.nC_mem)[None, :] < fresh.nC[:, None], fresh.Cw, 0.0)
+
+    def grab(case, o, fields):
+        for f in fields:
+            out[f"{case}__{f}"] = o[f].copy()
+
+    o = make_oracle(mesh, st, nthreads=1, use_analytical_GL_flux=1)
+    o.update_general_ice_model_data(0.0)
+    grab("general", o, RC.GENERAL_FIELDS)
+    o.solve_SIA()
+    grab("sia", o, RC.SIA_FIELDS)
+    U, V = RC.random_velocities(mesh)
+    o.basal_yield_stress(); o.SSA_gather_AaAc()
+    o["U_SSA_AaAc"][:] = U; o["V_SSA_AaAc"][:] = V
+    o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    grab("pieces", o, RC.PIECES_FIELDS)
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=RC.SOR_ITERS)
+    assert n == RC.SOR_ITERS
+    grab("sor", o, RC.SOR_FIELDS)
+    o2 = make_oracle(mesh, st, nthreads=1, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER)
+    o2.update_general_ice_model_data(0.0); o2.solve_SIA()
+    s = o2.solve_SSA()
+    assert s.n_outer == RC.SSA_OUTER
+    grab("ssa", o2, RC.SSA_FIELDS)
+    o2.calculate_ice_thickness_change(0.5)
+    grab("thk", o2, RC.THK_FIELDS)
+    d = o2.determine_timesteps()
+    out["cfl__dt_SIA_dt_SSA"] = np.array([min(d[0], d[2]), d[1]])
+    return out
+
+
+def _compare(got, want, keys=None):
+    bad = []
+    for k in sorted(keys or want):
+        try:
+            assert_bits_equal(np.asarray(got[k]), np.asarray(want[k]), k)
+        except AssertionError as e:
+            bad.append(str(e))
+    assert not bad, "\n".join(bad)
+
+
+@pytest.fixture(scope="module")
+def oracle_out():
+    return run_oracle(RC.golden_mesh())
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(GOLDEN)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here; the golden vectors stand in (test_golden_*)")
+def test_live_translated_reference_source_equals_oracle_and_golden(oracle_out, golden):
+    ref = run_reference_source(RC.golden_mesh())
+    assert len(ref) >= 120
+    _compare(oracle_out, ref)                               # every output of every routine, bit for bit
+    for k, a in ref.items():                                # and the committed golden file is what the reference source gives today
+        assert str(golden["sha256__" + k]) == hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest(), k
+    # the cases are not trivial
+    assert np.abs(ref["ssa__U_SSA"]).max() > 10.0 and np.abs(ref["sor__resU_AaAc"]).max() > 1.0 and ref["general__mask_shelf"].sum() > 50
+    assert ref["general__mask_gl"].sum() > 10 and np.abs(ref["thk__dHi_dt"]).max() > 0.1 and np.abs(ref["ssa__Qabs_GL_Ac"]).max() > 0.0
+
+
+def test_golden_reference_source_vectors_pin_the_oracle_and_the_mesh_substrate(oracle_out, golden):
+    names = [k[len("sha256__"):] for k in golden if k.startswith("sha256__")]
+    assert len(names) >= 120 and set(names) == set(oracle_out)
+    for k in names:
+        a = np.ascontiguousarray(oracle_out[k])
+        assert str(golden["sha256__" + k]) == hashlib.sha256(a.tobytes()).hexdigest(), f"{k}: the oracle no longer reproduces the reference source"
+    _compare(oracle_out, golden, [k for k in golden if not k.startswith("sha256__")])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_source(golden):
+    """The CUDA path against the outputs of the translated reference source: bit-exact wherever only + - * / sqrt are involved
+    (geometry, masks, gradients, thickness update, SOR sweeps at a prescribed count), <= 1e-13 behind one pow / tan."""
+    from tests.util import make_gpu
+
+    mesh = RC.golden_mesh()
+    st = RC.start_state(mesh)
+    g = make_gpu(mesh, st, use_analytical_GL_flux=1)
+    g.update_general_ice_model_data(0.0)
+    for f in RC.GENERAL_FIELDS:
+        assert_bits_equal(g.download(f), golden["general__" + f], f)
+    g.solve_SIA()
+    for f in ("D_SIA_Ac", "Up_SIA_Ac", "U_SIA", "V_SIA", "D_SIA"):
+        np.testing.assert_allclose(g.download(f), golden["sia__" + f], rtol=1e-13, atol=1e-13 * np.abs(golden["sia__" + f]).max(), err_msg=f)
+    U, V = RC.random_velocities(mesh)
+    g.ssa_prepare()
+    np.testing.assert_allclose(g.download("tau_c_AaAc"), golden["pieces__tau_c_AaAc"], rtol=1e-13)
+    g.upload("tau_c_AaAc", golden["pieces__tau_c_AaAc"])
+    g.upload("U_SSA_AaAc", U); g.upload("V_SSA_AaAc", V)
+    g.ssa_viscosity()
+    np.testing.assert_allclose(g.download("eta_AaAc"), golden["pieces__eta_AaAc"], rtol=1e-13)
+    assert_bits_equal(g.download("dU_SSA_dx_AaAc"), golden["pieces__dU_SSA_dx_AaAc"], "dU_SSA_dx_AaAc")
+    g.upload("eta_AaAc", golden["pieces__eta_AaAc"])
+    g.ssa_sliding_and_setup()
+    np.testing.assert_allclose(g.download("S_AaAc"), golden["pieces__S_AaAc"], rtol=1e-13)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):     # identical linear system -> the sweep itself must give the reference's bits
+        g.upload(f, golden["sor__" + f])
+    s = g.ssa_sor(max_inner=RC.SOR_ITERS)
+    assert s.n_inner_last == RC.SOR_ITERS
+    assert_bits_equal(g.download("U_SSA_AaAc"), golden["sor__U_SSA_AaAc"], "U_SSA_AaAc after the reference's SOR sweeps")
+    assert_bits_equal(g.download("V_SSA_AaAc"), golden["sor__V_SSA_AaAc"], "V_SSA_AaAc after the reference's SOR sweeps")
+    # whole solve_SSA, then mass continuity and the critical time steps
+    g2 = make_gpu(mesh, st, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER)
+    g2.update_general_ice_model_data(0.0); g2.solve_SIA()
+    s = g2.solve_SSA()
+    assert s.n_outer == RC.SSA_OUTER
+    for f in ("U_SSA", "V_SSA", "Up_SSA_Ac", "Qabs_GL_Ac"):
+        a, b = g2.download(f), golden["ssa__" + f]
+        assert np.linalg.norm(a - b) <= 1e-10 * np.linalg.norm(b), f
+    g2.calculate_ice_thickness_change(0.5)
+    for f in ("Hi", "dHi_dt"):
+        a, b = g2.download(f), golden["thk__" + f]
+        assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max(), f

@@ -120,6 +120,22 @@ static void circumcentre(const double *p, const double *q, const double *r, doub
   cc[1] = ay + (bx * c2 - cx * b2) / d;
 }
 
+/* NORM2 of a 2-vector as gfortran evaluates it: libgfortran's _gfortran_norm2_r8 (m4/norm2.m4), a scaled sum of squares; differs
+ * from sqrt(x*x + y*y) in the last bit for about one pair in three (tests/test_reference_source.py) */
+static double norm2_2(double x, double y)
+{
+  double result = 0.0, scale = 1.0;
+  const double v[2] = {x, y};
+  for (int k = 0; k < 2; k++) {
+    if (v[k] != 0.0) {
+      const double absX = fabs(v[k]);
+      if (scale < absX) { const double val = scale / absX; result = 1.0 + result * val * val; scale = absX; }
+      else { const double val = absX / scale; result += val * val; }
+    }
+  }
+  return scale * sqrt(result);
+}
+
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *Tri,
@@ -198,7 +214,7 @@ int ufm_mesh_geometry(int nV, int nTri, int nC_mem, const double *V, const int *
       double w;
       if (t2) {
         double dx = I2(Tricc, t1, 1, nTri) - I2(Tricc, t2, 1, nTri), dy = I2(Tricc, t1, 2, nTri) - I2(Tricc, t2, 2, nTri);
-        w = sqrt(dx * dx + dy * dy);
+        w = norm2_2(dx, dy);   /* norm2(mesh%Tricc(t1,:) - mesh%Tricc(t2,:)) */
       } else {
         int tei = Tri_edge_index[t1 - 1];
         if (tei == 1) w = fmax(0.0, ymax - I2(Tricc, t1, 2, nTri));

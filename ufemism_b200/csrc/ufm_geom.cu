@@ -683,14 +683,14 @@ __global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const 
   const double2 p = xy[v];
   double out;
   if (a.mode == 0) out = a.value;
-  else if (a.mode == 1) out = fmin(a.M_max, a.S_b * (a.E - hypot(p.x, p.y)));   // dist = NORM2( mesh%V( vi,:))
+  else if (a.mode == 1) out = fmin(a.M_max, a.S_b * (a.E - ufm_norm2_2(p.x, p.y)));   // dist = NORM2( mesh%V( vi,:))
   else if (a.mode == 2) {
     const double f3 = sqrt((p.x * p.x) + (p.y * p.y)) / a.R0;                     // x**2._dp: pow( x, 2) is exactly x*x
     const double f4 = fmax(0.0, 1.0 - pow(a.f2 * f3, 4.0 / 3.0));
     const double H = a.H0f1 * pow(f4, 3.0 / 7.0);
     out = a.lam_tp_spy * H * UFM_SEC_PER_YEAR;
   } else {
-    const double R = hypot(p.x, p.y);
+    const double R = ufm_norm2_2(p.x, p.y);
     out = R < 250000.0 ? 0.3 : fmax(-2.0, 0.3 - (R - 250000.0) / 200000.0);
   }
   SMB_year[v] = out;

@@ -41,6 +41,25 @@
 enum { MB_LAND = 1, MB_OCEAN = 2, MB_LAKE = 4, MB_ICE = 8, MB_SHEET = 16, MB_SHELF = 32, MB_COAST = 64, MB_MARGIN = 128,
        MB_GL = 256, MB_CF = 512, MB_CODE_SHIFT = 12 };
 
+// NORM2([x, y]) as gfortran evaluates it: libgfortran's _gfortran_norm2_r8 (m4/norm2.m4), a scaled sum of squares, NOT the
+// hypotenuse function of libm / CUDA.  Every operation is an IEEE + * / sqrt, so device and host give the reference's bits
+// (the library is built with -fmad=false).
+__host__ __device__ __forceinline__ double ufm_norm2_2(const double x, const double y)
+{
+  double result = 0.0, scale = 1.0;
+  if (x != 0.0) {
+    const double a = fabs(x);
+    if (scale < a) { const double val = scale / a; result = 1.0 + result * val * val; scale = a; }
+    else { const double val = a / scale; result += val * val; }
+  }
+  if (y != 0.0) {
+    const double a = fabs(y);
+    if (scale < a) { const double val = scale / a; result = 1.0 + result * val * val; scale = a; }
+    else { const double val = a / scale; result += val * val; }
+  }
+  return scale * sqrt(result);
+}
+
 struct SlicedEll {
   int n_rows = 0;            // padded to a multiple of 32
   int n_slices = 0;

@@ -174,12 +174,12 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
   Qabs[a] = q;
   double Fx = -(dHi_dx[a] - ((dSL_dx[a] - dHb_dx[a]) * rr));
   double Fy = -(dHi_dy[a] - ((dSL_dy[a] - dHb_dy[a]) * rr));
-  double F = hypot(Fx, Fy);
+  double F = ufm_norm2_2(Fx, Fy);
   Fx = Fx / F; Fy = Fy / F;
   const double ux = q * Fx / Hi_GL, uy = q * Fy / Hi_GL;
   Ux[a] = ux; Uy[a] = uy;
   UV[ac2m[a]] = make_double2(ux, uy);  // the gather of :494-495 happens after calculate_GL_flux in the reference
-  double Dx = Dx_[a], Dy = Dy_[a], D = hypot(Dx, Dy);
+  double Dx = Dx_[a], Dy = Dy_[a], D = ufm_norm2_2(Dx, Dy);
   Dx = Dx / D; Dy = Dy / D;
   Qp[a] = q * (Dx * Fx + Dy * Fy);
 }
