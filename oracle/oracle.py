@@ -1,4 +1,4 @@
-"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- see ufm_oracle.h, "PARITY UNPINNED").
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- see ufm_oracle.h, "PARITY PIN").
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
 import this module.  The ctypes structures are generated from the X-macro field lists in

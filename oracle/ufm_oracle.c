@@ -1,5 +1,5 @@
 /*
- * ufm_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See ufm_oracle.h ("PARITY UNPINNED").
+ * ufm_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See ufm_oracle.h ("PARITY PIN").
  *
  * Statement-by-statement CPU restatement of the UFEMISM v1.1.1 ice-dynamics hot path.
  * "Ranks" of the reference's MPI shared-memory SPMD model are OpenMP threads here: every

@@ -4,15 +4,25 @@
  * CPU restatement ("oracle") of the UFEMISM v1.1.1 ice-dynamics hot path.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY UNPINNED: the reference is Fortran 90 + MPI + NetCDF; this image has no Fortran
- * compiler, MPI or NetCDF, and the reference ships no tests, fixtures or golden vectors
- * (SURVEY.md section 0.2-0.3, 8c).  The oracle is therefore pinned only by (a) following the
- * Fortran statement by statement (file:line cited at every function), (b) model runs against the two
- * analytic solutions hard-coded in the reference (Halfar, Bueler: src/reference_fields_module.f90:707-795,
- * src/SMB_module.f90:240-283) and against two closed-form steady states of the heat equation (pure
- * conduction; the Robin profile the reference codes in replace_Ti_with_robin_solution), and (c) for the one
- * third-party routine on the path, LAPACK DGTSV, a bit-for-bit comparison with scipy's bundled LAPACK;
- * all in tests/test_oracle.py.
+ * PARITY PIN -- what it is and what it is not.  The reference is Fortran 90 + MPI + NetCDF; this image has no Fortran compiler,
+ * MPI or NetCDF, and the reference ships no tests, fixtures or golden vectors: there is no
+ * reference BUILD to compare with and, by the letter of the task statement, the oracle is "parity unpinned".  It is pinned as
+ * far as this environment allows:
+ *  (a) to the REFERENCE'S OWN SOURCE TEXT: oracle/f90py.py translates 64 routines of /root/reference/src (the SOR sweep, the whole
+ *      solve_SSA with the grounding-line flux, masks, gradients, SIA, thickness update, critical time steps, neighbour functions,
+ *      Ac / AaAc mesh construction, five-colouring, Voronoi areas, connection widths) statement by statement into Python and runs
+ *      them on the golden mesh; the oracle and the mesh substrate agree with them BIT FOR BIT (tests/test_reference_source.py), and
+ *      their outputs are committed as golden vectors (tests/golden/reference_source_600.npz) so that the pin also holds on machines
+ *      without the reference, incl. the B200 box, where the CUDA path is compared with them.  This check found -- and this file
+ *      now has fixed -- one discrepancy: gfortran's NORM2 is libgfortran's scaled sum of squares, not hypot();
+ *  (b) by following the Fortran statement by statement (file:line cited at every function);
+ *  (c) by model runs against the two analytic solutions hard-coded in the reference (Halfar, Bueler:
+ *      src/reference_fields_module.f90:707-795, src/SMB_module.f90:240-283) and against two closed-form steady states of the heat
+ *      equation (pure conduction; the Robin profile the reference codes in replace_Ti_with_robin_solution);
+ *  (d) for the one third-party routine on the path, LAPACK DGTSV, by a bit-for-bit comparison with scipy's bundled LAPACK
+ *      (tests/test_oracle.py).
+ * Not covered by (a): thermodynamics (update_ice_temperature; pinned by (b)-(d)) and what a translation cannot show -- code
+ * generation choices of gfortran itself (assumed: -O3 without -ffast-math, no FMA contraction, libm pow / tan / exp).
  *
  * Layout = the reference's: column-major, 1-based indices stored in the integer arrays, padded
  * ELL rows (width nC_mem for connectivity, nC_mem+1 for neighbour functions).
