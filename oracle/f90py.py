@@ -48,10 +48,11 @@ class S:
 
 class FArray:
     """1-based view of a numpy array with Fortran subscripts.  Element access returns numpy scalars (IEEE semantics)."""
-    __slots__ = ("a",)
+    __slots__ = ("a", "lb")
 
-    def __init__(self, a):
+    def __init__(self, a, lb=None):
         self.a = a
+        self.lb = tuple(lb) if lb is not None else (1,) * a.ndim   # lower bounds (DIMENSION(2:n) etc.)
 
     def _key(self, k):
         if not isinstance(k, tuple):
@@ -59,18 +60,18 @@ class FArray:
         if len(k) != self.a.ndim:
             raise IndexError(f"rank mismatch: {len(k)} subscripts for a rank-{self.a.ndim} array")
         out = []
-        for q, n in zip(k, self.a.shape):
+        for q, n, b in zip(k, self.a.shape, self.lb):
             if isinstance(q, S):
-                lo = 1 if q.lo is None else int(q.lo)
-                hi = n if q.hi is None else int(q.hi)
-                if lo < 1 or hi > n:
-                    raise IndexError(f"section {lo}:{hi} outside 1:{n}")
-                out.append(slice(lo - 1, hi))
+                lo = b if q.lo is None else int(q.lo)
+                hi = b + n - 1 if q.hi is None else int(q.hi)
+                if lo < b or hi > b + n - 1:
+                    raise IndexError(f"section {lo}:{hi} outside {b}:{b + n - 1}")
+                out.append(slice(lo - b, hi - b + 1))
             else:
                 q = int(q)
-                if q < 1 or q > n:
-                    raise IndexError(f"subscript {q} outside 1:{n} (the reference is built with -fbounds-check)")
-                out.append(q - 1)
+                if q < b or q > b + n - 1:
+                    raise IndexError(f"subscript {q} outside {b}:{b + n - 1} (the reference is built with -fbounds-check)")
+                out.append(q - b)
         return tuple(out)
 
     def __getitem__(self, k):
@@ -214,6 +215,16 @@ def _sign(a, b):
     return abs(a) if b >= 0 else -abs(a)
 
 
+def _minmax(elementwise, scalar, args):
+    args = [_unwrap(x) for x in args]
+    if any(isinstance(x, np.ndarray) for x in args):   # MAX / MIN are elemental
+        r = args[0]
+        for x in args[1:]:
+            r = elementwise(r, x)
+        return r
+    return scalar(args)
+
+
 def _libm(fn):
     def f(x):
         x = _unwrap(x)
@@ -230,7 +241,27 @@ def _libm(fn):
 
 
 def _wrap(x):
-    return FArray(x) if isinstance(x, np.ndarray) else x
+    """an actual argument as the dummy sees it: Fortran subscripts from 1 (explicit- and assumed-shape dummies do not inherit bounds)"""
+    if isinstance(x, np.ndarray):
+        return FArray(x)
+    if isinstance(x, FArray) and any(b != 1 for b in x.lb):
+        return FArray(x.a)
+    return x
+
+
+def _alloc(dtype, *bounds):
+    """zero array with the given extents; a bound is an extent n (1:n) or a pair (lo, hi)"""
+    lb = [b[0] if isinstance(b, tuple) else 1 for b in bounds]
+    shape = [int(b[1]) - int(b[0]) + 1 if isinstance(b, tuple) else int(b) for b in bounds]
+    return FArray(np.zeros(tuple(max(n, 0) for n in shape), dtype=dtype, order="F"), [int(q) for q in lb])
+
+
+def _dgtsv(dl, d, du, b):
+    """CALL DGTSV( n, 1, dl, d, du, b, ldb, info) through a real LAPACK (scipy's); arrays are overwritten as LAPACK does"""
+    from scipy.linalg import lapack
+    du2, d2, du3, x, info = lapack.dgtsv(np.array(_unwrap(dl)), np.array(_unwrap(d)), np.array(_unwrap(du)), np.array(_unwrap(b)))
+    _unwrap(b)[...] = x
+    return int(info)
 
 
 def _setc(obj, name, value):
@@ -244,13 +275,13 @@ def _setc(obj, name, value):
 
 
 _RT = {
-    "_wrap": _wrap, "_setc": _setc, "_S": S, "_FA": FArray, "_sp": _sp, "_div": _div, "_pow": _pow, "_sum": _sum, "_norm2": _norm2, "_do": _do_range, "_np": np,
+    "_wrap": _wrap, "_setc": _setc, "_alloc": _alloc, "_dgtsv": _dgtsv, "_S": S, "_FA": FArray, "_sp": _sp, "_div": _div, "_pow": _pow, "_sum": _sum, "_norm2": _norm2, "_do": _do_range, "_np": np,
     "abs": lambda x: np.abs(_unwrap(x)) if isinstance(_unwrap(x), np.ndarray) else abs(x), "sqrt": lambda x: np.sqrt(_unwrap(x)),
     # transcendental intrinsics go through libm (what gfortran calls), element by element -- numpy's own vectorised versions may
     # differ from libm in the last bit
     "exp": _libm(math.exp), "log": _libm(math.log), "tan": _libm(math.tan), "atan": _libm(math.atan), "sin": _libm(math.sin), "cos": _libm(math.cos),
     "asin": _libm(math.asin), "acos": _libm(math.acos), "atan2": lambda a, b: np.float64(math.atan2(a, b)),
-    "max": lambda *a: max(a), "min": lambda *a: min(a), "real": _real, "dble": _real, "int": lambda x, k=None: int(x), "nint": lambda x: int(round(float(x))),
+    "max": lambda *a: _minmax(np.maximum, max, a), "min": lambda *a: _minmax(np.minimum, min, a), "real": _real, "dble": _real, "int": lambda x, k=None: int(x), "nint": lambda x: int(round(float(x))),
     "sum": _sum, "maxval": lambda x: np.max(np.asarray(x)), "minval": lambda x: np.min(np.asarray(x)), "norm2": _norm2,
     "size": lambda x, d=None: np.asarray(x).size if d is None else np.asarray(x).shape[int(d) - 1],
     "mod": lambda a, b: math.fmod(a, b) if isinstance(a, (float, np.floating)) else int(math.fmod(a, b)), "sign": _sign,
@@ -258,7 +289,7 @@ _RT = {
     "erf": lambda x: np.float64(math.erf(x)), "floor": lambda x: int(math.floor(x)), "ceiling": lambda x: int(math.ceil(x)),
     "trim": lambda x: x.rstrip(), "len_trim": lambda x: len(x.rstrip()), "present": lambda x: x is not None, "huge": lambda x: np.float64(np.finfo(np.float64).max),
 }
-_INTRINSICS = set(_RT) - {"_wrap", "_setc", "_S", "_FA", "_sp", "_div", "_pow", "_sum", "_norm2", "_do", "_np"}
+_INTRINSICS = set(_RT) - {"_wrap", "_setc", "_alloc", "_dgtsv", "_S", "_FA", "_sp", "_div", "_pow", "_sum", "_norm2", "_do", "_np"}
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -668,6 +699,17 @@ class Unit:
     def ex(self, s):
         return translate_expr(s, self.ctx)
 
+    def bounds(self, dims):
+        """'2:C%NZ, 3' -> '(2, c.nz), 3' for _alloc"""
+        out = []
+        for q in _split_top(dims):
+            parts = _split_top(q, ":")
+            if len(parts) == 2 and ":" in q:
+                out.append(f"({self.ex(parts[0])}, {self.ex(parts[1])})")
+            else:
+                out.append(self.ex(q))
+        return ", ".join(out)
+
     def outs(self):
         """scalar dummies the caller must receive back"""
         r = []
@@ -736,6 +778,9 @@ class Unit:
             else:
                 dims = ", ".join(f"int({self.ex(a)})" for a in args[:nd])
                 self.emit(depth, f"{tgt} = _FA(_np.zeros(({dims},), dtype={dt}, order='F'))")
+            return
+        if name == "dgtsv":   # ( n, nrhs, dl, d, du, b, ldb, info)
+            self.emit(depth, f"{self.ex(args[7])} = _dgtsv({self.ex(args[2])}, {self.ex(args[3])}, {self.ex(args[4])}, {self.ex(args[5])})")
             return
         if name == "mpi_abort":
             self.emit(depth, "raise RuntimeError('MPI_ABORT')")
@@ -820,11 +865,16 @@ class Unit:
         if u.startswith("ALLOCATE"):
             inner = st[st.index("(") + 1:_matching_paren(st, st.index("("))]
             for ent in _split_top(inner):
-                m2 = re.match(r"^(\w+)\s*\((.*)\)$", ent.strip())
-                name = m2.group(1).lower()
-                dims = ", ".join(f"int({self.ex(d)})" for d in _split_top(m2.group(2)))
-                dt = "_np.int32" if self.decl[name]["type"].startswith("integer") or self.decl[name]["type"].startswith("logical") else "_np.float64"
-                self.emit(depth, f"{self.ctx.rename(name)} = _FA(_np.zeros(({dims},), dtype={dt}, order='F'))")
+                ent = ent.strip()
+                j = ent.rindex("(")
+                target, dims = ent[:j].strip(), ent[j + 1:-1]
+                name = target.lower()
+                if "%" in target:       # a component: its type is not known here; the hot path only allocates REAL(dp) components
+                    parent, last = self.ex(target).rsplit(".", 1)
+                    self.emit(depth, f"setattr({parent}, {last!r}, _alloc(_np.float64, {self.bounds(dims)}))")
+                else:
+                    dt = "_np.int32" if self.decl[name]["type"].startswith("integer") or self.decl[name]["type"].startswith("logical") else "_np.float64"
+                    self.emit(depth, f"{self.ctx.rename(name)} = _alloc({dt}, {self.bounds(dims)})")
             return depth
         if u.startswith("DEALLOCATE") or u.startswith("NULLIFY"):
             self.emit(depth, "pass")
@@ -853,10 +903,10 @@ class Unit:
                 if d["dims"] is not None:   # an actual argument may be an array expression or a section (numpy): give it Fortran subscripts
                     self.emit(1, f"{self.ctx.rename(name)} = _wrap({self.ctx.rename(name)})")
                 continue
-            if d["dims"] is not None and not d["allocatable"] and ":" not in d["dims"]:
-                dims = ", ".join(f"int({self.ex(q)})" for q in _split_top(d["dims"]))
+            deferred = d["dims"] is not None and any(q.strip() == ":" for q in _split_top(d["dims"]))
+            if d["dims"] is not None and not d["allocatable"] and not deferred:
                 dt = "_np.float64" if d["type"].startswith("real") else "_np.int32"
-                self.emit(1, f"{self.ctx.rename(name)} = _FA(_np.zeros(({dims},), dtype={dt}, order='F'))")
+                self.emit(1, f"{self.ctx.rename(name)} = _alloc({dt}, {self.bounds(d['dims'])})")
                 if d.get("init"):
                     self.emit(1, f"{self.ctx.rename(name)}.fill({self.ex(d['init'])})")
             elif d["dims"] is None and d.get("init") is not None:

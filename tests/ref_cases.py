@@ -16,6 +16,9 @@ SIA_FIELDS = ["D_SIA_Ac", "Ux_SIA_Ac", "Uy_SIA_Ac", "Up_SIA_Ac", "Uo_SIA_Ac", "U
 PIECES_FIELDS = ["tau_c_AaAc", "phi_fric_AaAc", "dU_SSA_dx_AaAc", "dU_SSA_dy_AaAc", "dV_SSA_dx_AaAc", "dV_SSA_dy_AaAc", "eta_AaAc", "N_AaAc", "S_AaAc"]
 SOR_FIELDS = ["RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc", "U_SSA_AaAc", "V_SSA_AaAc", "resU_AaAc", "resV_AaAc"]
 SSA_FIELDS = ["U_SSA", "V_SSA", "Ux_SSA_Ac", "Uy_SSA_Ac", "Up_SSA_Ac", "Uo_SSA_Ac", "eta_AaAc", "N_AaAc", "S_AaAc", "tau_c_AaAc", "Qabs_GL_Ac", "Qp_GL_Ac", "U_SSA_AaAc", "V_SSA_AaAc"]
+THERMO_FIELDS = ["Ti", "W_3D", "U_3D", "V_3D", "frictional_heating", "Ki", "Cpi", "Ti_pmp", "dzeta_dx", "dzeta_dy", "dzeta_dz", "A_flow_mean"]
+THERMO_BENCHMARKS = ("EISMINT_1", "none")   # EISMINT ice properties / temperature-dependent properties with sliding
+THERMO_SSA_OUTER = 3
 MESH_FIELDS = ["A", "Cw", "Nx", "Ny", "Nxx", "Nxy", "Nyy", "NxTri", "NyTri", "Aci", "iAci", "VAc", "Nx_Ac", "Ny_Ac", "Np_Ac", "No_Ac", "edge_index_Ac", "nCAaAc", "CAaAc", "VAaAc",
                "Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "colour", "colour_vi", "colour_nV"]
 

@@ -13,20 +13,22 @@ CONSTANTS = dict(dp=8, pi=np.float64(3.141592653589793), sec_per_year=np.float64
 
 # (file, units).  Interfaces of all units are declared first, so the order of translation does not matter.
 UNITS = [
-    ("zeta_module.f90", ["vertical_integrate", "vertical_average"]),
+    ("zeta_module.f90", ["vertical_integrate", "vertical_average", "initialize_zeta_discretization", "calculate_zeta_derivatives"]),
     ("mesh_help_functions_module.f90", ["is_boundary_segment", "is_in_triangle", "cross2", "find_triangle_area", "find_connection_widths",
                                         "find_Voronoi_cell_areas", "find_Voronoi_cell_vertices", "find_Voronoi_cell_vertices_free",
                                         "find_Voronoi_cell_vertices_corner", "find_Voronoi_cell_vertices_edge", "crop_circumcenter", "line_from_points",
                                         "line_line_intersection"]),
     ("general_ice_model_data_module.f90", ["is_floating", "determine_masks", "ice_physical_properties", "update_general_ice_model_data"]),
     ("mesh_derivatives_module.f90", ["get_neighbour_functions_vertex_gr", "get_neighbour_functions", "get_mesh_derivatives_vertex", "get_mesh_derivatives",
-                                     "get_mesh_derivatives_vertex_3D", "get_mesh_derivatives_3D", "apply_Neumann_boundary", "apply_Neumann_boundary_3D"]),
+                                     "get_mesh_derivatives_vertex_3D", "get_mesh_derivatives_3D", "apply_Neumann_boundary", "apply_Neumann_boundary_3D",
+                                     "get_upwind_derivative_vertex_3D"]),
     ("mesh_ArakawaC_module.f90", ["make_Ac_mesh", "find_Ac_edge_indices", "make_combined_AaAc_mesh", "get_mesh_derivatives_vertex_Ac", "get_mesh_derivatives_Ac",
                                   "get_mesh_derivatives_vertex_AaAc", "get_mesh_derivatives_AaAc", "get_mesh_curvatures_vertex_AaAc", "apply_Neumann_boundary_AaAc",
                                   "map_Aa_to_Ac", "map_Aa_to_Ac_3D", "map_Ac_to_Aa", "map_Ac_to_Aa_3D", "rotate_xy_to_po"]),
     ("ice_dynamics_module.f90", ["calculate_ice_thickness_change", "solve_SIA", "solve_SIA_3D", "SSA_effective_viscosity", "SSA_sliding_term", "basal_yield_stress",
                                  "calculate_GL_flux", "solve_SSA_linearised", "solve_SSA"]),
     ("UFEMISM_main_model.f90", ["determine_timesteps_and_actions"]),
+    ("thermodynamics_module.f90", ["bottom_frictional_heating", "tridiagonal_solve", "replace_Ti_with_robin_solution", "update_ice_temperature"]),
     ("mesh_five_colour_module.f90", None),   # None = every unit of the file
 ]
 
@@ -44,10 +46,10 @@ def program(config):
              ssa_rn_tol=np.float64(config.SSA_RN_tol), ssa_max_outer_loops=int(config.SSA_max_outer_loops),
              ssa_max_residual_uv=np.float64(config.SSA_max_residual_UV), ssa_sor_omega=np.float64(config.SSA_SOR_omega),
              ssa_max_inner_loops=int(config.SSA_max_inner_loops), choice_sliding_law="Coulomb_regularised", do_benchmark_experiment=True,
-             choice_benchmark_experiment="", nconmax=16,
+             choice_benchmark_experiment="", nconmax=16, dt_thermo=np.float64(config.dt_thermo),
              c_sliding=np.float64(1.0e7), m_sliding=np.float64(1.0) / np.float64(3.0))   # configuration_module.f90:172-173
     consts = dict(CONSTANTS)
-    consts.update(c=C, par=F.NS(master=True, i=0, n=1, mem=F.NS(n=0)), mpi_in_place=None, mpi_double_precision=None, mpi_max=None, mpi_comm_world=None, ierr=0, cerr=0)
+    consts.update(c=C, p_zeta=F.NS(), par=F.NS(master=True, i=0, n=1, mem=F.NS(n=0)), mpi_in_place=None, mpi_double_precision=None, mpi_max=None, mpi_comm_world=None, ierr=0, cerr=0)
     P = F.Program(consts)
     texts = {fn: open(os.path.join(REF_SRC, fn)).read() for fn, _ in UNITS}
     units = {fn: (u if u is not None else F.unit_names(texts[fn])) for fn, u in UNITS}
@@ -71,6 +73,7 @@ def mesh_ns(mesh):
     M = mesh.nVAaAc
     m.nxtri, m.nytri, m.r, m.tric = np.array(mesh.NxTri, order="F"), np.array(mesh.NyTri, order="F"), np.array(mesh.R), np.array(mesh.TriC, order="F")
     m.t1, m.t2, m.ntriaaac = 1, mesh.nTri, 0
+    m.itri, m.nitri, m.tri = np.array(mesh.iTri, order="F"), np.array(mesh.niTri), np.array(mesh.Tri, order="F")
     # src/restart_module.f90:81 / mesh_creation_module.f90: tol_dist = ((xmax - xmin) + (ymax - ymin)) * tol / 2 with tol = 1E-9_dp
     m.tol_dist = ((np.float64(mesh.xmax) - mesh.xmin) + (np.float64(mesh.ymax) - mesh.ymin)) * np.float64(1e-9) / np.float64(2.0)
     m.v1, m.v2, m.ac1, m.ac2, m.a1, m.a2 = 1, mesh.nV, 1, mesh.nAc, 1, M

@@ -1,15 +1,17 @@
 """The oracle, the mesh substrate and the CUDA path against the REFERENCE'S OWN SOURCE.
 
-The Fortran reference cannot be compiled here, but its source can be read: oracle/f90py.py translates the text of 64 hot-path
+The Fortran reference cannot be compiled here, but its source can be read: oracle/f90py.py translates the text of 71 hot-path
 routines (src/ice_dynamics_module.f90, general_ice_model_data_module.f90, mesh_ArakawaC_module.f90, mesh_derivatives_module.f90,
-mesh_five_colour_module.f90, mesh_help_functions_module.f90 (Voronoi cell areas, connection widths), zeta_module.f90, UFEMISM_main_model.f90) statement by statement into
+mesh_five_colour_module.f90, mesh_help_functions_module.f90 (Voronoi cell areas, connection widths), zeta_module.f90,
+thermodynamics_module.f90, UFEMISM_main_model.f90) statement by statement into
 Python (single MPI rank, IEEE double arithmetic in source order, libm for the transcendental intrinsics) and this module runs them
 on the golden 600-vertex mesh:
 
 * `test_live_*` (only where /root/reference is mounted): translated reference == oracle / mesh substrate, **bit for bit**, for
   update_general_ice_model_data (all 22 masks, every gradient), calculate_ice_thickness_change, solve_SIA, basal_yield_stress,
   SSA_effective_viscosity, SSA_sliding_term, the five-colour SOR sweep with its Neumann pass, the whole solve_SSA with the
-  analytical grounding-line flux, the critical time steps, find_Voronoi_cell_areas, find_connection_widths, get_neighbour_functions, make_Ac_mesh (+ the combined AaAc mesh and
+  analytical grounding-line flux, the critical time steps, update_ice_temperature (one heat-equation step with DGTSV from a real LAPACK,
+  EISMINT and temperature-dependent ice properties), find_Voronoi_cell_areas, find_connection_widths, get_neighbour_functions, make_Ac_mesh (+ the combined AaAc mesh and
   its neighbour functions) and calculate_five_colouring_AaAc (the SOR order).
 * `test_golden_*` (everywhere): the same comparison against the committed outputs of the translated reference
   (tests/golden/reference_source_600.npz, written by tests/golden/make_reference_source_golden.py), so the pin travels to machines
@@ -106,6 +108,25 @@ def run_reference_source(mesh):
         setattr(region, "t0_" + t, np.float64(0.0))
     P.determine_timesteps_and_actions(region, np.float64(1e12))
     out["cfl__dt_SIA_dt_SSA"] = np.array([region.dt_sia, region.dt_ssa])
+    # thermodynamics: one implicit step of the heat equation (solve_SIA_3D incl. W, frictional heating, zeta Jacobians, upwind
+    # advection, DGTSV through a real LAPACK, 3-D Neumann pass), EISMINT and temperature-dependent ice properties
+    from oracle.oracle import Oracle
+    from ufemism_b200 import scenarios as S
+    for bm in RC.THERMO_BENCHMARKS:
+        stt = S.state_thermo_dome(mesh, benchmark=bm)
+        ot = Oracle(mesh, benchmark=bm, nthreads=1)               # container of zeroed reference arrays
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            ot[k][:] = stt[k]
+        Pt = RS.program(ot.cfg)
+        Pt.C.do_benchmark_experiment, Pt.C.choice_benchmark_experiment = (bm != "none"), bm
+        icet = RS.ice_ns(ot)
+        Pt.update_general_ice_model_data(mref, icet, np.float64(0.0))
+        if bm == "none":
+            Pt.C.ssa_max_outer_loops = RC.THERMO_SSA_OUTER
+            Pt.solve_ssa(mref, icet)
+        Pt.initialize_zeta_discretization()
+        Pt.update_ice_temperature(mref, icet, F.NS(applied=F.NS(t2m=np.array(stt["T2m"], order="F"))), F.NS(smb_year=np.array(stt["SMB_year"])))
+        grab("thermo_" + bm, icet, RC.THERMO_FIELDS)
     return out
 
 
@@ -155,6 +176,19 @@ def run_oracle(mesh):
     grab("thk", o2, RC.THK_FIELDS)
     d = o2.determine_timesteps()
     out["cfl__dt_SIA_dt_SSA"] = np.array([min(d[0], d[2]), d[1]])
+    from oracle.oracle import Oracle
+    from ufemism_b200 import scenarios as S
+    for bm in RC.THERMO_BENCHMARKS:
+        stt = S.state_thermo_dome(mesh, benchmark=bm)
+        ot = Oracle(mesh, benchmark=bm, nthreads=1, SSA_max_outer_loops=RC.THERMO_SSA_OUTER)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            ot[k][:] = stt[k]
+        ot.update_general_ice_model_data(0.0)
+        if bm == "none":
+            ot.solve_SSA()
+        rc, nu = ot.update_ice_temperature()
+        assert (rc, nu) == (0, 0)
+        grab("thermo_" + bm, ot, RC.THERMO_FIELDS)
     return out
 
 
@@ -244,3 +278,18 @@ def test_gpu_matches_reference_source(golden):
     for f in ("Hi", "dHi_dt"):
         a, b = g2.download(f), golden["thk__" + f]
         assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max(), f
+    # thermodynamics: the reference's update_ice_temperature (translated) vs ufm_update_ice_temperature
+    from ufemism_b200 import scenarios as S
+    from ufemism_b200.capi import IceModelGPU
+    for bm in RC.THERMO_BENCHMARKS:
+        stt = S.state_thermo_dome(mesh, benchmark=bm)
+        gt = IceModelGPU(mesh, benchmark=bm, thermo=True, SSA_max_outer_loops=RC.THERMO_SSA_OUTER)
+        for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
+            gt.upload(k, stt[k])
+        gt.update_general_ice_model_data(0.0)
+        if bm == "none":
+            gt.solve_SSA()
+        assert gt.update_ice_temperature().n_unstable == 0
+        for f in ("Ti", "W_3D", "U_3D", "frictional_heating"):
+            b = golden[f"thermo_{bm}__{f}"]
+            np.testing.assert_allclose(gt.download(f), b, rtol=1e-12, atol=1e-12 * max(np.abs(b).max(), 1e-300), err_msg=f"{bm} {f}")
