@@ -8,9 +8,10 @@
  * MPI or NetCDF, and the reference ships no tests, fixtures or golden vectors: there is no
  * reference BUILD to compare with and, by the letter of the task statement, the oracle is "parity unpinned".  It is pinned as
  * far as this environment allows:
- *  (a) to the REFERENCE'S OWN SOURCE TEXT: oracle/f90py.py translates 64 routines of /root/reference/src (the SOR sweep, the whole
+ *  (a) to the REFERENCE'S OWN SOURCE TEXT: oracle/f90py.py translates 71 routines of /root/reference/src (the SOR sweep, the whole
  *      solve_SSA with the grounding-line flux, masks, gradients, SIA, thickness update, critical time steps, neighbour functions,
- *      Ac / AaAc mesh construction, five-colouring, Voronoi areas, connection widths) statement by statement into Python and runs
+ *      Ac / AaAc mesh construction, five-colouring, Voronoi areas, connection widths, update_ice_temperature with its DGTSV going to
+ *      a real LAPACK) statement by statement into Python and runs
  *      them on the golden mesh; the oracle and the mesh substrate agree with them BIT FOR BIT (tests/test_reference_source.py), and
  *      their outputs are committed as golden vectors (tests/golden/reference_source_600.npz) so that the pin also holds on machines
  *      without the reference, incl. the B200 box, where the CUDA path is compared with them.  This check found -- and this file
@@ -21,8 +22,7 @@
  *      equation (pure conduction; the Robin profile the reference codes in replace_Ti_with_robin_solution);
  *  (d) for the one third-party routine on the path, LAPACK DGTSV, by a bit-for-bit comparison with scipy's bundled LAPACK
  *      (tests/test_oracle.py).
- * Not covered by (a): thermodynamics (update_ice_temperature; pinned by (b)-(d)) and what a translation cannot show -- code
- * generation choices of gfortran itself (assumed: -O3 without -ffast-math, no FMA contraction, libm pow / tan / exp).
+ * Not covered by (a): what a translation cannot show -- code generation choices of gfortran itself (assumed: -O3 without -ffast-math, no FMA contraction, libm pow / tan / exp).
  *
  * Layout = the reference's: column-major, 1-based indices stored in the integer arrays, padded
  * ELL rows (width nC_mem for connectivity, nC_mem+1 for neighbour functions).
