@@ -4,7 +4,8 @@ live comparison (tests/test_reference_source.py) and the GPU comparison use iden
 import numpy as np
 
 SOR_ITERS = 4          # C%SSA_max_inner_loops of the SOR case (the sweep starts far from convergence: all of them run)
-SSA_OUTER = 5          # C%SSA_max_outer_loops of the solve_SSA case
+SSA_OUTER = 4          # C%SSA_max_outer_loops of the solve_SSA case
+SSA_INNER = 12         # C%SSA_max_inner_loops of the solve_SSA case (the reference warns and carries on; keeps the Python run short)
 
 GENERAL_FIELDS = (["mask_land", "mask_ocean", "mask_lake", "mask_ice", "mask_sheet", "mask_shelf", "mask_coast", "mask_margin", "mask_gl", "mask_cf", "mask"] +
                   [f + "_Ac" for f in ("mask_land", "mask_ocean", "mask_lake", "mask_ice", "mask_sheet", "mask_shelf", "mask_coast", "mask_margin", "mask_gl", "mask_cf", "mask")] +
@@ -18,7 +19,8 @@ SOR_FIELDS = ["RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc", "U_SSA_AaAc", 
 SSA_FIELDS = ["U_SSA", "V_SSA", "Ux_SSA_Ac", "Uy_SSA_Ac", "Up_SSA_Ac", "Uo_SSA_Ac", "eta_AaAc", "N_AaAc", "S_AaAc", "tau_c_AaAc", "Qabs_GL_Ac", "Qp_GL_Ac", "U_SSA_AaAc", "V_SSA_AaAc"]
 THERMO_FIELDS = ["Ti", "W_3D", "U_3D", "V_3D", "frictional_heating", "Ki", "Cpi", "Ti_pmp", "dzeta_dx", "dzeta_dy", "dzeta_dz", "A_flow_mean"]
 THERMO_BENCHMARKS = ("EISMINT_1", "none")   # EISMINT ice properties / temperature-dependent properties with sliding
-THERMO_SSA_OUTER = 3
+THERMO_SSA_OUTER = 2
+THERMO_SSA_INNER = 8
 MESH_FIELDS = ["A", "Cw", "Nx", "Ny", "Nxx", "Nxy", "Nyy", "NxTri", "NyTri", "Aci", "iAci", "VAc", "Nx_Ac", "Ny_Ac", "Np_Ac", "No_Ac", "edge_index_Ac", "nCAaAc", "CAaAc", "VAaAc",
                "Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "colour", "colour_vi", "colour_nV"]
 
@@ -42,3 +44,22 @@ def start_state(mesh):
 def random_velocities(mesh):
     rng = np.random.default_rng(20211103)
     return rng.normal(0.0, 50.0, mesh.nVAaAc), rng.normal(0.0, 50.0, mesh.nVAaAc)
+
+
+# closed-form benchmark mass balance (run_SMB_model's benchmark branches) and the analytic solutions, at these (benchmark, time) pairs
+SMB_CASES = [("EISMINT_1", 0.0), ("EISMINT_2", 3000.0), ("EISMINT_2", -5.0), ("EISMINT_3", 7000.0), ("EISMINT_4", 0.0), ("EISMINT_5", 4000.0),
+             ("EISMINT_6", 33000.0), ("Halfar", 10.0), ("Bueler", 500.0), ("MISMIP_mod", 1.0), ("mesh_generation_test", 0.0)]
+H0, R0, LAMBDA = 3000.0, 500000.0, 5.0      # config_Bueler_*: halfar_solution_H0 / _R0, bueler_solution_lambda
+ANALYTIC_TIMES = (0.0, 1000.0)
+
+
+def remap_map(mesh, n_dst=300):
+    """A synthetic type_remapping_conservative (src/data_types_module.f90:544-556): for every destination vertex 1..6 source
+    vertices with weights; the weights are arbitrary -- only their APPLICATION is on the path."""
+    rng = np.random.default_rng(99)
+    cnt = rng.integers(1, 7, n_dst)
+    vli2 = np.cumsum(cnt).astype(np.int32)
+    vli1 = (vli2 - cnt + 1).astype(np.int32)
+    n = int(vli2[-1])
+    return dict(vli1=vli1, vli2=vli2, vi=rng.integers(1, mesh.nV + 1, n).astype(np.int32), w0=rng.random(n), w1x=rng.normal(0, 1e3, n), w1y=rng.normal(0, 1e3, n),
+                d_src=rng.normal(1000.0, 300.0, mesh.nV))

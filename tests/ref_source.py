@@ -29,6 +29,9 @@ UNITS = [
                                  "calculate_GL_flux", "solve_SSA_linearised", "solve_SSA"]),
     ("UFEMISM_main_model.f90", ["determine_timesteps_and_actions"]),
     ("thermodynamics_module.f90", ["bottom_frictional_heating", "tridiagonal_solve", "replace_Ti_with_robin_solution", "update_ice_temperature"]),
+    ("SMB_module.f90", ["run_SMB_model", "EISMINT_SMB", "Bueler_solution_MB"]),
+    ("reference_fields_module.f90", ["Halfar_solution", "Bueler_solution"]),
+    ("mesh_mapping_module.f90", ["remap_cons_1st_order_2D", "remap_cons_2nd_order_2D"]),
     ("mesh_five_colour_module.f90", None),   # None = every unit of the file
 ]
 

@@ -1,9 +1,9 @@
 """The oracle, the mesh substrate and the CUDA path against the REFERENCE'S OWN SOURCE.
 
-The Fortran reference cannot be compiled here, but its source can be read: oracle/f90py.py translates the text of 71 hot-path
+The Fortran reference cannot be compiled here, but its source can be read: oracle/f90py.py translates the text of 78 hot-path
 routines (src/ice_dynamics_module.f90, general_ice_model_data_module.f90, mesh_ArakawaC_module.f90, mesh_derivatives_module.f90,
 mesh_five_colour_module.f90, mesh_help_functions_module.f90 (Voronoi cell areas, connection widths), zeta_module.f90,
-thermodynamics_module.f90, UFEMISM_main_model.f90) statement by statement into
+thermodynamics_module.f90, SMB_module.f90, reference_fields_module.f90, mesh_mapping_module.f90, UFEMISM_main_model.f90) statement by statement into
 Python (single MPI rank, IEEE double arithmetic in source order, libm for the transcendental intrinsics) and this module runs them
 on the golden 600-vertex mesh:
 
@@ -11,7 +11,8 @@ on the golden 600-vertex mesh:
   update_general_ice_model_data (all 22 masks, every gradient), calculate_ice_thickness_change, solve_SIA, basal_yield_stress,
   SSA_effective_viscosity, SSA_sliding_term, the five-colour SOR sweep with its Neumann pass, the whole solve_SSA with the
   analytical grounding-line flux, the critical time steps, update_ice_temperature (one heat-equation step with DGTSV from a real LAPACK,
-  EISMINT and temperature-dependent ice properties), find_Voronoi_cell_areas, find_connection_widths, get_neighbour_functions, make_Ac_mesh (+ the combined AaAc mesh and
+  EISMINT and temperature-dependent ice properties), run_SMB_model (every benchmark branch), the Halfar / Bueler solutions, the
+  application of a conservative remapping (1st and 2nd order), find_Voronoi_cell_areas, find_connection_widths, get_neighbour_functions, make_Ac_mesh (+ the combined AaAc mesh and
   its neighbour functions) and calculate_five_colouring_AaAc (the SOR order).
 * `test_golden_*` (everywhere): the same comparison against the committed outputs of the translated reference
   (tests/golden/reference_source_600.npz, written by tests/golden/make_reference_source_golden.py), so the pin travels to machines
@@ -94,9 +95,9 @@ def run_reference_source(mesh):
     ice2 = RS.ice_ns(o)
     P.update_general_ice_model_data(mref, ice2, np.float64(0.0))
     P.solve_sia(mref, ice2)
-    P.C.ssa_max_outer_loops = RC.SSA_OUTER
+    P.C.ssa_max_outer_loops, P.C.ssa_max_inner_loops = RC.SSA_OUTER, RC.SSA_INNER
     P.solve_ssa(mref, ice2)
-    P.C.ssa_max_outer_loops = 50
+    P.C.ssa_max_outer_loops, P.C.ssa_max_inner_loops = 50, 10000
     grab("ssa", ice2, RC.SSA_FIELDS)
     # mass continuity with those velocities, then the critical time steps
     smb, bmb = F.NS(smb_year=np.array(st["SMB_year"])), F.NS(bmb=np.array(st["BMB"]))
@@ -122,11 +123,32 @@ def run_reference_source(mesh):
         icet = RS.ice_ns(ot)
         Pt.update_general_ice_model_data(mref, icet, np.float64(0.0))
         if bm == "none":
-            Pt.C.ssa_max_outer_loops = RC.THERMO_SSA_OUTER
+            Pt.C.ssa_max_outer_loops, Pt.C.ssa_max_inner_loops = RC.THERMO_SSA_OUTER, RC.THERMO_SSA_INNER
             Pt.solve_ssa(mref, icet)
         Pt.initialize_zeta_discretization()
         Pt.update_ice_temperature(mref, icet, F.NS(applied=F.NS(t2m=np.array(stt["T2m"], order="F"))), F.NS(smb_year=np.array(stt["SMB_year"])))
         grab("thermo_" + bm, icet, RC.THERMO_FIELDS)
+    # run_SMB_model, benchmark branches (row N1), and the analytic solutions the benchmarks start from
+    P.C.halfar_solution_h0, P.C.halfar_solution_r0, P.C.bueler_solution_lambda = np.float64(RC.H0), np.float64(RC.R0), np.float64(RC.LAMBDA)
+    for bm, t in RC.SMB_CASES:
+        P.C.do_benchmark_experiment, P.C.choice_benchmark_experiment = True, bm
+        smbm = F.NS(smb_year=np.full(mesh.nV, -9.0), smb=np.zeros((mesh.nV, 12), order="F"))
+        P.run_smb_model(mref, None, None, np.float64(t), smbm, None)
+        out[f"smb__{bm}_{t:g}"] = np.array(smbm.smb_year.a)
+    for t in RC.ANALYTIC_TIMES:
+        out[f"analytic__halfar_{t:g}"] = np.array([P.halfar_solution(np.float64(RC.H0), np.float64(RC.R0), x, y, np.float64(t)) for x, y in np.asarray(mesh.V)])
+        out[f"analytic__bueler_{t:g}"] = np.array([P.bueler_solution(np.float64(RC.H0), np.float64(RC.R0), np.float64(RC.LAMBDA), x, y, np.float64(t)) for x, y in np.asarray(mesh.V)])
+    # application of a conservative remapping (row N3)
+    mp = RC.remap_map(mesh)
+    mapns = F.NS(**{k: np.array(v) for k, v in mp.items() if k != "d_src"})
+    dst = F.NS(v1=1, v2=len(mp["vli1"]))
+    for order in (1, 2):
+        d_dst = np.zeros(len(mp["vli1"]))
+        if order == 1:
+            P.remap_cons_1st_order_2d(dst, mapns, np.array(mp["d_src"]), d_dst)
+        else:
+            P.remap_cons_2nd_order_2d(mref, dst, mapns, np.array(mp["d_src"]), d_dst)
+        out[f"remap__order{order}"] = d_dst
     return out
 
 
@@ -167,7 +189,7 @@ def run_oracle(mesh):
     n, res, _, _ = o.solve_SSA_linearised(max_inner=RC.SOR_ITERS)
     assert n == RC.SOR_ITERS
     grab("sor", o, RC.SOR_FIELDS)
-    o2 = make_oracle(mesh, st, nthreads=1, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER)
+    o2 = make_oracle(mesh, st, nthreads=1, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER, SSA_max_inner_loops=RC.SSA_INNER)
     o2.update_general_ice_model_data(0.0); o2.solve_SIA()
     s = o2.solve_SSA()
     assert s.n_outer == RC.SSA_OUTER
@@ -180,7 +202,7 @@ def run_oracle(mesh):
     from ufemism_b200 import scenarios as S
     for bm in RC.THERMO_BENCHMARKS:
         stt = S.state_thermo_dome(mesh, benchmark=bm)
-        ot = Oracle(mesh, benchmark=bm, nthreads=1, SSA_max_outer_loops=RC.THERMO_SSA_OUTER)
+        ot = Oracle(mesh, benchmark=bm, nthreads=1, SSA_max_outer_loops=RC.THERMO_SSA_OUTER, SSA_max_inner_loops=RC.THERMO_SSA_INNER)
         for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
             ot[k][:] = stt[k]
         ot.update_general_ice_model_data(0.0)
@@ -189,6 +211,20 @@ def run_oracle(mesh):
         rc, nu = ot.update_ice_temperature()
         assert (rc, nu) == (0, 0)
         grab("thermo_" + bm, ot, RC.THERMO_FIELDS)
+    from oracle.oracle import bueler_solution, halfar_solution
+    for bm, t in RC.SMB_CASES:
+        ob = Oracle(mesh, benchmark=bm, nthreads=1)
+        ob["SMB_year"][:] = -9.0
+        ob.run_SMB_benchmark(t, RC.H0, RC.R0, RC.LAMBDA)
+        out[f"smb__{bm}_{t:g}"] = ob["SMB_year"].copy()
+    V = np.asarray(mesh.V)
+    for t in RC.ANALYTIC_TIMES:
+        out[f"analytic__halfar_{t:g}"] = halfar_solution(RC.H0, RC.R0, V[:, 0], V[:, 1], t)
+        out[f"analytic__bueler_{t:g}"] = bueler_solution(RC.H0, RC.R0, RC.LAMBDA, V[:, 0], V[:, 1], t)
+    mp = RC.remap_map(mesh)
+    for order in (1, 2):
+        out[f"remap__order{order}"] = o.remap_cons_2D(order, mp["vli1"], mp["vli2"], mp["vi"], mp["w0"], mp["w1x"] if order == 2 else None,
+                                                     mp["w1y"] if order == 2 else None, mp["d_src"])
     return out
 
 
@@ -267,7 +303,7 @@ def test_gpu_matches_reference_source(golden):
     assert_bits_equal(g.download("U_SSA_AaAc"), golden["sor__U_SSA_AaAc"], "U_SSA_AaAc after the reference's SOR sweeps")
     assert_bits_equal(g.download("V_SSA_AaAc"), golden["sor__V_SSA_AaAc"], "V_SSA_AaAc after the reference's SOR sweeps")
     # whole solve_SSA, then mass continuity and the critical time steps
-    g2 = make_gpu(mesh, st, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER)
+    g2 = make_gpu(mesh, st, use_analytical_GL_flux=1, SSA_max_outer_loops=RC.SSA_OUTER, SSA_max_inner_loops=RC.SSA_INNER)
     g2.update_general_ice_model_data(0.0); g2.solve_SIA()
     s = g2.solve_SSA()
     assert s.n_outer == RC.SSA_OUTER
@@ -283,7 +319,7 @@ def test_gpu_matches_reference_source(golden):
     from ufemism_b200.capi import IceModelGPU
     for bm in RC.THERMO_BENCHMARKS:
         stt = S.state_thermo_dome(mesh, benchmark=bm)
-        gt = IceModelGPU(mesh, benchmark=bm, thermo=True, SSA_max_outer_loops=RC.THERMO_SSA_OUTER)
+        gt = IceModelGPU(mesh, benchmark=bm, thermo=True, SSA_max_outer_loops=RC.THERMO_SSA_OUTER, SSA_max_inner_loops=RC.THERMO_SSA_INNER)
         for k in ("Hi", "Hb", "SL", "SMB_year", "BMB", "T2m", "GHF", "Ti"):
             gt.upload(k, stt[k])
         gt.update_general_ice_model_data(0.0)
