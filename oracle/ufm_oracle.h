@@ -8,7 +8,7 @@
  * MPI or NetCDF, and the reference ships no tests, fixtures or golden vectors: there is no
  * reference BUILD to compare with and, by the letter of the task statement, the oracle is "parity unpinned".  It is pinned as
  * far as this environment allows:
- *  (a) to the REFERENCE'S OWN SOURCE TEXT: oracle/f90py.py translates 71 routines of /root/reference/src (the SOR sweep, the whole
+ *  (a) to the REFERENCE'S OWN SOURCE TEXT: oracle/f90py.py translates 78 routines of /root/reference/src (the SOR sweep, the whole
  *      solve_SSA with the grounding-line flux, masks, gradients, SIA, thickness update, critical time steps, neighbour functions,
  *      Ac / AaAc mesh construction, five-colouring, Voronoi areas, connection widths, update_ice_temperature with its DGTSV going to
  *      a real LAPACK) statement by statement into Python and runs
