@@ -208,7 +208,12 @@ def _do_range(a, b, step=1):
 
 
 def _real(x, kind=None):
-    return np.asarray(x, np.float64) if isinstance(x, (np.ndarray, FArray)) else np.float64(x)
+    """REAL( x, dp) is a double; REAL( x) without a kind is DEFAULT real, i.e. single precision: the value is rounded to 24 bits
+    (it is kept in a double here, which is what every later mixed-kind operation with a _dp operand would promote it to)"""
+    if isinstance(x, (np.ndarray, FArray)):
+        a = np.asarray(_unwrap(x), np.float64)
+        return a if kind is not None else a.astype(np.float32).astype(np.float64)
+    return np.float64(x) if kind is not None else np.float64(np.float32(x))
 
 
 def _sign(a, b):

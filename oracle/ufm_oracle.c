@@ -70,7 +70,12 @@ void ora_config_defaults(ora_config *c)
 void ora_partition_list(int ntot, int i, int n, int *i1, int *i2)
 {
   if (ntot > n * 2) {
-    long a = ((long)ntot * i) / n + 1, b = ((long)ntot * (i + 1)) / n;
+    /* i1 = MAX(1, FLOOR(REAL(ntot*i/n)) + 1), i2 = MIN(ntot, FLOOR(REAL(ntot*(i+1)/n))), src/mesh_help_functions_module.f90:1483-1484:
+     * integer division, then REAL() WITHOUT a kind, i.e. single precision.  Above 2**24 = 16 777 216 the quotient is rounded to 24
+     * bits, so the reference's ranges shift and can even miss the last element (ntot = 16 777 217, 8 ranks: nobody owns it) -- a
+     * latent defect of the reference for lists longer than 16.7 M, found by running its source through oracle/f90py.py.  Restated
+     * as coded; every list of the BASELINE configurations (<= 16.0 M combined-mesh vertices) is below that length. */
+    long a = (long)floorf((float)(((long)ntot * i) / n)) + 1, b = (long)floorf((float)(((long)ntot * (i + 1)) / n));
     *i1 = (int)(a < 1 ? 1 : a);
     *i2 = (int)(b > ntot ? ntot : b);
   } else {

@@ -137,7 +137,7 @@ def test_partition_list_semantics():
     import ctypes
     from oracle.oracle import lib
     L = lib()
-    for ntot, n in ((10, 4), (7, 8), (1000003, 16), (5, 2)):
+    for ntot, n in ((10, 4), (7, 8), (1000003, 16), (5, 2), (3999413, 8), (16001557, 16)):   # incl. the AaAc sizes of BASELINE configs 3 and 5
         seen = []
         for i in range(n):
             a, b = ctypes.c_int(), ctypes.c_int()

@@ -55,21 +55,7 @@ def run_reference_source(mesh):
             out[f"{case}__{f}"] = np.array(_arr(getattr(ns, f)))
 
     # mesh operators from the primary mesh data
-    mm = RS.mesh_ns(mesh)
-    for f in ("nx", "ny", "nxx", "nxy", "nyy", "nxtri", "nytri"):
-        getattr(mm, f).a[...] = -7.0
-    mm.a.a[...] = -7.0; mm.cw.a[...] = 0.0
-    P.find_voronoi_cell_areas(mm)
-    P.find_connection_widths(mm)            # the reference leaves Cw beyond nC(vi) untouched: compared as zeros on both sides
-    P.get_neighbour_functions(mm)
-    P.make_ac_mesh(mm)                      # includes find_Ac_edge_indices and make_combined_AaAc_mesh with its neighbour functions
-    P.calculate_five_colouring_aaac(mm)
-    nAc = int(mm.nac)
-    assert nAc == mesh.nAc
-    for f in RC.MESH_FIELDS:
-        a = np.array(_arr(getattr(mm, f)))
-        want = np.asarray(getattr(mesh, f)).shape
-        out[f"mesh__{f}"] = a[: want[0]] if a.ndim >= 1 and a.shape[0] > want[0] else a
+    out.update(reference_mesh_operators(P, mesh))
     # geometry, masks, gradients
     mref = RS.mesh_ns(mesh)
     ice = RS.ice_ns(o)
@@ -149,6 +135,28 @@ def run_reference_source(mesh):
         else:
             P.remap_cons_2nd_order_2d(mref, dst, mapns, np.array(mp["d_src"]), d_dst)
         out[f"remap__order{order}"] = d_dst
+    return out
+
+
+def reference_mesh_operators(P, mesh):
+    """Secondary mesh data as the translated reference derives them from the primary data: find_Voronoi_cell_areas,
+    find_connection_widths, get_neighbour_functions, make_Ac_mesh (incl. find_Ac_edge_indices, make_combined_AaAc_mesh and its
+    neighbour functions), calculate_five_colouring_AaAc."""
+    out = {}
+    mm = RS.mesh_ns(mesh)
+    for f in ("nx", "ny", "nxx", "nxy", "nyy", "nxtri", "nytri"):
+        getattr(mm, f).a[...] = -7.0
+    mm.a.a[...] = -7.0; mm.cw.a[...] = 0.0
+    P.find_voronoi_cell_areas(mm)
+    P.find_connection_widths(mm)            # the reference leaves Cw beyond nC(vi) untouched: compared as zeros on both sides
+    P.get_neighbour_functions(mm)
+    P.make_ac_mesh(mm)
+    P.calculate_five_colouring_aaac(mm)
+    assert int(mm.nac) == mesh.nAc
+    for f in RC.MESH_FIELDS:
+        a = np.array(_arr(getattr(mm, f)))
+        want = np.asarray(getattr(mesh, f)).shape
+        out[f"mesh__{f}"] = a[: want[0]] if a.ndim >= 1 and a.shape[0] > want[0] else a
     return out
 
 
@@ -329,3 +337,57 @@ def test_gpu_matches_reference_source(golden):
         for f in ("Ti", "W_3D", "U_3D", "frictional_heating"):
             b = golden[f"thermo_{bm}__{f}"]
             np.testing.assert_allclose(gt.download(f), b, rtol=1e-12, atol=1e-12 * max(np.abs(b).max(), 1e-300), err_msg=f"{bm} {f}")
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
+def test_live_partition_list_as_coded():
+    """partition_list (src/mesh_help_functions_module.f90:1475-1496), the rank ranges behind every loop of the reference: the
+    oracle's restatement against the translated source for 2700 (ntot, i, n) triples, including lists longer than 2**24, where the
+    reference's single-precision REAL() shifts the ranges (and can drop the last element -- restated as coded, see ufm_oracle.c)."""
+    import ctypes
+
+    from oracle import f90py as F
+    from oracle.oracle import lib
+
+    P = F.Program({"dp": 8})
+    P.add(open(os.path.join(RS.REF_SRC, "mesh_help_functions_module.f90")).read(), ["partition_list"])
+    L = lib()
+    rng = np.random.default_rng(1)
+    cases = [(10, 4), (7, 8), (5, 2), (1000003, 16), (3999413, 8), (16001557, 16), (16777217, 8), (20000001, 16), (33554433, 3), (9, 4), (8, 4), (1, 1), (2, 1)]
+    cases += [(int(rng.integers(1, 40_000_000)), int(rng.integers(1, 17))) for _ in range(300)]
+    lost = 0
+    for ntot, n in cases:
+        covered = 0
+        for i in range(n):
+            a, b = ctypes.c_int(), ctypes.c_int()
+            L.ora_partition_list(ntot, i, n, ctypes.byref(a), ctypes.byref(b))
+            assert (a.value, b.value) == tuple(int(x) for x in P.partition_list(ntot, i, n, 0, 0)), (ntot, i, n)
+            covered += max(0, b.value - a.value + 1)
+        if ntot <= 1 << 24:
+            assert covered == ntot, (ntot, n)            # below 2**24 the ranges tile the list
+        lost += covered != ntot
+    assert lost > 0                                       # above it they need not (the reference's latent defect, as coded)
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
+@pytest.mark.parametrize("which", ["fan_degree_10_14_16", "seed_3_lattice_order", "seed_5"])
+def test_live_mesh_operators_on_other_meshes(which):
+    """The mesh substrate against the translated reference on meshes with other shapes than the golden one: vertices of degree
+    10, 14 and 16 (= nC_mem), lattice (non-shuffled) vertex order, another seed.  Areas, connection widths, every neighbour
+    function, the Ac numbering / orientation, the AaAc connectivity and the five-colouring must be the reference's, bit for bit."""
+    from oracle.oracle import OraConfig, lib
+    from tests.conftest import fan_mesh
+    from ufemism_b200 import mesh as M
+    import ctypes
+
+    mesh = {"fan_degree_10_14_16": lambda: fan_mesh(nv=500), "seed_3_lattice_order": lambda: M.square_mesh_with_nv(750e3, 350, seed=3, order="lattice"),
+            "seed_5": lambda: M.square_mesh_with_nv(400e3, 300, seed=5)}[which]()
+    if which.startswith("fan"):
+        assert sorted(set(mesh.nC.tolist()))[-1] == mesh.nC_mem
+    c = OraConfig()
+    lib().ora_config_defaults(ctypes.byref(c))
+    np.seterr(all="ignore")
+    ref = reference_mesh_operators(RS.program(c), mesh)
+    got = {f"mesh__{f}": np.asarray(getattr(mesh, f)) for f in RC.MESH_FIELDS}
+    got["mesh__Cw"] = np.where(np.arange(mesh.nC_mem)[None, :] < mesh.nC[:, None], mesh.Cw, 0.0)
+    _compare(got, ref)
