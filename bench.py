@@ -239,7 +239,7 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
                             "unit_costs_s": {k: round(v, 6) for k, v in T.items()}},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-           "note": "CPU restatement of the Fortran hot path (oracle/); the Fortran reference itself cannot be built here (no gfortran/MPI/NetCDF)"}
+           "note": "CPU restatement of the Fortran hot path (oracle/), bit-identical to the reference's own source run through oracle/f90py.py (tests/test_reference_source.py); the Fortran reference itself cannot be built here (no gfortran/MPI/NetCDF)"}
     print(json.dumps(out), flush=True)
 
 

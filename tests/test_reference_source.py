@@ -391,3 +391,39 @@ def test_live_mesh_operators_on_other_meshes(which):
     got = {f"mesh__{f}": np.asarray(getattr(mesh, f)) for f in RC.MESH_FIELDS}
     got["mesh__Cw"] = np.where(np.arange(mesh.nC_mem)[None, :] < mesh.nC[:, None], mesh.Cw, 0.0)
     _compare(got, ref)
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
+@pytest.mark.parametrize("scenario_name", ["halfar", "mismip", "eismint_ice_free", "thermo_dome_realistic"])
+def test_live_per_step_routines_on_other_states(scenario_name):
+    """update_general_ice_model_data (masks!), solve_SIA and calculate_ice_thickness_change of the translated reference vs the oracle on
+    states that exercise other branches than the golden ice-stream case: a land-based dome (no ocean), the MISMIP sloping bed (coast,
+    grounding line, thin shelf), an ice-free start (every mask empty, zero diffusivity) and a dome with the Arrhenius flow factor."""
+    from oracle import f90py as F
+    from oracle.oracle import Oracle
+    from ufemism_b200 import scenarios as S
+
+    np.seterr(all="ignore")
+    mesh = RC.golden_mesh()
+    bm = {"halfar": "Halfar", "mismip": "MISMIP_mod", "eismint_ice_free": "EISMINT_1", "thermo_dome_realistic": "none"}[scenario_name]
+    st = {"halfar": lambda: S.state_halfar(mesh), "mismip": lambda: S.state_mismip(mesh), "eismint_ice_free": lambda: S.state_eismint1(mesh),
+          "thermo_dome_realistic": lambda: S.state_thermo_dome(mesh, benchmark="none")}[scenario_name]()
+    o = Oracle(mesh, benchmark=bm, nthreads=1)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB") + (("Ti",) if bm == "none" else ()):
+        o[k][:] = st[k]
+    P = RS.program(o.cfg)
+    P.C.do_benchmark_experiment, P.C.choice_benchmark_experiment = (bm != "none"), bm
+    mref, ice = RS.mesh_ns(mesh), RS.ice_ns(o)
+    fields = RC.GENERAL_FIELDS + RC.SIA_FIELDS + RC.THK_FIELDS + (["A_flow", "A_flow_Ac", "Ti_Ac", "Ti_pmp", "Cpi", "Ki"] if bm == "none" else [])
+    for step, dt in enumerate((0.5, 2.0)):
+        P.update_general_ice_model_data(mref, ice, np.float64(0.0))
+        P.solve_sia(mref, ice)
+        P.calculate_ice_thickness_change(mref, ice, F.NS(smb_year=np.array(st["SMB_year"])), F.NS(bmb=np.array(st["BMB"])), np.float64(dt), np.zeros(mesh.nV, np.int32))
+        o.update_general_ice_model_data(0.0); o.solve_SIA(); o.calculate_ice_thickness_change(dt)
+        _compare({f: o[f] for f in fields}, {f: _arr(getattr(ice, f)) for f in fields})
+    if scenario_name == "eismint_ice_free":
+        assert not st["Hi"].any() and o["mask_ice"].any() and o["Hi"].max() > 0.0     # ice appears only through the mass balance
+    elif scenario_name == "mismip":
+        assert o["mask_gl"].any() and o["mask_shelf"].any() and o["mask_coast"].any()
+    else:
+        assert o["mask_sheet"].any() and np.abs(o["dHi_dt"]).max() > 0.0
