@@ -427,3 +427,66 @@ def test_live_per_step_routines_on_other_states(scenario_name):
         assert o["mask_gl"].any() and o["mask_shelf"].any() and o["mask_coast"].any()
     else:
         assert o["mask_sheet"].any() and np.abs(o["dHi_dt"]).max() > 0.0
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
+def test_live_region_loop_scheduling():
+    """Three steps of the region loop with the reference's own determine_timesteps_and_actions (critical time steps, the eight
+    timers, the do_* flags, src/UFEMISM_main_model.f90:708-843) and its own per-step routines, called in run_model's order (:78-214;
+    the CPU components between them are the benchmark no-ops) vs ora_run_model: same dt, time, timers and flags after every step,
+    and the same thickness, bit for bit."""
+    from oracle import f90py as F
+    from oracle.oracle import T_BMB, T_CLIMATE, T_ELRA, T_OUTPUT, T_SIA, T_SMB, T_SSA, T_THERMO
+
+    np.seterr(all="ignore")
+    mesh = RC.golden_mesh()
+    st = RC.start_state(mesh)
+    # dt_max and the fixed timers are set long, so that the critical time steps of the dynamics decide the step (the golden mesh is coarse)
+    cfg = dict(use_analytical_GL_flux=1, SSA_max_outer_loops=2, SSA_max_inner_loops=5, dt_max=1000.0)
+    o = make_oracle(mesh, st, nthreads=1, **cfg)
+    P = RS.program(o.cfg)
+    P.C.choice_benchmark_experiment = st["benchmark"]
+    C = P.C
+    C.dt_max, C.dt_thermo, C.dt_climate, C.dt_smb, C.dt_bmb, C.dt_bedrock_elra, C.dt_output = (np.float64(v) for v in (1000.0, 700.0, 650.0, 600.0, 550.0, 800.0, 5000.0))
+    mref, ice = RS.mesh_ns(mesh), RS.ice_ns(o)
+    smb, bmb = F.NS(smb_year=np.array(st["SMB_year"]), smb=np.zeros((mesh.nV, 12), order="F")), F.NS(bmb=np.array(st["BMB"]))
+    # initialise_model, src/UFEMISM_main_model.f90:352-390
+    reg = F.NS(mesh=mref, ice=ice, time=np.float64(0.0), dt=np.float64(0.0), dt_prev=np.float64(1000.0), dt_sia=np.float64(0.0), dt_ssa=np.float64(0.0),
+               do_solve_sia=True, do_solve_ssa=True, do_thermodynamics=False, do_climate=True, do_smb=True, do_bmb=True, do_elra=True, do_write_output=True)
+    for t in ("sia", "ssa", "thermo", "climate", "smb", "bmb", "elra", "output"):
+        setattr(reg, "t0_" + t, np.float64(0.0))
+    r = o.region(0.0)
+    for k, v in ((T_THERMO, 700.0), (T_CLIMATE, 650.0), (T_SMB, 600.0), (T_BMB, 550.0), (T_ELRA, 800.0), (T_OUTPUT, 5000.0)):
+        r.dtc[k] = v
+    r.t1[T_THERMO] = 700.0
+    t_end = np.float64(1e12)
+    dts = []
+    for step in range(3):
+        reg.t0_elra = reg.time                                                         # run_ELRA_model, benchmark branch
+        P.calculate_ice_thickness_change(mref, ice, smb, bmb, reg.dt, np.zeros(mesh.nV, np.int32))
+        P.update_general_ice_model_data(mref, ice, reg.time)
+        if reg.do_solve_sia:
+            P.solve_sia(mref, ice); reg.t0_sia = reg.time
+        if reg.do_solve_ssa:
+            P.solve_ssa(mref, ice); reg.t0_ssa = reg.time
+        if reg.do_climate:
+            reg.t0_climate = reg.time
+        if reg.do_smb:
+            P.run_smb_model(mref, ice, None, reg.time, smb, None); reg.t0_smb = reg.time
+        if reg.do_bmb:
+            reg.t0_bmb = reg.time
+        if reg.do_thermodynamics:
+            P.update_ice_temperature(mref, ice, None, smb); reg.t0_thermo = reg.time    # MISMIP_mod: returns at once (thermodynamics_module.f90:58)
+        if reg.do_write_output:
+            reg.t0_output = reg.time
+        P.determine_timesteps_and_actions(reg, t_end)
+        assert o.run_model(r, float(t_end), max_steps=1) == 0
+        got = [reg.dt, reg.time, reg.dt_prev, reg.dt_sia, reg.dt_ssa] + [getattr(reg, "t1_" + t) for t in ("sia", "ssa", "thermo", "climate", "smb", "bmb", "elra", "output")]
+        want = [r.dt, r.time, r.dt_prev, r.dtc[T_SIA], r.dtc[T_SSA]] + [r.t1[k] for k in (T_SIA, T_SSA, T_THERMO, T_CLIMATE, T_SMB, T_BMB, T_ELRA, T_OUTPUT)]
+        assert [float(x) for x in got] == [float(x) for x in want], (step, got, want)
+        flags = [reg.do_solve_sia, reg.do_solve_ssa, reg.do_thermodynamics, reg.do_climate, reg.do_smb, reg.do_bmb, reg.do_elra, reg.do_write_output]
+        assert [bool(x) for x in flags] == [bool(r.do_[k]) for k in (T_SIA, T_SSA, T_THERMO, T_CLIMATE, T_SMB, T_BMB, T_ELRA, T_OUTPUT)], step
+        for f in ("Hi", "U_SSA", "D_SIA_Ac", "SMB_year"):
+            assert_bits_equal(o[f] if f != "SMB_year" else o["SMB_year"], _arr(getattr(ice, f)) if f != "SMB_year" else smb.smb_year.a, f"step {step} {f}")
+        dts.append(float(r.dt))
+    assert r.n_steps == 3 and r.n_ssa >= 2 and min(dts) < 500.0 and len(set(dts)) == 3, dts     # every step is set by a critical time step of the dynamics
