@@ -21,7 +21,7 @@ THERMO_FIELDS = ["Ti", "W_3D", "U_3D", "V_3D", "frictional_heating", "Ki", "Cpi"
 THERMO_BENCHMARKS = ("EISMINT_1", "none")   # EISMINT ice properties / temperature-dependent properties with sliding
 THERMO_SSA_OUTER = 2
 THERMO_SSA_INNER = 8
-MESH_FIELDS = ["A", "Cw", "Nx", "Ny", "Nxx", "Nxy", "Nyy", "NxTri", "NyTri", "Aci", "iAci", "VAc", "Nx_Ac", "Ny_Ac", "Np_Ac", "No_Ac", "edge_index_Ac", "nCAaAc", "CAaAc", "VAaAc",
+MESH_FIELDS = ["A", "Cw", "R", "Nx", "Ny", "Nxx", "Nxy", "Nyy", "NxTri", "NyTri", "Aci", "iAci", "VAc", "Nx_Ac", "Ny_Ac", "Np_Ac", "No_Ac", "edge_index_Ac", "nCAaAc", "CAaAc", "VAaAc",
                "Nx_AaAc", "Ny_AaAc", "Nxx_AaAc", "Nxy_AaAc", "Nyy_AaAc", "colour", "colour_vi", "colour_nV"]
 
 

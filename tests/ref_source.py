@@ -14,7 +14,7 @@ CONSTANTS = dict(dp=8, pi=np.float64(3.141592653589793), sec_per_year=np.float64
 # (file, units).  Interfaces of all units are declared first, so the order of translation does not matter.
 UNITS = [
     ("zeta_module.f90", ["vertical_integrate", "vertical_average", "initialize_zeta_discretization", "calculate_zeta_derivatives"]),
-    ("mesh_help_functions_module.f90", ["is_boundary_segment", "is_in_triangle", "cross2", "find_triangle_area", "find_connection_widths",
+    ("mesh_help_functions_module.f90", ["is_boundary_segment", "is_in_triangle", "cross2", "find_triangle_area", "find_connection_widths", "determine_mesh_resolution",
                                         "find_Voronoi_cell_areas", "find_Voronoi_cell_vertices", "find_Voronoi_cell_vertices_free",
                                         "find_Voronoi_cell_vertices_corner", "find_Voronoi_cell_vertices_edge", "crop_circumcenter", "line_from_points",
                                         "line_line_intersection"]),

@@ -149,6 +149,8 @@ def reference_mesh_operators(P, mesh):
     mm.a.a[...] = -7.0; mm.cw.a[...] = 0.0
     P.find_voronoi_cell_areas(mm)
     P.find_connection_widths(mm)            # the reference leaves Cw beyond nC(vi) untouched: compared as zeros on both sides
+    mm.r.a[...] = -7.0
+    P.determine_mesh_resolution(mm)
     P.get_neighbour_functions(mm)
     P.make_ac_mesh(mm)
     P.calculate_five_colouring_aaac(mm)

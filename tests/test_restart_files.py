@@ -363,3 +363,86 @@ def test_relabelled_five_colouring_gives_the_same_colouring(mesh):
         rc = lib.ufm_mesh_five_colouring_labelled(Mv, mesh.nC_mem, p(mesh.nCAaAc), p(mesh.CAaAc), None if label is None else p(label), p(colour), p(cvi), p(cn))
         assert rc == 0
         assert np.array_equal(colour, mesh.colour) and np.array_equal(cvi, mesh.colour_vi) and np.array_equal(cn, mesh.colour_nV)
+
+
+# ---- live cross-check of the file layouts against the reference's source text (where it is mounted) ----
+REF_SRC = "/root/reference/src"
+
+
+def _reference_layout(routine, type_name):
+    """(dimension list, variable list) as `routine` of netcdf_module.f90 defines them, names resolved through the
+    `name_dim_* / name_var_*` defaults of `type_name` in data_types_netcdf_module.f90."""
+    import re
+
+    from oracle import f90py as F
+    st = [s for _, s in F.extract_unit(open(os.path.join(REF_SRC, "netcdf_module.f90")).read(), routine)]
+    types = open(os.path.join(REF_SRC, "data_types_netcdf_module.f90")).read()
+    body = types[types.index(f"TYPE {type_name}"):types.index(f"END TYPE {type_name}")]
+    names = {m.group(1): m.group(2).strip() for m in re.finditer(r"::\s*(name_(?:dim|var)_\w+)\s*=\s*'([^']*)'", body)}
+    dims, variables, alias = [], [], {}
+    for s in st:
+        m = re.match(r"CALL create_dim\(\s*netcdf%ncid,\s*netcdf%(name_dim_\w+)\s*,\s*(.+?),\s*netcdf%(id_dim_\w+)\s*\)", s)
+        if m:
+            dims.append(names[m.group(1)])
+            alias["netcdf%" + m.group(3)] = names[m.group(1)]
+            continue
+        m = re.match(r"(\w+)\s*=\s*netcdf%(id_dim_\w+)$", s)          # "vi = netcdf%id_dim_vi": short aliases used in the definitions
+        if m:
+            alias[m.group(1)] = alias["netcdf%" + m.group(2)]
+            continue
+        m = re.match(r"CALL create_(double|int)_var\(\s*netcdf%ncid,\s*netcdf%(name_var_\w+)\s*,\s*\[([^\]]*)\],\s*netcdf%id_var_\w+\s*,\s*long_name='([^']*)'(?:,\s*units='([^']*)')?\s*\)", s)
+        if m:
+            variables.append((names[m.group(2)], m.group(1)[0], [alias[d.strip()] for d in m.group(3).split(",")], m.group(4), m.group(5)))
+    return dims, variables
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="/root/reference is not mounted here")
+def test_live_restart_layout_is_the_reference_sources(mesh, tmp_path):
+    """Dimensions and variables of a file written by ufm_restart_create, read back with scipy, against what create_restart_file_mesh
+    defines in the reference's source: same names, order, types, dimension order, long_name and units."""
+    dims, variables = _reference_layout("create_restart_file_mesh", "type_netcdf_restart")
+    assert len(dims) == 14 and len(variables) == 32
+    fn = str(tmp_path / "restart_ANT_00001.nc")
+    R.create_restart(fn, mesh, ZETA)
+    f = netcdf_file(fn, "r", mmap=False)
+    assert list(f.dimensions) == dims
+    assert list(f.variables) == [v[0] for v in variables]
+    for name, ty, fdims, long_name, units in variables:
+        v = f.variables[name]
+        assert v.dimensions == tuple(reversed(fdims)), name
+        assert v.data.dtype == (np.dtype(">f8") if ty == "d" else np.dtype(">i4")), name
+        assert v.long_name == long_name.encode() and getattr(v, "units", None) == (units.encode() if units else None), name
+    f.close()
+    # the hard-coded expectation of the non-live tests above is that very list
+    assert [(n, t, d, l, u) for n, t, d, l, u in MESH_VARS + RESTART_VARS] == variables
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="/root/reference is not mounted here")
+def test_live_help_field_table_is_the_reference_sources(mesh, tmp_path):
+    """Every field create_help_field_mesh knows (name, type, dimensions, long_name, units), parsed from the reference's source,
+    against the file ufm_help_fields_create writes when asked for all of them."""
+    import re
+
+    from oracle import f90py as F
+    st = [s for _, s in F.extract_unit(open(os.path.join(REF_SRC, "netcdf_module.f90")).read(), "create_help_field_mesh")]
+    table = []
+    for s in st:
+        m = re.search(r"CALL create_(double|int)_var\(\s*netcdf%ncid,\s*'(\w+)',\s*\[([^\]]*)\],\s*id_var,\s*long_name='([^']*)'(?:,\s*units='([^']*)')?", s)
+        if m:
+            fd = [{"vi": "vi", "t": "time", "z": "zeta", "m": "month"}[d.strip()] for d in m.group(3).split(",")]
+            table.append((m.group(2), m.group(1)[0], fd, m.group(4), m.group(5)))
+    assert len(table) == 74
+    fn = str(tmp_path / "help_fields_ANT_00001.nc")
+    R.create_help_fields(fn, mesh, ZETA, [t[0] for t in table])
+    f = netcdf_file(fn, "r", mmap=False)
+    assert list(f.variables)[len(MESH_VARS):] == [t[0] for t in table]
+    for name, ty, fdims, long_name, units in table:
+        v = f.variables[name]
+        assert v.dimensions == tuple(reversed(fdims)), name
+        assert v.data.dtype == (np.dtype(">f8") if ty == "d" else np.dtype(">i4")), name
+        assert v.long_name == long_name.encode() and getattr(v, "units", None) == (units.encode() if units else None), name
+    f.close()
+    # and the mesh part of the help_fields file is defined exactly like the restart file's
+    d1, v1 = _reference_layout("create_restart_file_mesh", "type_netcdf_restart")
+    d2, v2 = _reference_layout("create_help_fields_file_mesh", "type_netcdf_help_fields")
+    assert d1 == d2 and v1[:len(MESH_VARS)] == v2 == [(n, t, d, l, u) for n, t, d, l, u in MESH_VARS]
