@@ -39,7 +39,8 @@ def build_cuda(force=False, verbose=False):
                 cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
                 subprocess.run(cmd, check=True)
             objs.append(o)
-        subprocess.run([NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp"] + objs, check=True)
+        # the arch is given at link time too: without it nvcc adds an empty default-arch (sm_52) fatbin to the library
+        subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp"] + objs, check=True)
     return LIB
 
 
