@@ -148,7 +148,17 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------------
 # CPU restatement: per-routine unit costs at full size (bounded sample), scaled by iteration counts
 # ------------------------------------------------------------------------------------------------
-def cpu_unit_costs(m, st, nthreads, sor_iters=100, reps=5):
+def cpu_unit_costs(m, st, nthreads, sor_iters=100, reps=5, min_seconds=10.0):
+    """The sample is bounded to about 10-30 s of CPU work: if the first pass (5 reps + 100 SOR iterations) took less than
+    `min_seconds` on this host, it is repeated once with proportionally more reps / iterations and that longer sample is reported."""
+    T = _cpu_unit_costs(m, st, nthreads, sor_iters, reps)
+    if T["sample_seconds"] < min_seconds:
+        f = min(6, int(np.ceil(1.25 * min_seconds / max(T["sample_seconds"], 1e-3))))
+        T = _cpu_unit_costs(m, st, nthreads, sor_iters * f, reps * f)
+    return T
+
+
+def _cpu_unit_costs(m, st, nthreads, sor_iters, reps):
     from oracle.oracle import Oracle
 
     o = Oracle(m, benchmark=st["benchmark"], nthreads=nthreads, use_analytical_GL_flux=1)
