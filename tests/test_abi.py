@@ -114,3 +114,272 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".f90")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "ufm_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+# ---- the Fortran shim has never been compiled here (no Fortran compiler): hold its BIND(C) types and INTERFACE blocks to the header ----
+def _c_kind(decl):
+    """'int' | 'double' | 'i64' | 'ptr' for a C parameter / member declaration (arrays in parameter position are pointers)."""
+    d = decl.strip()
+    if "*" in d or re.search(r"\[[^\]]*\]\s*$", d):
+        return "ptr"
+    base = re.sub(r"\b(const|unsigned|signed)\b", "", d)
+    base = re.sub(r"\b\w+\s*$", "", base).strip()          # drop the name
+    if base in ("long long", "long", "size_t", "int64_t", "uint64_t"):
+        return "i64"
+    if base in ("int", ""):                                # "unsigned x" leaves ""
+        return "int"
+    if base == "double":
+        return "double"
+    raise AssertionError(f"unhandled C declaration {decl!r}")
+
+
+def _header_model():
+    txt = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    txt = re.sub(r"//[^\n]*", "", txt)
+    structs = {}
+    for body, name in re.findall(r"typedef struct \w+\s*\{(.*?)\}\s*(\w+)\s*;", txt, flags=re.S):
+        members = []
+        for stmt in body.split(";"):
+            stmt = " ".join(stmt.split())
+            if not stmt:
+                continue
+            m = re.match(r"(.*?)([\w\s\*\[\],]+)$", stmt)
+            # "const double *V, *A" / "int nV, nAc" / "double zeta[UFM_MAX_NZ]"
+            first, *rest = [p.strip() for p in stmt.split(",")]
+            ty = re.sub(r"[\*\s]*\w+\s*(\[[^\]]*\])?$", "", first).strip()
+            for p in [first[len(ty):].strip()] + rest:
+                nm = re.search(r"(\w+)\s*(\[[^\]]*\])?$", p).group(1)
+                arr = "[" in p
+                kind = "ptr" if "*" in p else _c_kind(ty + " x")
+                members.append((nm, kind + ("[]" if arr else "")))
+        structs[name] = members
+    funcs = {}
+    for ret, name, args in re.findall(r"^\s*((?:const\s+)?\w+\s*\**)\s*(ufm_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.M | re.S):
+        args = " ".join(args.split())
+        params = [] if args in ("void", "") else [_c_kind(a) for a in args.split(",")]
+        funcs[name] = ("ptr" if "*" in ret else "int" if ret.strip() == "int" else "void", params)
+    return structs, funcs
+
+
+def _f90_kind(spec):
+    s = spec.upper().replace(" ", "")
+    if s.startswith("INTEGER(C_INT)"):
+        return "int"
+    if s.startswith("INTEGER(C_LONG_LONG)") or s.startswith("INTEGER(C_SIZE_T)") or s.startswith("INTEGER(C_LONG)"):
+        return "i64"
+    if s.startswith("REAL(C_DOUBLE)"):
+        return "double"
+    if s.startswith("TYPE(C_PTR)"):
+        return "ptr"
+    if s.startswith("CHARACTER(KIND=C_CHAR)"):
+        return "char"
+    if s.startswith("TYPE(UFM_"):
+        return "struct"
+    raise AssertionError(f"unhandled Fortran declaration {spec!r}")
+
+
+def _split_entities(s):
+    """'a, b( 3), c' -> [('a', False), ('b', True), ('c', False)]"""
+    out, depth, cur = [], 0, ""
+    for ch in s + ",":
+        if ch == "(":
+            depth += 1
+        if ch == ")":
+            depth -= 1
+        if ch == "," and depth == 0:
+            cur = cur.strip()
+            if cur:
+                out.append((re.match(r"\w+", cur).group(0), "(" in cur))
+            cur = ""
+        else:
+            cur += ch
+    return out
+
+
+def _shim_model():
+    src = open(os.path.join(ROOT, "ufemism_b200", "fortran", "ufemism_b200_shim.f90")).read()
+    src = re.sub(r"&\s*\n\s*", " ", src)                                   # continuation lines
+    lines = [ln.split("!")[0].rstrip() for ln in src.splitlines()]
+    types, funcs, i = {}, {}, 0
+    while i < len(lines):
+        ln = lines[i].strip()
+        m = re.match(r"TYPE, BIND\(C\) :: (\w+)", ln)
+        if m:
+            members = []
+            i += 1
+            while not lines[i].strip().upper().startswith("END TYPE"):
+                if "::" in lines[i]:
+                    spec, ents = lines[i].split("::")
+                    for nm, arr in _split_entities(ents):
+                        members.append((nm, _f90_kind(spec) + ("[]" if arr else "")))
+                i += 1
+            types[m.group(1)] = members
+        m = re.match(r"FUNCTION (\w+)\(\s*(.*?)\)\s*BIND\(C, NAME='(\w+)'\)\s*RESULT\(\s*(\w+)\)", ln)
+        if m:
+            fname, dummies, cname, res = m.group(1), [d.strip() for d in m.group(2).split(",") if d.strip()], m.group(3), m.group(4)
+            decl, raw = {}, {}
+            i += 1
+            while not lines[i].strip().upper().startswith("END FUNCTION"):
+                if "::" in lines[i] and not lines[i].strip().upper().startswith("IMPORT"):
+                    spec, ents = lines[i].split("::")
+                    by_value = "VALUE" in spec.upper()
+                    for nm, arr in _split_entities(ents):
+                        k = raw[nm] = _f90_kind(spec)
+                        # BIND(C) passes everything by reference unless VALUE; arrays, structs and characters always are references
+                        decl[nm] = k if (by_value and k in ("int", "double", "i64", "ptr") and not arr) else "ptr"
+                        if by_value:
+                            assert not arr and k != "struct", (fname, nm)
+                i += 1
+            assert set(dummies) | {res} == set(decl), (fname, dummies, sorted(decl))
+            funcs[cname] = (fname, {"int": "int", "ptr": "ptr"}[raw[res]], [decl[d] for d in dummies])
+        i += 1
+    return types, funcs
+
+
+def test_fortran_shim_types_and_interfaces_match_header():
+    c_structs, c_funcs = _header_model()
+    f_types, f_funcs = _shim_model()
+    assert len(f_types) >= 6 and len(f_funcs) >= 28
+    for name, members in f_types.items():
+        assert name in c_structs, name
+        assert members == c_structs[name], (name, [(a, b) for a, b in zip(members, c_structs[name]) if a != b], len(members), len(c_structs[name]))
+    for cname, (fname, ret, params) in f_funcs.items():
+        assert fname == cname                                   # the shim binds each entry point under its own name
+        c_ret, c_params = c_funcs[cname]
+        assert ret == c_ret, cname
+        assert params == c_params, (cname, params, c_params)
+    # every CALL of / reference to a ufm_ function in the wrappers has an INTERFACE
+    body = open(os.path.join(ROOT, "ufemism_b200", "fortran", "ufemism_b200_shim.f90")).read()
+    body = "\n".join(ln.split("!")[0] for ln in body.splitlines())
+    for name in set(re.findall(r"\b(ufm_\w+)\s*\(", body)):
+        assert name in f_funcs or name in f_types, f"{name} used in the shim without an INTERFACE"
+
+
+# ---- live: every derived-type component the shim touches exists in the reference's type definitions ----
+REF_SRC = "/root/reference/src"
+
+
+def _f90_types(text):
+    """{type name (lower): {component (lower): type name of the component (lower) or None}} of every TYPE ... END TYPE in `text`."""
+    text = re.sub(r"&\s*\n\s*", " ", text)
+    types, cur = {}, None
+    for ln in text.splitlines():
+        ln = ln.split("!")[0].strip()
+        m = re.match(r"TYPE(?:\s*,\s*BIND\(C\))?\s*(?:::)?\s*(\w+)$", ln, flags=re.I)
+        if m and cur is None:
+            cur = types.setdefault(m.group(1).lower(), {})
+            continue
+        if re.match(r"END TYPE", ln, flags=re.I):
+            cur = None
+            continue
+        if cur is not None and "::" in ln:
+            spec, ents = ln.split("::", 1)
+            tm = re.match(r"\s*TYPE\(\s*(\w+)\s*\)", spec, flags=re.I)
+            for nm, _ in _split_entities(ents.split("=")[0] if "(" not in ents else ents):
+                cur[nm.lower()] = tm.group(1).lower() if tm else None
+    return types
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="/root/reference is not mounted here")
+def test_live_shim_components_exist_in_the_reference_types():
+    """`mesh%Nx_AaAc`, `ice%dHs_dt`, `climate%applied%T2m`, `region%init%netcdf_restart%filename`, `C%SSA_SOR_omega`, ... : every
+    component chain in the shim resolves through the TYPE definitions of the reference's own modules (and the shim's BIND(C) types),
+    the module procedures it calls exist with that many arguments, and the ONLY lists name things the modules define."""
+    shim = open(os.path.join(ROOT, "ufemism_b200", "fortran", "ufemism_b200_shim.f90")).read()
+    types = {}
+    mods = {}
+    for fn in ("data_types_module.f90", "data_types_netcdf_module.f90", "configuration_module.f90", "parallel_module.f90", "mesh_memory_module.f90"):
+        mods[fn] = open(os.path.join(REF_SRC, fn)).read()
+        types.update(_f90_types(mods[fn]))
+    types.update(_f90_types(shim))
+    assert {"type_mesh", "type_ice_model", "type_model_region", "constants_type", "parallel_info", "ufm_mesh_desc"} <= set(types)
+    module_vars = {"c": "constants_type", "par": "parallel_info"}      # configuration_module.f90:725, parallel_module.f90:22
+
+    # USE ... ONLY lists
+    for mod, only in re.findall(r"USE (\w+),\s*ONLY:\s*([^\n]+)", shim):
+        txt = mods[mod + ".f90"]
+        for name in [n.strip() for n in only.split(",")]:
+            assert re.search(rf"\b{name}\b", txt, flags=re.I), f"{mod} does not define {name}"
+
+    # procedures of the shim, their TYPE(...) variables and component chains
+    body = re.sub(r"&\s*\n\s*", " ", shim[shim.index("CONTAINS"):])
+    n_chains = 0
+    for m in re.finditer(r"^\s*(?:SUBROUTINE|FUNCTION) (\w+)(.*?)^\s*END (?:SUBROUTINE|FUNCTION)", body, flags=re.S | re.M):
+        var_type = dict(module_vars)
+        stmts = []
+        for ln in m.group(2).splitlines():
+            ln = re.sub(r"'[^']*'", "''", ln.split("!")[0])
+            if "::" in ln:
+                spec, ents = ln.split("::", 1)
+                tm = re.match(r"\s*TYPE\(\s*(\w+)\s*\)", spec, flags=re.I)
+                if tm:
+                    for nm, _ in _split_entities(ents):
+                        var_type[nm.lower()] = tm.group(1).lower()
+            else:
+                stmts.append(ln)
+        for chain in re.findall(r"\b([A-Za-z_]\w*(?:\s*%\s*\w+)+)", "\n".join(stmts)):
+            parts = [p.strip().lower() for p in chain.split("%")]
+            assert parts[0] in var_type, (m.group(1), chain)
+            t = var_type[parts[0]]
+            for comp in parts[1:]:
+                assert t in types, (m.group(1), chain, t)
+                assert comp in types[t], f"{m.group(1)}: {chain}: type {t} has no component {comp}"
+                t = types[t][comp]
+            n_chains += 1
+    assert n_chains > 150
+
+    # module procedures called: sync (parallel_module), allocate_mesh_primary (mesh_memory_module) with the reference's argument count
+    sig = re.search(r"SUBROUTINE allocate_mesh_primary\(([^)]*)\)", mods["mesh_memory_module.f90"]).group(1)
+    call = re.search(r"CALL allocate_mesh_primary\(([^\n]*)\)", body).group(1)
+    assert len(sig.split(",")) == len(call.split(","))
+    assert re.search(r"SUBROUTINE sync\b", mods["parallel_module.f90"])
+
+
+def test_shim_has_no_undeclared_names_and_balanced_blocks():
+    """IMPLICIT NONE lint for the never-compiled shim: every name used in an executable statement is a local / dummy / module entity,
+    a USE ... ONLY name, an MPI entity, an ISO_C_BINDING entity or an intrinsic; block constructs are balanced."""
+    shim = open(os.path.join(ROOT, "ufemism_b200", "fortran", "ufemism_b200_shim.f90")).read()
+    shim = re.sub(r"&\s*\n\s*", " ", shim)
+    head, body = shim[:shim.index("\nCONTAINS")], shim[shim.index("\nCONTAINS"):]
+    strip = lambda ln: re.sub(r"'[^']*'", "''", ln).split("!")[0]
+    known = {"c_int", "c_double", "c_ptr", "c_char", "c_long_long", "c_null_ptr", "c_null_char", "c_loc", "c_f_pointer",
+             # intrinsics and keywords the shim uses
+             "int", "size", "merge", "trim", "len_trim", "minval", "maxval", "associated", "allocate", "deallocate", "if", "then", "else", "end", "do", "while",
+             "call", "return", "select", "case", "default", "write", "and", "or", "not", "true", "false", "dp"}
+    for only in re.findall(r"USE \w+,\s*ONLY:\s*([^\n]+)", head):
+        known |= {n.strip().lower() for n in only.split(",")}
+    for ln in head.splitlines():
+        ln = strip(ln)
+        if "::" in ln and not re.match(r"\s*(IMPORT|USE)\b", ln):
+            known |= {nm.lower() for nm, _ in _split_entities(re.sub(r"=\s*[^,]+", "", ln.split("::", 1)[1]))}
+    known |= {n.lower() for n in re.findall(r"^\s*(?:TYPE, BIND\(C\) ::|FUNCTION|SUBROUTINE) (\w+)", shim, flags=re.M)}
+    n_proc = 0
+    for m in re.finditer(r"^\s*(SUBROUTINE|FUNCTION) (\w+)\s*\(([^)]*)\)([^\n]*)\n(.*?)^\s*END \1", body, flags=re.S | re.M):
+        local = {d.strip().lower() for d in m.group(3).split(",") if d.strip()}
+        res = re.search(r"RESULT\(\s*(\w+)", m.group(4))
+        if res:
+            local.add(res.group(1).lower())
+        declared, depth = set(), {"if": 0, "do": 0, "select": 0}
+        for ln in m.group(5).splitlines():
+            ln = strip(ln)
+            if "::" in ln:
+                declared |= {nm.lower() for nm, _ in _split_entities(ln.split("::", 1)[1])}
+                ln = ln.split("::", 1)[1]                      # bounds expressions of the declared entities are checked too
+            for st in ln.split(";"):
+                st = st.strip()
+                if re.match(r"IF\b.*\bTHEN$", st): depth["if"] += 1
+                if re.match(r"END IF\b", st): depth["if"] -= 1
+                if re.match(r"DO\b", st): depth["do"] += 1
+                if re.match(r"END DO\b", st): depth["do"] -= 1
+                if re.match(r"SELECT CASE\b", st): depth["select"] += 1
+                if re.match(r"END SELECT\b", st): depth["select"] -= 1
+                assert min(depth.values()) >= 0, (m.group(2), st)
+                st = re.sub(r"%\s*\w+", "", st)                                    # components are checked by the live test
+                st = re.sub(r"\b\d+(\.\d*)?(_dp)?\b|\.\w+\.", " ", st)             # literals, .AND. / .NOT.
+                for name in re.findall(r"[A-Za-z_]\w*", st):
+                    n = name.lower()
+                    assert n in local or n in declared or n in known or n.startswith("mpi_"), f"{m.group(2)}: '{name}' is not declared ({st.strip()[:80]})"
+        assert local <= declared | {""}, (m.group(2), local - declared)           # every dummy / result has a declaration
+        assert set(depth.values()) == {0}, (m.group(2), depth)
+        n_proc += 1
+    assert n_proc == 19
