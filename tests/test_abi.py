@@ -383,3 +383,29 @@ def test_shim_has_no_undeclared_names_and_balanced_blocks():
         assert set(depth.values()) == {0}, (m.group(2), depth)
         n_proc += 1
     assert n_proc == 19
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_a_gpu(lib, tmp_path):
+    """host/ufemism_host.hpp + host/run_steps.cpp (the compiled twin of the Fortran shim) compile warning-free against the header and link
+    against the library; without a CUDA device the first call ends like the reference's fatal errors do: a message naming the routine on
+    stderr, then abort -- never a silent CPU path.  (With a GPU the same program is run against the oracle by tests/test_gpu_parity.py.)"""
+    import numpy as np
+    import torch
+
+    exe, libdir = str(tmp_path / "run_steps"), os.path.join(ROOT, "ufemism_b200")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "host", "run_steps.cpp"),
+                    "-o", exe, "-L", libdir, "-lufemism_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present: the run is covered by test_cpp_host_mirror")
+    N, E, W = 5, 8, 4
+    M = N + E
+    inp = tmp_path / "in.bin"
+    with open(inp, "wb") as f:
+        np.array([N, E, W], np.int32).tofile(f)
+        # sizes in the order run_steps.cpp reads them; the contents never matter: ufm_create fails first
+        for n, dt in ((N * 2, "f8"), (N, "f8"), (N, "i4"), (N * W, "i4"), (N * W, "f8"), (N, "i4"), (N * (W + 1), "f8"), (N * (W + 1), "f8"), (E * 4, "i4"), (N * W, "i4"),
+                      (E, "i4"), (E * 4, "f8"), (E * 4, "f8"), (E * 4, "f8"), (E, "f8"), (M, "i4"), (M * W, "i4")) + ((M * (W + 1), "f8"),) * 5 + ((M * 5, "i4"), (5, "i4")) + ((N, "f8"),) * 5:
+            np.zeros(n, dt).tofile(f)
+    r = subprocess.run([exe, str(inp), str(tmp_path / "out.bin"), "1", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and not (tmp_path / "out.bin").exists()
+    assert "ufm_create" in r.stderr and ("CPU fallback" in r.stderr or "CUDA" in r.stderr), r.stderr
