@@ -2,6 +2,7 @@
 src/reference_fields_module.f90:707-795), its own committed golden vectors, and the properties and quirks
 SURVEY.md sections 0 and 4 list.  PARITY UNPINNED: the Fortran reference cannot be run here (see oracle/ufm_oracle.h)."""
 import os
+import re
 
 import numpy as np
 import pytest
@@ -416,3 +417,39 @@ def test_bueler_run_tracks_analytic_solution():
         errs.append(rel_l2(o["Hi"], Ha))
         assert abs(o["Hi"].max() / Ha.max() - 1.0) < 3e-3
     assert errs[0] < 0.05 and errs[1] < 0.025 and errs[1] < 0.6 * errs[0], errs
+
+
+def test_gcc_code_generation_assumptions_behind_the_parity_contract(tmp_path):
+    """The bit-level contract assumes what GCC -O3 without -ffast-math does with the hot path's arithmetic -- gfortran (the reference's
+    compiler, `-O3`, no -march, no -ffast-math: src/Makefile.mpif90:11) and the oracle's gcc share that middle / back end:
+    `x**3.0_dp` stays a libm `pow` call (not x*x*x), `x**2` is x*x (exact either way), a*b+c is a separate multiply and add on baseline
+    x86-64 (no FMA contraction), and the oracle's own object code contains no fused multiply-add."""
+    import shutil
+    import subprocess
+
+    from oracle import oracle as O
+
+    src = tmp_path / "p.c"
+    src.write_text("#include <math.h>\n"
+                   "double p3(double x) { return pow(x, 3.0); }\n"
+                   "double p2(double x) { return pow(x, 2.0); }\n"
+                   "double pm(double x) { return pow(x, -0.35); }\n"
+                   "double ma(double a, double b, double c) { return a * b + c; }\n")
+    asm = subprocess.run(["/usr/bin/gcc", "-O3", "-fno-fast-math", "-S", "-o", "-", str(src)], capture_output=True, text=True, check=True).stdout
+    fn = {}
+    cur = None
+    for ln in asm.splitlines():
+        if ln and not ln[0].isspace() and ln.endswith(":") and not ln.startswith("."):
+            cur = ln[:-1]
+            fn[cur] = []
+        elif cur and ln.strip() and not ln.strip().startswith("."):
+            fn[cur].append(ln.strip())
+    assert any("pow" in i for i in fn["p3"]) and not any(i.startswith("mulsd") for i in fn["p3"])
+    assert any("pow" in i for i in fn["pm"])
+    assert any(i.startswith("mulsd") for i in fn["p2"]) and not any("pow" in i for i in fn["p2"])
+    ops = [i.split()[0] for i in fn["ma"] if i.split()[0] != "endbr64"]
+    assert ops[:2] == ["mulsd", "addsd"] and not any("fmadd" in i for i in fn["ma"])
+    if shutil.which("objdump"):
+        O.build()
+        dis = subprocess.run(["objdump", "-d", os.path.join(os.path.dirname(O.__file__), "libufm_oracle.so")], capture_output=True, text=True, check=True).stdout
+        assert not re.search(r"vfn?m(add|sub)", dis)
