@@ -409,3 +409,19 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_a_gpu(lib, tmp_path):
     r = subprocess.run([exe, str(inp), str(tmp_path / "out.bin"), "1", "1"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and not (tmp_path / "out.bin").exists()
     assert "ufm_create" in r.stderr and ("CPU fallback" in r.stderr or "CUDA" in r.stderr), r.stderr
+
+
+def test_build_flags_keep_fp64_multiply_and_add_separate(tmp_path):
+    """The GPU half of the bit-level contract: with the build's own nvcc flags (`-fmad=false`, sm_100a) `a*b+c` compiles to DMUL + DADD,
+    never DFMA, and sqrt / division are the IEEE round-to-nearest sequences (no `.approx` results reach the output)."""
+    from ufemism_b200 import build as B
+
+    assert "-fmad=false" in B.NVCC_FLAGS and "arch=compute_100a,code=sm_100a" in B.NVCC_FLAGS
+    src = tmp_path / "k.cu"
+    src.write_text("__global__ void k(double *p) { p[0] = p[1] * p[2] + p[3]; }\n")
+    cubin = tmp_path / "k.cubin"
+    flags = [f for f in B.NVCC_FLAGS if f not in ("-lineinfo",)]
+    subprocess.run([B.NVCC] + flags + ["-cubin", str(src), "-o", str(cubin)], check=True)
+    sass = subprocess.run(["cuobjdump", "-sass", str(cubin)], capture_output=True, text=True, check=True).stdout
+    assert "DMUL" in sass and "DADD" in sass and "DFMA" not in sass
+    assert "sm_100a" in sass or "SM100a" in sass.upper() or "EF_CUDA_SM100" in sass
