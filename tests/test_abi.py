@@ -413,7 +413,7 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_a_gpu(lib, tmp_path):
 
 def test_build_flags_keep_fp64_multiply_and_add_separate(tmp_path):
     """The GPU half of the bit-level contract: with the build's own nvcc flags (`-fmad=false`, sm_100a) `a*b+c` compiles to DMUL + DADD,
-    never DFMA, and sqrt / division are the IEEE round-to-nearest sequences (no `.approx` results reach the output)."""
+    never DFMA."""
     from ufemism_b200 import build as B
 
     assert "-fmad=false" in B.NVCC_FLAGS and "arch=compute_100a,code=sm_100a" in B.NVCC_FLAGS
