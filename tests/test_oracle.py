@@ -453,3 +453,58 @@ def test_gcc_code_generation_assumptions_behind_the_parity_contract(tmp_path):
         O.build()
         dis = subprocess.run(["objdump", "-d", os.path.join(os.path.dirname(O.__file__), "libufm_oracle.so")], capture_output=True, text=True, check=True).stdout
         assert not re.search(r"vfn?m(add|sub)", dis)
+
+
+def test_sor_sweep_is_a_dataflow_not_a_phase_order(mesh_2k):
+    """What the five colour phases (and the grid barriers of the CUDA sweep) really order: a row must see its lower-coloured neighbours
+    already updated and its higher-coloured ones not yet.  Any execution order that respects those per-row dependencies -- here a random
+    one that mixes all five colours -- gives the colour-by-colour result bit for bit."""
+    m = mesh_2k
+    M_ = m.nVAaAc
+    rng = np.random.default_rng(11)
+    U0 = rng.normal(0, 100.0, M_); V0 = rng.normal(0, 100.0, M_)
+    is_edge = np.concatenate([m.edge_index, m.edge_index_Ac]) > 0
+    colour = np.asarray(m.colour)
+    nbrs = [m.CAaAc[ai, :m.nCAaAc[ai]] - 1 for ai in range(M_)]
+
+    ref = _sor_system(m)
+    o = _sor_system(m)
+    o["U_SSA_AaAc"][:] = U0; o["V_SSA_AaAc"][:] = V0
+    o.solve_SSA_linearised(max_inner=1, force_iters=True)            # fills eu, ev, RHS (they do not depend on U, V)
+    eu, ev, rx, ry = (np.array(o[k]) for k in ("eu_i_AaAc", "ev_i_AaAc", "RHSx_AaAc", "RHSy_AaAc"))
+    U, V = U0.copy(), V0.copy()
+    omega = 1.2
+    Nxx, Nyy, Nxy = m.Nxx_AaAc, m.Nyy_AaAc, m.Nxy_AaAc
+    mixed = 0
+    for it in range(1, 3):
+        pending = np.array([0 if is_edge[ai] else int(np.sum((colour[nbrs[ai]] < colour[ai]) & ~is_edge[nbrs[ai]])) for ai in range(M_)])
+        ready = [ai for ai in range(M_) if not is_edge[ai] and pending[ai] == 0]
+        order = []
+        while ready:
+            ai = ready.pop(int(rng.integers(len(ready))))
+            order.append(ai)
+            n = m.nCAaAc[ai]
+            nb = nbrs[ai]
+            uxy = U[ai] * Nxy[ai, n]; vxy = V[ai] * Nxy[ai, n]           # get_mesh_curvatures_vertex_AaAc as coded: home value throughout
+            for c in range(n):
+                uxy = uxy + U[ai] * Nxy[ai, c]; vxy = vxy + V[ai] * Nxy[ai, c]
+            su = sv = 0.0
+            for c in range(n):
+                su = su + U[nb[c]] * (4.0 * Nxx[ai, c] + Nyy[ai, c])
+                sv = sv + V[nb[c]] * (4.0 * Nyy[ai, c] + Nxx[ai, c])
+            ru = ((su + (3.0 * vxy) + (eu[ai] * U[ai])) - rx[ai]) / eu[ai]
+            rv = ((sv + (3.0 * uxy) + (ev[ai] * V[ai])) - ry[ai]) / ev[ai]
+            U[ai] = U[ai] - omega * ru; V[ai] = V[ai] - omega * rv
+            for j in nb:
+                if not is_edge[j] and colour[j] > colour[ai]:
+                    pending[j] -= 1
+                    if pending[j] == 0:
+                        ready.append(j)
+        assert len(order) == int(np.sum(~is_edge))
+        c_seq = colour[np.array(order)]
+        mixed += int(np.sum(c_seq[1:] < c_seq[:-1]))                      # how often a lower colour ran after a higher one
+        o.apply_Neumann_boundary_AaAc(U); o.apply_Neumann_boundary_AaAc(V)
+        ref["U_SSA_AaAc"][:] = U0; ref["V_SSA_AaAc"][:] = V0
+        ref.solve_SSA_linearised(max_inner=it, force_iters=True)
+        assert np.array_equal(U, ref["U_SSA_AaAc"]) and np.array_equal(V, ref["V_SSA_AaAc"]), it
+    assert mixed > 1000                                                   # the order really was not colour by colour
