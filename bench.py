@@ -301,8 +301,18 @@ def run_ours(args):
             g.upload(k, st[k])
         return g.region(0.0)
 
-    def one_by_one(r, n, host=None):
+    def one_by_one(r, n, host=None, marks=None):
+        """`marks`: a list that receives one CUDA event before the first step and one after every step (per-step device times for the
+        "SSA solve time per step" report; the events cost nothing measurable and do not change what e0 / e1 bracket)."""
         rows = []
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                marks.append(ev)
+
+        mark()
         for _ in range(n):
             a = (r.n_sia, r.n_ssa, r.n_outer_total, r.n_sor_total)
             if host is None:
@@ -310,6 +320,7 @@ def run_ours(args):
             else:
                 g.run_model_host(r, 1e12, 1, host)
             rows.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
+            mark()
         return rows
 
     # ---------------- device-resident run: `value` ----------------
@@ -320,11 +331,20 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_model0 = r.time
+    marks = []
     e0.record(stream)
-    rows = one_by_one(r, args.steps)
+    rows = one_by_one(r, args.steps, marks=marks)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    step_ms = None
+    try:   # per-step device times (reporting only; never allowed to take the bench line down)
+        step_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(len(marks) - 1)]
+        if len(step_ms) != len(rows):
+            step_ms = None
+    except Exception as ex:  # noqa: BLE001
+        log(f"[bench] per-step times unavailable: {ex}")
+        step_ms = None
     clocks = sampler.stop() if sampler else None
     cnt = g.counters()
     yrs = r.time - t_model0
@@ -432,6 +452,17 @@ def run_ours(args):
                             "sor_share_of_step": cnt.sor_ms / ms},
                "ssa": {"model_years": yrs, "n_ssa_solves": int(sum(x["ssa"] for x in rows)), "n_outer": int(sum(x["n_outer"] for x in rows)),
                        "n_sor": int(sum(x["n_sor"] for x in rows))}}
+        if step_ms:
+            # "SSA solve time / step" (BASELINE metric): device time of the steps that ran solve_SSA minus that of the steps that did not
+            w_ = [t_ for t_, x in zip(step_ms, rows) if x["ssa"]]
+            wo = [t_ for t_, x in zip(step_ms, rows) if not x["ssa"]]
+            out["ssa"]["ms_per_step_with_ssa_solve"] = sum(w_) / len(w_) if w_ else None
+            out["ssa"]["ms_per_step_without_ssa_solve"] = sum(wo) / len(wo) if wo else None
+            if w_ and wo:
+                out["ssa"]["ms_per_ssa_solve"] = sum(w_) / len(w_) - sum(wo) / len(wo)
+                out["ssa"]["n_outer_per_solve"] = out["ssa"]["n_outer"] / max(out["ssa"]["n_ssa_solves"], 1)
+                out["ssa"]["n_sor_per_solve"] = out["ssa"]["n_sor"] / max(out["ssa"]["n_ssa_solves"], 1)
+            out["ssa"]["step_ms"] = [round(t_, 3) for t_ in step_ms]
         if regions:
             out["independent_regions_mode"] = regions
         if sor_forced:
