@@ -41,3 +41,96 @@ def test_roofline_denominator_is_the_measured_peak_when_present():
         assert peak == float(json.load(open(p))["hbm_gbs"]) and src.startswith("measured")
     else:
         assert src.startswith("fallback") and 6000.0 < peak < 8000.0
+
+
+def test_ours_arm_bookkeeping_with_a_fake_device(monkeypatch, capsys):
+    """bench.py's own arm end to end on a FAKE device: torch.cuda and the ctypes wrapper are replaced by stand-ins that only count, so
+    this checks the harness (warm-up / timed split, per-step marks, the JSON contract keys, the CPU leg at a small size) and nothing about
+    the product.  The real arm needs a B200 (`python bench.py`)."""
+    import argparse
+    import time
+
+    import torch
+
+    from ufemism_b200 import capi
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    class FakeStream:
+        cuda_stream = 0
+
+    class FakeModel:
+        def __init__(self, mesh, **kw):
+            self.cnt = capi.Counters()
+            self.cnt.sor_bytes_per_iteration = 200.0 * mesh.nVAaAc
+            self.k = 0
+
+        def upload_mesh(self, m): self.k = 0
+        def set_stream(self, s): pass
+        def upload(self, k, v): pass
+        def host_register(self, a): pass
+        def set_params(self, **kw): pass
+        def close(self): pass
+        def region(self, t): return capi.Region()
+        def reset_counters(self): self.cnt.kernel_launches = self.cnt.sor_iterations = self.cnt.sor_launches = 0; self.cnt.sor_ms = self.cnt.h2d_bytes = self.cnt.d2h_bytes = 0.0
+        def counters(self): return capi.Counters.from_buffer_copy(self.cnt)      # a snapshot, like ufm_counters_get
+
+        def _step(self, r, solve):
+            r.dt = 0.5; r.time += 0.5; r.n_steps += 1; r.n_sia += 1
+            self.cnt.kernel_launches += 7
+            if solve:
+                r.n_ssa += 1; r.n_outer_total += 50; r.n_sor_total += 150
+                self.cnt.kernel_launches += 150; self.cnt.sor_iterations += 150; self.cnt.sor_launches += 50; self.cnt.sor_ms += 0.05
+                time.sleep(0.002)
+
+        def run_model(self, r, t_end, max_steps=1):
+            self._step(r, self.k % 2 == 0); self.k += 1
+
+        def run_model_host(self, r, t_end, n, host):
+            self.cnt.h2d_bytes += 52e6; self.cnt.d2h_bytes += 76e6
+            self.run_model(r, t_end)
+
+        def ssa_sor(self, max_inner=0, force_iters=False):
+            self.cnt.sor_iterations += max_inner; self.cnt.sor_ms += 0.17 * max_inner; self.cnt.sor_launches += 1
+
+    class FakeSampler:
+        def __init__(self, index=0): pass
+        def stop(self): return {"sm_mhz": 1900.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3, "source": "fake"}
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "set_stream", lambda s: None)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(capi, "IceModelGPU", FakeModel)
+    monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
+    monkeypatch.setattr(bench, "cpu_unit_costs", lambda m, st, n: bench._cpu_unit_costs(m, st, n, 5, 1))   # keep the CPU leg to a second
+    monkeypatch.delenv("WORLD_SIZE", raising=False); monkeypatch.delenv("RANK", raising=False)
+    keep = os.path.join(ROOT, "gpurun_out", "config3_step_counts.json")
+    saved = open(keep).read() if os.path.exists(keep) else None
+    try:
+        bench.run_ours(argparse.Namespace(gpus=1, steps=4, warmup=3, impl="ours", nv=6000, exact_xy=1, no_cpu=False, no_regions=True, multi="partition"))
+    finally:
+        if saved is not None:
+            open(keep, "w").write(saved)
+    line = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks",
+              "e2e", "gpu_launches", "roofline", "cpu_baseline", "ssa"):
+        assert k in out, k
+    assert out["steps"] == 4 and out["warmup"] == 3 and out["n_gpus"] == 1 and out["dtype"] == "f64" and out["vs_baseline"] is None and "model" not in out["config"]
+    assert out["ssa"]["model_years"] == 2.0 and out["ssa"]["n_ssa_solves"] == 2 and out["gpu_launches"] == 4 * 7 + 2 * 150
+    assert len(out["ssa"]["step_ms"]) == 4 and out["ssa"]["ms_per_ssa_solve"] > 1.0 and out["ssa"]["n_sor_per_solve"] == 150.0
+    assert out["e2e"]["h2d_bytes_per_step"] == 52e6 and out["e2e"]["d2h_bytes_per_step"] == 76e6 and out["e2e"]["same_trajectory_as_value"]
+    assert set(out["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and out["roofline"]["bound"] == "hbm"
+    assert abs(out["roofline"]["frac"] - out["roofline"]["achieved"] / out["roofline"]["peak"]) < 1e-12
+    assert set(out["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and out["cpu_baseline"]["kind"] == "port"
