@@ -206,6 +206,13 @@ int ufm_mesh_secondary_get(ufm_handle *h, ufm_mesh_desc *out, const double **Tri
 int ufm_partition_set(ufm_handle *h, int rank, int nranks);
 /* host-only: owner rank (0..nranks-1) of each of the nV+nAc combined-mesh vertices, as ufm_mesh_upload will assign them */
 int ufm_partition_owners(const ufm_mesh_desc *mesh, int nranks, unsigned char *owner_out);
+/* host-only (planning / tests): the device row order ufm_mesh_upload derives from these per-row keys -- block (1..5 = colour of
+ * calculate_five_colouring_AaAc, src/mesh_five_colour_module.f90:18-137; 6 = domain-edge row), owner rank, partition-boundary flag,
+ * "late" flag, degree, Morton code, x coordinate.  n_bands = 0: (degree, Morton) inside a group, the default; n_bands > 0: the
+ * experimental x-band order selected by the environment variable UFM_ROW_ORDER=bands:<n>[:<window>].  Results of every kernel are
+ * independent of this order (rows of one colour are never neighbours). */
+int ufm_plan_row_order(int M, const unsigned char *block, const unsigned char *owner, const unsigned char *boundary, const unsigned char *late,
+                       const unsigned char *degree, const unsigned *morton, const double *X, int n_bands, int deg_window, int *order_out);
 int ufm_comm_export(ufm_handle *h, void *blob /* UFM_COMM_BLOB_BYTES */);
 int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_BYTES, in rank order */);
 

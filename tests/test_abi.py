@@ -454,3 +454,44 @@ def test_live_reference_citations_point_into_the_reference():
             if not (1 <= lo <= hi <= n_lines[p]):
                 bad.append((os.path.relpath(f, ROOT), what, f"file has {n_lines[p]} lines"))
     assert n > 300 and not bad, bad[:10]
+
+
+def test_device_row_order_matches_numpy(lib):
+    """ufm_plan_row_order = the host code ufm_mesh_upload orders the combined-mesh rows with.  Default order: block, owner, boundary, late,
+    degree, Morton -- equal to numpy's lexsort of the same keys (stable, index as the last key).  Experimental x-band order
+    (UFM_ROW_ORDER=bands:n:w): same groups; inside a group the bands ascend window by window apart from the degree sort inside
+    windows of w rows, and every window holds what the (band, Morton) order puts there."""
+    import numpy as np
+
+    rng = np.random.default_rng(3)
+    M = 50000
+    block = rng.integers(1, 7, M).astype(np.uint8)
+    owner = rng.integers(0, 2, M).astype(np.uint8)
+    boundary = (rng.random(M) < 0.05).astype(np.uint8)
+    late = np.where((block == 5) & (rng.random(M) < 0.02), 0, 1).astype(np.uint8)
+    degree = rng.integers(4, 9, M).astype(np.uint8)
+    morton = rng.integers(0, 2**32, M, dtype=np.uint64).astype(np.uint32)
+    X = rng.random(M) * 3.6e6 - 1.8e6
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.ufm_plan_row_order.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    order = np.empty(M, np.int32)
+    assert lib.ufm_plan_row_order(M, p(block), p(owner), p(boundary), p(late), p(degree), p(morton), p(X), 0, 4096, p(order)) == 0
+    want = np.lexsort((np.arange(M), morton, degree, late, boundary, owner, block))
+    assert np.array_equal(order, want)
+
+    nb, w = 16, 256
+    assert lib.ufm_plan_row_order(M, p(block), p(owner), p(boundary), p(late), p(degree), p(morton), p(X), nb, w, p(order)) == 0
+    assert np.array_equal(np.sort(order), np.arange(M))
+    band = np.minimum((X - X.min()) * (nb / (X.max() - X.min())), nb - 1).astype(np.int64)
+    base = np.lexsort((np.arange(M), morton, band, late, boundary, owner, block))         # before the windowed degree sort
+    gkey = lambda o: np.stack([block[o], owner[o], boundary[o], late[o]], 1)
+    assert np.array_equal(gkey(order), gkey(base))                                        # same groups in the same places
+    change = np.flatnonzero(np.any(np.diff(gkey(base), axis=0) != 0, axis=1)) + 1
+    for a, b in zip(np.r_[0, change], np.r_[change, M]):
+        for k in range(a, b, w):
+            win_o, win_b = order[k:min(k + w, b)], base[k:min(k + w, b)]
+            assert np.array_equal(np.sort(win_o), np.sort(win_b))                         # a window holds the rows (band, Morton) order puts there
+            assert np.all(np.diff(degree[win_o].astype(int)) >= 0)                        # sorted by degree inside the window
+            for dgr in np.unique(degree[win_o]):                                          # and stably: (band, Morton) order survives per degree
+                assert np.array_equal(win_o[degree[win_o] == dgr], win_b[degree[win_b] == dgr])
+    assert lib.ufm_plan_row_order(M, None, p(owner), p(boundary), p(late), p(degree), p(morton), p(X), 0, 4096, p(order)) == -2

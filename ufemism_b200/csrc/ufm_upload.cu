@@ -373,6 +373,79 @@ extern "C" int ufm_partition_owners(const ufm_mesh_desc *d, int nranks, unsigned
   return 0;
 }
 
+// Device row order of the AaAc mesh: block-major (blocks 1..5 = colours, 6 = domain-edge rows), then owner rank, partition-boundary rows
+// last, the colour-5 rows the Neumann pass reads first, and inside such a group
+//   n_bands == 0: (degree, Morton)                                            -- the order measured in DESIGN.md section 4
+//   n_bands  > 0: n_bands x-bands, Morton inside a band, the degree sorted only inside windows of deg_window rows (experimental; it
+//                 puts the rows a row depends on at nearly the same relative position of the previous colour block, which a sweep
+//                 without grid barriers between the colours needs: tools/sor_dataflow_analysis.py).
+// Results never depend on the order inside a colour block.  Host only; checked against numpy by tests/test_abi.py.
+static void ufm_row_order_impl(int M, const unsigned char *blkv, const unsigned char *owner, const unsigned char *isb, const unsigned char *late,
+                               const unsigned char *degv, const uint32_t *mort, const double *X, int n_bands, int deg_window, std::vector<int> &m_order)
+{
+  m_order.resize(M);
+  std::iota(m_order.begin(), m_order.end(), 0);
+  n_bands = std::max(0, std::min(n_bands, 65535));
+  deg_window = std::max(UFM_SLICE, deg_window);
+  auto group_less = [&](int a, int b, bool &equal) {
+    equal = false;
+    if (blkv[a] != blkv[b]) return blkv[a] < blkv[b];
+    if (owner[a] != owner[b]) return owner[a] < owner[b];
+    if (isb[a] != isb[b]) return isb[a] < isb[b];
+    if (late[a] != late[b]) return late[a] < late[b];
+    equal = true;
+    return false;
+  };
+  if (n_bands == 0) {
+    __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
+      bool eq;
+      const bool lt = group_less(a, b, eq);
+      if (!eq) return lt;
+      if (degv[a] != degv[b]) return degv[a] < degv[b];
+      return mort[a] < mort[b];
+    });
+    return;
+  }
+  double x0 = 1e300, x1 = -1e300;
+  for (int i = 0; i < M; i++) { x0 = std::min(x0, X[i]); x1 = std::max(x1, X[i]); }
+  std::vector<unsigned short> band(M);
+  const double bs = (double)n_bands / std::max(x1 - x0, 1e-300);
+  for (int i = 0; i < M; i++) band[i] = (unsigned short)std::min((double)(n_bands - 1), std::max(0.0, (X[i] - x0) * bs));
+  __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
+    bool eq;
+    const bool lt = group_less(a, b, eq);
+    if (!eq) return lt;
+    if (band[a] != band[b]) return band[a] < band[b];
+    return mort[a] < mort[b];
+  });
+  // window index of every row inside its group, then the degree sorted inside the windows (stable: band / Morton order survives)
+  std::vector<int> window(M);
+  for (int k = 0, start = 0; k < M; k++) {
+    bool eq = true;
+    if (k > 0) group_less(m_order[k - 1], m_order[k], eq);
+    if (!eq) start = k;
+    window[m_order[k]] = (k - start) / deg_window;
+  }
+  __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
+    bool eq;
+    const bool lt = group_less(a, b, eq);
+    if (!eq) return lt;
+    if (window[a] != window[b]) return window[a] < window[b];
+    return degv[a] < degv[b];
+  });
+}
+
+// host-only planning / test entry point (no device work): the row order ufm_mesh_upload would use for these keys
+extern "C" int ufm_plan_row_order(int M, const unsigned char *block, const unsigned char *owner, const unsigned char *boundary, const unsigned char *late,
+                                  const unsigned char *degree, const unsigned *morton, const double *X, int n_bands, int deg_window, int *order_out)
+{
+  if (M < 0 || !block || !owner || !boundary || !late || !degree || !morton || !X || !order_out) return ufm_set_error(-2, "ufm_plan_row_order: bad argument");
+  std::vector<int> o;
+  ufm_row_order_impl(M, block, owner, boundary, late, degree, morton, X, n_bands, deg_window, o);
+  memcpy(order_out, o.data(), sizeof(int) * (size_t)M);
+  return 0;
+}
+
 int ufm_mesh_free_impl(ufm_handle *h)
 {
   cudaDeviceSynchronize();   // nothing may still be reading the arrays that are handed back to the arena
@@ -487,8 +560,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     for (int ai = 0; ai < M; ai++)
       for (int c = 1; c <= degv[ai]; c++)
         if (owner[F2(d->CAaAc, ai + 1, c, ldM) - 1] != owner[ai]) { isb[ai] = 1; break; }
-  std::vector<int> m_order(M);
-  std::iota(m_order.begin(), m_order.end(), 0);
+  std::vector<int> m_order;
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
   // single-GPU layout: the colour-5 rows that the Neumann pass reads (non-edge rows adjacent to a domain-edge row) lead
   // their colour block, so that the pass can run inside the fifth colour phase as soon as those few slices are done
@@ -500,15 +572,16 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       for (int c = 1; c <= degv[ai]; c++)
         if (is_edge[F2(d->CAaAc, ai + 1, c, ldM) - 1]) { late[ai] = 0; n_adj5++; break; }
     }
-  __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
-    int ba = blk(a), bb = blk(b);
-    if (ba != bb) return ba < bb;
-    if (owner[a] != owner[b]) return owner[a] < owner[b];
-    if (isb[a] != isb[b]) return isb[a] < isb[b];
-    if (late[a] != late[b]) return late[a] < late[b];
-    if (degv[a] != degv[b]) return degv[a] < degv[b];
-    return mort[a] < mort[b];
-  });
+  // row order inside the colour blocks: (degree, Morton), or the experimental x-band order (UFM_ROW_ORDER=bands:<n>[:<window>])
+  int n_bands = 0, deg_window = 4096;
+  if (const char *e = getenv("UFM_ROW_ORDER")) {
+    if (sscanf(e, "bands:%d:%d", &n_bands, &deg_window) < 1) n_bands = 0;
+  }
+  {
+    std::vector<unsigned char> blkv(M);
+    for (int ai = 0; ai < M; ai++) blkv[ai] = (unsigned char)blk(ai);
+    ufm_row_order_impl(M, blkv.data(), owner.data(), isb.data(), late.data(), degv.data(), mort.data(), X.data(), n_bands, deg_window, m_order);
+  }
   std::vector<int> m_r2d(M), m_d2r;
   m_d2r.reserve((size_t)M + 12 * (size_t)P * UFM_CHUNK);
   {
