@@ -47,6 +47,14 @@ if len(rows) >= 3:
                 f.write(f"{h} [{u}] = {v}\n")
 EOF
 
+step "row-order probe: default (degree, Morton) vs x-bands (UFM_ROW_ORDER), 100 forced SOR iterations, checksum of U,V must agree"
+for ORDER in default bands:16 bands:64 bands:256; do
+  if [ "$ORDER" = default ]; then unset UFM_ROW_ORDER; else export UFM_ROW_ORDER=$ORDER; fi
+  timeout 300 python tools/sor_probe.py --iters 100 --reps 2 --checksum > $OUT/${TAG}_sor_probe_order_${ORDER/:/}.json 2> $OUT/${TAG}_sor_probe_order_${ORDER/:/}.err
+  echo "$ORDER rc=$?"; cut -c1-400 $OUT/${TAG}_sor_probe_order_${ORDER/:/}.json
+done
+unset UFM_ROW_ORDER
+
 step "ncu --set full: fused viscosity + setup kernel (inside a real solve)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ssa_viscosity -s 2 -c 1 -f -o $OUT/visc_${TAG} \
   python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_visc.log 2>&1

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--order", default="random")
     ap.add_argument("--others", action="store_true", help="also time the per-step kernels")
     ap.add_argument("--thermo", action="store_true", help="time update_ice_temperature (row N2) on the same mesh, EISMINT ice properties")
+    ap.add_argument("--checksum", action="store_true", help="add a sha256 of the downloaded (U, V) after the timed iterations (row-order experiments must not change it)")
     ap.add_argument("--variants", default="", help="semicolon-separated env settings to compare in one process, e.g. "
                     "'UFM_SOR_CHUNK=1;UFM_SOR_CHUNK=1,UFM_SOR_BAR=1' (the library re-reads them on every SOR launch)")
     a = ap.parse_args()
@@ -53,6 +54,12 @@ def main():
     cn = g.counters()
     out = {"ranks": world, "nV": m.nV, "M": m.nVAaAc, "exact_xy": a.exact_xy, "iters": a.iters, "us_per_iteration": res,
            "algorithmic_GB": cn.sor_bytes_per_iteration / 1e9, "achieved_GBps_best": cn.sor_bytes_per_iteration / (min(res) * 1e-6) / 1e9}
+    if a.checksum:
+        import hashlib
+
+        import numpy as np
+        out["row_order"] = os.environ.get("UFM_ROW_ORDER", "default")
+        out["uv_sha256"] = hashlib.sha256(np.ascontiguousarray(g.download("U_SSA_AaAc")).tobytes() + np.ascontiguousarray(g.download("V_SSA_AaAc")).tobytes()).hexdigest()
     if a.variants:
         import numpy as np
         base = None
