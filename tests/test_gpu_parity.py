@@ -172,6 +172,29 @@ def test_sor_schedule_variants_bit_exact(mesh_10k, monkeypatch, variant):
     assert st.last_max_residual == res
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("UFM_TEST_EXPERIMENTAL"), reason="experimental device row order, not measured yet: run with UFM_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("order", ["bands:16:256", "bands:64", "bands:3:32"])
+def test_experimental_band_row_order_bit_exact(mesh_10k, monkeypatch, order):
+    """UFM_ROW_ORDER=bands:n[:window] (x-bands, Morton inside a band, degree sorted inside windows; groundwork for a sweep without grid
+    barriers between colours) only moves rows inside their colour block: geometry, the SOR sweep at a prescribed
+    count and the whole solve must give the oracle's bits / counts exactly as the default order does."""
+    monkeypatch.setenv("UFM_ROW_ORDER", order)
+    o, g = _ssa_setup_pair(mesh_10k, nthreads=8)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=57, force_iters=True)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    st = g.ssa_sor(max_inner=57, force_iters=True)
+    assert st.n_inner_last == 57 == n
+    assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
+    assert_bits_equal(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
+    assert st.last_max_residual == res
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert (sg.n_outer, sg.n_inner_total) == (so.n_outer, so.n_inner_total)
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10 and rel_l2(g.download("V_SSA"), o["V_SSA"]) <= 1e-10
+
+
 def test_sor_presummed_xy_within_tolerance(mesh_10k):
     o, g = _ssa_setup_pair(mesh_10k, exact_xy=0)
     o.basal_yield_stress(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()

@@ -47,6 +47,10 @@ if len(rows) >= 3:
                 f.write(f"{h} [{u}] = {v}\n")
 EOF
 
+step "experimental tests (skipped in the default suite): x-band row order must be bit-identical"
+UFM_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k experimental > $OUT/${TAG}_gpu_experimental.log 2>&1
+echo "rc=$?"; tail -3 $OUT/${TAG}_gpu_experimental.log
+
 step "row-order probe: default (degree, Morton) vs x-bands (UFM_ROW_ORDER), 100 forced SOR iterations, checksum of U,V must agree"
 for ORDER in default bands:16 bands:64 bands:256; do
   if [ "$ORDER" = default ]; then unset UFM_ROW_ORDER; else export UFM_ROW_ORDER=$ORDER; fi
