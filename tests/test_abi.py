@@ -495,3 +495,26 @@ def test_device_row_order_matches_numpy(lib):
             for dgr in np.unique(degree[win_o]):                                          # and stably: (band, Morton) order survives per degree
                 assert np.array_equal(win_o[degree[win_o] == dgr], win_b[degree[win_b] == dgr])
     assert lib.ufm_plan_row_order(M, None, p(owner), p(boundary), p(late), p(degree), p(morton), p(X), 0, 4096, p(order)) == -2
+
+
+def test_kernel_resources_fit_the_launch_configurations(lib):
+    """Static guard (cuobjdump, no GPU): the persistent SOR kernel runs 1024 threads per CTA, one CTA per SM, so it must stay within
+    64 registers per thread and must not spill more than a few bytes; the library holds sm_100a code only."""
+    import shutil
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import kernel_resources as K
+
+    elfs = subprocess.run(["cuobjdump", "-lelf", K.LIB], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert all("sm_100a" in ln for ln in elfs if ln.strip())
+    rows = K.resources()
+    names = K.demangle([r[0] for r in rows])
+    sor = [(names[fn], reg, stack) for fn, reg, stack, _, _ in rows if names[fn].startswith("void k_ssa_sor<")]
+    assert len(sor) == 8                                              # <EXACT, GLFIX, MULTI>
+    for name, reg, stack in sor:
+        assert reg <= 64 and stack <= 32, (name, reg, stack)
+    by_name = {re.sub(r"\(.*", "", names[fn]): (reg, stack) for fn, reg, stack, _, _ in rows}
+    assert by_name["void k_ssa_viscosity<false, 4>"][0] <= 64          # __launch_bounds__(256, 4): the default fused viscosity kernel
+    assert len(rows) >= 40
