@@ -518,3 +518,18 @@ def test_kernel_resources_fit_the_launch_configurations(lib):
     by_name = {re.sub(r"\(.*", "", names[fn]): (reg, stack) for fn, reg, stack, _, _ in rows}
     assert by_name["void k_ssa_viscosity<false, 4>"][0] <= 64          # __launch_bounds__(256, 4): the default fused viscosity kernel
     assert len(rows) >= 40
+
+
+def test_every_environment_switch_is_documented():
+    import glob
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    used = set()
+    for f in glob.glob(os.path.join(ROOT, "ufemism_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "ufemism_b200", "*.py")):
+        if f.endswith((".o", ".so")):
+            continue
+        used |= set(re.findall(r'getenv\("(UFM_\w+)"\)|environ(?:\.get)?[\[(]\s*"(UFM_\w+)"', open(f, errors="replace").read()))
+    names = {a or b for a, b in used}
+    assert len(names) >= 12
+    for n in sorted(names):
+        assert n in doc, f"{n} is read by the library but missing from INTEGRATION.md"
