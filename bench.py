@@ -29,27 +29,39 @@ sys.path.insert(0, ROOT)
 
 METRIC = "model_yr_per_wall_hr"
 UNIT = "model-yr/wall-hr"
-COUNTS_FILE = os.path.join(ROOT, "profiles", "config3_step_counts.json")
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_workload(nv, seed=20211103):
+def build_workload(nv, seed=20211103, order="random"):
+    """BASELINE configs[2].  `order` is the HOST vertex numbering the reference-layout arrays are built in: "random" mimics the poor index
+    locality of refinement-ordered meshes (the default, as in round 1), "morton" is a locality-preserving numbering (the CPU arm's best case).
+    The device path renumbers at upload and does not care."""
     from ufemism_b200 import mesh as M
     from ufemism_b200 import scenarios as S
 
     c = S.CONFIG3
     t = time.time()
-    m = M.square_mesh_with_nv(c["half_width"], nv, seed=seed, order="random")
+    m = M.square_mesh_with_nv(c["half_width"], nv, seed=seed, order=order)
     st = S.state_ssa_icestream(m, scale=1.0, Hb=c["Hb"], H_shelf=c["H_shelf"])
-    log(f"[bench] mesh nV={m.nV} nAc={m.nAc} nVAaAc={m.nVAaAc} built in {time.time() - t:.1f}s")
+    log(f"[bench] mesh nV={m.nV} nAc={m.nAc} nVAaAc={m.nVAaAc} (host vertex order: {order}) built in {time.time() - t:.1f}s")
     return m, st
 
 
 def workload_name(m):
     return f"config3_ssa_icestream_flatbed_nV{m.nV}_AaAc{m.nVAaAc}_MISMIP_mod_GLflux"
+
+
+def bench_config(m, args, world):
+    """The `config` object of the JSON line -- the SAME function in both arms, so the driver's same_config check compares like with like."""
+    part = world > 1 and args.multi == "partition"
+    return {"workload": workload_name(m),
+            "parallelism": (f"one region, vertex-partitioned into {world} x-strips (one per GPU), NVLink P2P halo pushes" if part
+                            else f"{world} independent region(s), one per GPU (no data-path collective)"),
+            "flush": "inputs larger than L2 (SOR streams ~1 GB of coefficients per iteration)", "exact_xy": int(args.exact_xy),
+            "host_vertex_order": args.order}
 
 
 class ClockSampler:
@@ -219,57 +231,149 @@ def ssa_solve_time(step_ms, rows):
         return {}
 
 
-def load_counts(nv, n):
-    """Per-step iteration counts of this workload (identical on CPU and GPU by the parity tests), recorded by the GPU arm."""
-    if os.path.exists(COUNTS_FILE):
-        c = json.load(open(COUNTS_FILE))
-        if abs(c.get("nV", 0) - nv) <= 0.02 * nv and len(c.get("steps", [])) >= n:
-            return c["steps"][:n], f"iteration counts from {os.path.relpath(COUNTS_FILE, ROOT)}"
-    return None, None
+# ------------------------------------------------------------------------------------------------
+# CPU restatement run FOR REAL: the same region loop, step by step, on all host cores -- the CPU arm and the full-size parity check
+# ------------------------------------------------------------------------------------------------
+PARITY_FIELDS = ("Hi", "U_SSA", "V_SSA")
+PARITY_GATES = {"rel_l2_U": 1e-10, "rel_l2_V": 1e-10, "rel_l2_Hi": 1e-8}   # north_star; stop tests at ice_dynamics_module.f90:601-691
 
 
-def counts_from_small_oracle(n_steps, nthreads):
-    """Fallback: iteration counts from the oracle itself on a 1/16-size mesh of the same geometry."""
-    m, st = build_workload(62500)
+def cpu_trajectory(m, st, nthreads, n_warm, n_steps):
+    """n_warm + n_steps passes of ora_run_model (max_steps = 1) from the workload's start state.  Returns per-step wall seconds and
+    iteration counts, the model time, and the final Hi / U_SSA / V_SSA (reference vertex order)."""
     from oracle.oracle import Oracle
 
     o = Oracle(m, benchmark=st["benchmark"], nthreads=nthreads, use_analytical_GL_flux=1)
     for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
         o[k][:] = st[k]
     r = o.region(0.0)
-    steps = []
-    for _ in range(n_steps):
+    rows, secs = [], []
+    t_warm_end = 0.0
+    for k in range(n_warm + n_steps):
         a = (r.n_sia, r.n_ssa, r.n_outer_total, r.n_sor_total)
+        t = time.perf_counter()
         o.run_model(r, 1e12, max_steps=1)
-        steps.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
-    return steps, "iteration counts from the oracle on a 62.5k-vertex mesh of the same geometry (counts file absent)"
+        secs.append(time.perf_counter() - t)
+        rows.append(dict(dt=r.dt, sia=int(r.n_sia - a[0]), ssa=int(r.n_ssa - a[1]), n_outer=int(r.n_outer_total - a[2]), n_sor=int(r.n_sor_total - a[3])))
+        if k == n_warm - 1:
+            t_warm_end = r.time
+    return {"rows": rows, "step_s": secs, "time": r.time, "time_after_warmup": t_warm_end,
+            "fields": {f: np.array(o[f], dtype=np.float64, copy=True) for f in PARITY_FIELDS}}
+
+
+def field_digest(fields):
+    import hashlib
+
+    return {f: hashlib.sha256(np.ascontiguousarray(fields[f]).tobytes()).hexdigest()[:16] for f in PARITY_FIELDS}
+
+
+def parity_report(gpu_fields, gpu_rows, gpu_time, cpu):
+    """GPU trajectory vs the CPU restatement's on the same mesh and inputs after the same steps (north_star gates)."""
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+    cr = cpu["rows"]
+    n = min(len(cr), len(gpu_rows))
+    out = {"rel_l2_U": rel(gpu_fields["U_SSA"], cpu["fields"]["U_SSA"]), "rel_l2_V": rel(gpu_fields["V_SSA"], cpu["fields"]["V_SSA"]),
+           "rel_l2_Hi": rel(gpu_fields["Hi"], cpu["fields"]["Hi"]),
+           "max_abs_dHi_m": float(np.max(np.abs(gpu_fields["Hi"] - cpu["fields"]["Hi"]))),
+           "n_sor_equal": all(cr[k]["n_sor"] == gpu_rows[k]["n_sor"] for k in range(n)),
+           "n_outer_equal": all(cr[k]["n_outer"] == gpu_rows[k]["n_outer"] for k in range(n)),
+           "dt_equal": all(cr[k]["dt"] == gpu_rows[k]["dt"] for k in range(n)),
+           "steps_compared": n, "model_time_equal": bool(cpu["time"] == gpu_time),
+           "bit_identical": {f: bool(np.array_equal(gpu_fields[f], cpu["fields"][f])) for f in PARITY_FIELDS},
+           "gates": PARITY_GATES, "umax_m_per_yr": float(np.max(np.abs(cpu["fields"]["U_SSA"])))}
+    out["passed"] = bool(all(out[k] <= g for k, g in PARITY_GATES.items()) and out["n_sor_equal"] and out["n_outer_equal"] and out["dt_equal"])
+    return out
+
+
+def cpu_line(traj, n_warm, nthreads, m, what):
+    timed_s = float(sum(traj["step_s"][n_warm:]))
+    yrs = traj["time"] - traj["time_after_warmup"]
+    n = max(len(traj["step_s"]) - n_warm, 1)
+    return {"value": yrs / timed_s * 3600.0, "unit": UNIT, "cores": nthreads, "kind": "port", "ms_per_step": timed_s / n * 1e3,
+            "sample": (f"{what}: the oracle's region loop run for real on the {m.nV}-vertex workload, {n_warm} warm-up + {n} timed steps "
+                       f"({sum(traj['step_s']):.1f} s of CPU work on {nthreads} threads), same steps as the GPU arm"),
+            "model_years": yrs, "n_sor": int(sum(x["n_sor"] for x in traj["rows"][n_warm:])), "n_outer": int(sum(x["n_outer"] for x in traj["rows"][n_warm:]))}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     nthreads = os.cpu_count() or 1
-    m, st = build_workload(args.nv)
-    T = cpu_unit_costs(m, st, nthreads)
-    total = args.warmup + args.steps
-    steps, how = load_counts(m.nV, total)
-    if steps is None:
-        steps, how = counts_from_small_oracle(total, nthreads)
-    timed = steps[args.warmup:]
-    yrs = sum(s["dt"] for s in timed)
-    secs = sum(cpu_step_seconds(T, s["sia"], s["ssa"], s["n_outer"], s["n_sor"]) for s in timed)
-    value = yrs / secs * 3600.0
-    sample = (f"{T['sample_reps']} passes of every hot-path routine + {T['sample_sor_iterations']} forced SOR iterations at full size ({m.nV} vertices, {T['sample_seconds']:.1f} s of CPU work), "
-              f"scaled per step by its iteration counts; {how}")
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": secs / max(len(timed), 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": workload_name(m), "flush": "inputs larger than L2"},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
-                            "unit_costs_s": {k: round(v, 6) for k, v in T.items()}},
-           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    m, st = build_workload(args.nv, order=args.order)
+    t = time.time()
+    traj = cpu_trajectory(m, st, nthreads, args.warmup, args.steps)
+    log(f"[bench] CPU trajectory: {args.warmup}+{args.steps} steps in {time.time() - t:.1f}s")
+    base = cpu_line(traj, args.warmup, nthreads, m, "CPU restatement (oracle/)")
+    # for the record / the GPU arm's cross-check: final fields of this trajectory
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez(os.path.join(ROOT, "gpurun_out", "reference_arm_trajectory.npz"), workload=workload_name(m), order=args.order, warmup=args.warmup, steps=args.steps,
+                 rows=json.dumps(traj["rows"]), step_s=np.array(traj["step_s"]), time=traj["time"], **traj["fields"])
+    except Exception as ex:  # noqa: BLE001
+        log(f"[bench] could not write the trajectory file: {ex}")
+    base["final_field_sha256_16"] = field_digest(traj["fields"])
+    # the same job on the other host vertex numbering (locality-preserving if the main one is random and vice versa): the restatement keeps the
+    # reference's strided column-major ELL rows, so its speed depends on the numbering the mesh generator happened to produce
+    other = "morton" if args.order == "random" else "random"
+    if not args.no_other_order:
+        try:
+            m2, st2 = build_workload(args.nv, order=other)
+            t = time.time()
+            traj2 = cpu_trajectory(m2, st2, nthreads, args.warmup, args.steps)
+            log(f"[bench] CPU trajectory ({other} order): {time.time() - t:.1f}s")
+            base["other_host_vertex_order"] = dict(cpu_line(traj2, args.warmup, nthreads, m2, f"same job, host vertex order '{other}'"), order=other)
+            del m2, st2, traj2
+        except Exception as ex:  # noqa: BLE001
+            base["other_host_vertex_order"] = {"error": str(ex)}
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong" if (world > 1 and args.multi == "partition") else "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(m, args, world),
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
            "note": "CPU restatement of the Fortran hot path (oracle/), bit-identical to the reference's own source run through oracle/f90py.py (tests/test_reference_source.py); the Fortran reference itself cannot be built here (no gfortran/MPI/NetCDF)"}
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Per-step streaming kernels: algorithmic bytes of SURVEY 8(d) (from the actual degree sums) / CUDA-event time
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(m):
+    N, E, M = m.nV, m.nAc, m.nVAaAc
+    dAa, dM = float(np.sum(m.nC)), float(np.sum(m.nCAaAc))
+    return {"geom": 200.0 * N + 20.0 * dAa + 290.0 * E,          # K-GEOM: one update_general_ice_model_data (benchmark flow factor)
+            "sia": 84.0 * E + 28.0 * N + 4.0 * dAa,              # K-SIA: D_SIA_3D kept in registers, scalar A
+            "thk": 60.0 * N + 44.0 * dAa,                        # K-THK
+            "cfl": 24.0 * E + 40.0 * N,                          # K-CFL (no thermodynamics)
+            "visc": 80.0 * M + 20.0 * dM + 130.0 * M}            # K-VISC (+RN) and K-SLID+LIN: one fused launch here
+
+
+def kernel_rooflines(g, m, torch, stream, peak, reps=12):
+    """Every per-step routine launched `reps` times round robin (so each one finds the L2 full of the others' data: ~2 GB go through
+    between two launches of the same routine), each call bracketed by CUDA events on the library's stream, nothing else in between."""
+    calls = {"geom": lambda: g.update_general_ice_model_data(0.0), "sia": g.solve_SIA, "thk": lambda: g.calculate_ice_thickness_change(0.0),
+             "cfl": g.determine_timesteps, "visc": g.ssa_viscosity}
+    g.update_general_ice_model_data(0.0); g.ssa_prepare()
+    ev = {k: [] for k in calls}
+    for rep in range(reps + 2):
+        for k, fn in calls.items():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream)
+            if rep >= 2:
+                ev[k].append((e0, e1))
+    torch.cuda.synchronize()
+    B = algorithmic_bytes(m)
+    out = {}
+    for k, pairs in ev.items():
+        ms = float(np.median([a.elapsed_time(b) for a, b in pairs]))
+        gbs = B[k] / (ms * 1e-3) / 1e9
+        out[k] = {"ms": ms, "algorithmic_bytes": B[k], "achieved_GBps": gbs, "frac": gbs / peak}
+    out["how"] = (f"median of {reps} launches per routine, round robin, CUDA events around each call on the library's stream; thk at dt = 0 (same reads and writes); "
+                  "cfl includes its 3-scalar device-to-host read; visc = viscosity + RN partials + sliding term + linear-system setup in one launch (+ the 64-CTA sum)")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -300,7 +404,7 @@ def run_ours(args):
     #   src/UFEMISM_program.f90:194-229); per-GPU work fixed -> "weak" scaling, no data-path communication.
     part = world > 1 and args.multi == "partition"
     dev = torch.device("cuda", local)
-    m, st = build_workload(args.nv)
+    m, st = build_workload(args.nv, order=args.order)
     t = time.time()
     g = IceModelGPU(m, benchmark=st["benchmark"], device=local, rank=rank if part else 0, nranks=world if part else 1,
                     use_analytical_GL_flux=S.CONFIG3["use_analytical_GL_flux"], exact_xy=args.exact_xy)
@@ -370,6 +474,8 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     cnt = g.counters()
     yrs = r.time - t_model0
+    gpu_time_final = r.time
+    gpu_fields = {f: g.download(f) for f in PARITY_FIELDS} if rank == 0 else None   # after the timed region: what the parity check compares
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -459,10 +565,7 @@ def run_ours(args):
         achieved = cnt.sor_bytes_per_iteration / t_iter / 1e9 if cnt.sor_iterations else 0.0
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if part else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(m),
-                          "parallelism": (f"one region, SSA solve vertex-partitioned into {world} x-strips, NVLink P2P pushes after each colour sweep (CUDA IPC), per-step streaming kernels replicated"
-                                          if part else f"{world} independent region(s), one per GPU (no data-path collective)"),
-                          "flush": "inputs larger than L2 (SOR streams ~1 GB of coefficients per iteration)", "exact_xy": int(args.exact_xy)},
+               "config": bench_config(m, args, world),
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cnt2.h2d_bytes / args.steps, "d2h_bytes_per_step": cnt2.d2h_bytes / args.steps,
                        "ms_per_step": ms2 / args.steps, "same_trajectory_as_value": bool(same)},
@@ -483,17 +586,29 @@ def run_ours(args):
             for v in sor_forced.values():
                 v["frac"] = v["achieved_GBps"] / pk
             out["roofline"]["steady_state_100_forced_iterations"] = sor_forced
-        # record the per-step counts for the CPU arms
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        json.dump({"nV": m.nV, "warmup": args.warmup, "steps": warm_rows + rows}, open(os.path.join(ROOT, "gpurun_out", "config3_step_counts.json"), "w"))
+        if world == 1:
+            try:
+                out["roofline_kernels"] = kernel_rooflines(g, m, torch, stream, peak)
+            except Exception as ex:  # noqa: BLE001  (reporting only)
+                out["roofline_kernels"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu:
+            # the CPU restatement runs the SAME warm-up + timed steps for real: the CPU baseline and the full-size parity check in one
             nthreads = os.cpu_count() or 1
-            T = cpu_unit_costs(m, st, nthreads)
-            secs = sum(cpu_step_seconds(T, s["sia"], s["ssa"], s["n_outer"], s["n_sor"]) for s in rows)
-            out["cpu_baseline"] = {"value": yrs / secs * 3600.0, "unit": UNIT, "cores": nthreads, "kind": "port",
-                                   "sample": (f"{T['sample_reps']} passes of every hot-path routine + {T['sample_sor_iterations']} forced SOR iterations at full size ({m.nV} vertices, "
-                                              f"{T['sample_seconds']:.1f} s of CPU work), scaled by this run's own per-step iteration counts"),
-                                   "unit_costs_s": {k: round(v, 6) for k, v in T.items()}}
+            t = time.time()
+            traj = cpu_trajectory(m, st, nthreads, args.warmup, args.steps)
+            log(f"[bench] CPU trajectory: {args.warmup}+{args.steps} steps in {time.time() - t:.1f}s")
+            out["cpu_baseline"] = cpu_line(traj, args.warmup, nthreads, m, "CPU restatement (oracle/)")
+            out["parity"] = parity_report(gpu_fields, warm_rows + rows, gpu_time_final, traj)
+            out["parity"]["what"] = (f"device-resident GPU run vs the CPU restatement on the same {m.nV}-vertex mesh and inputs after the same {args.warmup + args.steps} steps "
+                                     "(Hi, U_SSA, V_SSA in reference vertex order; iteration counts and dt per step)")
+            ref_file = os.path.join(ROOT, "gpurun_out", "reference_arm_trajectory.npz")
+            if os.path.exists(ref_file):   # the --impl reference arm ran here before: its final fields must be the ones this arm's CPU run produced
+                try:
+                    z = np.load(ref_file)
+                    if str(z["workload"]) == workload_name(m) and int(z["warmup"]) == args.warmup and int(z["steps"]) == args.steps and str(z["order"]) == args.order:
+                        out["parity"]["reference_arm_file_bit_identical"] = bool(all(np.array_equal(z[f], traj["fields"][f]) for f in PARITY_FIELDS))
+                except Exception:  # noqa: BLE001
+                    pass
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -507,7 +622,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nv", type=int, default=1000000)
     ap.add_argument("--exact-xy", dest="exact_xy", type=int, default=1)
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU restatement run (no cpu_baseline, no parity object)")
+    ap.add_argument("--order", default="random", choices=["random", "morton", "lattice"], help="host vertex numbering of the workload mesh (see build_workload)")
+    ap.add_argument("--no-other-order", dest="no_other_order", action="store_true", help="--impl reference: skip the second trajectory on the other host vertex numbering")
+    ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the legs after the headline (configs 1, 2, 4, warm-state solve)")
     ap.add_argument("--no-regions", action="store_true", help="N > 1: skip the extra independent-regions measurement")
     ap.add_argument("--multi", default="partition", choices=["partition", "regions"], help="what N > 1 GPUs do (see run_ours)")
     args = ap.parse_args()

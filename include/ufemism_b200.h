@@ -222,6 +222,9 @@ int ufm_state_download(ufm_handle *h, int field, void *host);
 /* 1 when `field` can be copied with the resident mesh and parameters (Ti needs realistic flow factors or a thermodynamics mesh,
  * W_3D / GHF / T2m a thermodynamics mesh), 0 when not, < 0 on a bad handle / field id */
 int ufm_field_resident(ufm_handle *h, int field);
+/* sizes of what is resident: dims[0] = 1 when a mesh is resident (else 0 and the rest 0), dims[1] = nV, dims[2] = nAc,
+ * dims[3] = nVAaAc = nV + nAc (mesh%nV, mesh%nAc, mesh%nVAaAc: src/data_types_module.f90:216-345), dims[4] = C%nZ */
+int ufm_resident_dims(ufm_handle *h, int dims[5]);
 
 /* Page-lock a host array (e.g. one of the Fortran host's MPI shared-memory windows, src/parallel_module.f90:144-160) so that
  * ufm_state_upload / ufm_state_download DMA it directly instead of bouncing through a staging buffer.  Optional. */

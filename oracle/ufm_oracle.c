@@ -1383,9 +1383,14 @@ void ora_region_init(ora_region *r, double start_time)
 int ora_run_model(const ora_mesh *m, ora_ice *ice, const ora_config *c, ora_region *r, double t_end, long max_steps)
 {
   long steps = 0;
+  /* the thermodynamics timer runs on C%dt_thermo (src/UFEMISM_main_model.f90:369,797) */
+  if (c->dt_thermo > 0.0 && r->n_steps == 0 && r->dtc[ORA_T_THERMO] != c->dt_thermo) {
+    r->dtc[ORA_T_THERMO] = c->dt_thermo;
+    r->t1[ORA_T_THERMO] = r->t0[ORA_T_THERMO] + c->dt_thermo;
+  }
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
-    /* run_ELRA_model: benchmark -> t0_ELRA = time */
-    r->t0[ORA_T_ELRA] = r->time;
+    /* run_ELRA_model (src/bedrock_ELRA_module.f90:22-66): benchmark -> t0_ELRA = time; realistic -> only when the deformation rate is due */
+    if (c->benchmark != ORA_BM_NONE || r->do_[ORA_T_ELRA]) r->t0[ORA_T_ELRA] = r->time;
     ora_calculate_ice_thickness_change(m, ice, c, r->dt);
     ora_update_general_ice_model_data(m, ice, c, r->time);
     if (r->do_[ORA_T_SIA]) { ora_solve_SIA(m, ice, c); r->t0[ORA_T_SIA] = r->time; r->n_sia++; }

@@ -148,15 +148,22 @@ def test_sor_bit_exact_at_prescribed_iterations(mesh_10k, k, nthreads):
 
 
 @pytest.mark.parametrize("variant", [
-    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
-    {"UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
-    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "0"},
-    {"UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "1"},
-    {"UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "1"},
-], ids=["plain", "equal_share", "fused_neumann", "release_barrier", "default"])
+    {"UFM_SOR_DATAFLOW": "0", "UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_DATAFLOW": "0", "UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_DATAFLOW": "0", "UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "0"},
+    {"UFM_SOR_DATAFLOW": "0", "UFM_SOR_CHUNK": "0", "UFM_SOR_FUSE_BC": "0", "UFM_SOR_BAR": "1"},
+    {"UFM_SOR_DATAFLOW": "0", "UFM_SOR_CHUNK": "1", "UFM_SOR_FUSE_BC": "1", "UFM_SOR_BAR": "1"},
+    {"UFM_SOR_DATAFLOW": "1"},
+    {"UFM_SOR_DATAFLOW": "1", "UFM_SOR_GRID": "2"},
+    {"UFM_SOR_DATAFLOW": "1", "UFM_SOR_GRID": "1"},
+    {"UFM_SOR_DATAFLOW": "1", "UFM_SOR_GRID": "7", "UFM_ROW_ORDER": "bands:5:64"},
+], ids=["plain", "equal_share", "fused_neumann", "release_barrier", "barrier_default", "dataflow", "dataflow_2_ctas", "dataflow_1_cta", "dataflow_7_ctas_5_bands"])
 def test_sor_schedule_variants_bit_exact(mesh_10k, monkeypatch, variant):
-    """The SOR kernel's scheduling switches (equal slice shares per warp, Neumann pass inside the fifth colour phase,
-    release/acquire grid barrier) only reorder work inside a colour phase: every variant must give the oracle's bits."""
+    """The SOR kernels only reorder work: the barrier kernel's scheduling switches (equal slice shares per warp, Neumann pass inside the
+    fifth colour phase, release/acquire grid barrier) inside a colour phase, the dataflow kernel (the single-GPU default; no grid barrier
+    between the colours, every slice waits for the stage holding its lower-coloured neighbours) across the colours of one iteration.
+    UFM_SOR_GRID shrinks the grid so that this small mesh is swept in several rounds per colour (at 2 CTAs: 4-5 rounds).  Every variant
+    must give the oracle's bits."""
     for k_, v_ in variant.items():
         monkeypatch.setenv(k_, v_)
     o, g = _ssa_setup_pair(mesh_10k, nthreads=8)
@@ -190,6 +197,29 @@ def test_experimental_band_row_order_bit_exact(mesh_10k, monkeypatch, order):
     assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
     assert_bits_equal(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
     assert st.last_max_residual == res
+    so, sg = o.solve_SSA(), g.solve_SSA()
+    assert (sg.n_outer, sg.n_inner_total) == (so.n_outer, so.n_inner_total)
+    assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10 and rel_l2(g.download("V_SSA"), o["V_SSA"]) <= 1e-10
+
+
+def test_dataflow_sor_at_250k_vertices_bit_exact():
+    """The dataflow sweep at a size where the full grid (148 x 32 warps) sweeps every colour in two rounds: forced iterations and the
+    whole solve_SSA against the oracle -- bit-exact sweep, identical iteration counts."""
+    m = get_mesh(250000, half_width=S.CONFIG3["half_width"])
+    st = S.state_ssa_icestream(m, scale=1.0, Hb=S.CONFIG3["Hb"], H_shelf=S.CONFIG3["H_shelf"])   # the bench workload at a quarter of its size
+    o, g = make_oracle(m, st, nthreads=16, use_analytical_GL_flux=1), make_gpu(m, st, use_analytical_GL_flux=1)
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    o.basal_yield_stress(); o.calculate_GL_flux(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    n, res, _, _ = o.solve_SSA_linearised(max_inner=12, force_iters=True)
+    for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
+        g.upload(f, o[f])
+    st_ = g.ssa_sor(max_inner=12, force_iters=True)
+    assert st_.n_inner_last == 12 == n
+    assert_bits_equal(g.download("U_SSA_AaAc"), o["U_SSA_AaAc"], "U_SSA_AaAc")
+    assert_bits_equal(g.download("V_SSA_AaAc"), o["V_SSA_AaAc"], "V_SSA_AaAc")
+    assert st_.last_max_residual == res
+    o.cfg.SSA_max_outer_loops = 6; g.set_params(SSA_max_outer_loops=6)
     so, sg = o.solve_SSA(), g.solve_SSA()
     assert (sg.n_outer, sg.n_inner_total) == (so.n_outer, so.n_inner_total)
     assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10 and rel_l2(g.download("V_SSA"), o["V_SSA"]) <= 1e-10

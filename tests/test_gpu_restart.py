@@ -123,6 +123,33 @@ def test_restart_and_help_fields_written_from_the_device(mesh_2k, tmp_path):
         assert_bits_equal(g2.download(n), g.download(n), f"after restart {n}")
 
 
+def test_files_of_another_mesh_or_vertical_grid_are_refused(mesh_2k, tmp_path):
+    """A restart / help_fields file whose `vi` or `zeta` dimension differs from the resident mesh / config (a file of the mesh before a mesh
+    update, another nZ) is refused with an error before anything is moved, as the reference stops in NetCDF on a shape mismatch -- the frame
+    buffers are sized from the file."""
+    from tests.conftest import get_mesh
+    from tests.test_gpu_parity import scenario
+    from ufemism_b200.capi import UfmError
+
+    other = get_mesh(3000)
+    g = make_gpu(mesh_2k, scenario(mesh_2k, "mismip"))
+    fn, hf = str(tmp_path / "restart_other.nc"), str(tmp_path / "help_other.nc")
+    R.create_restart(fn, other, ZETA, {"TriC": other.TriC})
+    R.create_help_fields(hf, other, ZETA, ["Hi", "lat"], {"TriC": other.TriC})
+    hi = g.download("Hi")
+    for call in (lambda: g.write_restart(fn, 1.0), lambda: g.load_restart(fn, 1.0), lambda: g.write_help_fields(hf, 1.0, ["Hi"])):
+        with pytest.raises(UfmError) as e:
+            call()
+        assert e.value.rc == -12 and "vertices" in str(e.value)
+    assert g.write_help_fields(hf, 1.0, ["lat"], host={"lat": np.zeros(other.nV)}) == 1     # host-only fields do not involve the resident mesh
+    fz = str(tmp_path / "restart_nz.nc")
+    R.create_restart(fz, mesh_2k, ZETA[:-1], {"TriC": mesh_2k.TriC})
+    with pytest.raises(UfmError) as e:
+        g.write_restart(fz, 1.0)
+    assert e.value.rc == -14
+    assert_bits_equal(g.download("Hi"), hi, "Hi untouched")
+
+
 # ---- drop-in loop: ufm_run_model_host moves the host's fields every step; copies overlap each other and the SSA solve ----
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("overlap", ["1", "0"])

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ufemism_b200", "libufemism_b200.so")
 # kernels whose instruction mix is listed (substring of the demangled name)
-SASS_OF = ["k_ssa_sor<true, true, false>", "k_ssa_sor_tma<true, true, false>", "k_ssa_viscosity<false, 4>", "k_geom_ac", "k_thk<1>", "k_sia_ac("]
+SASS_OF = ["k_ssa_sor<true, true, false>", "k_ssa_viscosity<false, 4>", "k_geom_ac", "k_thk<1>", "k_sia_ac("]
 MEM = re.compile(r"\b(LDG|STG|LDS|STS|LDL|STL|RED|ATOMG|ATOMS|UBLKCP|SYNCS|LDGSTS|SHFL|BAR|MEMBAR|CCTL|ERRBAR|LDGDEPBAR|DEPBAR|MUFU|DFMA|DADD|DMUL)(\.[A-Z0-9_.]+)?")
 
 

@@ -72,7 +72,6 @@ int ufm_create(int device, const ufm_params *params, ufm_handle **out)
   h->device = device;
   h->P = *params;
   h->num_sms = prop.multiProcessorCount;
-  { const char *e = getenv("UFM_SOR_TMA"); h->sor_tma = e ? atoi(e) : 0; }
   memset(&h->cnt, 0, sizeof(h->cnt));
   derive_params(h);
   UFM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -385,6 +384,14 @@ int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int ord
 }
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }
+int ufm_resident_dims(ufm_handle *h, int dims[5])
+{
+  if (!h || !dims) return ufm_set_error(-2, "NULL argument");
+  dims[0] = h->has_mesh ? 1 : 0;
+  dims[1] = h->has_mesh ? h->mesh.nV : 0; dims[2] = h->has_mesh ? h->mesh.nAc : 0; dims[3] = h->has_mesh ? h->mesh.M : 0;
+  dims[4] = h->P.nZ;
+  return 0;
+}
 int ufm_field_resident(ufm_handle *h, int field)
 {
   if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
@@ -559,6 +566,18 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     return ufm_set_error(-4, "ufm_run_model: without a benchmark experiment SMB and BMB come from the host's climate / SMB / BMB models each dt_SMB; use ufm_run_model_host or the step-wise entry points");
   long steps = 0;
   int rc;
+  // run_ELRA_model knows every benchmark experiment but this one (bedrock_ELRA_module.f90:35-52)
+  if (b == UFM_BM_MESH_GENERATION_TEST)
+    return ufm_set_error(-1, "benchmark experiment \"mesh_generation_test\" not implemented in run_ELRA_model!");
+  // drop-in mode moves the host's fields at the top of every step and the host's own components (ELRA bedrock update, climate / SMB /
+  // BMB on their timers) run between steps: one step per call
+  if (host && max_steps != 1) return ufm_set_error(-2, "ufm_run_model_host: max_steps must be 1 (the host's components run between the steps)");
+  // the thermodynamics timer runs on C%dt_thermo (UFEMISM_main_model.f90:369,797), the step the heat equation integrates over
+  if (h->P.dt_thermo > 0.0 && r->dtc[UFM_T_THERMO] != h->P.dt_thermo) {
+    if (r->n_steps != 0) return ufm_set_error(-2, "ufm_run_model: region timer dt_thermo = %g but the handle's parameters say %g", r->dtc[UFM_T_THERMO], h->P.dt_thermo);
+    r->dtc[UFM_T_THERMO] = h->P.dt_thermo;
+    r->t1[UFM_T_THERMO] = r->t0[UFM_T_THERMO] + h->P.dt_thermo;
+  }
   // drop-in mode: UFM_XFER_OVERLAP=0 falls back to one synchronous copy per field (A/B measurements)
   bool overlap = false;
   if (host) {
@@ -590,7 +609,9 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     return 0;
   };
   while (r->time < t_end && (max_steps <= 0 || steps < max_steps)) {
-    r->t0[UFM_T_ELRA] = r->time;  // run_ELRA_model, benchmark branch (bedrock_ELRA_module.f90:35-47)
+    // run_ELRA_model (bedrock_ELRA_module.f90:22-66): the benchmark branch only moves the timer on; a realistic run does so when the
+    // deformation rate is due (the host computes it and updates Hb between the steps, then uploads Hb / dHb_dt with the step's inputs)
+    if (b != UFM_BM_NONE || r->do_[UFM_T_ELRA]) r->t0[UFM_T_ELRA] = r->time;
     if (host) {
       const struct { int f; const void *p; } in[] = {{UFM_F_HI, host->Hi}, {UFM_F_HB, host->Hb}, {UFM_F_SL, host->SL}, {UFM_F_DHB_DT, host->dHb_dt},
                                                      {UFM_F_SMB_YEAR, host->SMB_year}, {UFM_F_BMB, host->BMB}, {UFM_F_MASK_NOICE, host->mask_noice}};

@@ -27,6 +27,10 @@
 #define MAIL_EPOCH 40       // own epoch counter
 #define MAIL_ABORT 41       // set when a peer wait timed out
 #define MAIL_WORDS 64
+// dataflow SOR sweep (k_ssa_sor_df): stage counters
+#define DF_NONE 0xFFFFu
+#define DF_CNT_STRIDE 8      // one 32 B sector per counter
+#define DF_MAX_STAGES 256
 
 // src/parameters_module.f90:9-21
 #define UFM_PI 3.141592653589793
@@ -124,6 +128,12 @@ struct DevMesh {
   int *corner_nbr = nullptr;   // [4*16] neighbour position
   int *corner_row = nullptr;   // [4*16] bc row of that neighbour, or -1 when it is not an edge vertex
   double sor_bytes = 0;        // sum_i (80 + 20 n_i) over swept vertices
+  // dataflow SOR sweep (k_ssa_sor_df, single GPU): x-band row order, no "adjacent colour-5 rows first" grouping
+  bool df_layout = false;
+  unsigned short *df_need = nullptr, *df_need_bc = nullptr;   // [n_slices], [n_bc + 4]
+  unsigned *df_stage_cnt = nullptr;                           // [DF_MAX_STAGES * DF_CNT_STRIDE]
+  int df_ready_for = 0;        // warps in the grid for which df_need was computed (0: not yet)
+  int df_n_stages = 0, df_base[5] = {}, df_K[5] = {}, df_act[5] = {};
   // ---- thermodynamics only (present when the mesh was uploaded with Tri) ----
   bool has_tri = false;
   int nTri = 0;
@@ -203,8 +213,10 @@ struct ufm_handle {
   int sor_grid = 0, sor_block = 1024;
   size_t sor_smem = 0;
   int sor_chunk = 0, sor_fuse_bc = 0, sor_bar = 0;  // SOR scheduling switches (env UFM_SOR_CHUNK / _FUSE_BC / _BAR)
+  int sor_df = 0;                // 1: dataflow sweep kernel (env UFM_SOR_DATAFLOW, needs the mesh's df_layout)
+  const void *carveout_done_for = nullptr;   // kernel variant whose L1 carve-out preference has been set on this handle's device
+  int visc_minb = -1;            // resident CTAs per SM of the viscosity kernel (env UFM_VISC_MINB)
   unsigned long long *sor_trace = nullptr;   // tuning aid, see SorArgs::trace
-  int sor_tma = 0;               // 1: TMA-staged SOR kernel (env UFM_SOR_TMA, default set in ufm_create)
   int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload
   bool comm_connected = false;
   CommDev comm;

@@ -601,6 +601,23 @@ int ufm_restart_append(const char *filename, double time, const ufm_restart_fram
   return (int)(rec + 1);
 }
 
+/* the file must describe the mesh and the vertical grid that are resident on the handle: the frame buffers below are sized from the
+ * file's dimensions while ufm_state_download / _upload move mesh.nV x P.nZ elements (a file of the previous mesh, after a mesh update,
+ * or with another nZ would otherwise overflow them; the reference stops in NetCDF on such a shape mismatch) */
+static int check_file_matches_handle(ufm_handle *h, const char *who, const char *filename, long long nV, long long nZ, long long nM = -1)
+{
+  int d[5];
+  int rc = ufm_resident_dims(h, d);
+  if (rc) return rc;
+  if (!d[0]) return ufm_set_error(-2, "%s: no mesh resident", who);
+  if (nV != d[1])
+    return ufm_set_error(-12, "%s: \"%s\" holds %lld vertices, the resident mesh %d (a file of another mesh?)", who, filename, nV, d[1]);
+  if (nM >= 0 && nM != d[3])
+    return ufm_set_error(-12, "%s: \"%s\" holds %lld combined-mesh vertices, the resident mesh %d", who, filename, nM, d[3]);
+  if (nZ != d[4]) return ufm_set_error(-14, "   ERROR: nZ in \"%s\" (%lld) doesnt match nZ in config (%d)!", filename, nZ, d[4]);
+  return 0;
+}
+
 /* the same with the fields the device owns (Hi, Hb, Hs, U_SIA, V_SIA, U_SSA, V_SSA, Ti) downloaded from the handle;
  * FirnDepth (nV,12) and MeltPreviousYear (nV) belong to the host's SMB model (NULL: fill value) */
 int ufm_restart_write(ufm_handle *h, const char *filename, double time, const double *FirnDepth, const double *MeltPreviousYear)
@@ -611,6 +628,7 @@ int ufm_restart_write(ufm_handle *h, const char *filename, double time, const do
   if (rc) return rc;
   long long nV = 0, nZ = 0;
   if ((rc = inquire_dim(f, "vi", &nV)) || (rc = inquire_dim(f, "zeta", &nZ))) return rc;
+  if ((rc = check_file_matches_handle(h, "ufm_restart_write", filename, nV, nZ))) return rc;
   const long long rec = f.numrecs;
   std::vector<double> buf((size_t)(nV * nZ));
   if ((rc = put_record(fd.fd, f, "time", rec, &time))) return rc;
@@ -745,6 +763,7 @@ int ufm_restart_load(ufm_handle *h, const char *filename, double time_to_restart
   if (rc) return rc;
   long long nV = 0, nZ = 0;
   if ((rc = inquire_dim(f, "vi", &nV)) || (rc = inquire_dim(f, "zeta", &nZ))) return rc;
+  if ((rc = check_file_matches_handle(h, "ufm_restart_load", filename, nV, nZ))) return rc;
   close(fd.fd); fd.fd = -1;
   std::vector<double> Hi((size_t)nV), Hb((size_t)nV), U((size_t)nV), V((size_t)nV), Ti((size_t)(nV * nZ));
   ufm_restart_frame_out o;
@@ -796,6 +815,11 @@ int ufm_help_fields_write(ufm_handle *h, const char *filename, double time, int 
   long long nV = 0, nZ = 0;
   if ((rc = inquire_dim(f, "vi", &nV)) || (rc = inquire_dim(f, "zeta", &nZ))) return rc;
   const long long rec = f.numrecs;
+  for (int k = 0; k < n_fields && h; k++) {   // any field that comes from the device: the file must describe the resident mesh (checked before the frame is started)
+    if (skipped_help_field(names[k]) || (host_data && host_data[k])) continue;
+    const HelpField *hf = find_help_field(names[k]);
+    if (hf && hf->src != SRC_HOST) { if ((rc = check_file_matches_handle(h, "ufm_help_fields_write", filename, nV, nZ))) return rc; break; }
+  }
   if ((rc = put_record(fd.fd, f, "time", rec, &time))) return rc;
   std::vector<double> buf, buf2;
   for (int k = 0; k < n_fields; k++) {
@@ -824,6 +848,7 @@ int ufm_help_fields_write(ufm_handle *h, const char *filename, double time, int 
       } else {                                        // phi_fric_AaAc(1:nV), tau_c_AaAc(1:nV), :470-473
         long long nM = 0;
         if ((rc = inquire_dim(f, "ai", &nM))) return rc;
+        if ((rc = check_file_matches_handle(h, "ufm_help_fields_write", filename, nV, nZ, nM))) return rc;
         buf2.resize((size_t)nM);
         if ((rc = ufm_state_download(h, hf->src == SRC_PHI_AA ? UFM_F_PHI_FRIC_AAAC : UFM_F_TAU_C_AAAC, buf2.data()))) return rc;
         memcpy(buf.data(), buf2.data(), (size_t)nV * 8);

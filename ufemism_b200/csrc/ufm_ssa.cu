@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 
@@ -472,7 +473,13 @@ struct SorArgs {
   double omega, tol;
   unsigned long long *ctrl;
   unsigned long long *sctl;   // device-side solve control, or NULL when driven call by call
+  // dataflow sweep (k_ssa_sor_df, single GPU): stage (c, k) = round k of colour c; st_K[c] rounds of st_act[c] slices each
+  unsigned *stage_cnt;            // [n_stages * DF_CNT_STRIDE] CTAs that have passed the stage, monotone over the iterations of a launch
+  const unsigned short *need;     // [n_slices] stage that must be complete before the slice gathers its neighbours (DF_NONE: none)
+  const unsigned short *need_bc;  // [n_bc + 4] the same for the Neumann rows
+  int n_stages, st_base[5], st_K[5], st_act[5];
 };
+#define DF_SPIN_LIMIT 4000000
 
 __device__ __forceinline__ double2 bc_mean(const SorArgs &a, int row)
 {
@@ -519,8 +526,8 @@ __device__ __forceinline__ void neumann_row(const SorArgs &a, const int r)
 // coefficient and neighbour load of the row is issued before the first use: ~4W independent loads in flight per
 // thread, which is what makes the sweep bandwidth- rather than latency-bound); n = row degree (<= W; the
 // padding entries of a mixed-degree slice point at the home row with zero coefficients and are not accumulated).
-template <int W, bool EXACT, bool MULTI>
-__device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, const int lane, const int p, const int n, double tmax)
+template <int W, bool EXACT>
+__device__ __forceinline__ double2 sor_row_value(const SorArgs &a, const long long o, const int lane, const int p, const int n, double &tmax)
 {
   int j[W];
   double cu[W], cv[W], nx[W];
@@ -552,7 +559,12 @@ __device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, c
   const double resV = (LHSy - r2.y) / e2.y;
   tmax = fmax(tmax, fabs(resU));
   tmax = fmax(tmax, fabs(resV));
-  store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
+  return make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
+}
+template <int W, bool EXACT, bool MULTI>
+__device__ __forceinline__ double sor_row(const SorArgs &a, const long long o, const int lane, const int p, const int n, double tmax)
+{
+  store_row<MULTI>(a, p, sor_row_value<W, EXACT>(a, o, lane, p, n, tmax));
   return tmax;
 }
 
@@ -765,265 +777,325 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
 }
 
 // =============================================================================================
-// TMA-staged variant of the SOR kernel.  Same arithmetic, same phases, same barriers; only the way the
-// read-only per-slice streams (neighbour indices, cU, cV, Nxy row, e, RHS, home Nxy, degrees) reach the SM differs:
-// lane 0 of every warp issues 1-D bulk async copies (cp.async.bulk, the TMA engine) of the NEXT slices of its warp into
-// a private ring of shared-memory stages and all lanes wait on the stage's mbarrier.  The copies are contiguous
-// because of the sliced-ELL layout (one slice = w*32 consecutive entries per array).  Bytes in flight no longer cost
-// registers, so the stream stays deep (TMA_STAGES x 8.4 KB per warp) while the SM computes the current slice.
-// (U,V) itself is NOT staged: it changes during the kernel and is gathered through the generic path as before.
+// Dataflow SOR sweep (single GPU): the same row updates in an order that respects every read-after-write dependency of the
+// colour-by-colour sweep, WITHOUT a grid barrier between the colours (one grid barrier per iteration remains: the stop test of
+// ice_dynamics_module.f90:676-689 needs the global max residual before the next iteration may touch U).
+//
+// The result of a sweep does not depend on the global phase order, only on every row seeing its lower-coloured neighbours already
+// updated and its higher-coloured ones not yet (tests/test_oracle.py::test_sor_sweep_is_a_dataflow_not_a_phase_order), so:
+//   * a colour block of n slices is swept in K = ceil(n / warps) rounds of act = ceil(n / K) slices; round k of colour c is
+//     "stage" st_base[c] + k.  Every warp walks through all stages in order (it has at most one slice per stage) and reports each
+//     stage it has passed; per stage one shared-memory counter per CTA, and the last warp of a CTA adds 1 to the stage's global
+//     counter with a gpu-scope release.  Stage g is complete when its counter has reached (iteration x CTAs); completeness is
+//     monotone in g because every warp passes the stages in order.
+//   * need[s] (k_sor_need, once per mesh) is the highest stage holding a lower-coloured neighbour of a row of slice s.  A warp issues
+//     the read-only streams of its slice, then (only if that stage is not yet known to be complete) polls the counter, then gathers.
+//     With the x-band row order (ufm_row_order_impl) need[s] lies about one round ahead of the slice's own position in the previous
+//     colour, i.e. almost a whole colour phase in the past: nobody waits, and a warp that is done with colour c early simply goes on
+//     with colour c+1, so the ramp-down of one colour overlaps the ramp-up of the next.
+//   * the Neumann rows (apply_Neumann_boundary_AaAc) are "stage-less" readers with their own need_bc[r]; they are taken by the warps
+//     that have no slice in the fifth colour (or by everybody when there are none), their index lists fetched before the wait.
+// Deadlock-free: waits only ever target lower stages, all CTAs are co-resident (cooperative launch), and every poll loop gives up
+// after DF_SPIN_LIMIT polls (flag bit 3 -> rc -9) instead of hanging the GPU.
 // =============================================================================================
-#define TMA_WARPS 12
-#define TMA_STAGES 2
-#define TMA_WMAX 8
-#define ST_IDX 0
-#define ST_CU 1024
-#define ST_CV 3072
-#define ST_NXY 5120
-#define ST_E 7168
-#define ST_RHS 7680
-#define ST_H0 8192
-#define ST_DEG 8448
-#define TMA_STAGE_BYTES 8576
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+#ifdef DF_EXP_NO_ACQUIRE   // timing experiment only (NOT correct): no L1 invalidation
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { return ld_relaxed_u32(p); }
+#else
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+#endif
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+struct DfState {
+  int it;                // SOR iteration of this launch, 1-based: a stage is complete when its counter has reached it x CTAs
+  int known;             // highest stage this warp knows to be complete in this iteration (-1: none)
+};
+// make sure stage `nd` is complete (nd < 0: nothing to wait for).  Must be called by all 32 lanes with the same nd.
+// Three levels: the warp's own `known`; the CTA's (*s_known = it << 16 | known + 1, so that it never needs a reset: a value from
+// another iteration reads as "nothing known"); and the slow path, a real call (kept out of line for the registers): poll, then one
+// acquire that also looks up to 32 stages ahead.  An acquire drops the SM's whole L1 (CCTL.IVALL) -- the reason for sharing what it
+// learnt with the other 31 warps of the CTA: any L1 line they fetch from then on is at least that fresh.
+__device__ __noinline__ int df_wait_slow(const unsigned *stage_cnt, unsigned long long *ctrl, const unsigned target, const int nd, const int n_stages)
 {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-               "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// issue the bulk copies of slice s into stage st (called by lane 0 only); slices wider than TMA_WMAX are not staged
-template <bool EXACT>
-__device__ __forceinline__ void tma_issue(const SorArgs &a, const int s, char *st, unsigned long long *bar)
-{
-  const long long o = a.off[s];
-  const int w = (int)((a.off[s + 1] - o) >> 5);
-  const int p = s * 32;
-  if (w > TMA_WMAX || w == 0) { mbar_expect_tx(bar, 32u); bulk_g2s(st + ST_DEG, a.deg + p, 32u, bar); return; }
-  const unsigned bi = (unsigned)w * 128u, bd = (unsigned)w * 256u;
-  mbar_expect_tx(bar, bi + 2u * bd + (EXACT ? bd : 0u) + 512u + 512u + 256u + 32u);
-  bulk_g2s(st + ST_IDX, a.idx + o, bi, bar);
-  bulk_g2s(st + ST_CU, a.cU + o, bd, bar);
-  bulk_g2s(st + ST_CV, a.cV + o, bd, bar);
-  if (EXACT) bulk_g2s(st + ST_NXY, a.nxy + o, bd, bar);
-  bulk_g2s(st + ST_E, a.E + p, 512u, bar);
-  bulk_g2s(st + ST_RHS, a.RHS + p, 512u, bar);
-  bulk_g2s(st + ST_H0, (EXACT ? a.nxy0 : a.nxysum) + p, 256u, bar);
-  bulk_g2s(st + ST_DEG, a.deg + p, 32u, bar);
-}
-
-template <int W, bool EXACT, bool MULTI>
-__device__ __forceinline__ double sor_row_st(const SorArgs &a, const char *st, const int lane, const int p, const int n, double tmax)
-{
-  const int *sidx = (const int *)(st + ST_IDX);
-  const double *scu = (const double *)(st + ST_CU), *scv = (const double *)(st + ST_CV), *snx = (const double *)(st + ST_NXY);
-  int j[W];
-#pragma unroll
-  for (int c = 0; c < W; c++) j[c] = sidx[c * 32 + lane];
-  const double2 u = a.UV[p];
-  double2 nb[W];
-#pragma unroll
-  for (int c = 0; c < W; c++) nb[c] = a.UV[j[c]];
-  const double2 e2 = ((const double2 *)(st + ST_E))[lane], r2 = ((const double2 *)(st + ST_RHS))[lane];
-  const double h = ((const double *)(st + ST_H0))[lane];
-  double Uxy = u.x * h, Vxy = u.y * h;
-  if (EXACT) {
-#pragma unroll
-    for (int c = 0; c < W; c++) if (c < n) { const double t = snx[c * 32 + lane]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    int spins = 0;
+    while (ld_relaxed_u32(stage_cnt + nd * DF_CNT_STRIDE) < target) {
+      ++spins;
+      if ((spins & 1023) == 0 && *((volatile unsigned long long *)(ctrl + 13))) break;   // somebody else has given up: so do we
+      if (spins > DF_SPIN_LIMIT) { *((volatile unsigned long long *)(ctrl + 13)) = 1ull; break; }
+    }
   }
-  double sumU = 0.0, sumV = 0.0;
+  __syncwarp();
+  const int gi = min(nd + lane, n_stages - 1);
+  const unsigned ok = __ballot_sync(0xffffffffu, ld_acquire_u32(stage_cnt + gi * DF_CNT_STRIDE) >= target);
+  __syncwarp();
+  const int run = ok == 0xffffffffu ? 32 : __ffs((int)~ok) - 1;
+  return min(nd + max(run, 1) - 1, n_stages - 1);
+}
+__device__ __forceinline__ void df_signal(unsigned *sh_cnt, unsigned *cnt, const int g, const int lane, const unsigned n_warps);
+__device__ __forceinline__ void df_wait(const SorArgs &a, DfState &d, volatile unsigned *s_known, unsigned *sh_cnt, int &pend, const int nd)
+{
+  if (nd <= d.known) return;
+  const unsigned v = *s_known;
+  if ((int)(v >> 16) == d.it) d.known = max(d.known, (int)(v & 0xFFFFu) - 1);
+  if (nd <= d.known) return;
+  // about to poll, possibly to block: whoever waits for this warp's last stage must not be kept waiting (deadlock otherwise)
+  if (pend >= 0) { df_signal(sh_cnt, a.stage_cnt, pend, threadIdx.x & 31, blockDim.x >> 5); pend = -1; }
+  d.known = df_wait_slow(a.stage_cnt, a.ctrl, (unsigned)d.it * gridDim.x, nd, a.n_stages);
+  if ((threadIdx.x & 31) == 0) atomicMax((unsigned *)s_known, ((unsigned)d.it << 16) | (unsigned)(d.known + 1));
+}
+// the calling warp has passed stage g.  Its stores of that stage precede the call in program order; every warp makes its own stores
+// visible device-wide (release at gpu scope: a fence that finds nothing outstanding when the call is deferred, see k_ssa_sor_df) before
+// it counts itself in, and the last warp of the CTA publishes the stage.
+__device__ __forceinline__ void df_signal(unsigned *sh_cnt, unsigned *cnt, const int g, const int lane, const unsigned n_warps)
+{
+  __syncwarp();
+  if (lane == 0) {
+    unsigned old;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sh_cnt + g);
+#ifdef DF_EXP_NO_RELEASE   // timing experiment only (NOT correct): no fence before the count
+    asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(1u) : "memory");
+#else
+    asm volatile("atom.release.gpu.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sa), "r"(1u) : "memory");
+#endif
+    if (old == n_warps - 1u) {   // last warp of this CTA: the other 31 released their stores at gpu scope before they counted themselves in
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+      sh_cnt[g] = 0u;            // next use: next iteration, after the grid barrier
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt + g * DF_CNT_STRIDE), "r"(1u) : "memory");
+    }
+  }
+}
+
+// stage of the (swept) row at device position q, or -1 for rows outside the five colour blocks
+__device__ __forceinline__ int df_stage_of(const int *rng15, const int *st_base, const int *st_act, const int q)
+{
+  const int sq = q >> 5;
 #pragma unroll
-  for (int c = 0; c < W; c++) if (c < n) { sumU = sumU + nb[c].x * scu[c * 32 + lane]; sumV = sumV + nb[c].y * scv[c * 32 + lane]; }
+  for (int c = 0; c < 5; c++)
+    if (sq >= rng15[3 * c] && sq < rng15[3 * c + 2]) return st_base[c] + (sq - rng15[3 * c]) / st_act[c];
+  return -1;
+}
+struct NeedArgs {
+  int rng15[15], st_base[5], st_act[5];
+  int n_slices;
+  const long long *off; const unsigned char *deg; const int *idx;
+  int n_bc; const int *bc_ptr, *bc_nbr, *corner, *corner_nbr, *corner_row;
+  unsigned short *need, *need_bc;
+};
+// one warp per slice (colours 2..5), then one thread per Neumann row
+__global__ void k_sor_need(NeedArgs a)
+{
+  const int lane = threadIdx.x & 31;
+  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wg; s < a.n_slices; s += nw) {
+    int c = -1;
+    for (int k = 0; k < 5; k++) if (s >= a.rng15[3 * k] && s < a.rng15[3 * k + 2]) c = k;
+    int nd = -1;
+    if (c >= 1) {
+      const long long o = a.off[s];
+      const int p = s * 32 + lane, n = a.deg[p];
+      if (n != UFM_DEG_PAD)
+        for (int cc = 0; cc < n; cc++) {
+          const int q = a.idx[o + (long long)cc * 32 + lane];
+          const int g = df_stage_of(a.rng15, a.st_base, a.st_act, q);
+          if (g >= 0 && g < a.st_base[c]) nd = max(nd, g);   // lower colours only; same colour never adjacent
+        }
+      for (int o2 = 16; o2 > 0; o2 >>= 1) nd = max(nd, __shfl_xor_sync(0xffffffffu, nd, o2));
+    }
+    if (lane == 0) a.need[s] = nd < 0 ? (unsigned short)DF_NONE : (unsigned short)nd;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_bc + 4; r += gridDim.x * blockDim.x) {
+    int nd = -1;
+    if (r < a.n_bc) {
+      for (int k = a.bc_ptr[r]; k < a.bc_ptr[r + 1]; k++) nd = max(nd, df_stage_of(a.rng15, a.st_base, a.st_act, a.bc_nbr[k]));
+    } else {
+      const int kc = r - a.n_bc, n = a.corner[4 + kc];
+      for (int q = 0; q < n; q++) {
+        const int row = a.corner_row[kc * 16 + q];
+        if (row >= 0) { for (int k = a.bc_ptr[row]; k < a.bc_ptr[row + 1]; k++) nd = max(nd, df_stage_of(a.rng15, a.st_base, a.st_act, a.bc_nbr[k])); }
+        else nd = max(nd, df_stage_of(a.rng15, a.st_base, a.st_act, a.corner_nbr[kc * 16 + q]));
+      }
+    }
+    a.need_bc[r] = nd < 0 ? (unsigned short)DF_NONE : (unsigned short)nd;
+  }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ double2 sor_row_generic(const SorArgs &a, const long long o, const int w, const int lane, const int p, const int n, double &tmax)
+{
+  // rare high-degree rows (slice width > 8): same accumulation order, loads not batched
+  const double2 u = a.UV[p];
+  const double h = EXACT ? a.nxy0[p] : a.nxysum[p];
+  double sumU = 0.0, sumV = 0.0, Uxy = u.x * h, Vxy = u.y * h;
+  for (int cc = 0; cc < w; cc++) {
+    if (cc < n) {
+      const long long e = o + (long long)cc * 32 + lane;
+      const double2 nbv = a.UV[a.idx[e]];
+      sumU = sumU + nbv.x * a.cU[e];
+      sumV = sumV + nbv.y * a.cV[e];
+      if (EXACT) { const double t = a.nxy[e]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
+    }
+  }
+  const double2 e2 = a.E[p], r2 = a.RHS[p];
   const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
   const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
   const double resU = (LHSx - r2.x) / e2.x;
   const double resV = (LHSy - r2.y) / e2.y;
   tmax = fmax(tmax, fabs(resU));
   tmax = fmax(tmax, fabs(resV));
-  store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
-  return tmax;
+  return make_double2(u.x - a.omega * resU, u.y - a.omega * resV);
 }
 
-template <bool EXACT, bool GLFIX, bool MULTI>
-__global__ void __launch_bounds__(TMA_WARPS * 32, 1) k_ssa_sor_tma(SorArgs a)
+// 32 Neumann rows (one per lane), r0 = first row: index lists first, then the wait, then one round of gathers
+__device__ __forceinline__ void df_neumann_chunk(const SorArgs &a, DfState &d, volatile unsigned *s_known, unsigned *sh_cnt, const int r0)
 {
-  extern __shared__ __align__(128) char smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  const int nblocks = gridDim.x, P = MULTI ? a.cm.P : 1, rank = MULTI ? a.cm.rank : 0;
+  const int r = r0 + (int)(threadIdx.x & 31), r_end = a.bc_end + 4;
+  const bool mine = r < r_end, edge = r < a.bc_end;
+  int b = 0, e = 0, j[4] = {0, 0, 0, 0};
+  int nd = -1;
+  if (mine) { const unsigned v = a.need_bc[r]; nd = v == DF_NONE ? -1 : (int)v; }
+  if (mine && edge) {
+    b = a.bc_ptr[r]; e = a.bc_ptr[r + 1];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (b + k < e) j[k] = a.bc_nbr[b + k];
+  }
+  int ndw = nd;
+  for (int o2 = 16; o2 > 0; o2 >>= 1) ndw = max(ndw, __shfl_xor_sync(0xffffffffu, ndw, o2));
+  int none = -1;   // nothing pending here: the stage loop has flushed
+  df_wait(a, d, s_known, sh_cnt, none, ndw);
+  if (!mine) return;
+  if (edge) {
+    double su = 0.0, sv = 0.0;
+    double2 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (b + k < e) q[k] = __ldcg(a.UV + j[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (b + k < e) { su = su + q[k].x; sv = sv + q[k].y; }
+    for (int k = b + 4; k < e; k++) { const double2 t = __ldcg(a.UV + a.bc_nbr[k]); su = su + t.x; sv = sv + t.y; }
+    const double nv = (double)(e - b);
+    a.UV[a.bc_pos[r]] = make_double2(su / nv, sv / nv);
+  } else neumann_row<false>(a, r);
+}
+
+template <bool EXACT, bool GLFIX>
+__global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor_df(SorArgs a)
+{
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nblocks = gridDim.x;
+  const unsigned n_warps = blockDim.x >> 5;
   unsigned *bar = (unsigned *)(a.ctrl + 32);
-  volatile unsigned long long *mail = MULTI ? a.cm.mail[rank] : nullptr;
-  __shared__ double sh[TMA_WARPS];
-  __shared__ int s_rng[15];
-  __shared__ __align__(8) unsigned long long s_full[TMA_WARPS][TMA_STAGES];
-  char *my = smem + (size_t)warp * TMA_STAGES * TMA_STAGE_BYTES;
-  if (a.sctl && a.sctl[SCTL_STOP]) return;
-  if (threadIdx.x < 15) s_rng[threadIdx.x] = a.rng[((threadIdx.x / 3) * P + rank) * 3 + (threadIdx.x % 3)];
-  if (lane == 0) for (int q = 0; q < TMA_STAGES; q++) mbar_init(&s_full[warp][q], 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __shared__ double sh[SOR_BLOCK / 32];
+  // per stage: {first slice of this CTA, end of the colour block, warps of this CTA with a slice in the stage, -} -- a flat loop over
+  // the stages that looks its bounds up here keeps the registers for the loads in flight
+  extern __shared__ int4 s_stage[];
+  unsigned *sh_cnt = (unsigned *)(s_stage + a.n_stages);
+  __shared__ unsigned s_known;   // see df_wait
+  if (a.sctl && a.sctl[SCTL_STOP]) return;   // uniform over the grid: nobody enters a barrier
+  for (int g = threadIdx.x; g < a.n_stages; g += blockDim.x) {
+    int c = 0;
+    while (c < 4 && g >= a.st_base[c + 1]) c++;
+    const int k = g - a.st_base[c], act = a.st_act[c];
+    const int lo = (int)(((long long)act * blockIdx.x) / nblocks), hi = (int)(((long long)act * (blockIdx.x + 1)) / nblocks);
+    s_stage[g] = make_int4(a.rng[3 * c] + k * act + lo, a.rng[3 * c + 2], hi - lo, 0);
+    sh_cnt[g] = 0u;
+  }
+  if (threadIdx.x == 0) s_known = 0u;
+  unsigned phase = *((volatile unsigned *)bar) & 0x80000000u;
   __syncthreads();
-  unsigned phbits = 0u;   // bit q = parity the next wait on stage q expects
-  int it = 0;
   bool done = false;
   unsigned flags = 0;
-  double maxres = 0.0;
-  unsigned long long epoch = MULTI ? mail[MAIL_EPOCH] : 0ull;
-  while (!done && it < a.max_inner) {
-    it++;
-    if (tid == 0) a.ctrl[(it + 1) % 3] = 0ull;
-    double tmax = 0.0;
-    for (int c = 0; c < 5; c++) {
-      const int s_beg = s_rng[3 * c] + wg, s_bnd = s_rng[3 * c + 1], s_end = s_rng[3 * c + 2];
-      bool waited = !MULTI;
-      // prologue: fill the ring
-      if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < TMA_STAGES; q++) { const int sq = s_beg + q * nw; if (sq < s_end) tma_issue<EXACT>(a, sq, my + q * TMA_STAGE_BYTES, &s_full[warp][q]); }
-      }
-      int k = 0;
-      for (int s = s_beg; s < s_end; s += nw, k++) {
-        const int q = k % TMA_STAGES;
-        const char *st = my + q * TMA_STAGE_BYTES;
-        if (MULTI && !waited && s >= s_bnd) {
-          if (lane == 0) wait_peers(a.cm, epoch);
-          __syncwarp();
-          waited = true;
-        }
-        mbar_wait(&s_full[warp][q], (phbits >> q) & 1u);
-        phbits ^= 1u << q;
+  DfState d;
+  d.it = 0;
+  // Neumann work: chunks of 32 rows for the warps without a slice in the fifth colour, if there are enough of them
+  const int bc_chunks = (a.bc_end + 4 - a.bc_begin + 31) >> 5;
+  while (!done && d.it < a.max_inner) {
+    d.it++;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctrl[(d.it + 1) % 3] = 0ull;
+    if (lane == 0) sh[wib] = 0.0;   // this warp's max residual (kept here, not in a register, across the slices)
+    d.known = -1;
+    // Signals are deferred: the stage of the slice just stored is reported in the middle of the NEXT slice, after that slice's loads
+    // have been consumed and before its store -- the release fence then finds this warp's earlier stores long acknowledged and no load
+    // outstanding, i.e. costs nothing; reported right after the store it would stall the warp for an L2 round trip per slice.
+    int pend = -1;
+#pragma unroll 1
+    for (int g = 0; g < a.n_stages; g++) {
+      const volatile int *tg = (const volatile int *)(s_stage + g);   // volatile: looked up per stage, not kept in registers
+      const int s = tg[0] + wib;
+      if (wib < tg[2] && s < tg[1]) {
+        const long long o = a.off[s];
+        const int w = (int)((a.off[s + 1] - o) >> 5);
         const int p = s * 32 + lane;
-        const int n = ((const unsigned char *)(st + ST_DEG))[lane];
-        bool skip = (n == UFM_DEG_PAD);
-        if (GLFIX) { if (!skip && (a.mflag[p] & 2)) skip = true; }
-        if (!skip) {
-          const long long o = a.off[s];
-          const int w = (int)((a.off[s + 1] - o) >> 5);
-          switch (w) {  // warp-uniform
-            case 3: tmax = sor_row_st<3, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            case 4: tmax = sor_row_st<4, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            case 5: tmax = sor_row_st<5, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            case 6: tmax = sor_row_st<6, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            case 7: tmax = sor_row_st<7, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            case 8: tmax = sor_row_st<8, EXACT, MULTI>(a, st, lane, p, n, tmax); break;
-            default: {  // unstaged slice (w > TMA_WMAX or w < 3): generic path with the same accumulation order
-              const double2 u = a.UV[p];
-              const double h = EXACT ? a.nxy0[p] : a.nxysum[p];
-              double sumU = 0.0, sumV = 0.0, Uxy = u.x * h, Vxy = u.y * h;
-              for (int cc = 0; cc < w; cc++) {
-                if (cc < n) {
-                  const long long e = o + (long long)cc * 32 + lane;
-                  const double2 nbv = a.UV[a.idx[e]];
-                  sumU = sumU + nbv.x * a.cU[e];
-                  sumV = sumV + nbv.y * a.cV[e];
-                  if (EXACT) { const double t = a.nxy[e]; Uxy = Uxy + u.x * t; Vxy = Vxy + u.y * t; }
-                }
-              }
-              const double2 e2 = a.E[p], r2 = a.RHS[p];
-              const double LHSx = sumU + (3.0 * Vxy) + (e2.x * u.x);
-              const double LHSy = sumV + (3.0 * Uxy) + (e2.y * u.y);
-              const double resU = (LHSx - r2.x) / e2.x;
-              const double resV = (LHSy - r2.y) / e2.y;
-              tmax = fmax(tmax, fabs(resU));
-              tmax = fmax(tmax, fabs(resV));
-              store_row<MULTI>(a, p, make_double2(u.x - a.omega * resU, u.y - a.omega * resV));
-            }
-          }
+        const int n = a.deg[p];
+        const unsigned ndu = a.need[s];   // fetched together with the slice header: no extra latency
+        bool on = n != UFM_DEG_PAD;
+        if (GLFIX) { if (a.mflag[p] & 2) on = false; }
+        // the rows this slice reads must have been updated (warp-wide; almost always known already, see df_wait)
+        df_wait(a, d, &s_known, sh_cnt, pend, ndu == DF_NONE ? -1 : (int)ndu);
+        double tmax = 0.0;
+        double2 nv = make_double2(0.0, 0.0);
+        if (on) switch (w) {   // w is warp-uniform
+          case 3: nv = sor_row_value<3, EXACT>(a, o, lane, p, n, tmax); break;
+          case 4: nv = sor_row_value<4, EXACT>(a, o, lane, p, n, tmax); break;
+          case 5: nv = sor_row_value<5, EXACT>(a, o, lane, p, n, tmax); break;
+          case 6: nv = sor_row_value<6, EXACT>(a, o, lane, p, n, tmax); break;
+          case 7: nv = sor_row_value<7, EXACT>(a, o, lane, p, n, tmax); break;
+          case 8: nv = sor_row_value<8, EXACT>(a, o, lane, p, n, tmax); break;
+          default: nv = sor_row_generic<EXACT>(a, o, w, lane, p, n, tmax);
         }
-        __syncwarp();   // every lane is done reading this stage: refill it with the slice TMA_STAGES ahead
-        if (lane == 0) { const int sn = s + TMA_STAGES * nw; if (sn < s_end) tma_issue<EXACT>(a, sn, my + q * TMA_STAGE_BYTES, &s_full[warp][q]); }
-      }
-      if (c == 4) {
-        for (int o = 16; o > 0; o >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-        if (lane == 0) sh[warp] = tmax;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double m = 0.0;
-          for (int q = 0; q < TMA_WARPS; q++) m = fmax(m, sh[q]);
-          atomicMax(a.ctrl + (it % 3), (unsigned long long)__double_as_longlong(m));
-        }
-      }
-      ++epoch;
-      grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
-        if (MULTI && c == 4) {
-          const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
-          for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
-        }
-      });
-    }
-    if (MULTI) {
-      if (threadIdx.x == 0) wait_peers(a.cm, epoch);
-      __syncthreads();
-    }
-    for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
-      if (r < a.bc_end) store_row<MULTI>(a, a.bc_pos[r], bc_mean(a, r));
-      else {
-        const int k = r - a.bc_end;
-        if (!((a.corner_mask >> k) & 1)) continue;
-        const int n = a.corner[4 + k];
-        double su = 0.0, sv = 0.0;
-        for (int q = 0; q < n; q++) {
-          const int row = a.corner_row[k * 16 + q];
-          const double2 v = row >= 0 ? bc_mean(a, row) : a.UV[a.corner_nbr[k * 16 + q]];
-          su = su + v.x; sv = sv + v.y;
-        }
-        store_row<MULTI>(a, a.corner[k], make_double2(su / (double)n, sv / (double)n));
+#ifndef DF_EXP_NO_REDUCE
+        for (int o2 = 16; o2 > 0; o2 >>= 1) tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));   // (needs every load of the slice)
+        if (lane == 0) { volatile double *q = sh + wib; if (tmax > *q) *q = tmax; }
+#endif
+        if (pend >= 0) df_signal(sh_cnt, a.stage_cnt, pend, lane, n_warps);
+        if (on) a.UV[p] = nv;
+        pend = g;
+      } else {
+        if (pend >= 0) df_signal(sh_cnt, a.stage_cnt, pend, lane, n_warps);
+        df_signal(sh_cnt, a.stage_cnt, g, lane, n_warps);
+        pend = -1;
       }
     }
-    ++epoch;
-    grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
-    if (MULTI) {
-      unsigned long long r = 0ull;
-      for (int q = 0; q < P; q++) { const unsigned long long v = mail[MAIL_RESID + (it % 3) * UFM_MAX_RANKS + q]; r = v > r ? v : r; }
-      maxres = __longlong_as_double((long long)r);
-      if (mail[MAIL_ABORT]) { flags |= 4; done = true; }
-    } else {
-      maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (it % 3))));
+    if (pend >= 0) df_signal(sh_cnt, a.stage_cnt, pend, lane, n_warps);
+    // apply_Neumann_boundary_AaAc (mesh_ArakawaC_module.f90:660-724)
+    {
+      const int nw = nblocks * (int)n_warps;
+      const int act5 = a.st_act[4];
+      if (nw - act5 >= bc_chunks) {
+        const int lo5 = (int)(((long long)act5 * blockIdx.x) / nblocks), hi5 = (int)(((long long)act5 * (blockIdx.x + 1)) / nblocks);
+        if (wib >= hi5 - lo5) {
+          const int i = (int)n_warps * (int)blockIdx.x - lo5 + (wib - (hi5 - lo5));   // index of this warp among the warps without colour-5 work
+          if (i < bc_chunks) df_neumann_chunk(a, d, &s_known, sh_cnt, a.bc_begin + 32 * i);
+        }
+      } else {
+        for (int i = blockIdx.x * (int)n_warps + wib; i < bc_chunks; i += nw) df_neumann_chunk(a, d, &s_known, sh_cnt, a.bc_begin + 32 * i);
+      }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int k = 0; k < (int)n_warps; k++) m = fmax(m, sh[k]);
+      atomicMax(a.ctrl + (d.it % 3), (unsigned long long)__double_as_longlong(m));
+    }
+    grid_barrier_rel(bar, nblocks, phase);
+    const double maxres = __longlong_as_double((long long)*((volatile unsigned long long *)(a.ctrl + (d.it % 3))));
+    if (*((volatile unsigned long long *)(a.ctrl + 13))) { flags |= 8; done = true; }
     if (!a.force_iters && !done) {
       if (maxres < a.tol) done = true;
       else if (maxres > 1E6) {
+        const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
         for (int p = tid; p < a.Mp; p += nt) a.UV[p] = make_double2(0.0, 0.0);
         flags |= 1; done = true;
-      } else if (it == a.max_inner) flags |= 2;
+      } else if (d.it == a.max_inner) flags |= 2;
     }
   }
-  if (MULTI) {
-    if (threadIdx.x == 0) wait_peers(a.cm, epoch);
-    __syncthreads();
-    if (tid == 0) mail[MAIL_EPOCH] = epoch;
-  }
-  if (tid == 0) {
-    a.ctrl[8] = (unsigned long long)it; a.ctrl[9] = flags; a.ctrl[10] = (unsigned long long)__double_as_longlong(maxres);
-    if (a.sctl) {   // bookkeeping of solve_SSA's outer loop (:530-540)
-      a.sctl[SCTL_NINNER] += (unsigned long long)it; a.sctl[SCTL_NLAST] = (unsigned long long)it;
-      a.sctl[SCTL_MAXRES] = (unsigned long long)__double_as_longlong(maxres);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long mr = d.it > 0 ? *((volatile unsigned long long *)(a.ctrl + (d.it % 3))) : 0ull;   // max residual of the last iteration
+    a.ctrl[8] = (unsigned long long)d.it; a.ctrl[9] = flags; a.ctrl[10] = mr;
+    if (a.sctl) {
+      a.sctl[SCTL_NINNER] += (unsigned long long)d.it; a.sctl[SCTL_NLAST] = (unsigned long long)d.it;
+      a.sctl[SCTL_MAXRES] = mr;
       if (flags & 2) a.sctl[SCTL_RC] |= 1ull;
-      if (flags & 4) { a.sctl[SCTL_RC] |= 4ull; a.sctl[SCTL_STOP] = 1ull; }
+      if (flags & 8) { a.sctl[SCTL_RC] |= 8ull; a.sctl[SCTL_STOP] = 1ull; }
       if (flags & 1) {
         if (a.sctl[SCTL_RESET]) { a.sctl[SCTL_RC] |= 2ull; a.sctl[SCTL_STOP] = 1ull; }
         else a.sctl[SCTL_RESET] = 1ull;
@@ -1152,8 +1224,8 @@ static int enqueue_viscosity(ufm_handle *h, bool fuse, bool device_ctl)
   fill_visc_args(h, a, fuse, device_ctl);
   {
     // resident CTAs per SM: 2 (about 120 registers, every load of a row in flight at once), 3 or 4 (64 registers, twice the warps)
-    static int minb = -1;
-    if (minb < 0) { const char *e = getenv("UFM_VISC_MINB"); minb = e ? atoi(e) : UFM_VISC_MINB_DEFAULT; }
+    if (h->visc_minb < 0) { const char *e = getenv("UFM_VISC_MINB"); h->visc_minb = e ? atoi(e) : UFM_VISC_MINB_DEFAULT; }
+    const int minb = h->visc_minb;
     if (minb == 6) k_ssa_viscosity<false, 6><<<h->num_sms * 6, 256, 0, h->stream>>>(a);
     else if (minb == 5) k_ssa_viscosity<false, 5><<<h->num_sms * 5, 256, 0, h->stream>>>(a);
     else if (minb == 4) k_ssa_viscosity<false, 4><<<h->num_sms * 4, 256, 0, h->stream>>>(a);
@@ -1210,13 +1282,9 @@ typedef void (*sor_kernel_t)(SorArgs);
 static sor_kernel_t pick_sor(const ufm_handle *h)
 {
   const bool ex = h->P.exact_xy != 0, gl = h->P.use_analytical_GL_flux != 0, mu = h->mesh.P > 1;
-  if (h->sor_tma) {
-    if (mu) {
-      if (ex) return gl ? k_ssa_sor_tma<true, true, true> : k_ssa_sor_tma<true, false, true>;
-      return gl ? k_ssa_sor_tma<false, true, true> : k_ssa_sor_tma<false, false, true>;
-    }
-    if (ex) return gl ? k_ssa_sor_tma<true, true, false> : k_ssa_sor_tma<true, false, false>;
-    return gl ? k_ssa_sor_tma<false, true, false> : k_ssa_sor_tma<false, false, false>;
+  if (h->sor_df && !mu) {
+    if (ex) return gl ? k_ssa_sor_df<true, true> : k_ssa_sor_df<true, false>;
+    return gl ? k_ssa_sor_df<false, true> : k_ssa_sor_df<false, false>;
   }
   if (mu) {
     if (ex) return gl ? k_ssa_sor<true, true, true> : k_ssa_sor<true, false, true>;
@@ -1234,28 +1302,66 @@ int ufm_sor_configure(ufm_handle *h)
   if (getenv("UFM_SOR_TRACE") && !h->sor_trace) { UFM_CUDA(cudaMalloc((void **)&h->sor_trace, 4096 * 24 * sizeof(unsigned long long))); UFM_CUDA(cudaMemset(h->sor_trace, 0, 4096 * 24 * sizeof(unsigned long long))); }
   { const char *e = getenv("UFM_SOR_BAR"); h->sor_bar = e ? atoi(e) : UFM_SOR_BAR_DEFAULT; }
   { const char *e = getenv("UFM_SOR_FUSE_BC"); h->sor_fuse_bc = e ? atoi(e) : UFM_SOR_FUSE_BC_DEFAULT; }
-  h->sor_block = h->sor_tma ? TMA_WARPS * 32 : SOR_BLOCK;
-  h->sor_smem = h->sor_tma ? (size_t)TMA_WARPS * TMA_STAGES * TMA_STAGE_BYTES : 0;
-  if (h->sor_smem) UFM_CUDA(cudaFuncSetAttribute((const void *)pick_sor(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sor_smem));
+  h->sor_block = SOR_BLOCK;
+  h->sor_smem = 0;
+  { const char *e = getenv("UFM_SOR_DATAFLOW"); h->sor_df = (h->mesh.df_layout && h->mesh.P == 1 && (!e || atoi(e) != 0)) ? 1 : 0; }
+  // one CTA of 1024 threads per SM; UFM_SOR_GRID (tests only) shrinks the grid so that small meshes are swept in several rounds per colour
+  int grid_target = h->num_sms;
+  { const char *e = getenv("UFM_SOR_GRID"); if (e && atoi(e) > 0 && atoi(e) < grid_target) grid_target = atoi(e); }
+  if (h->sor_df) {
+    // the stage table depends only on the mesh and the grid (the occupancy query below confirms that the grid is resident)
+    DevMesh &m = h->mesh;
+    const int nw = grid_target * (h->sor_block / 32);
+    int base = 0;
+    for (int c = 0; c < 5; c++) {
+      const int n = m.rng[c][0][2] - m.rng[c][0][0];
+      const int K = n > 0 ? (n + nw - 1) / nw : 1;
+      m.df_K[c] = K; m.df_act[c] = n > 0 ? (n + K - 1) / K : 1; m.df_base[c] = base;
+      base += K;
+    }
+    m.df_n_stages = base;
+    if (base > DF_MAX_STAGES) h->sor_df = 0;   // meshes far beyond one GPU's memory: barrier kernel
+    else h->sor_smem = (size_t)base * (sizeof(int4) + sizeof(unsigned));
+  }
   // The streaming kernels keep ~230 B of loads per thread in flight and reuse gathered (U,V) lines: they want the unified
   // L1 / shared-memory array as L1 (a 120 KB shared-memory carve-out costs the sweep 30 %).  UFM_L1_CARVEOUT
   // (percent of shared memory, -1 = leave the driver's default) exists for A/B measurements.
   {
-    static const void *done_for = nullptr;   // once per kernel variant: ufm_sor_configure runs before every piecewise SOR call
+    // once per kernel variant and handle (the attribute is per device): ufm_sor_configure runs before every piecewise SOR call
     const void *fn = (const void *)pick_sor(h);
-    if (done_for != fn && !h->sor_tma) {
+    if (h->carveout_done_for != fn) {
       const char *e = getenv("UFM_L1_CARVEOUT");
       const int pct = e ? atoi(e) : 0;
       if (pct >= 0) {
         UFM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         UFM_CUDA(cudaFuncSetAttribute((const void *)k_ssa_viscosity<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
       }
-      done_for = fn;
+      h->carveout_done_for = fn;
     }
   }
   UFM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_sor(h), h->sor_block, h->sor_smem));
   if (per_sm < 1) return ufm_set_error(-3, "SOR kernel cannot be made resident");
-  h->sor_grid = per_sm * h->num_sms;
+  h->sor_grid = getenv("UFM_SOR_GRID") ? std::min(per_sm * h->num_sms, grid_target) : per_sm * h->num_sms;
+  if (h->sor_df) {
+    // need[] of the dataflow sweep for this grid (once per mesh and grid)
+    DevMesh &m = h->mesh;
+    const int nw = h->sor_grid * (h->sor_block / 32);
+    if (h->sor_grid != grid_target) return ufm_set_error(-3, "dataflow SOR sweep: %d CTAs resident, expected %d", h->sor_grid, grid_target);
+    if (m.df_ready_for != nw) {
+      NeedArgs na;
+      for (int c = 0; c < 5; c++) {
+        for (int q = 0; q < 3; q++) na.rng15[3 * c + q] = m.rng[c][0][q];
+        na.st_base[c] = m.df_base[c]; na.st_act[c] = m.df_act[c];
+      }
+      na.n_slices = m.m.n_slices; na.off = m.m.off; na.deg = m.m.deg; na.idx = m.m_idx;
+      na.n_bc = m.n_bc; na.bc_ptr = m.bc_ptr; na.bc_nbr = m.bc_nbr; na.corner = m.corner_dev; na.corner_nbr = m.corner_nbr; na.corner_row = m.corner_row;
+      na.need = m.df_need; na.need_bc = m.df_need_bc;
+      k_sor_need<<<h->num_sms * 8, 256, 0, h->stream>>>(na);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      m.df_ready_for = nw;
+    }
+  }
   return 0;
 }
 
@@ -1274,7 +1380,10 @@ static int enqueue_sor(ufm_handle *h, int max_inner, int force_iters, bool devic
   a.bc_pos = m.bc_pos; a.bc_ptr = m.bc_ptr; a.bc_nbr = m.bc_nbr;
   a.corner_nbr = m.corner_nbr; a.corner_row = m.corner_row;
   a.chunk = h->sor_chunk; a.trace = h->sor_trace; a.bar_rel = h->sor_bar;
-  a.fuse_bc = (h->sor_fuse_bc && m.P == 1 && !h->sor_tma) ? 1 : 0; a.adj_end = m.adj5_end;
+  a.fuse_bc = (h->sor_fuse_bc && m.P == 1 && !m.df_layout) ? 1 : 0; a.adj_end = m.adj5_end;
+  a.stage_cnt = m.df_stage_cnt; a.need = m.df_need; a.need_bc = m.df_need_bc; a.n_stages = m.df_n_stages;
+  for (int c = 0; c < 5; c++) { a.st_base[c] = m.df_base[c]; a.st_K[c] = m.df_K[c]; a.st_act[c] = m.df_act[c]; }
+  if (h->sor_df) UFM_CUDA(cudaMemsetAsync(m.df_stage_cnt, 0, sizeof(unsigned) * DF_CNT_STRIDE * (size_t)std::max(1, m.df_n_stages), h->stream));
   a.Mp = m.Mp; a.max_inner = max_inner; a.force_iters = force_iters; a.omega = h->P.SSA_SOR_omega; a.tol = h->P.SSA_max_residual_UV;
   a.ctrl = s.ctrl; a.sctl = device_ctl ? s.ctrl + SCTL_BASE : nullptr;
   UFM_CUDA(cudaMemsetAsync(s.ctrl, 0, 16 * sizeof(unsigned long long), h->stream));
@@ -1303,6 +1412,7 @@ int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *
     st->did_reset = (int)(res[1] & 1);
     st->rc = (res[1] & 2) ? 1 : 0;
     if (res[1] & 4) return ufm_set_error(-7, "SOR: wait for a peer GPU timed out (partitioned run)");
+    if (res[1] & 8) return ufm_set_error(-9, "SOR: a dependency wait of the dataflow sweep timed out");
     double r;
     memcpy(&r, &res[2], sizeof(r));
     st->last_max_residual = r;
@@ -1347,6 +1457,7 @@ int ufm_k_ssa_outer_loop(ufm_handle *h, ufm_ssa_stats *st)
   memcpy(&d, &c[SCTL_MAXRES], sizeof(d)); st->last_max_residual = d;
   st->rc = (c[SCTL_RC] & 2) ? -1 : ((c[SCTL_RC] & 1) ? 1 : 0);
   if (c[SCTL_RC] & 4) return ufm_set_error(-7, "SOR: wait for a peer GPU timed out (partitioned run)");
+  if (c[SCTL_RC] & 8) return ufm_set_error(-9, "SOR: a dependency wait of the dataflow sweep timed out");
   return 0;
 }
 

@@ -564,18 +564,25 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
   // single-GPU layout: the colour-5 rows that the Neumann pass reads (non-edge rows adjacent to a domain-edge row) lead
   // their colour block, so that the pass can run inside the fifth colour phase as soon as those few slices are done
+  // ... unless the dataflow sweep (k_ssa_sor_df, the single-GPU default) will run: it orders the rows of every colour block
+  // by x-band / Morton alone, so that a row's lower-coloured neighbours sit at about the same relative position of their blocks
   std::vector<unsigned char> late(M, 1);
   int n_adj5 = 0;
-  if (P == 1)
+  const char *env_order = getenv("UFM_ROW_ORDER");
+  {
+    const char *e = getenv("UFM_SOR_DATAFLOW");
+    m.df_layout = P == 1 && (!e || atoi(e) != 0) && !(env_order && !strncmp(env_order, "default", 7));
+  }
+  if (P == 1 && !m.df_layout)
     for (int ai = 0; ai < M; ai++) {
       if (colour[ai] != 5 || is_edge[ai]) continue;
       for (int c = 1; c <= degv[ai]; c++)
         if (is_edge[F2(d->CAaAc, ai + 1, c, ldM) - 1]) { late[ai] = 0; n_adj5++; break; }
     }
   // row order inside the colour blocks: (degree, Morton), or the experimental x-band order (UFM_ROW_ORDER=bands:<n>[:<window>])
-  int n_bands = 0, deg_window = 4096;
-  if (const char *e = getenv("UFM_ROW_ORDER")) {
-    if (sscanf(e, "bands:%d:%d", &n_bands, &deg_window) < 1) n_bands = 0;
+  int n_bands = m.df_layout ? 64 : 0, deg_window = 4096;
+  if (env_order) {
+    if (sscanf(env_order, "bands:%d:%d", &n_bands, &deg_window) < 1) n_bands = m.df_layout ? 64 : 0;
   }
   {
     std::vector<unsigned char> blkv(M);
@@ -752,6 +759,12 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     std::vector<int> rnga(18);
     for (int b = 0; b < 6; b++) { rnga[3 * b] = m.rng[b][0][0]; rnga[3 * b + 1] = rnga[3 * b + 2] = (b < 5 ? m.rng[b + 1][0][0] : m.Mp / UFM_SLICE); }
     UP(rngv, m.rng_dev); UP(rnga, m.rng_all_dev); UP(cornv, m.corner_dev);
+    if (m.df_layout) {
+      int rc_;
+      if ((rc_ = ufm_arena_alloc(h, sizeof(unsigned short) * (size_t)m.m.n_slices, (void **)&m.df_need))) return rc_;
+      if ((rc_ = ufm_arena_alloc(h, sizeof(unsigned short) * ((size_t)m.n_bc + 4), (void **)&m.df_need_bc))) return rc_;
+      if ((rc_ = ufm_arena_alloc(h, sizeof(unsigned) * DF_CNT_STRIDE * DF_MAX_STAGES, (void **)&m.df_stage_cnt))) return rc_;
+    }
     UP(bc_pos, m.bc_pos); UP(bc_ptr, m.bc_ptr); UP(bc_nbr, m.bc_nbr); UP(cn, m.corner_nbr); UP(cr, m.corner_row);
   }
 

@@ -207,6 +207,15 @@ def make_points(xmin, xmax, ymin, ymax, h, seed=20211103, jitter=0.18, order="ra
     rest = np.concatenate([border, pts])
     if order == "random":
         rest = rest[rng.permutation(len(rest))]
+    elif order == "morton":   # locality-preserving numbering: Z-curve of the vertex coordinates (the CPU arm's best case)
+        def spread(v):
+            v = v.astype(np.uint64) & np.uint64(0xFFFF)
+            for sh, msk in ((8, 0x00FF00FF), (4, 0x0F0F0F0F), (2, 0x33333333), (1, 0x55555555)):
+                v = (v | (v << np.uint64(sh))) & np.uint64(msk)
+            return v
+        fx = np.clip((rest[:, 0] - xmin) / Lx * 65535.0, 0, 65535)
+        fy = np.clip((rest[:, 1] - ymin) / Ly * 65535.0, 0, 65535)
+        rest = rest[np.argsort(spread(fx) | (spread(fy) << np.uint64(1)), kind="stable")]
     elif order != "lattice":
         raise ValueError(order)
     return np.concatenate([corners, rest])
