@@ -225,6 +225,14 @@ int ufm_field_resident(ufm_handle *h, int field);
 /* sizes of what is resident: dims[0] = 1 when a mesh is resident (else 0 and the rest 0), dims[1] = nV, dims[2] = nAc,
  * dims[3] = nVAaAc = nV + nAc (mesh%nV, mesh%nAc, mesh%nVAaAc: src/data_types_module.f90:216-345), dims[4] = C%nZ */
 int ufm_resident_dims(ufm_handle *h, int dims[5]);
+/* bit 0 (1): the device evaluates x**y with the bits of this host's libm pow; bit 1 (2): likewise tan on 0.07 <= |x| <= 0.78 (the friction
+ * angles of the yield stress).  In detail -- 1: the device evaluates x**y with the bits of this host's libm pow (glibc's algorithm re-stated on the device with the tables of the
+ * running libm, validated at ufm_create), so that viscosity, sliding law, SIA diffusivity and grounding-line flux are bit-identical with a
+ * CPU run on the same machine; 0: CUDA's pow (within 2 ulp) because the tables were not found / did not validate / UFM_POW_EXACT=0 */
+int ufm_pow_mode(ufm_handle *h);
+/* host: the same evaluation (libm's pow off its main path); for tests */
+double ufm_pow_host(double x, double y);
+double ufm_tan_host(double x);
 
 /* Page-lock a host array (e.g. one of the Fortran host's MPI shared-memory windows, src/parallel_module.f90:144-160) so that
  * ufm_state_upload / ufm_state_download DMA it directly instead of bouncing through a staging buffer.  Optional. */

@@ -160,7 +160,7 @@ def test_sor_bit_exact_at_prescribed_iterations(mesh_10k, k, nthreads):
 ], ids=["plain", "equal_share", "fused_neumann", "release_barrier", "barrier_default", "dataflow", "dataflow_2_ctas", "dataflow_1_cta", "dataflow_7_ctas_5_bands"])
 def test_sor_schedule_variants_bit_exact(mesh_10k, monkeypatch, variant):
     """The SOR kernels only reorder work: the barrier kernel's scheduling switches (equal slice shares per warp, Neumann pass inside the
-    fifth colour phase, release/acquire grid barrier) inside a colour phase, the dataflow kernel (the single-GPU default; no grid barrier
+    fifth colour phase, release/acquire grid barrier) inside a colour phase, the dataflow kernel (opt-in; no grid barrier
     between the colours, every slice waits for the stage holding its lower-coloured neighbours) across the colours of one iteration.
     UFM_SOR_GRID shrinks the grid so that this small mesh is swept in several rounds per colour (at 2 CTAs: 4-5 rounds).  Every variant
     must give the oracle's bits."""
@@ -202,15 +202,20 @@ def test_experimental_band_row_order_bit_exact(mesh_10k, monkeypatch, order):
     assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10 and rel_l2(g.download("V_SSA"), o["V_SSA"]) <= 1e-10
 
 
-def test_dataflow_sor_at_250k_vertices_bit_exact():
-    """The dataflow sweep at a size where the full grid (148 x 32 warps) sweeps every colour in two rounds: forced iterations and the
-    whole solve_SSA against the oracle -- bit-exact sweep, identical iteration counts."""
+@pytest.mark.parametrize("dataflow", ["0", "1"])
+def test_dataflow_sor_at_250k_vertices_bit_exact(monkeypatch, dataflow):
+    """Both SOR kernels at a size where the full grid (148 x 32 warps) sweeps every colour in two rounds: forced iterations and the
+    whole solve_SSA (with the analytical grounding-line flux) against the oracle -- bit-exact sweep, identical iteration counts."""
+    monkeypatch.setenv("UFM_SOR_DATAFLOW", dataflow)
     m = get_mesh(250000, half_width=S.CONFIG3["half_width"])
     st = S.state_ssa_icestream(m, scale=1.0, Hb=S.CONFIG3["Hb"], H_shelf=S.CONFIG3["H_shelf"])   # the bench workload at a quarter of its size
     o, g = make_oracle(m, st, nthreads=16, use_analytical_GL_flux=1), make_gpu(m, st, use_analytical_GL_flux=1)
     o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
     o.basal_yield_stress(); o.calculate_GL_flux(); o.SSA_gather_AaAc(); o.SSA_effective_viscosity(); o.SSA_sliding_term()
-    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"]); g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
+    g.ssa_prepare(); g.upload("tau_c_AaAc", o["tau_c_AaAc"])
+    # the grounding-line rows are held at the analytical flux velocity, which sits behind a pow() and a tan(): start both sides from the oracle's bits
+    g.upload("U_SSA_AaAc", o["U_SSA_AaAc"]); g.upload("V_SSA_AaAc", o["V_SSA_AaAc"])
+    g.ssa_viscosity(); g.upload("eta_AaAc", o["eta_AaAc"]); g.ssa_sliding_and_setup()
     n, res, _, _ = o.solve_SSA_linearised(max_inner=12, force_iters=True)
     for f in ("RHSx_AaAc", "RHSy_AaAc", "eu_i_AaAc", "ev_i_AaAc"):
         g.upload(f, o[f])
@@ -223,6 +228,47 @@ def test_dataflow_sor_at_250k_vertices_bit_exact():
     so, sg = o.solve_SSA(), g.solve_SSA()
     assert (sg.n_outer, sg.n_inner_total) == (so.n_outer, so.n_inner_total)
     assert rel_l2(g.download("U_SSA"), o["U_SSA"]) <= 1e-10 and rel_l2(g.download("V_SSA"), o["V_SSA"]) <= 1e-10
+
+
+def test_device_pow_has_the_host_libms_bits(mesh_10k):
+    """ufm_pow.cuh: with the host libm's tables found and validated (pow_mode 1) everything behind a pow() -- SIA diffusivity and velocities,
+    effective viscosity, sliding term -- is bit-identical with the oracle, not merely within an ulp or two."""
+    st = scenario(mesh_10k, "icestream")
+    o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
+    if not g.pow_mode() & 1:
+        pytest.skip("pow tables of this host's libm not usable: CUDA pow, tolerance-level parity only")
+    o.update_general_ice_model_data(0.0); g.update_general_ice_model_data(0.0)
+    o.solve_SIA(); g.solve_SIA()
+    for f in ("D_SIA_Ac", "Ux_SIA_Ac", "Up_SIA_Ac", "U_SIA", "D_SIA"):
+        assert_bits_equal(g.download(f), o[f], f)
+    o.basal_yield_stress(); o.SSA_gather_AaAc(); g.ssa_prepare()
+    if g.pow_mode() & 2:          # tan of the friction angle too
+        assert_bits_equal(g.download("tau_c_AaAc"), o["tau_c_AaAc"], "tau_c_AaAc")
+    x, y = mesh_10k.VAaAc[:, 0], mesh_10k.VAaAc[:, 1]
+    U = 100.0 * np.sin(x / 2e5) * np.cos(y / 3e5); V = -80.0 * np.cos(x / 2.5e5) * np.sin(y / 2e5)
+    o["U_SSA_AaAc"][:] = U; o["V_SSA_AaAc"][:] = V
+    g.upload("U_SSA_AaAc", U); g.upload("V_SSA_AaAc", V); g.upload("tau_c_AaAc", o["tau_c_AaAc"])
+    o.SSA_effective_viscosity(); o.SSA_sliding_term(); g.ssa_viscosity()
+    for f in ("eta_AaAc", "N_AaAc", "S_AaAc"):
+        assert_bits_equal(g.download(f), o[f], f)
+
+
+def test_whole_trajectory_bit_identical_with_exact_pow_and_tan(mesh_10k):
+    """With pow and tan evaluated as the host's libm does, a hybrid SIA / SSA run on the MISMIP bed with the analytical grounding-line flux
+    (pow and tan inside calculate_GL_flux, a spatially varying friction angle) is bit-identical with the oracle step after step: thickness,
+    velocities, masks, time steps, iteration counts."""
+    st = scenario(mesh_10k, "mismip")
+    o = make_oracle(mesh_10k, st, nthreads=8, use_analytical_GL_flux=1)
+    g = make_gpu(mesh_10k, st, use_analytical_GL_flux=1)
+    if g.pow_mode() != 3:
+        pytest.skip("pow / tan tables of this host's libm not usable")
+    ro, rg = o.region(0.0), g.region(0.0)
+    for step in range(12):
+        o.run_model(ro, 1e12, max_steps=1); g.run_model(rg, 1e12, max_steps=1)
+        assert (rg.time, rg.dt, rg.n_sor_total, rg.n_outer_total) == (ro.time, ro.dt, ro.n_sor_total, ro.n_outer_total), step
+        for f in ("Hi", "U_SSA", "V_SSA", "U_SIA", "Hs", "mask", "mask_gl_Ac", "Qabs_GL_Ac"):
+            assert_bits_equal(g.download(f), o[f], f"step {step} {f}")
+    assert ro.n_ssa >= 3 and np.abs(o["U_SSA"]).max() > 1.0
 
 
 def test_sor_presummed_xy_within_tolerance(mesh_10k):

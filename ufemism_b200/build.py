@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libufemism_b200.so")
 CU_SOURCES = ["ufm_api.cu", "ufm_upload.cu", "ufm_ssa.cu", "ufm_geom.cu", "ufm_thermo.cu"]
 # host-only sources of the same library (compiled by nvcc's host compiler): restart / help_fields files, secondary mesh data
-HOST_SOURCES = ["ufm_netcdf.cpp", "ufm_mesh_primary.cpp", "mesh_host.c"]
+HOST_SOURCES = ["ufm_netcdf.cpp", "ufm_mesh_primary.cpp", "ufm_pow_host.cpp", "mesh_host.c"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -30,7 +30,7 @@ def _stale(target, sources):
 
 def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES + HOST_SOURCES]
-    deps = srcs + [os.path.join(CSRC, "ufm_internal.cuh"), os.path.join(HERE, "..", "include", "ufemism_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "ufm_internal.cuh"), os.path.join(CSRC, "ufm_pow.cuh"), os.path.join(HERE, "..", "include", "ufemism_b200.h")]
     if force or _stale(LIB, deps):
         objs = []
         for s in srcs:

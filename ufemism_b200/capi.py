@@ -127,7 +127,7 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get",
-            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims",
+            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host",
             "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
             "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
             "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
@@ -184,6 +184,11 @@ def load_library():
         L.ufm_thermo_heat.argtypes = [p, p]
         L.ufm_field_resident.argtypes = [p, i]
         L.ufm_resident_dims.argtypes = [p, p]
+        L.ufm_pow_mode.argtypes = [p]
+        L.ufm_pow_host.argtypes = [d, d]
+        L.ufm_pow_host.restype = d
+        L.ufm_tan_host.argtypes = [d]
+        L.ufm_tan_host.restype = d
         s = ctypes.c_char_p
         L.ufm_restart_create.argtypes = [s, p, i, p]
         L.ufm_restart_append.argtypes = [s, d, p]
@@ -523,18 +528,23 @@ class IceModelGPU:
         self._ck(self.L.ufm_counters_get(self.h, ctypes.byref(c)))
         return c
 
-    def sor_trace(self):
-        """Phase timestamps of the SOR kernel's fourth iteration, shape (n_ctas, 6, 4) in ns (needs UFM_SOR_TRACE=1)."""
+    def sor_trace(self, raw=False):
+        """Phase timestamps of the SOR kernel's fourth iteration, shape (n_ctas, 6, 4) in ns (needs UFM_SOR_TRACE=1); raw: the whole
+        tuning buffer (tools/df_stats_probe.py)."""
         buf = np.zeros(4096 * 24, np.uint64)
         n = self.L.ufm_sor_trace_get(self.h, buf.ctypes.data_as(ctypes.c_void_p), buf.size)
         if n < 0:
             self._ck(n)
-        return buf[: n * 24].reshape(n, 6, 4)
+        return buf if raw else buf[: n * 24].reshape(n, 6, 4)
 
     def reset_counters(self):
         self._ck(self.L.ufm_counters_reset(self.h))
 
     # ---- restart / help_fields files (reference format; ufemism_b200/restart.py holds the host-only half) ----
+    def pow_mode(self) -> int:
+        """bit 0: device pow has the bits of the host's libm (ufm_pow.cuh), bit 1: so has tan on the yield-stress range; 0: CUDA's pow / tan."""
+        return int(self.L.ufm_pow_mode(self.h))
+
     def field_resident(self, name) -> bool:
         return self._ck(self.L.ufm_field_resident(self.h, _REF_NAMES[name.upper()][0]), allow_warning=True) == 1
 

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "ufm_internal.cuh"
+#include "ufm_pow.cuh"
 
 int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d);
 int ufm_mesh_free_impl(ufm_handle *h);
@@ -76,6 +77,18 @@ int ufm_create(int device, const ufm_params *params, ufm_handle **out)
   derive_params(h);
   UFM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
+  {
+    // x**y with the host libm's bits on the device (ufm_pow.cuh): tables found in this process's libm and validated once per process,
+    // then copied into every kernel translation unit on this handle's device
+    static UfmPowTab tab;
+    static int built = 0, reason = 0;
+    if (!built) { reason = ufm_powtab_build(&tab); built = 1; }
+    h->pow_reason = reason;
+    if (tab.enabled) {
+      if (ufm_ssa_powtab_init(&tab) || ufm_geom_powtab_init(&tab) || ufm_thermo_powtab_init(&tab)) { delete h; return ufm_set_error(-3, "ufm_create: could not upload the pow tables"); }
+      h->pow_exact = tab.tan_enabled ? 3 : 1;
+    }
+  }
   UFM_CUDA(cudaEventCreate(&h->ev0));
   UFM_CUDA(cudaEventCreate(&h->ev1));
   *out = h;
@@ -278,6 +291,14 @@ static bool is_pinned(const ufm_handle *h, const void *p, size_t bytes)
   return false;
 }
 
+// a field behind one of the cached critical time steps is about to change from outside the kernels that reduce them (ufm_k_cfl)
+static void cfl_invalidate(ufm_handle *h, int field)
+{
+  if (field == UFM_F_D_SIA_AC) h->cfl_ok[0] = false;
+  if (field == UFM_F_U_SSA || field == UFM_F_V_SSA) h->cfl_ok[1] = false;
+  if (field == UFM_F_U_3D || field == UFM_F_V_3D) h->cfl_ok[2] = false;
+}
+
 static int field_copy(ufm_handle *h, int field, void *host, int to_device)
 {
   if (!h || !h->has_mesh) return ufm_set_error(-2, "no mesh resident");
@@ -300,6 +321,7 @@ static int field_copy(ufm_handle *h, int field, void *host, int to_device)
   if (!to_device && field >= UFM_F_DU_DX_AAAC && field <= UFM_F_DV_DY_AAAC) { if ((rc = ufm_k_ssa_gradients(h))) return rc; }
   if (to_device) {
     if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
+    cfl_invalidate(h, field);
     const void *src = host;
     if (!is_pinned(h, host, bytes)) { memcpy(h->staging, host, bytes); src = h->staging; }
     UFM_CUDA(cudaMemcpyAsync(h->dev_staging, src, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -372,6 +394,7 @@ int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int ord
   if (map->nV_dst != h->mesh.nV) return ufm_set_error(-2, "ufm_remap_apply: map is for %d destination vertices, the resident mesh has %d", map->nV_dst, h->mesh.nV);
   const int slot = stash_slot(h, field, false);
   if (slot < 0 || !h->stash[slot].d) return ufm_set_error(-2, "ufm_remap_apply: field %d was not stashed on the old mesh", field);
+  cfl_invalidate(h, field);
   for (int i = 0; i < map->n_tot; i++) if (map->vi[i] < 1 || map->vi[i] > h->stash[slot].n) return ufm_set_error(-2, "ufm_remap_apply: source vertex index out of range");
   FieldRef r;
   int rc = field_ref(h, field, &r);
@@ -384,6 +407,7 @@ int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int ord
 }
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }
+int ufm_pow_mode(ufm_handle *h) { return h ? h->pow_exact : ufm_set_error(-2, "NULL handle"); }
 int ufm_resident_dims(ufm_handle *h, int dims[5])
 {
   if (!h || !dims) return ufm_set_error(-2, "NULL argument");
@@ -557,6 +581,127 @@ static int xfer_finish(ufm_handle *h)
   return 0;
 }
 
+// ---- device-driven region loop ---------------------------------------------------------------------------------------------
+// For the benchmark experiments whose step needs nothing from the host (no SSA solve: solve_SSA sets the velocities to zero; a
+// time-independent closed-form mass balance; no thermodynamics on the mesh): determine_timesteps_and_actions
+// (src/UFEMISM_main_model.f90:708-843) runs in a one-thread kernel at the end of every step, the step's kernels read the time step
+// and their "due" flags from device memory, and the host enqueues UFM_DEVICE_BATCH steps between synchronisations instead of one.
+// Same arithmetic, same order: identical trajectories (tests/test_gpu_parity.py::test_device_loop_matches_host_loop).
+struct StepCtl {
+  ufm_region r;
+  double t_end, dt_max;
+  long long steps_left;
+  int g_run, g_sia, g_smb, g_thermo;   // gates of the next step's kernels
+  int sia3d_on_thermo_timer;           // EISMINT experiments (update_ice_temperature's velocity half feeds the critical time step)
+};
+__global__ void k_step_control(StepCtl *c, unsigned long long *keys)
+{
+  if (!c->g_run) return;
+  ufm_region &r = c->r;
+  // what the step that has just run did (run_model, :78-214)
+  r.t0[UFM_T_ELRA] = r.time;
+  if (r.do_[UFM_T_SIA]) { r.t0[UFM_T_SIA] = r.time; r.n_sia++; }
+  if (r.do_[UFM_T_SSA]) { r.t0[UFM_T_SSA] = r.time; r.n_ssa++; }
+  if (r.do_[UFM_T_CLIMATE]) r.t0[UFM_T_CLIMATE] = r.time;
+  if (r.do_[UFM_T_SMB]) r.t0[UFM_T_SMB] = r.time;
+  if (r.do_[UFM_T_BMB]) r.t0[UFM_T_BMB] = r.time;
+  if (r.do_[UFM_T_THERMO]) r.t0[UFM_T_THERMO] = r.time;
+  if (r.do_[UFM_T_OUTPUT]) r.t0[UFM_T_OUTPUT] = r.time;
+  // determine_timesteps_and_actions
+  const double dt_correction_factor = 0.9;
+  const double dt_D_2D_min = ord_unkey(keys[0]) * dt_correction_factor, dt_V_2D_SSA_min = ord_unkey(keys[1]) * dt_correction_factor,
+               dt_V_3D_SIA_min = ord_unkey(keys[2]) * dt_correction_factor;
+  r.dt_crit_last[0] = dt_D_2D_min; r.dt_crit_last[1] = dt_V_2D_SSA_min; r.dt_crit_last[2] = dt_V_3D_SIA_min;
+  r.dt = fmin(fmin(fmin(dt_D_2D_min, dt_V_2D_SSA_min), dt_V_3D_SIA_min), c->dt_max);
+  if (fabs(1.0 - r.dt / r.dt_prev) > 0.1) r.dt_prev = r.dt;
+  r.dtc[UFM_T_SIA] = fmin(c->dt_max, fmin(dt_D_2D_min, dt_V_3D_SIA_min));
+  r.dtc[UFM_T_SSA] = fmin(c->dt_max, dt_V_2D_SSA_min);
+  double t_next_action = 0.0;
+  for (int k = 0; k < UFM_NT; k++) { r.t1[k] = r.t0[k] + r.dtc[k]; if (k == 0 || r.t1[k] < t_next_action) t_next_action = r.t1[k]; }
+  r.dt = t_next_action - r.time;
+  for (int k = 0; k < UFM_NT; k++) r.do_[k] = (t_next_action == r.t1[k]);
+  if (t_next_action >= c->t_end) {
+    r.dt = c->t_end - r.time;
+    r.do_[UFM_T_SIA] = r.do_[UFM_T_SSA] = r.do_[UFM_T_THERMO] = r.do_[UFM_T_CLIMATE] = r.do_[UFM_T_SMB] = r.do_[UFM_T_BMB] = 1;
+  }
+  r.time = r.time + r.dt;
+  r.n_steps++;
+  c->steps_left--;
+  // gates of the next step and the minima its producers will reduce again
+  c->g_run = (r.time < c->t_end && c->steps_left != 0) ? 1 : 0;
+  c->g_sia = (c->g_run && r.do_[UFM_T_SIA]) ? 1 : 0;
+  c->g_smb = (c->g_run && r.do_[UFM_T_SMB]) ? 1 : 0;
+  c->g_thermo = (c->g_run && r.do_[UFM_T_THERMO] && c->sia3d_on_thermo_timer) ? 1 : 0;
+  if (c->g_sia) keys[0] = ord_key(1000.0);
+  if (c->g_thermo) keys[2] = ord_key(1000.0);
+}
+
+static bool device_loop_applies(const ufm_handle *h, const ufm_host_ice *host)
+{
+  const int b = h->P.benchmark;
+  const char *e = getenv("UFM_DEVICE_LOOP");
+  if (e && atoi(e) == 0) return false;
+  // no SSA solve, a mass balance that does not depend on time (the time-dependent ones go through the host's libm: sin, pow), no
+  // column thermodynamics on the device, one GPU
+  return !host && (b == UFM_BM_EISMINT_1 || b == UFM_BM_EISMINT_4 || b == UFM_BM_HALFAR) && !h->mesh.has_tri && !h->st.realistic_A && h->mesh.P == 1;
+}
+
+#define UFM_DEVICE_BATCH 64
+static int run_model_device(ufm_handle *h, ufm_region *r, double t_end, long max_steps)
+{
+  int rc;
+  const int b = h->P.benchmark;
+  if (!h->stepctl_dev) {
+    UFM_CUDA(cudaMalloc(&h->stepctl_dev, sizeof(StepCtl)));
+    UFM_CUDA(cudaMallocHost(&h->stepctl_host, sizeof(StepCtl)));
+  }
+  StepCtl *cd = (StepCtl *)h->stepctl_dev, *ch = (StepCtl *)h->stepctl_host;
+  if (!(r->time < t_end) || max_steps < 0) return 0;
+  // a clean start: zero SSA velocities (what solve_SSA does for these experiments whenever it is due) and every cached critical
+  // time step valid for the fields as they are now
+  if ((rc = ufm_k_ssa_zero(h))) return rc;
+  { double d3[3]; if ((rc = ufm_k_cfl(h, d3))) return rc; }
+  const bool eismint = b >= UFM_BM_EISMINT_1 && b <= UFM_BM_EISMINT_6;
+  memset(ch, 0, sizeof(*ch));
+  ch->r = *r; ch->t_end = t_end; ch->dt_max = h->P.dt_max; ch->steps_left = max_steps > 0 ? max_steps : -1;
+  ch->sia3d_on_thermo_timer = eismint ? 1 : 0;
+  ch->g_run = 1; ch->g_sia = r->do_[UFM_T_SIA] ? 1 : 0; ch->g_smb = r->do_[UFM_T_SMB] ? 1 : 0;
+  ch->g_thermo = (r->do_[UFM_T_THERMO] && eismint) ? 1 : 0;
+  UFM_CUDA(cudaMemcpyAsync(cd, ch, sizeof(StepCtl), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = ufm_cfl_key_reset(h, (ch->g_sia ? 1 : 0) | (ch->g_thermo ? 4 : 0)))) return rc;
+  h->gate[0] = &cd->g_run; h->gate[1] = &cd->g_sia; h->gate[2] = &cd->g_smb; h->gate[3] = &cd->g_thermo;
+  h->dt_dev = &cd->r.dt;
+  long enq = 0;
+  const long steps0 = r->n_steps;
+  bool done = false;
+  rc = 0;
+  while (!done && !rc) {
+    const long nb = (max_steps > 0 && max_steps - enq < UFM_DEVICE_BATCH) ? max_steps - enq : UFM_DEVICE_BATCH;
+    for (long k = 0; k < nb && !rc; k++) {
+      if ((rc = ufm_k_thickness(h, 0.0))) break;
+      if ((rc = ufm_k_geom(h, 0.0))) break;
+      if ((rc = ufm_k_sia(h))) break;
+      if ((rc = ufm_k_smb_benchmark(h, 0.0, r->H0, r->R0, r->lambda))) break;
+      if (eismint) { if ((rc = ufm_k_sia3d(h))) break; if ((rc = ufm_k_cfl3d_enqueue(h))) break; }
+      k_step_control<<<1, 1, 0, h->stream>>>(cd, h->st.ctrl + CTRL_CFL_KEYS);
+      h->cnt.kernel_launches++;
+      enq++;
+    }
+    if (rc) break;
+    if ((rc = ufm_cuda_check(cudaMemcpyAsync(ch, cd, sizeof(StepCtl), cudaMemcpyDeviceToHost, h->stream), "device loop: read back"))) break;
+    if ((rc = ufm_cuda_check(cudaStreamSynchronize(h->stream), "device loop: synchronise"))) break;
+    done = !ch->g_run || (max_steps > 0 && enq >= max_steps);
+  }
+  h->gate[0] = h->gate[1] = h->gate[2] = h->gate[3] = nullptr;
+  h->dt_dev = nullptr;
+  if (rc) return rc;
+  // ufm_k_thickness swaps Hi / Hi_prev on the host at every enqueued step; steps enqueued after the end did not run
+  if ((enq - (ch->r.n_steps - steps0)) & 1) { double *t = h->st.Hi; h->st.Hi = h->st.Hi_alt; h->st.Hi_alt = t; }
+  *r = ch->r;
+  h->cfl_ok[0] = h->cfl_ok[1] = h->cfl_ok[2] = true;   // reduced by the last step that changed the fields behind them
+  return 0;
+}
+
 static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_steps, const ufm_host_ice *host)
 {
   NEED_MESH(h);
@@ -578,6 +723,7 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     r->dtc[UFM_T_THERMO] = h->P.dt_thermo;
     r->t1[UFM_T_THERMO] = r->t0[UFM_T_THERMO] + h->P.dt_thermo;
   }
+  if (device_loop_applies(h, host)) return run_model_device(h, r, t_end, max_steps);
   // drop-in mode: UFM_XFER_OVERLAP=0 falls back to one synchronous copy per field (A/B measurements)
   bool overlap = false;
   if (host) {

@@ -13,7 +13,9 @@
 #include <cstring>
 
 #include "ufm_internal.cuh"
+#include "ufm_pow.cuh"
 
+int ufm_geom_powtab_init(const UfmPowTab *t) { return ufm_powtab_upload_tu(t); }
 static inline int grid_for(long long n, int b) { return (int)((n + b - 1) / b); }
 
 __device__ __forceinline__ bool g_is_floating(double Hi, double Hb, double SL)
@@ -38,11 +40,16 @@ __device__ __forceinline__ unsigned g_bits1(double Hi, double Hb, double SL)
   return b | (code << MB_CODE_SHIFT);
 }
 
+// Device-driven region loop (ufm_api.cu, run_model_device): the per-step kernels are enqueued many steps ahead; whether a step still
+// runs, and which of its actions are due, is decided on the device (k_step_control) and read here.  gate == NULL: always run.
+#define UFM_GATE(g) do { if ((g) && !*((const volatile int *)(g))) return; } while (0)
+
 // ---- Aa stage 1: Hs, dHs_dt, primary mask bits ----
 __global__ void k_geom_aa1(int nV, const double *__restrict__ Hi, const double *__restrict__ Hb, const double *__restrict__ SL,
                            const double *__restrict__ dHb_dt, const double *__restrict__ dHi_dt, double *__restrict__ Hs,
-                           double *__restrict__ dHs_dt, unsigned *__restrict__ mbits)
+                           double *__restrict__ dHs_dt, unsigned *__restrict__ mbits, const int *gate)
 {
+  UFM_GATE(gate);
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
   const double hi = Hi[v], hb = Hb[v], sl = SL[v];
@@ -62,9 +69,11 @@ struct GeomAa2Args {
   const double *Hi, *Hs;
   unsigned *mbits;
   double *dHi_dx, *dHi_dy, *dHs_dx, *dHs_dy, *sx, *sy;
+  const int *gate;
 };
 __global__ void __launch_bounds__(256) k_geom_aa2(GeomAa2Args a)
 {
+  UFM_GATE(a.gate);
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int s = wg; s < a.n_slices; s += nw) {
@@ -116,9 +125,11 @@ struct GeomAcArgs {
   double *dHi[4], *dHb[4], *dHs[4], *dSL[4];
   double *sx, *sy;
   unsigned *mbits_Ac;
+  const int *gate;
 };
 __global__ void __launch_bounds__(256) k_geom_ac(GeomAcArgs a)
 {
+  UFM_GATE(a.gate);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nAc) return;
   const int4 v = a.Aci[i];
@@ -189,20 +200,24 @@ __global__ void __launch_bounds__(256) k_flow_mean(int n, int nVp, ZetaConst Z, 
   A_mean[i] = out;
 }
 
+// dt_D_2D of one staggered vertex (UFEMISM_main_model.f90:752; the kind-less 1E-09 is a single-precision literal)
+__device__ __forceinline__ double cfl_dt_D(const double dist2, const double D) { return dist2 / (-6.0 * UFM_PI * (D - (double)1E-09f)); }
+
 // solve_SIA with a per-layer flow factor: f(k) = m_enh_sia * A_flow_Ac(aci,k) * zeta(k)**n, integrated in registers
 __global__ void __launch_bounds__(256) k_sia_ac_T(int nAc, int nVp, ZetaConst Z, double m_enh_sia, const int4 *__restrict__ Aci, const double *__restrict__ Ti,
                                                   const unsigned *__restrict__ mbits_Ac, const double *__restrict__ Hi_Ac, const double *__restrict__ hx,
                                                   const double *__restrict__ hy, const double *__restrict__ hp, const double *__restrict__ ho,
-                                                  double *__restrict__ D_SIA_Ac, double *__restrict__ Ux, double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo)
+                                                  double *__restrict__ D_SIA_Ac, double *__restrict__ Ux, double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo,
+                                                  const double *__restrict__ dist2, unsigned long long *cfl_key)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nAc) return;
+  const bool in = i < nAc;
   double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
-  if (mbits_Ac[i] & MB_SHEET) {
+  if (in && (mbits_Ac[i] & MB_SHEET)) {
     const double D_uv_3D_cutoff = -1E5;
     const int4 v = Aci[i];
     const double H = Hi_Ac[i], sp = hp[i], so = ho[i];
-    const double D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
+    const double D_0 = ufm_pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
     const double twoH = 2.0 * H;
     double I[UFM_MAX_NZ];
     I[Z.nZ - 1] = 0.0;
@@ -223,7 +238,8 @@ __global__ void __launch_bounds__(256) k_sia_ac_T(int nAc, int nVp, ZetaConst Z,
     }
     D = H * avg; ux = avg * hx[i]; uy = avg * hy[i]; up = avg * sp; uo = avg * so;
   }
-  D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo;
+  if (in) { D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo; }
+  block_min_to_key(in ? cfl_dt_D(dist2[i], D) : 1000.0, cfl_key);
 }
 
 // ---- solve_SIA on Ac (ice_dynamics_module.f90:240-306); the 3-D diffusivity profile stays in registers.
@@ -233,16 +249,18 @@ struct SiaConst { int nZ; double I[UFM_MAX_NZ]; double dz[UFM_MAX_NZ]; };
 __global__ void __launch_bounds__(256) k_sia_ac(int nAc, SiaConst K, const unsigned *__restrict__ mbits_Ac, const double *__restrict__ Hi_Ac,
                                                 const double *__restrict__ hx, const double *__restrict__ hy, const double *__restrict__ hp,
                                                 const double *__restrict__ ho, double *__restrict__ D_SIA_Ac, double *__restrict__ Ux,
-                                                double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo)
+                                                double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo,
+                                                const double *__restrict__ dist2, unsigned long long *cfl_key, const int *gate)
 {
+  UFM_GATE(gate);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nAc) return;
+  const bool in = i < nAc;
   double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
-  if (mbits_Ac[i] & MB_SHEET) {
+  if (in && (mbits_Ac[i] & MB_SHEET)) {
     const double D_uv_3D_cutoff = -1E5;
     const double H = Hi_Ac[i], sp = hp[i], so = ho[i];
     // (rho g H)**n_flow * (hp**2 + ho**2)**((n_flow-1)/2)   [x**1.0 == x]
-    const double D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
+    const double D_0 = ufm_pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (sp * sp + so * so);
     const double twoH = 2.0 * H;
     double prev = D_0 * (twoH * K.I[0]);
     if (prev < D_uv_3D_cutoff) prev = D_uv_3D_cutoff;
@@ -255,7 +273,9 @@ __global__ void __launch_bounds__(256) k_sia_ac(int nAc, SiaConst K, const unsig
     }
     D = H * avg; ux = avg * hx[i]; uy = avg * hy[i]; up = avg * sp; uo = avg * so;
   }
-  D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo;
+  if (in) { D_SIA_Ac[i] = D; Ux[i] = ux; Uy[i] = uy; Up[i] = up; Uo[i] = uo; }
+  // epilogue: this vertex's diffusive critical time step, reduced over the CTA into the cached minimum (see ufm_k_cfl)
+  block_min_to_key(in ? cfl_dt_D(dist2[i], D) : 1000.0, cfl_key);
 }
 
 // ---- solve_SIA_3D, U_3D / V_3D half (ice_dynamics_module.f90:317-367) + apply_Neumann_boundary_3D
@@ -264,8 +284,9 @@ template <bool REALISTIC>
 __global__ void __launch_bounds__(256) k_sia3d_uv(int nV, int nVp, SiaConst K, ZetaConst Z, double m_enh_sia, const double *__restrict__ Ti,
                                                   const unsigned *__restrict__ mbits, const double *__restrict__ Hi, const double *__restrict__ hx,
                                                   const double *__restrict__ hy, const double *__restrict__ U_SSA, const double *__restrict__ V_SSA,
-                                                  double *__restrict__ U3, double *__restrict__ V3)
+                                                  double *__restrict__ U3, double *__restrict__ V3, const int *gate)
 {
+  UFM_GATE(gate);
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
   const double us = U_SSA[v], vs = V_SSA[v], H = Hi[v];
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(256) k_sia3d_uv(int nV, int nVp, SiaConst K, Z
   double D_0 = 0.0, dx = 0.0, dy = 0.0;
   if (!plain) {
     dx = hx[v]; dy = hy[v];
-    D_0 = pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (dx * dx + dy * dy);
+    D_0 = ufm_pow(UFM_ICE_DENSITY * UFM_GRAV * H, UFM_N_FLOW) * (dx * dx + dy * dy);
     if (REALISTIC) {
       I[Z.nZ - 1] = 0.0;
       double fk1 = m_enh_sia * g_arrhenius(Ti[(size_t)(Z.nZ - 1) * nVp + v]) * Z.z3[Z.nZ - 1];
@@ -299,8 +320,9 @@ __global__ void __launch_bounds__(256) k_sia3d_uv(int nV, int nVp, SiaConst K, Z
 // vertices 1..4) from all neighbours at their new values
 __global__ void __launch_bounds__(256) k_neumann_3d(int stage, int n_slices, int nVp, int nZ, const long long *__restrict__ off,
                                                     const unsigned char *__restrict__ deg, const unsigned char *__restrict__ edge,
-                                                    const int *__restrict__ dev2ref, const int *__restrict__ C, double *U3, double *V3)
+                                                    const int *__restrict__ dev2ref, const int *__restrict__ C, double *U3, double *V3, const int *gate = nullptr)
 {
+  UFM_GATE(gate);
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int s = wg; s < n_slices; s += nw) {
@@ -332,9 +354,11 @@ struct SiaAaArgs {
   const int *iAci;
   const double *Ux, *Uy, *D;
   double *U_SIA, *V_SIA, *D_SIA;
+  const int *gate;
 };
 __global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
 {
+  UFM_GATE(a.gate);
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int s = wg; s < a.n_slices; s += nw) {
@@ -366,6 +390,8 @@ struct ThkArgs {
   const double *A, *Cw, *UpSIA, *UpSSA, *Hi, *SMB, *BMB;
   const int *noice;
   double dt;
+  const double *dt_dev;              // device-driven loop: the time step lives on the device (else NULL)
+  const int *gate;
   double *factor, *smb;              // pass 1 out / pass 2 in
   double *Hi_new, *dHi_dt;           // pass 2 out
 };
@@ -384,6 +410,8 @@ __device__ __forceinline__ double thk_entry(const ThkArgs &a, long long e, int v
 template <int PASS>
 __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
 {
+  UFM_GATE(a.gate);
+  if (a.dt_dev) a.dt = *a.dt_dev;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   for (int s = wg; s < a.n_slices; s += nw) {
@@ -478,47 +506,32 @@ __global__ void __launch_bounds__(256) k_remap_apply(int nV_dst, int order, cons
 }
 
 // ---- critical time steps (UFEMISM_main_model.f90:747-768) ----
-__device__ __forceinline__ unsigned long long ord_key(double x)
+// `which`: bit 0 dt_D_2D, bit 1 dt_V_2D_SSA, bit 2 dt_V_3D_SIA -- only the minima whose cached value is stale are recomputed
+__global__ void __launch_bounds__(256) k_cfl(int which, int nV, int nVp, int nAc, int nZ, const double *__restrict__ dist2, const double *__restrict__ D_SIA_Ac,
+                                             const double *__restrict__ U, const double *__restrict__ V, const double *__restrict__ rmin,
+                                             const double *__restrict__ sqrtApi, const double *__restrict__ U3, const double *__restrict__ V3, unsigned long long *keys,
+                                             const int *gate)
 {
-  unsigned long long b = (unsigned long long)__double_as_longlong(x);
-  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__host__ __device__ __forceinline__ double ord_unkey(unsigned long long k)
-{
-  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-  double x;
-#ifdef __CUDA_ARCH__
-  x = __longlong_as_double((long long)b);
-#else
-  memcpy(&x, &b, sizeof(x));
-#endif
-  return x;
-}
-__global__ void __launch_bounds__(256) k_cfl(int nV, int nVp, int nAc, int nZ, const int4 *__restrict__ Aci, const double *__restrict__ Dx_,
-                                             const double *__restrict__ Dy_, const double *__restrict__ D_SIA_Ac, const double *__restrict__ U,
-                                             const double *__restrict__ V, const double *__restrict__ sqrtApi, const double *__restrict__ U3,
-                                             const double *__restrict__ V3, unsigned long long *keys)
-{
+  UFM_GATE(gate);
   double mD = 1000.0, mS = 1000.0, m3 = 1000.0;
-  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  for (int i = t0; i < nAc; i += nt) {
-    const int4 v = Aci[i];
-    const double dx = Dx_[i], dy = Dy_[i];
-    const double dist = sqrt(dx * dx + dy * dy);
-    const double dtD = (dist * dist) / (-6.0 * UFM_PI * (D_SIA_Ac[i] - (double)1E-09f));  // single-precision literal at :752
-    mD = fmin(dtD, mD);
-    mS = fmin(dist / (fabs(U[v.x]) + fabs(V[v.x])), mS);
-    mS = fmin(dist / (fabs(U[v.y]) + fabs(V[v.y])), mS);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((which & 1) && i < nAc) mD = cfl_dt_D(dist2[i], D_SIA_Ac[i]);
+  if (i < nV) {
+    // the reference takes dist / (|U| + |V|) at both ends of every connection and SQRT(A/pi) / (|U| + |V|) per vertex (:754-762); IEEE
+    // division is monotone in its numerator, so per vertex that is the smallest numerator (rmin, fixed per mesh) over the same sum
+    if (which & 2) mS = rmin[i] / (fabs(U[i]) + fabs(V[i]));
+    if (which & 4) {
+      const double r = sqrtApi[i];
+      for (int k = 0; k < nZ; k++) m3 = fmin(r / (fabs(U3[(size_t)k * nVp + i]) + fabs(V3[(size_t)k * nVp + i])), m3);
+    }
   }
-  for (int i = t0; i < nV; i += nt) {
-    const double r = sqrtApi[i];
-    mS = fmin(r / (fabs(U[i]) + fabs(V[i])), mS);
-    for (int k = 0; k < nZ; k++) m3 = fmin(r / (fabs(U3[(size_t)k * nVp + i]) + fabs(V3[(size_t)k * nVp + i])), m3);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    mD = fmin(mD, __shfl_xor_sync(0xffffffffu, mD, o)); mS = fmin(mS, __shfl_xor_sync(0xffffffffu, mS, o)); m3 = fmin(m3, __shfl_xor_sync(0xffffffffu, m3, o));
-  }
-  if ((threadIdx.x & 31) == 0) { atomicMin(keys + 0, ord_key(mD)); atomicMin(keys + 1, ord_key(mS)); atomicMin(keys + 2, ord_key(m3)); }
+  if (which & 1) block_min_to_key(mD, keys + 0);
+  if (which & 2) { __syncthreads(); block_min_to_key(mS, keys + 1); }
+  if (which & 4) { __syncthreads(); block_min_to_key(m3, keys + 2); }
+}
+__global__ void k_cfl_key_reset(int which, unsigned long long *keys)
+{
+  if (threadIdx.x < 3 && ((which >> threadIdx.x) & 1)) keys[threadIdx.x] = ord_key(1000.0);
 }
 
 // ---- permuted copies between reference order (device staging) and device order ----
@@ -592,18 +605,18 @@ int ufm_k_geom(ufm_handle *h, double time)
     if (time < 25000.0) A_flow = 1.0E-16; else if (time < 50000.0) A_flow = 1.0E-17; else if (time < 75000.0) A_flow = 1.0E-16;
   }
   s.A_flow_const = A_flow;
-  k_geom_aa1<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, s.Hi, s.Hb, s.SL, s.dHb_dt, s.dHi_dt, s.Hs, s.dHs_dt, s.mbits);
+  k_geom_aa1<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, s.Hi, s.Hb, s.SL, s.dHb_dt, s.dHi_dt, s.Hs, s.dHs_dt, s.mbits, h->gate[0]);
   GeomAa2Args a2;
   a2.n_slices = m.aa.n_slices; a2.off = m.aa.off; a2.deg = m.aa.deg; a2.C = m.aa_C; a2.Nx = m.aa_Nx; a2.Ny = m.aa_Ny; a2.Nx0 = m.aa_Nx0; a2.Ny0 = m.aa_Ny0;
   a2.Hi = s.Hi; a2.Hs = s.Hs; a2.mbits = s.mbits; a2.dHi_dx = s.dHi_dx; a2.dHi_dy = s.dHi_dy; a2.dHs_dx = s.dHs_dx; a2.dHs_dy = s.dHs_dy;
-  a2.sx = s.dHs_dx_shelf; a2.sy = s.dHs_dy_shelf;
+  a2.sx = s.dHs_dx_shelf; a2.sy = s.dHs_dy_shelf; a2.gate = h->gate[0];
   int g2 = grid_for((long long)m.aa.n_slices * 32, 256);
   k_geom_aa2<<<g2, 256, 0, h->stream>>>(a2);
   GeomAcArgs ac;
   ac.nAc = m.nAc; ac.Aci = m.ac_Aci; ac.Np = m.ac_Np;
   for (int k = 0; k < 4; k++) { ac.Nx[k] = m.ac_Nx[k]; ac.Ny[k] = m.ac_Ny[k]; ac.No[k] = m.ac_No[k]; ac.dHi[k] = s.dHi_Ac[k]; ac.dHb[k] = s.dHb_Ac[k]; ac.dHs[k] = s.dHs_Ac[k]; ac.dSL[k] = s.dSL_Ac[k]; }
   ac.Hi = s.Hi; ac.Hb = s.Hb; ac.SL = s.SL; ac.Hs = s.Hs; ac.mbits = s.mbits;
-  ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac;
+  ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac; ac.gate = h->gate[0];
   k_geom_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(ac);
   h->cnt.kernel_launches += 3;
   if (s.realistic_A) {
@@ -630,19 +643,25 @@ int ufm_k_sia(ufm_handle *h)
   for (int k = K.nZ - 1; k >= 1; k--) K.I[k - 1] = K.I[k] - 0.5 * (f[k] + f[k - 1]) * (h->P.zeta[k] - h->P.zeta[k - 1]);
   K.dz[0] = 0.0;
   for (int k = 1; k < K.nZ; k++) K.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
+  // the diffusive critical time step is re-reduced by the kernel below (device-driven loop: k_step_control resets the key, and only
+  // when the solve is due)
+  if (!h->gate[1]) { int rc_ = ufm_cfl_key_reset(h, 1); if (rc_) return rc_; }
   if (s.realistic_A) {
     ZetaConst Z;
     Z.nZ = h->P.nZ; Z.dz[0] = 0.0;
     for (int k = 1; k < Z.nZ; k++) Z.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
     for (int k = 0; k < Z.nZ; k++) Z.z3[k] = h->zeta3[k];
     k_sia_ac_T<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.nVp, Z, h->P.m_enh_sia, m.ac_Aci, s.Ti, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1],
-                                                            s.dHs_Ac[2], s.dHs_Ac[3], s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3]);
+                                                            s.dHs_Ac[2], s.dHs_Ac[3], s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3],
+                                                            m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0);
   } else
   k_sia_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, K, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1], s.dHs_Ac[2], s.dHs_Ac[3],
-                                                       s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3]);
+                                                       s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3],
+                                                       m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0, h->gate[1]);
+  h->cfl_ok[0] = true;
   SiaAaArgs a;
   a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.iAci = m.aa_iAci; a.Ux = s.U_SIA_Ac[0]; a.Uy = s.U_SIA_Ac[1]; a.D = s.D_SIA_Ac;
-  a.U_SIA = s.U_SIA; a.V_SIA = s.V_SIA; a.D_SIA = s.D_SIA;
+  a.U_SIA = s.U_SIA; a.V_SIA = s.V_SIA; a.D_SIA = s.D_SIA; a.gate = h->gate[1];
   k_sia_aa<<<grid_for((long long)m.aa.n_slices * 32, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches += 2;
   return ufm_cuda_check(cudaGetLastError(), "k_sia");
@@ -662,13 +681,14 @@ int ufm_k_sia3d(ufm_handle *h)
   for (int k = 1; k < K.nZ; k++) K.dz[k] = Z.dz[k] = h->P.zeta[k] - h->P.zeta[k - 1];
   for (int k = 0; k < K.nZ; k++) Z.z3[k] = h->zeta3[k];
   if (s.realistic_A)
-    k_sia3d_uv<true><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D);
+    k_sia3d_uv<true><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D, h->gate[3]);
   else
-    k_sia3d_uv<false><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D);
+    k_sia3d_uv<false><<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, m.nVp, K, Z, h->P.m_enh_sia, s.Ti, s.mbits, s.Hi, s.dHs_dx, s.dHs_dy, s.U_SSA, s.V_SSA, s.U_3D, s.V_3D, h->gate[3]);
   int g = grid_for((long long)m.aa.n_slices * 32, 256);
-  k_neumann_3d<<<g, 256, 0, h->stream>>>(0, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D);
-  k_neumann_3d<<<g, 256, 0, h->stream>>>(1, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(0, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D, h->gate[3]);
+  k_neumann_3d<<<g, 256, 0, h->stream>>>(1, m.aa.n_slices, m.nVp, h->P.nZ, m.aa.off, m.aa.deg, m.aa_edge, m.aa_dev2ref, m.aa_C, s.U_3D, s.V_3D, h->gate[3]);
   h->cnt.kernel_launches += 3;
+  h->cfl_ok[2] = false;   // reduced again from the final (U,V)_3D by the next ufm_cfl (once per thermodynamics step)
   return ufm_cuda_check(cudaGetLastError(), "k_sia3d");
 }
 
@@ -676,8 +696,9 @@ int ufm_k_sia3d(ufm_handle *h)
 //      the constants of Halfar / MISMIP_mod, mesh_generation_test.  Everything that does not depend on the vertex is
 //      evaluated on the host with the host libm, as the reference does once per call. ----
 struct SmbArgs { int mode; double E, S_b, M_max, H0f1, f2, R0, lam_tp_spy, value; };
-__global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const double2 *__restrict__ xy, double *__restrict__ SMB_year)
+__global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const double2 *__restrict__ xy, double *__restrict__ SMB_year, const int *gate)
 {
+  UFM_GATE(gate);
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
   const double2 p = xy[v];
@@ -686,8 +707,8 @@ __global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const 
   else if (a.mode == 1) out = fmin(a.M_max, a.S_b * (a.E - ufm_norm2_2(p.x, p.y)));   // dist = NORM2( mesh%V( vi,:))
   else if (a.mode == 2) {
     const double f3 = sqrt((p.x * p.x) + (p.y * p.y)) / a.R0;                     // x**2._dp: pow( x, 2) is exactly x*x
-    const double f4 = fmax(0.0, 1.0 - pow(a.f2 * f3, 4.0 / 3.0));
-    const double H = a.H0f1 * pow(f4, 3.0 / 7.0);
+    const double f4 = fmax(0.0, 1.0 - ufm_pow(a.f2 * f3, 4.0 / 3.0));
+    const double H = a.H0f1 * ufm_pow(f4, 3.0 / 7.0);
     out = a.lam_tp_spy * H * UFM_SEC_PER_YEAR;
   } else {
     const double R = ufm_norm2_2(p.x, p.y);
@@ -724,7 +745,7 @@ int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double
     f2 = pow(tp / t0, -beta);
     a.mode = 2; a.H0f1 = H0 * f1; a.f2 = f2; a.R0 = R0; a.lam_tp_spy = lambda / tp;
   } else return ufm_set_error(-4, "no closed-form SMB for benchmark %d: SMB_year comes from the host", b);
-  k_smb_benchmark<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, a, m.aa_xy, s.SMB_year);
+  k_smb_benchmark<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, a, m.aa_xy, s.SMB_year, h->gate[2]);
   h->cnt.kernel_launches++;
   return ufm_cuda_check(cudaGetLastError(), "k_smb_benchmark");
 }
@@ -790,6 +811,7 @@ int ufm_k_thickness(ufm_handle *h, double dt)
   a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.edge = m.aa_edge; a.C = m.aa_C; a.iAci = m.aa_iAci; a.A = m.aa_A; a.Cw = m.ac_Cw;
   a.UpSIA = s.U_SIA_Ac[2]; a.UpSSA = s.U_SSA_Ac[2]; a.Hi = s.Hi; a.SMB = s.SMB_year; a.BMB = s.BMB; a.noice = s.mask_noice; a.dt = dt;
   a.factor = s.thk_factor; a.smb = s.thk_smb; a.Hi_new = s.Hi_alt; a.dHi_dt = s.dHi_dt;
+  a.dt_dev = h->dt_dev; a.gate = h->gate[0];
   int g = grid_for((long long)m.aa.n_slices * 32, 256);
   k_thk<1><<<g, 256, 0, h->stream>>>(a);
   k_thk<2><<<g, 256, 0, h->stream>>>(a);
@@ -799,14 +821,39 @@ int ufm_k_thickness(ufm_handle *h, double dt)
   return ufm_cuda_check(cudaGetLastError(), "k_thk");
 }
 
+int ufm_cfl_key_reset(ufm_handle *h, int which)
+{
+  k_cfl_key_reset<<<1, 32, 0, h->stream>>>(which, h->st.ctrl + CTRL_CFL_KEYS);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_cfl_key_reset");
+}
+
+// the 3-D critical time step alone, re-reduced from (U,V)_3D into its key; no host synchronisation (device-driven loop, gate: thermodynamics due)
+int ufm_k_cfl3d_enqueue(ufm_handle *h)
+{
+  DevMesh &m = h->mesh; DevState &s = h->st;
+  k_cfl<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(4, m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_dist2, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
+                                                    m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, s.ctrl + CTRL_CFL_KEYS, h->gate[3]);
+  h->cnt.kernel_launches++;
+  return ufm_cuda_check(cudaGetLastError(), "k_cfl (3-D)");
+}
+
 int ufm_k_cfl(ufm_handle *h, double out3[3])
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   unsigned long long *keys = s.ctrl + CTRL_CFL_KEYS;
-  UFM_CUDA(cudaMemsetAsync(keys, 0xFF, 3 * sizeof(unsigned long long), h->stream));
-  k_cfl<<<h->num_sms * 4, 256, 0, h->stream>>>(m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_Aci, m.ac_Dx, m.ac_Dy, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
-                                               m.aa_sqrtApi, s.U_3D, s.V_3D, keys);
-  h->cnt.kernel_launches++;
+  int which = 0;
+  for (int k = 0; k < 3; k++) if (!h->cfl_ok[k]) which |= 1 << k;
+  if (getenv("UFM_CFL_RECOMPUTE")) which = 7;   // A/B and tests: ignore the cached minima
+  if (which) {
+    int rc = ufm_cfl_key_reset(h, which);
+    if (rc) return rc;
+    const int n = (which & 1) ? (m.nAc > m.nV ? m.nAc : m.nV) : m.nV;   // thread i: staggered vertex i (bit 0) and vertex i (bits 1, 2)
+    k_cfl<<<grid_for(n, 256), 256, 0, h->stream>>>(which, m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_dist2, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
+                                                   m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, keys, nullptr);
+    h->cnt.kernel_launches++;
+    h->cfl_ok[0] = h->cfl_ok[1] = h->cfl_ok[2] = true;
+  }
   unsigned long long *res = (unsigned long long *)(s.scal_h + 16);
   UFM_CUDA(cudaMemcpyAsync(res, keys, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));

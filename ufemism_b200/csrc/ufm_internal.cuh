@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/ufemism_b200.h"
 
@@ -64,6 +65,44 @@ __host__ __device__ __forceinline__ double ufm_norm2_2(const double x, const dou
   return scale * sqrt(result);
 }
 
+// order-preserving integer image of a double (atomicMin on it = minimum of the doubles); critical time steps
+__host__ __device__ __forceinline__ unsigned long long ord_key(double x)
+{
+  unsigned long long b;
+#ifdef __CUDA_ARCH__
+  b = (unsigned long long)__double_as_longlong(x);
+#else
+  memcpy(&b, &x, sizeof(b));
+#endif
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double ord_unkey(unsigned long long k)
+{
+  unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  double x;
+#ifdef __CUDA_ARCH__
+  x = __longlong_as_double((long long)b);
+#else
+  memcpy(&x, &b, sizeof(x));
+#endif
+  return x;
+}
+#ifdef __CUDACC__
+// minimum over a 256-thread CTA, then one atomicMin on the key (every thread of the CTA must call this)
+__device__ __forceinline__ void block_min_to_key(double v, unsigned long long *key)
+{
+  __shared__ double sh_min[8];
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh_min[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < (blockDim.x >> 5) ? sh_min[threadIdx.x] : 1000.0;
+    for (int o = 4; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0 && v < 1000.0) atomicMin(key, ord_key(v));   // the keys start at 1000 (the reference's initial value, UFEMISM_main_model.f90:736-738)
+  }
+}
+#endif
+
 struct SlicedEll {
   int n_rows = 0;            // padded to a multiple of 32
   int n_slices = 0;
@@ -90,6 +129,7 @@ struct DevMesh {
   double *aa_Nx0 = nullptr, *aa_Ny0 = nullptr;  // home coefficients Nx(vi,nC+1)
   double *aa_A = nullptr;     // Voronoi area
   double *aa_sqrtApi = nullptr;  // SQRT(A/pi) (CFL)
+  double *aa_rmin = nullptr;     // MIN( SQRT(A/pi), shortest connection ): numerator of the vertex's SSA critical time step
   unsigned char *aa_edge = nullptr;  // edge_index
   // ---- Ac ----
   int4 *ac_Aci = nullptr;     // vi, vj, vl, vr (device Aa idx)
@@ -97,6 +137,7 @@ struct DevMesh {
   double *ac_Np = nullptr;
   double *ac_Cw = nullptr;    // Cw( Aci(aci,1), ci ) as used at ice_dynamics_module.f90:95
   double *ac_Dx = nullptr, *ac_Dy = nullptr;  // V(vj)-V(vi)
+  double *ac_dist2 = nullptr;    // dist**2 with dist = SQRT(Dx**2 + Dy**2), as at UFEMISM_main_model.f90:751-752
   // ---- AaAc ----
   SlicedEll m;
   int *m_idx = nullptr;                   // neighbour positions
@@ -213,6 +254,17 @@ struct ufm_handle {
   int sor_grid = 0, sor_block = 1024;
   size_t sor_smem = 0;
   int sor_chunk = 0, sor_fuse_bc = 0, sor_bar = 0;  // SOR scheduling switches (env UFM_SOR_CHUNK / _FUSE_BC / _BAR)
+  // critical time steps (determine_timesteps_and_actions, UFEMISM_main_model.f90:747-773): each of the three minima only changes when
+  // the field behind it does, so the kernels that write D_SIA_Ac / (U,V)_SSA / (U,V)_3D reduce it in their epilogue into
+  // ctrl[CTRL_CFL_KEYS + k]; cfl_ok[k] == false (a field was uploaded, remapped, ...) makes ufm_cfl recompute it from the fields
+  bool cfl_ok[3] = {false, false, false};
+  // device-driven region loop (ufm_api.cu run_model_device): while it enqueues steps these point at the control block's gates
+  // (run, SIA due, SMB due, thermodynamics timer due) and at the time step; NULL otherwise
+  const int *gate[4] = {nullptr, nullptr, nullptr, nullptr};
+  const double *dt_dev = nullptr;
+  void *stepctl_dev = nullptr, *stepctl_host = nullptr;   // StepCtl in device / pinned host memory
+  int pow_exact = 0;             // 1: device pow reproduces the host libm's bits (ufm_pow.cuh), 0: CUDA's pow (within 2 ulp)
+  int pow_reason = 0;            // why not, when pow_exact == 0 (return code of ufm_powtab_build)
   int sor_df = 0;                // 1: dataflow sweep kernel (env UFM_SOR_DATAFLOW, needs the mesh's df_layout)
   const void *carveout_done_for = nullptr;   // kernel variant whose L1 carve-out preference has been set on this handle's device
   int visc_minb = -1;            // resident CTAs per SM of the viscosity kernel (env UFM_VISC_MINB)
@@ -272,6 +324,8 @@ int ufm_k_remap_stash(ufm_handle *h, int slot, double *field_dev);
 int ufm_k_remap_apply(ufm_handle *h, int slot, const ufm_remap_cons *map, int order, double *field_dev);
 int ufm_k_thickness(ufm_handle *h, double dt);
 int ufm_k_cfl(ufm_handle *h, double out3[3]);
+int ufm_cfl_key_reset(ufm_handle *h, int which);
+int ufm_k_cfl3d_enqueue(ufm_handle *h);
 int ufm_k_ssa_prepare(ufm_handle *h);
 int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2]);
 int ufm_k_ssa_sliding_setup(ufm_handle *h);
@@ -285,3 +339,8 @@ int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out);
 int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double lambda);
 int ufm_k_permute(ufm_handle *h, int kind, int is_int, int to_device, void *dev_field, void *dev_staging, int n_ref);
 int ufm_sor_configure(ufm_handle *h);
+struct UfmPowTab;
+int ufm_ssa_powtab_init(const UfmPowTab *t);
+int ufm_geom_powtab_init(const UfmPowTab *t);
+int ufm_thermo_powtab_init(const UfmPowTab *t);
+extern "C" int ufm_powtab_build(UfmPowTab *out);

@@ -21,6 +21,7 @@
 #include <cstdio>
 
 #include "ufm_internal.cuh"
+#include "ufm_pow.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -171,7 +172,7 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
     const double A_GL = (mbits[v.x] & MB_SHEET) ? A_mean[v.x] : A_mean[v.y];
     factor_Tsai = 8.0 * 0.61 * A_GL * tsai_c1 * tsai_c2 / tsai_c3;
   }
-  double q = factor_Tsai * pow(Hi_GL, UFM_N_FLOW + 2.0) / tan(phi_fric_GL * (UFM_PI / 180.0));
+  double q = factor_Tsai * ufm_pow(Hi_GL, UFM_N_FLOW + 2.0) / ufm_tan(phi_fric_GL * (UFM_PI / 180.0));
   Qabs[a] = q;
   double Fx = -(dHi_dx[a] - ((dSL_dx[a] - dHb_dx[a]) * rr));
   double Fy = -(dHi_dy[a] - ((dSL_dy[a] - dHb_dy[a]) * rr));
@@ -213,7 +214,7 @@ __global__ void k_ssa_prepare(PrepArgs a)
   unsigned char fl = 0;
   if (a.A_mean) {
     const double A = s >= 0 ? a.A_mean[s] : a.A_mean_Ac[~s];
-    a.Afac[p] = pow(a.m_enh_ssa * 0.5 * A, -1.0 / UFM_N_FLOW);   // first factor of eta (ice_dynamics_module.f90:718)
+    a.Afac[p] = ufm_pow(a.m_enh_ssa * 0.5 * A, -1.0 / UFM_N_FLOW);   // first factor of eta (ice_dynamics_module.f90:718)
   }
   if (s >= 0) { Hi = a.Hi[s]; Hb = a.Hb[s]; SL = a.SL[s]; sx = a.sx[s]; sy = a.sy[s]; U = a.U[s]; V = a.V[s]; }
   else {
@@ -226,7 +227,7 @@ __global__ void k_ssa_prepare(PrepArgs a)
   double Hm = fmax(0.1, Hi);
   double pore_water_pressure = 0.96 * UFM_ICE_DENSITY * UFM_GRAV * Hm * lambda_p;
   double phi = fmax(p_min, fmin(p_max, (p_min + (p_max - p_min) * (1.0 + (Hb - pf2) / (pf2 - pf1)))));
-  double tau_c = tan((UFM_PI / 180.0) * phi) * (UFM_ICE_DENSITY * UFM_GRAV * Hm - pore_water_pressure);
+  double tau_c = ufm_tan((UFM_PI / 180.0) * phi) * (UFM_ICE_DENSITY * UFM_GRAV * Hm - pore_water_pressure);
   if (!d_is_floating(Hi, Hb, SL)) fl |= 1;
   a.UV[p] = make_double2(U, V);
   a.rhsnum[p] = make_double2(UFM_ICE_DENSITY * UFM_GRAV * sx, UFM_ICE_DENSITY * UFM_GRAV * sy);
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256, MINB) k_ssa_viscosity(ViscArgs a)
         if (STORE_GRAD) { a.dU[p] = make_double2(ux, uy); a.dV[p] = make_double2(vx, vy); }
         else {
           const double epsilon_sq_0 = 1E-12;
-          const double eta = (a.Afac ? a.Afac[p] : a.visc_A) * pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
+          const double eta = (a.Afac ? a.Afac[p] : a.visc_A) * ufm_pow(ux * ux + vy * vy + ux * vy + 0.25 * ((uy + vx) * (uy + vx)) + epsilon_sq_0, (1.0 - UFM_N_FLOW) / (2.0 * UFM_N_FLOW));
           const double Nn = eta * hm;
           const double dn = Nn - nold;
           s_dn = dn * dn; s_n = Nn * Nn;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256, MINB) k_ssa_viscosity(ViscArgs a)
           if (a.fuse_setup) {   // identical expressions to k_ssa_setup
             const double delta_v = 1E-3, q_plastic = 0.30;
             const double2 u = a.UV[p];
-            const double S = tauc * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
+            const double S = tauc * (ufm_pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
             a.RHS[p] = make_double2(rn.x / eta, rn.y / eta);
             double eu = cu0, ev = cv0;
             if (mf & 1) { const double t = S / (hm * eta); eu = eu - t; ev = ev - t; }
@@ -422,7 +423,7 @@ __global__ void k_ssa_setup(SetupArgs a)
   const double delta_v = 1E-3, q_plastic = 0.30;
   const double2 u = a.UV[p];
   const double eta = a.eta[p];
-  double S = a.tau_c[p] * (pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
+  double S = a.tau_c[p] * (ufm_pow(delta_v * delta_v + u.x * u.x + u.y * u.y, 0.5 * (q_plastic - 1.0))) / a.thr;
   const double2 r = a.rhsnum[p];
   a.RHS[p] = make_double2(r.x / eta, r.y / eta);
   double eu = a.cU0[p], ev = a.cV0[p];
@@ -449,6 +450,7 @@ __global__ void k_ssa_setup(SetupArgs a)
 #ifndef SOR_MIN_BLOCKS
 #define SOR_MIN_BLOCKS 1
 #endif
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 struct SorArgs {
   CommDev cm;
   const long long *off;
@@ -587,7 +589,6 @@ __device__ __forceinline__ void grid_barrier_rel(unsigned *bar, const int nblock
   __syncthreads();
 }
 
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 template <bool MULTI>
 __device__ __forceinline__ void colour_share(const SorArgs &a, const int *s_rng, const int c, const int wg, const int nw, int &first, int &end, int &step)
 {
@@ -699,7 +700,20 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
         // colours 1-4 and is final.  The wait is on work that was started first in this phase and never waits itself.
         const unsigned long long target = (unsigned long long)it * (unsigned long long)(a.adj_end - s_rng[12]);
         bool ready = false;
-        for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) {
+        // who takes the Neumann rows: with equal shares the warps that have no slice in this phase (they get here at once, so the pass
+        // is over long before the sweep is; taken by the first CTAs' threads after their own slices it was the tail of the iteration:
+        // 7 us between the last slice and the barrier, profiles/r02a_trace_bands64.json), otherwise everybody
+        int r0 = a.bc_begin + tid, rs = nt;
+        if (a.chunk) {
+          const int n5 = s_rng[14] - s_rng[12], k5 = (n5 + nw - 1) / nw, act5 = k5 > 0 ? (n5 + k5 - 1) / k5 : 0;
+          if ((nw - act5) * 32 >= a.bc_end + 4 - a.bc_begin) {
+            const int lo5 = (int)(((long long)act5 * blockIdx.x) / gridDim.x), hi5 = (int)(((long long)act5 * (blockIdx.x + 1)) / gridDim.x);
+            const int wib = (int)(threadIdx.x >> 5), nwb = (int)(blockDim.x >> 5);
+            r0 = wib >= hi5 - lo5 ? a.bc_begin + (nwb * (int)blockIdx.x - lo5 + (wib - (hi5 - lo5))) * 32 + lane : a.bc_end + 4;
+            rs = (nw - act5) * 32;
+          }
+        }
+        for (int r = r0; r < a.bc_end + 4; r += rs) {
           if (!ready) { while (*((volatile unsigned long long *)(a.ctrl + 12)) < target) { } __threadfence(); ready = true; }
           neumann_row<MULTI>(a, r);
         }
@@ -821,6 +835,9 @@ __device__ __noinline__ int df_wait_slow(const unsigned *stage_cnt, unsigned lon
     int spins = 0;
     while (ld_relaxed_u32(stage_cnt + nd * DF_CNT_STRIDE) < target) {
       ++spins;
+#ifdef DF_POLL_SLEEP_NS
+      __nanosleep(DF_POLL_SLEEP_NS);   // back off: thousands of warps polling one counter would queue in front of the updates of that counter
+#endif
       if ((spins & 1023) == 0 && *((volatile unsigned long long *)(ctrl + 13))) break;   // somebody else has given up: so do we
       if (spins > DF_SPIN_LIMIT) { *((volatile unsigned long long *)(ctrl + 13)) = 1ull; break; }
     }
@@ -841,7 +858,17 @@ __device__ __forceinline__ void df_wait(const SorArgs &a, DfState &d, volatile u
   if (nd <= d.known) return;
   // about to poll, possibly to block: whoever waits for this warp's last stage must not be kept waiting (deadlock otherwise)
   if (pend >= 0) { df_signal(sh_cnt, a.stage_cnt, pend, threadIdx.x & 31, blockDim.x >> 5); pend = -1; }
+#ifdef DF_STATS   // tuning build: how often the slow path runs, whether it had to block, how far the look-ahead got
+  const bool blocked = ld_relaxed_u32(a.stage_cnt + nd * DF_CNT_STRIDE) < (unsigned)d.it * gridDim.x;
+  const unsigned long long t0 = gtime();
+#endif
   d.known = df_wait_slow(a.stage_cnt, a.ctrl, (unsigned)d.it * gridDim.x, nd, a.n_stages);
+#ifdef DF_STATS
+  if (a.trace && (threadIdx.x & 31) == 0) {
+    unsigned long long *q = a.trace + blockIdx.x * 8;
+    atomicAdd(q + 0, 1ull); atomicAdd(q + 1, blocked ? 1ull : 0ull); atomicAdd(q + 2, gtime() - t0); atomicAdd(q + 3, (unsigned long long)(d.known - nd + 1));
+  }
+#endif
   if ((threadIdx.x & 31) == 0) atomicMax((unsigned *)s_known, ((unsigned)d.it << 16) | (unsigned)(d.known + 1));
 }
 // the calling warp has passed stage g.  Its stores of that stage precede the call in program order; every warp makes its own stores
@@ -881,6 +908,7 @@ struct NeedArgs {
   const long long *off; const unsigned char *deg; const int *idx;
   int n_bc; const int *bc_ptr, *bc_nbr, *corner, *corner_nbr, *corner_row;
   unsigned short *need, *need_bc;
+  unsigned long long *trace;
 };
 // one warp per slice (colours 2..5), then one thread per Neumann row
 __global__ void k_sor_need(NeedArgs a)
@@ -903,6 +931,9 @@ __global__ void k_sor_need(NeedArgs a)
       for (int o2 = 16; o2 > 0; o2 >>= 1) nd = max(nd, __shfl_xor_sync(0xffffffffu, nd, o2));
     }
     if (lane == 0) a.need[s] = nd < 0 ? (unsigned short)DF_NONE : (unsigned short)nd;
+#ifdef DF_STATS
+    if (lane == 0 && a.trace && nd >= 0) atomicAdd(a.trace + 4096 * 12 + min(63, a.st_base[c] + (s - a.rng15[3 * c]) / a.st_act[c] - nd), 1ull);   // histogram of the slack in stages
+#endif
   }
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_bc + 4; r += gridDim.x * blockDim.x) {
     int nd = -1;
@@ -1122,11 +1153,16 @@ __global__ void k_push_uv(CommDev cm, int n_slices, const unsigned char *sowner,
 // ---------------------------------------------------------------------------------------------
 // scatter AaAc -> Aa / Ac and rotate_xy_to_po (mesh_ArakawaC_module.f90:815-844)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_ssa_finish(int nV, int nAc, const int *aa2m, const int *ac2m, const double2 *UV, const double *Dx_, const double *Dy_,
-                             double *U, double *V, double *Ux, double *Uy, double *Up, double *Uo)
+__global__ void __launch_bounds__(256) k_ssa_finish(int nV, int nAc, const int *aa2m, const int *ac2m, const double2 *UV, const double *Dx_, const double *Dy_,
+                                                    double *U, double *V, double *Ux, double *Uy, double *Up, double *Uo, const double *rmin, unsigned long long *cfl_key)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nV) { const double2 q = UV[aa2m[i]]; U[i] = q.x; V[i] = q.y; }
+  double mS = 1000.0;
+  if (i < nV) {
+    const double2 q = UV[aa2m[i]];
+    U[i] = q.x; V[i] = q.y;
+    mS = rmin[i] / (fabs(q.x) + fabs(q.y));   // epilogue: this vertex's SSA critical time step (see k_cfl)
+  }
   if (i < nAc) {
     const double2 q = UV[ac2m[i]];
     const double Dx = Dx_[i], Dy = Dy_[i], D = sqrt(Dx * Dx + Dy * Dy);
@@ -1134,6 +1170,7 @@ __global__ void k_ssa_finish(int nV, int nAc, const int *aa2m, const int *ac2m, 
     Up[i] = q.x * Dx / D + q.y * Dy / D;
     Uo[i] = q.y * Dx / D - q.x * Dy / D;
   }
+  block_min_to_key(mS, cfl_key);
 }
 
 __global__ void k_zero_d(size_t n, double *p) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.0; }
@@ -1149,6 +1186,8 @@ __global__ void k_sum_mask_sheet(int nV, const unsigned *mbits, unsigned long lo
 // =============================================================================================
 // host launchers
 // =============================================================================================
+int ufm_ssa_powtab_init(const UfmPowTab *t) { return ufm_powtab_upload_tu(t); }
+
 static inline int grid_for(int n, int b) { return (n + b - 1) / b; }
 
 int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out)
@@ -1171,7 +1210,8 @@ int ufm_k_ssa_zero(ufm_handle *h)
   UFM_CUDA(cudaMemsetAsync(s.U_SSA, 0, sizeof(double) * (size_t)m.nVp, h->stream));
   UFM_CUDA(cudaMemsetAsync(s.V_SSA, 0, sizeof(double) * (size_t)m.nVp, h->stream));
   for (int k = 0; k < 4; k++) UFM_CUDA(cudaMemsetAsync(s.U_SSA_Ac[k], 0, sizeof(double) * (size_t)m.nAcp, h->stream));
-  return 0;
+  h->cfl_ok[1] = true;   // zero velocities: the SSA critical time step is the reference's initial 1000 yr
+  return ufm_cfl_key_reset(h, 2);
 }
 
 int ufm_k_ssa_prepare(ufm_handle *h)
@@ -1304,7 +1344,7 @@ int ufm_sor_configure(ufm_handle *h)
   { const char *e = getenv("UFM_SOR_FUSE_BC"); h->sor_fuse_bc = e ? atoi(e) : UFM_SOR_FUSE_BC_DEFAULT; }
   h->sor_block = SOR_BLOCK;
   h->sor_smem = 0;
-  { const char *e = getenv("UFM_SOR_DATAFLOW"); h->sor_df = (h->mesh.df_layout && h->mesh.P == 1 && (!e || atoi(e) != 0)) ? 1 : 0; }
+  { const char *e = getenv("UFM_SOR_DATAFLOW"); h->sor_df = (h->mesh.df_layout && h->mesh.P == 1 && e && atoi(e) != 0) ? 1 : 0; }
   // one CTA of 1024 threads per SM; UFM_SOR_GRID (tests only) shrinks the grid so that small meshes are swept in several rounds per colour
   int grid_target = h->num_sms;
   { const char *e = getenv("UFM_SOR_GRID"); if (e && atoi(e) > 0 && atoi(e) < grid_target) grid_target = atoi(e); }
@@ -1355,7 +1395,7 @@ int ufm_sor_configure(ufm_handle *h)
       }
       na.n_slices = m.m.n_slices; na.off = m.m.off; na.deg = m.m.deg; na.idx = m.m_idx;
       na.n_bc = m.n_bc; na.bc_ptr = m.bc_ptr; na.bc_nbr = m.bc_nbr; na.corner = m.corner_dev; na.corner_nbr = m.corner_nbr; na.corner_row = m.corner_row;
-      na.need = m.df_need; na.need_bc = m.df_need_bc;
+      na.need = m.df_need; na.need_bc = m.df_need_bc; na.trace = h->sor_trace;
       k_sor_need<<<h->num_sms * 8, 256, 0, h->stream>>>(na);
       UFM_CUDA(cudaGetLastError());
       h->cnt.kernel_launches++;
@@ -1471,8 +1511,11 @@ int ufm_k_ssa_finish(ufm_handle *h)
     k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm);
     h->cnt.kernel_launches += 2;
   }
+  int rc_ = ufm_cfl_key_reset(h, 2);
+  if (rc_) return rc_;
   k_ssa_finish<<<grid_for(n, 256), 256, 0, h->stream>>>(m.nV, m.nAc, m.aa2m, m.ac2m, s.UV, m.ac_Dx, m.ac_Dy, s.U_SSA, s.V_SSA,
-                                                        s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3]);
+                                                        s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3], m.aa_rmin, s.ctrl + CTRL_CFL_KEYS + 1);
+  h->cfl_ok[1] = true;
   h->cnt.kernel_launches++;
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_finish");
 }

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "ufm_internal.cuh"
+#include "ufm_pow.cuh"
 
 #ifndef UFM_HEAT_MINB_DEFAULT
 #define UFM_HEAT_MINB_DEFAULT 6
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128, MINB) k_thermo_heat(ThermoArgs a, ThermoC
     if (sheet) {
       const double delta_v = 1E-3, q_plastic = 0.30;
       const double u = a.U_SSA[v], vv = a.V_SSA[v];
-      const double beta_base = a.tau_c[a.aa2m[v]] * (pow(delta_v * delta_v + u * u + vv * vv, 0.5 * (q_plastic - 1.0))) / K.ten_q;
+      const double beta_base = a.tau_c[a.aa2m[v]] * (ufm_pow(delta_v * delta_v + u * u + vv * vv, 0.5 * (q_plastic - 1.0))) / K.ten_q;
       fh = beta_base * (u * u + vv * vv);
     }
     a.fric[v] = fh;
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(256) k_thermo_finish(int nV, ThermoArgs a, The
 }
 
 // =============================================================================================
+int ufm_thermo_powtab_init(const UfmPowTab *t) { return ufm_powtab_upload_tu(t); }
 static inline int grid_for(long long n, int b) { return (int)((n + b - 1) / b); }
 
 static bool thermo_skipped(const ufm_handle *h)

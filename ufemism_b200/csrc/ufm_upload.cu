@@ -456,6 +456,7 @@ int ufm_mesh_free_impl(ufm_handle *h)
   h->mesh = DevMesh();
   h->st = DevState();
   h->has_mesh = false;
+  h->cfl_ok[0] = h->cfl_ok[1] = h->cfl_ok[2] = false;   // cached critical time steps belong to the state that goes away
   return 0;
 }
 
@@ -564,14 +565,15 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
   // single-GPU layout: the colour-5 rows that the Neumann pass reads (non-edge rows adjacent to a domain-edge row) lead
   // their colour block, so that the pass can run inside the fifth colour phase as soon as those few slices are done
-  // ... unless the dataflow sweep (k_ssa_sor_df, the single-GPU default) will run: it orders the rows of every colour block
-  // by x-band / Morton alone, so that a row's lower-coloured neighbours sit at about the same relative position of their blocks
+  // ... unless the dataflow sweep (k_ssa_sor_df, opt-in: UFM_SOR_DATAFLOW=1; measured slower than the barrier kernel)
+  // will run: it orders the rows of every colour block by x-band / Morton alone, so that a row's lower-coloured neighbours sit at
+  // about the same relative position of their blocks
   std::vector<unsigned char> late(M, 1);
   int n_adj5 = 0;
   const char *env_order = getenv("UFM_ROW_ORDER");
   {
     const char *e = getenv("UFM_SOR_DATAFLOW");
-    m.df_layout = P == 1 && (!e || atoi(e) != 0) && !(env_order && !strncmp(env_order, "default", 7));
+    m.df_layout = P == 1 && e && atoi(e) != 0;
   }
   if (P == 1 && !m.df_layout)
     for (int ai = 0; ai < M; ai++) {
@@ -791,6 +793,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     m.has_tri = has_tri; m.nTri = has_tri ? d->nTri : 0;
     std::vector<int> iT(has_tri ? ne : 0, -1);
     std::vector<double2> xy(m.nVp, make_double2(0.0, 0.0));   // vertex coordinates: benchmark SMB closed forms, upwind search
+    std::vector<double> rmin(m.nVp, 1.0);
     std::vector<double> Rr(has_tri ? m.nVp : 0, 1.0);
 #pragma omp parallel for schedule(static)
     for (int s = 0; s < m.aa.n_slices; s++) {
@@ -823,12 +826,21 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
         xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
         A[p] = d->A[vi];
         sA[p] = std::sqrt(d->A[vi] / UFM_PI);
+        // numerator of the vertex's SSA critical time step: SQRT(A/pi) or its shortest connection (UFEMISM_main_model.f90:751-762)
+        double rm = sA[p];
+        for (int c = 1; c <= n; c++) {
+          const int vc = F2(d->C, vi + 1, c, ldV);
+          if (vc < 1 || vc > N) continue;
+          const double ddx = F2(d->V, vc, 1, ldV) - xy[p].x, ddy = F2(d->V, vc, 2, ldV) - xy[p].y;
+          rm = std::min(rm, std::sqrt(ddx * ddx + ddy * ddy));
+        }
+        rmin[p] = rm;
       }
     }
     if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
     lap("Aa ELL fill");
     UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci);
-    UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
+    UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(rmin, m.aa_rmin); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
     if (!derive_aa) { UP(nx, m.aa_Nx); UP(ny, m.aa_Ny); UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); }
     else {
       double **q4[] = {&m.aa_Nx, &m.aa_Ny};
@@ -874,7 +886,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   {
     std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
     const bool derive_ac = !d->Nx_Ac || !d->Ny_Ac || !d->No_Ac || !d->Np_Ac;   // derived on the device below
-    std::vector<double> c4[3][4], np(derive_ac ? 0 : m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0);
+    std::vector<double> c4[3][4], np(derive_ac ? 0 : m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0), dist2(m.nAcp, 1.0);
     for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(derive_ac ? 0 : m.nAcp, 0.0);
     int bad_ac = 0;
 #pragma omp parallel for schedule(static)
@@ -895,10 +907,12 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       cw[p] = F2(d->Cw, v[0], ci, ldV);
       dx[p] = F2(d->V, v[1], 1, ldV) - F2(d->V, v[0], 1, ldV);
       dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
+      const double dist = std::sqrt(dx[p] * dx[p] + dy[p] * dy[p]);
+      dist2[p] = dist * dist;   // dist**2 of UFEMISM_main_model.f90:752
     }
     if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
     lap("Ac fill");
-    UP(aci, m.ac_Aci); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy);
+    UP(aci, m.ac_Aci); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy); UP(dist2, m.ac_dist2);
     if (!derive_ac) {
       UP(np, m.ac_Np);
       for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }

@@ -322,6 +322,51 @@ def build_mesh(points, xmin, xmax, ymin, ymax, nC_mem=NC_MEM) -> Mesh:
                 colour=colour, colour_vi=colour_vi, colour_nV=colour_nV)
 
 
+class PrimaryMesh:
+    """Only the PRIMARY mesh data (V, Tri, nC, C, niTri, iTri, edge_index + the domain bounds): what the reference holds right after mesh
+    generation / a mesh update / reading a restart file, before it derives the secondary data (``src/mesh_creation_module.f90:1724-1737``).
+    ``IceModelGPU(mesh, primary_only=True)`` hands exactly this to ``ufm_mesh_upload_primary``, which derives the rest in the library.
+    ``nAc`` / ``nVAaAc`` are Euler's counts (nV + nTri - 1 edges), so that field shapes are known without the secondary data."""
+
+    def __init__(self, points, xmin, xmax, ymin, ymax, nC_mem=NC_MEM):
+        from scipy.spatial import Delaunay
+
+        lib = _load()
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        tri = Delaunay(pts).simplices.astype(np.int64)
+        a, b, c = pts[tri[:, 0]], pts[tri[:, 1]], pts[tri[:, 2]]
+        cross = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+        good = np.abs(cross) > 1e-12 * (xmax - xmin) * (ymax - ymin)
+        tri, cross = tri[good], cross[good]
+        flip = cross < 0
+        tri[flip] = tri[flip][:, [0, 2, 1]]
+        self.xmin, self.xmax, self.ymin, self.ymax = float(xmin), float(xmax), float(ymin), float(ymax)
+        self.nV, self.nTri, self.nC_mem = len(pts), len(tri), nC_mem
+        self.V = np.asfortranarray(pts)
+        self.Tri = np.asfortranarray((tri + 1).astype(np.int32))
+        x, y = pts[:, 0], pts[:, 1]
+        N, E, S, W = y == ymax, x == xmax, y == ymin, x == xmin
+        ei = np.zeros(self.nV, np.int32)
+        ei[N] = 1; ei[E] = 3; ei[S] = 5; ei[W] = 7; ei[N & E] = 2; ei[S & E] = 4; ei[S & W] = 6; ei[N & W] = 8
+        self.edge_index = ei
+        self.nC = np.zeros(self.nV, np.int32)
+        self.C = np.zeros((self.nV, nC_mem), np.int32, order="F")
+        self.niTri = np.zeros(self.nV, np.int32)
+        self.iTri = np.zeros((self.nV, nC_mem), np.int32, order="F")
+        rc = lib.ufm_mesh_connectivity(self.nV, self.nTri, _p(self.Tri), nC_mem, _p(self.nC), _p(self.C), _p(self.niTri), _p(self.iTri))
+        if rc:
+            raise RuntimeError(f"ufm_mesh_connectivity failed rc={rc}")
+        self.nAc = self.nV + self.nTri - 1          # Euler: V - E + F = 1 for a triangulated disc
+        self.nVAaAc = self.nV + self.nAc
+
+
+def primary_mesh_with_nv(half_width, nv_target, seed=20211103, order="random") -> PrimaryMesh:
+    area = (2.0 * half_width) ** 2
+    h = np.sqrt(2.0 * area / (np.sqrt(3.0) * nv_target))
+    pts = make_points(-half_width, half_width, -half_width, half_width, h, seed=seed, order=order)
+    return PrimaryMesh(pts, -half_width, half_width, -half_width, half_width)
+
+
 def make_mesh(xmin, xmax, ymin, ymax, h, seed=20211103, order="random", warp=None, nC_mem=NC_MEM) -> Mesh:
     pts = make_points(xmin, xmax, ymin, ymax, h, seed=seed, order=order, warp=warp)
     return build_mesh(pts, xmin, xmax, ymin, ymax, nC_mem=nC_mem)
