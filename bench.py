@@ -712,6 +712,12 @@ def run_ours(args):
         ms3 = float(tt.item())
         regions = {"value": world * (r3.time - t3) / (ms3 * 1e-3) * 3600.0, "unit": UNIT, "ms_per_step": ms3 / args.steps, "scaling": "weak",
                    "what": f"{world} independent regions of the same workload, one per GPU, no communication (aggregate model-years)"}
+        # the un-partitioned pass doubles as the in-run check of the partitioned one: same steps, same bits
+        if rank == 0:
+            same_bits = {f: bool(np.array_equal(g.download(f), gpu_fields[f])) for f in PARITY_FIELDS}
+            regions["partitioned_bit_identical"] = bool(all(same_bits.values()) and r3.time == gpu_time_final and r3.n_sor_total == r.n_sor_total and r3.n_outer_total == r.n_outer_total)
+            regions["partitioned_vs_single_gpu"] = {"fields_bit_identical": same_bits, "model_time_equal": bool(r3.time == gpu_time_final),
+                                                    "n_sor": [int(r.n_sor_total), int(r3.n_sor_total)], "n_outer": [int(r.n_outer_total), int(r3.n_outer_total)]}
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -744,6 +750,8 @@ def run_ours(args):
         if step_ms:
             out["ssa"].update(ssa_solve_time(step_ms, rows))
         if regions:
+            out["partitioned_bit_identical"] = regions.pop("partitioned_bit_identical", None)
+            out["partitioned_vs_single_gpu"] = regions.pop("partitioned_vs_single_gpu", None)
             out["independent_regions_mode"] = regions
         if sor_forced:
             pk, _ = hbm_peak()

@@ -357,6 +357,33 @@ def test_run_model_halfar(mesh_2k):
     assert np.abs(g.download("Hi") - o["Hi"]).max() <= 1e-8 * o["Hi"].max()
 
 
+@pytest.mark.parametrize("graph", ["1", "0"])
+@pytest.mark.parametrize("name", ["halfar", "eismint1"])
+def test_device_loop_matches_host_loop(mesh_2k, monkeypatch, name, graph):
+    """run_model_device (the step's kernels gated and timed by a control block on the device, 64 steps enqueued per synchronisation) against
+    the host-driven loop: same region state after every call (time, dt, timers, flags, counters), same fields bit for bit -- with max_steps
+    that end inside a batch, with an end time, and across repeated calls."""
+    st = S.state_halfar(mesh_2k) if name == "halfar" else S.state_eismint1(mesh_2k)
+    gs = []
+    for loop in ("0", "1"):
+        monkeypatch.setenv("UFM_DEVICE_LOOP", loop)
+        monkeypatch.setenv("UFM_DEVICE_GRAPH", graph)          # pairs of steps as one CUDA graph / plain launches
+        g = make_gpu(mesh_2k, st)
+        r = g.region(0.0)
+        snaps = []
+        for t_end, ms in ((1e12, 1), (1e12, 7), (1e12, 100), (12.5, 0), (30.0, 0), (30.0, 5)):
+            g.run_model(r, t_end, max_steps=ms)
+            snaps.append((r.time, r.dt, r.dt_prev, list(r.t0), list(r.t1), list(r.dtc), list(r.do_), r.n_steps, r.n_sia, r.n_ssa, list(r.dt_crit_last),
+                          g.download("Hi").copy(), g.download("Hi_prev").copy(), g.download("U_SIA").copy(), g.download("U_3D").copy(), g.determine_timesteps()))
+        gs.append(snaps)
+    assert gs[0][-1][7] > 100                                              # more than one batch of 64 steps
+    for a, b in zip(*gs):
+        assert a[:11] == b[:11]
+        for x, y in zip(a[11:15], b[11:15]):
+            assert_bits_equal(y, x)
+        assert a[15] == b[15]
+
+
 def test_run_model_mismip_hybrid(mesh_2k):
     """Hybrid SIA/SSA (config 4 physics) for a few model years: thickness and velocities track the oracle."""
     st = scenario(mesh_2k, "mismip")

@@ -203,6 +203,8 @@ int ufm_comm_connect(ufm_handle *h, const void *blobs)
     }
     h->comm.uv[q] = (double2 *)ptr[0]; h->comm.partials[q] = (double *)ptr[1]; h->comm.mail[q] = (unsigned long long *)ptr[2];
   }
+  h->comm.nbr = h->mesh.nbr_mask & ~(1u << me);
+  { const char *e = getenv("UFM_PEER_ALL"); if (e && atoi(e) != 0) h->comm.nbr = ((1u << P) - 1u) & ~(1u << me); }   // A/B: every phase signals every peer (round 1)
   h->comm_connected = true;
   return 0;
 }
@@ -675,22 +677,49 @@ static int run_model_device(ufm_handle *h, ufm_region *r, double t_end, long max
   const long steps0 = r->n_steps;
   bool done = false;
   rc = 0;
-  while (!done && !rc) {
-    const long nb = (max_steps > 0 && max_steps - enq < UFM_DEVICE_BATCH) ? max_steps - enq : UFM_DEVICE_BATCH;
-    for (long k = 0; k < nb && !rc; k++) {
-      if ((rc = ufm_k_thickness(h, 0.0))) break;
-      if ((rc = ufm_k_geom(h, 0.0))) break;
-      if ((rc = ufm_k_sia(h))) break;
-      if ((rc = ufm_k_smb_benchmark(h, 0.0, r->H0, r->R0, r->lambda))) break;
-      if (eismint) { if ((rc = ufm_k_sia3d(h))) break; if ((rc = ufm_k_cfl3d_enqueue(h))) break; }
-      k_step_control<<<1, 1, 0, h->stream>>>(cd, h->st.ctrl + CTRL_CFL_KEYS);
-      h->cnt.kernel_launches++;
-      enq++;
+  auto enqueue_step = [&]() -> int {
+    int rc_;
+    if ((rc_ = ufm_k_thickness(h, 0.0))) return rc_;
+    if ((rc_ = ufm_k_geom(h, 0.0))) return rc_;
+    if ((rc_ = ufm_k_sia(h))) return rc_;
+    if ((rc_ = ufm_k_smb_benchmark(h, 0.0, r->H0, r->R0, r->lambda))) return rc_;
+    if (eismint) { if ((rc_ = ufm_k_sia3d(h))) return rc_; if ((rc_ = ufm_k_cfl3d_enqueue(h))) return rc_; }
+    k_step_control<<<1, 1, 0, h->stream>>>(cd, h->st.ctrl + CTRL_CFL_KEYS);
+    h->cnt.kernel_launches++;
+    return ufm_cuda_check(cudaGetLastError(), "k_step_control");
+  };
+  // Two consecutive steps as ONE CUDA graph (two, because the thickness update swaps the Hi / Hi_prev buffers: after a pair the
+  // pointers are back where they were and the same graph can be launched again): a step of a 10 k-vertex mesh is a dozen kernels of a
+  // few microseconds each, so launching them one by one from the host costs more than running them.  UFM_DEVICE_GRAPH=0 or a stream
+  // that cannot be captured: plain launches.
+  cudaGraphExec_t exec = nullptr;
+  {
+    const char *e = getenv("UFM_DEVICE_GRAPH");
+    const long long before = h->cnt.kernel_launches;
+    if ((!e || atoi(e) != 0) && cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc1 = enqueue_step();
+      if (!rc1) rc1 = enqueue_step();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (rc1 || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+      if (graph) cudaGraphDestroy(graph);
     }
-    if (rc) break;
-    if ((rc = ufm_cuda_check(cudaMemcpyAsync(ch, cd, sizeof(StepCtl), cudaMemcpyDeviceToHost, h->stream), "device loop: read back"))) break;
-    if ((rc = ufm_cuda_check(cudaStreamSynchronize(h->stream), "device loop: synchronise"))) break;
-    done = !ch->g_run || (max_steps > 0 && enq >= max_steps);
+    cudaGetLastError();
+    const long long per_pair = h->cnt.kernel_launches - before;   // kernels in one graph launch
+    h->cnt.kernel_launches = before;
+    while (!done && !rc) {
+      const long nb = (max_steps > 0 && max_steps - enq < UFM_DEVICE_BATCH) ? max_steps - enq : UFM_DEVICE_BATCH;
+      if (exec) {
+        for (long k = 0; k < nb && !rc; k += 2) { rc = ufm_cuda_check(cudaGraphLaunch(exec, h->stream), "device loop: graph launch"); enq += 2; h->cnt.kernel_launches += per_pair; }
+      } else {
+        for (long k = 0; k < nb && !rc; k++) { rc = enqueue_step(); enq++; }
+      }
+      if (rc) break;
+      if ((rc = ufm_cuda_check(cudaMemcpyAsync(ch, cd, sizeof(StepCtl), cudaMemcpyDeviceToHost, h->stream), "device loop: read back"))) break;
+      if ((rc = ufm_cuda_check(cudaStreamSynchronize(h->stream), "device loop: synchronise"))) break;
+      done = !ch->g_run || (max_steps > 0 && enq >= max_steps);
+    }
+    if (exec) { cudaGraphExecDestroy(exec); enq = 0; }   // the host's Hi / Hi_prev pointers saw an even number of swaps (the captured pair)
   }
   h->gate[0] = h->gate[1] = h->gate[2] = h->gate[3] = nullptr;
   h->dt_dev = nullptr;

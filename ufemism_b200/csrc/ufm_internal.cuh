@@ -157,6 +157,7 @@ struct DevMesh {
   int *rng_all_dev = nullptr;        // [b*3 + {0,1,2}]: whole blocks (all owners)
   unsigned char *m_xmask = nullptr;  // per row: bit q set -> rank q reads this row, push new (U,V) to it
   unsigned char *m_sowner = nullptr; // per slice: owner rank
+  unsigned nbr_mask = 0;             // ranks this rank exchanges rows with (CommDev::nbr)
   int bc_rng[UFM_MAX_RANKS + 1] = {};  // Neumann rows grouped by owner
   int corner_owner[4] = {};
   int n_chunks = 0;
@@ -224,6 +225,7 @@ struct DevState {
 // peer-mapped buffers of the other ranks of a partitioned run (CUDA IPC), index = rank; [own rank] = own buffers
 struct CommDev {
   int P, rank;
+  unsigned nbr;   // bit q: rank q reads rows of this rank or owns rows this rank reads (for x-strips: the two neighbours)
   double2 *uv[UFM_MAX_RANKS];
   double *partials[UFM_MAX_RANKS];
   unsigned long long *mail[UFM_MAX_RANKS];

@@ -92,7 +92,7 @@ __global__ void k_peer_barrier(CommDev cm) { if (threadIdx.x == 0 && blockIdx.x 
 // signals `epoch` into the mailbox of every peer.  Nobody waits for the peers here: rows that read peer-owned rows are
 // swept last in a phase and wait_peers() is called just before them, so the NVLink latency hides behind interior work.
 template <bool MULTI, class F>
-__device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, const CommDev &cm, const unsigned long long epoch, F &&pre)
+__device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, const CommDev &cm, const unsigned long long epoch, const unsigned to, F &&pre)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -113,8 +113,10 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, c
         *gen = (unsigned)epoch;
         pre();
         __threadfence_system();
+        // `to`: the ranks that will wait for this epoch -- after a colour sweep only those that read rows of this rank (the strip's
+        // neighbours); after the fifth colour (max residual) and after the Neumann pass (end of the solve) everybody
         for (int q = 0; q < cm.P; q++)
-          if (q != cm.rank) *((volatile unsigned long long *)(cm.mail[q] + MAIL_FLAG + cm.rank)) = epoch;
+          if (q != cm.rank && ((to >> q) & 1u)) *((volatile unsigned long long *)(cm.mail[q] + MAIL_FLAG + cm.rank)) = epoch;
       } else {
         while (*gen != (unsigned)epoch) { }
       }
@@ -123,13 +125,13 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, const int nblocks, c
   }
   __syncthreads();
 }
-// wait (on local memory) until every peer has signalled `epoch`; called by one lane, followed by a fence that also drops
+// wait (on local memory) until every peer in `from` has signalled `epoch`; called by one lane, followed by a fence that also drops
 // stale L1 lines of rows the peers have pushed
-__device__ __forceinline__ void wait_peers(const CommDev &cm, const unsigned long long epoch)
+__device__ __forceinline__ void wait_peers(const CommDev &cm, const unsigned long long epoch, const unsigned from)
 {
   volatile unsigned long long *mine = cm.mail[cm.rank];
   for (int q = 0; q < cm.P; q++) {
-    if (q == cm.rank) continue;
+    if (q == cm.rank || !((from >> q) & 1u)) continue;
     long long spins = 0;
     while (mine[MAIL_FLAG + q] < epoch) {
       if (++spins > SPIN_LIMIT) { mine[MAIL_ABORT] = 1ull; break; }
@@ -647,7 +649,8 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
       if (tr) __syncthreads();
       for (int s = s_first; s < s_end; s += s_step) {
         if (MULTI && !waited && s >= s_bnd) {  // first boundary slice of this warp: the peers' previous phase must have landed
-          if (lane == 0) wait_peers(a.cm, epoch);
+          // the previous epoch was a colour sweep (signalled to the neighbours) or, at c == 0, the Neumann pass (signalled to all)
+          if (lane == 0) wait_peers(a.cm, epoch, a.cm.nbr);
           __syncwarp();
           waited = true;
         }
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
       // (and, after the fifth colour, this rank's max residual: the MPI_ALLREDUCE MAX of :673)
       ++epoch;
       if (!MULTI && a.bar_rel) grid_barrier_rel(bar, nblocks, phase);
-      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {
+      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, c == 4 ? 0xffffffffu : a.cm.nbr, [&]() {
         if (MULTI && c == 4) {
           const unsigned long long r = *((volatile unsigned long long *)(a.ctrl + (it % 3)));
           for (int q = 0; q < P; q++) *((volatile unsigned long long *)(a.cm.mail[q] + MAIL_RESID + (it % 3) * UFM_MAX_RANKS + rank)) = r;
@@ -745,13 +748,13 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
     // (recomputed here from non-edge rows only, so the whole pass is one hazard-free phase).
     if (MULTI || !fused) {
       if (MULTI) {  // the Neumann rows may read peer-owned rows of the fifth colour
-        if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+        if (threadIdx.x == 0) wait_peers(a.cm, epoch, 0xffffffffu);   // fifth-colour epoch: every rank's residual has arrived with it
         __syncthreads();
       }
       for (int r = a.bc_begin + tid; r < a.bc_end + 4; r += nt) neumann_row<MULTI>(a, r);
       ++epoch;
       if (!MULTI && a.bar_rel) grid_barrier_rel(bar, nblocks, phase);
-      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, [&]() {});
+      else grid_barrier<MULTI>(bar, nblocks, a.cm, epoch, 0xffffffffu, [&]() {});
     }
     if (MULTI) {
       // every rank's residual was published before it signalled the fifth-colour epoch, which wait_peers() above has seen
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
     }
   }
   if (MULTI) {  // leave only when every peer push of this solve has landed in our (U,V)
-    if (threadIdx.x == 0) wait_peers(a.cm, epoch);
+    if (threadIdx.x == 0) wait_peers(a.cm, epoch, 0xffffffffu);
     __syncthreads();
     if (tid == 0) mail[MAIL_EPOCH] = epoch;
   }

@@ -684,6 +684,14 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
           }
       }
     }
+    // the ranks this rank exchanges rows with: the readers of its rows and the owners of the rows it reads
+    m.nbr_mask = 0;
+    for (int ai = 0; ai < M && P > 1; ai++) {
+      const unsigned xm = xmask[m_r2d[ai]];
+      if (!xm) continue;
+      if (owner[ai] == m.rank) m.nbr_mask |= xm;
+      else if ((xm >> m.rank) & 1u) m.nbr_mask |= 1u << owner[ai];
+    }
     for (int sl = 0; sl < m.m.n_slices; sl++)
       for (int l = 0; l < UFM_SLICE; l++) { int ai = m_d2r[sl * UFM_SLICE + l]; if (ai >= 0) { sowner[sl] = owner[ai]; break; } }
     UP(xmask, m.m_xmask); UP(sowner, m.m_sowner);
