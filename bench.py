@@ -639,7 +639,8 @@ def run_ours(args):
     cnt = g.counters()
     yrs = r.time - t_model0
     gpu_time_final = r.time
-    gpu_fields = {f: g.download(f) for f in PARITY_FIELDS} if rank == 0 else None   # after the timed region: what the parity check compares
+    # after the timed region: what the parity check compares (partitioned run: a collective gather by owner)
+    gpu_fields = {f: (g.download_global(dist, f, device=dev) if part else g.download(f)) for f in PARITY_FIELDS} if (rank == 0 or part) else None
     if world > 1:
         tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

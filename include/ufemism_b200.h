@@ -213,6 +213,13 @@ int ufm_partition_owners(const ufm_mesh_desc *mesh, int nranks, unsigned char *o
  * independent of this order (rows of one colour are never neighbours). */
 int ufm_plan_row_order(int M, const unsigned char *block, const unsigned char *owner, const unsigned char *boundary, const unsigned char *late,
                        const unsigned char *degree, const unsigned *morton, const double *X, int n_bands, int deg_window, int *order_out);
+/* Owner rank of every combined-mesh vertex of the resident mesh, reference order: entries 1..nV the Aa vertices, nV+1..nV+nAc the
+ * staggered ones (x-strips holding equally many vertices, cf. partition_domain_x_balanced, src/mesh_help_functions_module.f90:1337-1404).
+ * Returns 1 when the per-step kernels are partitioned too: thickness update, geometry, SIA, yield stress, scatter and critical time
+ * steps then run for the rank's own elements only (halo values exchanged over NVLink), and ufm_state_download is valid for OWNED
+ * elements only -- what each MPI rank of the reference writes into the shared window; 0 when they are replicated (single GPU,
+ * experiments with column thermodynamics, UFM_PARTITION_STEP=0) and every rank holds every field completely. */
+int ufm_partition_owner_of(ufm_handle *h, unsigned char *owner_out /* nV + nAc */);
 int ufm_comm_export(ufm_handle *h, void *blob /* UFM_COMM_BLOB_BYTES */);
 int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_BYTES, in rank order */);
 

@@ -2,9 +2,11 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
 
-Every rank holds the whole mesh/state and sweeps its own x-strip; rows a neighbour strip reads are pushed by the sweep
-kernel over NVLink.  Colour sweeps are order-free, reductions use a rank-independent fixed tree -> results must be
-BIT-IDENTICAL to the single-GPU run, with identical iteration counts."""
+Storage is replicated, work is partitioned: every rank computes its own x-strip -- the SSA solve (rows a neighbour strip reads are pushed by
+the sweep kernel over NVLink) and the per-step kernels (thickness update, geometry, SIA, yield stress, critical time steps; thickness,
+out-flux factors and edge velocities of the strip boundary exchanged once per kernel).  Colour sweeps are order-free, reductions use a
+rank-independent fixed tree or are exact (min, integer sum) -> results must be BIT-IDENTICAL to the single-GPU run, with identical
+iteration counts and time steps."""
 import os
 import sys
 
@@ -35,9 +37,13 @@ def main():
             g.upload(k, st[k])
         r = g.region(0.0)
         g.run_model(r, 1e12, max_steps=3)
-        res = {f: g.download(f) for f in ("Hi", "U_SSA", "V_SSA", "Up_SSA_Ac", "U_SIA")}
+        dev = torch.device("cuda", local)
+        # partitioned per-step kernels: a rank's download is valid for the elements it owns; the global field is put together by owner
+        res = {f: g.download_global(dist, f, device=dev) for f in ("Hi", "U_SSA", "V_SSA", "Up_SSA_Ac", "U_SIA", "Hs", "dHs_dx", "mask", "mask_gl_Ac", "D_SIA", "dHi_dt")}
         counts = (r.n_steps, r.n_ssa, r.n_outer_total, r.n_sor_total, r.time)
-        # every rank must hold the same complete answer
+        if rank == 0:
+            print(f"gl={gl}: per-step kernels partitioned: {g.owners()[1]}", flush=True)
+        # every rank must arrive at the same complete answer
         for f, a in res.items():
             t = torch.from_numpy(a.copy()).cuda()
             ref = t.clone()

@@ -127,7 +127,7 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get",
-            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host",
+            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host", "ufm_partition_owner_of",
             "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
             "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
             "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
@@ -185,6 +185,7 @@ def load_library():
         L.ufm_field_resident.argtypes = [p, i]
         L.ufm_resident_dims.argtypes = [p, p]
         L.ufm_pow_mode.argtypes = [p]
+        L.ufm_partition_owner_of.argtypes = [p, p]
         L.ufm_pow_host.argtypes = [d, d]
         L.ufm_pow_host.restype = d
         L.ufm_tan_host.argtypes = [d]
@@ -541,6 +542,36 @@ class IceModelGPU:
         self._ck(self.L.ufm_counters_reset(self.h))
 
     # ---- restart / help_fields files (reference format; ufemism_b200/restart.py holds the host-only half) ----
+    def owners(self):
+        """(owner rank of every AaAc vertex in reference order, per-step kernels partitioned?) -- see ufm_partition_owner_of."""
+        out = np.zeros(self.mesh.nVAaAc, np.uint8)
+        rc = self._ck(self.L.ufm_partition_owner_of(self.h, out.ctypes.data_as(ctypes.c_void_p)), allow_warning=True)
+        return out, rc == 1
+
+    def download_global(self, dist, name, device=None):
+        """Collective: the complete field on every rank of a partitioned run.  With partitioned per-step kernels a rank's download is valid
+        for the elements it owns; the pieces are put together with an all-gather over ``torch.distributed`` (what the reference's shared
+        MPI window does for free)."""
+        import torch
+
+        a = self.download(name)
+        own, part = self.owners()
+        if self.nranks <= 1 or not part:
+            return a
+        _, kind, _ = _REF_NAMES[name.upper()]
+        m = self.mesh
+        own_k = {"Aa": own[: m.nV], "Ac": own[m.nV:], "AaAc": own, "3D": own[: m.nV], "12": own[: m.nV]}[kind]
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if device is not None:
+            t = t.to(device)
+        parts = [torch.empty_like(t) for _ in range(self.nranks)]
+        dist.all_gather(parts, t)
+        out = np.empty_like(a)
+        for q in range(self.nranks):
+            sel = own_k == q
+            out[sel] = parts[q].cpu().numpy()[sel]
+        return out
+
     def pow_mode(self) -> int:
         """bit 0: device pow has the bits of the host's libm (ufm_pow.cuh), bit 1: so has tan on the yield-stress range; 0: CUDA's pow / tan."""
         return int(self.L.ufm_pow_mode(self.h))

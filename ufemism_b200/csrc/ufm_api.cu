@@ -177,12 +177,14 @@ int ufm_comm_export(ufm_handle *h, void *blob)
 {
   if (!h || !h->has_mesh || !blob) return ufm_set_error(-2, "ufm_comm_export: no mesh resident");
   UFM_CUDA(cudaSetDevice(h->device));
-  static_assert(3 * sizeof(cudaIpcMemHandle_t) <= UFM_COMM_BLOB_BYTES, "blob too small");
+  static_assert(4 * sizeof(cudaIpcMemHandle_t) <= UFM_COMM_BLOB_BYTES, "blob too small");
   memset(blob, 0, UFM_COMM_BLOB_BYTES);
-  cudaIpcMemHandle_t hd[3];
+  cudaIpcMemHandle_t hd[4];
+  memset(hd, 0, sizeof(hd));
   UFM_CUDA(cudaIpcGetMemHandle(&hd[0], h->st.UV));
   UFM_CUDA(cudaIpcGetMemHandle(&hd[1], h->st.partials));
   UFM_CUDA(cudaIpcGetMemHandle(&hd[2], h->st.mail));
+  if (h->st.xbuf) UFM_CUDA(cudaIpcGetMemHandle(&hd[3], h->st.xbuf));
   memcpy(blob, hd, sizeof(hd));
   return 0;
 }
@@ -194,15 +196,18 @@ int ufm_comm_connect(ufm_handle *h, const void *blobs)
   const int P = h->mesh.P, me = h->mesh.rank;
   for (int q = 0; q < P; q++) {
     if (q == me) continue;
-    cudaIpcMemHandle_t hd[3];
+    cudaIpcMemHandle_t hd[4];
     memcpy(hd, (const char *)blobs + (size_t)q * UFM_COMM_BLOB_BYTES, sizeof(hd));
-    void *ptr[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3; k++) {
+    void *ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    const int nh = h->st.xbuf ? 4 : 3;
+    for (int k = 0; k < nh; k++) {
       UFM_CUDA(cudaIpcOpenMemHandle(&ptr[k], hd[k], cudaIpcMemLazyEnablePeerAccess));
-      h->ipc_opened[3 * q + k] = ptr[k];
+      h->ipc_opened[4 * q + k] = ptr[k];
     }
     h->comm.uv[q] = (double2 *)ptr[0]; h->comm.partials[q] = (double *)ptr[1]; h->comm.mail[q] = (unsigned long long *)ptr[2];
+    h->comm.xbuf[q] = (double *)ptr[3];
   }
+  h->comm.xbuf[me] = h->st.xbuf;
   h->comm.nbr = h->mesh.nbr_mask & ~(1u << me);
   { const char *e = getenv("UFM_PEER_ALL"); if (e && atoi(e) != 0) h->comm.nbr = ((1u << P) - 1u) & ~(1u << me); }   // A/B: every phase signals every peer (round 1)
   h->comm_connected = true;
@@ -211,7 +216,7 @@ int ufm_comm_connect(ufm_handle *h, const void *blobs)
 }  // extern "C"
 int ufm_comm_reset(ufm_handle *h)
 {
-  for (int k = 0; k < 3 * UFM_MAX_RANKS; k++) if (h->ipc_opened[k]) { cudaIpcCloseMemHandle(h->ipc_opened[k]); h->ipc_opened[k] = nullptr; }
+  for (int k = 0; k < 4 * UFM_MAX_RANKS; k++) if (h->ipc_opened[k]) { cudaIpcCloseMemHandle(h->ipc_opened[k]); h->ipc_opened[k] = nullptr; }
   h->comm_connected = false;
   return 0;
 }
@@ -410,6 +415,14 @@ int ufm_remap_apply(ufm_handle *h, int field, const ufm_remap_cons *map, int ord
 int ufm_state_upload(ufm_handle *h, int field, const void *host) { return field_copy(h, field, (void *)host, 1); }
 int ufm_state_download(ufm_handle *h, int field, void *host) { return field_copy(h, field, host, 0); }
 int ufm_pow_mode(ufm_handle *h) { return h ? h->pow_exact : ufm_set_error(-2, "NULL handle"); }
+int ufm_partition_owner_of(ufm_handle *h, unsigned char *owner_out)
+{
+  if (!h || !h->has_mesh || !owner_out) return ufm_set_error(-2, "ufm_partition_owner_of: no mesh resident");
+  const int M = h->mesh.M;
+  if (h->mesh.P <= 1 || !h->owner_ref) { memset(owner_out, 0, (size_t)M); return 0; }
+  memcpy(owner_out, h->owner_ref->data(), (size_t)M);
+  return h->mesh.part_step ? 1 : 0;
+}
 int ufm_resident_dims(ufm_handle *h, int dims[5])
 {
   if (!h || !dims) return ufm_set_error(-2, "NULL argument");

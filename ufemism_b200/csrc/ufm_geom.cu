@@ -47,11 +47,12 @@ __device__ __forceinline__ unsigned g_bits1(double Hi, double Hb, double SL)
 // ---- Aa stage 1: Hs, dHs_dt, primary mask bits ----
 __global__ void k_geom_aa1(int nV, const double *__restrict__ Hi, const double *__restrict__ Hb, const double *__restrict__ SL,
                            const double *__restrict__ dHb_dt, const double *__restrict__ dHi_dt, double *__restrict__ Hs,
-                           double *__restrict__ dHs_dt, unsigned *__restrict__ mbits, const int *gate)
+                           double *__restrict__ dHs_dt, unsigned *__restrict__ mbits, const int *gate, const unsigned char *__restrict__ act)
 {
   UFM_GATE(gate);
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nV) return;
+  if (act && !act[v]) return;   // partitioned: own vertices and the ones an owned Aa / Ac element reads
   const double hi = Hi[v], hb = Hb[v], sl = SL[v];
   Hs[v] = g_Hs(hi, hb, sl);
   dHs_dt[v] = dHb_dt[v] + dHi_dt[v];
@@ -70,6 +71,7 @@ struct GeomAa2Args {
   unsigned *mbits;
   double *dHi_dx, *dHi_dy, *dHs_dx, *dHs_dy, *sx, *sy;
   const int *gate;
+  const unsigned char *own; int rank;
 };
 __global__ void __launch_bounds__(256) k_geom_aa2(GeomAa2Args a)
 {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) k_geom_aa2(GeomAa2Args a)
     const int w = (int)((a.off[s + 1] - o) >> 5);
     const int v = s * 32 + lane;
     const int n = a.deg[v];
-    if (n == UFM_DEG_PAD) continue;
+    if (n == UFM_DEG_PAD || !UFM_OWNED(a.own, v, a.rank)) continue;
     const double hi = a.Hi[v], hs = a.Hs[v];
     const unsigned own = a.mbits[v];
     double ix = a.Nx0[v] * hi, iy = a.Ny0[v] * hi, sx = a.Nx0[v] * hs, sy = a.Ny0[v] * hs;
@@ -126,12 +128,13 @@ struct GeomAcArgs {
   double *sx, *sy;
   unsigned *mbits_Ac;
   const int *gate;
+  const unsigned char *own; int rank;
 };
 __global__ void __launch_bounds__(256) k_geom_ac(GeomAcArgs a)
 {
   UFM_GATE(a.gate);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nAc) return;
+  if (i >= a.nAc || !UFM_OWNED(a.own, i, a.rank)) return;
   const int4 v = a.Aci[i];
   const int vv[4] = {v.x, v.y, v.z, v.w};
   double hi[4], hb[4], sl[4], hs[4];
@@ -208,10 +211,10 @@ __global__ void __launch_bounds__(256) k_sia_ac_T(int nAc, int nVp, ZetaConst Z,
                                                   const unsigned *__restrict__ mbits_Ac, const double *__restrict__ Hi_Ac, const double *__restrict__ hx,
                                                   const double *__restrict__ hy, const double *__restrict__ hp, const double *__restrict__ ho,
                                                   double *__restrict__ D_SIA_Ac, double *__restrict__ Ux, double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo,
-                                                  const double *__restrict__ dist2, unsigned long long *cfl_key)
+                                                  const double *__restrict__ dist2, unsigned long long *cfl_key, const unsigned char *__restrict__ own, int rank)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = i < nAc;
+  const bool in = i < nAc && UFM_OWNED(own, i, rank);
   double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
   if (in && (mbits_Ac[i] & MB_SHEET)) {
     const double D_uv_3D_cutoff = -1E5;
@@ -250,11 +253,12 @@ __global__ void __launch_bounds__(256) k_sia_ac(int nAc, SiaConst K, const unsig
                                                 const double *__restrict__ hx, const double *__restrict__ hy, const double *__restrict__ hp,
                                                 const double *__restrict__ ho, double *__restrict__ D_SIA_Ac, double *__restrict__ Ux,
                                                 double *__restrict__ Uy, double *__restrict__ Up, double *__restrict__ Uo,
-                                                const double *__restrict__ dist2, unsigned long long *cfl_key, const int *gate)
+                                                const double *__restrict__ dist2, unsigned long long *cfl_key, const int *gate,
+                                                const unsigned char *__restrict__ own, int rank)
 {
   UFM_GATE(gate);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = i < nAc;
+  const bool in = i < nAc && UFM_OWNED(own, i, rank);
   double D = 0.0, ux = 0.0, uy = 0.0, up = 0.0, uo = 0.0;
   if (in && (mbits_Ac[i] & MB_SHEET)) {
     const double D_uv_3D_cutoff = -1E5;
@@ -355,6 +359,7 @@ struct SiaAaArgs {
   const double *Ux, *Uy, *D;
   double *U_SIA, *V_SIA, *D_SIA;
   const int *gate;
+  const unsigned char *own; int rank;
 };
 __global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
 {
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
     const int w = (int)((a.off[s + 1] - o) >> 5);
     const int v = s * 32 + lane;
     const int n = a.deg[v];
-    if (n == UFM_DEG_PAD) continue;
+    if (n == UFM_DEG_PAD || !UFM_OWNED(a.own, v, a.rank)) continue;
     const double dn = (double)n;
     double u = 0.0, vv = 0.0, dd = 0.0;
     for (int c = 0; c < w; c++) {
@@ -392,6 +397,7 @@ struct ThkArgs {
   double dt;
   const double *dt_dev;              // device-driven loop: the time step lives on the device (else NULL)
   const int *gate;
+  const unsigned char *own; int rank;
   double *factor, *smb;              // pass 1 out / pass 2 in
   double *Hi_new, *dHi_dt;           // pass 2 out
 };
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
     const int w = (int)((a.off[s + 1] - o) >> 5);
     const int v = s * 32 + lane;
     const int n = a.deg[v];
-    if (n == UFM_DEG_PAD) continue;
+    if (n == UFM_DEG_PAD || !UFM_OWNED(a.own, v, a.rank)) continue;
     const double hv = a.Hi[v], Av = a.A[v];
     if (PASS == 1) {
       double Vi_out = 0.0;
@@ -510,13 +516,13 @@ __global__ void __launch_bounds__(256) k_remap_apply(int nV_dst, int order, cons
 __global__ void __launch_bounds__(256) k_cfl(int which, int nV, int nVp, int nAc, int nZ, const double *__restrict__ dist2, const double *__restrict__ D_SIA_Ac,
                                              const double *__restrict__ U, const double *__restrict__ V, const double *__restrict__ rmin,
                                              const double *__restrict__ sqrtApi, const double *__restrict__ U3, const double *__restrict__ V3, unsigned long long *keys,
-                                             const int *gate)
+                                             const int *gate, const unsigned char *__restrict__ own_aa, const unsigned char *__restrict__ own_ac, int rank)
 {
   UFM_GATE(gate);
   double mD = 1000.0, mS = 1000.0, m3 = 1000.0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((which & 1) && i < nAc) mD = cfl_dt_D(dist2[i], D_SIA_Ac[i]);
-  if (i < nV) {
+  if ((which & 1) && i < nAc && UFM_OWNED(own_ac, i, rank)) mD = cfl_dt_D(dist2[i], D_SIA_Ac[i]);
+  if (i < nV && UFM_OWNED(own_aa, i, rank)) {
     // the reference takes dist / (|U| + |V|) at both ends of every connection and SQRT(A/pi) / (|U| + |V|) per vertex (:754-762); IEEE
     // division is monotone in its numerator, so per vertex that is the smallest numerator (rmin, fixed per mesh) over the same sum
     if (which & 2) mS = rmin[i] / (fabs(U[i]) + fabs(V[i]));
@@ -605,18 +611,18 @@ int ufm_k_geom(ufm_handle *h, double time)
     if (time < 25000.0) A_flow = 1.0E-16; else if (time < 50000.0) A_flow = 1.0E-17; else if (time < 75000.0) A_flow = 1.0E-16;
   }
   s.A_flow_const = A_flow;
-  k_geom_aa1<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, s.Hi, s.Hb, s.SL, s.dHb_dt, s.dHi_dt, s.Hs, s.dHs_dt, s.mbits, h->gate[0]);
+  k_geom_aa1<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, s.Hi, s.Hb, s.SL, s.dHb_dt, s.dHi_dt, s.Hs, s.dHs_dt, s.mbits, h->gate[0], m.part_step ? m.act_aa1 : nullptr);
   GeomAa2Args a2;
   a2.n_slices = m.aa.n_slices; a2.off = m.aa.off; a2.deg = m.aa.deg; a2.C = m.aa_C; a2.Nx = m.aa_Nx; a2.Ny = m.aa_Ny; a2.Nx0 = m.aa_Nx0; a2.Ny0 = m.aa_Ny0;
   a2.Hi = s.Hi; a2.Hs = s.Hs; a2.mbits = s.mbits; a2.dHi_dx = s.dHi_dx; a2.dHi_dy = s.dHi_dy; a2.dHs_dx = s.dHs_dx; a2.dHs_dy = s.dHs_dy;
-  a2.sx = s.dHs_dx_shelf; a2.sy = s.dHs_dy_shelf; a2.gate = h->gate[0];
+  a2.sx = s.dHs_dx_shelf; a2.sy = s.dHs_dy_shelf; a2.gate = h->gate[0]; a2.own = m.part_step ? m.own_aa : nullptr; a2.rank = m.rank;
   int g2 = grid_for((long long)m.aa.n_slices * 32, 256);
   k_geom_aa2<<<g2, 256, 0, h->stream>>>(a2);
   GeomAcArgs ac;
   ac.nAc = m.nAc; ac.Aci = m.ac_Aci; ac.Np = m.ac_Np;
   for (int k = 0; k < 4; k++) { ac.Nx[k] = m.ac_Nx[k]; ac.Ny[k] = m.ac_Ny[k]; ac.No[k] = m.ac_No[k]; ac.dHi[k] = s.dHi_Ac[k]; ac.dHb[k] = s.dHb_Ac[k]; ac.dHs[k] = s.dHs_Ac[k]; ac.dSL[k] = s.dSL_Ac[k]; }
   ac.Hi = s.Hi; ac.Hb = s.Hb; ac.SL = s.SL; ac.Hs = s.Hs; ac.mbits = s.mbits;
-  ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac; ac.gate = h->gate[0];
+  ac.Hi_Ac = s.Hi_Ac; ac.Hb_Ac = s.Hb_Ac; ac.SL_Ac = s.SL_Ac; ac.Hs_Ac = s.Hs_Ac; ac.sx = s.dHs_dx_shelf_Ac; ac.sy = s.dHs_dy_shelf_Ac; ac.mbits_Ac = s.mbits_Ac; ac.gate = h->gate[0]; ac.own = m.part_step ? m.own_ac : nullptr; ac.rank = m.rank;
   k_geom_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(ac);
   h->cnt.kernel_launches += 3;
   if (s.realistic_A) {
@@ -653,15 +659,20 @@ int ufm_k_sia(ufm_handle *h)
     for (int k = 0; k < Z.nZ; k++) Z.z3[k] = h->zeta3[k];
     k_sia_ac_T<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.nVp, Z, h->P.m_enh_sia, m.ac_Aci, s.Ti, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1],
                                                             s.dHs_Ac[2], s.dHs_Ac[3], s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3],
-                                                            m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0);
+                                                            m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0, m.part_step ? m.own_ac : nullptr, m.rank);
   } else
   k_sia_ac<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, K, s.mbits_Ac, s.Hi_Ac, s.dHs_Ac[0], s.dHs_Ac[1], s.dHs_Ac[2], s.dHs_Ac[3],
                                                        s.D_SIA_Ac, s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.U_SIA_Ac[2], s.U_SIA_Ac[3],
-                                                       m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0, h->gate[1]);
+                                                       m.ac_dist2, s.ctrl + CTRL_CFL_KEYS + 0, h->gate[1], m.part_step ? m.own_ac : nullptr, m.rank);
   h->cfl_ok[0] = true;
   SiaAaArgs a;
   a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.iAci = m.aa_iAci; a.Ux = s.U_SIA_Ac[0]; a.Uy = s.U_SIA_Ac[1]; a.D = s.D_SIA_Ac;
-  a.U_SIA = s.U_SIA; a.V_SIA = s.V_SIA; a.D_SIA = s.D_SIA; a.gate = h->gate[1];
+  a.U_SIA = s.U_SIA; a.V_SIA = s.V_SIA; a.D_SIA = s.D_SIA; a.gate = h->gate[1]; a.own = m.part_step ? m.own_aa : nullptr; a.rank = m.rank;
+  if (m.part_step) {   // the diagnostic map to the vertices and the next thickness update read staggered vertices of the neighbour strips
+    double *arr[4] = {s.U_SIA_Ac[2], s.U_SIA_Ac[0], s.U_SIA_Ac[1], s.D_SIA_Ac};
+    int rc_x = ufm_halo_exchange(h, 1, 4, arr);
+    if (rc_x) return rc_x;
+  }
   k_sia_aa<<<grid_for((long long)m.aa.n_slices * 32, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches += 2;
   return ufm_cuda_check(cudaGetLastError(), "k_sia");
@@ -696,11 +707,12 @@ int ufm_k_sia3d(ufm_handle *h)
 //      the constants of Halfar / MISMIP_mod, mesh_generation_test.  Everything that does not depend on the vertex is
 //      evaluated on the host with the host libm, as the reference does once per call. ----
 struct SmbArgs { int mode; double E, S_b, M_max, H0f1, f2, R0, lam_tp_spy, value; };
-__global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const double2 *__restrict__ xy, double *__restrict__ SMB_year, const int *gate)
+__global__ void __launch_bounds__(256) k_smb_benchmark(int nV, SmbArgs a, const double2 *__restrict__ xy, double *__restrict__ SMB_year, const int *gate,
+                                                       const unsigned char *__restrict__ own, int rank)
 {
   UFM_GATE(gate);
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nV) return;
+  if (v >= nV || !UFM_OWNED(own, v, rank)) return;
   const double2 p = xy[v];
   double out;
   if (a.mode == 0) out = a.value;
@@ -745,7 +757,7 @@ int ufm_k_smb_benchmark(ufm_handle *h, double time, double H0, double R0, double
     f2 = pow(tp / t0, -beta);
     a.mode = 2; a.H0f1 = H0 * f1; a.f2 = f2; a.R0 = R0; a.lam_tp_spy = lambda / tp;
   } else return ufm_set_error(-4, "no closed-form SMB for benchmark %d: SMB_year comes from the host", b);
-  k_smb_benchmark<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, a, m.aa_xy, s.SMB_year, h->gate[2]);
+  k_smb_benchmark<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(m.nV, a, m.aa_xy, s.SMB_year, h->gate[2], m.part_step ? m.own_aa : nullptr, m.rank);
   h->cnt.kernel_launches++;
   return ufm_cuda_check(cudaGetLastError(), "k_smb_benchmark");
 }
@@ -811,13 +823,23 @@ int ufm_k_thickness(ufm_handle *h, double dt)
   a.n_slices = m.aa.n_slices; a.off = m.aa.off; a.deg = m.aa.deg; a.edge = m.aa_edge; a.C = m.aa_C; a.iAci = m.aa_iAci; a.A = m.aa_A; a.Cw = m.ac_Cw;
   a.UpSIA = s.U_SIA_Ac[2]; a.UpSSA = s.U_SSA_Ac[2]; a.Hi = s.Hi; a.SMB = s.SMB_year; a.BMB = s.BMB; a.noice = s.mask_noice; a.dt = dt;
   a.factor = s.thk_factor; a.smb = s.thk_smb; a.Hi_new = s.Hi_alt; a.dHi_dt = s.dHi_dt;
-  a.dt_dev = h->dt_dev; a.gate = h->gate[0];
+  a.dt_dev = h->dt_dev; a.gate = h->gate[0]; a.own = m.part_step ? m.own_aa : nullptr; a.rank = m.rank;
   int g = grid_for((long long)m.aa.n_slices * 32, 256);
   k_thk<1><<<g, 256, 0, h->stream>>>(a);
+  if (m.part_step) {   // the out-flux factors of the neighbour strips' vertices scale the fluxes that come in from them
+    double *arr[1] = {s.thk_factor};
+    int rc_x = ufm_halo_exchange(h, 0, 1, arr);
+    if (rc_x) return rc_x;
+  }
   k_thk<2><<<g, 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches += 2;
   // Hi_prev = Hi ; Hi = new  (pointer swap: the old buffer IS Hi_prev)
   double *t = s.Hi; s.Hi = s.Hi_alt; s.Hi_alt = t;
+  if (m.part_step) {   // the new thickness of the vertices the neighbour strips read (geometry, next thickness update)
+    double *arr[1] = {s.Hi};
+    int rc_x = ufm_halo_exchange(h, 0, 1, arr);
+    if (rc_x) return rc_x;
+  }
   return ufm_cuda_check(cudaGetLastError(), "k_thk");
 }
 
@@ -833,7 +855,7 @@ int ufm_k_cfl3d_enqueue(ufm_handle *h)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   k_cfl<<<grid_for(m.nV, 256), 256, 0, h->stream>>>(4, m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_dist2, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
-                                                    m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, s.ctrl + CTRL_CFL_KEYS, h->gate[3]);
+                                                    m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, s.ctrl + CTRL_CFL_KEYS, h->gate[3], nullptr, nullptr, 0);
   h->cnt.kernel_launches++;
   return ufm_cuda_check(cudaGetLastError(), "k_cfl (3-D)");
 }
@@ -850,11 +872,21 @@ int ufm_k_cfl(ufm_handle *h, double out3[3])
     if (rc) return rc;
     const int n = (which & 1) ? (m.nAc > m.nV ? m.nAc : m.nV) : m.nV;   // thread i: staggered vertex i (bit 0) and vertex i (bits 1, 2)
     k_cfl<<<grid_for(n, 256), 256, 0, h->stream>>>(which, m.nV, m.nVp, m.nAc, h->P.nZ, m.ac_dist2, s.D_SIA_Ac, s.U_SSA, s.V_SSA,
-                                                   m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, keys, nullptr);
+                                                   m.aa_rmin, m.aa_sqrtApi, s.U_3D, s.V_3D, keys, nullptr, m.part_step ? m.own_aa : nullptr,
+                                                   m.part_step ? m.own_ac : nullptr, m.rank);
     h->cnt.kernel_launches++;
     h->cfl_ok[0] = h->cfl_ok[1] = h->cfl_ok[2] = true;
   }
   unsigned long long *res = (unsigned long long *)(s.scal_h + 16);
+  if (m.part_step) {
+    // every rank holds the minima over ITS elements (they stay cached as such): minimum over the ranks on a copy
+    // (the MPI_ALLREDUCE MIN of UFEMISM_main_model.f90:764-766)
+    unsigned long long *tmp = s.ctrl + CTRL_CFL_TMP;
+    UFM_CUDA(cudaMemcpyAsync(tmp, keys, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    int rc = ufm_peer_allreduce(h, tmp, 3, 0);
+    if (rc) return rc;
+    keys = tmp;
+  }
   UFM_CUDA(cudaMemcpyAsync(res, keys, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
   const double dt_correction_factor = 0.9;

@@ -16,6 +16,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#ifdef __cplusplus
+#include <vector>
+#endif
 
 #include "../../include/ufemism_b200.h"
 
@@ -27,7 +30,8 @@
 #define MAIL_RESID 8        // [3][8] max-residual bits of rank q for SOR iteration it%3
 #define MAIL_EPOCH 40       // own epoch counter
 #define MAIL_ABORT 41       // set when a peer wait timed out
-#define MAIL_WORDS 64
+#define MAIL_RED 64         // [2][8][4] small all-reduce slots: parity, rank, value (critical time steps, mask_sheet count)
+#define MAIL_WORDS 128
 // dataflow SOR sweep (k_ssa_sor_df): stage counters
 #define DF_NONE 0xFFFFu
 #define DF_CNT_STRIDE 8      // one 32 B sector per counter
@@ -103,6 +107,9 @@ __device__ __forceinline__ void block_min_to_key(double v, unsigned long long *k
 }
 #endif
 
+// partitioned per-step kernels: does the calling rank own element idx?  own == NULL: single GPU / replicated kernels, everything is "owned"
+#define UFM_OWNED(own, idx, rank) (!(own) || (own)[idx] == (unsigned char)(rank))
+
 struct SlicedEll {
   int n_rows = 0;            // padded to a multiple of 32
   int n_slices = 0;
@@ -158,6 +165,16 @@ struct DevMesh {
   unsigned char *m_xmask = nullptr;  // per row: bit q set -> rank q reads this row, push new (U,V) to it
   unsigned char *m_sowner = nullptr; // per slice: owner rank
   unsigned nbr_mask = 0;             // ranks this rank exchanges rows with (CommDev::nbr)
+  // ---- per-step kernels partitioned by owner: storage stays replicated, every Aa / Ac element is computed by the rank whose
+  //      x-strip holds it; what a neighbour strip reads (thickness, out-flux factors, edge velocities) is exchanged once per kernel ----
+  bool part_step = false;
+  unsigned char *own_aa = nullptr, *own_ac = nullptr;   // owner rank per Aa / Ac device index (255: padding)
+  unsigned char *act_aa1 = nullptr;                     // 1: k_geom_aa1 runs here on this rank (owned, or read by an owned Aa / Ac element)
+  // halo lists, CSR over the peers: this rank SENDS x?_s_idx[x?_s_ptr[q] .. x?_s_ptr[q+1]) to rank q and RECEIVES x?_r_idx[...] from it
+  // (device indices; a receive list is the peer's send list in the same order).  xa: Aa vertices, xc: Ac vertices
+  int *xa_s_idx = nullptr, *xa_r_idx = nullptr, *xc_s_idx = nullptr, *xc_r_idx = nullptr;
+  int xa_s_ptr[UFM_MAX_RANKS + 1] = {}, xa_r_ptr[UFM_MAX_RANKS + 1] = {}, xc_s_ptr[UFM_MAX_RANKS + 1] = {}, xc_r_ptr[UFM_MAX_RANKS + 1] = {};
+  int x_region = 0;                  // doubles per (parity, sender) region of the exchange buffer
   int bc_rng[UFM_MAX_RANKS + 1] = {};  // Neumann rows grouped by owner
   int corner_owner[4] = {};
   int n_chunks = 0;
@@ -218,6 +235,7 @@ struct DevState {
   double *red_scratch = nullptr;   // [2*64] block sums of the RN reduction tree
   unsigned long long *ctrl = nullptr;  // SOR control block
   unsigned long long *mail = nullptr;  // mailbox for peer GPUs
+  double *xbuf = nullptr;              // halo exchange buffer the peers write into: [2 parities][P senders][x_region]
   double *scal = nullptr;          // small result scratch (device), mirrored in pinned host memory
   double *scal_h = nullptr;
 };
@@ -229,12 +247,14 @@ struct CommDev {
   double2 *uv[UFM_MAX_RANKS];
   double *partials[UFM_MAX_RANKS];
   unsigned long long *mail[UFM_MAX_RANKS];
+  double *xbuf[UFM_MAX_RANKS];
 };
 
 // words of DevState::ctrl (unsigned long long[128]) -- one table so that no two users overlap:
 //   [0..2] SOR max-residual slots   [8..10] SOR results   [12] SOR fused-Neumann counter   [16] mask_sheet sum
 //   [24..26] CFL minima keys   [28..29] thermodynamics status   [30] RN-reduction ticket   [32..95] SOR grid barrier   [96..103] SCTL_*
 #define CTRL_CFL_KEYS 24
+#define CTRL_CFL_TMP 104          // [104..106] all-reduced copy of the CFL keys (partitioned per-step kernels)
 #define CTRL_THERMO_STATUS 28
 #define CTRL_RN_TICKET 30
 #define UFM_XFER_SLOTS 20
@@ -274,7 +294,9 @@ struct ufm_handle {
   int part_rank = 0, part_n = 1;   // set by ufm_partition_set before the mesh upload
   bool comm_connected = false;
   CommDev comm;
-  void *ipc_opened[3 * UFM_MAX_RANKS] = {};
+  void *ipc_opened[4 * UFM_MAX_RANKS] = {};
+  int xparity = 0;                 // parity of the next halo exchange / small all-reduce (double-buffered regions)
+  std::vector<unsigned char> *owner_ref = nullptr;   // owner rank of every AaAc vertex in REFERENCE order (partitioned runs; ufm_partition_owner_of)
   // remap stash: a field of the OLD mesh and its Aa gradients, reference order, survives ufm_mesh_upload
   struct Stash { int field = -1; int n = 0; double *d = nullptr, *ddx = nullptr, *ddy = nullptr; } stash[4];
   // host buffers page-locked with ufm_host_register (base, bytes): field copies from/to them are DMA'd directly
@@ -299,7 +321,7 @@ struct ufm_handle {
   void *secondary = nullptr;     // ufm_secondary: host arrays derived by ufm_mesh_upload_primary (ufm_mesh_primary.cpp)
   // the three buffers peers map through CUDA IPC keep allocations of their own (outside the arena); like the arena they survive
   // ufm_mesh_free and are reused by the next upload when large enough (cudaFree / cudaMalloc cost 0.2 s of a re-upload)
-  struct OwnBuf { void *p = nullptr; size_t bytes = 0; } own_buf[3];
+  struct OwnBuf { void *p = nullptr; size_t bytes = 0; } own_buf[4];
   double *scal_h_keep = nullptr;
   void *staging = nullptr;       // pinned host staging for upload/download permutation
   size_t staging_bytes = 0;
@@ -333,6 +355,9 @@ int ufm_k_ssa_viscosity(ufm_handle *h, double sums2[2]);
 int ufm_k_ssa_sliding_setup(ufm_handle *h);
 int ufm_k_ssa_gradients(ufm_handle *h);
 int ufm_comm_reset(ufm_handle *h);
+int ufm_halo_exchange(ufm_handle *h, int kind, int narr, double *const *arrays);   // kind 0: Aa lists, 1: Ac lists; collective
+int ufm_peer_allreduce(ufm_handle *h, unsigned long long *vals_dev, int n, int op);  // op 0: min (ordered keys), 1: sum; collective
+int ufm_push_uv_halo(ufm_handle *h);
 int ufm_k_ssa_sor(ufm_handle *h, int max_inner, int force_iters, ufm_ssa_stats *stats);
 int ufm_k_ssa_finish(ufm_handle *h);
 int ufm_k_ssa_outer_loop(ufm_handle *h, ufm_ssa_stats *stats);

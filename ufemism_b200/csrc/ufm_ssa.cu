@@ -155,10 +155,11 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
                           const double *__restrict__ dSL_dy, const double *__restrict__ dHb_dx, const double *__restrict__ dHb_dy,
                           const double *__restrict__ Dx_, const double *__restrict__ Dy_, double factor_Tsai_noA,
                           double *Qabs, double *Qp, double *Ux, double *Uy, const int *__restrict__ ac2m, double2 *UV,
-                          const double *__restrict__ A_mean, double tsai_c1, double tsai_c2, double tsai_c3)
+                          const double *__restrict__ A_mean, double tsai_c1, double tsai_c2, double tsai_c3,
+                          const unsigned char *__restrict__ own, int rank)
 {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= nAc) return;
+  if (a >= nAc || !UFM_OWNED(own, a, rank)) return;
   Qabs[a] = 0.0; Qp[a] = 0.0;
   if (!(mbits_Ac[a] & MB_GL)) return;
   int4 v = Aci[a];
@@ -167,7 +168,10 @@ __global__ void k_gl_flux(int nAc, const int4 *__restrict__ Aci, const unsigned 
   double TAFj = Hi[v.y] - ((SL[v.y] - Hb[v.y]) * rr);
   double lambda_GL = TAFi / (TAFi - TAFj);
   double Hi_GL = (Hi[v.x] * (1.0 - lambda_GL)) + (Hi[v.y] * lambda_GL);
-  double phi_fric_GL = (mbits[v.x] & MB_SHEET) ? phi_m[aa2m[v.x]] : phi_m[aa2m[v.y]];
+  // ice%phi_fric_AaAc of the sheet-side vertex.  In a partitioned run that vertex may belong to the neighbour strip, whose yield-stress
+  // pass this rank does not see: the angle is a function of the bed alone (basal_yield_stress :806-808), re-evaluated here with the same expression
+  const int vg = (mbits[v.x] & MB_SHEET) ? v.x : v.y;
+  double phi_fric_GL = own ? fmax(5.0, fmin(20.0, (5.0 + (20.0 - 5.0) * (1.0 + (Hb[vg] - 0.0) / (0.0 - (-1000.0)))))) : phi_m[aa2m[vg]];
   // factor_Tsai = 8 Q0 A (rho g)^n (1-rho_i/rho_w)^(n-1) / 4^n ; the A-independent part is evaluated on the host
   double factor_Tsai = A_flow * factor_Tsai_noA;
   if (A_mean) {  // temperature-dependent flow factor of the grounded side (:894-900); factor evaluated left to right as at :906-909
@@ -205,11 +209,13 @@ struct PrepArgs {
   double2 *UV, *rhsnum;
   double *tau_c, *phi, *Hm;
   unsigned char *mflag;
+  const unsigned char *sowner; int rank;   // partitioned per-step kernels: rows of this rank's slices only (else NULL)
 };
 __global__ void k_ssa_prepare(PrepArgs a)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Mp) return;
+  if (a.sowner && a.sowner[p >> 5] != a.rank) return;
   int s = a.src[p];
   if (s == INT_MIN) return;
   double Hi, Hb, SL, sx, sy, U, V;
@@ -1138,6 +1144,75 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor_df(SorArg
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo exchange of the partitioned per-step kernels.  Storage is replicated, so an element has the same index on every
+// GPU; what a rank computes for its own elements and a neighbour strip reads travels as: pack into the READER's exchange buffer
+// (NVLink P2P stores; one region per parity and sender) -> peer barrier -> unpack from the own buffer into the own arrays.
+// Two parities: a rank may pack exchange k+1 while a slower neighbour still unpacks exchange k.
+// ---------------------------------------------------------------------------------------------
+struct XArgs {
+  CommDev cm;
+  int parity, region, narr;
+  const int *idx;
+  int ptr[UFM_MAX_RANKS + 1];
+  double *arr[4];
+};
+__global__ void __launch_bounds__(256) k_xpack(XArgs a)
+{
+  const int P = a.cm.P, me = a.cm.rank;
+  for (int q = 0; q < P; q++) {
+    const int b = a.ptr[q], n = a.ptr[q + 1] - b;
+    if (q == me || n == 0) continue;
+    double *dst = a.cm.xbuf[q] + ((size_t)a.parity * P + me) * a.region;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * a.narr; i += gridDim.x * blockDim.x) {
+      const int k = i / n, j = i - k * n;
+      dst[(size_t)k * n + j] = a.arr[k][a.idx[b + j]];
+    }
+  }
+  __threadfence_system();
+}
+__global__ void __launch_bounds__(256) k_xunpack(XArgs a)
+{
+  const int P = a.cm.P, me = a.cm.rank;
+  for (int q = 0; q < P; q++) {
+    const int b = a.ptr[q], n = a.ptr[q + 1] - b;
+    if (q == me || n == 0) continue;
+    const double *src = a.cm.xbuf[me] + ((size_t)a.parity * P + q) * a.region;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * a.narr; i += gridDim.x * blockDim.x) {
+      const int k = i / n, j = i - k * n;
+      a.arr[k][a.idx[b + j]] = __ldcv(src + (size_t)k * n + j);   // written by a peer: never from a stale cache line
+    }
+  }
+}
+// all-reduce of up to 4 words over the ranks: op 0 = minimum (order-preserving keys of doubles), 1 = sum.  One thread.
+__global__ void k_peer_allreduce(CommDev cm, int parity, unsigned long long *vals, int n, int op)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int q = 0; q < cm.P; q++)
+    for (int k = 0; k < n; k++) *((volatile unsigned long long *)(cm.mail[q] + MAIL_RED + (parity * UFM_MAX_RANKS + cm.rank) * 4 + k)) = vals[k];
+  peer_sync(cm);
+  volatile unsigned long long *mine = cm.mail[cm.rank];
+  for (int k = 0; k < n; k++) {
+    unsigned long long r = mine[MAIL_RED + (parity * UFM_MAX_RANKS) * 4 + k];
+    for (int q = 1; q < cm.P; q++) {
+      const unsigned long long v = mine[MAIL_RED + (parity * UFM_MAX_RANKS + q) * 4 + k];
+      r = op == 0 ? (v < r ? v : r) : r + v;
+    }
+    vals[k] = r;
+  }
+}
+// rows of this rank that a peer reads (xmask): their (U,V) as set up by the gather / the grounding-line flux, before the first viscosity pass
+__global__ void __launch_bounds__(256) k_push_uv_halo(CommDev cm, int Mp, const unsigned char *xmask, const unsigned char *sowner, const double2 *UV)
+{
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Mp; p += gridDim.x * blockDim.x) {
+    const unsigned xm = xmask[p];
+    if (!xm || sowner[p >> 5] != cm.rank) continue;
+    const double2 v = UV[p];
+    for (int q = 0; q < cm.P; q++) if ((xm >> q) & 1u) cm.uv[q][p] = v;
+  }
+  __threadfence_system();
+}
+
 // all-gather of the final (U,V): every rank pushes its own rows to all peers (partitioned runs only)
 __global__ void k_push_uv(CommDev cm, int n_slices, const unsigned char *sowner, const unsigned char *deg, const double2 *UV)
 {
@@ -1157,16 +1232,17 @@ __global__ void k_push_uv(CommDev cm, int n_slices, const unsigned char *sowner,
 // scatter AaAc -> Aa / Ac and rotate_xy_to_po (mesh_ArakawaC_module.f90:815-844)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ssa_finish(int nV, int nAc, const int *aa2m, const int *ac2m, const double2 *UV, const double *Dx_, const double *Dy_,
-                                                    double *U, double *V, double *Ux, double *Uy, double *Up, double *Uo, const double *rmin, unsigned long long *cfl_key)
+                                                    double *U, double *V, double *Ux, double *Uy, double *Up, double *Uo, const double *rmin, unsigned long long *cfl_key,
+                                                    const unsigned char *__restrict__ own_aa, const unsigned char *__restrict__ own_ac, int rank)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double mS = 1000.0;
-  if (i < nV) {
+  if (i < nV && UFM_OWNED(own_aa, i, rank)) {
     const double2 q = UV[aa2m[i]];
     U[i] = q.x; V[i] = q.y;
     mS = rmin[i] / (fabs(q.x) + fabs(q.y));   // epilogue: this vertex's SSA critical time step (see k_cfl)
   }
-  if (i < nAc) {
+  if (i < nAc && UFM_OWNED(own_ac, i, rank)) {
     const double2 q = UV[ac2m[i]];
     const double Dx = Dx_[i], Dy = Dy_[i], D = sqrt(Dx * Dx + Dy * Dy);
     Ux[i] = q.x; Uy[i] = q.y;
@@ -1178,10 +1254,10 @@ __global__ void __launch_bounds__(256) k_ssa_finish(int nV, int nAc, const int *
 
 __global__ void k_zero_d(size_t n, double *p) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.0; }
 
-__global__ void k_sum_mask_sheet(int nV, const unsigned *mbits, unsigned long long *out)
+__global__ void k_sum_mask_sheet(int nV, const unsigned *mbits, unsigned long long *out, const unsigned char *__restrict__ own, int rank)
 {
   unsigned long long c = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) c += (mbits[i] & MB_SHEET) ? 1 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nV; i += gridDim.x * blockDim.x) c += (UFM_OWNED(own, i, rank) && (mbits[i] & MB_SHEET)) ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -1191,14 +1267,58 @@ __global__ void k_sum_mask_sheet(int nV, const unsigned *mbits, unsigned long lo
 // =============================================================================================
 int ufm_ssa_powtab_init(const UfmPowTab *t) { return ufm_powtab_upload_tu(t); }
 
+int ufm_halo_exchange(ufm_handle *h, int kind, int narr, double *const *arrays)
+{
+  DevMesh &m = h->mesh;
+  if (!m.part_step) return 0;
+  if (!h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
+  if (narr < 1 || narr > 4) return ufm_set_error(-2, "ufm_halo_exchange: 1..4 arrays");
+  XArgs a;
+  a.cm = h->comm; a.parity = h->xparity; a.region = m.x_region; a.narr = narr;
+  for (int k = 0; k < 4; k++) a.arr[k] = k < narr ? arrays[k] : nullptr;
+  a.idx = kind == 0 ? m.xa_s_idx : m.xc_s_idx;
+  memcpy(a.ptr, kind == 0 ? m.xa_s_ptr : m.xc_s_ptr, sizeof(a.ptr));
+  k_xpack<<<h->num_sms, 256, 0, h->stream>>>(a);
+  k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm);
+  a.idx = kind == 0 ? m.xa_r_idx : m.xc_r_idx;
+  memcpy(a.ptr, kind == 0 ? m.xa_r_ptr : m.xc_r_ptr, sizeof(a.ptr));
+  k_xunpack<<<h->num_sms, 256, 0, h->stream>>>(a);
+  h->cnt.kernel_launches += 3;
+  h->xparity ^= 1;
+  return ufm_cuda_check(cudaGetLastError(), "halo exchange");
+}
+
+int ufm_peer_allreduce(ufm_handle *h, unsigned long long *vals_dev, int n, int op)
+{
+  if (h->mesh.P <= 1) return 0;
+  if (!h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
+  if (n < 1 || n > 4) return ufm_set_error(-2, "ufm_peer_allreduce: 1..4 words");
+  k_peer_allreduce<<<1, 32, 0, h->stream>>>(h->comm, h->xparity, vals_dev, n, op);
+  h->cnt.kernel_launches++;
+  h->xparity ^= 1;
+  return ufm_cuda_check(cudaGetLastError(), "k_peer_allreduce");
+}
+
+int ufm_push_uv_halo(ufm_handle *h)
+{
+  DevMesh &m = h->mesh;
+  if (m.P <= 1) return 0;
+  if (!h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
+  k_push_uv_halo<<<h->num_sms * 2, 256, 0, h->stream>>>(h->comm, m.Mp, m.m_xmask, m.m_sowner, h->st.UV);
+  k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm);
+  h->cnt.kernel_launches += 2;
+  return ufm_cuda_check(cudaGetLastError(), "k_push_uv_halo");
+}
+
 static inline int grid_for(int n, int b) { return (n + b - 1) / b; }
 
 int ufm_k_sum_mask_sheet(ufm_handle *h, long long *out)
 {
   DevState &s = h->st;
   UFM_CUDA(cudaMemsetAsync(s.ctrl + 16, 0, sizeof(unsigned long long), h->stream));
-  k_sum_mask_sheet<<<h->num_sms * 2, 256, 0, h->stream>>>(h->mesh.nV, s.mbits, s.ctrl + 16);
+  k_sum_mask_sheet<<<h->num_sms * 2, 256, 0, h->stream>>>(h->mesh.nV, s.mbits, s.ctrl + 16, h->mesh.part_step ? h->mesh.own_aa : nullptr, h->mesh.rank);
   h->cnt.kernel_launches++;
+  if (h->mesh.part_step) { int rc_x = ufm_peer_allreduce(h, s.ctrl + 16, 1, 1); if (rc_x) return rc_x; }   // SUM( ice%mask_sheet) over the ranks
   unsigned long long v = 0;
   UFM_CUDA(cudaMemcpyAsync(&v, s.ctrl + 16, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   UFM_CUDA(cudaStreamSynchronize(h->stream));
@@ -1227,6 +1347,7 @@ int ufm_k_ssa_prepare(ufm_handle *h)
   a.Ux_Ac = s.U_SSA_Ac[0]; a.Uy_Ac = s.U_SSA_Ac[1]; a.mbits_Ac = s.mbits_Ac; a.gl_fix = h->P.use_analytical_GL_flux;
   a.A_mean = s.realistic_A ? s.A_mean : nullptr; a.A_mean_Ac = s.A_mean_Ac; a.m_enh_ssa = h->P.m_enh_ssa; a.Afac = s.Afac;
   a.UV = s.UV; a.rhsnum = s.rhsnum; a.tau_c = s.tau_c; a.phi = s.phi; a.Hm = s.Hm; a.mflag = s.mflag;
+  a.sowner = m.part_step ? m.m_sowner : nullptr; a.rank = m.rank;
   k_ssa_prepare<<<grid_for(m.Mp, 256), 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches++;
   if (h->P.use_analytical_GL_flux) {
@@ -1238,8 +1359,13 @@ int ufm_k_ssa_prepare(ufm_handle *h)
                                                            s.dHi_Ac[0], s.dHi_Ac[1], s.dSL_Ac[0], s.dSL_Ac[1], s.dHb_Ac[0], s.dHb_Ac[1],
                                                            m.ac_Dx, m.ac_Dy, f, s.Qabs_GL_Ac, s.Qp_GL_Ac, s.U_SSA_Ac[0], s.U_SSA_Ac[1],
                                                            m.ac2m, s.UV, s.realistic_A ? s.A_mean : nullptr, pow(UFM_ICE_DENSITY * UFM_GRAV, UFM_N_FLOW),
-                                                           pow(1.0 - (UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY), UFM_N_FLOW - 1.0), pow(4.0, UFM_N_FLOW));
+                                                           pow(1.0 - (UFM_ICE_DENSITY / UFM_SEAWATER_DENSITY), UFM_N_FLOW - 1.0), pow(4.0, UFM_N_FLOW),
+                                                           m.part_step ? m.own_ac : nullptr, m.rank);
     h->cnt.kernel_launches++;
+  }
+  if (m.part_step) {   // the start values of the rows the neighbour strips read (viscosity, first sweep)
+    int rc_x = ufm_push_uv_halo(h);
+    if (rc_x) return rc_x;
   }
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_prepare");
 }
@@ -1508,7 +1634,7 @@ int ufm_k_ssa_finish(ufm_handle *h)
 {
   DevMesh &m = h->mesh; DevState &s = h->st;
   int n = m.nV > m.nAc ? m.nV : m.nAc;
-  if (m.P > 1) {
+  if (m.P > 1 && !m.part_step) {   // replicated per-step kernels: every rank scatters every row, so it needs every row
     if (!h->comm_connected) return ufm_set_error(-6, "partitioned mesh but ufm_comm_connect has not been called");
     k_push_uv<<<h->num_sms * 4, 256, 0, h->stream>>>(h->comm, m.m.n_slices, m.m_sowner, m.m.deg, s.UV);
     k_peer_barrier<<<1, 32, 0, h->stream>>>(h->comm);
@@ -1517,8 +1643,14 @@ int ufm_k_ssa_finish(ufm_handle *h)
   int rc_ = ufm_cfl_key_reset(h, 2);
   if (rc_) return rc_;
   k_ssa_finish<<<grid_for(n, 256), 256, 0, h->stream>>>(m.nV, m.nAc, m.aa2m, m.ac2m, s.UV, m.ac_Dx, m.ac_Dy, s.U_SSA, s.V_SSA,
-                                                        s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3], m.aa_rmin, s.ctrl + CTRL_CFL_KEYS + 1);
+                                                        s.U_SSA_Ac[0], s.U_SSA_Ac[1], s.U_SSA_Ac[2], s.U_SSA_Ac[3], m.aa_rmin, s.ctrl + CTRL_CFL_KEYS + 1,
+                                                        m.part_step ? m.own_aa : nullptr, m.part_step ? m.own_ac : nullptr, m.rank);
   h->cfl_ok[1] = true;
   h->cnt.kernel_launches++;
+  if (m.part_step) {   // the next thickness update of the neighbour strips reads the parallel velocity on the staggered vertices it shares with us
+    double *arr[1] = {s.U_SSA_Ac[2]};
+    int rc_x = ufm_halo_exchange(h, 1, 1, arr);
+    if (rc_x) return rc_x;
+  }
   return ufm_cuda_check(cudaGetLastError(), "k_ssa_finish");
 }

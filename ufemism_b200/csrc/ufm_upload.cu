@@ -948,6 +948,84 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
 
   lap("Ac + permutation upload");
+  // ---- per-step kernels partitioned by owner: owner of every Aa / Ac element, where stage 1 of the geometry has to run
+  //      redundantly (the vertices an owned element reads), and the halo lists.  Every rank derives every list from the same owner
+  //      array, so a receive list is the peer's send list by construction. ----
+  {
+    const int b_ = h->P.benchmark;
+    const char *e = getenv("UFM_PARTITION_STEP");
+    // experiments with a column model on the device (update_ice_temperature / solve_SIA_3D on the thermodynamics timer) keep the
+    // replicated per-step kernels: their 3-D fields are not exchanged
+    m.part_step = P > 1 && !(e && atoi(e) == 0) && b_ != UFM_BM_NONE && !(b_ >= UFM_BM_EISMINT_1 && b_ <= UFM_BM_EISMINT_6) && !m.has_tri;
+    if (h->owner_ref) { delete h->owner_ref; h->owner_ref = nullptr; }
+    if (P > 1) h->owner_ref = new std::vector<unsigned char>(owner);
+  }
+  if (m.part_step) {
+    const int me = m.rank;
+    std::vector<unsigned char> own_aa(m.nVp, 255), own_ac(m.nAcp, 255), act1(m.nVp, 0);
+    for (int v = 0; v < N; v++) own_aa[aa_r2d[v]] = owner[v];
+    for (int a = 0; a < E; a++) own_ac[ac_r2d[a]] = owner[N + a];
+    // reads[q] marks (reference index) the Aa vertices / Ac vertices that rank q reads: neighbours of its vertices, the four vertices of
+    // its staggered vertices; the staggered vertices around its vertices
+    std::vector<std::vector<int>> sa(P), ra(P), sc(P), rc(P);
+    std::vector<unsigned char> rd_aa((size_t)N * P, 0), rd_ac((size_t)E * P, 0);
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < N; v++) {
+      const int q = owner[v];
+      for (int c = 1; c <= d->nC[v]; c++) {
+        const int u = F2(d->C, v + 1, c, ldV) - 1, a = F2(d->iAci, v + 1, c, ldV) - 1;
+        if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1;      // benign race: every writer stores 1
+        if (a >= 0 && a < E) rd_ac[(size_t)a * P + q] = 1;
+      }
+    }
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < E; a++) {
+      const int q = owner[N + a];
+      for (int k = 1; k <= 4; k++) { const int u = F2(d->Aci, a + 1, k, ldAc) - 1; if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1; }
+    }
+    // lists in device-index order (deterministic on every rank)
+    for (int p_ = 0; p_ < m.nVp; p_++) {
+      const int v = aa_d2r[p_];
+      if (v < 0) continue;
+      const int o = owner[v];
+      if (o == me || rd_aa[(size_t)v * P + me]) act1[p_] = 1;
+      for (int q = 0; q < P; q++) {
+        if (q == o || !rd_aa[(size_t)v * P + q]) continue;
+        if (o == me) sa[q].push_back(p_);
+        if (q == me) ra[o].push_back(p_);
+      }
+    }
+    for (int p_ = 0; p_ < m.nAcp; p_++) {
+      const int a = ac_d2r[p_];
+      if (a < 0) continue;
+      const int o = owner[N + a];
+      for (int q = 0; q < P; q++) {
+        if (q == o || !rd_ac[(size_t)a * P + q]) continue;
+        if (o == me) sc[q].push_back(p_);
+        if (q == me) rc[o].push_back(p_);
+      }
+    }
+    auto flat = [&](const std::vector<std::vector<int>> &L, int *ptr, std::vector<int> &out) {
+      out.clear(); ptr[0] = 0;
+      for (int q = 0; q < P; q++) { out.insert(out.end(), L[q].begin(), L[q].end()); ptr[q + 1] = (int)out.size(); }
+      if (out.empty()) out.push_back(0);
+    };
+    std::vector<int> f1, f2, f3, f4;
+    flat(sa, m.xa_s_ptr, f1); flat(ra, m.xa_r_ptr, f2); flat(sc, m.xc_s_ptr, f3); flat(rc, m.xc_r_ptr, f4);
+    UP(own_aa, m.own_aa); UP(own_ac, m.own_ac); UP(act1, m.act_aa1);
+    UP(f1, m.xa_s_idx); UP(f2, m.xa_r_idx); UP(f3, m.xc_s_idx); UP(f4, m.xc_r_idx);
+    // one region of the exchange buffer holds the largest message of any ordered pair of ranks: up to 4 arrays per Ac entry
+    // (solve_SIA: Up, Ux, Uy, D), 1 per Aa entry -- sized from the global maxima so that every rank uses the same stride
+    size_t worst = 1;
+    {
+      std::vector<size_t> cnt_a((size_t)P * P, 0), cnt_c((size_t)P * P, 0);
+      for (int v = 0; v < N; v++) for (int q = 0; q < P; q++) if (q != owner[v] && rd_aa[(size_t)v * P + q]) cnt_a[(size_t)owner[v] * P + q]++;
+      for (int a = 0; a < E; a++) for (int q = 0; q < P; q++) if (q != owner[N + a] && rd_ac[(size_t)a * P + q]) cnt_c[(size_t)owner[N + a] * P + q]++;
+      for (size_t k = 0; k < cnt_a.size(); k++) worst = std::max(worst, std::max(cnt_a[k], 4 * cnt_c[k]));
+    }
+    m.x_region = (int)((worst + 31) & ~(size_t)31);
+  }
+  lap("partition: owners + halo lists");
   // ---- state, zero-filled ----
   DevState &s = h->st;
   const size_t nv = m.nVp, na = m.nAcp, nm = m.Mp, nz = (size_t)h->P.nZ;
@@ -970,6 +1048,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   ZE_OWN(nm, s.UV, 0); ZE(nm, s.RHS); ZE(nm, s.E); ZE(nm, s.rhsnum); ZE(nm, s.dU); ZE(nm, s.dV);
   ZE(nm, s.eta); ZE(nm, s.N); ZE(nm, s.S); ZE(nm, s.tau_c); ZE(nm, s.phi); ZE(nm, s.Hm); ZE(nm, s.mflag);
   ZE_OWN(2 * (size_t)m.m.n_slices + 2, s.partials, 1); ZE(128, s.ctrl); ZE(64, s.scal); ZE(128, s.red_scratch); ZE_OWN(MAIL_WORDS, s.mail, 2);
+  if (m.part_step) ZE_OWN(2 * (size_t)P * (size_t)m.x_region, s.xbuf, 3);
   lap("state: AaAc arrays, IPC bufs");
   if (!h->scal_h_keep) UFM_CUDA(cudaMallocHost((void **)&h->scal_h_keep, 64 * sizeof(double)));
   s.scal_h = h->scal_h_keep;
@@ -989,8 +1068,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // single-GPU view of the peer tables: this rank only
   memset(&h->comm, 0, sizeof(h->comm));
   h->comm.P = m.P; h->comm.rank = m.rank;
-  h->comm.uv[m.rank] = s.UV; h->comm.partials[m.rank] = s.partials; h->comm.mail[m.rank] = s.mail;
+  h->comm.uv[m.rank] = s.UV; h->comm.partials[m.rank] = s.partials; h->comm.mail[m.rank] = s.mail; h->comm.xbuf[m.rank] = s.xbuf;
   h->comm_connected = false;
+  h->xparity = 0;
   h->cnt.sor_bytes_per_iteration = m.sor_bytes;
   const int rc_cfg = ufm_sor_configure(h);
   lap("SOR configure");
