@@ -220,6 +220,9 @@ int ufm_plan_row_order(int M, const unsigned char *block, const unsigned char *o
  * elements only -- what each MPI rank of the reference writes into the shared window; 0 when they are replicated (single GPU,
  * experiments with column thermodynamics, UFM_PARTITION_STEP=0) and every rank holds every field completely. */
 int ufm_partition_owner_of(ufm_handle *h, unsigned char *owner_out /* nV + nAc */);
+/* host-only planning: the number of Aa / Ac values rank s sends to rank q in one halo exchange of the partitioned per-step kernels
+ * (cnt[s * nranks + q]) -- what replaces the reference's MPI shared-memory window for the strip boundaries */
+int ufm_partition_halo_counts(const ufm_mesh_desc *mesh, int nranks, int *cnt_aa /* nranks^2 */, int *cnt_ac /* nranks^2 */);
 int ufm_comm_export(ufm_handle *h, void *blob /* UFM_COMM_BLOB_BYTES */);
 int ufm_comm_connect(ufm_handle *h, const void *blobs /* nranks * UFM_COMM_BLOB_BYTES, in rank order */);
 

@@ -25,13 +25,42 @@ def test_cpu_cost_model_adds_what_a_step_runs():
     assert bench.cpu_step_seconds(T, 1, 1, 2, 3) == 15.0 + 16.0 + 2 * 96.0 + 3 * 128.0
 
 
-def test_recorded_step_counts_match_the_bench_workload():
-    """profiles/config3_step_counts.json (written by the GPU arm) is what --impl reference scales its unit costs by."""
-    steps, how = bench.load_counts(1000785, 11)
-    assert steps is not None and len(steps) == 11 and "config3_step_counts" in how
-    assert all(set(s) >= {"dt", "sia", "ssa", "n_outer", "n_sor"} for s in steps)
-    assert steps[0]["sia"] == 1 and steps[0]["ssa"] == 1 and steps[0]["dt"] > 0.0    # first step: both solvers due at once (UFEMISM_main_model.f90:352-390)
-    assert bench.load_counts(250000, 11) == (None, None)                              # another mesh: counts do not apply
+def test_cpu_trajectory_and_parity_report():
+    """The CPU arm runs the oracle's region loop for real; the parity report compares a (here: second CPU) trajectory with it field by
+    field and step by step, and fails on a perturbed field, a different iteration count or a different time step."""
+    import copy
+
+    import numpy as np
+
+    m, st = bench.build_workload(4000)
+    tr = bench.cpu_trajectory(m, st, 2, 2, 3)
+    assert len(tr["rows"]) == 5 == len(tr["step_s"]) and tr["time"] > tr["time_after_warmup"] > 0.0
+    assert tr["rows"][0]["sia"] == 1 and tr["rows"][0]["ssa"] == 1 and tr["rows"][0]["n_sor"] > 0     # first step: both solvers due at once
+    line = bench.cpu_line(tr, 2, 2, m, "test")
+    assert line["kind"] == "port" and line["cores"] == 2 and line["value"] > 0 and abs(line["model_years"] - (tr["time"] - tr["time_after_warmup"])) < 1e-12
+    same = bench.parity_report(tr["fields"], tr["rows"], tr["time"], tr)
+    assert same["passed"] and all(same["bit_identical"].values()) and same["rel_l2_U"] == 0.0 and same["steps_compared"] == 5
+    bad = {k: v.copy() for k, v in tr["fields"].items()}
+    bad["U_SSA"][10] += 1e-6 * max(1.0, abs(bad["U_SSA"]).max())
+    rep = bench.parity_report(bad, tr["rows"], tr["time"], tr)
+    assert not rep["passed"] and not rep["bit_identical"]["U_SSA"] and rep["bit_identical"]["Hi"] and rep["rel_l2_U"] > 1e-10
+    rows = copy.deepcopy(tr["rows"]); rows[1]["n_sor"] += 1
+    assert not bench.parity_report(tr["fields"], rows, tr["time"], tr)["passed"]
+    rows = copy.deepcopy(tr["rows"]); rows[2]["dt"] *= 1.0 + 1e-15
+    assert not bench.parity_report(tr["fields"], rows, tr["time"], tr)["dt_equal"]
+    tr2 = bench.cpu_trajectory(m, st, 1, 2, 3)                                       # other thread count: same bits (rank-independent sums)
+    assert bench.parity_report(tr2["fields"], tr2["rows"], tr2["time"], tr)["passed"]
+
+
+def test_both_arms_print_the_same_config_object():
+    import argparse
+
+    m, _ = bench.build_workload(3000)
+    a = argparse.Namespace(exact_xy=1, order="random", multi="partition")
+    assert bench.bench_config(m, a, 1) == bench.bench_config(m, a, 1) and "model" not in bench.bench_config(m, a, 1)
+    assert "x-strips" in bench.bench_config(m, a, 4)["parallelism"] and bench.bench_config(m, a, 1)["workload"] == bench.workload_name(m)
+    b = bench.algorithmic_bytes(m)
+    assert b["geom"] > b["thk"] > b["cfl"] > 0 and b["visc"] > b["geom"] * 0.9
 
 
 def test_roofline_denominator_is_the_measured_peak_when_present():
@@ -72,8 +101,11 @@ def test_ours_arm_bookkeeping_with_a_fake_device(monkeypatch, capsys):
             self.cnt = capi.Counters()
             self.cnt.sor_bytes_per_iteration = 200.0 * mesh.nVAaAc
             self.k = 0
+            self.nV = mesh.nV
 
         def upload_mesh(self, m): self.k = 0
+        def download(self, name): import numpy as np; return np.zeros(self.nV)
+        def pow_mode(self): return 3
         def set_stream(self, s): pass
         def upload(self, k, v): pass
         def host_register(self, a): pass
@@ -113,15 +145,9 @@ def test_ours_arm_bookkeeping_with_a_fake_device(monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
     monkeypatch.setattr(capi, "IceModelGPU", FakeModel)
     monkeypatch.setattr(bench, "ClockSampler", FakeSampler)
-    monkeypatch.setattr(bench, "cpu_unit_costs", lambda m, st, n: bench._cpu_unit_costs(m, st, n, 5, 1))   # keep the CPU leg to a second
     monkeypatch.delenv("WORLD_SIZE", raising=False); monkeypatch.delenv("RANK", raising=False)
-    keep = os.path.join(ROOT, "gpurun_out", "config3_step_counts.json")
-    saved = open(keep).read() if os.path.exists(keep) else None
-    try:
-        bench.run_ours(argparse.Namespace(gpus=1, steps=4, warmup=3, impl="ours", nv=6000, exact_xy=1, no_cpu=False, no_regions=True, multi="partition"))
-    finally:
-        if saved is not None:
-            open(keep, "w").write(saved)
+    bench.run_ours(argparse.Namespace(gpus=1, steps=4, warmup=3, impl="ours", nv=6000, exact_xy=1, no_cpu=False, no_regions=True, multi="partition",
+                                      order="random", no_extras=True, no_other_order=True))
     line = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1]
     out = json.loads(line)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "clocks",
@@ -134,3 +160,6 @@ def test_ours_arm_bookkeeping_with_a_fake_device(monkeypatch, capsys):
     assert set(out["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and out["roofline"]["bound"] == "hbm"
     assert abs(out["roofline"]["frac"] - out["roofline"]["achieved"] / out["roofline"]["peak"]) < 1e-12
     assert set(out["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and out["cpu_baseline"]["kind"] == "port"
+    assert set(out["parity"]) >= {"rel_l2_U", "rel_l2_V", "rel_l2_Hi", "n_sor_equal", "n_outer_equal", "passed"} and out["parity"]["steps_compared"] == 7
+    assert not out["parity"]["passed"]                        # the fake device returns zeros: the report must say so
+    assert out["config"] == bench.bench_config(bench.build_workload(6000)[0], argparse.Namespace(exact_xy=1, order="random", multi="partition"), 1)

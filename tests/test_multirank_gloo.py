@@ -76,3 +76,39 @@ def test_partition_owners_are_balanced_x_strips(P):
         if (own[nb[ai, :n]] != own[ai]).any():
             cross += 1
     assert cross < 0.35 * m.nVAaAc * (P / 8) + 0.1 * m.nVAaAc
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+def test_halo_plan_of_the_partitioned_per_step_kernels(P):
+    """ufm_partition_halo_counts (host only) = the lists ufm_mesh_upload builds for the partitioned per-step kernels: rank s sends rank q
+    every own Aa vertex that q reads (a neighbour of one of q's vertices, or one of the four vertices of one of q's staggered vertices)
+    and every own staggered vertex on a connection of one of q's vertices.  Checked against a numpy restatement from C / iAci / Aci;
+    x-strips only talk to their neighbour strips, and the traffic is a boundary effect (O(sqrt N))."""
+    import numpy as np
+
+    from tests.conftest import get_mesh
+    from ufemism_b200 import capi
+
+    m = get_mesh(10000)
+    own = capi.partition_owners(m, P).astype(np.int64)
+    oa, oc = own[: m.nV], own[m.nV:]
+    ca, cc = capi.partition_halo_counts(m, P)
+    rd_aa = np.zeros((m.nV, P), bool); rd_ac = np.zeros((m.nAc, P), bool)
+    for c in range(m.nC_mem):
+        has = c < m.nC
+        u, a = m.C[has, c] - 1, m.iAci[has, c] - 1
+        rd_aa[u, oa[has]] = True
+        rd_ac[a, oa[has]] = True
+    for k in range(4):
+        rd_aa[m.Aci[:, k] - 1, oc] = True
+    want_a, want_c = np.zeros((P, P), np.int64), np.zeros((P, P), np.int64)
+    for s in range(P):
+        for q in range(P):
+            if s != q:
+                want_a[s, q] = np.sum(rd_aa[oa == s, q]); want_c[s, q] = np.sum(rd_ac[oc == s, q])
+    assert np.array_equal(ca, want_a) and np.array_equal(cc, want_c)
+    far = np.abs(np.subtract.outer(np.arange(P), np.arange(P))) > 1
+    # strips exchange with their neighbour strips only -- except vertex 1, which every domain-boundary staggered vertex names as its
+    # fourth vertex with a zero coefficient (src/mesh_ArakawaC_module.f90:165-167)
+    assert (ca[far] <= 1).all() and not cc[far].any()
+    assert 0 < ca.sum() < 0.1 * m.nV * P and 0 < cc.sum() < 0.1 * m.nAc * P   # a boundary effect

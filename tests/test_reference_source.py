@@ -444,7 +444,7 @@ def test_live_region_loop_scheduling():
     mesh = RC.golden_mesh()
     st = RC.start_state(mesh)
     # dt_max and the fixed timers are set long, so that the critical time steps of the dynamics decide the step (the golden mesh is coarse)
-    cfg = dict(use_analytical_GL_flux=1, SSA_max_outer_loops=2, SSA_max_inner_loops=5, dt_max=1000.0)
+    cfg = dict(use_analytical_GL_flux=1, SSA_max_outer_loops=2, SSA_max_inner_loops=5, dt_max=1000.0, dt_thermo=700.0)   # C%dt_thermo sets the thermodynamics timer
     o = make_oracle(mesh, st, nthreads=1, **cfg)
     P = RS.program(o.cfg)
     P.C.choice_benchmark_experiment = st["benchmark"]

@@ -358,6 +358,31 @@ static void ufm_partition_owners_impl(const std::vector<double> &X, int P, std::
   for (int k = 0; k < M; k++) owner[byx[k]] = (unsigned char)(((long long)k * P) / M);
 }
 
+// Who reads what across the partition (per-step kernels): rd_aa[v*P + q] = 1 when rank q reads Aa vertex v -- v is a neighbour of one
+// of q's vertices (gradients, masks, thickness fluxes) or one of the four vertices of one of q's staggered vertices (map_Aa_to_Ac,
+// get_mesh_derivatives_Ac); rd_ac[a*P + q] = 1 when staggered vertex a lies on a connection of one of q's vertices (thickness fluxes,
+// map_Ac_to_Aa).  Reference (0-based) indices.
+static void ufm_partition_reads_impl(const ufm_mesh_desc *d, const std::vector<unsigned char> &owner, int P, std::vector<unsigned char> &rd_aa,
+                                     std::vector<unsigned char> &rd_ac)
+{
+  const int N = d->nV, E = d->nAc, ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E;
+  rd_aa.assign((size_t)N * P, 0); rd_ac.assign((size_t)E * P, 0);
+#pragma omp parallel for schedule(static)
+  for (int v = 0; v < N; v++) {
+    const int q = owner[v];
+    for (int c = 1; c <= d->nC[v]; c++) {
+      const int u = F2(d->C, v + 1, c, ldV) - 1, a = F2(d->iAci, v + 1, c, ldV) - 1;
+      if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1;      // benign race: every writer stores 1
+      if (a >= 0 && a < E) rd_ac[(size_t)a * P + q] = 1;
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int a = 0; a < E; a++) {
+    const int q = owner[N + a];
+    for (int k = 1; k <= 4; k++) { const int u = F2(d->Aci, a + 1, k, ldAc) - 1; if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1; }
+  }
+}
+
 // host-only planning entry point (no device work): the partition ufm_mesh_upload will use
 extern "C" int ufm_partition_owners(const ufm_mesh_desc *d, int nranks, unsigned char *owner_out)
 {
@@ -370,6 +395,25 @@ extern "C" int ufm_partition_owners(const ufm_mesh_desc *d, int nranks, unsigned
   std::vector<unsigned char> owner;
   ufm_partition_owners_impl(X, nranks, owner);
   memcpy(owner_out, owner.data(), owner.size());
+  return 0;
+}
+
+// host-only planning entry point: how many Aa / Ac values rank s sends to rank q in one halo exchange of the partitioned per-step
+// kernels (cnt[s*P + q]; the diagonal is 0)
+extern "C" int ufm_partition_halo_counts(const ufm_mesh_desc *d, int nranks, int *cnt_aa, int *cnt_ac)
+{
+  if (!d || !d->V || !d->Aci || !d->C || !d->nC || !d->iAci || !cnt_aa || !cnt_ac) return ufm_set_error(-2, "ufm_partition_halo_counts: NULL argument");
+  if (nranks < 1 || nranks > UFM_MAX_RANKS) return ufm_set_error(-2, "ufm_partition_halo_counts: nranks out of range");
+  const int N = d->nV, E = d->nAc, ldV = d->ldV ? d->ldV : N, ldAc = d->ldAc ? d->ldAc : E, P = nranks;
+  std::vector<double> X((size_t)N + E);
+  for (int v = 1; v <= N; v++) X[v - 1] = F2(d->V, v, 1, ldV);
+  for (int a = 1; a <= E; a++) X[N + a - 1] = 0.5 * (X[F2(d->Aci, a, 1, ldAc) - 1] + X[F2(d->Aci, a, 2, ldAc) - 1]);
+  std::vector<unsigned char> owner, rd_aa, rd_ac;
+  ufm_partition_owners_impl(X, P, owner);
+  ufm_partition_reads_impl(d, owner, P, rd_aa, rd_ac);
+  for (int k = 0; k < P * P; k++) cnt_aa[k] = cnt_ac[k] = 0;
+  for (int v = 0; v < N; v++) for (int q = 0; q < P; q++) if (q != owner[v] && rd_aa[(size_t)v * P + q]) cnt_aa[owner[v] * P + q]++;
+  for (int a = 0; a < E; a++) for (int q = 0; q < P; q++) if (q != owner[N + a] && rd_ac[(size_t)a * P + q]) cnt_ac[owner[N + a] * P + q]++;
   return 0;
 }
 
@@ -968,21 +1012,8 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     // reads[q] marks (reference index) the Aa vertices / Ac vertices that rank q reads: neighbours of its vertices, the four vertices of
     // its staggered vertices; the staggered vertices around its vertices
     std::vector<std::vector<int>> sa(P), ra(P), sc(P), rc(P);
-    std::vector<unsigned char> rd_aa((size_t)N * P, 0), rd_ac((size_t)E * P, 0);
-#pragma omp parallel for schedule(static)
-    for (int v = 0; v < N; v++) {
-      const int q = owner[v];
-      for (int c = 1; c <= d->nC[v]; c++) {
-        const int u = F2(d->C, v + 1, c, ldV) - 1, a = F2(d->iAci, v + 1, c, ldV) - 1;
-        if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1;      // benign race: every writer stores 1
-        if (a >= 0 && a < E) rd_ac[(size_t)a * P + q] = 1;
-      }
-    }
-#pragma omp parallel for schedule(static)
-    for (int a = 0; a < E; a++) {
-      const int q = owner[N + a];
-      for (int k = 1; k <= 4; k++) { const int u = F2(d->Aci, a + 1, k, ldAc) - 1; if (u >= 0 && u < N) rd_aa[(size_t)u * P + q] = 1; }
-    }
+    std::vector<unsigned char> rd_aa, rd_ac;
+    ufm_partition_reads_impl(d, owner, P, rd_aa, rd_ac);
     // lists in device-index order (deterministic on every rank)
     for (int p_ = 0; p_ < m.nVp; p_++) {
       const int v = aa_d2r[p_];
