@@ -321,11 +321,15 @@ def run_reference(args):
     other = "morton" if args.order == "random" else "random"
     if not args.no_other_order:
         try:
+            n2 = min(args.steps, 6)        # a shorter window keeps this arm within a few minutes; compared with the main run over the same steps
             m2, st2 = build_workload(args.nv, order=other)
             t = time.time()
-            traj2 = cpu_trajectory(m2, st2, nthreads, args.warmup, args.steps)
+            traj2 = cpu_trajectory(m2, st2, nthreads, args.warmup, n2)
             log(f"[bench] CPU trajectory ({other} order): {time.time() - t:.1f}s")
-            base["other_host_vertex_order"] = dict(cpu_line(traj2, args.warmup, nthreads, m2, f"same job, host vertex order '{other}'"), order=other)
+            same_window = {"rows": traj["rows"][: args.warmup + n2], "step_s": traj["step_s"][: args.warmup + n2], "time_after_warmup": traj["time_after_warmup"],
+                           "time": traj["time_after_warmup"] + sum(x["dt"] for x in traj["rows"][args.warmup: args.warmup + n2])}
+            base["other_host_vertex_order"] = dict(cpu_line(traj2, args.warmup, nthreads, m2, f"same job, host vertex order '{other}'"), order=other,
+                                                   main_order_over_the_same_steps=cpu_line(same_window, args.warmup, nthreads, m, f"host vertex order '{args.order}'")["value"])
             del m2, st2, traj2
         except Exception as ex:  # noqa: BLE001
             base["other_host_vertex_order"] = {"error": str(ex)}
@@ -720,6 +724,28 @@ def run_ours(args):
             regions["partitioned_vs_single_gpu"] = {"fields_bit_identical": same_bits, "model_time_equal": bool(r3.time == gpu_time_final),
                                                     "n_sor": [int(r.n_sor_total), int(r3.n_sor_total)], "n_outer": [int(r.n_outer_total), int(r3.n_outer_total)]}
 
+    # N > 1: BASELINE configs[4], the size the partition is for (~4 M vertices), on the same ranks
+    config5 = None
+    if part and not args.no_config5:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import config5_probe
+
+            g.close()
+            config5 = config5_probe.run(args.nv5, dist=dist, torch=torch, rank=rank, world=world, local=local, log=log)
+            ref1 = os.path.join(ROOT, "profiles", "config5_4M_1gpu_r02.json")
+            if os.path.exists(ref1):
+                one = json.load(open(ref1))
+                if one.get("workload") == config5["workload"]:
+                    config5["one_gpu"] = {k: one[k] for k in ("ms_per_step", "sor_us_per_iteration_forced", "sor_us_per_iteration_in_solve") if k in one}
+                    config5["one_gpu"]["source"] = "profiles/config5_4M_1gpu_r02.json (same script on one B200, this round)"
+                    config5["speedup_sor_iteration"] = one["sor_us_per_iteration_forced"] / config5["sor_us_per_iteration_forced"]
+                    config5["efficiency_sor_iteration"] = config5["speedup_sor_iteration"] / world
+                    config5["speedup_step"] = one["ms_per_step"] / config5["ms_per_step"]
+                    config5["efficiency_step"] = config5["speedup_step"] / world
+        except Exception as ex:  # noqa: BLE001  (reporting only)
+            config5 = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         if part:
@@ -750,6 +776,8 @@ def run_ours(args):
                        "n_sor": int(sum(x["n_sor"] for x in rows))}}
         if step_ms:
             out["ssa"].update(ssa_solve_time(step_ms, rows))
+        if config5:
+            out["config5_4M"] = config5
         if regions:
             out["partitioned_bit_identical"] = regions.pop("partitioned_bit_identical", None)
             out["partitioned_vs_single_gpu"] = regions.pop("partitioned_vs_single_gpu", None)
@@ -817,6 +845,8 @@ def main():
     ap.add_argument("--no-other-order", dest="no_other_order", action="store_true", help="--impl reference: skip the second trajectory on the other host vertex numbering")
     ap.add_argument("--no-extras", dest="no_extras", action="store_true", help="skip the legs after the headline (configs 1, 2, 4, warm-state solve)")
     ap.add_argument("--no-regions", action="store_true", help="N > 1: skip the extra independent-regions measurement")
+    ap.add_argument("--no-config5", dest="no_config5", action="store_true", help="N > 1: skip the ~4 M-vertex leg (BASELINE configs[4])")
+    ap.add_argument("--nv5", type=int, default=4000000, help="vertices of the config-5 leg")
     ap.add_argument("--multi", default="partition", choices=["partition", "regions"], help="what N > 1 GPUs do (see run_ours)")
     args = ap.parse_args()
     if args.warmup < 3:

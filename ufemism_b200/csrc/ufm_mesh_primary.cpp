@@ -19,6 +19,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "ufm_internal.cuh"
@@ -40,7 +42,15 @@ struct ufm_secondary {
   std::vector<double> V, A, Cw, Tricc, VAc, VAaAc, R, NxTri, NyTri;
   std::vector<int> nC, C, niTri, iTri, edge_index, Tri, Tri_edge_index, iAci, Aci, edge_index_Ac, nCAaAc, CAaAc, colour, colour_vi, colour_nV;
   ufm_mesh_desc desc;
+  // the five-colouring may still be running on its own thread (ufm_mesh_upload_primary overlaps it with the colour-independent half of the
+  // upload): colour, colour_vi and colour_nV are final once colour_join() has returned
+  std::thread colour_thread;
+  std::vector<int> label;
+  int colour_rc = 0;
+  int colour_join() { if (colour_thread.joinable()) colour_thread.join(); return colour_rc; }
+  ~ufm_secondary() { colour_join(); }
 };
+extern thread_local std::function<int()> *g_ufm_colour_wait;   // ufm_upload.cu
 
 void ufm_secondary_free(ufm_handle *h)
 {
@@ -58,8 +68,15 @@ void compact(std::vector<T> &dst, const T *src, int n, int cols, int ld)
 }
 }  // namespace
 
-// host-only half: everything ufm_mesh_upload_primary derives before it touches the device
+// host-only half: everything ufm_mesh_upload_primary derives before it touches the device.  async_colour: return while the five-colouring
+// (sequential by construction, a third of the whole re-upload) is still running on its own thread
+static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour);
 extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **derived)
+{
+  int rc = derive_secondary_impl(p, derived, false);
+  return rc;
+}
+static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour)
 {
   if (!derived) return ufm_set_error(-2, "ufm_mesh_derive_secondary: NULL output");
   *derived = nullptr;
@@ -104,12 +121,7 @@ extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **deriv
   if (bad_t) return ufm_set_error(-2, "ufm_mesh_upload_primary: Tri(%d,:) out of range", bad_t);
   lap("copy + validate");
 
-  s->A.resize(N); s->Cw.assign((size_t)N * W, 0.0); s->Tricc.resize((size_t)T * 2); s->Tri_edge_index.resize(T);
-  int rc = ufm_mesh_geometry(N, T, W, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(), s->edge_index.data(),
-                             p->xmin, p->xmax, p->ymin, p->ymax, s->Tricc.data(), s->Tri_edge_index.data(), s->A.data(), s->Cw.data());
-  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: Voronoi areas / connection widths failed (%d): C / iTri / Tri are inconsistent", rc);
-  lap("Voronoi areas, Cw");
-
+  int rc = 0;
   // a planar triangulation of a simply connected domain has exactly nV + nTri - 1 edges (Euler)
   const int nAc_max = N + T;
   s->ldAc = nAc_max;
@@ -129,7 +141,8 @@ extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **deriv
 
   // The colouring's delete loop hops from a vertex to its neighbours; meshes come numbered in refinement order (random in space), so
   // run it on a Morton relabelling of the graph: same decisions, same colours (see ufm_mesh_five_colouring_labelled), rows in cache.
-  std::vector<int> label(M);
+  std::vector<int> &label = s->label;
+  label.resize(M);
   {
     std::vector<unsigned long long> key(M);
     const double *X = s->VAaAc.data(), *Y = X + M;
@@ -149,9 +162,20 @@ extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **deriv
   }
   lap("Morton labels");
   s->colour.resize(M); s->colour_vi.assign((size_t)M * 5, 0); s->colour_nV.assign(5, 0);
-  rc = ufm_mesh_five_colouring_labelled(M, W, s->nCAaAc.data(), s->CAaAc.data(), label.data(), s->colour.data(), s->colour_vi.data(), s->colour_nV.data());
-  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: five-colouring failed (%d)%s", rc, rc == -2 ? " (the reference aborts in IDENTIFY)" : "");
-  lap("five-colouring");
+  s->colour_thread = std::thread([s, M, W]() {
+    s->colour_rc = ufm_mesh_five_colouring_labelled(M, W, s->nCAaAc.data(), s->CAaAc.data(), s->label.data(), s->colour.data(), s->colour_vi.data(), s->colour_nV.data());
+  });
+  // ... while this thread goes on with what does not need the colours
+  s->A.resize(N); s->Cw.assign((size_t)N * W, 0.0); s->Tricc.resize((size_t)T * 2); s->Tri_edge_index.resize(T);
+  rc = ufm_mesh_geometry(N, T, W, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(), s->edge_index.data(),
+                             p->xmin, p->xmax, p->ymin, p->ymax, s->Tricc.data(), s->Tri_edge_index.data(), s->A.data(), s->Cw.data());
+  if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: Voronoi areas / connection widths failed (%d): C / iTri / Tri are inconsistent", rc);
+  lap("Voronoi areas, Cw");
+
+  if (!async_colour) {
+    if ((rc = s->colour_join())) return ufm_set_error(-2, "ufm_mesh_upload_primary: five-colouring failed (%d)%s", rc, rc == -2 ? " (the reference aborts in IDENTIFY)" : "");
+    lap("five-colouring (rest)");
+  }
 
   ufm_mesh_desc &d = s->desc;
   memset(&d, 0, sizeof(d));
@@ -194,11 +218,18 @@ extern "C" int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *p)
 {
   if (!h) return ufm_set_error(-2, "NULL handle");
   void *derived = nullptr;
-  int rc = ufm_mesh_derive_secondary(p, &derived);
+  int rc = derive_secondary_impl(p, &derived, true);
   if (rc) return rc;
   ufm_secondary *s = (ufm_secondary *)derived;
   const auto t0 = std::chrono::steady_clock::now();
+  // ufm_mesh_upload sorts, fills and uploads the Aa / Ac arrays first and asks for the colours only then
+  std::function<int()> wait = [s]() {
+    const int rc_c = s->colour_join();
+    return rc_c ? ufm_set_error(-2, "ufm_mesh_upload_primary: five-colouring failed (%d)%s", rc_c, rc_c == -2 ? " (the reference aborts in IDENTIFY)" : "") : 0;
+  };
+  g_ufm_colour_wait = &wait;
   rc = ufm_mesh_upload(h, &s->desc);   // drops the arrays derived for the previous mesh
+  g_ufm_colour_wait = nullptr;
   if (getenv("UFM_UPLOAD_TIMING"))
     fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", "ufm_mesh_upload", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   if (rc) { delete s; return rc; }

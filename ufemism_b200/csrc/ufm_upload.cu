@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <vector>
 
@@ -441,13 +442,13 @@ static void ufm_row_order_impl(int M, const unsigned char *blkv, const unsigned 
     return false;
   };
   if (n_bands == 0) {
-    __gnu_parallel::stable_sort(m_order.begin(), m_order.end(), [&](int a, int b) {
-      bool eq;
-      const bool lt = group_less(a, b, eq);
-      if (!eq) return lt;
-      if (degv[a] != degv[b]) return degv[a] < degv[b];
-      return mort[a] < mort[b];
-    });
+    // one packed key per row (block | owner | boundary | late | degree | Morton: 49 bits) instead of six indirections per comparison; ties
+    // (equal keys) keep index order, i.e. the order a stable sort of the separate keys gives
+    std::vector<uint64_t> key(M);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < M; i++)
+      key[i] = ((uint64_t)blkv[i] << 46) | ((uint64_t)owner[i] << 42) | ((uint64_t)(isb[i] != 0) << 41) | ((uint64_t)(late[i] != 0) << 40) | ((uint64_t)degv[i] << 32) | (uint64_t)mort[i];
+    __gnu_parallel::sort(m_order.begin(), m_order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
     return;
   }
   double x0 = 1e300, x1 = -1e300;
@@ -489,6 +490,10 @@ extern "C" int ufm_plan_row_order(int M, const unsigned char *block, const unsig
   memcpy(order_out, o.data(), sizeof(int) * (size_t)M);
   return 0;
 }
+
+// set by ufm_mesh_upload_primary for the duration of its ufm_mesh_upload call: blocks until colour_vi / colour_nV of the descriptor are
+// final (they are computed concurrently with the colour-independent half of the upload) and returns the colouring's return code
+thread_local std::function<int()> *g_ufm_colour_wait = nullptr;
 
 int ufm_mesh_free_impl(ufm_handle *h)
 {
@@ -540,17 +545,22 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // ---- coordinates of all AaAc vertices, bounding box ----
   std::vector<double> X(M), Y(M);
   double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+#pragma omp parallel for schedule(static) reduction(min : x0, y0) reduction(max : x1, y1)
   for (int v = 1; v <= N; v++) {
     X[v - 1] = F2(d->V, v, 1, ldV); Y[v - 1] = F2(d->V, v, 2, ldV);
     x0 = std::min(x0, X[v - 1]); x1 = std::max(x1, X[v - 1]); y0 = std::min(y0, Y[v - 1]); y1 = std::max(y1, Y[v - 1]);
   }
+  int bad_aci = 0;
+#pragma omp parallel for schedule(static) reduction(max : bad_aci)
   for (int a = 1; a <= E; a++) {
     int vi = F2(d->Aci, a, 1, ldAc), vj = F2(d->Aci, a, 2, ldAc);
-    if (vi < 1 || vi > N || vj < 1 || vj > N) return ufm_set_error(-2, "ufm_mesh_upload: Aci out of range at aci=%d", a);
+    if (vi < 1 || vi > N || vj < 1 || vj > N) { bad_aci = std::max(bad_aci, a); continue; }
     X[N + a - 1] = 0.5 * (X[vi - 1] + X[vj - 1]); Y[N + a - 1] = 0.5 * (Y[vi - 1] + Y[vj - 1]);
   }
+  if (bad_aci) return ufm_set_error(-2, "ufm_mesh_upload: Aci out of range at aci=%d", bad_aci);
   const double sx = 65535.0 / std::max(x1 - x0, 1e-300), sy = 65535.0 / std::max(y1 - y0, 1e-300);
   std::vector<uint32_t> mort(M);
+#pragma omp parallel for schedule(static)
   for (int i = 0; i < M; i++) mort[i] = morton2(X[i], Y[i], x0, y0, sx, sy);
 
   lap("coordinates + morton");
@@ -566,6 +576,175 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   for (int p = 0; p < E; p++) { ac_r2d[ac_order[p]] = p; ac_d2r[p] = ac_order[p]; }
 
   lap("Aa/Ac sort");
+  // The Aa and Ac arrays below do not depend on the colouring: ufm_mesh_upload_primary computes it on another thread meanwhile.
+  // ---- Aa sliced ELL ----
+  {
+    std::vector<unsigned char> deg(m.nVp, UFM_DEG_PAD), edge(m.nVp, 0);
+    for (int p = 0; p < N; p++) {
+      int n = d->nC[aa_d2r[p]];
+      if (n < 2 || n > W) return ufm_set_error(-2, "ufm_mesh_upload: nC(%d) = %d out of range", aa_d2r[p] + 1, n);
+      deg[p] = (unsigned char)n;
+      edge[p] = (unsigned char)d->edge_index[aa_d2r[p]];
+    }
+    std::vector<long long> off;
+    build_slices(deg, off);
+    m.aa.n_rows = m.nVp; m.aa.n_slices = m.nVp / UFM_SLICE; m.aa.n_entries = off.back();
+    size_t ne = (size_t)off.back();
+    std::vector<int> Cn(ne), iA(ne, 0);
+    const bool derive_aa = !d->Nx || !d->Ny;   // no Aa neighbour functions from the host: derived on the device below
+    std::vector<double> nx(derive_aa ? 0 : ne, 0.0), ny(derive_aa ? 0 : ne, 0.0), nx0(derive_aa ? 0 : m.nVp, 0.0), ny0(derive_aa ? 0 : m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
+    int bad_vertex = 0;
+    // thermodynamics: triangles around every vertex (iTri order is the search order of get_upwind_derivative_vertex_3D)
+    const bool has_tri = d->Tri && d->niTri && d->iTri && d->R && d->NxTri && d->NyTri && d->nTri > 0;
+    m.has_tri = has_tri; m.nTri = has_tri ? d->nTri : 0;
+    std::vector<int> iT(has_tri ? ne : 0, -1);
+    std::vector<double2> xy(m.nVp, make_double2(0.0, 0.0));   // vertex coordinates: benchmark SMB closed forms, upwind search
+    std::vector<double> rmin(m.nVp, 1.0);
+    std::vector<double> Rr(has_tri ? m.nVp : 0, 1.0);
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < m.aa.n_slices; s++) {
+      int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
+      for (int l = 0; l < UFM_SLICE; l++) {
+        int p = s * UFM_SLICE + l, vi = aa_d2r[p];
+        for (int c = 0; c < w; c++) Cn[(size_t)off[s] + (size_t)c * UFM_SLICE + l] = p < N ? p : 0;
+        if (vi < 0) continue;
+        int n = deg[p];
+        for (int c = 1; c <= n; c++) {
+          size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
+          int vc = F2(d->C, vi + 1, c, ldV), aci = F2(d->iAci, vi + 1, c, ldV);
+          if (vc < 1 || vc > N || aci < 1 || aci > E) { bad_vertex = vi + 1; continue; }
+          Cn[e] = aa_r2d[vc - 1];
+          int first = (F2(d->Aci, aci, 1, ldAc) == vi + 1);
+          iA[e] = ac_r2d[aci - 1] | (first ? (int)0x80000000u : 0);
+          if (!derive_aa) { nx[e] = F2(d->Nx, vi + 1, c, ldV); ny[e] = F2(d->Ny, vi + 1, c, ldV); }
+        }
+        if (!derive_aa) { nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV); ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV); }
+        if (has_tri) {
+          const int nt = d->niTri[vi];
+          if (nt < 0 || nt > n) { bad_vertex = vi + 1; continue; }
+          for (int c = 1; c <= nt; c++) {
+            const int ti = F2(d->iTri, vi + 1, c, ldV);
+            if (ti < 1 || ti > d->nTri) { bad_vertex = vi + 1; continue; }
+            iT[(size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l] = ti - 1;
+          }
+          Rr[p] = d->R[vi];
+        }
+        xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
+        A[p] = d->A[vi];
+        sA[p] = std::sqrt(d->A[vi] / UFM_PI);
+        // numerator of the vertex's SSA critical time step: SQRT(A/pi) or its shortest connection (UFEMISM_main_model.f90:751-762)
+        double rm = sA[p];
+        for (int c = 1; c <= n; c++) {
+          const int vc = F2(d->C, vi + 1, c, ldV);
+          if (vc < 1 || vc > N) continue;
+          const double ddx = F2(d->V, vc, 1, ldV) - xy[p].x, ddy = F2(d->V, vc, 2, ldV) - xy[p].y;
+          rm = std::min(rm, std::sqrt(ddx * ddx + ddy * ddy));
+        }
+        rmin[p] = rm;
+      }
+    }
+    if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
+    lap("Aa ELL fill");
+    UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci);
+    UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(rmin, m.aa_rmin); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
+    if (!derive_aa) { UP(nx, m.aa_Nx); UP(ny, m.aa_Ny); UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); }
+    else {
+      double **q4[] = {&m.aa_Nx, &m.aa_Ny};
+      for (double **q : q4) { int rc_ = ufm_arena_alloc(h, std::max<size_t>(ne, 1) * sizeof(double), (void **)q); if (rc_) return rc_; }
+      double **q2[] = {&m.aa_Nx0, &m.aa_Ny0};
+      for (double **q : q2) { int rc_ = ufm_arena_alloc(h, (size_t)m.nVp * sizeof(double), (void **)q); if (rc_) return rc_; }
+      k_derive_nf_Aa<<<(m.aa.n_slices * 32 + 127) / 128, 128, 0, h->stream>>>(m.aa.n_slices, m.aa.off, m.aa.deg, m.aa_edge, m.aa_C, m.aa_xy,
+                                                                              m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      UFM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (has_tri) {
+      const int nT = d->nTri, ldT = d->ldTri ? d->ldTri : nT;
+      std::vector<TriRec> tr(nT);
+      int bad_tri = 0;
+#pragma omp parallel for schedule(static)
+      for (int t = 0; t < nT; t++) {
+        TriRec q;
+        int v[3];
+        bool ok = true;
+        for (int k = 0; k < 3; k++) {
+          v[k] = F2(d->Tri, t + 1, k + 1, ldT);
+          if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
+          q.v[k] = aa_r2d[v[k] - 1];
+          q.nx[k] = F2(d->NxTri, t + 1, k + 1, ldT);
+          q.ny[k] = F2(d->NyTri, t + 1, k + 1, ldT);
+        }
+        if (!ok) bad_tri = t + 1;
+        q.ax = F2(d->V, v[0], 1, ldV); q.ay = F2(d->V, v[0], 2, ldV);
+        q.bx = F2(d->V, v[1], 1, ldV); q.by = F2(d->V, v[1], 2, ldV);
+        q.cx = F2(d->V, v[2], 1, ldV); q.cy = F2(d->V, v[2], 2, ldV);
+        q.pad = 0;
+        tr[t] = q;
+      }
+      if (bad_tri) return ufm_set_error(-2, "ufm_mesh_upload: Tri(%d,:) out of range", bad_tri);
+      UP(iT, m.aa_iTri); UP(Rr, m.aa_R); UP(tr, m.tri);
+    }
+  }
+
+  lap("Aa (+ triangle) upload");
+  // ---- Ac arrays ----
+  {
+    std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
+    const bool derive_ac = !d->Nx_Ac || !d->Ny_Ac || !d->No_Ac || !d->Np_Ac;   // derived on the device below
+    std::vector<double> c4[3][4], np(derive_ac ? 0 : m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0), dist2(m.nAcp, 1.0);
+    for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(derive_ac ? 0 : m.nAcp, 0.0);
+    int bad_ac = 0;
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < E; p++) {
+      int a = ac_d2r[p] + 1;
+      int v[4];
+      bool ok = true;
+      for (int k = 0; k < 4; k++) {
+        v[k] = F2(d->Aci, a, k + 1, ldAc);
+        if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
+        if (!derive_ac) { c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc); }
+      }
+      aci[p] = make_int4(aa_r2d[v[0] - 1], aa_r2d[v[1] - 1], aa_r2d[v[2] - 1], aa_r2d[v[3] - 1]);
+      if (!derive_ac) np[p] = d->Np_Ac[a - 1];
+      int ci = 0;
+      for (int c = 1; c <= d->nC[v[0] - 1]; c++) if (F2(d->C, v[0], c, ldV) == v[1]) { ci = c; break; }
+      if (!ci || !ok) { bad_ac = a; continue; }
+      cw[p] = F2(d->Cw, v[0], ci, ldV);
+      dx[p] = F2(d->V, v[1], 1, ldV) - F2(d->V, v[0], 1, ldV);
+      dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
+      const double dist = std::sqrt(dx[p] * dx[p] + dy[p] * dy[p]);
+      dist2[p] = dist * dist;   // dist**2 of UFEMISM_main_model.f90:752
+    }
+    if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
+    lap("Ac fill");
+    UP(aci, m.ac_Aci); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy); UP(dist2, m.ac_dist2);
+    if (!derive_ac) {
+      UP(np, m.ac_Np);
+      for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
+    } else {
+      NfAcArgs a;
+      a.nAc = E; a.Aci = m.ac_Aci; a.xy = m.aa_xy; a.edge = m.aa_edge;
+      const size_t bytes = (size_t)m.nAcp * sizeof(double);
+      int rc_ = ufm_arena_alloc(h, bytes, (void **)&m.ac_Np);
+      if (rc_) return rc_;
+      UFM_CUDA(cudaMemset(m.ac_Np, 0, bytes));
+      for (int k = 0; k < 4; k++) {
+        double **q3[] = {&m.ac_Nx[k], &m.ac_Ny[k], &m.ac_No[k]};
+        for (double **q : q3) { if ((rc_ = ufm_arena_alloc(h, bytes, (void **)q))) return rc_; UFM_CUDA(cudaMemset(*q, 0, bytes)); }
+        a.Nx[k] = m.ac_Nx[k]; a.Ny[k] = m.ac_Ny[k]; a.No[k] = m.ac_No[k];
+      }
+      a.Np = m.ac_Np;
+      UFM_CUDA(cudaDeviceSynchronize());
+      k_derive_nf_Ac<<<(E + 255) / 256, 256, 0, h->stream>>>(a);
+      UFM_CUDA(cudaGetLastError());
+      h->cnt.kernel_launches++;
+      UFM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  }
+  // ---- the five-colouring is needed from here on (ufm_mesh_upload_primary: wait for the thread that computes it) ----
+  if (g_ufm_colour_wait) { const int rc_w = (*g_ufm_colour_wait)(); if (rc_w) return rc_w; }
+  lap("wait for the five-colouring");
   // ---- AaAc order: colour-major, (degree, Morton) inside a colour, edge block last ----
   std::vector<int> colour(M, 0);
   for (int c = 1; c <= 5; c++) {
@@ -577,20 +756,28 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     }
   }
   std::vector<unsigned char> is_edge(M), degv(M);
+  int bad_row = 0, bad_kind = 0;   // first offending vertex is not needed: any one will do for the message
+#pragma omp parallel for schedule(static)
   for (int ai = 0; ai < M; ai++) {
-    if (colour[ai] == 0) return ufm_set_error(-2, "ufm_mesh_upload: AaAc vertex %d has no colour", ai + 1);
     is_edge[ai] = ai < N ? (d->edge_index[ai] > 0) : (d->edge_index_Ac[ai - N] > 0);
-    int n = d->nCAaAc[ai];
-    if (n < 1 || n > W) return ufm_set_error(-2, "ufm_mesh_upload: nCAaAc(%d) = %d out of range", ai + 1, n);
-    degv[ai] = (unsigned char)n;
+    const int n = d->nCAaAc[ai];
+    degv[ai] = (unsigned char)(n < 0 ? 0 : (n > 255 ? 255 : n));
+    if (colour[ai] == 0) { bad_row = ai + 1; bad_kind = 1; }
+    else if (n < 1 || n > W) { bad_row = ai + 1; bad_kind = 2; }
   }
+  if (bad_kind == 1) return ufm_set_error(-2, "ufm_mesh_upload: AaAc vertex %d has no colour", bad_row);
+  if (bad_kind == 2) return ufm_set_error(-2, "ufm_mesh_upload: nCAaAc(%d) = %d out of range", bad_row, d->nCAaAc[bad_row - 1]);
   // the sweep relies on same-coloured vertices being non-adjacent (check_solution, mesh_five_colour_module.f90:318-343)
+  int bad_a = 0, bad_b = 0;
+#pragma omp parallel for schedule(static)
   for (int ai = 0; ai < M; ai++)
     for (int c = 1; c <= degv[ai]; c++) {
-      int ac = F2(d->CAaAc, ai + 1, c, ldM);
-      if (ac < 1 || ac > M) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
-      if (colour[ac - 1] == colour[ai]) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", ai + 1, ac);
+      const int ac = F2(d->CAaAc, ai + 1, c, ldM);
+      if (ac < 1 || ac > M) { bad_a = ai + 1; bad_b = -1; }
+      else if (colour[ac - 1] == colour[ai]) { bad_a = ai + 1; bad_b = ac; }
     }
+  if (bad_b == -1) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
+  if (bad_a) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", bad_a, bad_b);
   lap("colour + validity checks");
   // owner rank of every AaAc row: x-strips balanced by row count (cf. partition_domain_x_balanced,
   // src/mesh_help_functions_module.f90:1337-1404, which the reference uses for mesh generation)
@@ -823,171 +1010,6 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   }
 
   lap("boundary lists");
-  // ---- Aa sliced ELL ----
-  {
-    std::vector<unsigned char> deg(m.nVp, UFM_DEG_PAD), edge(m.nVp, 0);
-    for (int p = 0; p < N; p++) {
-      int n = d->nC[aa_d2r[p]];
-      if (n < 2 || n > W) return ufm_set_error(-2, "ufm_mesh_upload: nC(%d) = %d out of range", aa_d2r[p] + 1, n);
-      deg[p] = (unsigned char)n;
-      edge[p] = (unsigned char)d->edge_index[aa_d2r[p]];
-    }
-    std::vector<long long> off;
-    build_slices(deg, off);
-    m.aa.n_rows = m.nVp; m.aa.n_slices = m.nVp / UFM_SLICE; m.aa.n_entries = off.back();
-    size_t ne = (size_t)off.back();
-    std::vector<int> Cn(ne), iA(ne, 0);
-    const bool derive_aa = !d->Nx || !d->Ny;   // no Aa neighbour functions from the host: derived on the device below
-    std::vector<double> nx(derive_aa ? 0 : ne, 0.0), ny(derive_aa ? 0 : ne, 0.0), nx0(derive_aa ? 0 : m.nVp, 0.0), ny0(derive_aa ? 0 : m.nVp, 0.0), A(m.nVp, 1.0), sA(m.nVp, 1.0);
-    int bad_vertex = 0;
-    // thermodynamics: triangles around every vertex (iTri order is the search order of get_upwind_derivative_vertex_3D)
-    const bool has_tri = d->Tri && d->niTri && d->iTri && d->R && d->NxTri && d->NyTri && d->nTri > 0;
-    m.has_tri = has_tri; m.nTri = has_tri ? d->nTri : 0;
-    std::vector<int> iT(has_tri ? ne : 0, -1);
-    std::vector<double2> xy(m.nVp, make_double2(0.0, 0.0));   // vertex coordinates: benchmark SMB closed forms, upwind search
-    std::vector<double> rmin(m.nVp, 1.0);
-    std::vector<double> Rr(has_tri ? m.nVp : 0, 1.0);
-#pragma omp parallel for schedule(static)
-    for (int s = 0; s < m.aa.n_slices; s++) {
-      int w = (int)((off[s + 1] - off[s]) / UFM_SLICE);
-      for (int l = 0; l < UFM_SLICE; l++) {
-        int p = s * UFM_SLICE + l, vi = aa_d2r[p];
-        for (int c = 0; c < w; c++) Cn[(size_t)off[s] + (size_t)c * UFM_SLICE + l] = p < N ? p : 0;
-        if (vi < 0) continue;
-        int n = deg[p];
-        for (int c = 1; c <= n; c++) {
-          size_t e = (size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l;
-          int vc = F2(d->C, vi + 1, c, ldV), aci = F2(d->iAci, vi + 1, c, ldV);
-          if (vc < 1 || vc > N || aci < 1 || aci > E) { bad_vertex = vi + 1; continue; }
-          Cn[e] = aa_r2d[vc - 1];
-          int first = (F2(d->Aci, aci, 1, ldAc) == vi + 1);
-          iA[e] = ac_r2d[aci - 1] | (first ? (int)0x80000000u : 0);
-          if (!derive_aa) { nx[e] = F2(d->Nx, vi + 1, c, ldV); ny[e] = F2(d->Ny, vi + 1, c, ldV); }
-        }
-        if (!derive_aa) { nx0[p] = F2(d->Nx, vi + 1, n + 1, ldV); ny0[p] = F2(d->Ny, vi + 1, n + 1, ldV); }
-        if (has_tri) {
-          const int nt = d->niTri[vi];
-          if (nt < 0 || nt > n) { bad_vertex = vi + 1; continue; }
-          for (int c = 1; c <= nt; c++) {
-            const int ti = F2(d->iTri, vi + 1, c, ldV);
-            if (ti < 1 || ti > d->nTri) { bad_vertex = vi + 1; continue; }
-            iT[(size_t)off[s] + (size_t)(c - 1) * UFM_SLICE + l] = ti - 1;
-          }
-          Rr[p] = d->R[vi];
-        }
-        xy[p] = make_double2(F2(d->V, vi + 1, 1, ldV), F2(d->V, vi + 1, 2, ldV));
-        A[p] = d->A[vi];
-        sA[p] = std::sqrt(d->A[vi] / UFM_PI);
-        // numerator of the vertex's SSA critical time step: SQRT(A/pi) or its shortest connection (UFEMISM_main_model.f90:751-762)
-        double rm = sA[p];
-        for (int c = 1; c <= n; c++) {
-          const int vc = F2(d->C, vi + 1, c, ldV);
-          if (vc < 1 || vc > N) continue;
-          const double ddx = F2(d->V, vc, 1, ldV) - xy[p].x, ddy = F2(d->V, vc, 2, ldV) - xy[p].y;
-          rm = std::min(rm, std::sqrt(ddx * ddx + ddy * ddy));
-        }
-        rmin[p] = rm;
-      }
-    }
-    if (bad_vertex) return ufm_set_error(-2, "ufm_mesh_upload: C/iAci out of range at vertex %d", bad_vertex);
-    lap("Aa ELL fill");
-    UP(off, m.aa.off); UP(deg, m.aa.deg); UP(Cn, m.aa_C); UP(iA, m.aa_iAci);
-    UP(A, m.aa_A); UP(sA, m.aa_sqrtApi); UP(rmin, m.aa_rmin); UP(edge, m.aa_edge); UP(xy, m.aa_xy);
-    if (!derive_aa) { UP(nx, m.aa_Nx); UP(ny, m.aa_Ny); UP(nx0, m.aa_Nx0); UP(ny0, m.aa_Ny0); }
-    else {
-      double **q4[] = {&m.aa_Nx, &m.aa_Ny};
-      for (double **q : q4) { int rc_ = ufm_arena_alloc(h, std::max<size_t>(ne, 1) * sizeof(double), (void **)q); if (rc_) return rc_; }
-      double **q2[] = {&m.aa_Nx0, &m.aa_Ny0};
-      for (double **q : q2) { int rc_ = ufm_arena_alloc(h, (size_t)m.nVp * sizeof(double), (void **)q); if (rc_) return rc_; }
-      k_derive_nf_Aa<<<(m.aa.n_slices * 32 + 127) / 128, 128, 0, h->stream>>>(m.aa.n_slices, m.aa.off, m.aa.deg, m.aa_edge, m.aa_C, m.aa_xy,
-                                                                              m.aa_Nx, m.aa_Ny, m.aa_Nx0, m.aa_Ny0);
-      UFM_CUDA(cudaGetLastError());
-      h->cnt.kernel_launches++;
-      UFM_CUDA(cudaStreamSynchronize(h->stream));
-    }
-    if (has_tri) {
-      const int nT = d->nTri, ldT = d->ldTri ? d->ldTri : nT;
-      std::vector<TriRec> tr(nT);
-      int bad_tri = 0;
-#pragma omp parallel for schedule(static)
-      for (int t = 0; t < nT; t++) {
-        TriRec q;
-        int v[3];
-        bool ok = true;
-        for (int k = 0; k < 3; k++) {
-          v[k] = F2(d->Tri, t + 1, k + 1, ldT);
-          if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
-          q.v[k] = aa_r2d[v[k] - 1];
-          q.nx[k] = F2(d->NxTri, t + 1, k + 1, ldT);
-          q.ny[k] = F2(d->NyTri, t + 1, k + 1, ldT);
-        }
-        if (!ok) bad_tri = t + 1;
-        q.ax = F2(d->V, v[0], 1, ldV); q.ay = F2(d->V, v[0], 2, ldV);
-        q.bx = F2(d->V, v[1], 1, ldV); q.by = F2(d->V, v[1], 2, ldV);
-        q.cx = F2(d->V, v[2], 1, ldV); q.cy = F2(d->V, v[2], 2, ldV);
-        q.pad = 0;
-        tr[t] = q;
-      }
-      if (bad_tri) return ufm_set_error(-2, "ufm_mesh_upload: Tri(%d,:) out of range", bad_tri);
-      UP(iT, m.aa_iTri); UP(Rr, m.aa_R); UP(tr, m.tri);
-    }
-  }
-
-  lap("Aa (+ triangle) upload");
-  // ---- Ac arrays ----
-  {
-    std::vector<int4> aci(m.nAcp, make_int4(0, 0, 0, 0));
-    const bool derive_ac = !d->Nx_Ac || !d->Ny_Ac || !d->No_Ac || !d->Np_Ac;   // derived on the device below
-    std::vector<double> c4[3][4], np(derive_ac ? 0 : m.nAcp, 0.0), cw(m.nAcp, 0.0), dx(m.nAcp, 1.0), dy(m.nAcp, 0.0), dist2(m.nAcp, 1.0);
-    for (int q = 0; q < 3; q++) for (int k = 0; k < 4; k++) c4[q][k].assign(derive_ac ? 0 : m.nAcp, 0.0);
-    int bad_ac = 0;
-#pragma omp parallel for schedule(static)
-    for (int p = 0; p < E; p++) {
-      int a = ac_d2r[p] + 1;
-      int v[4];
-      bool ok = true;
-      for (int k = 0; k < 4; k++) {
-        v[k] = F2(d->Aci, a, k + 1, ldAc);
-        if (v[k] < 1 || v[k] > N) { ok = false; v[k] = 1; }
-        if (!derive_ac) { c4[0][k][p] = F2(d->Nx_Ac, a, k + 1, ldAc); c4[1][k][p] = F2(d->Ny_Ac, a, k + 1, ldAc); c4[2][k][p] = F2(d->No_Ac, a, k + 1, ldAc); }
-      }
-      aci[p] = make_int4(aa_r2d[v[0] - 1], aa_r2d[v[1] - 1], aa_r2d[v[2] - 1], aa_r2d[v[3] - 1]);
-      if (!derive_ac) np[p] = d->Np_Ac[a - 1];
-      int ci = 0;
-      for (int c = 1; c <= d->nC[v[0] - 1]; c++) if (F2(d->C, v[0], c, ldV) == v[1]) { ci = c; break; }
-      if (!ci || !ok) { bad_ac = a; continue; }
-      cw[p] = F2(d->Cw, v[0], ci, ldV);
-      dx[p] = F2(d->V, v[1], 1, ldV) - F2(d->V, v[0], 1, ldV);
-      dy[p] = F2(d->V, v[1], 2, ldV) - F2(d->V, v[0], 2, ldV);
-      const double dist = std::sqrt(dx[p] * dx[p] + dy[p] * dy[p]);
-      dist2[p] = dist * dist;   // dist**2 of UFEMISM_main_model.f90:752
-    }
-    if (bad_ac) return ufm_set_error(-2, "ufm_mesh_upload: Aci(%d,:) is out of range or not a connection in C", bad_ac);
-    lap("Ac fill");
-    UP(aci, m.ac_Aci); UP(cw, m.ac_Cw); UP(dx, m.ac_Dx); UP(dy, m.ac_Dy); UP(dist2, m.ac_dist2);
-    if (!derive_ac) {
-      UP(np, m.ac_Np);
-      for (int k = 0; k < 4; k++) { UP(c4[0][k], m.ac_Nx[k]); UP(c4[1][k], m.ac_Ny[k]); UP(c4[2][k], m.ac_No[k]); }
-    } else {
-      NfAcArgs a;
-      a.nAc = E; a.Aci = m.ac_Aci; a.xy = m.aa_xy; a.edge = m.aa_edge;
-      const size_t bytes = (size_t)m.nAcp * sizeof(double);
-      int rc_ = ufm_arena_alloc(h, bytes, (void **)&m.ac_Np);
-      if (rc_) return rc_;
-      UFM_CUDA(cudaMemset(m.ac_Np, 0, bytes));
-      for (int k = 0; k < 4; k++) {
-        double **q3[] = {&m.ac_Nx[k], &m.ac_Ny[k], &m.ac_No[k]};
-        for (double **q : q3) { if ((rc_ = ufm_arena_alloc(h, bytes, (void **)q))) return rc_; UFM_CUDA(cudaMemset(*q, 0, bytes)); }
-        a.Nx[k] = m.ac_Nx[k]; a.Ny[k] = m.ac_Ny[k]; a.No[k] = m.ac_No[k];
-      }
-      a.Np = m.ac_Np;
-      UFM_CUDA(cudaDeviceSynchronize());
-      k_derive_nf_Ac<<<(E + 255) / 256, 256, 0, h->stream>>>(a);
-      UFM_CUDA(cudaGetLastError());
-      h->cnt.kernel_launches++;
-      UFM_CUDA(cudaStreamSynchronize(h->stream));
-    }
-  }
   UP(aa_r2d, m.aa_ref2dev); UP(aa_d2r, m.aa_dev2ref); UP(ac_r2d, m.ac_ref2dev); UP(ac_d2r, m.ac_dev2ref);
   UP(m_r2d, m.m_ref2dev); UP(m_d2r, m.m_dev2ref);
 
