@@ -358,7 +358,7 @@ def algorithmic_bytes(m):
 def kernel_rooflines(g, m, torch, stream, peak, reps=12):
     """Every per-step routine launched `reps` times round robin (so each one finds the L2 full of the others' data: ~2 GB go through
     between two launches of the same routine), each call bracketed by CUDA events on the library's stream, nothing else in between."""
-    calls = {"geom": lambda: g.update_general_ice_model_data(0.0), "sia": g.solve_SIA, "thk": lambda: g.calculate_ice_thickness_change(0.0),
+    calls = {"geom": lambda: g.update_general_ice_model_data(0.0), "sia": g.solve_SIA, "thk": lambda: g.calculate_ice_thickness_change(1e-3),
              "cfl": g.determine_timesteps, "visc": g.ssa_viscosity}
     g.update_general_ice_model_data(0.0); g.ssa_prepare()
     ev = {k: [] for k in calls}
@@ -375,7 +375,7 @@ def kernel_rooflines(g, m, torch, stream, peak, reps=12):
         ms = float(np.median([a.elapsed_time(b) for a, b in pairs]))
         gbs = B[k] / (ms * 1e-3) / 1e9
         out[k] = {"ms": ms, "algorithmic_bytes": B[k], "achieved_GBps": gbs, "frac": gbs / peak}
-    out["how"] = (f"median of {reps} launches per routine, round robin, CUDA events around each call on the library's stream; thk at dt = 0 (same reads and writes); "
+    out["how"] = (f"median of {reps} launches per routine, round robin, CUDA events around each call on the library's stream; thk with dt = 1e-3 yr (a real update: in-fluxes gather their source's out-flux factor, which a dt of 0 would skip); "
                   "cfl includes its 3-scalar device-to-host read; visc = viscosity + RN partials + sliding term + linear-system setup in one launch (+ the 64-CTA sum)")
     return out
 
@@ -751,13 +751,13 @@ def run_ours(args):
         if part:
             peak, peak_src = peak * world, peak_src + f" x {world} GPUs"
         traffic, traffic_src = None, None
-        tf = os.path.join(ROOT, "profiles", "sor_traffic_r01.json")
+        tf = os.path.join(ROOT, "profiles", "sor_traffic_r02.json")
         if os.path.exists(tf):
             tj = json.load(open(tf))
             if abs(tj["nVAaAc"] - m.nVAaAc) <= 0.02 * m.nVAaAc and int(args.exact_xy) == 1:
                 # ncu dram__bytes_read+write per SOR iteration x mean iterations per launch of this run
                 traffic = tj["dram_bytes_per_iteration"] * cnt.sor_iterations / max(cnt.sor_launches, 1)
-                traffic_src = "ncu --set full capture of 10 forced iterations (profiles/sor_traffic_r01.json) scaled to this run's mean iterations per launch"
+                traffic_src = "ncu --set full capture of 10 forced iterations (profiles/sor_traffic_r02.json) scaled to this run's mean iterations per launch"
         t_iter = cnt.sor_ms * 1e-3 / max(cnt.sor_iterations, 1)
         achieved = cnt.sor_bytes_per_iteration / t_iter / 1e9 if cnt.sor_iterations else 0.0
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

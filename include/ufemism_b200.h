@@ -243,6 +243,9 @@ int ufm_pow_mode(ufm_handle *h);
 /* host: the same evaluation (libm's pow off its main path); for tests */
 double ufm_pow_host(double x, double y);
 double ufm_tan_host(double x);
+/* host twin of the device's x / n for a vertex degree n (k_sia_aa: map_Ac_to_Aa, src/mesh_ArakawaC_module.f90:770-791, divides every term
+ * by nC(vi)): one multiply and two fused multiply-adds with 1.0 / n, the bits of the IEEE division; for tests */
+double ufm_div_small_host(double x, int n);
 
 /* Page-lock a host array (e.g. one of the Fortran host's MPI shared-memory windows, src/parallel_module.f90:144-160) so that
  * ufm_state_upload / ufm_state_download DMA it directly instead of bouncing through a staging buffer.  Optional. */

@@ -324,8 +324,9 @@ void ora_calculate_ice_thickness_change(const ora_mesh *m, ora_ice *ice, const o
       A1(ice->Hi_prev, vi) = A1(ice->Hi, vi);
       A1(ice->Hi, vi) = A1(ice->Hi, vi) + (A1(ice->dHi_dt, vi) * dt);
     }
-    /* boundary conditions, :189-228 (identical in the benchmark and the realistic branch) */
-    for (int vi = r.v1; vi <= r.v2; vi++) if (A1(m->edge_index, vi) > 0) A1(ice->Hi, vi) = 0.0;
+    /* boundary conditions, :189-228 (identical in the benchmark and the realistic branch; 'SSA_icestream' has none, :206) */
+    if (c->benchmark != ORA_BM_SSA_ICESTREAM)
+      for (int vi = r.v1; vi <= r.v2; vi++) if (A1(m->edge_index, vi) > 0) A1(ice->Hi, vi) = 0.0;
     SYNC
     for (int vi = r.v1; vi <= r.v2; vi++) if (A1(ice->mask_noice, vi) == 1) A1(ice->Hi, vi) = 0.0;
     SYNC

@@ -533,3 +533,25 @@ def test_every_environment_switch_is_documented():
     assert len(names) >= 12
     for n in sorted(names):
         assert n in doc, f"{n} is read by the library but missing from INTEGRATION.md"
+
+
+def test_division_by_a_vertex_degree_has_the_bits_of_the_ieee_division(lib):
+    """k_sia_aa divides every term of map_Ac_to_Aa's average by nC(vi) (src/mesh_ArakawaC_module.f90:770-791); the device does it with
+    1.0 / nC and two fused multiply-adds (csrc/ufm_pow.cuh: ufm_div_small).  The host twin of that function must equal the division
+    bit for bit: random doubles of every magnitude, velocity-sized ones, numerators a few ulp off an exact multiple, zeros and tiny ones."""
+    import ctypes
+
+    import numpy as np
+
+    f = np.vectorize(lambda x, n: lib.ufm_div_small_host(ctypes.c_double(x), int(n)), otypes=[np.float64])
+    rng = np.random.default_rng(5)
+    for n in range(1, 18):
+        bits = rng.integers(0, 2**64, 3000, dtype=np.uint64).view(np.float64)
+        anyx = bits[np.isfinite(bits)]
+        vel = rng.normal(0, 1.0, 3000) * 10.0 ** rng.uniform(-12, 6, 3000)
+        q = rng.uniform(1, 2, 3000) * 2.0 ** rng.integers(-20, 20, 3000)
+        near = ((q * n).view(np.int64) + rng.integers(-3, 4, 3000)).view(np.float64) * rng.choice([-1.0, 1.0], 3000)
+        special = np.array([0.0, -0.0, 5e-324, -5e-324, 1e-300, -1e-290, 1e-280, 2.2250738585072014e-308, 1.7976931348623157e308, -1.7976931348623157e308])
+        x = np.concatenate([anyx, vel, near, special])
+        got, want = f(x, n), x / float(n)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (n, x[got.view(np.uint64) != want.view(np.uint64)][:5])

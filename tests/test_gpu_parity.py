@@ -61,9 +61,15 @@ def test_solve_SIA(mesh_10k, name):
     assert (o["D_SIA_Ac"] <= 0).all()  # negative by construction
 
 
-@pytest.mark.parametrize("name,dt", [("halfar", 0.05), ("halfar", 0.0), ("mismip", 0.5), ("mismip", 40.0)])
-def test_thickness_update_bit_exact(mesh_10k, name, dt):
-    st = scenario(mesh_10k, name)
+@pytest.mark.parametrize("name,dt", [("halfar", 0.05), ("halfar", 0.0), ("mismip", 0.5), ("mismip", 40.0), ("icestream_as_coded", 0.5)])
+@pytest.mark.parametrize("edge_pass", ["1", "0"])
+def test_thickness_update_bit_exact(mesh_10k, name, dt, edge_pass, monkeypatch):
+    monkeypatch.setenv("UFM_THK_EDGE", edge_pass)   # 1: flux once per staggered vertex (k_thk_flux), 0: from the velocities in both vertex passes
+    if name == "icestream_as_coded":
+        # 'SSA_icestream' is the one benchmark without a thickness boundary condition (ice_dynamics_module.f90:206): edge vertices keep their ice
+        st = dict(scenario(mesh_10k, "icestream"), benchmark="SSA_icestream")
+    else:
+        st = scenario(mesh_10k, name)
     if name == "mismip":
         st["SMB_year"] = np.where(np.hypot(mesh_10k.V[:, 0], mesh_10k.V[:, 1]) > 400e3, -3.0, 0.3)  # melt-all + limiter branches
     o, g = make_oracle(mesh_10k, st), make_gpu(mesh_10k, st)
@@ -84,6 +90,8 @@ def test_thickness_update_bit_exact(mesh_10k, name, dt):
         assert_bits_equal(g.download(f), o[f], f)
     if dt > 0 and name == "mismip":
         assert (o["Hi"] >= -1e-9).all() and (o["Hi"] == 0).any()  # limiter keeps H >= 0 up to rounding
+    edge = (mesh_10k.edge_index > 0) & (noice == 0)
+    assert (o["Hi"][edge] > 0).any() if name == "icestream_as_coded" else (o["Hi"][edge] == 0).all()
 
 
 def _ssa_setup_pair(mesh, nthreads=1, **params):

@@ -1,0 +1,25 @@
+#!/bin/bash
+# per-step kernels after the degree-division and edge-flux changes: parity tests, timings (both thickness variants), ncu captures
+set -u
+OUT=gpurun_out; TAG=r02s; mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "thickness or SIA or run_model or device_loop or trajectory or reference_source or hybrid" > $OUT/${TAG}_tests.log 2>&1; tail -3 $OUT/${TAG}_tests.log
+for e in 1 0; do
+  UFM_THK_EDGE=$e timeout 300 python tools/sor_probe.py --iters 5 --reps 1 --others > $OUT/${TAG}_others_edge$e.json 2> $OUT/${TAG}_others_edge$e.err; cut -c1-900 $OUT/${TAG}_others_edge$e.json
+done
+capture() {
+  local name=$1 rx=$2 skip=$3; shift 3
+  timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$rx" -s $skip -c 1 -f -o $OUT/${name}_${TAG} "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1
+  echo "$name rc=$?"
+  python tools/ncu_raw_summary.py $OUT/${name}_${TAG}.ncu-rep > $OUT/${name}_${TAG}_raw.txt 2>/dev/null
+}
+P="python tools/sor_probe.py --iters 5 --reps 1 --others"
+capture sia_ac ".*k_sia_ac\\(.*" 2 $P
+capture sia_aa ".*k_sia_aa.*" 2 $P
+capture thk_flux ".*k_thk_flux.*" 2 $P
+capture thk1 ".*k_thk<1, true>.*" 2 $P
+capture thk2 ".*k_thk<2, true>.*" 2 $P
+export UFM_THK_EDGE=0
+capture thk1_old ".*k_thk<1, false>.*" 2 $P
+capture thk2_old ".*k_thk<2, false>.*" 2 $P
+ls $OUT | grep $TAG

@@ -107,7 +107,7 @@ def main():
                 fn()
             g.synchronize()
             return (time.perf_counter() - t) / n * 1e3
-        out["ms"] = {"geom": tm(lambda: g.update_general_ice_model_data(0.0)), "sia": tm(g.solve_SIA), "thk": tm(lambda: g.calculate_ice_thickness_change(0.0)),
+        out["ms"] = {"geom": tm(lambda: g.update_general_ice_model_data(0.0)), "sia": tm(g.solve_SIA), "thk": tm(lambda: g.calculate_ice_thickness_change(1e-3)),
                      "cfl": tm(g.determine_timesteps), "prepare": tm(g.ssa_prepare), "visc": tm(g.ssa_viscosity), "setup": tm(g.ssa_sliding_and_setup),
                      "sor_1iter_launch": tm(lambda: g.ssa_sor(max_inner=1, force_iters=True)), "finish": tm(g.ssa_finish)}
     if a.thermo and world == 1:

@@ -372,12 +372,13 @@ __global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
     const int v = s * 32 + lane;
     const int n = a.deg[v];
     if (n == UFM_DEG_PAD || !UFM_OWNED(a.own, v, a.rank)) continue;
-    const double dn = (double)n;
+    const double dn = (double)n, rn = 1.0 / dn;
     double u = 0.0, vv = 0.0, dd = 0.0;
     for (int c = 0; c < w; c++) {
       if (c < n) {
         const int ac = a.iAci[o + (long long)c * 32 + lane] & 0x7fffffff;
-        u = u + a.Ux[ac] / dn; vv = vv + a.Uy[ac] / dn; dd = dd + a.D[ac] / dn;
+        // term / nC(vi), term by term as the reference does; ufm_div_small = the same bits without 3 n divisions per vertex
+        u = u + ufm_div_small(a.Ux[ac], dn, rn); vv = vv + ufm_div_small(a.Uy[ac], dn, rn); dd = dd + ufm_div_small(a.D[ac], dn, rn);
       }
     }
     a.U_SIA[v] = u; a.V_SIA[v] = vv; a.D_SIA[v] = dd;
@@ -398,7 +399,9 @@ struct ThkArgs {
   const double *dt_dev;              // device-driven loop: the time step lives on the device (else NULL)
   const int *gate;
   const unsigned char *own; int rank;
+  int clamp_edge;                    // 0 only for 'SSA_icestream': no boundary condition on the thickness (:189-206)
   double *factor, *smb;              // pass 1 out / pass 2 in
+  const double *flux;                // edge pass out (EDGE variants): h_upwind * Upar * Cw per Ac vertex
   double *Hi_new, *dHi_dt;           // pass 2 out
 };
 __device__ __forceinline__ double thk_entry(const ThkArgs &a, long long e, int v, double hv, int *other)
@@ -413,7 +416,23 @@ __device__ __forceinline__ double thk_entry(const ThkArgs &a, long long e, int v
   *other = j;
   return first ? -dVi : dVi;
 }
-template <int PASS>
+// Edge pass (UFM_THK_EDGE=1): the flux of a connection is the same number seen from either end (:66-113 computes it once per Ac vertex
+// and stores it twice with opposite signs), so one thread per Ac vertex evaluates h_upwind * Upar * Cw -- the first two of the three
+// multiplications, dt follows in the vertex passes -- and the vertex passes gather one value per connection instead of four.
+__global__ void __launch_bounds__(256) k_thk_flux(int nAc, const int4 *__restrict__ Aci, const double *__restrict__ UpSIA, const double *__restrict__ UpSSA,
+                                                  const double *__restrict__ Cw, const double *__restrict__ Hi, double *__restrict__ flux,
+                                                  const int *gate, const unsigned char *__restrict__ own_aa, int rank)
+{
+  UFM_GATE(gate);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nAc) return;
+  const int4 v = Aci[i];
+  if (own_aa && own_aa[v.x] != rank && own_aa[v.y] != rank) return;   // partitioned: the connections of the vertices this rank updates
+  const double Upar = UpSIA[i] + UpSSA[i];
+  const double h_up = (Upar > 0.0) ? Hi[v.x] : Hi[v.y];
+  flux[i] = h_up * Upar * Cw[i];
+}
+template <int PASS, bool EDGE>
 __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
 {
   UFM_GATE(a.gate);
@@ -432,7 +451,9 @@ __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
       for (int c = 0; c < w; c++) {
         if (c < n) {
           int j;
-          const double en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
+          double en;
+          if (EDGE) { const int ia = a.iAci[o + (long long)c * 32 + lane]; const double dVi = a.flux[ia & 0x7fffffff] * a.dt; en = ia < 0 ? -dVi : dVi; }
+          else en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
           if (!(en > 0.0)) Vi_out = Vi_out - en;
         }
       }
@@ -448,7 +469,14 @@ __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
       for (int c = 0; c < w; c++) {
         if (c < n) {
           int j;
-          double en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
+          double en;
+          if (EDGE) {
+            const long long e = o + (long long)c * 32 + lane;
+            const int ia = a.iAci[e];
+            j = a.C[e];
+            const double d = a.flux[ia & 0x7fffffff] * a.dt;
+            en = ia < 0 ? -d : d;
+          } else en = thk_entry(a, o + (long long)c * 32 + lane, v, hv, &j);
           if (en < 0.0) { if (fv < 1.0) en = en * fv; }
           else if (en > 0.0) { const double fj = a.factor[j]; if (fj < 1.0) en = -((-en) * fj); }
           dVi = dVi + en;
@@ -457,7 +485,7 @@ __global__ void __launch_bounds__(256) k_thk(ThkArgs a)
       double dh = (dVi + a.smb[v]) / (Av * a.dt);
       if (a.dt == 0.0) dh = 0.0;
       double hn = hv + (dh * a.dt);
-      if (a.edge[v] > 0) hn = 0.0;
+      if (a.clamp_edge && a.edge[v] > 0) hn = 0.0;
       if (a.noice[v] == 1) hn = 0.0;
       a.dHi_dt[v] = dh; a.Hi_new[v] = hn;
     }
@@ -824,14 +852,23 @@ int ufm_k_thickness(ufm_handle *h, double dt)
   a.UpSIA = s.U_SIA_Ac[2]; a.UpSSA = s.U_SSA_Ac[2]; a.Hi = s.Hi; a.SMB = s.SMB_year; a.BMB = s.BMB; a.noice = s.mask_noice; a.dt = dt;
   a.factor = s.thk_factor; a.smb = s.thk_smb; a.Hi_new = s.Hi_alt; a.dHi_dt = s.dHi_dt;
   a.dt_dev = h->dt_dev; a.gate = h->gate[0]; a.own = m.part_step ? m.own_aa : nullptr; a.rank = m.rank;
+  a.clamp_edge = h->P.benchmark != UFM_BM_SSA_ICESTREAM;
   int g = grid_for((long long)m.aa.n_slices * 32, 256);
-  k_thk<1><<<g, 256, 0, h->stream>>>(a);
+  const char *edge_env = getenv("UFM_THK_EDGE");      // read per call: A/B runs and tests switch it inside one process
+  const bool edge = !edge_env || atoi(edge_env) != 0;
+  a.flux = s.thk_flux;
+  if (edge) {
+    k_thk_flux<<<grid_for(m.nAc, 256), 256, 0, h->stream>>>(m.nAc, m.ac_Aci, a.UpSIA, a.UpSSA, a.Cw, a.Hi, s.thk_flux, a.gate, a.own, a.rank);
+    h->cnt.kernel_launches++;
+    k_thk<1, true><<<g, 256, 0, h->stream>>>(a);
+  } else k_thk<1, false><<<g, 256, 0, h->stream>>>(a);
   if (m.part_step) {   // the out-flux factors of the neighbour strips' vertices scale the fluxes that come in from them
     double *arr[1] = {s.thk_factor};
     int rc_x = ufm_halo_exchange(h, 0, 1, arr);
     if (rc_x) return rc_x;
   }
-  k_thk<2><<<g, 256, 0, h->stream>>>(a);
+  if (edge) k_thk<2, true><<<g, 256, 0, h->stream>>>(a);
+  else k_thk<2, false><<<g, 256, 0, h->stream>>>(a);
   h->cnt.kernel_launches += 2;
   // Hi_prev = Hi ; Hi = new  (pointer swap: the old buffer IS Hi_prev)
   double *t = s.Hi; s.Hi = s.Hi_alt; s.Hi_alt = t;

@@ -208,7 +208,7 @@ struct DevState {
   double *Hi = nullptr, *Hi_alt = nullptr, *Hb = nullptr, *SL = nullptr, *Hs = nullptr, *dHb_dt = nullptr, *dHi_dt = nullptr, *dHs_dt = nullptr;
   double *dHi_dx = nullptr, *dHi_dy = nullptr, *dHs_dx = nullptr, *dHs_dy = nullptr, *dHs_dx_shelf = nullptr, *dHs_dy_shelf = nullptr;
   double *U_SIA = nullptr, *V_SIA = nullptr, *D_SIA = nullptr, *U_SSA = nullptr, *V_SSA = nullptr, *SMB_year = nullptr, *BMB = nullptr;
-  double *thk_factor = nullptr, *thk_smb = nullptr;
+  double *thk_factor = nullptr, *thk_smb = nullptr, *thk_flux = nullptr;
   double *U_3D = nullptr, *V_3D = nullptr;  // (nV,nZ) device layout k-major: [k*nVp + v]
   double *Ti = nullptr;                     // (nV,nZ) englacial temperature, k-major (realistic flow factor or thermodynamics)
   double *Ti_new = nullptr, *W_3D = nullptr;  // (nV,nZ) thermodynamics

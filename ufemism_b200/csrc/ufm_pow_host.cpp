@@ -176,6 +176,12 @@ extern "C" int ufm_powtab_build(UfmPowTab *out)
   return 0;
 }
 
+extern "C" double ufm_div_small_host(double x, int n)
+{
+  const double d = (double)n;
+  return ufm_div_small(x, d, 1.0 / d);
+}
+
 extern "C" double ufm_tan_host(double x)
 {
   if (g_host_state == 0) g_host_state = ufm_powtab_build(&g_host_tab) == 0 ? 1 : -1;

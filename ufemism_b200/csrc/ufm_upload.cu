@@ -1093,7 +1093,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     ZE(nv * nz, s.Ti_new); ZE(nv * nz, s.W_3D); ZE(nv, s.GHF); ZE(nv * 12, s.T2m); ZE(nv, s.fric_heat);
   }
   ZE(nv, s.mask_noice); ZE(nv, s.mbits);
-  double **ac_d[] = {&s.Hi_Ac, &s.Hb_Ac, &s.SL_Ac, &s.Hs_Ac, &s.dHs_dx_shelf_Ac, &s.dHs_dy_shelf_Ac, &s.D_SIA_Ac, &s.Qabs_GL_Ac, &s.Qp_GL_Ac};
+  double **ac_d[] = {&s.Hi_Ac, &s.Hb_Ac, &s.SL_Ac, &s.Hs_Ac, &s.dHs_dx_shelf_Ac, &s.dHs_dy_shelf_Ac, &s.D_SIA_Ac, &s.Qabs_GL_Ac, &s.Qp_GL_Ac, &s.thk_flux};
   for (double **p : ac_d) ZE(na, *p);
   for (int k = 0; k < 4; k++) { ZE(na, s.dHi_Ac[k]); ZE(na, s.dHb_Ac[k]); ZE(na, s.dHs_Ac[k]); ZE(na, s.dSL_Ac[k]); ZE(na, s.U_SIA_Ac[k]); ZE(na, s.U_SSA_Ac[k]); }
   ZE(na, s.mbits_Ac);
