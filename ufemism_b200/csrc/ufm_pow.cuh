@@ -23,7 +23,7 @@
 // division per vertex instead of one per neighbour: the averages of map_Ac_to_Aa divide every term by the vertex degree).
 // q0 = RN(x rd) is within 2 ulp of x/d; e = x - d q0 is exact in an fma; q0 + e rd differs from x/d by <= 2^-105 |x/d|, while for a divisor
 // of at most 5 significant bits x/d is never closer than 2^-59 |x/d| to a rounding boundary -> RN(q0 + e rd) = RN(x/d).  Tiny and zero
-// numerators (underflow in e, the sign of zero) take the division itself.  Checked against the division on 10^9 numerators per
+// numerators (underflow in e) take the division itself, a zero is returned as it is (d > 0; zeros are common: ice-free cells).  Checked against the division on 10^9 numerators per
 // divisor 1..17 when it was written and in tests/test_abi.py on every run (ufm_div_small_host is this function on the host).
 #ifdef __CUDACC__
 __host__ __device__ __forceinline__
@@ -32,9 +32,11 @@ static inline
 #endif
 double ufm_div_small(const double x, const double d, const double rd)
 {
-  if (!(fabs(x) >= 1e-280)) return x / d;
   const double q0 = x * rd;
-  return fma(fma(-q0, d, x), rd, q0);
+  double r = fma(fma(-q0, d, x), rd, q0);
+  if (x == 0.0) r = x;                       // +-0 / d = +-0 (d > 0); the fma chain would turn -0 into +0
+  else if (!(fabs(x) >= 1e-280)) r = x / d;  // underflow territory (and NaN): the division itself; never taken by model fields
+  return r;
 }
 
 struct UfmPowTab {

@@ -425,6 +425,48 @@ extern "C" int ufm_partition_halo_counts(const ufm_mesh_desc *d, int nranks, int
 //                 puts the rows a row depends on at nearly the same relative position of the previous colour block, which a sweep
 //                 without grid barriers between the colours needs: tools/sor_dataflow_analysis.py).
 // Results never depend on the order inside a colour block.  Host only; checked against numpy by tests/test_abi.py.
+// Stage 1 of the default row order, independent of the colouring: rows by (owner, boundary, degree, Morton, index).  One packed key per
+// row instead of four indirections per comparison.
+static void ufm_row_presort(int M, const unsigned char *owner, const unsigned char *isb, const unsigned char *degv, const uint32_t *mort, std::vector<int> &pre)
+{
+  pre.resize(M);
+  std::iota(pre.begin(), pre.end(), 0);
+  std::vector<uint64_t> key(M);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < M; i++) key[i] = ((uint64_t)owner[i] << 42) | ((uint64_t)(isb[i] != 0) << 41) | ((uint64_t)degv[i] << 32) | (uint64_t)mort[i];
+  __gnu_parallel::sort(pre.begin(), pre.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+}
+// Stage 2: a stable distribution of the pre-sorted rows over the buckets (block, owner, boundary, late).  Inside a bucket owner and
+// boundary are constant, so the rows keep the (degree, Morton, index) order of stage 1: the result is the lexicographic order by
+// (block, owner, boundary, late, degree, Morton, index).
+static void ufm_row_order_from_presorted(int M, const std::vector<int> &pre, const unsigned char *blkv, const unsigned char *owner, const unsigned char *isb,
+                                         const unsigned char *late, std::vector<int> &m_order)
+{
+  int P = 1;
+  for (int i = 0; i < M; i++) P = std::max(P, (int)owner[i] + 1);
+  auto bucket = [&](int i) { return (((int)blkv[i] * P + (int)owner[i]) * 2 + (isb[i] != 0)) * 2 + (late[i] != 0); };
+  const int nb = 256 * P * 4;
+  const int T = std::max(1, omp_get_max_threads());
+  std::vector<size_t> cnt((size_t)T * nb, 0);
+  // per-thread counts over contiguous pieces of the pre-sorted list, then a bucket-major / thread-minor prefix sum: stable
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < T; t++) {   // T pieces, however many threads actually run
+    const size_t lo = (size_t)M * t / T, hi = (size_t)M * (t + 1) / T;
+    size_t *c = cnt.data() + (size_t)t * nb;
+    for (size_t k = lo; k < hi; k++) c[bucket(pre[k])]++;
+  }
+  size_t run = 0;
+  for (int b = 0; b < nb; b++)
+    for (int t = 0; t < T; t++) { const size_t c = cnt[(size_t)t * nb + b]; cnt[(size_t)t * nb + b] = run; run += c; }
+  m_order.resize(M);
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < T; t++) {
+    const size_t lo = (size_t)M * t / T, hi = (size_t)M * (t + 1) / T;
+    size_t *c = cnt.data() + (size_t)t * nb;
+    for (size_t k = lo; k < hi; k++) { const int i = pre[k]; m_order[c[bucket(i)]++] = i; }
+  }
+}
+
 static void ufm_row_order_impl(int M, const unsigned char *blkv, const unsigned char *owner, const unsigned char *isb, const unsigned char *late,
                                const unsigned char *degv, const uint32_t *mort, const double *X, int n_bands, int deg_window, std::vector<int> &m_order)
 {
@@ -442,13 +484,11 @@ static void ufm_row_order_impl(int M, const unsigned char *blkv, const unsigned 
     return false;
   };
   if (n_bands == 0) {
-    // one packed key per row (block | owner | boundary | late | degree | Morton: 49 bits) instead of six indirections per comparison; ties
-    // (equal keys) keep index order, i.e. the order a stable sort of the separate keys gives
-    std::vector<uint64_t> key(M);
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < M; i++)
-      key[i] = ((uint64_t)blkv[i] << 46) | ((uint64_t)owner[i] << 42) | ((uint64_t)(isb[i] != 0) << 41) | ((uint64_t)(late[i] != 0) << 40) | ((uint64_t)degv[i] << 32) | (uint64_t)mort[i];
-    __gnu_parallel::sort(m_order.begin(), m_order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+    // the default order (block, owner, boundary, late, degree, Morton, index) in two stages, so that ufm_mesh_upload can run the expensive
+    // one while the five-colouring -- which decides block and late -- is still being computed on another thread
+    std::vector<int> pre;
+    ufm_row_presort(M, owner, isb, degv, mort, pre);
+    ufm_row_order_from_presorted(M, pre, blkv, owner, isb, late, m_order);
     return;
   }
   double x0 = 1e300, x1 = -1e300;
@@ -742,6 +782,56 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       UFM_CUDA(cudaStreamSynchronize(h->stream));
     }
   }
+  // ---- colour-independent half of the AaAc row order: degree, domain edge, owner strip, partition boundary, and the rows sorted by
+  //      (owner, boundary, degree, Morton) -- the colouring below only distributes them over the colour blocks ----
+  std::vector<unsigned char> is_edge(M), degv(M);
+  {
+    int bad_row0 = 0;
+#pragma omp parallel for schedule(static)
+    for (int ai = 0; ai < M; ai++) {
+      is_edge[ai] = ai < N ? (d->edge_index[ai] > 0) : (d->edge_index_Ac[ai - N] > 0);
+      const int n = d->nCAaAc[ai];
+      degv[ai] = (unsigned char)(n < 0 ? 0 : (n > 255 ? 255 : n));
+      if (n < 1 || n > W) bad_row0 = ai + 1;
+    }
+    if (bad_row0) return ufm_set_error(-2, "ufm_mesh_upload: nCAaAc(%d) = %d out of range", bad_row0, d->nCAaAc[bad_row0 - 1]);
+    int bad_c = 0;
+#pragma omp parallel for schedule(static)
+    for (int ai = 0; ai < M; ai++)
+      for (int c = 1; c <= degv[ai]; c++) {
+        const int ac = F2(d->CAaAc, ai + 1, c, ldM);
+        if (ac < 1 || ac > M) bad_c = ai + 1;
+      }
+    if (bad_c) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
+  }
+  // owner rank of every AaAc row: x-strips balanced by row count (cf. partition_domain_x_balanced,
+  // src/mesh_help_functions_module.f90:1337-1404, which the reference uses for mesh generation)
+  const int P = h->part_n;
+  m.P = P; m.rank = h->part_rank;
+  std::vector<unsigned char> owner(M, 0);
+  ufm_partition_owners_impl(X, P, owner);
+  // rows that read a row owned by another rank ("boundary" rows of the partition) are swept last in every phase, so
+  // that the wait for the peers' pushes of the previous phase hides behind the interior rows
+  std::vector<unsigned char> isb(M, 0);
+  if (P > 1) {
+#pragma omp parallel for schedule(static)
+    for (int ai = 0; ai < M; ai++)
+      for (int c = 1; c <= degv[ai]; c++)
+        if (owner[F2(d->CAaAc, ai + 1, c, ldM) - 1] != owner[ai]) { isb[ai] = 1; break; }
+  }
+  const char *env_order = getenv("UFM_ROW_ORDER");
+  {
+    const char *e = getenv("UFM_SOR_DATAFLOW");
+    m.df_layout = P == 1 && e && atoi(e) != 0;
+  }
+  // row order inside the colour blocks: (degree, Morton), or the experimental x-band order (UFM_ROW_ORDER=bands:<n>[:<window>])
+  int n_bands = m.df_layout ? 64 : 0, deg_window = 4096;
+  if (env_order) {
+    if (sscanf(env_order, "bands:%d:%d", &n_bands, &deg_window) < 1) n_bands = m.df_layout ? 64 : 0;
+  }
+  std::vector<int> m_presorted;
+  if (n_bands == 0) ufm_row_presort(M, owner.data(), isb.data(), degv.data(), mort.data(), m_presorted);
+  lap("AaAc rows pre-sorted");
   // ---- the five-colouring is needed from here on (ufm_mesh_upload_primary: wait for the thread that computes it) ----
   if (g_ufm_colour_wait) { const int rc_w = (*g_ufm_colour_wait)(); if (rc_w) return rc_w; }
   lap("wait for the five-colouring");
@@ -755,43 +845,20 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       colour[ai - 1] = c;
     }
   }
-  std::vector<unsigned char> is_edge(M), degv(M);
-  int bad_row = 0, bad_kind = 0;   // first offending vertex is not needed: any one will do for the message
+  int bad_row = 0;
 #pragma omp parallel for schedule(static)
-  for (int ai = 0; ai < M; ai++) {
-    is_edge[ai] = ai < N ? (d->edge_index[ai] > 0) : (d->edge_index_Ac[ai - N] > 0);
-    const int n = d->nCAaAc[ai];
-    degv[ai] = (unsigned char)(n < 0 ? 0 : (n > 255 ? 255 : n));
-    if (colour[ai] == 0) { bad_row = ai + 1; bad_kind = 1; }
-    else if (n < 1 || n > W) { bad_row = ai + 1; bad_kind = 2; }
-  }
-  if (bad_kind == 1) return ufm_set_error(-2, "ufm_mesh_upload: AaAc vertex %d has no colour", bad_row);
-  if (bad_kind == 2) return ufm_set_error(-2, "ufm_mesh_upload: nCAaAc(%d) = %d out of range", bad_row, d->nCAaAc[bad_row - 1]);
+  for (int ai = 0; ai < M; ai++) if (colour[ai] == 0) bad_row = ai + 1;
+  if (bad_row) return ufm_set_error(-2, "ufm_mesh_upload: AaAc vertex %d has no colour", bad_row);
   // the sweep relies on same-coloured vertices being non-adjacent (check_solution, mesh_five_colour_module.f90:318-343)
   int bad_a = 0, bad_b = 0;
 #pragma omp parallel for schedule(static)
   for (int ai = 0; ai < M; ai++)
     for (int c = 1; c <= degv[ai]; c++) {
       const int ac = F2(d->CAaAc, ai + 1, c, ldM);
-      if (ac < 1 || ac > M) { bad_a = ai + 1; bad_b = -1; }
-      else if (colour[ac - 1] == colour[ai]) { bad_a = ai + 1; bad_b = ac; }
+      if (colour[ac - 1] == colour[ai]) { bad_a = ai + 1; bad_b = ac; }
     }
-  if (bad_b == -1) return ufm_set_error(-2, "ufm_mesh_upload: CAaAc out of range");
   if (bad_a) return ufm_set_error(-2, "ufm_mesh_upload: invalid five-colouring (vertices %d, %d)", bad_a, bad_b);
   lap("colour + validity checks");
-  // owner rank of every AaAc row: x-strips balanced by row count (cf. partition_domain_x_balanced,
-  // src/mesh_help_functions_module.f90:1337-1404, which the reference uses for mesh generation)
-  const int P = h->part_n;
-  m.P = P; m.rank = h->part_rank;
-  std::vector<unsigned char> owner(M, 0);
-  ufm_partition_owners_impl(X, P, owner);
-  // rows that read a row owned by another rank ("boundary" rows of the partition) are swept last in every phase, so
-  // that the wait for the peers' pushes of the previous phase hides behind the interior rows
-  std::vector<unsigned char> isb(M, 0);
-  if (P > 1)
-    for (int ai = 0; ai < M; ai++)
-      for (int c = 1; c <= degv[ai]; c++)
-        if (owner[F2(d->CAaAc, ai + 1, c, ldM) - 1] != owner[ai]) { isb[ai] = 1; break; }
   std::vector<int> m_order;
   auto blk = [&](int ai) { return is_edge[ai] ? 6 : colour[ai]; };
   // single-GPU layout: the colour-5 rows that the Neumann pass reads (non-edge rows adjacent to a domain-edge row) lead
@@ -801,26 +868,21 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // about the same relative position of their blocks
   std::vector<unsigned char> late(M, 1);
   int n_adj5 = 0;
-  const char *env_order = getenv("UFM_ROW_ORDER");
-  {
-    const char *e = getenv("UFM_SOR_DATAFLOW");
-    m.df_layout = P == 1 && e && atoi(e) != 0;
-  }
-  if (P == 1 && !m.df_layout)
+  if (P == 1 && !m.df_layout) {
+#pragma omp parallel for schedule(static) reduction(+ : n_adj5)
     for (int ai = 0; ai < M; ai++) {
       if (colour[ai] != 5 || is_edge[ai]) continue;
       for (int c = 1; c <= degv[ai]; c++)
         if (is_edge[F2(d->CAaAc, ai + 1, c, ldM) - 1]) { late[ai] = 0; n_adj5++; break; }
     }
-  // row order inside the colour blocks: (degree, Morton), or the experimental x-band order (UFM_ROW_ORDER=bands:<n>[:<window>])
-  int n_bands = m.df_layout ? 64 : 0, deg_window = 4096;
-  if (env_order) {
-    if (sscanf(env_order, "bands:%d:%d", &n_bands, &deg_window) < 1) n_bands = m.df_layout ? 64 : 0;
   }
   {
     std::vector<unsigned char> blkv(M);
+#pragma omp parallel for schedule(static)
     for (int ai = 0; ai < M; ai++) blkv[ai] = (unsigned char)blk(ai);
-    ufm_row_order_impl(M, blkv.data(), owner.data(), isb.data(), late.data(), degv.data(), mort.data(), X.data(), n_bands, deg_window, m_order);
+    if (n_bands == 0) ufm_row_order_from_presorted(M, m_presorted, blkv.data(), owner.data(), isb.data(), late.data(), m_order);
+    else ufm_row_order_impl(M, blkv.data(), owner.data(), isb.data(), late.data(), degv.data(), mort.data(), X.data(), n_bands, deg_window, m_order);
+    std::vector<int>().swap(m_presorted);
   }
   std::vector<int> m_r2d(M), m_d2r;
   m_d2r.reserve((size_t)M + 12 * (size_t)P * UFM_CHUNK);
@@ -850,6 +912,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
   // ---- AaAc sliced ELL ----
   {
     std::vector<unsigned char> deg(m.Mp, UFM_DEG_PAD);
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < m.Mp; p++) if (m_d2r[p] >= 0) deg[p] = degv[m_d2r[p]];
     std::vector<long long> off;
     build_slices(deg, off);
@@ -923,6 +986,7 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       if (owner[ai] == m.rank) m.nbr_mask |= xm;
       else if ((xm >> m.rank) & 1u) m.nbr_mask |= 1u << owner[ai];
     }
+#pragma omp parallel for schedule(static)
     for (int sl = 0; sl < m.m.n_slices; sl++)
       for (int l = 0; l < UFM_SLICE; l++) { int ai = m_d2r[sl * UFM_SLICE + l]; if (ai >= 0) { sowner[sl] = owner[ai]; break; } }
     UP(xmask, m.m_xmask); UP(sowner, m.m_sowner);
@@ -955,7 +1019,9 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
       UFM_CUDA(cudaStreamSynchronize(h->stream));
     }
     std::vector<int> aa2m(m.nVp, 0), ac2m(m.nAcp, 0);
+#pragma omp parallel for schedule(static)
     for (int v = 0; v < N; v++) aa2m[aa_r2d[v]] = m_r2d[v];
+#pragma omp parallel for schedule(static)
     for (int a = 0; a < E; a++) ac2m[ac_r2d[a]] = m_r2d[N + a];
     UP(aa2m, m.aa2m); UP(ac2m, m.ac2m);
   }
