@@ -158,60 +158,6 @@ def hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU restatement: per-routine unit costs at full size (bounded sample), scaled by iteration counts
-# ------------------------------------------------------------------------------------------------
-def cpu_unit_costs(m, st, nthreads, sor_iters=100, reps=5, min_seconds=10.0):
-    """The sample is bounded to about 10-30 s of CPU work: if the first pass (5 reps + 100 SOR iterations) took less than
-    `min_seconds` on this host, it is repeated once with proportionally more reps / iterations and that longer sample is reported."""
-    T = _cpu_unit_costs(m, st, nthreads, sor_iters, reps)
-    if T["sample_seconds"] < min_seconds:
-        f = min(6, int(np.ceil(1.25 * min_seconds / max(T["sample_seconds"], 1e-3))))
-        T = _cpu_unit_costs(m, st, nthreads, sor_iters * f, reps * f)
-    return T
-
-
-def _cpu_unit_costs(m, st, nthreads, sor_iters, reps):
-    from oracle.oracle import Oracle
-
-    o = Oracle(m, benchmark=st["benchmark"], nthreads=nthreads, use_analytical_GL_flux=1)
-    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
-        o[k][:] = st[k]
-    T = {}
-
-    def tm(name, fn, reps=1):
-        t = time.perf_counter()
-        for _ in range(reps):
-            fn()
-        T[name] = (time.perf_counter() - t) / reps
-
-    o.update_general_ice_model_data(0.0)  # warm the page tables
-    tm("geom", lambda: o.update_general_ice_model_data(0.0), reps)
-    tm("sia", o.solve_SIA, reps)
-    tm("thk", lambda: o.calculate_ice_thickness_change(0.0), reps)
-    o.update_general_ice_model_data(0.0)
-    tm("cfl", o.determine_timesteps, reps)
-    tm("ssa_prepare", lambda: (o.basal_yield_stress(), o.calculate_GL_flux(), o.SSA_gather_AaAc()), reps)
-    tm("visc", o.SSA_effective_viscosity, reps)
-    tm("slid", o.SSA_sliding_term, reps)
-    o.solve_SSA_linearised(max_inner=1, force_iters=True)
-    t = time.perf_counter()
-    o.solve_SSA_linearised(max_inner=sor_iters, force_iters=True)
-    T["sor_iter"] = (time.perf_counter() - t) / sor_iters  # includes the O(M) RHS/centre-coefficient setup once (small)
-    T["sample_seconds"] = reps * sum(v for k, v in T.items() if k != "sor_iter") + T["sor_iter"] * (sor_iters + 1)
-    T["sample_sor_iterations"] = sor_iters
-    T["sample_reps"] = reps
-    return T
-
-
-def cpu_step_seconds(T, did_sia, did_ssa, n_outer, n_sor):
-    t = T["thk"] + T["geom"] + T["cfl"]
-    if did_sia:
-        t += T["sia"]
-    if did_ssa:
-        t += T["ssa_prepare"] + n_outer * (T["visc"] + T["slid"]) + n_sor * T["sor_iter"]
-    return t
-
-
 def ssa_solve_time(step_ms, rows):
     """"SSA solve time / step" (BASELINE metric) from per-step device times: mean time of the steps that ran solve_SSA minus that of the
     steps that did not.  Reporting only: any problem yields an empty dict, never an exception."""

@@ -18,13 +18,6 @@ def test_ssa_solve_time_from_per_step_times():
     assert bench.ssa_solve_time(None, rows) == {} and bench.ssa_solve_time([1.0], [{}]) == {}
 
 
-def test_cpu_cost_model_adds_what_a_step_runs():
-    T = dict(geom=1.0, sia=2.0, thk=4.0, cfl=8.0, ssa_prepare=16.0, visc=32.0, slid=64.0, sor_iter=128.0)
-    assert bench.cpu_step_seconds(T, 0, 0, 0, 0) == 13.0                       # thickness + geometry + CFL every step
-    assert bench.cpu_step_seconds(T, 1, 0, 0, 0) == 15.0
-    assert bench.cpu_step_seconds(T, 1, 1, 2, 3) == 15.0 + 16.0 + 2 * 96.0 + 3 * 128.0
-
-
 def test_cpu_trajectory_and_parity_report():
     """The CPU arm runs the oracle's region loop for real; the parity report compares a (here: second CPU) trajectory with it field by
     field and step by step, and fails on a perturbed field, a different iteration count or a different time step."""

@@ -651,7 +651,10 @@ __global__ void __launch_bounds__(SOR_BLOCK, SOR_MIN_BLOCKS) k_ssa_sor(SorArgs a
       colour_share<MULTI>(a, s_rng, c, wg, nw, s_first, s_end, s_step);
       bool waited = !MULTI;
       const bool tr = a.trace && it == 4;
-      if (tr && threadIdx.x == 0) { s_tr[0] = ~0ull; s_tr[1] = 0ull; a.trace[(blockIdx.x * 6 + c) * 4 + 0] = gtime(); }
+      if (tr && threadIdx.x == 0) {
+        s_tr[0] = ~0ull; s_tr[1] = 0ull; a.trace[(blockIdx.x * 6 + c) * 4 + 0] = gtime();
+        if (c == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); a.trace[(blockIdx.x * 6 + 5) * 4 + 0] = sm; }   // which SM this CTA sits on
+      }
       if (tr) __syncthreads();
       for (int s = s_first; s < s_end; s += s_step) {
         if (MULTI && !waited && s >= s_bnd) {  // first boundary slice of this warp: the peers' previous phase must have landed
