@@ -884,25 +884,50 @@ int ufm_mesh_upload_impl(ufm_handle *h, const ufm_mesh_desc *d)
     else ufm_row_order_impl(M, blkv.data(), owner.data(), isb.data(), late.data(), degv.data(), mort.data(), X.data(), n_bands, deg_window, m_order);
     std::vector<int>().swap(m_presorted);
   }
+  // layout: blocks 1..5 = colours (swept rows), 6 = domain-edge rows; inside a block one group per (owner, interior / boundary), every
+  // group padded to a whole chunk.  m_order is sorted by group, so a group's rows are one run of it: sizes by a parallel count, starts by a
+  // prefix sum, then every row is placed independently.
   std::vector<int> m_r2d(M), m_d2r;
-  m_d2r.reserve((size_t)M + 12 * (size_t)P * UFM_CHUNK);
   {
-    int k = 0;
-    for (int b = 1; b <= 6; b++) {  // blocks 1..5 = colours (swept rows), 6 = domain-edge rows
+    const int NG = 6 * P * 2;
+    auto grp = [&](int ai) { return ((blk(ai) - 1) * P + owner[ai]) * 2 + (isb[ai] != 0); };
+    std::vector<long long> gcnt(NG, 0);
+    {
+      const int T = std::max(1, omp_get_max_threads());
+      std::vector<long long> part((size_t)T * NG, 0);
+#pragma omp parallel for schedule(static, 1)
+      for (int t = 0; t < T; t++) {
+        const size_t lo = (size_t)M * t / T, hi = (size_t)M * (t + 1) / T;
+        long long *c = part.data() + (size_t)t * NG;
+        for (size_t k = lo; k < hi; k++) c[grp(m_order[k])]++;
+      }
+      for (int t = 0; t < T; t++) for (int q = 0; q < NG; q++) gcnt[q] += part[(size_t)t * NG + q];
+    }
+    std::vector<long long> first_k(NG + 1, 0), start(NG, 0);
+    long long size = 0;
+    for (int b = 1; b <= 6; b++)
       for (int r = 0; r < P; r++) {
-        m.rng[b - 1][r][0] = (int)(m_d2r.size() / UFM_SLICE);
+        m.rng[b - 1][r][0] = (int)(size / UFM_SLICE);
         for (int bd = 0; bd < 2; bd++) {
-          if (bd == 1) m.rng[b - 1][r][1] = (int)(m_d2r.size() / UFM_SLICE);
-          while (k < M && blk(m_order[k]) == b && owner[m_order[k]] == r && isb[m_order[k]] == bd) {
-            m_r2d[m_order[k]] = (int)m_d2r.size();
-            m_d2r.push_back(m_order[k]);
-            k++;
-          }
-          if (bd == 1) m.rng[b - 1][r][2] = (int)((m_d2r.size() + UFM_SLICE - 1) / UFM_SLICE);
-          while (m_d2r.size() % UFM_CHUNK) m_d2r.push_back(-1);
+          const int q = ((b - 1) * P + r) * 2 + bd;
+          if (bd == 1) m.rng[b - 1][r][1] = (int)(size / UFM_SLICE);
+          start[q] = size; first_k[q + 1] = first_k[q] + gcnt[q];
+          size += gcnt[q];
+          if (bd == 1) m.rng[b - 1][r][2] = (int)((size + UFM_SLICE - 1) / UFM_SLICE);
+          size = (size + UFM_CHUNK - 1) / UFM_CHUNK * UFM_CHUNK;
         }
       }
+    if (first_k[NG] != M) return ufm_set_error(-2, "ufm_mesh_upload: internal error in the AaAc row layout");
+    m_d2r.assign((size_t)size, -1);
+    bool sorted_ok = true;
+#pragma omp parallel for schedule(static) reduction(&& : sorted_ok)
+    for (int k = 0; k < M; k++) {
+      const int ai = m_order[k], q = grp(ai);
+      if (k < first_k[q] || k >= first_k[q + 1]) { sorted_ok = false; continue; }   // m_order not grouped: cannot happen
+      const long long pos = start[q] + (k - first_k[q]);
+      m_r2d[ai] = (int)pos; m_d2r[(size_t)pos] = ai;
     }
+    if (!sorted_ok) return ufm_set_error(-2, "ufm_mesh_upload: internal error in the AaAc row order");
   }
   m.Mp = (int)m_d2r.size();
   m.n_chunks = m.Mp / UFM_CHUNK;
