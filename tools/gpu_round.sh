@@ -50,8 +50,8 @@ capture geom_aa2 ".*k_geom_aa2.*" 2 python tools/sor_probe.py --iters 5 --reps 1
 capture sia_ac ".*k_sia_ac\\(.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
 capture sia_aa ".*k_sia_aa.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
 capture thk_flux ".*k_thk_flux.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
-capture thk1 ".*k_thk<1, true>.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
-capture thk2 ".*k_thk<2, true>.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
+capture thk1 ".*k_thk<\\(int\\)1, \\(bool\\)1>.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
+capture thk2 ".*k_thk<\\(int\\)2, \\(bool\\)1>.*" 2 python tools/sor_probe.py --iters 5 --reps 1 --others
 
 step "upload probe (mesh update / restart data path, 1 M vertices)"
 timeout 900 python tools/upload_probe.py --out $OUT/upload_probe_1M_${TAG}.json 2> $OUT/upload_probe_1M_${TAG}_phases.log | cut -c1-600

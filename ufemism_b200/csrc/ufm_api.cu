@@ -112,6 +112,7 @@ int ufm_destroy(ufm_handle *h)
   if (h->xfer_host) cudaFreeHost(h->xfer_host);
   for (auto e : h->xfer_ev) if (e) cudaEventDestroy(e);
   if (h->xfer_stream) cudaStreamDestroy(h->xfer_stream);
+  if (h->xfer_stream_out) cudaStreamDestroy(h->xfer_stream_out);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   for (auto e : h->ev_pool) if (e) cudaEventDestroy(e);
   cudaStreamDestroy(h->own_stream);
@@ -539,10 +540,12 @@ static int xfer_prepare(ufm_handle *h, bool need_host_slots)
   const size_t slot = (((size_t)h->mesh.nV * sizeof(double)) + 255) & ~(size_t)255;
   if (!h->xfer_stream) {
     UFM_CUDA(cudaStreamCreateWithFlags(&h->xfer_stream, cudaStreamNonBlocking));
+    UFM_CUDA(cudaStreamCreateWithFlags(&h->xfer_stream_out, cudaStreamNonBlocking));
     for (auto &e : h->xfer_ev) UFM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   if (h->xfer_slot_bytes < slot) {
     UFM_CUDA(cudaStreamSynchronize(h->xfer_stream));
+    UFM_CUDA(cudaStreamSynchronize(h->xfer_stream_out));
     if (h->xfer_dev) cudaFree(h->xfer_dev);
     if (h->xfer_host) cudaFreeHost(h->xfer_host);
     h->xfer_dev = h->xfer_host = nullptr; h->xfer_slot_bytes = 0;
@@ -553,7 +556,9 @@ static int xfer_prepare(ufm_handle *h, bool need_host_slots)
   h->xfer_n_pending = 0;
   return 0;
 }
-static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int slot)
+// phase: 3 = copy and permutation (default); 1 = only enqueue the host -> device copy; 2 = only the permutation kernel that waits for it
+// (so that a step can put all its copies on the wire first and let the compute stream pick the fields up in the order it needs them)
+static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int slot, int phase = 3)
 {
   FieldRef r;
   int rc = field_ref(h, field, &r);
@@ -568,12 +573,16 @@ static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int s
   cudaEvent_t ev = h->xfer_ev[slot];
   if (to_device) {
     if (r.bits) return ufm_set_error(-2, "mask fields are outputs");
-    if (!direct) memcpy(hslot, host, bytes);
-    UFM_CUDA(cudaMemcpyAsync(dslot, hslot, bytes, cudaMemcpyHostToDevice, h->xfer_stream));
-    UFM_CUDA(cudaEventRecord(ev, h->xfer_stream));
-    UFM_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
-    rc = r.is_int ? ufm_perm_int(h, n, m.aa_ref2dev, r.i, (int *)dslot, 1) : ufm_perm_double(h, n, m.aa_ref2dev, r.d, r.stride, r.comp, (double *)dslot, 1);
-    h->cnt.h2d_bytes += (double)bytes;
+    if (phase & 1) {
+      if (!direct) memcpy(hslot, host, bytes);
+      UFM_CUDA(cudaMemcpyAsync(dslot, hslot, bytes, cudaMemcpyHostToDevice, h->xfer_stream));
+      UFM_CUDA(cudaEventRecord(ev, h->xfer_stream));
+      h->cnt.h2d_bytes += (double)bytes;
+    }
+    if (phase & 2) {
+      UFM_CUDA(cudaStreamWaitEvent(h->stream, ev, 0));
+      rc = r.is_int ? ufm_perm_int(h, n, m.aa_ref2dev, r.i, (int *)dslot, 1) : ufm_perm_double(h, n, m.aa_ref2dev, r.d, r.stride, r.comp, (double *)dslot, 1);
+    }
     return rc;
   }
   if (r.bits) rc = ufm_perm_mask(h, n, m.aa_ref2dev, r.bits, r.barg, r.bmode, (int *)dslot);
@@ -581,8 +590,8 @@ static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int s
   else rc = ufm_perm_double(h, n, m.aa_ref2dev, r.d, r.stride, r.comp, (double *)dslot, 0);
   if (rc) return rc;
   UFM_CUDA(cudaEventRecord(ev, h->stream));
-  UFM_CUDA(cudaStreamWaitEvent(h->xfer_stream, ev, 0));
-  UFM_CUDA(cudaMemcpyAsync(hslot, dslot, bytes, cudaMemcpyDeviceToHost, h->xfer_stream));
+  UFM_CUDA(cudaStreamWaitEvent(h->xfer_stream_out, ev, 0));
+  UFM_CUDA(cudaMemcpyAsync(hslot, dslot, bytes, cudaMemcpyDeviceToHost, h->xfer_stream_out));
   if (!direct) h->xfer_pending[h->xfer_n_pending++] = {host, hslot, bytes};
   h->cnt.d2h_bytes += (double)bytes;
   return 0;
@@ -591,6 +600,7 @@ static int xfer_begin(ufm_handle *h, int field, void *host, int to_device, int s
 static int xfer_finish(ufm_handle *h)
 {
   UFM_CUDA(cudaStreamSynchronize(h->xfer_stream));
+  UFM_CUDA(cudaStreamSynchronize(h->xfer_stream_out));
   for (int k = 0; k < h->xfer_n_pending; k++) memcpy(h->xfer_pending[k].dst, h->xfer_pending[k].src, h->xfer_pending[k].bytes);
   h->xfer_n_pending = 0;
   return 0;
@@ -800,28 +810,45 @@ static int run_model_impl(ufm_handle *h, ufm_region *r, double t_end, long max_s
     // run_ELRA_model (bedrock_ELRA_module.f90:22-66): the benchmark branch only moves the timer on; a realistic run does so when the
     // deformation rate is due (the host computes it and updates Hb between the steps, then uploads Hb / dHb_dt with the step's inputs)
     if (b != UFM_BM_NONE || r->do_[UFM_T_ELRA]) r->t0[UFM_T_ELRA] = r->time;
-    if (host) {
-      const struct { int f; const void *p; } in[] = {{UFM_F_HI, host->Hi}, {UFM_F_HB, host->Hb}, {UFM_F_SL, host->SL}, {UFM_F_DHB_DT, host->dHb_dt},
-                                                     {UFM_F_SMB_YEAR, host->SMB_year}, {UFM_F_BMB, host->BMB}, {UFM_F_MASK_NOICE, host->mask_noice}};
-      int slot = 0;
-      for (auto &q : in) {
-        if (!q.p) continue;
-        if ((rc = overlap ? xfer_begin(h, q.f, (void *)q.p, 1, slot++) : ufm_state_upload(h, q.f, q.p))) return rc;
-      }
+    // Drop-in mode, order of the step's transfers: every host -> device copy goes on the wire at once, the inputs of the thickness update
+    // first (Hi, SMB, BMB, mask_noice); the compute stream picks those up, updates the thickness and hands its results to the
+    // device -> host stream while the geometry's inputs (Hb, SL, dHb_dt) are still arriving in the other direction.  Outputs whose
+    // producer does not run in this step (velocities between two solves) are unchanged since the last step and leave first.
+    const struct { int f; const void *p; int late; } in[] = {{UFM_F_HI, host ? host->Hi : nullptr, 0}, {UFM_F_SMB_YEAR, host ? host->SMB_year : nullptr, 0},
+                                                             {UFM_F_BMB, host ? host->BMB : nullptr, 0}, {UFM_F_MASK_NOICE, host ? host->mask_noice : nullptr, 0},
+                                                             {UFM_F_HB, host ? host->Hb : nullptr, 1}, {UFM_F_SL, host ? host->SL : nullptr, 1},
+                                                             {UFM_F_DHB_DT, host ? host->dHb_dt : nullptr, 1}};
+    const int n_in = (int)(sizeof(in) / sizeof(in[0]));
+    auto pick_up = [&](int late) -> int {
+      for (int k = 0; k < n_in; k++)
+        if (in[k].p && in[k].late == late) { int rc_ = xfer_begin(h, in[k].f, (void *)in[k].p, 1, k, 2); if (rc_) return rc_; }
+      return 0;
+    };
+    if (host && overlap) {
+      if (!r->do_[UFM_T_SSA] && (rc = start_downloads(AFTER_SSA))) return rc;
+      if (!r->do_[UFM_T_SIA] && (rc = start_downloads(AFTER_SIA))) return rc;
+      for (int k = 0; k < n_in; k++) if (in[k].p && (rc = xfer_begin(h, in[k].f, (void *)in[k].p, 1, k, 1))) return rc;
+      if ((rc = pick_up(0))) return rc;
+    } else if (host) {
+      for (int k = 0; k < n_in; k++) if (in[k].p && (rc = ufm_state_upload(h, in[k].f, in[k].p))) return rc;
     }
     if ((rc = ufm_thickness_update(h, r->dt))) return rc;
     if ((rc = start_downloads(AFTER_THK))) return rc;
+    if (host && overlap && (rc = pick_up(1))) return rc;
     if ((rc = ufm_update_general(h, r->time))) return rc;
     if ((rc = start_downloads(AFTER_GENERAL))) return rc;
-    if (r->do_[UFM_T_SIA]) { if ((rc = ufm_solve_SIA(h))) return rc; r->t0[UFM_T_SIA] = r->time; r->n_sia++; }
-    if ((rc = start_downloads(AFTER_SIA))) return rc;
+    if (r->do_[UFM_T_SIA]) {
+      if ((rc = ufm_solve_SIA(h))) return rc;
+      r->t0[UFM_T_SIA] = r->time; r->n_sia++;
+      if ((rc = start_downloads(AFTER_SIA))) return rc;
+    }
     if (r->do_[UFM_T_SSA]) {
       ufm_ssa_stats st;
       rc = ufm_solve_SSA(h, &st);
       if (rc < 0) return rc;
       r->t0[UFM_T_SSA] = r->time; r->n_ssa++; r->n_sor_total += st.n_inner_total; r->n_outer_total += st.n_outer;
+      if ((rc = start_downloads(AFTER_SSA))) return rc;
     }
-    if ((rc = start_downloads(AFTER_SSA))) return rc;
     // climate / BMB: no-ops for the dynamics in the benchmark experiments (BMB = 0, src/BMB_module.f90:51-69)
     if (r->do_[UFM_T_CLIMATE]) r->t0[UFM_T_CLIMATE] = r->time;
     if (r->do_[UFM_T_SMB]) {   // run_SMB_model, benchmark branches: closed forms evaluated on the device (no host round trip)

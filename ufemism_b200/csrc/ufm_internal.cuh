@@ -312,7 +312,8 @@ struct ufm_handle {
   size_t arena_used = 0, arena_total = 0;
   // drop-in mode (ufm_run_model_host): per-field device / pinned-host slots and a copy stream, so that the H2D / D2H copies of a
   // step overlap each other and the SSA solve instead of being serialised with a host synchronisation each
-  cudaStream_t xfer_stream = nullptr;
+  cudaStream_t xfer_stream = nullptr;      // host -> device copies of drop-in mode
+  cudaStream_t xfer_stream_out = nullptr;  // device -> host copies (their own stream: the two directions use different copy engines)
   cudaEvent_t xfer_ev[2 * UFM_XFER_SLOTS] = {};
   char *xfer_dev = nullptr, *xfer_host = nullptr;   // UFM_XFER_SLOTS slots of xfer_slot_bytes each (host slots only if a buffer is not page-locked)
   size_t xfer_slot_bytes = 0;
