@@ -1,8 +1,9 @@
 """GPU parity tests proper: CUDA path (through the C ABI) vs the CPU oracle on the same inputs.
 
 Bar: BIT-EXACT wherever the arithmetic is add/mul/div/sqrt/compare (stencils, masks, thickness update,
-SOR sweep, Neumann pass, CFL); |rel| <= 1e-13 where one CUDA libm pow()/tan() sits on the path (<= 2 ulp vs
-glibc); north_star tolerances for composed results: velocities <= 1e-10 rel-L2 after the same SOR iteration
+SOR sweep, Neumann pass, CFL) and -- with the host libm's pow / tan re-stated on the device (csrc/ufm_pow.cuh, the default when the
+running libm is the glibc it knows) -- behind those two functions as well; |rel| <= 1e-13 is what the tests ask for behind a pow()/tan()
+so that they also hold with CUDA's own functions (UFM_POW_EXACT=0, <= 2 ulp vs glibc); north_star tolerances for composed results: velocities <= 1e-10 rel-L2 after the same SOR iteration
 count, ice thickness <= 1e-8 rel after N model years.
 """
 import numpy as np
