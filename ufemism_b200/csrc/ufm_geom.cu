@@ -361,7 +361,15 @@ struct SiaAaArgs {
   const int *gate;
   const unsigned char *own; int rank;
 };
-__global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
+// resident CTAs per SM the kernel is compiled for and connections per batch: measured at 1 M vertices (solve_SIA total, tools/probes_r02/
+// r02_probe_minb.sh): (1, 4) 0.100-0.102 ms, (4, 4) 0.093, (5, 4) 0.095, (4, 2) 0.093, (6, 2) 0.090, (1, 8) 0.112 -- latency bound: warps beat batch size
+#ifndef UFM_SIA_AA_MINB
+#define UFM_SIA_AA_MINB 6
+#endif
+#ifndef UFM_SIA_AA_CHUNK
+#define UFM_SIA_AA_CHUNK 2
+#endif
+__global__ void __launch_bounds__(256, UFM_SIA_AA_MINB) k_sia_aa(SiaAaArgs a)
 {
   UFM_GATE(a.gate);
   const int lane = threadIdx.x & 31;
@@ -374,23 +382,23 @@ __global__ void __launch_bounds__(256) k_sia_aa(SiaAaArgs a)
     if (n == UFM_DEG_PAD || !UFM_OWNED(a.own, v, a.rank)) continue;
     const double dn = (double)n, rn = 1.0 / dn;
     double u = 0.0, vv = 0.0, dd = 0.0;
-    // four connections at a time: all index loads, then all twelve gathers, then the sums in connection order (columns past the
+    // a batch of connections at a time: all index loads, then all gathers, then the sums in connection order (columns past the
     // vertex's own degree read entry 0 and are not added: unconditional loads are what lets the compiler put them in flight together).
-    // Measured (1 M vertices, ncu): one connection at a time with a division per term 81-92 us; this form 52 us; the three fields
+    // Measured (1 M vertices, ncu): one connection at a time with a division per term 81-92 us; batches of four 52 us; the three fields
     // split over blockIdx.y (three times the warps, a third of the gathers each) 60 us.
-    for (int c0 = 0; c0 < w; c0 += 4) {
-      int ac[4];
-      double x[4], y[4], z[4];
+    for (int c0 = 0; c0 < w; c0 += UFM_SIA_AA_CHUNK) {
+      int ac[UFM_SIA_AA_CHUNK];
+      double x[UFM_SIA_AA_CHUNK], y[UFM_SIA_AA_CHUNK], z[UFM_SIA_AA_CHUNK];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < UFM_SIA_AA_CHUNK; k++) {
         const int c = c0 + k < w ? c0 + k : w - 1;
         const int ia = a.iAci[o + (long long)c * 32 + lane] & 0x7fffffff;
         ac[k] = c0 + k < n ? ia : 0;
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) { x[k] = a.Ux[ac[k]]; y[k] = a.Uy[ac[k]]; z[k] = a.D[ac[k]]; }
+      for (int k = 0; k < UFM_SIA_AA_CHUNK; k++) { x[k] = a.Ux[ac[k]]; y[k] = a.Uy[ac[k]]; z[k] = a.D[ac[k]]; }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < UFM_SIA_AA_CHUNK; k++) {
         if (c0 + k < n) {
           // term / nC(vi), term by term as the reference does; ufm_div_small = the same bits without 3 n divisions per vertex
           u = u + ufm_div_small(x[k], dn, rn); vv = vv + ufm_div_small(y[k], dn, rn); dd = dd + ufm_div_small(z[k], dn, rn);
@@ -473,8 +481,12 @@ __device__ __forceinline__ void thk_chunk(const ThkArgs &a, const long long o, c
     }
   }
 }
+// resident CTAs per SM: thickness update total 0.098-0.099 ms at 1, 0.097 at 5, 0.094 at 6 (same probe)
+#ifndef UFM_THK_MINB
+#define UFM_THK_MINB 6
+#endif
 template <int PASS, bool EDGE>
-__global__ void __launch_bounds__(256) k_thk(ThkArgs a)
+__global__ void __launch_bounds__(256, UFM_THK_MINB) k_thk(ThkArgs a)
 {
   UFM_GATE(a.gate);
   if (a.dt_dev) a.dt = *a.dt_dev;
