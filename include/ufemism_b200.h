@@ -186,6 +186,9 @@ typedef struct ufm_mesh_primary {
 int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *mesh);
 /* the host-only half on its own (no device needed): derive, look, free; *derived is an opaque object */
 int ufm_mesh_derive_secondary(const ufm_mesh_primary *mesh, void **derived);
+/* the same with *derived_inout holding the object of an earlier call (or NULL): its buffers are reused and its contents replaced; on an
+ * error the old object is gone and *derived_inout is NULL */
+int ufm_mesh_derive_secondary_reuse(const ufm_mesh_primary *mesh, void **derived_inout);
 int ufm_mesh_derived_get(const void *derived, ufm_mesh_desc *out, const double **Tricc, const int **Tri_edge_index, const double **VAc,
                          const double **VAaAc, const int **colour);
 void ufm_mesh_derived_free(void *derived);

@@ -130,7 +130,7 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host", "ufm_div_small_host", "ufm_partition_owner_of", "ufm_partition_halo_counts",
             "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
             "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
-            "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
+            "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derive_secondary_reuse", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
             "ufm_mesh_secondary_get"]
 
 _lib = None
@@ -206,6 +206,7 @@ def load_library():
         L.ufm_output_filename.argtypes = [s, s, i, p, i]
         L.ufm_mesh_upload_primary.argtypes = [p, p]
         L.ufm_mesh_derive_secondary.argtypes = [p, p]
+        L.ufm_mesh_derive_secondary_reuse.argtypes = [p, p]
         L.ufm_mesh_derived_get.argtypes = [p] * 7
         L.ufm_mesh_derived_free.argtypes = [p]
         L.ufm_mesh_derived_free.restype = None
@@ -300,12 +301,17 @@ def _derived_to_dict(L, getter, obj, nV, nTri, W):
     return out
 
 
-def derive_secondary(mesh, thermo=False):
-    """Host-only: what ufm_mesh_upload_primary derives from the primary mesh data, as a dict of numpy arrays."""
+def derive_secondary(mesh, thermo=False, repeat=1):
+    """Host-only: what ufm_mesh_upload_primary derives from the primary mesh data, as a dict of numpy arrays.  repeat > 1 derives that
+    many times into the same object (buffers reused, as a re-upload does) and returns the last result."""
     L = load_library()
     p, keep = mesh_primary(mesh, thermo)
     obj = ctypes.c_void_p()
     rc = L.ufm_mesh_derive_secondary(ctypes.byref(p), ctypes.byref(obj))
+    for _ in range(repeat - 1):
+        if rc:
+            break
+        rc = L.ufm_mesh_derive_secondary_reuse(ctypes.byref(p), ctypes.byref(obj))
     if rc:
         raise UfmError(rc, L.ufm_last_error().decode())
     try:

@@ -29,6 +29,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+static double mh_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 #define I2(a, i, j, ld) (a)[((size_t)((j) - 1)) * (size_t)(ld) + (size_t)((i) - 1)]
 
@@ -385,91 +387,120 @@ int ufm_mesh_make_Ac(int nV, int nTri, int nC_mem, int nAc_max, const double *V,
    * (edges owned by lower vertices) + (its rank among vi's connections to higher vertices): a prefix sum, after which the
    * vertices can be processed independently with the reference's numbering reproduced exactly. */
   int err = 0;
-  memset(iAci, 0, sizeof(int) * (size_t)nV * nC_mem);
+  const int W = nC_mem;
   int *first = (int *)malloc(sizeof(int) * ((size_t)nV + 2));
-  if (!first) return -3;
+  /* Row-major scratch copies of what the loop below reaches through a NEIGHBOUR's index (C, iTri, Tri, V): the reference's arrays are
+   * column-major, so one vertex's connection list is spread over nC cache lines nV*4 bytes apart; here it is one line.  The edge
+   * numbers are written row-major too (a vertex also writes into its higher neighbours' rows) and transposed into iAci at the end. */
+  int *Cr = (int *)malloc(sizeof(int) * (size_t)nV * W), *iTr = (int *)malloc(sizeof(int) * (size_t)nV * W);
+  int *Tr = (int *)malloc(sizeof(int) * (size_t)nTri * 3), *iAr = (int *)malloc(sizeof(int) * (size_t)nV * W);
+  double *XY = (double *)malloc(sizeof(double) * (size_t)nV * 2);
+  if (!first || !Cr || !iTr || !Tr || !iAr || !XY) { free(first); free(Cr); free(iTr); free(Tr); free(iAr); free(XY); return -3; }
 #pragma omp parallel for schedule(static)
   for (int vi = 1; vi <= nV; vi++) {
     int k = 0;
-    for (int ci = 1; ci <= nC[vi - 1]; ci++) if (I2(C, vi, ci, nV) > vi) k++;
+    int *cr = Cr + (size_t)(vi - 1) * W, *tr = iTr + (size_t)(vi - 1) * W, *ar = iAr + (size_t)(vi - 1) * W;
+    for (int ci = 1; ci <= W; ci++) { cr[ci - 1] = ci <= nC[vi - 1] ? I2(C, vi, ci, nV) : 0; ar[ci - 1] = 0; }
+    for (int ci = 1; ci <= W; ci++) tr[ci - 1] = ci <= niTri[vi - 1] ? I2(iTri, vi, ci, nV) : 0;
+    for (int ci = 0; ci < nC[vi - 1]; ci++) if (cr[ci] > vi) k++;
     first[vi] = k;
+    XY[2 * (size_t)(vi - 1)] = I2(V, vi, 1, nV); XY[2 * (size_t)(vi - 1) + 1] = I2(V, vi, 2, nV);
   }
+#pragma omp parallel for schedule(static)
+  for (int ti = 1; ti <= nTri; ti++)
+    for (int n = 1; n <= 3; n++) Tr[3 * (size_t)(ti - 1) + n - 1] = I2(Tri, ti, n, nTri);
   long long tot = 0;
   for (int vi = 1; vi <= nV; vi++) { int k = first[vi]; first[vi] = (int)tot; tot += k; }
-  if (tot > nAc_max) { free(first); return -1; }
+  if (tot > nAc_max) { free(first); free(Cr); free(iTr); free(Tr); free(iAr); free(XY); return -1; }
   const int nAc_total = (int)tot;
-#define VX(v) I2(V, v, 1, nV)
-#define VY(v) I2(V, v, 2, nV)
+#define VX(v) XY[2 * (size_t)((v) - 1)]
+#define VY(v) XY[2 * (size_t)((v) - 1) + 1]
+#define TRI(t, n) Tr[3 * (size_t)((t) - 1) + (n) - 1]
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int vi = 1; vi <= nV; vi++) {
     int nAc = first[vi];
+    const int *cr = Cr + (size_t)(vi - 1) * W, *tr = iTr + (size_t)(vi - 1) * W;
     for (int ci = 1; ci <= nC[vi - 1]; ci++) {
-      int vj = I2(C, vi, ci, nV);
+      int vj = cr[ci - 1];
       if (vj <= vi) continue;
       nAc++;
-      I2(iAci, vi, ci, nV) = nAc;
+      iAr[(size_t)(vi - 1) * W + ci - 1] = nAc;
       I2(VAc, nAc, 1, nAc_max) = (VX(vi) + VX(vj)) / 2.0;
       I2(VAc, nAc, 2, nAc_max) = (VY(vi) + VY(vj)) / 2.0;
-      for (int cj = 1; cj <= nC[vj - 1]; cj++)
-        if (I2(C, vj, cj, nV) == vi) { I2(iAci, vj, cj, nV) = nAc; break; }
+      {
+        const int *cj_row = Cr + (size_t)(vj - 1) * W;
+        for (int cj = 1; cj <= nC[vj - 1]; cj++)
+          if (cj_row[cj - 1] == vi) { iAr[(size_t)(vj - 1) * W + cj - 1] = nAc; break; }
+      }
       int vl = 0, vr = 0;
       double Nxl[4], Nyl[4], Nxr[4], Nyr[4], Nx[4], Ny[4], Nzl, Nzr;
       if (!is_boundary_segment(edge_index, vi, vj)) {
         for (int iti = 1; iti <= niTri[vi - 1]; iti++) {
-          int ti = I2(iTri, vi, iti, nV);
+          int ti = tr[iti - 1];
           for (int n1 = 1; n1 <= 3; n1++) {
             int n2 = n1 + 1; if (n2 == 4) n2 = 1;
             int n3 = n2 + 1; if (n3 == 4) n3 = 1;
-            if (I2(Tri, ti, n1, nTri) == vi && I2(Tri, ti, n2, nTri) == vj) vl = I2(Tri, ti, n3, nTri);
-            else if (I2(Tri, ti, n1, nTri) == vj && I2(Tri, ti, n2, nTri) == vi) vr = I2(Tri, ti, n3, nTri);
+            if (TRI(ti, n1) == vi && TRI(ti, n2) == vj) vl = TRI(ti, n3);
+            else if (TRI(ti, n1) == vj && TRI(ti, n2) == vi) vr = TRI(ti, n3);
           }
         }
         if (!vl || !vr) { err = -2; continue; }
         I2(Aci, nAc, 1, nAc_max) = vi; I2(Aci, nAc, 2, nAc_max) = vj; I2(Aci, nAc, 3, nAc_max) = vl; I2(Aci, nAc, 4, nAc_max) = vr;
-        Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
-        Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
-        Nxr[0] = VY(vj) - VY(vr); Nxr[1] = VY(vr) - VY(vi); Nxr[2] = 0.0; Nxr[3] = VY(vi) - VY(vj);
-        Nyr[0] = VX(vr) - VX(vj); Nyr[1] = VX(vi) - VX(vr); Nyr[2] = 0.0; Nyr[3] = VX(vj) - VX(vi);
-        Nzl = ((VX(vj) - VX(vi)) * (VY(vl) - VY(vi))) - ((VY(vj) - VY(vi)) * (VX(vl) - VX(vi)));
-        Nzr = ((VX(vr) - VX(vi)) * (VY(vj) - VY(vi))) - ((VY(vr) - VY(vi)) * (VX(vj) - VX(vi)));
-        for (int k = 0; k < 4; k++) {
-          Nx[k] = -((Nxl[k] / Nzl) + (Nxr[k] / Nzr)) / 2.0;
-          Ny[k] = -((Nyl[k] / Nzl) + (Nyr[k] / Nzr)) / 2.0;
+        if (Nx_Ac && Ny_Ac && No_Ac) {
+          Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
+          Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
+          Nxr[0] = VY(vj) - VY(vr); Nxr[1] = VY(vr) - VY(vi); Nxr[2] = 0.0; Nxr[3] = VY(vi) - VY(vj);
+          Nyr[0] = VX(vr) - VX(vj); Nyr[1] = VX(vi) - VX(vr); Nyr[2] = 0.0; Nyr[3] = VX(vj) - VX(vi);
+          Nzl = ((VX(vj) - VX(vi)) * (VY(vl) - VY(vi))) - ((VY(vj) - VY(vi)) * (VX(vl) - VX(vi)));
+          Nzr = ((VX(vr) - VX(vi)) * (VY(vj) - VY(vi))) - ((VY(vr) - VY(vi)) * (VX(vj) - VX(vi)));
+          for (int k = 0; k < 4; k++) {
+            Nx[k] = -((Nxl[k] / Nzl) + (Nxr[k] / Nzr)) / 2.0;
+            Ny[k] = -((Nyl[k] / Nzl) + (Nyr[k] / Nzr)) / 2.0;
+          }
         }
       } else {
         for (int iti = 1; iti <= niTri[vi - 1]; iti++) {
-          int ti = I2(iTri, vi, iti, nV);
+          int ti = tr[iti - 1];
           for (int n1 = 1; n1 <= 3; n1++) {
             int n2 = n1 + 1; if (n2 == 4) n2 = 1;
             int n3 = n2 + 1; if (n3 == 4) n3 = 1;
-            if ((I2(Tri, ti, n1, nTri) == vi && I2(Tri, ti, n2, nTri) == vj) ||
-                (I2(Tri, ti, n1, nTri) == vj && I2(Tri, ti, n2, nTri) == vi)) vl = I2(Tri, ti, n3, nTri);
+            if ((TRI(ti, n1) == vi && TRI(ti, n2) == vj) || (TRI(ti, n1) == vj && TRI(ti, n2) == vi)) vl = TRI(ti, n3);
           }
         }
         if (!vl) { err = -2; continue; }
         I2(Aci, nAc, 1, nAc_max) = vi; I2(Aci, nAc, 2, nAc_max) = vj; I2(Aci, nAc, 3, nAc_max) = vl; I2(Aci, nAc, 4, nAc_max) = 1;
-        Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
-        Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
-        Nzl = ((VX(vj) - VX(vi)) * (VY(vl) - VY(vi))) - ((VY(vj) - VY(vi)) * (VX(vl) - VX(vi)));
-        for (int k = 0; k < 4; k++) { Nx[k] = -Nxl[k] / Nzl; Ny[k] = -Nyl[k] / Nzl; }
+        if (Nx_Ac && Ny_Ac && No_Ac) {
+          Nxl[0] = VY(vl) - VY(vj); Nxl[1] = VY(vi) - VY(vl); Nxl[2] = VY(vj) - VY(vi); Nxl[3] = 0.0;
+          Nyl[0] = VX(vj) - VX(vl); Nyl[1] = VX(vl) - VX(vi); Nyl[2] = VX(vi) - VX(vj); Nyl[3] = 0.0;
+          Nzl = ((VX(vj) - VX(vi)) * (VY(vl) - VY(vi))) - ((VY(vj) - VY(vi)) * (VX(vl) - VX(vi)));
+          for (int k = 0; k < 4; k++) { Nx[k] = -Nxl[k] / Nzl; Ny[k] = -Nyl[k] / Nzl; }
+        }
       }
-      double Ux = VX(vj) - VX(vi), Uy = VY(vj) - VY(vi), U = sqrt(Ux * Ux + Uy * Uy);
       /* the four operator arrays are optional: ufm_mesh_upload_primary lets the device derive them (k_derive_nf_Ac) */
-      if (Np_Ac) Np_Ac[nAc - 1] = 1.0 / U;
-      for (int k = 0; k < 4 && Nx_Ac && Ny_Ac && No_Ac; k++) {
-        I2(Nx_Ac, nAc, k + 1, nAc_max) = Nx[k];
-        I2(Ny_Ac, nAc, k + 1, nAc_max) = Ny[k];
-        I2(No_Ac, nAc, k + 1, nAc_max) = (Ny[k] * Ux - Nx[k] * Uy) / U;
+      if (Np_Ac || (Nx_Ac && Ny_Ac && No_Ac)) {
+        double Ux = VX(vj) - VX(vi), Uy = VY(vj) - VY(vi), U = sqrt(Ux * Ux + Uy * Uy);
+        if (Np_Ac) Np_Ac[nAc - 1] = 1.0 / U;
+        for (int k = 0; k < 4 && Nx_Ac && Ny_Ac && No_Ac; k++) {
+          I2(Nx_Ac, nAc, k + 1, nAc_max) = Nx[k];
+          I2(Ny_Ac, nAc, k + 1, nAc_max) = Ny[k];
+          I2(No_Ac, nAc, k + 1, nAc_max) = (Ny[k] * Ux - Nx[k] * Uy) / U;
+        }
       }
     }
   }
+#undef TRI
+  /* edge numbers back into the reference's column-major iAci (columns past nC stay 0) */
+  int unnumbered = 0;   /* a connection that its other end does not list (C not symmetric) was never numbered */
+#pragma omp parallel for schedule(static) reduction(| : unnumbered)
+  for (int vi = 1; vi <= nV; vi++) {
+    const int *ar = iAr + (size_t)(vi - 1) * W;
+    for (int ci = 1; ci <= W; ci++) { I2(iAci, vi, ci, nV) = ar[ci - 1]; if (ci <= nC[vi - 1] && ar[ci - 1] < 1) unnumbered = 1; }
+  }
+  free(Cr); free(iTr); free(Tr); free(iAr); free(XY);
+  if (unnumbered && !err) err = -2;
   free(first);
   if (err) return err;
   const int nAc = nAc_total;
-  /* a connection that its other end does not list (C not symmetric) was never numbered */
-  for (int vi = 1; vi <= nV && !err; vi++)
-    for (int ci = 1; ci <= nC[vi - 1]; ci++) if (I2(iAci, vi, ci, nV) < 1) { err = -2; break; }
-  if (err) return err;
   /* find_Ac_edge_indices, mesh_ArakawaC_module.f90:236-285 */
 #pragma omp parallel for schedule(static)
   for (int aci = 1; aci <= nAc; aci++) {
@@ -494,18 +525,34 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
                        double *VAaAc, int *nCAaAc, int *CAaAc)
 {
   int M = nV + nAc, err = 0;
-  memset(CAaAc, 0, sizeof(int) * (size_t)M * nC_mem);
+  const int W = nC_mem;
+  /* (neighbour vertex, edge number) pairs of every vertex in one row-major scratch row: the Ac loop below looks both up through the
+   * index of a THIRD vertex (the far corner of a triangle), which in the reference's column-major C / iAci costs one cache line per
+   * connection and array; here it is two lines per vertex */
+  double t0_ = mh_now();
+  int *CA = (int *)malloc(sizeof(int) * (size_t)nV * W * 2);
+  if (!CA) return -3;
 #pragma omp parallel for schedule(static)
   for (int vi = 1; vi <= nV; vi++) {
     I2(VAaAc, vi, 1, M) = I2(V, vi, 1, nV); I2(VAaAc, vi, 2, M) = I2(V, vi, 2, nV);
     nCAaAc[vi - 1] = nC[vi - 1];
-    for (int ci = 1; ci <= nC[vi - 1]; ci++) I2(CAaAc, vi, ci, M) = I2(iAci, vi, ci, nV) + nV;
+    int *row = CA + (size_t)(vi - 1) * W * 2;
+    for (int ci = 1; ci <= W; ci++) {
+      const int in = ci <= nC[vi - 1];
+      const int c = in ? I2(C, vi, ci, nV) : 0, ia = in ? I2(iAci, vi, ci, nV) : 0;
+      row[2 * (ci - 1)] = c; row[2 * (ci - 1) + 1] = ia;
+      I2(CAaAc, vi, ci, M) = in ? ia + nV : 0;
+    }
   }
+  double t1_ = mh_now();
+#define NB(v, ci) CA[((size_t)((v) - 1) * W + (ci) - 1) * 2]
+#define EN(v, ci) CA[((size_t)((v) - 1) * W + (ci) - 1) * 2 + 1]
 #pragma omp parallel for schedule(static)
   for (int aci = 1; aci <= nAc; aci++) {
     int ai = aci + nV;
     I2(VAaAc, ai, 1, M) = I2(VAc, aci, 1, ldAc); I2(VAaAc, ai, 2, M) = I2(VAc, aci, 2, ldAc);
     int e = edge_index_Ac[aci - 1];
+    int out[6] = {0, 0, 0, 0, 0, 0}, n_out = 0;
     if (e > 0) {
       int vi = I2(Aci, aci, 1, ldAc), vj = I2(Aci, aci, 2, ldAc), sw = 0;
       if (e == 1) { if (I2(V, vi, 1, nV) > I2(V, vj, 1, nV)) sw = 1; }
@@ -515,29 +562,33 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
       if (sw) { int t = vi; vi = vj; vj = t; }
       int vk = I2(Aci, aci, 3, ldAc), aci1 = 0, aci2 = 0;
       for (int ci = 1; ci <= nC[vk - 1]; ci++) {
-        if (I2(C, vk, ci, nV) == vi) aci1 = I2(iAci, vk, ci, nV);
-        else if (I2(C, vk, ci, nV) == vj) aci2 = I2(iAci, vk, ci, nV);
+        if (NB(vk, ci) == vi) aci1 = EN(vk, ci);
+        else if (NB(vk, ci) == vj) aci2 = EN(vk, ci);
       }
-      if (!aci1 || !aci2) { err = -1; continue; }
-      nCAaAc[ai - 1] = 4;
-      I2(CAaAc, ai, 1, M) = vi; I2(CAaAc, ai, 2, M) = aci1 + nV; I2(CAaAc, ai, 3, M) = aci2 + nV; I2(CAaAc, ai, 4, M) = vj;
+      if (!aci1 || !aci2) { err = -1; nCAaAc[ai - 1] = 0; }
+      else { n_out = 4; out[0] = vi; out[1] = aci1 + nV; out[2] = aci2 + nV; out[3] = vj; }
     } else {
       int vi = I2(Aci, aci, 1, ldAc), vj = I2(Aci, aci, 2, ldAc), vl = I2(Aci, aci, 3, ldAc), vr = I2(Aci, aci, 4, ldAc);
       int aci1 = 0, aci2 = 0, aci3 = 0, aci4 = 0;
       for (int ci = 1; ci <= nC[vr - 1]; ci++) {
-        if (I2(C, vr, ci, nV) == vi) aci1 = I2(iAci, vr, ci, nV);
-        else if (I2(C, vr, ci, nV) == vj) aci2 = I2(iAci, vr, ci, nV);
+        if (NB(vr, ci) == vi) aci1 = EN(vr, ci);
+        else if (NB(vr, ci) == vj) aci2 = EN(vr, ci);
       }
       for (int ci = 1; ci <= nC[vl - 1]; ci++) {
-        if (I2(C, vl, ci, nV) == vj) aci3 = I2(iAci, vl, ci, nV);
-        else if (I2(C, vl, ci, nV) == vi) aci4 = I2(iAci, vl, ci, nV);
+        if (NB(vl, ci) == vj) aci3 = EN(vl, ci);
+        else if (NB(vl, ci) == vi) aci4 = EN(vl, ci);
       }
-      if (!aci1 || !aci2 || !aci3 || !aci4) { err = -1; continue; }
-      nCAaAc[ai - 1] = 6;
-      I2(CAaAc, ai, 1, M) = vi; I2(CAaAc, ai, 2, M) = aci1 + nV; I2(CAaAc, ai, 3, M) = aci2 + nV;
-      I2(CAaAc, ai, 4, M) = vj; I2(CAaAc, ai, 5, M) = aci3 + nV; I2(CAaAc, ai, 6, M) = aci4 + nV;
+      if (!aci1 || !aci2 || !aci3 || !aci4) { err = -1; nCAaAc[ai - 1] = 0; }
+      else { n_out = 6; out[0] = vi; out[1] = aci1 + nV; out[2] = aci2 + nV; out[3] = vj; out[4] = aci3 + nV; out[5] = aci4 + nV; }
     }
+    if (n_out) nCAaAc[ai - 1] = n_out;
+    for (int k = 1; k <= W; k++) I2(CAaAc, ai, k, M) = k <= n_out ? out[k - 1] : 0;   /* every column written here: no memset pass over CAaAc */
   }
+#undef NB
+#undef EN
+  double t2_ = mh_now();
+  free(CA);
+  if (getenv("UFM_UPLOAD_TIMING")) fprintf(stderr, "[make_AaAc] Aa loop %.1f ms, Ac loop %.1f ms, free %.1f ms\n", (t1_ - t0_) * 1e3, (t2_ - t1_) * 1e3, (mh_now() - t2_) * 1e3);
   return err;
 }
 
@@ -566,34 +617,73 @@ static void dl_remove(dlist *q, int v)
  * colouring is identical; what changes is where the rows live in memory: with a space-filling-curve labelling the delete loop,
  * which walks from a deleted vertex to its neighbours, stays in cache (reference-ordered meshes are numbered in refinement
  * order, i.e. randomly in space). */
-int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label,
-                                     int *colour, int *colour_vi, int *colour_nV)
+/* bytes of scratch ufm_mesh_five_colouring_ws needs (a caller that colours mesh after mesh keeps the block: a fresh one costs a page
+ * fault per 4 KB, most of them on the one thread the algorithm runs on) */
+size_t ufm_mesh_five_colouring_ws_bytes(int M, int nC_mem)
 {
-  int *deg = (int *)malloc(sizeof(int) * ((size_t)M + 1));
-  int *L = (int *)malloc(sizeof(int) * (size_t)M * nC_mem);           /* row-major copy: L[(v-1)*nC_mem + c] */
-  char *inq = (char *)calloc((size_t)M + 1, 1);                       /* 0 none, 4 in Q4, 5 in Q5 */
-  int *S_vi = (int *)malloc(sizeof(int) * ((size_t)M + 1));
-  int *S_L = (int *)malloc(sizeof(int) * (size_t)M * 5);              /* deleted vertices have deg <= 5 */
+  const size_t m1 = ((size_t)M + 1 + 15) & ~(size_t)15;
+  return sizeof(int) * (m1 * 6 + (size_t)M * nC_mem + (size_t)M * 5) + m1 + 256;
+}
+int ufm_mesh_five_colouring_ws(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label,
+                               int *colour, int *colour_vi, int *colour_nV, void *ws)
+{
+  const double tc0_ = mh_now();
+  const size_t m1 = ((size_t)M + 1 + 15) & ~(size_t)15;
+  int *ip = (int *)(((uintptr_t)ws + 63) & ~(uintptr_t)63);
   dlist Q4 = {0}, Q5 = {0};
-  Q4.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q4.next = (int *)calloc((size_t)M + 1, sizeof(int));
-  Q5.prev = (int *)calloc((size_t)M + 1, sizeof(int)); Q5.next = (int *)calloc((size_t)M + 1, sizeof(int));
+  Q4.prev = ip; ip += m1; Q4.next = ip; ip += m1; Q5.prev = ip; ip += m1; Q5.next = ip; ip += m1;   /* these four and inq start at zero */
+  int *deg = ip; ip += m1;
+  int *S_vi = ip; ip += m1;
+  int *L = ip; ip += (size_t)M * nC_mem;                               /* row-major copy: L[(v-1)*nC_mem + c] */
+  int *S_L = ip; ip += (size_t)M * 5;                                  /* deleted vertices have deg <= 5 */
+  char *inq = (char *)ip;                                              /* 0 none, 4 in Q4, 5 in Q5 */
+  {
+    int *z = Q4.prev;
+    const long long nz = (long long)m1 * 4;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < nz; i++) z[i] = 0;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)m1; i++) inq[i] = 0;
+  }
   int rc = 0, Sn = 0, noofvert = M;
 #define LAB(v) (label ? label[(v) - 1] : (v))
 #pragma omp parallel for schedule(static)
   for (int v = 1; v <= M; v++) {
-    const int q = LAB(v);
-    deg[q] = nCAaAc[v - 1];
-    for (int c = 1; c <= nC_mem; c++) { const int w = I2(CAaAc, v, c, M); L[(size_t)(q - 1) * nC_mem + c - 1] = w > 0 ? LAB(w) : 0; }
+    const int q = LAB(v), n = nCAaAc[v - 1];
+    deg[q] = n;
+    int *row = L + (size_t)(q - 1) * nC_mem;
+    for (int c = 1; c <= nC_mem; c++) {   /* columns past the degree hold nothing (0 in the reference's array): not read */
+      const int w = c <= n ? I2(CAaAc, v, c, M) : 0;
+      row[c - 1] = w > 0 ? LAB(w) : 0;
+    }
   }
 #define CHECK(w) do { int d_ = deg[w]; \
     if (d_ <= 4) { if (inq[w] == 5) { dl_remove(&Q5, w); inq[w] = 0; } if (inq[w] != 4) { dl_push(&Q4, w); inq[w] = 4; } } \
     else if (d_ == 5) { if (inq[w] == 4) { dl_remove(&Q4, w); inq[w] = 0; } if (inq[w] != 5) { dl_push(&Q5, w); inq[w] = 5; } } \
     else { if (inq[w] == 4) { rc = -3; } if (inq[w] == 5) { dl_remove(&Q5, w); inq[w] = 0; } } } while (0)
-  for (int v0 = 1; v0 <= M; v0++) {   /* original index order */
-    const int v = LAB(v0);
-    if (deg[v] <= 4) { dl_push(&Q4, v); inq[v] = 4; }
-    else if (deg[v] == 5) { dl_push(&Q5, v); inq[v] = 5; }
+  /* initial queues: every vertex of degree <= 4 (Q4) / == 5 (Q5) pushed in ORIGINAL index order.  The lists live at the labelled
+   * positions, i.e. scattered; pieces of the index range are linked independently and then joined, which gives the lists the serial
+   * loop of dl_push calls would give */
+  {
+    enum { NPIECE = 64 };
+    int first4[NPIECE], last4[NPIECE], n4[NPIECE], first5[NPIECE], last5[NPIECE], n5[NPIECE];
+#pragma omp parallel for schedule(static, 1)
+    for (int pc = 0; pc < NPIECE; pc++) {
+      const int lo = (int)((long long)M * pc / NPIECE) + 1, hi = (int)((long long)M * (pc + 1) / NPIECE);
+      int f4 = 0, l4 = 0, c4 = 0, f5 = 0, l5 = 0, c5 = 0;
+      for (int v0 = lo; v0 <= hi; v0++) {
+        const int v = LAB(v0);
+        if (deg[v] <= 4) { Q4.prev[v] = l4; if (l4) Q4.next[l4] = v; else f4 = v; l4 = v; c4++; inq[v] = 4; }
+        else if (deg[v] == 5) { Q5.prev[v] = l5; if (l5) Q5.next[l5] = v; else f5 = v; l5 = v; c5++; inq[v] = 5; }
+      }
+      first4[pc] = f4; last4[pc] = l4; n4[pc] = c4; first5[pc] = f5; last5[pc] = l5; n5[pc] = c5;
+    }
+    for (int pc = 0; pc < NPIECE; pc++) {
+      if (n4[pc]) { if (Q4.tail) { Q4.next[Q4.tail] = first4[pc]; Q4.prev[first4[pc]] = Q4.tail; } else Q4.head = first4[pc]; Q4.tail = last4[pc]; Q4.n += n4[pc]; }
+      if (n5[pc]) { if (Q5.tail) { Q5.next[Q5.tail] = first5[pc]; Q5.prev[first5[pc]] = Q5.tail; } else Q5.head = first5[pc]; Q5.tail = last5[pc]; Q5.n += n5[pc]; }
+    }
   }
+  const double tc1_ = mh_now();
   while (noofvert > 5 && rc == 0) {
     if (Q4.n == 0) { rc = -2; break; }                 /* reference: IDENTIFY -> 'beep' + MPI_ABORT */
     int vi = Q4.tail;
@@ -625,8 +715,12 @@ int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const
     else { rc = -4; break; }
     noofvert--;
   }
+  const double tc2_ = mh_now();
   if (rc == 0) {
-    memset(colour, 0, sizeof(int) * (size_t)M);
+    {
+#pragma omp parallel for schedule(static)
+      for (int i = 0; i < M; i++) colour[i] = 0;
+    }
     int k = 0;
     for (int v = Q4.head; v && k < 5; v = Q4.next[v]) colour[v - 1] = ++k;     /* colour(Q4(1..5)) = 1..5 */
     if (k != 5 && M >= 5) rc = -5;
@@ -645,6 +739,7 @@ int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const
       colour[vi - 1] = col;
     }
   }
+  const double tc3_ = mh_now();
   if (rc == 0 && label) {   /* back to the caller's numbering; S_vi doubles as scratch */
 #pragma omp parallel for schedule(static)
     for (int v = 1; v <= M; v++) S_vi[v] = colour[label[v - 1] - 1];
@@ -662,8 +757,13 @@ int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const
     }
     if (bad) rc = -7;
   }
+  const double tc4_ = mh_now();
   if (rc == 0) {
-    memset(colour_vi, 0, sizeof(int) * (size_t)M * 5);
+    {
+      const long long nz = (long long)M * 5;
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < nz; i++) colour_vi[i] = 0;
+    }
     for (int c = 0; c < 5; c++) colour_nV[c] = 0;
     for (int v = 1; v <= M; v++) {
       int c = colour[v - 1];
@@ -671,8 +771,18 @@ int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const
       I2(colour_vi, colour_nV[c - 1], c, M) = v;
     }
   }
-  free(deg); free(L); free(inq); free(S_vi); free(S_L);
-  free(Q4.prev); free(Q4.next); free(Q5.prev); free(Q5.next);
+  const double tc5_ = mh_now();
+  if (getenv("UFM_UPLOAD_TIMING")) fprintf(stderr, "[five-colouring] set-up %.1f, delete loop %.1f, colour loop %.1f, relabel + check %.1f, colour_vi %.1f, free %.1f ms\n", (tc1_ - tc0_) * 1e3, (tc2_ - tc1_) * 1e3, (tc3_ - tc2_) * 1e3, (tc4_ - tc3_) * 1e3, (tc5_ - tc4_) * 1e3, (mh_now() - tc5_) * 1e3);
+  return rc;
+}
+
+int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label,
+                                     int *colour, int *colour_vi, int *colour_nV)
+{
+  void *ws = malloc(ufm_mesh_five_colouring_ws_bytes(M, nC_mem));
+  if (!ws) return -8;
+  const int rc = ufm_mesh_five_colouring_ws(M, nC_mem, nCAaAc, CAaAc, label, colour, colour_vi, colour_nV, ws);
+  free(ws);
   return rc;
 }
 

@@ -35,6 +35,9 @@ int ufm_mesh_make_AaAc(int nV, int nAc, int ldAc, int nC_mem, const double *V, c
                        const int *Aci, const int *edge_index_Ac, double *VAaAc, int *nCAaAc, int *CAaAc);
 int ufm_mesh_five_colouring_labelled(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label, int *colour, int *colour_vi,
                                      int *colour_nV);
+size_t ufm_mesh_five_colouring_ws_bytes(int M, int nC_mem);
+int ufm_mesh_five_colouring_ws(int M, int nC_mem, const int *nCAaAc, const int *CAaAc, const int *label, int *colour, int *colour_vi,
+                               int *colour_nV, void *ws);
 }
 
 struct ufm_secondary {
@@ -46,9 +49,12 @@ struct ufm_secondary {
   // upload): colour, colour_vi and colour_nV are final once colour_join() has returned
   std::thread colour_thread;
   std::vector<int> label;
+  std::vector<unsigned long long> sort_keys;   // scratch of the Morton relabelling, kept for the next mesh
+  void *colour_ws = nullptr;                   // scratch of the five-colouring (uninitialised memory, kept for the next mesh)
+  size_t colour_ws_bytes = 0;
   int colour_rc = 0;
   int colour_join() { if (colour_thread.joinable()) colour_thread.join(); return colour_rc; }
-  ~ufm_secondary() { colour_join(); }
+  ~ufm_secondary() { colour_join(); free(colour_ws); }
 };
 extern thread_local std::function<int()> *g_ufm_colour_wait;   // ufm_upload.cu
 
@@ -59,25 +65,65 @@ void ufm_secondary_free(ufm_handle *h)
 }
 
 namespace {
+// Size a host array without touching more memory than needed.  The arrays of one derivation are hundreds of megabytes; a std::vector
+// that is created (or assigned) anew value-initialises every element on one thread and page-faults its way through fresh memory --
+// measured as more than half of the time of the phases below.  ufm_mesh_upload_primary therefore hands the previous mesh's object back
+// (`recycle`): with some head room in the capacity a resize to a similar size touches nothing, and the routines that fill an array
+// completely (or fill_par below) run on all cores.
+template <class T>
+void grow(std::vector<T> &v, size_t n)
+{
+  if (v.capacity() < n) { std::vector<T>().swap(v); v.reserve(n + n / 16 + 64); }
+  v.resize(n);
+}
+template <class T>
+void fill_par(std::vector<T> &v, size_t n, T value)
+{
+  grow(v, n);
+  T *q = v.data();
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; i++) q[i] = value;
+}
 // copy an (n, cols) column-major array with leading dimension ld into a dense one
 template <class T>
 void compact(std::vector<T> &dst, const T *src, int n, int cols, int ld)
 {
-  dst.resize((size_t)n * cols);
-  for (int c = 0; c < cols; c++) memcpy(dst.data() + (size_t)c * n, src + (size_t)c * ld, sizeof(T) * (size_t)n);
+  grow(dst, (size_t)n * cols);
+  T *q = dst.data();
+#pragma omp parallel for schedule(static)
+  for (int c = 0; c < cols; c++) memcpy(q + (size_t)c * n, src + (size_t)c * ld, sizeof(T) * (size_t)n);
+}
+template <class T>
+void copy_par(std::vector<T> &dst, const T *src, size_t n)
+{
+  grow(dst, n);
+  T *q = dst.data();
+  const int parts = 16;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < parts; k++) { const size_t lo = n * k / parts, hi = n * (k + 1) / parts; memcpy(q + lo, src + lo, sizeof(T) * (hi - lo)); }
 }
 }  // namespace
 
 // host-only half: everything ufm_mesh_upload_primary derives before it touches the device.  async_colour: return while the five-colouring
 // (sequential by construction, a third of the whole re-upload) is still running on its own thread
-static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour);
+static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour, ufm_secondary *recycle);
 extern "C" int ufm_mesh_derive_secondary(const ufm_mesh_primary *p, void **derived)
 {
-  int rc = derive_secondary_impl(p, derived, false);
+  int rc = derive_secondary_impl(p, derived, false, nullptr);
   return rc;
 }
-static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour)
+// host-only, like ufm_mesh_derive_secondary, but *derived may hold the object of an earlier call, whose buffers are then reused (what
+// ufm_mesh_upload_primary does with the previous mesh's object)
+extern "C" int ufm_mesh_derive_secondary_reuse(const ufm_mesh_primary *p, void **derived)
 {
+  if (!derived) return ufm_set_error(-2, "ufm_mesh_derive_secondary_reuse: NULL argument");
+  ufm_secondary *old = (ufm_secondary *)*derived;
+  return derive_secondary_impl(p, derived, false, old);
+}
+// recycle: the object of the previous mesh (or NULL); its buffers are reused, its contents are gone when this returns, whatever it returns
+static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool async_colour, ufm_secondary *recycle)
+{
+  struct Recycled { ufm_secondary *s; ~Recycled() { delete s; } } recycled{recycle};   // deleted on every early return below
   if (!derived) return ufm_set_error(-2, "ufm_mesh_derive_secondary: NULL output");
   *derived = nullptr;
   if (!p || !p->V || !p->nC || !p->C || !p->niTri || !p->iTri || !p->edge_index || !p->Tri)
@@ -95,14 +141,18 @@ static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool
     fprintf(stderr, "[ufm_mesh_upload_primary] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
     t_last = t;
   };
-  ufm_secondary *s = new ufm_secondary();
+  if (recycle) recycle->colour_join();
+  ufm_secondary *s = recycle ? recycle : new ufm_secondary();
+  recycled.s = nullptr;
   struct Guard { ufm_secondary *s; ~Guard() { delete s; } } guard{s};
+  s->colour_rc = 0;
+  s->R.clear(); s->NxTri.clear(); s->NyTri.clear();
   s->nV = N; s->nTri = T; s->W = W;
   compact(s->V, p->V, N, 2, ldV);
   compact(s->C, p->C, N, W, ldV);
   compact(s->iTri, p->iTri, N, W, ldV);
   compact(s->Tri, p->Tri, T, 3, ldT);
-  s->nC.assign(p->nC, p->nC + N); s->niTri.assign(p->niTri, p->niTri + N); s->edge_index.assign(p->edge_index, p->edge_index + N);
+  copy_par(s->nC, p->nC, (size_t)N); copy_par(s->niTri, p->niTri, (size_t)N); copy_par(s->edge_index, p->edge_index, (size_t)N);
   // the host routines below index with what the arrays hold: validate first
   int bad_v = 0, bad_t = 0;
 #pragma omp parallel for schedule(static)
@@ -125,7 +175,8 @@ static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool
   // a planar triangulation of a simply connected domain has exactly nV + nTri - 1 edges (Euler)
   const int nAc_max = N + T;
   s->ldAc = nAc_max;
-  s->iAci.assign((size_t)N * W, 0); s->Aci.assign((size_t)nAc_max * 4, 0); s->VAc.assign((size_t)nAc_max * 2, 0.0); s->edge_index_Ac.assign(nAc_max, 0);
+  // make_Ac_mesh writes every entry of iAci and rows 1..nAc of the others; their rows nAc+1..nAc_max are never read
+  grow(s->iAci, (size_t)N * W); grow(s->Aci, (size_t)nAc_max * 4); grow(s->VAc, (size_t)nAc_max * 2); grow(s->edge_index_Ac, (size_t)nAc_max);
   const int nAc = ufm_mesh_make_Ac(N, T, W, nAc_max, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(),
                                    s->edge_index.data(), s->iAci.data(), s->Aci.data(), s->VAc.data(), nullptr, nullptr, nullptr, nullptr, s->edge_index_Ac.data());
   if (nAc <= 0) return ufm_set_error(-2, "ufm_mesh_upload_primary: make_Ac_mesh failed (%d): %s", nAc, nAc == -1 ? "more edges than nV + nTri" : "an edge without its triangle(s)");
@@ -133,7 +184,7 @@ static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool
   lap("make_Ac_mesh");
 
   const int M = N + nAc;
-  s->VAaAc.resize((size_t)M * 2); s->nCAaAc.resize(M); s->CAaAc.resize((size_t)M * W);
+  grow(s->VAaAc, (size_t)M * 2); grow(s->nCAaAc, (size_t)M); grow(s->CAaAc, (size_t)M * W);   // written completely by make_combined_AaAc_mesh
   rc = ufm_mesh_make_AaAc(N, nAc, nAc_max, W, s->V.data(), s->VAc.data(), s->nC.data(), s->C.data(), s->iAci.data(), s->Aci.data(), s->edge_index_Ac.data(),
                           s->VAaAc.data(), s->nCAaAc.data(), s->CAaAc.data());
   if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: make_combined_AaAc_mesh failed (%d)", rc);
@@ -142,9 +193,10 @@ static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool
   // The colouring's delete loop hops from a vertex to its neighbours; meshes come numbered in refinement order (random in space), so
   // run it on a Morton relabelling of the graph: same decisions, same colours (see ufm_mesh_five_colouring_labelled), rows in cache.
   std::vector<int> &label = s->label;
-  label.resize(M);
+  grow(label, (size_t)M);
   {
-    std::vector<unsigned long long> key(M);
+    std::vector<unsigned long long> &key = s->sort_keys;
+    grow(key, (size_t)M);
     const double *X = s->VAaAc.data(), *Y = X + M;
     const double sx = 65535.0 / (p->xmax - p->xmin), sy = 65535.0 / (p->ymax - p->ymin);
     auto spread = [](unsigned long long v) {
@@ -161,12 +213,21 @@ static int derive_secondary_impl(const ufm_mesh_primary *p, void **derived, bool
     for (int k = 0; k < M; k++) label[(int)(key[k] & 0xffffffffull)] = k + 1;
   }
   lap("Morton labels");
-  s->colour.resize(M); s->colour_vi.assign((size_t)M * 5, 0); s->colour_nV.assign(5, 0);
+  grow(s->colour, (size_t)M); grow(s->colour_vi, (size_t)M * 5); s->colour_nV.assign(5, 0);   // the colouring zeroes and fills colour_vi itself
+  {
+    const size_t need = ufm_mesh_five_colouring_ws_bytes(M, W);
+    if (s->colour_ws_bytes < need) {
+      free(s->colour_ws);
+      s->colour_ws_bytes = need + need / 16;
+      s->colour_ws = malloc(s->colour_ws_bytes);
+      if (!s->colour_ws) { s->colour_ws_bytes = 0; return ufm_set_error(-3, "ufm_mesh_upload_primary: out of host memory (five-colouring scratch)"); }
+    }
+  }
   s->colour_thread = std::thread([s, M, W]() {
-    s->colour_rc = ufm_mesh_five_colouring_labelled(M, W, s->nCAaAc.data(), s->CAaAc.data(), s->label.data(), s->colour.data(), s->colour_vi.data(), s->colour_nV.data());
+    s->colour_rc = ufm_mesh_five_colouring_ws(M, W, s->nCAaAc.data(), s->CAaAc.data(), s->label.data(), s->colour.data(), s->colour_vi.data(), s->colour_nV.data(), s->colour_ws);
   });
   // ... while this thread goes on with what does not need the colours
-  s->A.resize(N); s->Cw.assign((size_t)N * W, 0.0); s->Tricc.resize((size_t)T * 2); s->Tri_edge_index.resize(T);
+  grow(s->A, (size_t)N); fill_par(s->Cw, (size_t)N * W, 0.0); grow(s->Tricc, (size_t)T * 2); grow(s->Tri_edge_index, (size_t)T);
   rc = ufm_mesh_geometry(N, T, W, s->V.data(), s->Tri.data(), s->nC.data(), s->C.data(), s->niTri.data(), s->iTri.data(), s->edge_index.data(),
                              p->xmin, p->xmax, p->ymin, p->ymax, s->Tricc.data(), s->Tri_edge_index.data(), s->A.data(), s->Cw.data());
   if (rc) return ufm_set_error(-2, "ufm_mesh_upload_primary: Voronoi areas / connection widths failed (%d): C / iTri / Tri are inconsistent", rc);
@@ -218,7 +279,10 @@ extern "C" int ufm_mesh_upload_primary(ufm_handle *h, const ufm_mesh_primary *p)
 {
   if (!h) return ufm_set_error(-2, "NULL handle");
   void *derived = nullptr;
-  int rc = derive_secondary_impl(p, &derived, true);
+  // the previous mesh's derived arrays are valid "until the next upload": this is it -- their buffers are reused
+  ufm_secondary *old = (ufm_secondary *)h->secondary;
+  h->secondary = nullptr;
+  int rc = derive_secondary_impl(p, &derived, true, old);
   if (rc) return rc;
   ufm_secondary *s = (ufm_secondary *)derived;
   const auto t0 = std::chrono::steady_clock::now();
