@@ -320,6 +320,42 @@ def test_secondary_mesh_data_derived_from_a_restart_file(mesh, tmp_path):
         assert np.array_equal(d2[n], d[n]), n
 
 
+def test_derived_arrays_are_the_same_when_the_previous_meshs_buffers_are_reused():
+    """ufm_mesh_upload_primary hands the previous mesh's derived object back to the derivation, which reuses its buffers (no fresh
+    allocations, nothing zero-filled that will be overwritten).  Whatever mesh was there before -- larger, smaller, the same -- every
+    derived array, the colouring included, equals that of a derivation into a fresh object; a failed derivation leaves nothing behind."""
+    import ctypes
+
+    from ufemism_b200 import capi
+    from ufemism_b200 import mesh as M
+
+    L = capi.load_library()
+    meshes = [M.square_mesh_with_nv(750e3, n, seed=s) for n, s in ((1500, 3), (2600, 4), (900, 5), (900, 5))]
+    obj = ctypes.c_void_p()
+    names = ("A", "Cw", "Aci", "iAci", "edge_index_Ac", "nCAaAc", "CAaAc", "colour", "colour_vi", "colour_nV", "Tricc", "Tri_edge_index", "VAc", "VAaAc", "R", "NxTri", "NyTri")
+    for m in meshes:
+        p, keep = capi.mesh_primary(m, True)
+        assert L.ufm_mesh_derive_secondary_reuse(ctypes.byref(p), ctypes.byref(obj)) == 0, L.ufm_last_error()
+        d = capi._derived_to_dict(L, L.ufm_mesh_derived_get, obj, m.nV, m.nTri, m.nC_mem)
+        fresh = capi.derive_secondary(m, thermo=True)
+        assert (d["nV"], d["nAc"], d["ldAc"]) == (fresh["nV"], fresh["nAc"], fresh["ldAc"])
+        for n in names:
+            assert np.array_equal(d[n], fresh[n]), (m.nV, n)
+            assert np.array_equal(d[n], np.asarray(getattr(m, n))), (m.nV, n)
+    # without the thermodynamics arrays after a mesh that had them: the descriptor must not point at the old ones
+    p, keep = capi.mesh_primary(meshes[0], False)
+    assert L.ufm_mesh_derive_secondary_reuse(ctypes.byref(p), ctypes.byref(obj)) == 0
+    d = capi._derived_to_dict(L, L.ufm_mesh_derived_get, obj, meshes[0].nV, meshes[0].nTri, meshes[0].nC_mem)
+    assert "R" not in d and np.array_equal(d["CAaAc"], np.asarray(meshes[0].CAaAc))
+    # a broken mesh: error, and the object is gone (nothing stale to hand out)
+    bad = {n: np.array(getattr(meshes[0], n), order="F") for n in ("V", "nC", "C", "niTri", "iTri", "edge_index", "Tri")}
+    bad.update(xmin=meshes[0].xmin, xmax=meshes[0].xmax, ymin=meshes[0].ymin, ymax=meshes[0].ymax)
+    bad["C"][5, 0] = 0
+    p, keep = capi.mesh_primary(bad)
+    assert L.ufm_mesh_derive_secondary_reuse(ctypes.byref(p), ctypes.byref(obj)) != 0
+    assert not obj.value
+
+
 def test_derive_secondary_rejects_broken_primary_data(mesh):
     from ufemism_b200 import capi
 
