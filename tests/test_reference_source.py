@@ -432,6 +432,39 @@ def test_live_per_step_routines_on_other_states(scenario_name):
 
 
 @pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
+def test_live_thickness_update_of_the_SSA_icestream_experiment_keeps_the_domain_edge():
+    """calculate_ice_thickness_change sets the thickness of domain-edge vertices to zero for every experiment but 'SSA_icestream'
+    (src/ice_dynamics_module.f90:189-206: its branch is empty).  The translated reference and the oracle, switched to that experiment for
+    this one routine (geometry and SIA, which do not know the name, are evaluated as MISMIP_mod), agree bit for bit and leave ice on the edge."""
+    from oracle import f90py as F
+    from oracle.oracle import BENCHMARKS, Oracle
+    from ufemism_b200 import scenarios as S
+
+    np.seterr(all="ignore")
+    mesh = RC.golden_mesh()
+    st = S.state_ssa_icestream(mesh, scale=750e3 / 1800e3, Hb=-250.0, H_shelf=150.0)
+    o = Oracle(mesh, benchmark="MISMIP_mod", nthreads=1)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        o[k][:] = st[k]
+    o.update_general_ice_model_data(0.0); o.solve_SIA()
+    P = RS.program(o.cfg)
+    P.C.do_benchmark_experiment, P.C.choice_benchmark_experiment = True, "SSA_icestream"
+    mref, ice = RS.mesh_ns(mesh), RS.ice_ns(o)
+    P.calculate_ice_thickness_change(mref, ice, F.NS(smb_year=np.array(st["SMB_year"])), F.NS(bmb=np.array(st["BMB"])), np.float64(0.5), np.zeros(mesh.nV, np.int32))
+    o.cfg.benchmark = BENCHMARKS["SSA_icestream"]
+    o.calculate_ice_thickness_change(0.5)
+    _compare({f: o[f] for f in RC.THK_FIELDS}, {f: _arr(getattr(ice, f)) for f in RC.THK_FIELDS})
+    edge = mesh.edge_index > 0
+    assert (o["Hi"][edge] > 0).any(), "the edge keeps its ice in this experiment"
+    # ... and with any other experiment name the same update clears it
+    o2 = Oracle(mesh, benchmark="MISMIP_mod", nthreads=1)
+    for k in ("Hi", "Hb", "SL", "SMB_year", "BMB"):
+        o2[k][:] = st[k]
+    o2.update_general_ice_model_data(0.0); o2.solve_SIA(); o2.calculate_ice_thickness_change(0.5)
+    assert not o2["Hi"][edge].any()
+
+
+@pytest.mark.skipif(not RS.available(), reason="/root/reference is not mounted here")
 def test_live_region_loop_scheduling():
     """Three steps of the region loop with the reference's own determine_timesteps_and_actions (critical time steps, the eight
     timers, the do_* flags, src/UFEMISM_main_model.f90:708-843) and its own per-step routines, called in run_model's order (:78-214;
