@@ -245,6 +245,8 @@ int ufm_resident_dims(ufm_handle *h, int dims[5]);
 int ufm_pow_mode(ufm_handle *h);
 /* host: the same evaluation (libm's pow off its main path); for tests */
 double ufm_pow_host(double x, double y);
+/* host-only: what ufm_pow_mode would report on this host (the tables are looked for in the running libm.so.6 and validated on first use) */
+int ufm_powtab_status(void);
 double ufm_tan_host(double x);
 /* host twin of the device's x / n for a vertex degree n (k_sia_aa: map_Ac_to_Aa, src/mesh_ArakawaC_module.f90:770-791, divides every term
  * by nC(vi)): one multiply and two fused multiply-adds with 1.0 / n, the bits of the IEEE division; for tests */

@@ -555,3 +555,35 @@ def test_division_by_a_vertex_degree_has_the_bits_of_the_ieee_division(lib):
         x = np.concatenate([anyx, vel, near, special])
         got, want = f(x, n), x / float(n)
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (n, x[got.view(np.uint64) != want.view(np.uint64)][:5])
+
+
+def test_host_twin_of_the_device_pow_and_tan_has_libms_bits(lib):
+    """csrc/ufm_pow.cuh evaluates x**y and tan(x) on the device with glibc's own algorithm and the tables of the running libm.so.6;
+    csrc/ufm_pow_host.cpp finds those tables and holds a host build of the same instruction sequence to libm before anything is
+    uploaded.  Here: that the tables ARE found in this image's libm (otherwise the GPU path silently falls back to CUDA's pow / tan and the
+    bit-identity tests skip), and that the host twin equals libm's pow / tan (Python's math module calls them) bit for bit on arguments of
+    the kinds the model produces: Glen's law (n = 3), the viscosity and sliding exponents, the grounding-line flux powers, friction angles."""
+    import ctypes
+    import math
+    import struct
+
+    import numpy as np
+
+    rng = np.random.default_rng(11)
+    bits = lambda v: struct.pack("<d", v)
+    n_bad = 0
+    cases = [(10.0 ** rng.uniform(3, 8, 4000), 3.0),                      # (rho g H)**n_flow
+             (10.0 ** rng.uniform(-14, -2, 4000), (1.0 - 3.0) / (2.0 * 3.0)),  # effective strain rate ** ((1-n)/(2n))
+             (10.0 ** rng.uniform(-6, 7, 4000), 0.5 * (0.30 - 1.0)),      # sliding term
+             (10.0 ** rng.uniform(-20, -10, 3000), 1.0 / 3.0), (10.0 ** rng.uniform(0, 4, 3000), 4.0 / 3.0 + 1.0), (rng.uniform(0.01, 1.0, 3000), 3.0 / 7.0),
+             (10.0 ** rng.uniform(-3, 3, 3000), 2.75), (100.0 * np.ones(1), 0.30)]
+    for xs, y in cases:
+        for x in xs:
+            if bits(lib.ufm_pow_host(ctypes.c_double(float(x)), ctypes.c_double(y))) != bits(math.pow(float(x), y)):
+                n_bad += 1
+    assert n_bad == 0, f"{n_bad} pow results differ from libm"
+    # friction angles of basal_yield_stress: 5..20 degrees, and the rest of the range the device branch covers
+    for x in np.concatenate([np.deg2rad(rng.uniform(5.0, 20.0, 6000)), rng.uniform(0.07, 0.78, 6000), -rng.uniform(0.07, 0.78, 2000)]):
+        assert bits(lib.ufm_tan_host(ctypes.c_double(float(x)))) == bits(math.tan(float(x))), x
+    # the tables were found: the exact path is what a handle on this host would upload (0 would mean: CUDA's own functions, tolerance only)
+    assert lib.ufm_powtab_status() == 3

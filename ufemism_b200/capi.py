@@ -127,7 +127,7 @@ EXPORTED = ["ufm_create", "ufm_destroy", "ufm_set_params", "ufm_set_stream", "uf
             "ufm_mesh_upload", "ufm_mesh_free", "ufm_partition_set", "ufm_partition_owners", "ufm_comm_export", "ufm_comm_connect", "ufm_state_upload", "ufm_state_download", "ufm_host_register", "ufm_host_unregister", "ufm_remap_stash", "ufm_remap_apply", "ufm_thickness_update", "ufm_update_general",
             "ufm_solve_SIA", "ufm_solve_SIA_3D", "ufm_solve_SSA", "ufm_cfl", "ufm_ssa_prepare", "ufm_ssa_viscosity", "ufm_ssa_sliding_and_setup", "ufm_ssa_sor",
             "ufm_ssa_finish", "ufm_region_init", "ufm_run_model", "ufm_run_model_host", "ufm_counters_get", "ufm_counters_reset", "ufm_sor_trace_get",
-            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host", "ufm_div_small_host", "ufm_partition_owner_of", "ufm_partition_halo_counts",
+            "ufm_update_ice_temperature", "ufm_thermo_w3d", "ufm_thermo_heat", "ufm_field_resident", "ufm_resident_dims", "ufm_pow_mode", "ufm_pow_host", "ufm_tan_host", "ufm_powtab_status", "ufm_div_small_host", "ufm_partition_owner_of", "ufm_partition_halo_counts",
             "ufm_restart_create", "ufm_restart_append", "ufm_restart_write", "ufm_restart_inquire_mesh", "ufm_restart_read_mesh",
             "ufm_restart_inquire_init", "ufm_restart_read_init", "ufm_restart_load", "ufm_help_fields_create", "ufm_help_fields_write",
             "ufm_output_filename", "ufm_mesh_upload_primary", "ufm_mesh_derive_secondary", "ufm_mesh_derive_secondary_reuse", "ufm_mesh_derived_get", "ufm_mesh_derived_free",
@@ -190,6 +190,8 @@ def load_library():
         L.ufm_pow_host.restype = d
         L.ufm_tan_host.argtypes = [d]
         L.ufm_tan_host.restype = d
+        L.ufm_powtab_status.argtypes = []
+        L.ufm_powtab_status.restype = ctypes.c_int
         L.ufm_div_small_host.argtypes = [d, ctypes.c_int]
         L.ufm_div_small_host.restype = d
         s = ctypes.c_char_p

@@ -176,6 +176,14 @@ extern "C" int ufm_powtab_build(UfmPowTab *out)
   return 0;
 }
 
+// bit 0: this host's libm is the glibc whose pow the device re-states (tables found, 200 000 arguments bit-identical); bit 1: likewise tan.
+// What ufm_pow_mode reports for a handle, without a device.
+extern "C" int ufm_powtab_status(void)
+{
+  if (g_host_state == 0) g_host_state = ufm_powtab_build(&g_host_tab) == 0 ? 1 : -1;
+  return g_host_state == 1 ? (g_host_tab.enabled ? 1 : 0) | (g_host_tab.tan_enabled ? 2 : 0) : 0;
+}
+
 extern "C" double ufm_div_small_host(double x, int n)
 {
   const double d = (double)n;
