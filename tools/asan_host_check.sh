@@ -1,7 +1,8 @@
 #!/bin/bash
 # Host-side C / C++ of the product library under AddressSanitizer (+ UBSan for the C file): the mesh substrate (make_Ac_mesh,
 # make_combined_AaAc_mesh, Voronoi geometry, five-colouring with its scratch block) on four meshes incl. one with degree-16 vertices,
-# and the derivation of the secondary mesh data with reuse of the previous mesh's buffers (tests/test_restart_files.py).  No GPU needed.
+# the derivation of the secondary mesh data with reuse of the previous mesh's buffers, the NetCDF restart / help_fields writer and reader,
+# the host twin of the device pow / tan and the row-order planner (tests/test_restart_files.py, tests/test_abi.py).  No GPU needed.
 set -eu
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/asan; mkdir -p $OUT
@@ -15,7 +16,7 @@ out = "gpurun_out/asan"
 objs = []
 for s in B.CU_SOURCES + B.HOST_SOURCES:
     o = os.path.join(B.CSRC, os.path.splitext(s)[0] + ".o")
-    if s in ("ufm_mesh_primary.cpp", "mesh_host.c"):
+    if s in ("ufm_mesh_primary.cpp", "mesh_host.c", "ufm_netcdf.cpp", "ufm_pow_host.cpp"):
         o = os.path.join(out, os.path.splitext(s)[0] + "_asan.o")
         flags = list(B.NVCC_FLAGS)
         i = flags.index("-Xcompiler"); flags[i + 1] += ",-fsanitize=address,-fno-omit-frame-pointer,-g"
@@ -38,5 +39,5 @@ print("fan mesh", m.nV, "max degree", int(m.nC.max()))
 PY
 ASAN=$(gcc -print-file-name=libasan.so); UBSAN=$(gcc -print-file-name=libubsan.so)
 LD_PRELOAD=$ASAN:$UBSAN ASAN_OPTIONS=detect_leaks=0 python $OUT/substrate.py
-LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 UFM_B200_LIB=$PWD/$OUT/libufemism_b200_asan.so python -m pytest tests/test_restart_files.py -q -x -k "reused or derive or secondary" -p no:cacheprovider
+LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 UFM_B200_LIB=$PWD/$OUT/libufemism_b200_asan.so python -m pytest tests/test_restart_files.py tests/test_abi.py -q -x -k "not live and not cpp_host and not build_flags and not kernel_resources and not citations" -p no:cacheprovider
 echo "asan_host_check: clean"
