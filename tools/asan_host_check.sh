@@ -40,4 +40,16 @@ PY
 ASAN=$(gcc -print-file-name=libasan.so); UBSAN=$(gcc -print-file-name=libubsan.so)
 LD_PRELOAD=$ASAN:$UBSAN ASAN_OPTIONS=detect_leaks=0 python $OUT/substrate.py
 LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 UFM_B200_LIB=$PWD/$OUT/libufemism_b200_asan.so python -m pytest tests/test_restart_files.py tests/test_abi.py -q -x -k "not live and not cpp_host and not build_flags and not kernel_resources and not citations" -p no:cacheprovider
+# the CPU oracle itself (test infrastructure, but every parity claim leans on it): tests/test_oracle.py against an ASan / UBSan build
+gcc -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fopenmp -ffp-contract=off -fno-fast-math -fPIC -shared -o $OUT/libufm_oracle.so oracle/ufm_oracle.c -lm
+cat > $OUT/run_oracle.py <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import oracle.oracle as O
+O._LIB = os.path.join(os.getcwd(), "gpurun_out/asan/libufm_oracle.so")
+O.build = lambda force=False: O._LIB
+import pytest
+sys.exit(pytest.main(["tests/test_oracle.py", "-q", "-x", "-p", "no:cacheprovider", "-k", "not gcc_code_generation"]))
+PY
+LD_PRELOAD=$ASAN:$UBSAN ASAN_OPTIONS=detect_leaks=0 python $OUT/run_oracle.py
 echo "asan_host_check: clean"
